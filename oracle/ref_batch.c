@@ -1,0 +1,81 @@
+/*
+ * oracle/ref_batch.c -- TEST INFRASTRUCTURE.
+ * Thin driver compiled TOGETHER WITH the reference's own sources (taken where
+ * they lie under /root/reference; nothing is copied) into
+ * oracle/_ref/libcmsisdsp_ref.so.  It only adds pthread batch loops around the
+ * reference's public single-frame API and accessors for its preset instances,
+ * so tests and bench.py can drive the real reference through ctypes.
+ */
+#include "arm_math_types.h"
+#include "dsp/transform_functions.h"
+#include "arm_const_structs.h"
+#include <pthread.h>
+#include <stdlib.h>
+
+typedef struct {
+    int kind; uint32_t N; void *p, *out; uint64_t f0, f1; int ifft, bitrev;
+} job_t;
+
+static void *worker(void *arg)
+{
+    job_t *j = arg;
+    arm_cfft_instance_f32 Sf; arm_cfft_instance_q31 S31; arm_cfft_instance_q15 S15;
+    arm_rfft_fast_instance_f32 Sr;
+    switch (j->kind) {
+    case 0: if (arm_cfft_init_f32(&Sf, (uint16_t)j->N) != ARM_MATH_SUCCESS) return NULL; break;
+    case 1: if (arm_cfft_init_q31(&S31, (uint16_t)j->N) != ARM_MATH_SUCCESS) return NULL; break;
+    case 2: if (arm_cfft_init_q15(&S15, (uint16_t)j->N) != ARM_MATH_SUCCESS) return NULL; break;
+    default: if (arm_rfft_fast_init_f32(&Sr, (uint16_t)j->N) != ARM_MATH_SUCCESS) return NULL; break;
+    }
+    for (uint64_t f = j->f0; f < j->f1; f++) {
+        switch (j->kind) {
+        case 0: arm_cfft_f32(&Sf, (float32_t *)j->p + 2ull * j->N * f, (uint8_t)j->ifft, (uint8_t)j->bitrev); break;
+        case 1: arm_cfft_q31(&S31, (q31_t *)j->p + 2ull * j->N * f, (uint8_t)j->ifft, (uint8_t)j->bitrev); break;
+        case 2: arm_cfft_q15(&S15, (q15_t *)j->p + 2ull * j->N * f, (uint8_t)j->ifft, (uint8_t)j->bitrev); break;
+        default:
+            arm_rfft_fast_f32(&Sr, (float32_t *)j->p + (uint64_t)j->N * f,
+                              (float32_t *)j->out + (uint64_t)j->N * f, (uint8_t)j->ifft);
+            break;
+        }
+    }
+    return NULL;
+}
+
+static void run(int kind, uint32_t N, void *p, void *out, uint64_t nFrames, int ifft, int bitrev, int nthreads)
+{
+    if (nthreads < 1) nthreads = 1;
+    if ((uint64_t)nthreads > nFrames) nthreads = nFrames ? (int)nFrames : 1;
+    pthread_t *th = malloc((size_t)nthreads * sizeof *th);
+    job_t *jobs = malloc((size_t)nthreads * sizeof *jobs);
+    uint64_t per = (nFrames + (uint64_t)nthreads - 1) / (uint64_t)nthreads;
+    for (int t = 0; t < nthreads; t++) {
+        uint64_t f0 = per * (uint64_t)t, f1 = f0 + per;
+        if (f0 > nFrames) f0 = nFrames;
+        if (f1 > nFrames) f1 = nFrames;
+        jobs[t] = (job_t){kind, N, p, out, f0, f1, ifft, bitrev};
+        if (nthreads == 1) worker(&jobs[t]);
+        else pthread_create(&th[t], NULL, worker, &jobs[t]);
+    }
+    if (nthreads > 1)
+        for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+    free(th); free(jobs);
+}
+
+void ref_cfft_f32_batch(uint32_t N, float *p, uint64_t n, int ifft, int bitrev, int nt) { run(0, N, p, 0, n, ifft, bitrev, nt); }
+void ref_cfft_q31_batch(uint32_t N, int32_t *p, uint64_t n, int ifft, int bitrev, int nt) { run(1, N, p, 0, n, ifft, bitrev, nt); }
+void ref_cfft_q15_batch(uint32_t N, int16_t *p, uint64_t n, int ifft, int bitrev, int nt) { run(2, N, p, 0, n, ifft, bitrev, nt); }
+void ref_rfft_fast_f32_batch(uint32_t N, float *p, float *out, uint64_t n, int ifft, int nt) { run(3, N, p, out, n, ifft, 0, nt); }
+
+/* table accessors (the instance structs carry the pointers) */
+const float *ref_twiddle_f32(uint32_t N) { arm_cfft_instance_f32 S; return arm_cfft_init_f32(&S, (uint16_t)N) ? 0 : S.pTwiddle; }
+const int32_t *ref_twiddle_q31(uint32_t N) { arm_cfft_instance_q31 S; return arm_cfft_init_q31(&S, (uint16_t)N) ? 0 : S.pTwiddle; }
+const int16_t *ref_twiddle_q15(uint32_t N) { arm_cfft_instance_q15 S; return arm_cfft_init_q15(&S, (uint16_t)N) ? 0 : S.pTwiddle; }
+const float *ref_twiddle_rfft_f32(uint32_t N) { arm_rfft_fast_instance_f32 S; return arm_rfft_fast_init_f32(&S, (uint16_t)N) ? 0 : S.pTwiddleRFFT; }
+const uint16_t *ref_bitrev_f32(uint32_t N, uint16_t *len)
+{ arm_cfft_instance_f32 S; if (arm_cfft_init_f32(&S, (uint16_t)N)) return 0; *len = S.bitRevLength; return S.pBitRevTable; }
+const uint16_t *ref_bitrev_fixed(uint32_t N, uint16_t *len)
+{ arm_cfft_instance_q31 S; if (arm_cfft_init_q31(&S, (uint16_t)N)) return 0; *len = S.bitRevLength; return S.pBitRevTable; }
+uint32_t ref_sizeof_cfft_instance_f32(void) { return (uint32_t)sizeof(arm_cfft_instance_f32); }
+uint32_t ref_sizeof_cfft_instance_q31(void) { return (uint32_t)sizeof(arm_cfft_instance_q31); }
+uint32_t ref_sizeof_cfft_instance_q15(void) { return (uint32_t)sizeof(arm_cfft_instance_q15); }
+uint32_t ref_sizeof_rfft_fast_instance_f32(void) { return (uint32_t)sizeof(arm_rfft_fast_instance_f32); }

@@ -1,0 +1,107 @@
+"""ctypes access to the CPU checkers under oracle/ (TEST INFRASTRUCTURE).
+
+`oracle()`  -> oracle/liboracle.so            (the restatement, built on demand)
+`ref()`     -> oracle/_ref/libcmsisdsp_ref.so (the reference's own sources; prebuilt
+               in the build container, travels to the GPU box, None if absent)
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ODIR = os.path.join(ROOT, "oracle")
+LENGTHS = [16, 32, 64, 128, 256, 512, 1024, 2048, 4096]
+RLENGTHS = [32, 64, 128, 256, 512, 1024, 2048, 4096]
+
+_u16p = C.POINTER(C.c_uint16)
+
+
+def _declare(lib, prefix):
+    f = getattr
+    for name, t in (("cfft_f32", C.c_float), ("cfft_q31", C.c_int32), ("cfft_q15", C.c_int16)):
+        fn = f(lib, f"{prefix}_{name}_batch")
+        fn.argtypes = [C.c_uint32, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int]
+        fn.restype = None
+    fn = f(lib, f"{prefix}_rfft_fast_f32_batch")
+    fn.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int]
+    fn.restype = None
+    for name, t in (("twiddle_f32", C.c_float), ("twiddle_q31", C.c_int32),
+                    ("twiddle_q15", C.c_int16), ("twiddle_rfft_f32", C.c_float)):
+        fn = f(lib, f"{prefix}_{name}")
+        fn.argtypes = [C.c_uint32]
+        fn.restype = C.POINTER(t)
+    for name in ("bitrev_f32", "bitrev_fixed"):
+        fn = f(lib, f"{prefix}_{name}")
+        fn.argtypes = [C.c_uint32, _u16p]
+        fn.restype = _u16p
+
+
+class _Lib:
+    """Uniform numpy-level wrapper over liboracle.so / libcmsisdsp_ref.so."""
+
+    def __init__(self, lib, prefix):
+        self.lib, self.prefix = lib, prefix
+        _declare(lib, prefix)
+
+    def _fn(self, name):
+        return getattr(self.lib, f"{self.prefix}_{name}")
+
+    def cfft(self, kind, N, x, ifft=0, bitrev=1, threads=1):
+        """x: array [..., 2N] of float32 / int32 / int16; returns a transformed copy."""
+        dt = {"f32": np.float32, "q31": np.int32, "q15": np.int16}[kind]
+        y = np.ascontiguousarray(x, dtype=dt).copy()
+        assert y.size % (2 * N) == 0
+        self._fn(f"cfft_{kind}_batch")(N, y.ctypes.data, y.size // (2 * N), int(ifft), int(bitrev), int(threads))
+        return y
+
+    def rfft(self, N, x, ifft=0, threads=1, return_clobbered=False):
+        p = np.ascontiguousarray(x, dtype=np.float32).copy()
+        assert p.size % N == 0
+        out = np.empty_like(p)
+        self._fn("rfft_fast_f32_batch")(N, p.ctypes.data, out.ctypes.data, p.size // N, int(ifft), int(threads))
+        return (out, p) if return_clobbered else out
+
+    def table(self, name, N):
+        n = {"twiddle_f32": 2 * N, "twiddle_q31": 3 * N // 2, "twiddle_q15": 3 * N // 2,
+             "twiddle_rfft_f32": N}[name]
+        ptr = self._fn(name)(N)
+        return np.ctypeslib.as_array(ptr, shape=(n,)).copy()
+
+    def bitrev(self, which, N):
+        ln = C.c_uint16(0)
+        ptr = self._fn(f"bitrev_{which}")(N, C.byref(ln))
+        return np.ctypeslib.as_array(ptr, shape=(ln.value,)).copy()
+
+
+_cache = {}
+
+
+def oracle():
+    if "orc" not in _cache:
+        so = os.path.join(ODIR, "liboracle.so")
+        srcs = [os.path.join(ODIR, f) for f in os.listdir(ODIR) if f.startswith("orc_")]
+        if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+            subprocess.check_call(["make", "-C", ODIR, "liboracle.so"], stdout=subprocess.DEVNULL)
+        _cache["orc"] = _Lib(C.CDLL(so), "orc")
+    return _cache["orc"]
+
+
+def ref(fast=False):
+    key = "ref_fast" if fast else "ref"
+    if key not in _cache:
+        so = os.path.join(ODIR, "_ref", "libcmsisdsp_ref_fast.so" if fast else "libcmsisdsp_ref.so")
+        if not os.path.exists(so) and os.path.isdir("/root/reference"):
+            subprocess.check_call(["make", "-C", ODIR, "ref"], stdout=subprocess.DEVNULL)
+        _cache[key] = _Lib(C.CDLL(so), "ref") if os.path.exists(so) else None
+    return _cache[key]
+
+
+def perm_from_swaps(N, tab):
+    """Apply the ordered swap list to the identity: out[k] = in[perm[k]]."""
+    a = np.arange(N)
+    t = (np.asarray(tab, dtype=np.int64) // 8).reshape(-1, 2)
+    for x, y in t:
+        a[x], a[y] = a[y], a[x]
+    return a

@@ -1,0 +1,72 @@
+"""Pins the oracle restatement (oracle/liboracle.so) to the reference's own
+generic-C sources (oracle/_ref/libcmsisdsp_ref.so): tables entry for entry and
+every transform bit for bit, f32 included (both are built -ffp-contract=off)."""
+import numpy as np
+import pytest
+
+from oracle_lib import LENGTHS, RLENGTHS, oracle, ref
+
+pytestmark = pytest.mark.skipif(ref() is None, reason="oracle/_ref not built (needs /root/reference)")
+
+
+def bits(a):
+    a = np.ascontiguousarray(a)
+    return a.view({4: np.uint32, 2: np.uint16}[a.dtype.itemsize])
+
+
+@pytest.mark.parametrize("N", LENGTHS)
+def test_tables_identical(N):
+    o, r = oracle(), ref()
+    for name in ("twiddle_f32", "twiddle_q31", "twiddle_q15"):
+        assert np.array_equal(bits(o.table(name, N)), bits(r.table(name, N))), name
+    if N >= 32:
+        assert np.array_equal(bits(o.table("twiddle_rfft_f32", N)), bits(r.table("twiddle_rfft_f32", N)))
+    for which in ("f32", "fixed"):
+        assert np.array_equal(o.bitrev(which, N), r.bitrev(which, N)), which
+
+
+def _inputs(kind, N, rng, frames=6):
+    if kind == "f32":
+        x = rng.standard_normal((frames, 2 * N)).astype(np.float32)
+        x[1] *= 1e-3
+        x[2] *= 1e4
+        return x
+    info = np.iinfo(np.int32 if kind == "q31" else np.int16)
+    x = rng.integers(info.min, info.max, size=(frames + 4, 2 * N), endpoint=True).astype(info.dtype)
+    x[0] = info.min            # all 0x8000.. : saturation / wrap paths
+    x[1] = info.max
+    x[2, 0::2] = info.min
+    x[2, 1::2] = info.max
+    x[3] = np.where(np.arange(2 * N) % 4 < 2, info.max, info.min)
+    x[4] = (rng.standard_normal(2 * N) * 0.25 * info.max).clip(info.min, info.max).astype(info.dtype)
+    return x
+
+
+@pytest.mark.parametrize("kind", ["f32", "q31", "q15"])
+@pytest.mark.parametrize("N", LENGTHS)
+def test_cfft_bit_exact(kind, N):
+    rng = np.random.default_rng(1000 + N)
+    x = _inputs(kind, N, rng)
+    for ifft in (0, 1):
+        for bitrev in (0, 1):
+            a = oracle().cfft(kind, N, x, ifft, bitrev)
+            b = ref().cfft(kind, N, x, ifft, bitrev)
+            assert np.array_equal(bits(a), bits(b)), (kind, N, ifft, bitrev)
+
+
+@pytest.mark.parametrize("N", RLENGTHS)
+def test_rfft_bit_exact(N):
+    rng = np.random.default_rng(2000 + N)
+    x = rng.standard_normal((5, N)).astype(np.float32)
+    for ifft in (0, 1):
+        a, pa = oracle().rfft(N, x, ifft, return_clobbered=True)
+        b, pb = ref().rfft(N, x, ifft, return_clobbered=True)
+        assert np.array_equal(bits(a), bits(b)), (N, ifft)
+        assert np.array_equal(bits(pa), bits(pb)), ("clobbered input", N, ifft)
+
+
+def test_threads_agree():
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal((37, 2 * 256)).astype(np.float32)
+    assert np.array_equal(oracle().cfft("f32", 256, x, threads=1), oracle().cfft("f32", 256, x, threads=5))
+    assert np.array_equal(ref().cfft("f32", 256, x, threads=1), ref().cfft("f32", 256, x, threads=5))
