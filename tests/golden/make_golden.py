@@ -1,0 +1,92 @@
+#!/usr/bin/env python
+"""Regenerates the golden fixtures in this directory from the reference tree.
+
+Run in the build container only (needs /root/reference and oracle/_ref):
+    python tests/golden/make_golden.py
+
+Outputs
+  transform_patterns.npz  the reference's own test vectors for the FFT path
+        (Testing/Patterns/DSP/Transform/Transform{F32,Q31,Q15}/*.txt, written by
+        Testing/PatternGeneration/Transform.py from scipy.fftpack), re-packed as
+        arrays keyed "<type>/<c|r>/<noisy|step>/<N>/<input|ref|ifft_input>".
+  fft_bin_example.npz     Examples/ARM/arm_fft_bin_example/arm_fft_bin_data.c
+        (testInput_f32_10khz; expected peak bin 213).
+  ref_digests.json        sha256 of the outputs of the COMPILED REFERENCE
+        (oracle/_ref/libcmsisdsp_ref.so) on seeded inputs, per
+        (type, N, ifft, bitrev) -- pins bits where the reference's own tests only
+        pin tolerances.  Inputs come from tests/seeded_inputs.py.
+"""
+import hashlib
+import json
+import os
+import re
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+REF = "/root/reference"
+PAT = os.path.join(REF, "Testing/Patterns/DSP/Transform")
+
+
+def read_pattern(path):
+    with open(path) as f:
+        lines = [l.strip() for l in f if l.strip() and not l.startswith("//")]
+    tag, n = lines[0], int(lines[1])
+    vals = [int(x, 16) for x in lines[2:2 + n]]
+    if tag == "W":
+        return np.array(vals, dtype=np.uint32)
+    if tag == "H":
+        return np.array(vals, dtype=np.uint16)
+    raise ValueError(f"unknown tag {tag} in {path}")
+
+
+def main():
+    out = {}
+    for tname, ext, view in (("F32", "f32", np.float32), ("Q31", "q31", np.int32), ("Q15", "q15", np.int16)):
+        d = os.path.join(PAT, f"Transform{tname}")
+        for fn in sorted(os.listdir(d)):
+            m = re.match(r"(Complex|Real)(InputSamples|FFTSamples|InputIFFTSamples)_(Noisy|Step)_(\d+)_\d+_" + ext + r"\.txt$", fn)
+            if not m:
+                continue
+            cr, what, sig, n = m.groups()
+            what = {"InputSamples": "input", "FFTSamples": "ref", "InputIFFTSamples": "ifft_input"}[what]
+            key = f"{ext}/{'c' if cr == 'Complex' else 'r'}/{sig.lower()}/{n}/{what}"
+            out[key] = read_pattern(os.path.join(d, fn)).view(view)
+    np.savez_compressed(os.path.join(HERE, "transform_patterns.npz"), **out)
+    print("transform_patterns.npz:", len(out), "arrays")
+
+    src = open(os.path.join(REF, "Examples/ARM/arm_fft_bin_example/arm_fft_bin_data.c")).read()
+    body = src[src.index("testInput_f32_10khz"):]
+    body = body[body.index("{") + 1:body.index("};")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    vals = np.array([float(t.rstrip("f")) for t in re.findall(r"[-+]?\d*\.\d+(?:[eE][-+]?\d+)?f?|[-+]?\d+\.?f?", body) if t.strip()],
+                    dtype=np.float32)
+    assert vals.size == 2048, vals.size
+    np.savez_compressed(os.path.join(HERE, "fft_bin_example.npz"), input=vals, ref_index=np.int32(213))
+    print("fft_bin_example.npz:", vals.size, "floats")
+
+    from oracle_lib import LENGTHS, RLENGTHS, ref
+    from seeded_inputs import cfft_input, rfft_input
+    r = ref()
+    dig = {}
+    for kind in ("f32", "q31", "q15"):
+        for N in LENGTHS:
+            x = cfft_input(kind, N, frames=8, seed=N)
+            for ifft in (0, 1):
+                for bitrev in (0, 1):
+                    y = r.cfft(kind, N, x, ifft, bitrev)
+                    dig[f"cfft_{kind}/{N}/{ifft}/{bitrev}"] = hashlib.sha256(y.tobytes()).hexdigest()
+    for N in RLENGTHS:
+        x = rfft_input(N, frames=8, seed=N)
+        for ifft in (0, 1):
+            y = r.rfft(N, x, ifft)
+            dig[f"rfft_fast_f32/{N}/{ifft}"] = hashlib.sha256(y.tobytes()).hexdigest()
+    with open(os.path.join(HERE, "ref_digests.json"), "w") as f:
+        json.dump(dig, f, indent=0, sort_keys=True)
+    print("ref_digests.json:", len(dig), "digests")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,65 @@
+"""The oracle against the reference's OWN golden vectors and known-answer test
+(SURVEY.md section 8(c)), plus the committed digests of the compiled reference's
+outputs on seeded inputs (bit-level pin that also works where oracle/_ref is absent)."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from golden_checks import assert_like_reference, golden_cases, ref_digests
+from oracle_lib import LENGTHS, RLENGTHS, oracle
+from seeded_inputs import cfft_input, rfft_input
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.mark.parametrize("kind", ["f32", "q31", "q15"])
+def test_cfft_patterns(kind):
+    n = 0
+    for N, sig, ifft, x, ref in golden_cases(kind, "c"):
+        out = oracle().cfft(kind, N, x, ifft, 1).reshape(-1)
+        assert_like_reference(kind, "c", out, ref, N, ifft)
+        n += 1
+    assert n == 36          # 9 lengths x {noisy, step} x {fwd, inv}
+
+
+def test_rfft_patterns():
+    n = 0
+    for N, sig, ifft, x, ref in golden_cases("f32", "r"):
+        out = oracle().rfft(N, x, ifft).reshape(-1)
+        assert_like_reference("f32", "r", out, ref, N, ifft)
+        n += 1
+    assert n == 32          # 8 lengths x {noisy, step} x {fwd, inv}
+
+
+def test_fft_bin_example_known_answer():
+    """Examples/ARM/arm_fft_bin_example/arm_fft_bin_example_f32.c:127-155: CFFT-1024 of a
+    10 kHz tone, magnitude, arg-max must be bin 213."""
+    d = np.load(os.path.join(HERE, "golden", "fft_bin_example.npz"))
+    y = oracle().cfft("f32", 1024, d["input"], 0, 1).reshape(-1, 2)
+    mag = np.sqrt(y[:, 0].astype(np.float64) ** 2 + y[:, 1].astype(np.float64) ** 2)
+    assert int(np.argmax(mag)) == int(d["ref_index"]) == 213
+
+
+def test_digests_of_compiled_reference():
+    dig = ref_digests()
+    o = oracle()
+    for kind in ("f32", "q31", "q15"):
+        for N in LENGTHS:
+            x = cfft_input(kind, N, frames=8, seed=N)
+            for ifft in (0, 1):
+                for bitrev in (0, 1):
+                    y = o.cfft(kind, N, x, ifft, bitrev)
+                    assert hashlib.sha256(y.tobytes()).hexdigest() == dig[f"cfft_{kind}/{N}/{ifft}/{bitrev}"], \
+                        (kind, N, ifft, bitrev)
+    for N in RLENGTHS:
+        x = rfft_input(N, frames=8, seed=N)
+        for ifft in (0, 1):
+            y = o.rfft(N, x, ifft)
+            assert hashlib.sha256(y.tobytes()).hexdigest() == dig[f"rfft_fast_f32/{N}/{ifft}"], (N, ifft)
+
+
+def test_unsupported_length_is_noop():
+    x = np.arange(2 * 24, dtype=np.float32)
+    assert np.array_equal(oracle().cfft("f32", 24, x), x)
