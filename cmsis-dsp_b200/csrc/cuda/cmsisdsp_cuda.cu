@@ -1,0 +1,374 @@
+/*
+ * cmsisdsp_cuda.cu -- libcmsisdsp_cuda.so: sm_100a kernels for the batched CMSIS-DSP FFT
+ * hot path plus the C-ABI declared in include/cmsisdsp_cuda.h.
+ *
+ * One launch processes a whole batch of independent frames: a CTA holds PL::F frames,
+ * PL::T threads each (16 points per thread), and runs the phases of the plan's body
+ * (fft_body.cuh) with __syncthreads() between them.  HBM is touched exactly once per
+ * point on the way in and once on the way out.
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+#include <vector>
+
+#include "cmsisdsp_cuda.h"
+#include "fft_plans.cuh"
+
+using namespace b200fft;
+
+/* ------------------------------------------------------------------ error plumbing */
+
+static thread_local char g_err[256] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(int code, const char *what, cudaError_t e = cudaSuccess)
+{
+    if (e != cudaSuccess) snprintf(g_err, sizeof g_err, "%s: %s", what, cudaGetErrorString(e));
+    else snprintf(g_err, sizeof g_err, "%s", what);
+    return code;
+}
+#define CU_TRY(call)                                                       \
+    do {                                                                   \
+        cudaError_t e_ = (call);                                           \
+        if (e_ != cudaSuccess) return fail(CMSISDSP_CUDA_ERR_RUNTIME, #call, e_); \
+    } while (0)
+
+/* ------------------------------------------------------------------ kernel */
+
+template <class BODY, class PL>
+__global__ void __launch_bounds__(PL::kThreads) frame_kernel(typename BODY::Args base, uint64_t nFrames)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    typedef typename BODY::elem elem;
+    const int tid = threadIdx.x;
+    const int fl = tid / PL::T, i = tid % PL::T;
+    const uint64_t frame = (uint64_t)blockIdx.x * PL::F + fl;
+    const bool valid = frame < nFrames;
+    elem *sm = reinterpret_cast<elem *>(smem_raw) + fl * PL::kFrameElems;
+    const typename BODY::Args a = BODY::for_frame(base, valid ? frame : 0);
+    typename BODY::Regs r;
+
+    if (valid) BODY::template phase<0>(r, a, sm, i);
+    if constexpr (BODY::kPhases > 1) {
+        __syncthreads();
+        if (valid) BODY::template phase<1>(r, a, sm, i);
+    }
+    if constexpr (BODY::kPhases > 2) {
+        __syncthreads();
+        if (valid) BODY::template phase<2>(r, a, sm, i);
+        __syncthreads();
+        if (valid) BODY::template phase<3>(r, a, sm, i);
+    }
+}
+
+template <class BODY, class PL>
+static int launch(const typename BODY::Args &args, uint64_t nFrames, cudaStream_t st)
+{
+    if (nFrames == 0) return CMSISDSP_CUDA_OK;
+    const uint64_t ctas = (nFrames + PL::F - 1) / PL::F;
+    if (ctas > 0x7fffffffull) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "batch too large for one launch");
+    frame_kernel<BODY, PL><<<(unsigned)ctas, PL::kThreads, PL::kSmemBytes, st>>>(args, nFrames);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CU_TRY(cudaGetLastError());
+    return CMSISDSP_CUDA_OK;
+}
+
+template <class BODY, class PL>
+static int kinfo(int *threads, int *frames, int *smem, int *regs, int *ctasPerSm)
+{
+    cudaFuncAttributes fa;
+    CU_TRY(cudaFuncGetAttributes(&fa, frame_kernel<BODY, PL>));
+    int occ = 0;
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, frame_kernel<BODY, PL>, PL::kThreads, PL::kSmemBytes));
+    if (threads) *threads = PL::kThreads;
+    if (frames) *frames = PL::F;
+    if (smem) *smem = PL::kSmemBytes;
+    if (regs) *regs = fa.numRegs;
+    if (ctasPerSm) *ctasPerSm = occ;
+    return CMSISDSP_CUDA_OK;
+}
+
+/* ------------------------------------------------------------------ plan cache */
+
+static const uint32_t kLens[9] = {16, 32, 64, 128, 256, 512, 1024, 2048, 4096};
+static int len_index(uint32_t n)
+{
+    for (int i = 0; i < 9; i++)
+        if (kLens[i] == n) return i;
+    return -1;
+}
+
+struct DevPlan {
+    void *tw = nullptr;           /* twiddles */
+    uint16_t *perm = nullptr;     /* destination position of X[k] when bitReverseFlag == 0 */
+};
+struct DevState {
+    DevPlan plan[3][9];
+    float *twr[9] = {};           /* rfft twiddles, indexed by len_index(real length) */
+};
+static const int kMaxDev = 64;
+static DevState g_dev[kMaxDev];
+static std::mutex g_mu;
+
+static int cur_device(int *dev)
+{
+    cudaError_t e = cudaGetDevice(dev);
+    if (e != cudaSuccess) return fail(CMSISDSP_CUDA_ERR_NO_DEVICE, "cudaGetDevice", e);
+    if (*dev < 0 || *dev >= kMaxDev) return fail(CMSISDSP_CUDA_ERR_NO_DEVICE, "device index out of range");
+    return CMSISDSP_CUDA_OK;
+}
+
+extern "C" int cmsisdsp_cuda_plan_upload(int type, uint32_t fftLen, const void *pTwiddle,
+                                         const uint16_t *pBitRevTable, uint16_t bitRevLength)
+{
+    const int li = len_index(fftLen);
+    if (type < 0 || type > 2 || li < 0 || !pTwiddle || (!pBitRevTable && bitRevLength))
+        return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "plan_upload: bad type / length / pointer");
+    int dev;
+    int rc = cur_device(&dev);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(g_mu);
+    DevPlan &p = g_dev[dev].plan[type][li];
+    if (p.tw) return CMSISDSP_CUDA_OK;
+
+    const size_t twBytes = (type == CMSISDSP_CUDA_F32) ? (size_t)fftLen * 8
+                         : (type == CMSISDSP_CUDA_Q31) ? (size_t)fftLen * 6 : (size_t)fftLen * 3;
+    /* out[k] = scrambled[P[k]] after the swap list  =>  X[k] lives at scrambled position P[k] */
+    std::vector<uint16_t> perm(fftLen);
+    for (uint32_t k = 0; k < fftLen; k++) perm[k] = (uint16_t)k;
+    for (uint32_t i = 0; i + 1 < bitRevLength; i += 2) {
+        const uint32_t a = pBitRevTable[i] >> 3, b = pBitRevTable[i + 1] >> 3;
+        if (a >= fftLen || b >= fftLen) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "plan_upload: bit-reversal entry out of range");
+        const uint16_t t = perm[a]; perm[a] = perm[b]; perm[b] = t;
+    }
+    void *dtw = nullptr; uint16_t *dperm = nullptr;
+    CU_TRY(cudaMalloc(&dtw, twBytes));
+    CU_TRY(cudaMalloc((void **)&dperm, fftLen * sizeof(uint16_t)));
+    CU_TRY(cudaMemcpy(dtw, pTwiddle, twBytes, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(dperm, perm.data(), fftLen * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    p.perm = dperm;
+    p.tw = dtw;
+    return CMSISDSP_CUDA_OK;
+}
+
+extern "C" int cmsisdsp_cuda_rfft_plan_upload(uint32_t fftLenReal, const float *pTwiddleRFFT)
+{
+    const int li = len_index(fftLenReal);
+    if (li < 1 || !pTwiddleRFFT) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "rfft_plan_upload: bad length / pointer");
+    int dev;
+    int rc = cur_device(&dev);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_dev[dev].twr[li]) return CMSISDSP_CUDA_OK;
+    float *d = nullptr;
+    CU_TRY(cudaMalloc((void **)&d, fftLenReal * sizeof(float)));
+    CU_TRY(cudaMemcpy(d, pTwiddleRFFT, fftLenReal * sizeof(float), cudaMemcpyHostToDevice));
+    g_dev[dev].twr[li] = d;
+    return CMSISDSP_CUDA_OK;
+}
+
+extern "C" int cmsisdsp_cuda_plan_ready(int type, uint32_t fftLen)
+{
+    const int li = len_index(fftLen);
+    int dev;
+    if (type < 0 || type > 2 || li < 0 || cur_device(&dev)) return 0;
+    std::lock_guard<std::mutex> lk(g_mu);
+    return g_dev[dev].plan[type][li].tw != nullptr;
+}
+extern "C" int cmsisdsp_cuda_rfft_plan_ready(uint32_t fftLenReal)
+{
+    const int li = len_index(fftLenReal);
+    int dev;
+    if (li < 1 || cur_device(&dev)) return 0;
+    std::lock_guard<std::mutex> lk(g_mu);
+    return g_dev[dev].twr[li] != nullptr && g_dev[dev].plan[0][li - 1].tw != nullptr;
+}
+
+static int get_plan(int type, uint32_t fftLen, DevPlan *out)
+{
+    const int li = len_index(fftLen);
+    if (li < 0) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "unsupported fftLen (16..4096, power of two)");
+    int dev;
+    int rc = cur_device(&dev);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(g_mu);
+    *out = g_dev[dev].plan[type][li];
+    if (!out->tw) return fail(CMSISDSP_CUDA_ERR_NO_PLAN, "no plan uploaded for this (device, type, fftLen)");
+    return CMSISDSP_CUDA_OK;
+}
+
+/* ------------------------------------------------------------------ transforms */
+
+#define FOR_ALL_N(X) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096)
+#define FOR_RFFT_NC(X) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048)
+
+template <class AR, class PL>
+static int cfft_launch(void *d_p, uint64_t nFrames, bool inv, const DevPlan &pl, bool bitrev, int shl1, cudaStream_t st)
+{
+    typedef typename AR::elem elem;
+    if (inv) {
+        typedef CfftBody<PL, true> BODY;
+        typename BODY::Args a{(const elem *)d_p, (elem *)d_p, (const elem *)pl.tw, bitrev ? nullptr : pl.perm, 1.0f / (float)PL::N, shl1};
+        return launch<BODY, PL>(a, nFrames, st);
+    }
+    typedef CfftBody<PL, false> BODY;
+    typename BODY::Args a{(const elem *)d_p, (elem *)d_p, (const elem *)pl.tw, bitrev ? nullptr : pl.perm, 1.0f / (float)PL::N, shl1};
+    return launch<BODY, PL>(a, nFrames, st);
+}
+
+static int cfft_any(int type, void *d_p, uint32_t fftLen, uint64_t nFrames, uint8_t ifftFlag, uint8_t bitReverseFlag, void *stream)
+{
+    if (!d_p && nFrames) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "null data pointer");
+    DevPlan pl;
+    int rc = get_plan(type, fftLen, &pl);
+    if (rc) return rc;
+    const bool inv = (ifftFlag == 1), br = (bitReverseFlag != 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    int lg = 0;
+    while ((1u << lg) < fftLen) lg++;
+    const int shl1 = lg & 1;     /* N = 2*4^m: final << 1 (fixed point only) */
+    switch (fftLen) {
+#define CASE(n)                                                                                                   \
+    case n:                                                                                                       \
+        if (type == CMSISDSP_CUDA_F32) return cfft_launch<ArithF32, PlanCfftF32<n>::type>(d_p, nFrames, inv, pl, br, 0, st);          \
+        if (type == CMSISDSP_CUDA_Q31) return cfft_launch<ArithQ31, PlanCfftFix<ArithQ31, n>::type>(d_p, nFrames, inv, pl, br, shl1, st); \
+        return cfft_launch<ArithQ15, PlanCfftFix<ArithQ15, n>::type>(d_p, nFrames, inv, pl, br, shl1, st);
+        FOR_ALL_N(CASE)
+#undef CASE
+    }
+    return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "unsupported fftLen");
+}
+
+extern "C" int cmsisdsp_cuda_cfft_f32(void *d_p, uint32_t fftLen, uint64_t nFrames, uint8_t ifftFlag, uint8_t bitReverseFlag, void *stream)
+{ return cfft_any(CMSISDSP_CUDA_F32, d_p, fftLen, nFrames, ifftFlag, bitReverseFlag, stream); }
+extern "C" int cmsisdsp_cuda_cfft_q31(void *d_p, uint32_t fftLen, uint64_t nFrames, uint8_t ifftFlag, uint8_t bitReverseFlag, void *stream)
+{ return cfft_any(CMSISDSP_CUDA_Q31, d_p, fftLen, nFrames, ifftFlag, bitReverseFlag, stream); }
+extern "C" int cmsisdsp_cuda_cfft_q15(void *d_p, uint32_t fftLen, uint64_t nFrames, uint8_t ifftFlag, uint8_t bitReverseFlag, void *stream)
+{ return cfft_any(CMSISDSP_CUDA_Q15, d_p, fftLen, nFrames, ifftFlag, bitReverseFlag, stream); }
+
+extern "C" int cmsisdsp_cuda_rfft_fast_f32(const void *d_p, void *d_out, uint32_t fftLenReal, uint64_t nFrames, uint8_t ifftFlag, void *stream)
+{
+    if ((!d_p || !d_out) && nFrames) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "null data pointer");
+    if (d_p == d_out && nFrames) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "rfft_fast: p and pOut must not alias");
+    const int li = len_index(fftLenReal);
+    if (li < 1) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "unsupported rfft length (32..4096, power of two)");
+    DevPlan pl;
+    int rc = get_plan(CMSISDSP_CUDA_F32, fftLenReal / 2, &pl);
+    if (rc) return rc;
+    int dev;
+    rc = cur_device(&dev);
+    if (rc) return rc;
+    const float *twr;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        twr = g_dev[dev].twr[li];
+    }
+    if (!twr) return fail(CMSISDSP_CUDA_ERR_NO_PLAN, "no rfft plan uploaded for this (device, fftLen)");
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (fftLenReal / 2) {
+#define CASE(nc)                                                                                              \
+    case nc:                                                                                                  \
+        if (!ifftFlag) {                                                                                      \
+            typedef PlanRfftFwd<nc>::type PL;                                                                 \
+            typedef RfftFwdBody<PL> BODY;                                                                     \
+            BODY::Args a{(const cf32 *)d_p, (cf32 *)d_out, (const cf32 *)pl.tw, (const cf32 *)twr};           \
+            return launch<BODY, PL>(a, nFrames, st);                                                          \
+        } else {                                                                                              \
+            typedef PlanRfftInv<nc>::type PL;                                                                 \
+            typedef RfftInvBody<PL> BODY;                                                                     \
+            BODY::Args a{(const cf32 *)d_p, (cf32 *)d_out, (const cf32 *)pl.tw, (const cf32 *)twr, 1.0f / (float)nc}; \
+            return launch<BODY, PL>(a, nFrames, st);                                                          \
+        }
+        FOR_RFFT_NC(CASE)
+#undef CASE
+    }
+    return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "unsupported rfft length");
+}
+
+extern "C" int cmsisdsp_cuda_kernel_info(int op, uint32_t fftLen, int *threads, int *frames, int *smem, int *regs, int *ctasPerSm)
+{
+    const uint32_t n = (op >= 3) ? fftLen / 2 : fftLen;
+    switch (n) {
+#define CASE(nn)                                                                                                   \
+    case nn:                                                                                                       \
+        if (op == 0) return kinfo<CfftBody<PlanCfftF32<nn>::type, false>, PlanCfftF32<nn>::type>(threads, frames, smem, regs, ctasPerSm); \
+        if (op == 1) return kinfo<CfftBody<PlanCfftFix<ArithQ31, nn>::type, false>, PlanCfftFix<ArithQ31, nn>::type>(threads, frames, smem, regs, ctasPerSm); \
+        if (op == 2) return kinfo<CfftBody<PlanCfftFix<ArithQ15, nn>::type, false>, PlanCfftFix<ArithQ15, nn>::type>(threads, frames, smem, regs, ctasPerSm); \
+        break;
+        FOR_ALL_N(CASE)
+#undef CASE
+    }
+    switch (n) {
+#define CASE(nc)                                                                                                   \
+    case nc:                                                                                                       \
+        if (op == 3) return kinfo<RfftFwdBody<PlanRfftFwd<nc>::type>, PlanRfftFwd<nc>::type>(threads, frames, smem, regs, ctasPerSm); \
+        if (op == 4) return kinfo<RfftInvBody<PlanRfftInv<nc>::type>, PlanRfftInv<nc>::type>(threads, frames, smem, regs, ctasPerSm); \
+        break;
+        FOR_RFFT_NC(CASE)
+#undef CASE
+    }
+    return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "kernel_info: unsupported (op, fftLen)");
+}
+
+/* ------------------------------------------------------------------ plumbing */
+
+extern "C" int cmsisdsp_cuda_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    return n;
+}
+extern "C" int cmsisdsp_cuda_set_device(int device) { CU_TRY(cudaSetDevice(device)); return 0; }
+extern "C" int cmsisdsp_cuda_get_device(void) { int d = -1; if (cudaGetDevice(&d) != cudaSuccess) return -1; return d; }
+extern "C" int cmsisdsp_cuda_malloc(void **p, size_t bytes) { if (!p) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "null"); CU_TRY(cudaMalloc(p, bytes)); return 0; }
+extern "C" int cmsisdsp_cuda_free(void *p) { CU_TRY(cudaFree(p)); return 0; }
+extern "C" int cmsisdsp_cuda_host_alloc(void **p, size_t bytes) { if (!p) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "null"); CU_TRY(cudaHostAlloc(p, bytes, cudaHostAllocDefault)); return 0; }
+extern "C" int cmsisdsp_cuda_host_free(void *p) { CU_TRY(cudaFreeHost(p)); return 0; }
+extern "C" int cmsisdsp_cuda_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream)
+{ CU_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream)); return 0; }
+extern "C" int cmsisdsp_cuda_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream)
+{ CU_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream)); return 0; }
+extern "C" int cmsisdsp_cuda_stream_create(void **stream)
+{ if (!stream) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "null"); cudaStream_t s; CU_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); *stream = (void *)s; return 0; }
+extern "C" int cmsisdsp_cuda_stream_destroy(void *stream) { CU_TRY(cudaStreamDestroy((cudaStream_t)stream)); return 0; }
+extern "C" int cmsisdsp_cuda_stream_synchronize(void *stream) { CU_TRY(cudaStreamSynchronize((cudaStream_t)stream)); return 0; }
+
+extern "C" int cmsisdsp_cuda_is_device_pointer(const void *ptr)
+{
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, ptr);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(CMSISDSP_CUDA_ERR_RUNTIME, "cudaPointerGetAttributes", e); }
+    return (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) ? 1 : 0;
+}
+
+struct Timer { cudaEvent_t e0, e1; };
+extern "C" int cmsisdsp_cuda_timer_begin(void **timer, void *stream)
+{
+    if (!timer) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "null");
+    Timer *t = new Timer;
+    CU_TRY(cudaEventCreate(&t->e0));
+    CU_TRY(cudaEventCreate(&t->e1));
+    CU_TRY(cudaEventRecord(t->e0, (cudaStream_t)stream));
+    *timer = t;
+    return 0;
+}
+extern "C" int cmsisdsp_cuda_timer_end(void *timer, void *stream, float *ms)
+{
+    Timer *t = (Timer *)timer;
+    if (!t) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "null");
+    CU_TRY(cudaEventRecord(t->e1, (cudaStream_t)stream));
+    CU_TRY(cudaEventSynchronize(t->e1));
+    float v = 0;
+    CU_TRY(cudaEventElapsedTime(&v, t->e0, t->e1));
+    if (ms) *ms = v;
+    cudaEventDestroy(t->e0); cudaEventDestroy(t->e1);
+    delete t;
+    return 0;
+}
+
+extern "C" const char *cmsisdsp_cuda_last_error(void) { return g_err; }
+extern "C" uint64_t cmsisdsp_cuda_launch_count(void) { return g_launches.load(); }

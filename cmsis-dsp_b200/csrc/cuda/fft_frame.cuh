@@ -1,0 +1,208 @@
+/*
+ * fft_frame.cuh -- one-frame-per-thread-group Stockham FFT engine (host/device).
+ *
+ * A frame of N complex points is processed by T threads, E = N/T points per thread,
+ * in NP <= 3 register passes separated by shared-memory exchanges:
+ *
+ *   pass p (radix R, s = product of the radices before it), butterfly j in [0, N/R):
+ *       reads   x[j + t*N/R],               t = 0..R-1         (always lane-contiguous)
+ *       p = j / s, q = j % s
+ *       writes  y[q + s*(R*p + t')] = out_t' ,  out = DIF butterfly (twiddle AFTER the
+ *               butterfly: out_t' = DFT_R(x)[t'] * W_N^(s*p*t'))
+ *
+ * which is the decimation-in-frequency Stockham autosort recursion: same butterflies,
+ * same twiddles and same operand order as the reference's in-place DIF passes
+ * (arm_radix8_butterfly_f32 / arm_radix4_butterfly_q31 / _q15), but results come out in
+ * natural order, so arm_bitreversal2.c's swap pass disappears (bitReverseFlag = 0 is
+ * served by scattering through the plan's permutation instead).
+ *
+ * The first pass reads HBM directly into registers (lane-contiguous => coalesced) and
+ * the last pass writes HBM directly from registers; only the NP-1 exchanges touch
+ * shared memory (padded layout, see Plan::pad).
+ */
+#pragma once
+#include "fft_arith.cuh"
+
+#ifndef FFT_TRACE_SMEM
+#define FFT_TRACE_SMEM(ptr, bytes, is_store) ((void)0)
+#endif
+
+namespace b200fft {
+
+/* ---------------------------------------------------------------- pass descriptors */
+
+/* f32 pass: true radix-R butterfly, external twiddles from the N-entry (cos,+sin) table */
+template <int R_> struct PassF32 {
+    static constexpr int R = R_;
+    static constexpr bool kMirror = false;
+    static FFT_HD int out_index(int e) { return e; }
+    template <bool INV, int N, bool LASTPASS>
+    static FFT_HD void compute(cf32 *x, const cf32 *__restrict__ tw, int sp /* s*p */)
+    {
+        DftF32<R>::run(x);
+        if (!LASTPASS) {
+#pragma unroll
+            for (int t = 1; t < R; t++) x[t] = mul_conj(x[t], tw[sp * t]);
+        }
+    }
+};
+/* radix-8 f32 pass whose two butterflies per thread are a mirror pair (j, N/8 - j):
+ * used next to the real side of arm_rfft_fast_f32 so split/merge stay thread-local */
+struct PassF32Mirror8 : PassF32<8> { static constexpr bool kMirror = true; };
+
+/* fixed-point pass: one or two of the reference's DIF stages, executed back to back on the
+ * R = ra*rb points held by the thread. */
+template <class ARITH, int KA, int KB = -1> struct PassFix {
+    static constexpr int ra = (KA == ST_PRE2) ? 2 : 4;
+    static constexpr int rb = (KB < 0) ? 1 : 4;
+    static constexpr int R = ra * rb;
+    static constexpr bool kMirror = false;
+    typedef typename ARITH::work work;
+    typedef typename ARITH::twid twid;
+    typedef typename ARITH::elem telem;     /* twiddle tables use the storage element type */
+
+    /* element e = w + rb*v holds residue v + ra*w after the pass */
+    static FFT_HD int out_index(int e) { return (e / rb) + ra * (e % rb); }
+
+    static FFT_HD twid ldtw(const telem *__restrict__ tw, int idx) { return ARITH::load(tw[idx]); }
+
+    template <int K, bool INV>
+    static FFT_HD void stage4(work &a, work &b, work &c, work &d, const telem *__restrict__ tw, int ia)
+    {
+        if (K == ST_LAST4) {
+            twid z = {0, 0};
+            ARITH::template bfly4<K, INV>(a, b, c, d, z, z, z);
+        } else {
+            ARITH::template bfly4<K, INV>(a, b, c, d, ldtw(tw, ia), ldtw(tw, 2 * ia), ldtw(tw, 3 * ia));
+        }
+    }
+
+    template <bool INV, int N, bool LASTPASS>
+    static FFT_HD void compute(work *x, const telem *__restrict__ tw, int sp /* s*p */)
+    {
+        /* stage a on elements t = u + rb*v  (u < rb, v < ra), twiddle exponent sp + (N/R)*u */
+#pragma unroll
+        for (int u = 0; u < rb; u++) {
+            const int ia = sp + (N / R) * u;
+            if (KA == ST_PRE2)
+                ARITH::template bfly2<INV>(x[u], x[u + rb], ldtw(tw, ia));
+            else
+                stage4<KA, INV>(x[u], x[u + rb], x[u + 2 * rb], x[u + 3 * rb], tw, ia);
+        }
+        if (KB >= 0) {
+            /* stage b on elements u = 0..3 of each residue v, twiddle exponent ra*sp */
+#pragma unroll
+            for (int v = 0; v < ra; v++)
+                stage4<KB, INV>(x[rb * v], x[rb * v + 1], x[rb * v + 2], x[rb * v + 3], tw, ra * sp);
+        }
+    }
+};
+
+/* ---------------------------------------------------------------- plan */
+
+struct NoPass { static constexpr int R = 1; static constexpr bool kMirror = false; };
+
+template <class ARITH_, int N_, int T_, int F_, int PADA_, int PADB_, class P0_, class P1_ = NoPass, class P2_ = NoPass>
+struct Plan {
+    typedef ARITH_ Arith;
+    typedef P0_ P0; typedef P1_ P1; typedef P2_ P2;
+    static constexpr int N = N_;          /* complex points per frame */
+    static constexpr int T = T_;          /* threads per frame */
+    static constexpr int F = F_;          /* frames per CTA */
+    static constexpr int E = N / T;       /* points per thread */
+    static constexpr int NP = (P1::R == 1) ? 1 : ((P2::R == 1) ? 2 : 3);
+    static constexpr int S0 = 1, S1 = P0::R, S2 = P0::R * P1::R;
+    static_assert(P0::R * P1::R * P2::R == N, "radices must multiply to N");
+    static_assert(E % P0::R == 0 && E % P1::R == 0 && E % P2::R == 0, "E must be a multiple of every radix");
+    /* padded exchange layout: PADB extra elements after every 2^PADA elements */
+    static FFT_HD int pad(int i) { return PADB_ ? (i + ((i >> PADA_) * PADB_)) : i; }
+    static constexpr int kFrameElems = PADB_ ? (N + ((N - 1) >> PADA_) * PADB_ + PADB_) : N;
+    static constexpr int kSmemBytes = (NP > 1) ? F * kFrameElems * (int)sizeof(typename ARITH_::elem) : 0;
+    static constexpr int kThreads = T * F;
+};
+
+template <class PL, int P> struct PassOf;
+template <class PL> struct PassOf<PL, 0> { typedef typename PL::P0 type; static constexpr int S = PL::S0; };
+template <class PL> struct PassOf<PL, 1> { typedef typename PL::P1 type; static constexpr int S = PL::S1; };
+template <class PL> struct PassOf<PL, 2> { typedef typename PL::P2 type; static constexpr int S = PL::S2; };
+
+/* butterfly index handled by thread i as its b-th butterfly of a pass with NBF butterflies */
+template <bool MIRROR, int T, int NBF> FFT_HD int bfly_index(int i, int b)
+{
+    if (!MIRROR) return i + T * b;
+    return b == 0 ? i : (i == 0 ? NBF / 2 : NBF - i);
+}
+
+/* ---------------------------------------------------------------- engine */
+
+template <class PL> struct Engine {
+    typedef typename PL::Arith A;
+    typedef typename A::elem elem;
+    typedef typename A::work work;
+    static constexpr int N = PL::N, T = PL::T, E = PL::E, NP = PL::NP;
+
+    struct Regs { work v[E]; };
+
+    /* ---- shared-memory exchange ---- */
+    template <int P> static FFT_HD void smem_store(const Regs &r, elem *sm, int i)
+    {
+        typedef typename PassOf<PL, P>::type PS;
+        constexpr int R = PS::R, S = PassOf<PL, P>::S, NB = E / R, NBF = N / R;
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+            const int j = bfly_index<PS::kMirror, T, NBF>(i, b);
+            const int base = (j % S) + S * R * (j / S);
+#pragma unroll
+            for (int e = 0; e < R; e++) {
+                const int idx = PL::pad(base + S * PS::out_index(e));
+                FFT_TRACE_SMEM(&sm[idx], (int)sizeof(elem), 1);
+                sm[idx] = A::store(r.v[b * R + e]);
+            }
+        }
+    }
+    template <int P> static FFT_HD void smem_load(Regs &r, const elem *sm, int i)
+    {
+        typedef typename PassOf<PL, P>::type PS;
+        constexpr int R = PS::R, NB = E / R, NBF = N / R;
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+            const int j = bfly_index<PS::kMirror, T, NBF>(i, b);
+#pragma unroll
+            for (int e = 0; e < R; e++) {
+                const int idx = PL::pad(j + e * NBF);
+                FFT_TRACE_SMEM(&sm[idx], (int)sizeof(elem), 0);
+                r.v[b * R + e] = A::load(sm[idx]);
+            }
+        }
+    }
+
+    /* ---- butterflies of pass P on the registers ---- */
+    template <int P, bool INV, class TW> static FFT_HD void compute(Regs &r, const TW *__restrict__ tw, int i)
+    {
+        typedef typename PassOf<PL, P>::type PS;
+        constexpr int R = PS::R, S = PassOf<PL, P>::S, NB = E / R, NBF = N / R;
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+            const int j = bfly_index<PS::kMirror, T, NBF>(i, b);
+            const int sp = S * (j / S);
+            PS::template compute<INV, N, (P == NP - 1)>(&r.v[b * R], tw, sp);
+        }
+    }
+
+    /* index (within the frame) of register slot (b, e) on the input side of pass P / output side */
+    template <int P> static FFT_HD int in_index(int i, int b, int e)
+    {
+        typedef typename PassOf<PL, P>::type PS;
+        constexpr int NBF = N / PS::R;
+        return bfly_index<PS::kMirror, T, NBF>(i, b) + e * NBF;
+    }
+    template <int P> static FFT_HD int out_index(int i, int b, int e)
+    {
+        typedef typename PassOf<PL, P>::type PS;
+        constexpr int R = PS::R, S = PassOf<PL, P>::S, NBF = N / R;
+        const int j = bfly_index<PS::kMirror, T, NBF>(i, b);
+        return (j % S) + S * (R * (j / S) + PS::out_index(e));
+    }
+};
+
+}  // namespace b200fft

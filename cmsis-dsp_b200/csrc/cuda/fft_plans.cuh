@@ -1,0 +1,82 @@
+/*
+ * fft_plans.cuh -- the compile-time plan table: for every supported (type, length) the
+ * thread geometry, radix passes and exchange-buffer padding.  Shared by the CUDA kernels
+ * and by the CPU emulator used in the non-GPU tests.
+ *
+ * f32 lengths (complex): 16..4096     reference dispatch arm_cfft_f32.c:1263-1280
+ * q31/q15 lengths:       16..4096     reference dispatch arm_cfft_q31.c:712-750, arm_cfft_q15.c:679-717
+ *   N = 4^m   -> stages FIRST4, MID4.., LAST4            (arm_cfft_radix4_q31.c:153-473)
+ *   N = 2*4^m -> PRE2 then the same on both halves, <<1  (arm_cfft_q31.c:763-822)
+ * rfft_fast lengths (real): 32..4096  -> complex length N/2 with a Mirror8 pass next to
+ *   the real side (fft_body.cuh).
+ *
+ * Plan<Arith, N, T, F, PADA, PADB, passes...>: T threads per frame (16 points per thread
+ * wherever N >= 16), F frames per CTA, PADB padding elements after every 2^PADA elements
+ * of the exchange buffer.  Padding choices are validated by tests/test_emulator.py
+ * (bank-conflict counts of every exchange, measured by the emulator's smem trace).
+ */
+#pragma once
+#include "fft_body.cuh"
+
+namespace b200fft {
+
+typedef PassF32<2> F2;
+typedef PassF32<4> F4;
+typedef PassF32<8> F8;
+typedef PassF32<16> F16;
+typedef PassF32Mirror8 M8;
+
+/* ---- f32 complex ---- */
+template <int N> struct PlanCfftF32;
+template <> struct PlanCfftF32<16>   { typedef Plan<ArithF32, 16, 1, 128, 0, 0, F16> type; };
+template <> struct PlanCfftF32<32>   { typedef Plan<ArithF32, 32, 2, 64, 3, 1, F4, F8> type; };
+template <> struct PlanCfftF32<64>   { typedef Plan<ArithF32, 64, 4, 32, 3, 1, F8, F8> type; };
+template <> struct PlanCfftF32<128>  { typedef Plan<ArithF32, 128, 8, 16, 4, 1, F16, F8> type; };
+template <> struct PlanCfftF32<256>  { typedef Plan<ArithF32, 256, 16, 8, 4, 1, F16, F16> type; };
+template <> struct PlanCfftF32<512>  { typedef Plan<ArithF32, 512, 32, 4, 4, 1, F16, F8, F4> type; };
+template <> struct PlanCfftF32<1024> { typedef Plan<ArithF32, 1024, 64, 2, 4, 1, F16, F8, F8> type; };
+template <> struct PlanCfftF32<2048> { typedef Plan<ArithF32, 2048, 128, 1, 4, 1, F16, F16, F8> type; };
+template <> struct PlanCfftF32<4096> { typedef Plan<ArithF32, 4096, 256, 1, 4, 1, F16, F16, F16> type; };
+
+/* ---- rfft_fast_f32: NC = complex length = real length / 2 ---- */
+template <int NC> struct PlanRfftFwd;   /* trailing Mirror8 */
+template <> struct PlanRfftFwd<16>   { typedef Plan<ArithF32, 16, 1, 128, 0, 0, F2, M8> type; };
+template <> struct PlanRfftFwd<32>   { typedef Plan<ArithF32, 32, 2, 64, 3, 1, F4, M8> type; };
+template <> struct PlanRfftFwd<64>   { typedef Plan<ArithF32, 64, 4, 32, 3, 1, F8, M8> type; };
+template <> struct PlanRfftFwd<128>  { typedef Plan<ArithF32, 128, 8, 16, 4, 1, F16, M8> type; };
+template <> struct PlanRfftFwd<256>  { typedef Plan<ArithF32, 256, 16, 8, 4, 1, F4, F8, M8> type; };
+template <> struct PlanRfftFwd<512>  { typedef Plan<ArithF32, 512, 32, 4, 4, 1, F4, F16, M8> type; };
+template <> struct PlanRfftFwd<1024> { typedef Plan<ArithF32, 1024, 64, 2, 4, 1, F16, F8, M8> type; };
+template <> struct PlanRfftFwd<2048> { typedef Plan<ArithF32, 2048, 128, 1, 4, 1, F16, F16, M8> type; };
+
+template <int NC> struct PlanRfftInv;   /* leading Mirror8 */
+template <> struct PlanRfftInv<16>   { typedef Plan<ArithF32, 16, 1, 128, 0, 0, M8, F2> type; };
+template <> struct PlanRfftInv<32>   { typedef Plan<ArithF32, 32, 2, 64, 3, 1, M8, F4> type; };
+template <> struct PlanRfftInv<64>   { typedef Plan<ArithF32, 64, 4, 32, 3, 1, M8, F8> type; };
+template <> struct PlanRfftInv<128>  { typedef Plan<ArithF32, 128, 8, 16, 4, 1, M8, F16> type; };
+template <> struct PlanRfftInv<256>  { typedef Plan<ArithF32, 256, 16, 8, 4, 1, M8, F8, F4> type; };
+template <> struct PlanRfftInv<512>  { typedef Plan<ArithF32, 512, 32, 4, 4, 1, M8, F16, F4> type; };
+template <> struct PlanRfftInv<1024> { typedef Plan<ArithF32, 1024, 64, 2, 4, 1, M8, F8, F16> type; };
+template <> struct PlanRfftInv<2048> { typedef Plan<ArithF32, 2048, 128, 1, 4, 1, M8, F16, F16> type; };
+
+/* ---- q31 / q15 ---- */
+template <class AR, int N> struct PlanCfftFix;
+#define FIXPLAN(N_, T_, F_, PA_, PB_, ...)                                                   \
+    template <class AR> struct PlanCfftFix<AR, N_> {                                         \
+        /* 4-byte (q15) elements: one pad word per 32 elements; 8-byte (q31): per 16 */      \
+        typedef Plan<AR, N_, T_, F_, (PB_ && sizeof(typename AR::elem) == 4) ? 5 : PA_, PB_, __VA_ARGS__> type;                \
+    };
+#define PF(...) PassFix<AR, __VA_ARGS__>
+FIXPLAN(16,   1,   128, 0, 0, PF(ST_FIRST4, ST_LAST4))
+FIXPLAN(32,   2,   64,  3, 1, PF(ST_PRE2, ST_FIRST4), PF(ST_LAST4))
+FIXPLAN(64,   4,   32,  4, 1, PF(ST_FIRST4, ST_MID4), PF(ST_LAST4))
+FIXPLAN(128,  8,   16,  4, 1, PF(ST_PRE2, ST_FIRST4), PF(ST_MID4, ST_LAST4))
+FIXPLAN(256,  16,  8,   4, 1, PF(ST_FIRST4, ST_MID4), PF(ST_MID4, ST_LAST4))
+FIXPLAN(512,  32,  4,   4, 1, PF(ST_PRE2, ST_FIRST4), PF(ST_MID4, ST_MID4), PF(ST_LAST4))
+FIXPLAN(1024, 64,  2,   4, 1, PF(ST_FIRST4, ST_MID4), PF(ST_MID4, ST_MID4), PF(ST_LAST4))
+FIXPLAN(2048, 128, 1,   4, 1, PF(ST_PRE2, ST_FIRST4), PF(ST_MID4, ST_MID4), PF(ST_MID4, ST_LAST4))
+FIXPLAN(4096, 256, 1,   4, 1, PF(ST_FIRST4, ST_MID4), PF(ST_MID4, ST_MID4), PF(ST_MID4, ST_LAST4))
+#undef PF
+#undef FIXPLAN
+
+}  // namespace b200fft

@@ -1,0 +1,207 @@
+/*
+ * arm_cfft_exec.c -- exec functions of the FFT path: thin C over libcmsisdsp_cuda.
+ *
+ *   arm_cfft_f32 / q31 / q15   reference: arm_cfft_f32.c:1243-1298, arm_cfft_q31.c:704-755, arm_cfft_q15.c:671-722
+ *   arm_rfft_fast_f32          reference: arm_rfft_fast_f32.c:675-699
+ *   arm_*_batch_*              B200 extension (include/dsp/transform_functions.h)
+ *
+ * Data may live in host or device memory.  Host buffers are streamed through the device
+ * in chunks on three streams (copy-in, kernel, copy-out overlap; buffers obtained from
+ * cmsisdsp_cuda_host_alloc are pinned and get full-duplex PCIe).  Device buffers are
+ * transformed in place on the library's per-thread stream.  No CPU fallback exists: when
+ * the shim reports an error the batched call returns ARM_MATH_ARGUMENT_ERROR and the
+ * legacy void call records it for arm_cuda_last_status().
+ *
+ * Like the reference, unsupported lengths in a hand-built instance make the legacy exec
+ * functions a no-op (arm_cfft_f32.c:1263-1280 falls through its switch).
+ */
+#include "arm_math_types.h"
+#include "dsp/transform_functions.h"
+#include "cmsisdsp_cuda.h"
+
+#include <stdlib.h>
+
+#define NSTREAM 3
+#define CHUNK_BYTES ((size_t)16 << 20)
+
+typedef struct {
+    int device;
+    void *stream[NSTREAM];
+    void *buf[NSTREAM][2];      /* staging: [0] data / rfft input, [1] rfft output */
+    size_t cap[NSTREAM][2];
+} tls_ctx;
+
+static __thread tls_ctx g_ctx = { -1, {0}, {{0}}, {{0}} };
+static __thread arm_status g_last = ARM_MATH_SUCCESS;
+
+arm_status arm_cuda_last_status(void) { return g_last; }
+
+static int ctx_ready(void)
+{
+    int dev = cmsisdsp_cuda_get_device();
+    if (dev < 0) return CMSISDSP_CUDA_ERR_NO_DEVICE;
+    if (g_ctx.device == dev) return 0;
+    /* first use on this thread, or the caller switched device: (re)create streams lazily */
+    for (int i = 0; i < NSTREAM; i++) {
+        g_ctx.stream[i] = 0;
+        g_ctx.buf[i][0] = g_ctx.buf[i][1] = 0;
+        g_ctx.cap[i][0] = g_ctx.cap[i][1] = 0;
+        int rc = cmsisdsp_cuda_stream_create(&g_ctx.stream[i]);
+        if (rc) return rc;
+    }
+    g_ctx.device = dev;
+    return 0;
+}
+
+static int staging(int s, int which, size_t bytes, void **out)
+{
+    if (g_ctx.cap[s][which] < bytes) {
+        if (g_ctx.buf[s][which]) cmsisdsp_cuda_free(g_ctx.buf[s][which]);
+        g_ctx.buf[s][which] = 0;
+        g_ctx.cap[s][which] = 0;
+        int rc = cmsisdsp_cuda_malloc(&g_ctx.buf[s][which], bytes);
+        if (rc) return rc;
+        g_ctx.cap[s][which] = bytes;
+    }
+    *out = g_ctx.buf[s][which];
+    return 0;
+}
+
+static int ensure_plan(int type, uint32_t fftLen, const void *tw, const uint16_t *br, uint16_t brLen)
+{
+    if (cmsisdsp_cuda_plan_ready(type, fftLen)) return 0;
+    return cmsisdsp_cuda_plan_upload(type, fftLen, tw, br, brLen);
+}
+
+typedef int (*cfft_fn)(void *, uint32_t, uint64_t, uint8_t, uint8_t, void *);
+
+static int valid_len(uint32_t n) { return n >= 16 && n <= 4096 && (n & (n - 1)) == 0; }
+
+static arm_status cfft_batch(int type, cfft_fn fn, size_t scalarBytes, uint32_t fftLen, const void *tw,
+                             const uint16_t *br, uint16_t brLen, void *p, uint64_t nFrames,
+                             uint8_t ifftFlag, uint8_t bitReverseFlag)
+{
+    if (!p || !tw) return ARM_MATH_ARGUMENT_ERROR;
+    if (!valid_len(fftLen)) return ARM_MATH_ARGUMENT_ERROR;
+    if (nFrames == 0) return ARM_MATH_SUCCESS;
+    if (ctx_ready()) return ARM_MATH_ARGUMENT_ERROR;
+    if (ensure_plan(type, fftLen, tw, br, brLen)) return ARM_MATH_ARGUMENT_ERROR;
+
+    const size_t frameBytes = (size_t)2 * fftLen * scalarBytes;
+    const int onDevice = cmsisdsp_cuda_is_device_pointer(p);
+    if (onDevice < 0) return ARM_MATH_ARGUMENT_ERROR;
+    if (onDevice) {
+        if (fn(p, fftLen, nFrames, ifftFlag, bitReverseFlag, g_ctx.stream[0])) return ARM_MATH_ARGUMENT_ERROR;
+        return cmsisdsp_cuda_stream_synchronize(g_ctx.stream[0]) ? ARM_MATH_ARGUMENT_ERROR : ARM_MATH_SUCCESS;
+    }
+    uint64_t perChunk = CHUNK_BYTES / frameBytes;
+    if (perChunk == 0) perChunk = 1;
+    int rc = 0, s = 0;
+    for (uint64_t f = 0; f < nFrames && !rc; f += perChunk, s = (s + 1) % NSTREAM) {
+        const uint64_t n = (nFrames - f < perChunk) ? nFrames - f : perChunk;
+        char *h = (char *)p + f * frameBytes;
+        void *d;
+        /* the stream serialises reuse of its staging buffer */
+        if ((rc = staging(s, 0, (size_t)perChunk * frameBytes, &d))) break;
+        if ((rc = cmsisdsp_cuda_memcpy_h2d(d, h, (size_t)n * frameBytes, g_ctx.stream[s]))) break;
+        if ((rc = fn(d, fftLen, n, ifftFlag, bitReverseFlag, g_ctx.stream[s]))) break;
+        rc = cmsisdsp_cuda_memcpy_d2h(h, d, (size_t)n * frameBytes, g_ctx.stream[s]);
+    }
+    for (int i = 0; i < NSTREAM; i++)
+        if (cmsisdsp_cuda_stream_synchronize(g_ctx.stream[i])) rc = rc ? rc : -1;
+    return rc ? ARM_MATH_ARGUMENT_ERROR : ARM_MATH_SUCCESS;
+}
+
+arm_status arm_cfft_batch_f32(const arm_cfft_instance_f32 *S, float32_t *p, uint32_t nFrames, uint8_t ifftFlag, uint8_t bitReverseFlag)
+{
+    if (!S) return ARM_MATH_ARGUMENT_ERROR;
+    return cfft_batch(CMSISDSP_CUDA_F32, cmsisdsp_cuda_cfft_f32, sizeof(float32_t), S->fftLen, S->pTwiddle,
+                      S->pBitRevTable, S->bitRevLength, p, nFrames, ifftFlag, bitReverseFlag);
+}
+arm_status arm_cfft_batch_q31(const arm_cfft_instance_q31 *S, q31_t *p, uint32_t nFrames, uint8_t ifftFlag, uint8_t bitReverseFlag)
+{
+    if (!S) return ARM_MATH_ARGUMENT_ERROR;
+    return cfft_batch(CMSISDSP_CUDA_Q31, cmsisdsp_cuda_cfft_q31, sizeof(q31_t), S->fftLen, S->pTwiddle,
+                      S->pBitRevTable, S->bitRevLength, p, nFrames, ifftFlag, bitReverseFlag);
+}
+arm_status arm_cfft_batch_q15(const arm_cfft_instance_q15 *S, q15_t *p, uint32_t nFrames, uint8_t ifftFlag, uint8_t bitReverseFlag)
+{
+    if (!S) return ARM_MATH_ARGUMENT_ERROR;
+    return cfft_batch(CMSISDSP_CUDA_Q15, cmsisdsp_cuda_cfft_q15, sizeof(q15_t), S->fftLen, S->pTwiddle,
+                      S->pBitRevTable, S->bitRevLength, p, nFrames, ifftFlag, bitReverseFlag);
+}
+
+/* clobber != 0: also leave the N/2-point CFFT in p after a forward transform, the
+ * side effect of the reference's in-place CFFT on the input buffer (rfft_fast_f32.c:694) */
+static arm_status rfft_batch(const arm_rfft_fast_instance_f32 *S, float32_t *p, float32_t *pOut,
+                             uint64_t nFrames, uint8_t ifftFlag, int clobber)
+{
+    if (!S || !p || !pOut || p == pOut || !S->pTwiddleRFFT || !S->Sint.pTwiddle) return ARM_MATH_ARGUMENT_ERROR;
+    const uint32_t N = S->fftLenRFFT;
+    if (N < 32 || !valid_len(N) || S->Sint.fftLen != N / 2) return ARM_MATH_ARGUMENT_ERROR;
+    if (nFrames == 0) return ARM_MATH_SUCCESS;
+    if (ctx_ready()) return ARM_MATH_ARGUMENT_ERROR;
+    if (ensure_plan(CMSISDSP_CUDA_F32, N / 2, S->Sint.pTwiddle, S->Sint.pBitRevTable, S->Sint.bitRevLength))
+        return ARM_MATH_ARGUMENT_ERROR;
+    if (!cmsisdsp_cuda_rfft_plan_ready(N) && cmsisdsp_cuda_rfft_plan_upload(N, S->pTwiddleRFFT))
+        return ARM_MATH_ARGUMENT_ERROR;
+
+    const size_t frameBytes = (size_t)N * sizeof(float32_t);
+    const int inDev = cmsisdsp_cuda_is_device_pointer(p), outDev = cmsisdsp_cuda_is_device_pointer(pOut);
+    if (inDev < 0 || outDev < 0 || inDev != outDev) return ARM_MATH_ARGUMENT_ERROR;
+    if (inDev) {
+        if (cmsisdsp_cuda_rfft_fast_f32(p, pOut, N, nFrames, ifftFlag, g_ctx.stream[0])) return ARM_MATH_ARGUMENT_ERROR;
+        if (clobber && !ifftFlag && cmsisdsp_cuda_cfft_f32(p, N / 2, nFrames, 0, 1, g_ctx.stream[0])) return ARM_MATH_ARGUMENT_ERROR;
+        return cmsisdsp_cuda_stream_synchronize(g_ctx.stream[0]) ? ARM_MATH_ARGUMENT_ERROR : ARM_MATH_SUCCESS;
+    }
+    uint64_t perChunk = CHUNK_BYTES / frameBytes;
+    if (perChunk == 0) perChunk = 1;
+    int rc = 0, s = 0;
+    for (uint64_t f = 0; f < nFrames && !rc; f += perChunk, s = (s + 1) % NSTREAM) {
+        const uint64_t n = (nFrames - f < perChunk) ? nFrames - f : perChunk;
+        char *hin = (char *)p + f * frameBytes, *hout = (char *)pOut + f * frameBytes;
+        void *din, *dout;
+        if ((rc = staging(s, 0, (size_t)perChunk * frameBytes, &din))) break;
+        if ((rc = staging(s, 1, (size_t)perChunk * frameBytes, &dout))) break;
+        if ((rc = cmsisdsp_cuda_memcpy_h2d(din, hin, (size_t)n * frameBytes, g_ctx.stream[s]))) break;
+        if ((rc = cmsisdsp_cuda_rfft_fast_f32(din, dout, N, n, ifftFlag, g_ctx.stream[s]))) break;
+        if ((rc = cmsisdsp_cuda_memcpy_d2h(hout, dout, (size_t)n * frameBytes, g_ctx.stream[s]))) break;
+        if (clobber && !ifftFlag) {
+            if ((rc = cmsisdsp_cuda_cfft_f32(din, N / 2, n, 0, 1, g_ctx.stream[s]))) break;
+            rc = cmsisdsp_cuda_memcpy_d2h(hin, din, (size_t)n * frameBytes, g_ctx.stream[s]);
+        }
+    }
+    for (int i = 0; i < NSTREAM; i++)
+        if (cmsisdsp_cuda_stream_synchronize(g_ctx.stream[i])) rc = rc ? rc : -1;
+    return rc ? ARM_MATH_ARGUMENT_ERROR : ARM_MATH_SUCCESS;
+}
+
+arm_status arm_rfft_fast_batch_f32(const arm_rfft_fast_instance_f32 *S, float32_t *p, float32_t *pOut,
+                                   uint32_t nFrames, uint8_t ifftFlag)
+{
+    return rfft_batch(S, p, pOut, nFrames, ifftFlag, 0);
+}
+
+/* ---- legacy single-frame signatures ---- */
+
+static int legacy_len_ok(uint32_t n) { return valid_len(n); }
+
+void arm_cfft_f32(const arm_cfft_instance_f32 *S, float32_t *p1, uint8_t ifftFlag, uint8_t bitReverseFlag)
+{
+    if (!legacy_len_ok(S->fftLen)) { g_last = ARM_MATH_SUCCESS; return; }
+    g_last = arm_cfft_batch_f32(S, p1, 1, ifftFlag, bitReverseFlag);
+}
+void arm_cfft_q31(const arm_cfft_instance_q31 *S, q31_t *p1, uint8_t ifftFlag, uint8_t bitReverseFlag)
+{
+    if (!legacy_len_ok(S->fftLen)) { g_last = ARM_MATH_SUCCESS; return; }
+    g_last = arm_cfft_batch_q31(S, p1, 1, ifftFlag, bitReverseFlag);
+}
+void arm_cfft_q15(const arm_cfft_instance_q15 *S, q15_t *p1, uint8_t ifftFlag, uint8_t bitReverseFlag)
+{
+    if (!legacy_len_ok(S->fftLen)) { g_last = ARM_MATH_SUCCESS; return; }
+    g_last = arm_cfft_batch_q15(S, p1, 1, ifftFlag, bitReverseFlag);
+}
+void arm_rfft_fast_f32(const arm_rfft_fast_instance_f32 *S, float32_t *p, float32_t *pOut, uint8_t ifftFlag)
+{
+    g_last = rfft_batch(S, p, pOut, 1, ifftFlag, 1);
+}

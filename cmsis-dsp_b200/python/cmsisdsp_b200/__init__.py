@@ -1,0 +1,226 @@
+"""ctypes bindings of the B200 CMSIS-DSP FFT libraries (used by tests/, bench.py, smoke()).
+
+Two shared objects, both built in-tree by `cmsis-dsp_b200/csrc/Makefile`:
+
+  libcmsisdsp_b200.so   the C front library: arm_cfft_init_*/arm_cfft_* /arm_rfft_fast_* and the
+                        batched extensions, i.e. the reference's operator API for the FFT path
+                        (include/dsp/transform_functions.h)
+  libcmsisdsp_cuda.so   the CUDA shim it calls (include/cmsisdsp_cuda.h)
+
+This module is a binding, not an implementation: every transform goes through the C ABI.
+It raises immediately if the libraries are missing -- there is no Python/CPU fallback.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIBDIR = os.path.normpath(os.path.join(_HERE, "..", "..", "lib"))
+
+LENGTHS = [16, 32, 64, 128, 256, 512, 1024, 2048, 4096]
+RLENGTHS = [32, 64, 128, 256, 512, 1024, 2048, 4096]
+ARM_MATH_SUCCESS = 0
+ARM_MATH_ARGUMENT_ERROR = -1
+TYPE_ID = {"f32": 0, "q31": 1, "q15": 2}
+NP_DTYPE = {"f32": np.float32, "q31": np.int32, "q15": np.int16}
+C_SCALAR = {"f32": C.c_float, "q31": C.c_int32, "q15": C.c_int16}
+
+
+def _mk_cfft_instance(scalar):
+    class Inst(C.Structure):
+        _fields_ = [("fftLen", C.c_uint16), ("pTwiddle", C.POINTER(scalar)),
+                    ("pBitRevTable", C.POINTER(C.c_uint16)), ("bitRevLength", C.c_uint16)]
+    return Inst
+
+
+arm_cfft_instance_f32 = _mk_cfft_instance(C.c_float)
+arm_cfft_instance_q31 = _mk_cfft_instance(C.c_int32)
+arm_cfft_instance_q15 = _mk_cfft_instance(C.c_int16)
+CFFT_INSTANCE = {"f32": arm_cfft_instance_f32, "q31": arm_cfft_instance_q31, "q15": arm_cfft_instance_q15}
+
+
+class arm_rfft_fast_instance_f32(C.Structure):
+    _fields_ = [("Sint", arm_cfft_instance_f32), ("fftLenRFFT", C.c_uint16), ("pTwiddleRFFT", C.POINTER(C.c_float))]
+
+
+_libs = {}
+
+
+def _load(name):
+    path = os.path.join(LIBDIR, name)
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           f"or `make -C cmsis-dsp_b200/csrc` (there is no CPU fallback)")
+    return C.CDLL(path, mode=C.RTLD_GLOBAL)
+
+
+def cuda():
+    """libcmsisdsp_cuda.so with argtypes declared."""
+    if "cuda" in _libs:
+        return _libs["cuda"]
+    L = _load("libcmsisdsp_cuda.so")
+    vp, u32, u64, u8, i = C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint8, C.c_int
+    sig = {
+        "cmsisdsp_cuda_device_count": ([], i), "cmsisdsp_cuda_set_device": ([i], i), "cmsisdsp_cuda_get_device": ([], i),
+        "cmsisdsp_cuda_malloc": ([C.POINTER(vp), C.c_size_t], i), "cmsisdsp_cuda_free": ([vp], i),
+        "cmsisdsp_cuda_host_alloc": ([C.POINTER(vp), C.c_size_t], i), "cmsisdsp_cuda_host_free": ([vp], i),
+        "cmsisdsp_cuda_memcpy_h2d": ([vp, vp, C.c_size_t, vp], i), "cmsisdsp_cuda_memcpy_d2h": ([vp, vp, C.c_size_t, vp], i),
+        "cmsisdsp_cuda_stream_create": ([C.POINTER(vp)], i), "cmsisdsp_cuda_stream_destroy": ([vp], i),
+        "cmsisdsp_cuda_stream_synchronize": ([vp], i), "cmsisdsp_cuda_is_device_pointer": ([vp], i),
+        "cmsisdsp_cuda_timer_begin": ([C.POINTER(vp), vp], i), "cmsisdsp_cuda_timer_end": ([vp, vp, C.POINTER(C.c_float)], i),
+        "cmsisdsp_cuda_plan_upload": ([i, u32, vp, vp, C.c_uint16], i),
+        "cmsisdsp_cuda_rfft_plan_upload": ([u32, vp], i),
+        "cmsisdsp_cuda_plan_ready": ([i, u32], i), "cmsisdsp_cuda_rfft_plan_ready": ([u32], i),
+        "cmsisdsp_cuda_cfft_f32": ([vp, u32, u64, u8, u8, vp], i),
+        "cmsisdsp_cuda_cfft_q31": ([vp, u32, u64, u8, u8, vp], i),
+        "cmsisdsp_cuda_cfft_q15": ([vp, u32, u64, u8, u8, vp], i),
+        "cmsisdsp_cuda_rfft_fast_f32": ([vp, vp, u32, u64, u8, vp], i),
+        "cmsisdsp_cuda_last_error": ([], C.c_char_p), "cmsisdsp_cuda_launch_count": ([], u64),
+        "cmsisdsp_cuda_kernel_info": ([i, u32] + [C.POINTER(i)] * 5, i),
+    }
+    for name, (args, res) in sig.items():
+        fn = getattr(L, name)
+        fn.argtypes, fn.restype = args, res
+    _libs["cuda"] = L
+    return L
+
+
+def lib():
+    """libcmsisdsp_b200.so (the CMSIS-DSP C API) with argtypes declared."""
+    if "front" in _libs:
+        return _libs["front"]
+    cuda()
+    L = _load("libcmsisdsp_b200.so")
+    u8, u16, u32, i = C.c_uint8, C.c_uint16, C.c_uint32, C.c_int
+    for k, inst in CFFT_INSTANCE.items():
+        f = getattr(L, f"arm_cfft_init_{k}")
+        f.argtypes, f.restype = [C.POINTER(inst), u16], i
+        for n in LENGTHS:
+            f = getattr(L, f"arm_cfft_init_{n}_{k}")
+            f.argtypes, f.restype = [C.POINTER(inst)], i
+        f = getattr(L, f"arm_cfft_{k}")
+        f.argtypes, f.restype = [C.POINTER(inst), C.c_void_p, u8, u8], None
+        f = getattr(L, f"arm_cfft_batch_{k}")
+        f.argtypes, f.restype = [C.POINTER(inst), C.c_void_p, u32, u8, u8], i
+    L.arm_rfft_fast_init_f32.argtypes, L.arm_rfft_fast_init_f32.restype = [C.POINTER(arm_rfft_fast_instance_f32), u16], i
+    for n in RLENGTHS:
+        f = getattr(L, f"arm_rfft_fast_init_{n}_f32")
+        f.argtypes, f.restype = [C.POINTER(arm_rfft_fast_instance_f32)], i
+    L.arm_rfft_fast_f32.argtypes, L.arm_rfft_fast_f32.restype = [C.POINTER(arm_rfft_fast_instance_f32), C.c_void_p, C.c_void_p, u8], None
+    L.arm_rfft_fast_batch_f32.argtypes = [C.POINTER(arm_rfft_fast_instance_f32), C.c_void_p, C.c_void_p, u32, u8]
+    L.arm_rfft_fast_batch_f32.restype = i
+    L.arm_cuda_last_status.argtypes, L.arm_cuda_last_status.restype = [], i
+    _libs["front"] = L
+    return L
+
+
+def last_error():
+    return cuda().cmsisdsp_cuda_last_error().decode()
+
+
+def preset(kind, N):
+    """The constant instance arm_cfft_sR_<kind>_len<N> exported by the front library."""
+    return CFFT_INSTANCE[kind].in_dll(lib(), f"arm_cfft_sR_{kind}_len{N}")
+
+
+def rfft_preset(N):
+    return arm_rfft_fast_instance_f32.in_dll(lib(), f"arm_rfft_fast_sR_f32_len{N}")
+
+
+def cfft_instance(kind, N):
+    S = CFFT_INSTANCE[kind]()
+    st = getattr(lib(), f"arm_cfft_init_{kind}")(C.byref(S), N)
+    if st != ARM_MATH_SUCCESS:
+        raise ValueError(f"arm_cfft_init_{kind}({N}) -> {st}")
+    return S
+
+
+def rfft_instance(N):
+    S = arm_rfft_fast_instance_f32()
+    st = lib().arm_rfft_fast_init_f32(C.byref(S), N)
+    if st != ARM_MATH_SUCCESS:
+        raise ValueError(f"arm_rfft_fast_init_f32({N}) -> {st}")
+    return S
+
+
+def instance_tables(S, kind):
+    """numpy copies of (twiddle table, bit-reversal swap list) an instance points at."""
+    n = int(S.fftLen)
+    ntw = 2 * n if kind == "f32" else 3 * n // 2
+    tw = np.ctypeslib.as_array(S.pTwiddle, shape=(ntw,)).copy()
+    br = np.ctypeslib.as_array(S.pBitRevTable, shape=(int(S.bitRevLength),)).copy()
+    return tw, br
+
+
+# ---------------------------------------------------------------- host-buffer API (end to end)
+
+def cfft_batch(kind, N, x, ifft=0, bitrev=1, inplace=False):
+    """arm_cfft_batch_<kind> on a host numpy array [..., 2N]; returns the transformed array."""
+    y = np.ascontiguousarray(x, dtype=NP_DTYPE[kind])
+    if not inplace:
+        y = y.copy()
+    assert y.size % (2 * N) == 0
+    S = cfft_instance(kind, N)
+    st = getattr(lib(), f"arm_cfft_batch_{kind}")(C.byref(S), y.ctypes.data, y.size // (2 * N), int(ifft), int(bitrev))
+    if st != ARM_MATH_SUCCESS:
+        raise RuntimeError(f"arm_cfft_batch_{kind} -> {st}: {last_error()}")
+    return y
+
+
+def rfft_batch(N, x, ifft=0):
+    p = np.ascontiguousarray(x, dtype=np.float32)
+    assert p.size % N == 0
+    out = np.empty_like(p)
+    S = rfft_instance(N)
+    st = lib().arm_rfft_fast_batch_f32(C.byref(S), p.ctypes.data, out.ctypes.data, p.size // N, int(ifft))
+    if st != ARM_MATH_SUCCESS:
+        raise RuntimeError(f"arm_rfft_fast_batch_f32 -> {st}: {last_error()}")
+    return out
+
+
+# ---------------------------------------------------------------- device-pointer API (shim)
+
+def ensure_plans(kind, N):
+    S = cfft_instance(kind, N)
+    rc = cuda().cmsisdsp_cuda_plan_upload(TYPE_ID[kind], N, C.cast(S.pTwiddle, C.c_void_p),
+                                          C.cast(S.pBitRevTable, C.c_void_p), S.bitRevLength)
+    if rc:
+        raise RuntimeError(f"plan_upload({kind},{N}) -> {rc}: {last_error()}")
+
+
+def ensure_rfft_plans(N):
+    ensure_plans("f32", N // 2)
+    S = rfft_instance(N)
+    rc = cuda().cmsisdsp_cuda_rfft_plan_upload(N, C.cast(S.pTwiddleRFFT, C.c_void_p))
+    if rc:
+        raise RuntimeError(f"rfft_plan_upload({N}) -> {rc}: {last_error()}")
+
+
+def cfft_device(kind, N, dptr, n_frames, ifft=0, bitrev=1, stream=0):
+    rc = getattr(cuda(), f"cmsisdsp_cuda_cfft_{kind}")(dptr, N, n_frames, int(ifft), int(bitrev), stream)
+    if rc:
+        raise RuntimeError(f"cmsisdsp_cuda_cfft_{kind} -> {rc}: {last_error()}")
+
+
+def rfft_device(N, d_in, d_out, n_frames, ifft=0, stream=0):
+    rc = cuda().cmsisdsp_cuda_rfft_fast_f32(d_in, d_out, N, n_frames, int(ifft), stream)
+    if rc:
+        raise RuntimeError(f"cmsisdsp_cuda_rfft_fast_f32 -> {rc}: {last_error()}")
+
+
+def kernel_info(op, N):
+    v = [C.c_int(0) for _ in range(5)]
+    rc = cuda().cmsisdsp_cuda_kernel_info(op, N, *[C.byref(x) for x in v])
+    if rc:
+        raise RuntimeError(f"kernel_info -> {rc}: {last_error()}")
+    return dict(zip(("threads_per_cta", "frames_per_cta", "smem_bytes", "regs_per_thread", "ctas_per_sm"), [x.value for x in v]))
+
+
+def shard_frames(n_frames, world_size, rank):
+    """Contiguous block partition of the frame range over ranks:
+    rank g owns frames [g*ceil(B/G), min(B, (g+1)*ceil(B/G)))."""
+    per = -(-n_frames // world_size)
+    lo = min(n_frames, rank * per)
+    hi = min(n_frames, lo + per)
+    return lo, hi

@@ -1,0 +1,99 @@
+/*
+ * cmsisdsp_cuda.h -- C ABI of libcmsisdsp_cuda.so, the thin CUDA shim under the CMSIS-DSP
+ * front library (libcmsisdsp_b200.so).  Plain pointers and sizes only; no CUDA, C++ or
+ * torch types appear in any signature, so it can be bound from C, ctypes, cgo, JNI ...
+ *
+ * Every entry point works on the CURRENT device of the calling thread
+ * (cmsisdsp_cuda_set_device) and enqueues on the given stream (NULL = default stream,
+ * otherwise a cudaStream_t / CUstream handle cast to void*).  Transform entry points take
+ * DEVICE pointers; frames are contiguous.  There is no CPU fallback: without a CUDA device
+ * every call fails with CMSISDSP_CUDA_ERR_NO_DEVICE.
+ *
+ * What each entry point replaces in the reference (paths relative to the CMSIS-DSP tree):
+ *   cmsisdsp_cuda_cfft_f32        Source/TransformFunctions/arm_cfft_f32.c:1243-1298 (+ arm_cfft_radix8_f32.c:51-291,
+ *                                 arm_bitreversal2.c:84-108), looped over nFrames frames
+ *   cmsisdsp_cuda_cfft_q31        Source/TransformFunctions/arm_cfft_q31.c:704-755 (+ arm_cfft_radix4_q31.c:153-834)
+ *   cmsisdsp_cuda_cfft_q15        Source/TransformFunctions/arm_cfft_q15.c:671-722 (+ arm_cfft_radix4_q15.c:572-970,1434-1813)
+ *   cmsisdsp_cuda_rfft_fast_f32   Source/TransformFunctions/arm_rfft_fast_f32.c:675-699 (+ :316-462)
+ *   cmsisdsp_cuda_plan_upload     the residency of Source/CommonTables/arm_common_tables.c twiddle / bit-reversal
+ *                                 tables (:8523-26700) reached through arm_cfft_instance_* (transform_functions.h:282-424)
+ *   cmsisdsp_cuda_rfft_plan_upload  twiddleCoef_rfft_N (arm_common_tables.c:30820-34940) via arm_rfft_fast_instance_f32
+ */
+#ifndef CMSISDSP_CUDA_H
+#define CMSISDSP_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    CMSISDSP_CUDA_F32 = 0,
+    CMSISDSP_CUDA_Q31 = 1,
+    CMSISDSP_CUDA_Q15 = 2
+};
+
+enum {
+    CMSISDSP_CUDA_OK = 0,
+    CMSISDSP_CUDA_ERR_ARGUMENT = -1,      /* unsupported length / type / null pointer */
+    CMSISDSP_CUDA_ERR_NO_PLAN = -2,       /* tables for (type, length) not uploaded on this device */
+    CMSISDSP_CUDA_ERR_NO_DEVICE = -3,     /* no usable CUDA device */
+    CMSISDSP_CUDA_ERR_RUNTIME = -4        /* a CUDA runtime call failed; see cmsisdsp_cuda_last_error() */
+};
+
+/* ---- device / memory / stream plumbing for pure-C callers ---- */
+int  cmsisdsp_cuda_device_count(void);
+int  cmsisdsp_cuda_set_device(int device);
+int  cmsisdsp_cuda_get_device(void);
+int  cmsisdsp_cuda_malloc(void **devPtr, size_t bytes);
+int  cmsisdsp_cuda_free(void *devPtr);
+int  cmsisdsp_cuda_host_alloc(void **hostPtr, size_t bytes);          /* pinned host memory */
+int  cmsisdsp_cuda_host_free(void *hostPtr);
+int  cmsisdsp_cuda_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream);
+int  cmsisdsp_cuda_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream);
+int  cmsisdsp_cuda_stream_create(void **stream);
+int  cmsisdsp_cuda_stream_destroy(void *stream);
+int  cmsisdsp_cuda_stream_synchronize(void *stream);
+/* 1 if ptr is device (or managed) memory usable by kernels on the current device, 0 if host, <0 on error */
+int  cmsisdsp_cuda_is_device_pointer(const void *ptr);
+/* CUDA-event timing on `stream`: begin/end return an opaque timer; elapsed in milliseconds */
+int  cmsisdsp_cuda_timer_begin(void **timer, void *stream);
+int  cmsisdsp_cuda_timer_end(void *timer, void *stream, float *elapsedMs);
+
+/* ---- plans: device-resident tables, keyed by (device, type, fftLen) ---- */
+/* pTwiddle: f32 -> 2*fftLen floats (cos,+sin); q31/q15 -> 3*fftLen/2 values (3N/4 pairs).
+ * pBitRevTable/bitRevLength: the ordered swap list of the instance struct; it is expanded to the
+ * output permutation used when bitReverseFlag == 0.  Idempotent. */
+int  cmsisdsp_cuda_plan_upload(int type, uint32_t fftLen, const void *pTwiddle,
+                               const uint16_t *pBitRevTable, uint16_t bitRevLength);
+/* pTwiddleRFFT: fftLenReal floats = fftLenReal/2 (sin,cos) pairs; needs the f32 plan of fftLenReal/2 too */
+int  cmsisdsp_cuda_rfft_plan_upload(uint32_t fftLenReal, const float *pTwiddleRFFT);
+int  cmsisdsp_cuda_plan_ready(int type, uint32_t fftLen);              /* 1 / 0 */
+int  cmsisdsp_cuda_rfft_plan_ready(uint32_t fftLenReal);
+
+/* ---- transforms on device-resident batches (in place for cfft) ---- */
+int  cmsisdsp_cuda_cfft_f32(void *d_p, uint32_t fftLen, uint64_t nFrames,
+                            uint8_t ifftFlag, uint8_t bitReverseFlag, void *stream);
+int  cmsisdsp_cuda_cfft_q31(void *d_p, uint32_t fftLen, uint64_t nFrames,
+                            uint8_t ifftFlag, uint8_t bitReverseFlag, void *stream);
+int  cmsisdsp_cuda_cfft_q15(void *d_p, uint32_t fftLen, uint64_t nFrames,
+                            uint8_t ifftFlag, uint8_t bitReverseFlag, void *stream);
+/* d_p: nFrames*fftLenReal floats, left untouched (the reference clobbers it);
+ * d_out: nFrames*fftLenReal floats, packed {DC, Nyquist, Re1, Im1, ...}.  d_p and d_out must not alias. */
+int  cmsisdsp_cuda_rfft_fast_f32(const void *d_p, void *d_out, uint32_t fftLenReal, uint64_t nFrames,
+                                 uint8_t ifftFlag, void *stream);
+
+/* ---- diagnostics ---- */
+const char *cmsisdsp_cuda_last_error(void);        /* thread-local, never NULL */
+uint64_t    cmsisdsp_cuda_launch_count(void);      /* kernels launched by this library so far */
+/* static facts about the kernel chosen for (op, fftLen): op 0 cfft_f32, 1 cfft_q31, 2 cfft_q15,
+ * 3 rfft forward, 4 rfft inverse (fftLen = real length for 3/4).  Any out pointer may be NULL. */
+int  cmsisdsp_cuda_kernel_info(int op, uint32_t fftLen, int *threadsPerCta, int *framesPerCta,
+                               int *smemBytes, int *regsPerThread, int *ctasPerSm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,131 @@
+/*
+ * dsp/transform_functions.h -- the FFT-path slice of the CMSIS-DSP transform API, B200 build.
+ *
+ * Instance structs, init and exec prototypes are those of the reference's generic
+ * (non-Neon, non-MVE) branch, field for field and argument for argument
+ * (Include/dsp/transform_functions.h:282-331 q15, :347-394 q31, :410-460 f32, :813-849 rfft_fast),
+ * so existing callers re-link without source changes.  The `*_batch_*` functions at the end
+ * are the B200 extension: the same transform over nFrames contiguous frames in one call.
+ *
+ * Execution model: the exec functions run on the current CUDA device through
+ * libcmsisdsp_cuda (include/cmsisdsp_cuda.h).  Data pointers may be host pointers (the
+ * call stages them through device memory and returns when the result is back in the
+ * buffer) or device pointers (the call enqueues on the library's stream and returns after
+ * completion).  There is no CPU fallback: without a CUDA device the batched functions
+ * return ARM_MATH_ARGUMENT_ERROR and the legacy void functions latch the error in
+ * arm_cuda_last_status().
+ */
+#ifndef TRANSFORM_FUNCTIONS_H_
+#define TRANSFORM_FUNCTIONS_H_
+
+#include "arm_math_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------- q15 CFFT */
+typedef struct
+{
+          uint16_t  fftLen;          /* length of the FFT */
+    const q15_t    *pTwiddle;        /* points to the twiddle factor table */
+    const uint16_t *pBitRevTable;    /* points to the bit reversal table */
+          uint16_t  bitRevLength;    /* bit reversal table length */
+} arm_cfft_instance_q15;
+
+arm_status arm_cfft_init_4096_q15(arm_cfft_instance_q15 *S);
+arm_status arm_cfft_init_2048_q15(arm_cfft_instance_q15 *S);
+arm_status arm_cfft_init_1024_q15(arm_cfft_instance_q15 *S);
+arm_status arm_cfft_init_512_q15(arm_cfft_instance_q15 *S);
+arm_status arm_cfft_init_256_q15(arm_cfft_instance_q15 *S);
+arm_status arm_cfft_init_128_q15(arm_cfft_instance_q15 *S);
+arm_status arm_cfft_init_64_q15(arm_cfft_instance_q15 *S);
+arm_status arm_cfft_init_32_q15(arm_cfft_instance_q15 *S);
+arm_status arm_cfft_init_16_q15(arm_cfft_instance_q15 *S);
+arm_status arm_cfft_init_q15(arm_cfft_instance_q15 *S, uint16_t fftLen);
+void arm_cfft_q15(const arm_cfft_instance_q15 *S, q15_t *p1, uint8_t ifftFlag, uint8_t bitReverseFlag);
+
+/* ---------------------------------------------------------------- q31 CFFT */
+typedef struct
+{
+          uint16_t  fftLen;
+    const q31_t    *pTwiddle;
+    const uint16_t *pBitRevTable;
+          uint16_t  bitRevLength;
+} arm_cfft_instance_q31;
+
+arm_status arm_cfft_init_4096_q31(arm_cfft_instance_q31 *S);
+arm_status arm_cfft_init_2048_q31(arm_cfft_instance_q31 *S);
+arm_status arm_cfft_init_1024_q31(arm_cfft_instance_q31 *S);
+arm_status arm_cfft_init_512_q31(arm_cfft_instance_q31 *S);
+arm_status arm_cfft_init_256_q31(arm_cfft_instance_q31 *S);
+arm_status arm_cfft_init_128_q31(arm_cfft_instance_q31 *S);
+arm_status arm_cfft_init_64_q31(arm_cfft_instance_q31 *S);
+arm_status arm_cfft_init_32_q31(arm_cfft_instance_q31 *S);
+arm_status arm_cfft_init_16_q31(arm_cfft_instance_q31 *S);
+arm_status arm_cfft_init_q31(arm_cfft_instance_q31 *S, uint16_t fftLen);
+void arm_cfft_q31(const arm_cfft_instance_q31 *S, q31_t *p1, uint8_t ifftFlag, uint8_t bitReverseFlag);
+
+/* ---------------------------------------------------------------- f32 CFFT */
+typedef struct
+{
+          uint16_t   fftLen;
+    const float32_t *pTwiddle;
+    const uint16_t  *pBitRevTable;
+          uint16_t   bitRevLength;
+} arm_cfft_instance_f32;
+
+arm_status arm_cfft_init_4096_f32(arm_cfft_instance_f32 *S);
+arm_status arm_cfft_init_2048_f32(arm_cfft_instance_f32 *S);
+arm_status arm_cfft_init_1024_f32(arm_cfft_instance_f32 *S);
+arm_status arm_cfft_init_512_f32(arm_cfft_instance_f32 *S);
+arm_status arm_cfft_init_256_f32(arm_cfft_instance_f32 *S);
+arm_status arm_cfft_init_128_f32(arm_cfft_instance_f32 *S);
+arm_status arm_cfft_init_64_f32(arm_cfft_instance_f32 *S);
+arm_status arm_cfft_init_32_f32(arm_cfft_instance_f32 *S);
+arm_status arm_cfft_init_16_f32(arm_cfft_instance_f32 *S);
+arm_status arm_cfft_init_f32(arm_cfft_instance_f32 *S, uint16_t fftLen);
+void arm_cfft_f32(const arm_cfft_instance_f32 *S, float32_t *p1, uint8_t ifftFlag, uint8_t bitReverseFlag);
+
+/* ---------------------------------------------------------------- f32 fast RFFT */
+typedef struct
+{
+          arm_cfft_instance_f32 Sint;     /* internal CFFT structure (length fftLenRFFT/2) */
+          uint16_t   fftLenRFFT;          /* length of the real sequence */
+    const float32_t *pTwiddleRFFT;        /* twiddle factors of the real stage */
+} arm_rfft_fast_instance_f32;
+
+arm_status arm_rfft_fast_init_32_f32(arm_rfft_fast_instance_f32 *S);
+arm_status arm_rfft_fast_init_64_f32(arm_rfft_fast_instance_f32 *S);
+arm_status arm_rfft_fast_init_128_f32(arm_rfft_fast_instance_f32 *S);
+arm_status arm_rfft_fast_init_256_f32(arm_rfft_fast_instance_f32 *S);
+arm_status arm_rfft_fast_init_512_f32(arm_rfft_fast_instance_f32 *S);
+arm_status arm_rfft_fast_init_1024_f32(arm_rfft_fast_instance_f32 *S);
+arm_status arm_rfft_fast_init_2048_f32(arm_rfft_fast_instance_f32 *S);
+arm_status arm_rfft_fast_init_4096_f32(arm_rfft_fast_instance_f32 *S);
+arm_status arm_rfft_fast_init_f32(arm_rfft_fast_instance_f32 *S, uint16_t fftLen);
+void arm_rfft_fast_f32(const arm_rfft_fast_instance_f32 *S, float32_t *p, float32_t *pOut, uint8_t ifftFlag);
+
+/* ---------------------------------------------------------------- B200 extension: batches
+ *
+ * nFrames frames stored back to back (frame stride 2*fftLen scalars for CFFT, fftLenRFFT
+ * floats for RFFT), transformed exactly as nFrames calls of the single-frame function.
+ * Returns ARM_MATH_SUCCESS, or ARM_MATH_ARGUMENT_ERROR for a NULL / unsupported instance
+ * or a CUDA failure (text in cmsisdsp_cuda_last_error()).
+ * arm_rfft_fast_batch_f32 leaves p untouched in both directions (the single-frame forward
+ * call keeps the reference's documented side effect: p then holds the N/2-point CFFT). */
+arm_status arm_cfft_batch_f32(const arm_cfft_instance_f32 *S, float32_t *p, uint32_t nFrames,
+                              uint8_t ifftFlag, uint8_t bitReverseFlag);
+arm_status arm_cfft_batch_q31(const arm_cfft_instance_q31 *S, q31_t *p, uint32_t nFrames,
+                              uint8_t ifftFlag, uint8_t bitReverseFlag);
+arm_status arm_cfft_batch_q15(const arm_cfft_instance_q15 *S, q15_t *p, uint32_t nFrames,
+                              uint8_t ifftFlag, uint8_t bitReverseFlag);
+arm_status arm_rfft_fast_batch_f32(const arm_rfft_fast_instance_f32 *S, float32_t *p, float32_t *pOut,
+                                   uint32_t nFrames, uint8_t ifftFlag);
+/* status of the most recent legacy (void) exec call on this thread */
+arm_status arm_cuda_last_status(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRANSFORM_FUNCTIONS_H_ */

@@ -1,0 +1,206 @@
+/*
+ * tests/emu/emu.cpp -- CPU emulator of the CUDA kernel bodies (TEST INFRASTRUCTURE).
+ *
+ * Compiles the very same plan / pass / body templates the kernels are built from
+ * (cmsis-dsp_b200/csrc/cuda/fft_*.cuh) with g++, and executes a CTA as "for each phase,
+ * for each thread", which is exactly what __syncthreads() between phases guarantees on
+ * the device.  It lets the non-GPU test-suite check index math and the bit-exact
+ * fixed-point arithmetic against the oracle, and it records every shared-memory access
+ * so the bank-conflict degree of each exchange can be asserted without a GPU.
+ *
+ * It is not a fallback: nothing in the product links it.
+ */
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <vector>
+
+struct TraceRec { int phase, seq, tid, off, bytes, st; };
+static bool g_trace_on = false;
+static std::vector<TraceRec> g_trace;
+static const char *g_cta_base = nullptr;
+static int g_cur_phase = 0, g_cur_tid = 0, g_cur_seq = 0;
+
+#define FFT_TRACE_SMEM(ptr, bytes, is_store)                                                                  \
+    do {                                                                                                      \
+        if (g_trace_on)                                                                                       \
+            g_trace.push_back({g_cur_phase, g_cur_seq++, g_cur_tid, (int)((const char *)(ptr) - g_cta_base), \
+                               (bytes), (is_store)});                                                         \
+    } while (0)
+
+#include "fft_plans.cuh"
+
+using namespace b200fft;
+
+template <class BODY, int PH> struct PhaseRunner {
+    template <class ARGS, class ELEM>
+    static void run(std::vector<typename BODY::Regs> &regs, const ARGS *args, ELEM *smem, int T, int F, int frameElems,
+                    const bool *valid)
+    {
+        g_cur_phase = PH;
+        for (int tid = 0; tid < T * F; tid++) {
+            int fl = tid / T, i = tid % T;
+            g_cur_tid = tid;
+            g_cur_seq = 0;
+            if (!valid[fl]) continue;
+            BODY::template phase<PH>(regs[tid], args[fl], smem + (size_t)fl * frameElems, i);
+        }
+        if (PH + 1 < BODY::kPhases) PhaseRunner<BODY, (PH + 1 < BODY::kPhases ? PH + 1 : PH)>::run(regs, args, smem, T, F, frameElems, valid);
+    }
+};
+
+/* run one CTA worth of frames [f0, f0+F) */
+template <class PL, class BODY, class MAKEARGS>
+static void run_batch(uint64_t nFrames, MAKEARGS make)
+{
+    typedef typename BODY::elem elem;
+    constexpr int T = PL::T, F = PL::F;
+    std::vector<elem> smem((size_t)F * PL::kFrameElems + 16);
+    std::vector<typename BODY::Regs> regs((size_t)T * F);
+    std::vector<typename BODY::Args> args(F);
+    bool valid[F];
+    for (uint64_t f0 = 0; f0 < nFrames; f0 += F) {
+        for (int fl = 0; fl < F; fl++) {
+            valid[fl] = (f0 + fl) < nFrames;
+            if (valid[fl]) args[fl] = make(f0 + fl);
+        }
+        g_cta_base = (const char *)smem.data();
+        PhaseRunner<BODY, 0>::run(regs, args.data(), smem.data(), T, F, PL::kFrameElems, valid);
+        if (g_trace_on && f0 == 0) g_trace_on = false;   /* trace only the first CTA */
+    }
+}
+
+template <class AR, class PL, bool INV>
+static void cfft_run(typename AR::elem *data, uint64_t nFrames, const void *tw, const uint16_t *perm, int shl1)
+{
+    typedef CfftBody<PL, INV> BODY;
+    typedef typename AR::elem elem;
+    run_batch<PL, BODY>(nFrames, [&](uint64_t f) {
+        typename BODY::Args a;
+        a.in = data + f * PL::N;
+        a.out = data + f * PL::N;
+        a.tw = (const elem *)tw;
+        a.perm = perm;
+        a.scale = 1.0f / (float)PL::N;
+        a.shl1 = shl1;
+        return a;
+    });
+}
+
+template <int N> static void cfft_f32_n(float *d, uint64_t n, int inv, const void *tw, const uint16_t *perm)
+{
+    typedef typename PlanCfftF32<N>::type PL;
+    if (inv) cfft_run<ArithF32, PL, true>((cf32 *)d, n, tw, perm, 0);
+    else cfft_run<ArithF32, PL, false>((cf32 *)d, n, tw, perm, 0);
+}
+template <class AR, int N> static void cfft_fix_n(void *d, uint64_t n, int inv, const void *tw, const uint16_t *perm)
+{
+    typedef typename PlanCfftFix<AR, N>::type PL;
+    const int lg = __builtin_ctz(N), shl1 = lg & 1;
+    if (inv) cfft_run<AR, PL, true>((typename AR::elem *)d, n, tw, perm, shl1);
+    else cfft_run<AR, PL, false>((typename AR::elem *)d, n, tw, perm, shl1);
+}
+
+#define FOR_ALL_N(X) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096)
+#define FOR_RFFT_NC(X) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048)
+
+extern "C" {
+
+int emu_cfft(int type, uint32_t N, void *data, uint64_t nFrames, int ifft, int bitrev, const void *tw, const uint16_t *perm)
+{
+    const uint16_t *pp = bitrev ? nullptr : perm;
+    int inv = (ifft == 1);
+    switch (N) {
+#define CASE(n)                                                                      \
+    case n:                                                                          \
+        if (type == 0) cfft_f32_n<n>((float *)data, nFrames, inv, tw, pp);          \
+        else if (type == 1) cfft_fix_n<ArithQ31, n>(data, nFrames, inv, tw, pp);    \
+        else cfft_fix_n<ArithQ15, n>(data, nFrames, inv, tw, pp);                   \
+        return 0;
+        FOR_ALL_N(CASE)
+#undef CASE
+    default: return -1;
+    }
+}
+
+int emu_rfft(uint32_t Nreal, const float *in, float *out, uint64_t nFrames, int ifft, const void *tw, const void *twr)
+{
+    switch (Nreal / 2) {
+#define CASE(nc)                                                                                     \
+    case nc: {                                                                                       \
+        if (!ifft) {                                                                                 \
+            typedef PlanRfftFwd<nc>::type PL;                                                        \
+            typedef RfftFwdBody<PL> BODY;                                                            \
+            run_batch<PL, BODY>(nFrames, [&](uint64_t f) {                                           \
+                BODY::Args a;                                                                        \
+                a.in = (const cf32 *)in + f * nc; a.out = (cf32 *)out + f * nc;                      \
+                a.tw = (const cf32 *)tw; a.twr = (const cf32 *)twr;                                  \
+                return a;                                                                            \
+            });                                                                                      \
+        } else {                                                                                     \
+            typedef PlanRfftInv<nc>::type PL;                                                        \
+            typedef RfftInvBody<PL> BODY;                                                            \
+            run_batch<PL, BODY>(nFrames, [&](uint64_t f) {                                           \
+                BODY::Args a;                                                                        \
+                a.in = (const cf32 *)in + f * nc; a.out = (cf32 *)out + f * nc;                      \
+                a.tw = (const cf32 *)tw; a.twr = (const cf32 *)twr; a.scale = 1.0f / (float)nc;      \
+                return a;                                                                            \
+            });                                                                                      \
+        }                                                                                            \
+        return 0;                                                                                    \
+    }
+        FOR_RFFT_NC(CASE)
+#undef CASE
+    default: return -1;
+    }
+}
+
+void emu_trace_begin(void) { g_trace.clear(); g_trace_on = true; }
+
+/* Per (phase, is_store): number of warp-level requests and the shared-memory wavefronts they
+ * need (32 banks x 4 B; a request of 8 B/lane is served per half-warp, 16 B/lane per quarter
+ * warp).  out rows: phase, is_store, bytes, requests, ideal_wavefronts, wavefronts. Returns rows. */
+int emu_trace_stats(int64_t *out, int maxRows)
+{
+    struct Key { int phase, st, bytes; bool operator<(const Key &o) const { return phase != o.phase ? phase < o.phase : (st != o.st ? st < o.st : bytes < o.bytes); } };
+    std::map<Key, std::map<std::pair<int, int>, std::vector<TraceRec>>> groups;   /* key -> (warp, seq) -> lanes */
+    for (const TraceRec &r : g_trace) groups[{r.phase, r.st, r.bytes}][{r.tid / 32, r.seq}].push_back(r);
+    int row = 0;
+    for (auto &kv : groups) {
+        int64_t req = 0, ideal = 0, wf = 0;
+        const int lanesPerPhase = kv.first.bytes <= 4 ? 32 : (kv.first.bytes == 8 ? 16 : 8);
+        for (auto &g : kv.second) {
+            req++;
+            for (int ph = 0; ph < 32 / lanesPerPhase; ph++) {
+                std::map<int, std::vector<int>> bankWords;
+                bool any = false;
+                for (const TraceRec &r : g.second) {
+                    int lane = r.tid % 32;
+                    if (lane / lanesPerPhase != ph) continue;
+                    any = true;
+                    for (int b = 0; b < r.bytes; b += 4) {
+                        int word = (r.off + b) / 4;
+                        auto &v = bankWords[word % 32];
+                        bool seen = false;
+                        for (int w : v) seen |= (w == word);
+                        if (!seen) v.push_back(word);
+                    }
+                }
+                if (!any) continue;
+                int mx = 1;
+                for (auto &bw : bankWords) mx = std::max(mx, (int)bw.second.size());
+                ideal += 1;
+                wf += mx;
+            }
+        }
+        if (row < maxRows) {
+            int64_t *o = out + 6 * row;
+            o[0] = kv.first.phase; o[1] = kv.first.st; o[2] = kv.first.bytes; o[3] = req; o[4] = ideal; o[5] = wf;
+        }
+        row++;
+    }
+    return row;
+}
+
+}  /* extern "C" */

@@ -1,0 +1,99 @@
+"""The kernel bodies, compiled for the CPU (tests/emu/emu.cpp runs the very same
+fft_*.cuh templates phase by phase), against the oracle: index math, twiddle indexing and
+the bit-exact fixed-point arithmetic are checked here without a GPU.  Also asserts the
+bank-conflict degree of every shared-memory exchange from the emulator's access trace."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import cmsisdsp_b200 as cd
+from oracle_lib import LENGTHS, RLENGTHS, oracle, perm_from_swaps
+from seeded_inputs import cfft_input, rfft_input
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU_DIR = os.path.join(ROOT, "tests", "emu")
+CSRC = os.path.join(ROOT, "cmsis-dsp_b200", "csrc", "cuda")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    so = os.path.join(EMU_DIR, "libemu.so")
+    deps = [os.path.join(EMU_DIR, "emu.cpp")] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas",
+                               "-I", CSRC, os.path.join(EMU_DIR, "emu.cpp"), "-o", so])
+    L = C.CDLL(so)
+    L.emu_cfft.argtypes = [C.c_int, C.c_uint32, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.emu_rfft.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
+    L.emu_trace_stats.argtypes = [C.c_void_p, C.c_int]
+    return L
+
+
+def relrms(a, b):
+    a, b = a.astype(np.float64), b.astype(np.float64)
+    return float(np.sqrt(((a - b) ** 2).sum() / (b ** 2).sum()))
+
+
+def product_tables(kind, N):
+    """twiddles + permutation exactly as the front library would upload them"""
+    tw, br = cd.instance_tables(cd.cfft_instance(kind, N), kind)
+    return tw, perm_from_swaps(N, br).astype(np.uint16)
+
+
+@pytest.mark.parametrize("kind", ["f32", "q31", "q15"])
+@pytest.mark.parametrize("N", LENGTHS)
+def test_cfft_bodies(emu, kind, N):
+    tw, perm = product_tables(kind, N)
+    frames = 2 * {16: 128, 32: 64, 64: 32, 128: 16, 256: 8, 512: 4, 1024: 2}.get(N, 1) + 3   # ragged last CTA
+    x = cfft_input(kind, N, frames=max(frames, 6), seed=N)
+    for ifft in (0, 1):
+        for bitrev in (0, 1):
+            want = oracle().cfft(kind, N, x, ifft, bitrev)
+            got = x.copy()
+            assert emu.emu_cfft(cd.TYPE_ID[kind], N, got.ctypes.data, got.shape[0], ifft, bitrev, tw.ctypes.data, perm.ctypes.data) == 0
+            if kind == "f32":
+                assert relrms(got, want) <= 2e-6, (N, ifft, bitrev)       # north_star tolerance
+                for f in range(got.shape[0]):
+                    assert relrms(got[f], want[f]) <= 2e-6
+            else:
+                assert np.array_equal(got, want), (kind, N, ifft, bitrev)  # bit-exact
+
+
+@pytest.mark.parametrize("N", RLENGTHS)
+def test_rfft_bodies(emu, N):
+    tw, _ = cd.instance_tables(cd.cfft_instance("f32", N // 2), "f32")
+    S = cd.rfft_instance(N)
+    twr = np.ctypeslib.as_array(S.pTwiddleRFFT, shape=(N,)).copy()
+    x = rfft_input(N, frames=67, seed=N)
+    for ifft in (0, 1):
+        want = oracle().rfft(N, x, ifft)
+        got = np.zeros_like(x)
+        xin = x.copy()
+        assert emu.emu_rfft(N, xin.ctypes.data, got.ctypes.data, x.shape[0], ifft, tw.ctypes.data, twr.ctypes.data) == 0
+        assert np.array_equal(xin, x)                       # input left untouched
+        assert relrms(got, want) <= 2e-6, (N, ifft)
+
+
+def _trace(emu, run):
+    emu.emu_trace_begin()
+    run()
+    buf = np.zeros((64, 6), dtype=np.int64)
+    n = emu.emu_trace_stats(buf.ctypes.data, 64)
+    return buf[:n]
+
+
+@pytest.mark.parametrize("kind,limit", [("f32", 1.0), ("q31", 1.0), ("q15", 2.0)])
+@pytest.mark.parametrize("N", [256, 512, 1024, 2048, 4096])
+def test_exchange_bank_conflicts(emu, kind, N, limit):
+    """wavefronts / ideal wavefronts of every exchange load/store.  f32 and q31 (8-byte
+    elements, pad 1 per 16) must be conflict-free for N >= 256; q15 (4-byte elements)
+    currently tolerates 2-way conflicts on one exchange."""
+    tw, _ = product_tables(kind, N)
+    y = np.zeros((8, 2 * N), dtype=cd.NP_DTYPE[kind])
+    rows = _trace(emu, lambda: emu.emu_cfft(cd.TYPE_ID[kind], N, y.ctypes.data, 8, 0, 1, tw.ctypes.data, None))
+    assert len(rows) > 0
+    for ph, st, nbytes, req, ideal, wf in rows:
+        assert wf <= limit * ideal, (kind, N, int(ph), "store" if st else "load", wf / ideal)

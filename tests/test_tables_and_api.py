@@ -1,0 +1,102 @@
+"""CPU-side checks of the product's C front library (no GPU needed):
+tables value-identical to the reference / oracle, struct layouts, init contract, and that
+both shared objects export every symbol their public headers declare."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import cmsisdsp_b200 as cd
+from oracle_lib import LENGTHS, RLENGTHS, oracle, ref
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def bits(a):
+    a = np.ascontiguousarray(a)
+    return a.view({4: np.uint32, 2: np.uint16}[a.dtype.itemsize])
+
+
+@pytest.mark.parametrize("N", LENGTHS)
+def test_generated_tables_match_oracle_and_reference(N):
+    checkers = [oracle()] + ([ref()] if ref() is not None else [])
+    for kind, which in (("f32", "f32"), ("q31", "fixed"), ("q15", "fixed")):
+        for S in (cd.cfft_instance(kind, N), cd.preset(kind, N)):
+            tw, br = cd.instance_tables(S, kind)
+            for chk in checkers:
+                assert np.array_equal(bits(tw), bits(chk.table(f"twiddle_{kind}", N))), (kind, N)
+                assert np.array_equal(br, chk.bitrev(which, N)), (kind, N)
+    if N >= 32:
+        for S in (cd.rfft_instance(N), cd.rfft_preset(N)):
+            assert S.fftLenRFFT == N and S.Sint.fftLen == N // 2
+            twr = np.ctypeslib.as_array(S.pTwiddleRFFT, shape=(N,)).copy()
+            for chk in checkers:
+                assert np.array_equal(bits(twr), bits(chk.table("twiddle_rfft_f32", N)))
+
+
+def test_struct_layouts_match_reference():
+    # 32 / 32 / 32 / 48 bytes on LP64
+    assert C.sizeof(cd.arm_cfft_instance_f32) == 32
+    assert C.sizeof(cd.arm_cfft_instance_q31) == 32
+    assert C.sizeof(cd.arm_cfft_instance_q15) == 32
+    assert C.sizeof(cd.arm_rfft_fast_instance_f32) == 48
+    if ref() is not None:
+        L = ref().lib
+        for name, t in (("cfft_instance_f32", cd.arm_cfft_instance_f32), ("cfft_instance_q31", cd.arm_cfft_instance_q31),
+                        ("cfft_instance_q15", cd.arm_cfft_instance_q15), ("rfft_fast_instance_f32", cd.arm_rfft_fast_instance_f32)):
+            fn = getattr(L, f"ref_sizeof_{name}")
+            fn.restype = C.c_uint32
+            assert fn() == C.sizeof(t)
+
+
+def test_init_contract():
+    L = cd.lib()
+    for kind, inst in cd.CFFT_INSTANCE.items():
+        S = inst()
+        for bad in (0, 8, 24, 100, 8192, 4095):
+            assert getattr(L, f"arm_cfft_init_{kind}")(C.byref(S), bad) == cd.ARM_MATH_ARGUMENT_ERROR
+        for N in LENGTHS:
+            assert getattr(L, f"arm_cfft_init_{kind}")(C.byref(S), N) == cd.ARM_MATH_SUCCESS
+            assert S.fftLen == N
+            S2 = inst()
+            assert getattr(L, f"arm_cfft_init_{N}_{kind}")(C.byref(S2)) == cd.ARM_MATH_SUCCESS
+            assert bytes(S) == bytes(S2)
+    R = cd.arm_rfft_fast_instance_f32()
+    for bad in (0, 16, 48, 8192):
+        assert L.arm_rfft_fast_init_f32(C.byref(R), bad) == cd.ARM_MATH_ARGUMENT_ERROR
+    # NULL instance -> argument error (arm_rfft_fast_init_f32.c:87)
+    assert L.arm_rfft_fast_init_1024_f32(None) == cd.ARM_MATH_ARGUMENT_ERROR
+    for N in RLENGTHS:
+        assert L.arm_rfft_fast_init_f32(C.byref(R), N) == cd.ARM_MATH_SUCCESS
+
+
+def _declared_functions(header):
+    src = open(header).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = set(re.findall(r"\b((?:arm|cmsisdsp_cuda)_[A-Za-z0-9_]+)\s*\(", src))
+    return {n for n in names if not n.isupper()}
+
+
+def test_shared_objects_export_every_declared_symbol():
+    cu = cd.cuda()
+    for name in _declared_functions(os.path.join(ROOT, "include", "cmsisdsp_cuda.h")):
+        assert hasattr(cu, name), name
+    fr = cd.lib()
+    names = _declared_functions(os.path.join(ROOT, "include", "dsp", "transform_functions.h"))
+    assert len(names) == 48      # 3x(9 per-length inits + init + exec) + rfft (8+1+1) + 4 batch + last_status
+    for name in names:
+        assert hasattr(fr, name), name
+    for N in LENGTHS:
+        for kind in ("f32", "q31", "q15"):
+            cd.preset(kind, N)
+
+
+def test_shard_partition():
+    for B in (0, 1, 7, 8, 65536, 1000003):
+        for G in (1, 2, 4, 8):
+            parts = [cd.shard_frames(B, G, r) for r in range(G)]
+            assert parts[0][0] == 0 and parts[-1][1] == B
+            for (a, b), (c, d) in zip(parts, parts[1:]):
+                assert b == c and a <= b and c <= d
