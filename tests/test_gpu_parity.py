@@ -1,0 +1,265 @@
+"""GPU parity tests (run with `-m gpu` on a B200): the CUDA path, called through the C ABI
+(libcmsisdsp_b200.so front library and libcmsisdsp_cuda.so shim), against the CPU oracle on
+the same seeded inputs, against the reference's golden vectors, and -- at BASELINE.json's
+full sizes -- through size-independent properties.
+
+Bar (BASELINE.json north_star): q15/q31 bit-exact; f32 relative RMS error <= 2e-6.
+"""
+import ctypes as C
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import cmsisdsp_b200 as cd
+from golden_checks import assert_like_reference, golden_cases, ref_digests
+from oracle_lib import LENGTHS, RLENGTHS, oracle
+from seeded_inputs import cfft_input, rfft_input
+
+pytestmark = pytest.mark.gpu
+F32_TOL = 2e-6          # relative RMS, north_star
+NT = min(32, os.cpu_count() or 1)
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def relrms(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.sqrt(((a - b) ** 2).sum() / (b ** 2).sum()))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def device():
+    cu = cd.cuda()
+    assert cu.cmsisdsp_cuda_device_count() >= 1, "no CUDA device: these tests must run on a GPU box"
+    assert cu.cmsisdsp_cuda_set_device(0) == 0
+    return cu
+
+
+# ------------------------------------------------------------------ every (type, N, direction, order)
+
+@pytest.mark.parametrize("kind", ["f32", "q31", "q15"])
+@pytest.mark.parametrize("N", LENGTHS)
+def test_cfft_all_modes_host_buffers(kind, N):
+    x = cfft_input(kind, N, frames=301, seed=N)          # ragged: not a multiple of any frames-per-CTA
+    for ifft in (0, 1):
+        for bitrev in (0, 1):
+            want = oracle().cfft(kind, N, x, ifft, bitrev, threads=NT)
+            got = cd.cfft_batch(kind, N, x, ifft, bitrev)
+            if kind == "f32":
+                assert relrms(got, want) <= F32_TOL, (N, ifft, bitrev)
+                per_frame = np.sqrt(((got.astype(np.float64) - want) ** 2).sum(1) / (want.astype(np.float64) ** 2).sum(1))
+                assert per_frame.max() <= F32_TOL, (N, ifft, bitrev, per_frame.max())
+            else:
+                assert np.array_equal(got, want), (kind, N, ifft, bitrev)
+
+
+@pytest.mark.parametrize("N", RLENGTHS)
+def test_rfft_both_directions(N):
+    x = rfft_input(N, frames=203, seed=N)
+    xin = x.copy()
+    spec = cd.rfft_batch(N, xin, 0)
+    assert np.array_equal(xin, x)                          # the batched call leaves p untouched
+    assert relrms(spec, oracle().rfft(N, x, 0, threads=NT)) <= F32_TOL
+    want_spec = oracle().rfft(N, x, 0, threads=NT)
+    back = cd.rfft_batch(N, want_spec, 1)
+    assert relrms(back, oracle().rfft(N, want_spec, 1, threads=NT)) <= F32_TOL
+    assert relrms(back, x) <= F32_TOL                      # round trip
+
+
+def test_digests_of_compiled_reference_fixed_point():
+    """bit-level pin against outputs of the compiled reference (tests/golden/ref_digests.json)"""
+    dig = ref_digests()
+    for kind in ("q31", "q15"):
+        for N in LENGTHS:
+            x = cfft_input(kind, N, frames=8, seed=N)
+            for ifft in (0, 1):
+                for bitrev in (0, 1):
+                    y = cd.cfft_batch(kind, N, x, ifft, bitrev)
+                    assert hashlib.sha256(y.tobytes()).hexdigest() == dig[f"cfft_{kind}/{N}/{ifft}/{bitrev}"], (kind, N, ifft, bitrev)
+
+
+# ------------------------------------------------------------------ the reference's own tests
+
+@pytest.mark.parametrize("kind", ["f32", "q31", "q15"])
+def test_reference_cfft_patterns(kind):
+    n = 0
+    for N, sig, ifft, x, ref in golden_cases(kind, "c"):
+        out = cd.cfft_batch(kind, N, x, ifft, 1).reshape(-1)
+        assert_like_reference(kind, "c", out, ref, N, ifft)
+        n += 1
+    assert n == 36
+
+
+def test_reference_rfft_patterns():
+    n = 0
+    for N, sig, ifft, x, ref in golden_cases("f32", "r"):
+        out = cd.rfft_batch(N, x, ifft).reshape(-1)
+        assert_like_reference("f32", "r", out, ref, N, ifft)
+        n += 1
+    assert n == 32
+
+
+def test_fft_bin_example_known_answer():
+    d = np.load(os.path.join(HERE, "golden", "fft_bin_example.npz"))
+    S = cd.preset("f32", 1024)                               # arm_cfft_sR_f32_len1024, as the example uses
+    buf = d["input"].copy()
+    cd.lib().arm_cfft_f32(C.byref(S), buf.ctypes.data, 0, 1)
+    assert cd.lib().arm_cuda_last_status() == 0
+    y = buf.reshape(-1, 2).astype(np.float64)
+    assert int(np.argmax(np.hypot(y[:, 0], y[:, 1]))) == 213
+
+
+# ------------------------------------------------------------------ API behaviour
+
+def test_legacy_single_frame_signatures():
+    L = cd.lib()
+    for kind in ("f32", "q31", "q15"):
+        x = cfft_input(kind, 256, frames=1, seed=5)
+        buf = x.copy()
+        S = cd.cfft_instance(kind, 256)
+        getattr(L, f"arm_cfft_{kind}")(C.byref(S), buf.ctypes.data, 0, 1)
+        assert L.arm_cuda_last_status() == 0
+        want = oracle().cfft(kind, 256, x, 0, 1)
+        assert relrms(buf, want) <= F32_TOL if kind == "f32" else np.array_equal(buf, want)
+    # rfft forward: pOut = spectrum AND p is left holding the N/2-point CFFT, like the reference
+    x = rfft_input(512, frames=1, seed=6)
+    p, out = x.copy(), np.zeros_like(x)
+    S = cd.rfft_instance(512)
+    L.arm_rfft_fast_f32(C.byref(S), p.ctypes.data, out.ctypes.data, 0)
+    assert L.arm_cuda_last_status() == 0
+    want_out, want_p = oracle().rfft(512, x, 0, return_clobbered=True)
+    assert relrms(out, want_out) <= F32_TOL and relrms(p, want_p) <= F32_TOL
+    # inverse: p untouched
+    p2, back = want_out.copy(), np.zeros_like(x)
+    L.arm_rfft_fast_f32(C.byref(S), p2.ctypes.data, back.ctypes.data, 1)
+    assert np.array_equal(p2, want_out) and relrms(back, x) <= F32_TOL
+
+
+def test_edge_cases():
+    L = cd.lib()
+    S = cd.cfft_instance("f32", 64)
+    x = cfft_input("f32", 64, frames=3, seed=1)
+    buf = x.copy()
+    assert L.arm_cfft_batch_f32(C.byref(S), buf.ctypes.data, 0, 0, 1) == 0          # empty batch: no-op
+    assert np.array_equal(buf, x)
+    assert L.arm_cfft_batch_f32(None, buf.ctypes.data, 3, 0, 1) == cd.ARM_MATH_ARGUMENT_ERROR
+    assert L.arm_cfft_batch_f32(C.byref(S), None, 3, 0, 1) == cd.ARM_MATH_ARGUMENT_ERROR
+    bad = cd.arm_cfft_instance_f32()
+    bad.fftLen, bad.pTwiddle, bad.pBitRevTable, bad.bitRevLength = 24, S.pTwiddle, S.pBitRevTable, S.bitRevLength
+    assert L.arm_cfft_batch_f32(C.byref(bad), buf.ctypes.data, 3, 0, 1) == cd.ARM_MATH_ARGUMENT_ERROR
+    L.arm_cfft_f32(C.byref(bad), buf.ctypes.data, 0, 1)                             # unsupported length: silent no-op
+    assert np.array_equal(buf, x)
+    R = cd.rfft_instance(64)
+    r = rfft_input(64, frames=2, seed=2)
+    assert L.arm_rfft_fast_batch_f32(C.byref(R), r.ctypes.data, r.ctypes.data, 2, 0) == cd.ARM_MATH_ARGUMENT_ERROR   # aliasing
+    for frames in (1, 2, 31, 33, 127, 129):                                          # every tail shape of the CTA packing
+        for kind, N in (("f32", 16), ("q15", 32), ("q31", 128), ("f32", 1024)):
+            xi = cfft_input(kind, N, frames=frames, seed=frames)
+            got, want = cd.cfft_batch(kind, N, xi), oracle().cfft(kind, N, xi)
+            assert relrms(got, want) <= F32_TOL if kind == "f32" else np.array_equal(got, want)
+
+
+def test_device_pointer_path_matches_host_path():
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda", 0)
+    for kind, N in (("f32", 1024), ("q31", 512), ("q15", 2048)):
+        x = cfft_input(kind, N, frames=77, seed=3)
+        cd.ensure_plans(kind, N)
+        t = torch.from_numpy(x).to(dev)
+        cd.cfft_device(kind, N, t.data_ptr(), 77, 0, 1, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(t.cpu().numpy(), cd.cfft_batch(kind, N, x, 0, 1))
+        # front library accepts device pointers too
+        t2 = torch.from_numpy(x).to(dev)
+        S = cd.cfft_instance(kind, N)
+        assert getattr(cd.lib(), f"arm_cfft_batch_{kind}")(C.byref(S), t2.data_ptr(), 77, 0, 1) == 0
+        assert np.array_equal(t2.cpu().numpy(), t.cpu().numpy())
+
+
+# ------------------------------------------------------------------ BASELINE.json full sizes
+
+def test_config1_cfft_f32_1024_x4096_full_compare():
+    x = cfft_input("f32", 1024, frames=4096, seed=1)
+    want = oracle().cfft("f32", 1024, x, 0, 1, threads=NT)
+    got = cd.cfft_batch("f32", 1024, x, 0, 1)
+    assert relrms(got, want) <= F32_TOL
+    per_frame = np.sqrt(((got.astype(np.float64) - want) ** 2).sum(1) / (want.astype(np.float64) ** 2).sum(1))
+    assert per_frame.max() <= F32_TOL
+
+
+def test_config2_rfft_4096_x65536_properties():
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda", 0)
+    N, B = 4096, 65536
+    cd.ensure_rfft_plans(N)
+    st = torch.cuda.current_stream().cuda_stream
+    x = torch.randn(B, N, device=dev, generator=torch.Generator(device=dev).manual_seed(7))
+    spec, y = torch.empty_like(x), torch.empty_like(x)
+    cd.rfft_device(N, x.data_ptr(), spec.data_ptr(), B, 0, st)
+    cd.rfft_device(N, spec.data_ptr(), y.data_ptr(), B, 1, st)
+    torch.cuda.synchronize()
+    rt = ((y - x).double().pow(2).sum() / x.double().pow(2).sum()).sqrt().item()
+    assert rt <= F32_TOL                                           # forward -> inverse round trip over the full batch
+    # Parseval on the packed spectrum: sum x^2 = (DC^2 + Nyq^2 + 2 sum |X_k|^2) / N
+    e_t = x.double().pow(2).sum(1)
+    s = spec.double()
+    e_f = (s[:, 0] ** 2 + s[:, 1] ** 2 + 2 * s[:, 2:].pow(2).sum(1)) / N
+    assert ((e_f - e_t).abs() / e_t).max().item() < 1e-5
+    # linearity: F(a + 2b) = F(a) + 2 F(b) on a slice
+    a, b = x[:256], x[256:512]
+    lin = torch.empty_like(a)
+    cd.rfft_device(N, (a + 2 * b).contiguous().data_ptr(), lin.data_ptr(), 256, 0, st)
+    torch.cuda.synchronize()
+    ref_lin = spec[:256] + 2 * spec[256:512]
+    assert ((lin - ref_lin).double().pow(2).sum() / ref_lin.double().pow(2).sum()).sqrt().item() <= 2 * F32_TOL
+    # oracle parity on a stratified subsample of 1024 frames
+    idx = torch.arange(0, B, B // 1024, device=dev)
+    xs = x[idx].cpu().numpy()
+    assert relrms(spec[idx].cpu().numpy(), oracle().rfft(N, xs, 0, threads=NT)) <= F32_TOL
+    assert relrms(y[idx].cpu().numpy(), oracle().rfft(N, spec[idx].cpu().numpy(), 1, threads=NT)) <= F32_TOL
+
+
+@pytest.mark.parametrize("kind", ["q15", "q31"])
+@pytest.mark.parametrize("N", [256, 1024, 4096])
+def test_config3_fixed_point_1M_frames_bit_exact(kind, N):
+    """2^20 frames built by tiling 4096 distinct seeded frames 256 times: the first tile must be
+    memcmp-identical to the oracle and every other tile identical to the first (frames are
+    independent, so this pins all 2^20 outputs bit for bit)."""
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda", 0)
+    B, U = 1 << 20, 4096
+    base = cfft_input(kind, N, frames=U, seed=100 + N)
+    cd.ensure_plans(kind, N)
+    st = torch.cuda.current_stream().cuda_stream
+    for ifft, bitrev in ((0, 1), (1, 1), (0, 0)):
+        want = oracle().cfft(kind, N, base, ifft, bitrev, threads=NT)
+        t = torch.from_numpy(base).to(dev).repeat(B // U, 1)
+        assert t.shape == (B, 2 * N)
+        cd.cfft_device(kind, N, t.data_ptr(), B, ifft, bitrev, st)
+        torch.cuda.synchronize()
+        tiles = t.view(B // U, U, 2 * N)
+        assert np.array_equal(tiles[0].cpu().numpy(), want), (kind, N, ifft, bitrev)
+        assert bool((tiles == tiles[0:1]).all().item()), (kind, N, ifft, bitrev)
+        del t, tiles
+        torch.cuda.empty_cache()
+
+
+def test_config5_length_sweep_f32_large_batches():
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda", 0)
+    st = torch.cuda.current_stream().cuda_stream
+    for N in LENGTHS:
+        B = (1 << 28) // (8 * N)                 # 256 MiB of complex f32 per length
+        cd.ensure_plans("f32", N)
+        x = torch.randn(B, 2 * N, device=dev, generator=torch.Generator(device=dev).manual_seed(N))
+        y = x.clone()
+        cd.cfft_device("f32", N, y.data_ptr(), B, 0, 1, st)
+        fwd = y.clone()
+        cd.cfft_device("f32", N, y.data_ptr(), B, 1, 1, st)
+        torch.cuda.synchronize()
+        rt = ((y - x).double().pow(2).sum() / x.double().pow(2).sum()).sqrt().item()
+        assert rt <= F32_TOL, (N, rt)
+        idx = torch.arange(0, B, max(1, B // 512), device=dev)
+        want = oracle().cfft("f32", N, x[idx].cpu().numpy(), 0, 1, threads=NT)
+        assert relrms(fwd[idx].cpu().numpy(), want) <= F32_TOL, N
