@@ -39,7 +39,7 @@ def test_fft_bin_example_known_answer():
     d = np.load(os.path.join(HERE, "golden", "fft_bin_example.npz"))
     y = oracle().cfft("f32", 1024, d["input"], 0, 1).reshape(-1, 2)
     mag = np.sqrt(y[:, 0].astype(np.float64) ** 2 + y[:, 1].astype(np.float64) ** 2)
-    assert int(np.argmax(mag)) == int(d["ref_index"]) == 213
+    assert int(np.argmax(mag)) == int(d["ref_index"]) == 213      # bit-identical to the reference, so the first max wins
 
 
 def test_digests_of_compiled_reference():

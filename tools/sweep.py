@@ -1,0 +1,94 @@
+#!/usr/bin/env python
+"""Device-timed throughput sweep over every entry point and length (B200).
+
+For each (op, N) a batch of about --mib MiB is transformed --reps times; time is taken with
+CUDA events on the launch stream (shim timer), data resident in HBM and larger than L2.
+Prints one row per kernel: ms, Gsamples/s, algorithmic GB/s (one read + one write of the
+payload) and the fraction of the measured HBM peak.  Output also goes to --json.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "cmsis-dsp_b200", "python"))
+import torch  # noqa: E402
+import cmsisdsp_b200 as cd  # noqa: E402
+
+
+def timed(fn, reps, stream):
+    cu = cd.cuda()
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    t = C.c_void_p()
+    cu.cmsisdsp_cuda_timer_begin(C.byref(t), stream)
+    for _ in range(reps):
+        fn()
+    ms = C.c_float()
+    cu.cmsisdsp_cuda_timer_end(t, stream, C.byref(ms))
+    return ms.value / reps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--mib", type=int, default=1024)
+    ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--ops", default="cfft_f32,cfft_q31,cfft_q15,rfft_fwd,rfft_inv")
+    ap.add_argument("--lens", default="16,32,64,128,256,512,1024,2048,4096")
+    ap.add_argument("--json", default=None)
+    args = ap.parse_args()
+    peak = 6536.7
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peak = json.load(open(pk))["hbm_gbs"]
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    cd.cuda().cmsisdsp_cuda_set_device(0)
+    st = torch.cuda.current_stream().cuda_stream
+    rows = []
+    for op in args.ops.split(","):
+        for N in [int(v) for v in args.lens.split(",")]:
+            if op.startswith("rfft") and N < 32:
+                continue
+            nbytes = args.mib << 20
+            if op.startswith("cfft"):
+                kind = op.split("_")[1]
+                esz = {"f32": 8, "q31": 8, "q15": 4}[kind]
+                B = nbytes // (esz * N)
+                cd.ensure_plans(kind, N)
+                buf = torch.zeros(B * N * esz // 4, dtype=torch.int32, device=dev)
+                if kind == "f32":
+                    buf.view(torch.float32).normal_()
+                else:
+                    buf.random_(-2**20, 2**20)
+                fn = lambda: cd.cfft_device(kind, N, buf.data_ptr(), B, 0, 1, st)
+                alg = 2 * B * N * esz
+                samples = B * N
+                info = cd.kernel_info({"f32": 0, "q31": 1, "q15": 2}[kind], N)
+            else:
+                B = nbytes // (4 * N)
+                cd.ensure_rfft_plans(N)
+                a = torch.randn(B, N, device=dev)
+                b = torch.empty_like(a)
+                inv = int(op == "rfft_inv")
+                fn = lambda: cd.rfft_device(N, a.data_ptr(), b.data_ptr(), B, inv, st)
+                alg = 2 * B * N * 4
+                samples = B * N
+                info = cd.kernel_info(4 if inv else 3, N)
+            ms = timed(fn, args.reps, st)
+            gbs = alg / ms / 1e6
+            row = dict(op=op, N=N, frames=B, ms=ms, gsamples=samples / ms / 1e6, gbs=gbs, frac=gbs / peak, **info)
+            rows.append(row)
+            print(f"{op:9s} N={N:5d} B={B:9d} {ms:8.4f} ms {row['gsamples']:8.1f} GS/s {gbs:8.1f} GB/s {100*gbs/peak:5.1f}% "
+                  f"regs={info['regs_per_thread']} cta/sm={info['ctas_per_sm']} thr={info['threads_per_cta']} smem={info['smem_bytes']}", flush=True)
+            del fn
+            torch.cuda.empty_cache()
+    if args.json:
+        json.dump(dict(peak_gbs=peak, rows=rows), open(args.json, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
