@@ -47,32 +47,59 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock and throttle reasons sampled through NVML every ~20 ms during the timed region
+    (falls back to polling nvidia-smi when NVML is unavailable)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+        self.index, self.stop_flag = index, threading.Event()
+        self.sm, self.sm_max, self.reasons = [], None, set()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        self.sm.append(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+        r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for name, bit in (("hw_slowdown", n.nvmlClocksThrottleReasonHwSlowdown),
+                          ("hw_thermal_slowdown", n.nvmlClocksThrottleReasonHwThermalSlowdown),
+                          ("sw_thermal_slowdown", n.nvmlClocksThrottleReasonSwThermalSlowdown),
+                          ("sw_power_cap", n.nvmlClocksThrottleReasonSwPowerCap)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        t = [v.strip() for v in out.split(",")]
+        if len(t) >= 6 and t[0].isdigit():
+            self.sm.append(int(t[0]))
+            self.sm_max = int(t[1]) if t[1].isdigit() else self.sm_max
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), t[2:6]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(name)
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([t.strip() for t in out.split(",")])
+                self._sample_nvml() if self.nvml else self._sample_smi()
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.02 if self.nvml else 0.2)
 
     def summary(self):
-        sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
-        mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(sm), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def cpu_baseline_run(frames, repeats=3, fast=True):
@@ -261,7 +288,7 @@ def run_cuda(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-e2e", action="store_true")

@@ -103,7 +103,9 @@ static int len_index(uint32_t n)
 }
 
 struct DevPlan {
-    void *tw = nullptr;           /* twiddles */
+    void *tw = nullptr;           /* pass-ordered twiddles of the cfft plan (Plan::build_twiddles) */
+    void *tw_rfwd = nullptr;      /* f32 only: same for the rfft forward / inverse plans of complex length N */
+    void *tw_rinv = nullptr;
     uint16_t *perm = nullptr;     /* destination position of X[k] when bitReverseFlag == 0 */
 };
 struct DevState {
@@ -122,6 +124,48 @@ static int cur_device(int *dev)
     return CMSISDSP_CUDA_OK;
 }
 
+#define FOR_ALL_N(X) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096)
+#define FOR_RFFT_NC(X) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048)
+
+/* re-order the reference-layout twiddles into the plan's pass order and upload them */
+template <class PL> static int upload_pass_ordered(const void *base, void **dOut)
+{
+    typedef typename PL::Arith::elem elem;
+    std::vector<elem> host((size_t)PL::kTwEntries + 1);
+    PL::build_twiddles((const elem *)base, host.data());
+    void *d = nullptr;
+    CU_TRY(cudaMalloc(&d, host.size() * sizeof(elem)));
+    CU_TRY(cudaMemcpy(d, host.data(), host.size() * sizeof(elem), cudaMemcpyHostToDevice));
+    *dOut = d;
+    return CMSISDSP_CUDA_OK;
+}
+
+static int build_tables(int type, uint32_t fftLen, const void *base, DevPlan &p)
+{
+    int rc = CMSISDSP_CUDA_ERR_ARGUMENT;
+    switch (fftLen) {
+#define CASE(n)                                                                                         \
+    case n:                                                                                             \
+        if (type == CMSISDSP_CUDA_F32) rc = upload_pass_ordered<PlanCfftF32<n>::type>(base, &p.tw);     \
+        else if (type == CMSISDSP_CUDA_Q31) rc = upload_pass_ordered<PlanCfftFix<ArithQ31, n>::type>(base, &p.tw); \
+        else rc = upload_pass_ordered<PlanCfftFix<ArithQ15, n>::type>(base, &p.tw);                     \
+        break;
+        FOR_ALL_N(CASE)
+#undef CASE
+    }
+    if (rc || type != CMSISDSP_CUDA_F32) return rc;
+    switch (fftLen) {
+#define CASE(nc)                                                                       \
+    case nc:                                                                           \
+        rc = upload_pass_ordered<PlanRfftFwd<nc>::type>(base, &p.tw_rfwd);             \
+        if (!rc) rc = upload_pass_ordered<PlanRfftInv<nc>::type>(base, &p.tw_rinv);    \
+        break;
+        FOR_RFFT_NC(CASE)
+#undef CASE
+    }
+    return rc;
+}
+
 extern "C" int cmsisdsp_cuda_plan_upload(int type, uint32_t fftLen, const void *pTwiddle,
                                          const uint16_t *pBitRevTable, uint16_t bitRevLength)
 {
@@ -135,8 +179,6 @@ extern "C" int cmsisdsp_cuda_plan_upload(int type, uint32_t fftLen, const void *
     DevPlan &p = g_dev[dev].plan[type][li];
     if (p.tw) return CMSISDSP_CUDA_OK;
 
-    const size_t twBytes = (type == CMSISDSP_CUDA_F32) ? (size_t)fftLen * 8
-                         : (type == CMSISDSP_CUDA_Q31) ? (size_t)fftLen * 6 : (size_t)fftLen * 3;
     /* out[k] = scrambled[P[k]] after the swap list  =>  X[k] lives at scrambled position P[k] */
     std::vector<uint16_t> perm(fftLen);
     for (uint32_t k = 0; k < fftLen; k++) perm[k] = (uint16_t)k;
@@ -145,13 +187,14 @@ extern "C" int cmsisdsp_cuda_plan_upload(int type, uint32_t fftLen, const void *
         if (a >= fftLen || b >= fftLen) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "plan_upload: bit-reversal entry out of range");
         const uint16_t t = perm[a]; perm[a] = perm[b]; perm[b] = t;
     }
-    void *dtw = nullptr; uint16_t *dperm = nullptr;
-    CU_TRY(cudaMalloc(&dtw, twBytes));
+    uint16_t *dperm = nullptr;
     CU_TRY(cudaMalloc((void **)&dperm, fftLen * sizeof(uint16_t)));
-    CU_TRY(cudaMemcpy(dtw, pTwiddle, twBytes, cudaMemcpyHostToDevice));
     CU_TRY(cudaMemcpy(dperm, perm.data(), fftLen * sizeof(uint16_t), cudaMemcpyHostToDevice));
-    p.perm = dperm;
-    p.tw = dtw;
+    DevPlan np;
+    np.perm = dperm;
+    rc = build_tables(type, fftLen, pTwiddle, np);
+    if (rc) return rc;
+    p = np;
     return CMSISDSP_CUDA_OK;
 }
 
@@ -202,9 +245,6 @@ static int get_plan(int type, uint32_t fftLen, DevPlan *out)
 }
 
 /* ------------------------------------------------------------------ transforms */
-
-#define FOR_ALL_N(X) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096)
-#define FOR_RFFT_NC(X) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048)
 
 template <class AR, class PL>
 static int cfft_launch(void *d_p, uint64_t nFrames, bool inv, const DevPlan &pl, bool bitrev, int shl1, cudaStream_t st)
@@ -275,12 +315,12 @@ extern "C" int cmsisdsp_cuda_rfft_fast_f32(const void *d_p, void *d_out, uint32_
         if (!ifftFlag) {                                                                                      \
             typedef PlanRfftFwd<nc>::type PL;                                                                 \
             typedef RfftFwdBody<PL> BODY;                                                                     \
-            BODY::Args a{(const cf32 *)d_p, (cf32 *)d_out, (const cf32 *)pl.tw, (const cf32 *)twr};           \
+            BODY::Args a{(const cf32 *)d_p, (cf32 *)d_out, (const cf32 *)pl.tw_rfwd, (const cf32 *)twr};      \
             return launch<BODY, PL>(a, nFrames, st);                                                          \
         } else {                                                                                              \
             typedef PlanRfftInv<nc>::type PL;                                                                 \
             typedef RfftInvBody<PL> BODY;                                                                     \
-            BODY::Args a{(const cf32 *)d_p, (cf32 *)d_out, (const cf32 *)pl.tw, (const cf32 *)twr, 1.0f / (float)nc}; \
+            BODY::Args a{(const cf32 *)d_p, (cf32 *)d_out, (const cf32 *)pl.tw_rinv, (const cf32 *)twr, 1.0f / (float)nc}; \
             return launch<BODY, PL>(a, nFrames, st);                                                          \
         }
         FOR_RFFT_NC(CASE)

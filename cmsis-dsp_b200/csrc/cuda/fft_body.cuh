@@ -52,7 +52,7 @@ template <class PL, bool INV> struct CfftBody {
     struct Args {
         const elem *in;          /* frame base (device or emulated) */
         elem *out;               /* may alias in */
-        const elem *tw;          /* twiddle table for N */
+        const elem *tw;          /* pass-ordered twiddle table of this plan (Plan::build_twiddles) */
         const uint16_t *perm;    /* null => natural order; else destination position of X[k] */
         float scale;             /* f32 inverse: 1/N */
         int shl1;                /* fixed point, N = 2*4^m: final << 1 of every word */
@@ -158,7 +158,7 @@ template <class PL> struct RfftFwdBody {
     struct Args {
         const cf32 *in;      /* real frame viewed as N complex */
         cf32 *out;           /* packed spectrum: N complex = 2N floats */
-        const cf32 *tw;      /* CFFT twiddles for N */
+        const cf32 *tw;      /* pass-ordered CFFT twiddles of this plan */
         const cf32 *twr;     /* twiddleCoef_rfft_(2N): (sin,cos)(2*pi*k/(2N)), k < N */
     };
     static FFT_HD Args for_frame(Args a, uint64_t frame)

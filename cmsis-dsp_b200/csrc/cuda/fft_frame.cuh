@@ -16,6 +16,10 @@
  * natural order, so arm_bitreversal2.c's swap pass disappears (bitReverseFlag = 0 is
  * served by scattering through the plan's permutation instead).
  *
+ * Twiddles are read from a PASS-ORDERED copy of the reference tables (Plan::build_twiddles):
+ * entry [slot][j] for butterfly j, so a warp's twiddle load is one contiguous 256-byte
+ * request instead of a gather with stride t*8 bytes.
+ *
  * The first pass reads HBM directly into registers (lane-contiguous => coalesced) and
  * the last pass writes HBM directly from registers; only the NP-1 exchanges touch
  * shared memory (padded layout, see Plan::pad).
@@ -35,14 +39,26 @@ namespace b200fft {
 template <int R_> struct PassF32 {
     static constexpr int R = R_;
     static constexpr bool kMirror = false;
+    typedef cf32 telem;
     static FFT_HD int out_index(int e) { return e; }
-    template <bool INV, int N, bool LASTPASS>
-    static FFT_HD void compute(cf32 *x, const cf32 *__restrict__ tw, int sp /* s*p */)
+    /* twiddle slots per butterfly in the pass-ordered table (none on the last pass: W^0) */
+    static constexpr int slots(bool lastPass) { return lastPass ? 0 : R - 1; }
+    /* slot t-1 of butterfly j = W_N^(s*p*t), p = j / S: entry s*p*t of the reference table */
+    template <int N, int S> static void fill(const cf32 *base, cf32 *out, bool lastPass)
     {
+        constexpr int NBF = N / R;
+        if (lastPass) return;
+        for (int t = 1; t < R; t++)
+            for (int j = 0; j < NBF; j++) out[(t - 1) * NBF + j] = base[S * (j / S) * t];
+    }
+    template <bool INV, int N, bool LASTPASS>
+    static FFT_HD void compute(cf32 *x, const cf32 *__restrict__ twp, int j)
+    {
+        constexpr int NBF = N / R;
         DftF32<R>::run(x);
         if (!LASTPASS) {
 #pragma unroll
-            for (int t = 1; t < R; t++) x[t] = mul_conj(x[t], tw[sp * t]);
+            for (int t = 1; t < R; t++) x[t] = mul_conj(x[t], twp[(t - 1) * NBF + j]);
         }
     }
 };
@@ -64,43 +80,64 @@ template <class ARITH, int KA, int KB = -1> struct PassFix {
     /* element e = w + rb*v holds residue v + ra*w after the pass */
     static FFT_HD int out_index(int e) { return (e / rb) + ra * (e % rb); }
 
-    static FFT_HD twid ldtw(const telem *__restrict__ tw, int idx) { return ARITH::load(tw[idx]); }
+    static constexpr int ta = (KA == ST_PRE2) ? 1 : (KA == ST_LAST4 ? 0 : 3);   /* twiddles per stage-a butterfly */
+    static constexpr int tb = (KB < 0 || KB == ST_LAST4) ? 0 : 3;
+    static constexpr int slots(bool) { return rb * ta + tb; }
 
-    template <int K, bool INV>
-    static FFT_HD void stage4(work &a, work &b, work &c, work &d, const telem *__restrict__ tw, int ia)
+    /* pass-ordered table: slot (u*ta + m-1) of butterfly j = W^(m*(s*p + (N/R)*u)) for stage a,
+     * slot (rb*ta + m-1) = W^(m*ra*s*p) for stage b -- the entries ia, 2ia, 3ia the reference
+     * reads from twiddleCoef_N_q31/_q15 (arm_cfft_radix4_q31.c:229-266,307-317) */
+    template <int N, int S> static void fill(const telem *base, telem *out, bool)
+    {
+        constexpr int NBF = N / R;
+        for (int j = 0; j < NBF; j++) {
+            const int sp = S * (j / S);
+            for (int u = 0; u < rb; u++)
+                for (int m = 1; m <= ta; m++) out[(u * ta + m - 1) * NBF + j] = base[m * (sp + (N / R) * u)];
+            for (int m = 1; m <= tb; m++) out[(rb * ta + m - 1) * NBF + j] = base[m * ra * sp];
+        }
+    }
+
+    template <int K, bool INV, int NBF>
+    static FFT_HD void stage4(work &a, work &b, work &c, work &d, const telem *__restrict__ twp, int slot, int j)
     {
         if (K == ST_LAST4) {
             twid z = {0, 0};
             ARITH::template bfly4<K, INV>(a, b, c, d, z, z, z);
         } else {
-            ARITH::template bfly4<K, INV>(a, b, c, d, ldtw(tw, ia), ldtw(tw, 2 * ia), ldtw(tw, 3 * ia));
+            ARITH::template bfly4<K, INV>(a, b, c, d, ARITH::load(twp[slot * NBF + j]), ARITH::load(twp[(slot + 1) * NBF + j]),
+                                          ARITH::load(twp[(slot + 2) * NBF + j]));
         }
     }
 
     template <bool INV, int N, bool LASTPASS>
-    static FFT_HD void compute(work *x, const telem *__restrict__ tw, int sp /* s*p */)
+    static FFT_HD void compute(work *x, const telem *__restrict__ twp, int j)
     {
-        /* stage a on elements t = u + rb*v  (u < rb, v < ra), twiddle exponent sp + (N/R)*u */
+        constexpr int NBF = N / R;
+        /* stage a on elements t = u + rb*v  (u < rb, v < ra) */
 #pragma unroll
         for (int u = 0; u < rb; u++) {
-            const int ia = sp + (N / R) * u;
             if (KA == ST_PRE2)
-                ARITH::template bfly2<INV>(x[u], x[u + rb], ldtw(tw, ia));
+                ARITH::template bfly2<INV>(x[u], x[u + rb], ARITH::load(twp[u * NBF + j]));
             else
-                stage4<KA, INV>(x[u], x[u + rb], x[u + 2 * rb], x[u + 3 * rb], tw, ia);
+                stage4<KA, INV, NBF>(x[u], x[u + rb], x[u + 2 * rb], x[u + 3 * rb], twp, u * ta, j);
         }
         if (KB >= 0) {
-            /* stage b on elements u = 0..3 of each residue v, twiddle exponent ra*sp */
+            /* stage b on elements u = 0..3 of each residue v */
 #pragma unroll
             for (int v = 0; v < ra; v++)
-                stage4<KB, INV>(x[rb * v], x[rb * v + 1], x[rb * v + 2], x[rb * v + 3], tw, ra * sp);
+                stage4<KB, INV, NBF>(x[rb * v], x[rb * v + 1], x[rb * v + 2], x[rb * v + 3], twp, rb * ta, j);
         }
     }
 };
 
 /* ---------------------------------------------------------------- plan */
 
-struct NoPass { static constexpr int R = 1; static constexpr bool kMirror = false; };
+struct NoPass {
+    static constexpr int R = 1;
+    static constexpr bool kMirror = false;
+    static constexpr int slots(bool) { return 0; }
+};
 
 template <class ARITH_, int N_, int T_, int F_, int PADA_, int PADB_, class P0_, class P1_ = NoPass, class P2_ = NoPass>
 struct Plan {
@@ -119,12 +156,24 @@ struct Plan {
     static constexpr int kFrameElems = PADB_ ? (N + ((N - 1) >> PADA_) * PADB_ + PADB_) : N;
     static constexpr int kSmemBytes = (NP > 1) ? F * kFrameElems * (int)sizeof(typename ARITH_::elem) : 0;
     static constexpr int kThreads = T * F;
+    /* pass-ordered twiddle table: pass p owns slots_p * (N / R_p) entries starting at kTwOff<p> */
+    static constexpr int kTw0 = P0::slots(NP == 1) * (N / P0::R);
+    static constexpr int kTw1 = (NP > 1) ? P1::slots(NP == 2) * (N / P1::R) : 0;
+    static constexpr int kTw2 = (NP > 2) ? P2::slots(true) * (N / P2::R) : 0;
+    static constexpr int kTwEntries = kTw0 + kTw1 + kTw2;
+    /* build the table from the reference-layout twiddles (N entries f32, 3N/4 entries q31/q15) */
+    static void build_twiddles(const typename ARITH_::elem *base, typename ARITH_::elem *out)
+    {
+        P0::template fill<N, S0>(base, out, NP == 1);
+        if constexpr (NP > 1) P1::template fill<N, S1>(base, out + kTw0, NP == 2);
+        if constexpr (NP > 2) P2::template fill<N, S2>(base, out + kTw0 + kTw1, true);
+    }
 };
 
 template <class PL, int P> struct PassOf;
-template <class PL> struct PassOf<PL, 0> { typedef typename PL::P0 type; static constexpr int S = PL::S0; };
-template <class PL> struct PassOf<PL, 1> { typedef typename PL::P1 type; static constexpr int S = PL::S1; };
-template <class PL> struct PassOf<PL, 2> { typedef typename PL::P2 type; static constexpr int S = PL::S2; };
+template <class PL> struct PassOf<PL, 0> { typedef typename PL::P0 type; static constexpr int S = PL::S0, TWOFF = 0; };
+template <class PL> struct PassOf<PL, 1> { typedef typename PL::P1 type; static constexpr int S = PL::S1, TWOFF = PL::kTw0; };
+template <class PL> struct PassOf<PL, 2> { typedef typename PL::P2 type; static constexpr int S = PL::S2, TWOFF = PL::kTw0 + PL::kTw1; };
 
 /* butterfly index handled by thread i as its b-th butterfly of a pass with NBF butterflies */
 template <bool MIRROR, int T, int NBF> FFT_HD int bfly_index(int i, int b)
@@ -184,8 +233,7 @@ template <class PL> struct Engine {
 #pragma unroll
         for (int b = 0; b < NB; b++) {
             const int j = bfly_index<PS::kMirror, T, NBF>(i, b);
-            const int sp = S * (j / S);
-            PS::template compute<INV, N, (P == NP - 1)>(&r.v[b * R], tw, sp);
+            PS::template compute<INV, N, (P == NP - 1)>(&r.v[b * R], tw + PassOf<PL, P>::TWOFF, j);
         }
     }
 

@@ -76,11 +76,13 @@ static void cfft_run(typename AR::elem *data, uint64_t nFrames, const void *tw, 
 {
     typedef CfftBody<PL, INV> BODY;
     typedef typename AR::elem elem;
+    std::vector<elem> ordered((size_t)PL::kTwEntries + 1);
+    PL::build_twiddles((const elem *)tw, ordered.data());     /* same re-ordering the shim uploads */
     run_batch<PL, BODY>(nFrames, [&](uint64_t f) {
         typename BODY::Args a;
         a.in = data + f * PL::N;
         a.out = data + f * PL::N;
-        a.tw = (const elem *)tw;
+        a.tw = ordered.data();
         a.perm = perm;
         a.scale = 1.0f / (float)PL::N;
         a.shl1 = shl1;
@@ -132,19 +134,23 @@ int emu_rfft(uint32_t Nreal, const float *in, float *out, uint64_t nFrames, int 
         if (!ifft) {                                                                                 \
             typedef PlanRfftFwd<nc>::type PL;                                                        \
             typedef RfftFwdBody<PL> BODY;                                                            \
+            std::vector<cf32> ordered((size_t)PL::kTwEntries + 1);                                   \
+            PL::build_twiddles((const cf32 *)tw, ordered.data());                                    \
             run_batch<PL, BODY>(nFrames, [&](uint64_t f) {                                           \
                 BODY::Args a;                                                                        \
                 a.in = (const cf32 *)in + f * nc; a.out = (cf32 *)out + f * nc;                      \
-                a.tw = (const cf32 *)tw; a.twr = (const cf32 *)twr;                                  \
+                a.tw = ordered.data(); a.twr = (const cf32 *)twr;                                    \
                 return a;                                                                            \
             });                                                                                      \
         } else {                                                                                     \
             typedef PlanRfftInv<nc>::type PL;                                                        \
             typedef RfftInvBody<PL> BODY;                                                            \
+            std::vector<cf32> ordered((size_t)PL::kTwEntries + 1);                                   \
+            PL::build_twiddles((const cf32 *)tw, ordered.data());                                    \
             run_batch<PL, BODY>(nFrames, [&](uint64_t f) {                                           \
                 BODY::Args a;                                                                        \
                 a.in = (const cf32 *)in + f * nc; a.out = (cf32 *)out + f * nc;                      \
-                a.tw = (const cf32 *)tw; a.twr = (const cf32 *)twr; a.scale = 1.0f / (float)nc;      \
+                a.tw = ordered.data(); a.twr = (const cf32 *)twr; a.scale = 1.0f / (float)nc;        \
                 return a;                                                                            \
             });                                                                                      \
         }                                                                                            \
