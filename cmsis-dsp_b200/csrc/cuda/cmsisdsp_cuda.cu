@@ -9,6 +9,7 @@
  */
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -63,6 +64,178 @@ __global__ void __launch_bounds__(PL::kThreads) frame_kernel(typename BODY::Args
         __syncthreads();
         if (valid) BODY::template phase<3>(r, a, sm, i);
     }
+}
+
+/* ------------------------------------------------------------------ persistent TMA-staged kernel
+ *
+ * One CTA per resident slot, looping over frame groups (PL::F consecutive frames).  The
+ * next group is fetched with ONE bulk async copy (cp.async.bulk, the 1-D TMA path) into the
+ * other half of a double buffer while the current group is being transformed, so HBM reads
+ * never wait on the butterflies: bytes in flight per SM = resident CTAs x group size,
+ * independent of register pressure.  Completion is tracked by one mbarrier per buffer.
+ * Results leave through the registers (coalesced streaming stores), as in frame_kernel. */
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+
+template <class PL> struct StagedSmem {
+    typedef typename PL::Arith::elem elem;
+    static constexpr int kStageElems = PL::F * PL::N;                  /* one group, linear, as in HBM */
+    static constexpr int kStageBytes = kStageElems * (int)sizeof(elem);
+    static constexpr int kExchBytes = ((PL::NP > 1 ? PL::F * PL::kFrameElems * (int)sizeof(elem) : 0) + 15) & ~15;
+    static constexpr int kBytes = 2 * kStageBytes + kExchBytes + 16;   /* + two mbarriers */
+};
+
+template <class BODY, class PL>
+__global__ void __launch_bounds__(PL::kThreads) frame_kernel_staged(typename BODY::Args base, uint64_t nFrames)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    typedef typename BODY::elem elem;
+    typedef StagedSmem<PL> SM;
+    elem *stage0 = reinterpret_cast<elem *>(smem_raw);
+    elem *exch = reinterpret_cast<elem *>(smem_raw + 2 * SM::kStageBytes);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + 2 * SM::kStageBytes + SM::kExchBytes);
+
+    const int tid = threadIdx.x;
+    const int fl = tid / PL::T, i = tid % PL::T;
+    const uint64_t nGroups = (nFrames + PL::F - 1) / PL::F;
+    elem *sm = exch + fl * PL::kFrameElems;
+
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto group_bytes = [&](uint64_t g) -> uint32_t {
+        const uint64_t left = nFrames - g * PL::F;
+        return (uint32_t)((left < (uint64_t)PL::F ? left : (uint64_t)PL::F) * PL::N * sizeof(elem));
+    };
+    uint64_t g = blockIdx.x;
+    if (tid == 0 && g < nGroups) {
+        const uint32_t bytes = group_bytes(g);
+        mbar_expect_tx(&bar[0], bytes);
+        bulk_g2s(stage0, base.in + g * (uint64_t)SM::kStageElems, bytes, &bar[0]);
+    }
+    uint32_t parity[2] = {0u, 0u};
+    int cur = 0;
+    for (; g < nGroups; g += gridDim.x, cur ^= 1) {
+        const uint64_t gn = g + gridDim.x;
+        if (tid == 0 && gn < nGroups) {          /* prefetch the next group into the other buffer */
+            const uint32_t bytes = group_bytes(gn);
+            mbar_expect_tx(&bar[cur ^ 1], bytes);
+            bulk_g2s(stage0 + (cur ^ 1) * SM::kStageElems, base.in + gn * (uint64_t)SM::kStageElems, bytes, &bar[cur ^ 1]);
+        }
+        const uint64_t frame = g * PL::F + fl;
+        const bool valid = frame < nFrames;
+        typename BODY::Args a = BODY::for_frame(base, valid ? frame : 0);
+        a.in = stage0 + cur * SM::kStageElems + fl * PL::N;      /* the staged copy of this frame */
+        typename BODY::Regs r;
+
+        mbar_wait(&bar[cur], parity[cur]);
+        parity[cur] ^= 1u;
+        if (valid) BODY::template phase<0>(r, a, sm, i);
+        if constexpr (BODY::kPhases > 1) {
+            __syncthreads();
+            if (valid) BODY::template phase<1>(r, a, sm, i);
+        }
+        if constexpr (BODY::kPhases > 2) {
+            __syncthreads();
+            if (valid) BODY::template phase<2>(r, a, sm, i);
+            __syncthreads();
+            if (valid) BODY::template phase<3>(r, a, sm, i);
+        }
+        /* everyone is done with stage[cur] and the exchange buffer before the next iteration
+         * refills the former (prefetch of g + 2*gridDim) and overwrites the latter */
+        __syncthreads();
+    }
+}
+
+static int g_numSMs[64] = {0};
+static int num_sms()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (!g_numSMs[dev]) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        g_numSMs[dev] = n;
+    }
+    return g_numSMs[dev];
+}
+
+/* resident CTAs per SM of the staged kernel (also raises its dynamic shared memory limit once) */
+template <class BODY, class PL> static int staged_occupancy(int *occOut)
+{
+    static int occ[64] = {0};
+    int dev = 0;
+    CU_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(CMSISDSP_CUDA_ERR_NO_DEVICE, "device index out of range");
+    if (!occ[dev]) {
+        CU_TRY(cudaFuncSetAttribute(frame_kernel_staged<BODY, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, StagedSmem<PL>::kBytes));
+        int o = 0;
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, frame_kernel_staged<BODY, PL>, PL::kThreads, StagedSmem<PL>::kBytes));
+        if (o < 1) return fail(CMSISDSP_CUDA_ERR_RUNTIME, "staged kernel does not fit on an SM");
+        occ[dev] = o;
+    }
+    *occOut = occ[dev];
+    return CMSISDSP_CUDA_OK;
+}
+
+template <class BODY, class PL>
+static int launch_staged(const typename BODY::Args &args, uint64_t nFrames, cudaStream_t st)
+{
+    if (nFrames == 0) return CMSISDSP_CUDA_OK;
+    int occ = 0;
+    int rc = staged_occupancy<BODY, PL>(&occ);
+    if (rc) return rc;
+    const uint64_t groups = (nFrames + PL::F - 1) / PL::F;
+    const uint64_t slots = (uint64_t)occ * (uint64_t)num_sms();
+    const unsigned grid = (unsigned)(groups < slots ? groups : slots);
+    frame_kernel_staged<BODY, PL><<<grid, PL::kThreads, StagedSmem<PL>::kBytes, st>>>(args, nFrames);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CU_TRY(cudaGetLastError());
+    return CMSISDSP_CUDA_OK;
+}
+
+/* kernel flavour: 0 = direct loads (frame_kernel), 1 = persistent TMA-staged (default for the
+ * lengths listed in use_staged()).  CMSISDSP_CUDA_KERNEL=direct|staged overrides, for A/B runs. */
+static int kernel_override()
+{
+    static int v = -2;
+    if (v == -2) {
+        const char *e = getenv("CMSISDSP_CUDA_KERNEL");
+        v = !e ? -1 : (!strcmp(e, "direct") ? 0 : (!strcmp(e, "staged") ? 1 : -1));
+    }
+    return v;
+}
+static bool use_staged(uint32_t complexLen, const void *in)
+{
+    if (((uintptr_t)in & 15u) != 0) return false;          /* bulk copies need 16-byte aligned sources */
+    const int o = kernel_override();
+    if (o >= 0) return o == 1;
+    return complexLen >= 128;
 }
 
 template <class BODY, class PL>
@@ -250,14 +423,17 @@ template <class AR, class PL>
 static int cfft_launch(void *d_p, uint64_t nFrames, bool inv, const DevPlan &pl, bool bitrev, int shl1, cudaStream_t st)
 {
     typedef typename AR::elem elem;
-    if (inv) {
-        typedef CfftBody<PL, true> BODY;
-        typename BODY::Args a{(const elem *)d_p, (elem *)d_p, (const elem *)pl.tw, bitrev ? nullptr : pl.perm, 1.0f / (float)PL::N, shl1};
-        return launch<BODY, PL>(a, nFrames, st);
+    const bool staged = use_staged(PL::N, d_p);
+#define GO(INV_, STG_)                                                                                                       \
+    {                                                                                                                        \
+        typedef CfftBody<PL, INV_, STG_> BODY;                                                                               \
+        typename BODY::Args a{(const elem *)d_p, (elem *)d_p, (const elem *)pl.tw, bitrev ? nullptr : pl.perm, 1.0f / (float)PL::N, shl1}; \
+        if constexpr (STG_) return launch_staged<BODY, PL>(a, nFrames, st);                                                  \
+        else return launch<BODY, PL>(a, nFrames, st);                                                                        \
     }
-    typedef CfftBody<PL, false> BODY;
-    typename BODY::Args a{(const elem *)d_p, (elem *)d_p, (const elem *)pl.tw, bitrev ? nullptr : pl.perm, 1.0f / (float)PL::N, shl1};
-    return launch<BODY, PL>(a, nFrames, st);
+    if (inv) { if (staged) GO(true, true) else GO(true, false) }
+    if (staged) GO(false, true) else GO(false, false)
+#undef GO
 }
 
 static int cfft_any(int type, void *d_p, uint32_t fftLen, uint64_t nFrames, uint8_t ifftFlag, uint8_t bitReverseFlag, void *stream)
@@ -314,14 +490,14 @@ extern "C" int cmsisdsp_cuda_rfft_fast_f32(const void *d_p, void *d_out, uint32_
     case nc:                                                                                                  \
         if (!ifftFlag) {                                                                                      \
             typedef PlanRfftFwd<nc>::type PL;                                                                 \
-            typedef RfftFwdBody<PL> BODY;                                                                     \
-            BODY::Args a{(const cf32 *)d_p, (cf32 *)d_out, (const cf32 *)pl.tw_rfwd, (const cf32 *)twr};      \
-            return launch<BODY, PL>(a, nFrames, st);                                                          \
+            RfftFwdBody<PL>::Args a{(const cf32 *)d_p, (cf32 *)d_out, (const cf32 *)pl.tw_rfwd, (const cf32 *)twr}; \
+            if (use_staged(nc, d_p)) return launch_staged<RfftFwdBody<PL, true>, PL>(RfftFwdBody<PL, true>::Args{a.in, a.out, a.tw, a.twr}, nFrames, st); \
+            return launch<RfftFwdBody<PL>, PL>(a, nFrames, st);                                               \
         } else {                                                                                              \
             typedef PlanRfftInv<nc>::type PL;                                                                 \
-            typedef RfftInvBody<PL> BODY;                                                                     \
-            BODY::Args a{(const cf32 *)d_p, (cf32 *)d_out, (const cf32 *)pl.tw_rinv, (const cf32 *)twr, 1.0f / (float)nc}; \
-            return launch<BODY, PL>(a, nFrames, st);                                                          \
+            RfftInvBody<PL>::Args a{(const cf32 *)d_p, (cf32 *)d_out, (const cf32 *)pl.tw_rinv, (const cf32 *)twr, 1.0f / (float)nc}; \
+            if (use_staged(nc, d_p)) return launch_staged<RfftInvBody<PL, true>, PL>(RfftInvBody<PL, true>::Args{a.in, a.out, a.tw, a.twr, a.scale}, nFrames, st); \
+            return launch<RfftInvBody<PL>, PL>(a, nFrames, st);                                               \
         }
         FOR_RFFT_NC(CASE)
 #undef CASE

@@ -30,6 +30,14 @@ template <class V> FFT_HD V ld_stream(const V *p) { return *p; }
 template <class V> FFT_HD void st_stream(V *p, V v) { *p = v; }
 #endif
 
+/* frame input: STAGED = the frame was brought into shared memory by a bulk (TMA) copy and `p`
+ * points there; otherwise `p` is global memory and is read once with a streaming hint */
+template <bool STAGED, class V> FFT_HD V ld_in(const V *p)
+{
+    if (STAGED) return *p;
+    return ld_stream(p);
+}
+
 /* number of phases for a plan with NP passes: 1 -> 1, 2 -> 2, 3 -> 4 (the middle pass is split
  * into load+compute / store so the single exchange buffer can be reused) */
 template <int NP> struct PhaseCount { static constexpr int value = (NP == 1) ? 1 : (NP == 2 ? 2 : 4); };
@@ -39,7 +47,7 @@ template <> struct IsF32<cf32> { static constexpr bool value = true; };
 
 /* ------------------------------------------------------------------ CFFT */
 
-template <class PL, bool INV> struct CfftBody {
+template <class PL, bool INV, bool STAGED = false> struct CfftBody {
     typedef Engine<PL> Eng;
     typedef typename Eng::A A;
     typedef typename A::elem elem;
@@ -57,12 +65,14 @@ template <class PL, bool INV> struct CfftBody {
         float scale;             /* f32 inverse: 1/N */
         int shl1;                /* fixed point, N = 2*4^m: final << 1 of every word */
     };
+    /* frame-local view of the batch arguments; with STAGED the kernel overrides `in` */
     static FFT_HD Args for_frame(Args a, uint64_t frame)
     {
         a.in += frame * (uint64_t)N;
         a.out += frame * (uint64_t)N;
         return a;
     }
+    static constexpr bool kStaged = STAGED;
 
     static FFT_HD void gload(Regs &r, const Args &a, int i)
     {
@@ -71,7 +81,7 @@ template <class PL, bool INV> struct CfftBody {
         for (int b = 0; b < E / PS::R; b++)
 #pragma unroll
             for (int e = 0; e < PS::R; e++) {
-                work w = A::load(ld_stream(a.in + Eng::template in_index<0>(i, b, e)));
+                work w = A::load(ld_in<STAGED>(a.in + Eng::template in_index<0>(i, b, e)));
                 if (kF32 && INV) w.y = -w.y;                       /* conjugate input (cfft_f32.c:1252-1261) */
                 r.v[b * PS::R + e] = w;
             }
@@ -145,7 +155,7 @@ FFT_HD cf32 rfft_merge(cf32 A, cf32 B, cf32 tw)
  * (E == 16), so thread i holds bins {j + t*NBF} and {NBF - j + t*NBF}: every (k, Nh-k) pair is
  * thread-local.  Slot m of butterfly 0 pairs with slot 15-m (thread 0: butterfly 0 pairs
  * t <-> 8-t with t = 0 the packed DC/Nyquist bin, butterfly 1 pairs t <-> 7-t). */
-template <class PL> struct RfftFwdBody {
+template <class PL, bool STAGED = false> struct RfftFwdBody {
     typedef Engine<PL> Eng;
     typedef typename Eng::Regs Regs;
     typedef cf32 elem;
@@ -161,12 +171,14 @@ template <class PL> struct RfftFwdBody {
         const cf32 *tw;      /* pass-ordered CFFT twiddles of this plan */
         const cf32 *twr;     /* twiddleCoef_rfft_(2N): (sin,cos)(2*pi*k/(2N)), k < N */
     };
+    /* frame-local view of the batch arguments; with STAGED the kernel overrides `in` */
     static FFT_HD Args for_frame(Args a, uint64_t frame)
     {
         a.in += frame * (uint64_t)N;
         a.out += frame * (uint64_t)N;
         return a;
     }
+    static constexpr bool kStaged = STAGED;
 
     static FFT_HD void gload(Regs &r, const Args &a, int i)
     {
@@ -175,7 +187,7 @@ template <class PL> struct RfftFwdBody {
         for (int b = 0; b < E / PS::R; b++)
 #pragma unroll
             for (int e = 0; e < PS::R; e++)
-                r.v[b * PS::R + e] = ld_stream(a.in + Eng::template in_index<0>(i, b, e));
+                r.v[b * PS::R + e] = ld_in<STAGED>(a.in + Eng::template in_index<0>(i, b, e));
     }
     static FFT_HD void split_store(const Regs &r, const Args &a, int i)
     {
@@ -228,7 +240,7 @@ template <class PL> struct RfftFwdBody {
     }
 };
 
-template <class PL> struct RfftInvBody {
+template <class PL, bool STAGED = false> struct RfftInvBody {
     typedef Engine<PL> Eng;
     typedef typename Eng::Regs Regs;
     typedef cf32 elem;
@@ -244,12 +256,14 @@ template <class PL> struct RfftInvBody {
         const cf32 *twr;
         float scale;         /* 1/N */
     };
+    /* frame-local view of the batch arguments; with STAGED the kernel overrides `in` */
     static FFT_HD Args for_frame(Args a, uint64_t frame)
     {
         a.in += frame * (uint64_t)N;
         a.out += frame * (uint64_t)N;
         return a;
     }
+    static constexpr bool kStaged = STAGED;
 
     /* merge (rfft_fast_f32.c:405-462) then conjugate for the inverse CFFT (cfft_f32.c:1252-1261) */
     static FFT_HD cf32 mconj(cf32 z) { return {z.x, -z.y}; }
@@ -261,8 +275,8 @@ template <class PL> struct RfftInvBody {
             const int j0 = i, j1 = NBF - i;
 #pragma unroll
             for (int t = 0; t < 8; t++) {
-                g[t] = ld_stream(a.in + j0 + t * NBF);
-                g[8 + t] = ld_stream(a.in + j1 + t * NBF);
+                g[t] = ld_in<STAGED>(a.in + j0 + t * NBF);
+                g[8 + t] = ld_in<STAGED>(a.in + j1 + t * NBF);
             }
 #pragma unroll
             for (int t = 0; t < 8; t++) {
@@ -272,8 +286,8 @@ template <class PL> struct RfftInvBody {
         } else {
 #pragma unroll
             for (int t = 0; t < 8; t++) {
-                g[t] = ld_stream(a.in + t * NBF);
-                g[8 + t] = ld_stream(a.in + NBF / 2 + t * NBF);
+                g[t] = ld_in<STAGED>(a.in + t * NBF);
+                g[8 + t] = ld_in<STAGED>(a.in + NBF / 2 + t * NBF);
             }
             r.v[0] = mconj(cf32{0.5f * (g[0].x + g[0].y), 0.5f * (g[0].x - g[0].y)});   /* :425-431 */
 #pragma unroll
