@@ -40,6 +40,14 @@ static int fail(int code, const char *what, cudaError_t e = cudaSuccess)
 
 /* ------------------------------------------------------------------ kernel */
 
+/* barrier between two phases of a frame: when a frame's T threads sit inside one warp the
+ * exchange is warp-private and __syncwarp() is enough (no CTA-wide stall) */
+template <class PL> __device__ __forceinline__ void frame_sync()
+{
+    if constexpr (PL::T <= 32) __syncwarp();
+    else __syncthreads();
+}
+
 template <class BODY, class PL>
 __global__ void __launch_bounds__(PL::kThreads) frame_kernel(typename BODY::Args base, uint64_t nFrames)
 {
@@ -55,13 +63,13 @@ __global__ void __launch_bounds__(PL::kThreads) frame_kernel(typename BODY::Args
 
     if (valid) BODY::template phase<0>(r, a, sm, i);
     if constexpr (BODY::kPhases > 1) {
-        __syncthreads();
+        frame_sync<PL>();
         if (valid) BODY::template phase<1>(r, a, sm, i);
     }
     if constexpr (BODY::kPhases > 2) {
-        __syncthreads();
+        frame_sync<PL>();
         if (valid) BODY::template phase<2>(r, a, sm, i);
-        __syncthreads();
+        frame_sync<PL>();
         if (valid) BODY::template phase<3>(r, a, sm, i);
     }
 }
@@ -235,7 +243,8 @@ static bool use_staged(uint32_t complexLen, const void *in)
     if (((uintptr_t)in & 15u) != 0) return false;          /* bulk copies need 16-byte aligned sources */
     const int o = kernel_override();
     if (o >= 0) return o == 1;
-    return complexLen >= 128;
+    (void)complexLen;
+    return false;
 }
 
 template <class BODY, class PL>

@@ -29,100 +29,171 @@ struct alignas(8) cf32 { float x, y; };
 struct alignas(8) ci32 { int32_t x, y; };
 struct alignas(4) ci16 { int16_t x, y; };
 
-/* ------------------------------------------------------------------ f32 */
+/* ------------------------------------------------------------------ f32
+ *
+ * Complex values live in aligned register pairs, and on the device every complex add,
+ * subtract and multiply is issued as a PACKED fp32x2 instruction (FADD2 / FMUL2 / FFMA2,
+ * new in sm_100): one issue slot for the real and the imaginary lane.  ptxas folds the
+ * lane swap (.LO_HI), the half negation (.NP) and scalar broadcasts (.F32) into operand
+ * modifiers, so a radix-4 butterfly is 8 instructions and a complex multiply is 2. */
 
-FFT_HD cf32 cadd(cf32 a, cf32 b) { return {a.x + b.x, a.y + b.y}; }
-FFT_HD cf32 csub(cf32 a, cf32 b) { return {a.x - b.x, a.y - b.y}; }
-/* a * (-i) and a * (+i) */
-FFT_HD cf32 mul_mi(cf32 a) { return {a.y, -a.x}; }
-FFT_HD cf32 mul_pi(cf32 a) { return {-a.y, a.x}; }
+#if defined(__CUDA_ARCH__)
+FFT_HD float2 f2(cf32 a) { return make_float2(a.x, a.y); }
+FFT_HD cf32 c2(float2 a) { return {a.x, a.y}; }
+FFT_HD cf32 cadd(cf32 a, cf32 b) { return c2(__fadd2_rn(f2(a), f2(b))); }
+FFT_HD cf32 csub(cf32 a, cf32 b) { return c2(__fadd2_rn(f2(a), make_float2(-b.x, -b.y))); }
+/* a + (-i)*b  and  a + (+i)*b */
+FFT_HD cf32 cadd_mi(cf32 a, cf32 b) { return c2(__fadd2_rn(f2(a), make_float2(b.y, -b.x))); }
+FFT_HD cf32 cadd_pi(cf32 a, cf32 b) { return c2(__fadd2_rn(f2(a), make_float2(-b.y, b.x))); }
 /* a * conj(w), w = (cos, +sin) as stored in the reference's twiddle tables */
 FFT_HD cf32 mul_conj(cf32 a, cf32 w)
 {
-#if defined(__CUDA_ARCH__)
-    return {__fmaf_rn(a.x, w.x, a.y * w.y), __fmaf_rn(a.y, w.x, -(a.x * w.y))};
-#else
-    return {a.x * w.x + a.y * w.y, a.y * w.x - a.x * w.y};
-#endif
+    return c2(__ffma2_rn(f2(a), make_float2(w.x, w.x), __fmul2_rn(make_float2(a.y, a.x), make_float2(w.y, -w.y))));
 }
-/* a * (c - i s) with compile-time style constants */
-FFT_HD cf32 mul_cs(cf32 a, float c, float s) { return mul_conj(a, cf32{c, s}); }
+/* a * w (no conjugation) */
+FFT_HD cf32 mul_cplx(cf32 a, cf32 w)
+{
+    return c2(__ffma2_rn(f2(a), make_float2(w.x, w.x), __fmul2_rn(make_float2(a.y, a.x), make_float2(-w.y, w.y))));
+}
+FFT_HD cf32 cscale(cf32 a, float s) { return c2(__fmul2_rn(f2(a), make_float2(s, s))); }
+/* a*s + b */
+FFT_HD cf32 caxpy(cf32 a, float s, cf32 b) { return c2(__ffma2_rn(f2(a), make_float2(s, s), f2(b))); }
+#else
+FFT_HD cf32 cadd(cf32 a, cf32 b) { return {a.x + b.x, a.y + b.y}; }
+FFT_HD cf32 csub(cf32 a, cf32 b) { return {a.x - b.x, a.y - b.y}; }
+FFT_HD cf32 cadd_mi(cf32 a, cf32 b) { return {a.x + b.y, a.y - b.x}; }
+FFT_HD cf32 cadd_pi(cf32 a, cf32 b) { return {a.x - b.y, a.y + b.x}; }
+FFT_HD cf32 mul_conj(cf32 a, cf32 w) { return {a.x * w.x + a.y * w.y, a.y * w.x - a.x * w.y}; }
+FFT_HD cf32 mul_cplx(cf32 a, cf32 w) { return {a.x * w.x - a.y * w.y, a.y * w.x + a.x * w.y}; }
+FFT_HD cf32 cscale(cf32 a, float s) { return {a.x * s, a.y * s}; }
+FFT_HD cf32 caxpy(cf32 a, float s, cf32 b) { return {a.x * s + b.x, a.y * s + b.y}; }
+#endif
+/* a * (-i) and a * (+i) */
+FFT_HD cf32 mul_mi(cf32 a) { return {a.y, -a.x}; }
+FFT_HD cf32 mul_pi(cf32 a) { return {-a.y, a.x}; }
 
-template <int R> struct DftF32;
+/* cos(2*pi*k/128), k = 0..32; the other three quadrants follow by symmetry */
+FFT_HD constexpr float cos128_q(int k)
+{
+    constexpr float t[33] = {
+        1.000000000e+00f, 9.987954562e-01f, 9.951847267e-01f, 9.891765100e-01f,
+        9.807852804e-01f, 9.700312532e-01f, 9.569403357e-01f, 9.415440652e-01f,
+        9.238795325e-01f, 9.039892931e-01f, 8.819212643e-01f, 8.577286100e-01f,
+        8.314696123e-01f, 8.032075315e-01f, 7.730104534e-01f, 7.409511254e-01f,
+        7.071067812e-01f, 6.715589548e-01f, 6.343932842e-01f, 5.956993045e-01f,
+        5.555702330e-01f, 5.141027442e-01f, 4.713967368e-01f, 4.275550934e-01f,
+        3.826834324e-01f, 3.368898534e-01f, 2.902846773e-01f, 2.429801799e-01f,
+        1.950903220e-01f, 1.467304745e-01f, 9.801714033e-02f, 4.906767433e-02f,
+        0.000000000e+00f};
+    return t[k];
+}
+/* cos / sin of 2*pi*k/128 for any integer k >= 0 */
+FFT_HD constexpr float cos128(int k)
+{
+    k &= 127;
+    return k <= 32 ? cos128_q(k) : (k <= 64 ? -cos128_q(64 - k) : (k <= 96 ? -cos128_q(k - 64) : cos128_q(128 - k)));
+}
+FFT_HD constexpr float sin128(int k) { return cos128(k + 96); }   /* sin(x) = cos(x - pi/2) = cos(x + 3*pi/2) */
 
-template <> struct DftF32<2> {
-    static FFT_HD void run(cf32 *x)
+/* x * w_R^K,  w_R = exp(-2*pi*i/R),  K and R compile-time (R divides 128) */
+template <int R, int K> FFT_HD cf32 mul_wconst(cf32 x)
+{
+    constexpr int k = ((K % R) + R) % R;
+    if (k == 0) return x;
+    if (4 * k == R) return mul_mi(x);
+    if (2 * k == R) return {-x.x, -x.y};
+    if (4 * k == 3 * R) return mul_pi(x);
+    constexpr float c = cos128(k * (128 / R)), s = sin128(k * (128 / R));
+    return mul_conj(x, cf32{c, s});
+}
+
+/* position of output t inside the array after the in-place recursive DIF below */
+FFT_HD constexpr int dft_pos(int R, int t) { return R <= 4 ? t : (R / 4) * (t % 4) + dft_pos(R / 4, t / 4); }
+/* twiddle values a post-twiddled radix-R butterfly reads: 3 per radix-4 level (+ R-1 at the base) */
+FFT_HD constexpr int dft_tw_slots(int R) { return R <= 4 ? R - 1 : 3 + dft_tw_slots(R / 4); }
+
+FFT_HD void dft4(cf32 &x0, cf32 &x1, cf32 &x2, cf32 &x3)
+{
+    cf32 a0 = cadd(x0, x2), a1 = csub(x0, x2), a2 = cadd(x1, x3), a3 = csub(x1, x3);
+    x0 = cadd(a0, a2);
+    x2 = csub(a0, a2);
+    x1 = cadd_mi(a1, a3);
+    x3 = cadd_pi(a1, a3);
+}
+
+/*
+ * In-place radix-R DIF butterfly on x[OFF + STR*q], q < R, optionally followed by the
+ * Stockham post-twiddle  out[t] *= W^(e*t)  (TW = true), factored level by level:
+ * with q = q1 + (R/4) q2 and t = r2 + 4 t2,
+ *      out[t] = DFT_{R/4} over q1 { w_R^(q1 r2) * W^(e r2) * DFT_4 over q2 { x } } [t2] * W^(4 e t2)
+ * so each radix-4 level needs only W^(e'), W^(2e'), W^(3e') (e' = 4^level * e) -- the three
+ * twiddles the reference's radix-4/8 stages read per butterfly (arm_cfft_radix8_f32.c:149-287)
+ * -- instead of R-1 distinct table entries: 9 loads for R = 64 instead of 63.
+ * tw[s] = the s-th value of that list (Pass::fill order).  Output t ends up at dft_pos(R, t).
+ */
+template <int R, int OFF, int STR, bool TW> struct DftRec {
+    static FFT_HD void run(cf32 *x, const cf32 *tw)
     {
-        cf32 a = x[0], b = x[1];
-        x[0] = cadd(a, b);
-        x[1] = csub(a, b);
+        constexpr int Q = R / 4;
+#pragma unroll
+        for (int q1 = 0; q1 < Q; q1++)
+            dft4(x[OFF + STR * q1], x[OFF + STR * (q1 + Q)], x[OFF + STR * (q1 + 2 * Q)], x[OFF + STR * (q1 + 3 * Q)]);
+        step2<1>(x, tw);
+        step2<2>(x, tw);
+        step2<3>(x, tw);
+        DftRec<Q, OFF, STR, TW>::run(x, tw + 3);
+        DftRec<Q, OFF + STR * Q, STR, TW>::run(x, tw + 3);
+        DftRec<Q, OFF + STR * 2 * Q, STR, TW>::run(x, tw + 3);
+        DftRec<Q, OFF + STR * 3 * Q, STR, TW>::run(x, tw + 3);
+    }
+    template <int R2> static FFT_HD void step2(cf32 *x, const cf32 *tw) { qloop<R2, 0>(x, tw); }
+    template <int R2, int Q1> static FFT_HD void qloop(cf32 *x, const cf32 *tw)
+    {
+        constexpr int Q = R / 4;
+        if constexpr (Q1 < Q) {
+            cf32 v = mul_wconst<R, Q1 * R2>(x[OFF + STR * (Q1 + R2 * Q)]);
+            if constexpr (TW) v = mul_conj(v, tw[R2 - 1]);
+            x[OFF + STR * (Q1 + R2 * Q)] = v;
+            qloop<R2, Q1 + 1>(x, tw);
+        }
     }
 };
-
-template <> struct DftF32<4> {
-    static FFT_HD void run(cf32 *x) { run(x[0], x[1], x[2], x[3]); }
-    static FFT_HD void run(cf32 &x0, cf32 &x1, cf32 &x2, cf32 &x3)
+template <int OFF, int STR, bool TW> struct DftRec<4, OFF, STR, TW> {
+    static FFT_HD void run(cf32 *x, const cf32 *tw)
     {
-        cf32 a0 = cadd(x0, x2), a1 = csub(x0, x2), a2 = cadd(x1, x3), a3 = csub(x1, x3);
-        x0 = cadd(a0, a2);
-        x2 = csub(a0, a2);
-        x1 = {a1.x + a3.y, a1.y - a3.x};
-        x3 = {a1.x - a3.y, a1.y + a3.x};
+        dft4(x[OFF], x[OFF + STR], x[OFF + 2 * STR], x[OFF + 3 * STR]);
+        if constexpr (TW) {
+            x[OFF + STR] = mul_conj(x[OFF + STR], tw[0]);
+            x[OFF + 2 * STR] = mul_conj(x[OFF + 2 * STR], tw[1]);
+            x[OFF + 3 * STR] = mul_conj(x[OFF + 3 * STR], tw[2]);
+        }
     }
 };
-
-template <> struct DftF32<8> {
-    static FFT_HD void run(cf32 *x)
+template <int OFF, int STR, bool TW> struct DftRec<2, OFF, STR, TW> {
+    static FFT_HD void run(cf32 *x, const cf32 *tw)
     {
-        const float h = 0.70710678118654752f;
-        cf32 b0 = cadd(x[0], x[4]), c0 = csub(x[0], x[4]);
-        cf32 b1 = cadd(x[1], x[5]), c1 = csub(x[1], x[5]);
-        cf32 b2 = cadd(x[2], x[6]), c2 = csub(x[2], x[6]);
-        cf32 b3 = cadd(x[3], x[7]), c3 = csub(x[3], x[7]);
-        c1 = {(c1.x + c1.y) * h, (c1.y - c1.x) * h};       /* * w8^1 */
-        c2 = mul_mi(c2);                                    /* * w8^2 */
-        c3 = {(c3.y - c3.x) * h, -(c3.x + c3.y) * h};      /* * w8^3 */
-        DftF32<4>::run(b0, b1, b2, b3);
-        DftF32<4>::run(c0, c1, c2, c3);
-        x[0] = b0; x[2] = b1; x[4] = b2; x[6] = b3;
-        x[1] = c0; x[3] = c1; x[5] = c2; x[7] = c3;
+        cf32 a = x[OFF], b = x[OFF + STR];
+        x[OFF] = cadd(a, b);
+        x[OFF + STR] = csub(a, b);
+        if constexpr (TW) x[OFF + STR] = mul_conj(x[OFF + STR], tw[0]);
     }
 };
-
-template <> struct DftF32<16> {
-    static FFT_HD void run(cf32 *x)
-    {
-        const float h = 0.70710678118654752f, c1 = 0.92387953251128674f, s1 = 0.38268343236508977f;
-        /* step 1: four DFT4 over q2 for each q1 (elements q1 + 4 q2) */
-        DftF32<4>::run(x[0], x[4], x[8], x[12]);
-        DftF32<4>::run(x[1], x[5], x[9], x[13]);
-        DftF32<4>::run(x[2], x[6], x[10], x[14]);
-        DftF32<4>::run(x[3], x[7], x[11], x[15]);
-        /* now x[q1 + 4 r2] holds z[q1][r2]; multiply by w16^(q1*r2) */
-        x[5]  = mul_cs(x[5], c1, s1);                        /* 1 */
-        x[9]  = {(x[9].x + x[9].y) * h, (x[9].y - x[9].x) * h};      /* 2 */
-        x[13] = mul_cs(x[13], s1, c1);                       /* 3 */
-        x[6]  = {(x[6].x + x[6].y) * h, (x[6].y - x[6].x) * h};      /* 2 */
-        x[10] = mul_mi(x[10]);                               /* 4 */
-        x[14] = {(x[14].y - x[14].x) * h, -(x[14].x + x[14].y) * h}; /* 6 */
-        x[7]  = mul_cs(x[7], s1, c1);                        /* 3 */
-        x[11] = {(x[11].y - x[11].x) * h, -(x[11].x + x[11].y) * h}; /* 6 */
-        x[15] = mul_cs(x[15], -c1, -s1);                     /* 9 */
-        /* step 2: for each r2, DFT4 over q1 -> outputs t = r2 + 4 t2 */
-        DftF32<4>::run(x[0], x[1], x[2], x[3]);
-        DftF32<4>::run(x[4], x[5], x[6], x[7]);
-        DftF32<4>::run(x[8], x[9], x[10], x[11]);
-        DftF32<4>::run(x[12], x[13], x[14], x[15]);
-        /* x[4 r2 + t2] = y[r2 + 4 t2]: transpose to natural output order */
-        cf32 t;
-        t = x[1];  x[1]  = x[4];  x[4]  = t;
-        t = x[2];  x[2]  = x[8];  x[8]  = t;
-        t = x[3];  x[3]  = x[12]; x[12] = t;
-        t = x[6];  x[6]  = x[9];  x[9]  = t;
-        t = x[7];  x[7]  = x[13]; x[13] = t;
-        t = x[11]; x[11] = x[14]; x[14] = t;
-    }
+template <int OFF, int STR, bool TW> struct DftRec<1, OFF, STR, TW> {
+    static FFT_HD void run(cf32 *, const cf32 *) {}
 };
+
+/* natural-order radix-R butterfly: x[t] = DFT_R(x)[t] (* W^(e t) when TW) */
+template <int R, bool TW> FFT_HD void dft_f32(cf32 *x, const cf32 *tw)
+{
+    DftRec<R, 0, 1, TW>::run(x, tw);
+    if (R > 4) {
+        cf32 y[R];
+#pragma unroll
+        for (int t = 0; t < R; t++) y[t] = x[dft_pos(R, t)];
+#pragma unroll
+        for (int t = 0; t < R; t++) x[t] = y[t];
+    }
+}
 
 struct ArithF32 {
     typedef cf32 elem;

@@ -136,34 +136,50 @@ template <class PL, bool INV, bool STAGED = false> struct CfftBody {
 /* ------------------------------------------------------------------ RFFT (f32 only) */
 
 /* split stage for one bin: A = X[k], B = X[Nh-k], tw = twiddleCoef_rfft[k] = (sin,cos)
- * (arm_rfft_fast_f32.c:372-395) */
+ * (arm_rfft_fast_f32.c:372-395):
+ *   out = 0.5 * ( A + conj(B) + d.x * (tw.x, tw.y) + d.y * (tw.y, -tw.x) ),  d = (B.x - A.x, B.y + A.y) */
 FFT_HD cf32 rfft_split(cf32 A, cf32 B, cf32 tw)
 {
-    float t1a = B.x - A.x, t1b = B.y + A.y;
-    float p0 = tw.x * t1a, p1 = tw.y * t1a, p2 = tw.x * t1b, p3 = tw.y * t1b;
-    return {0.5f * (A.x + B.x + p0 + p3), 0.5f * (A.y - B.y + p1 - p2)};
+    const cf32 s = cadd(A, cf32{B.x, -B.y});
+    const cf32 d = cadd(B, cf32{-A.x, A.y});
+    const cf32 t = caxpy(mul_mi(tw), d.y, caxpy(tw, d.x, s));
+    return cscale(t, 0.5f);
 }
-/* merge stage for one bin (arm_rfft_fast_f32.c:436-455) */
+/* merge stage for one bin (arm_rfft_fast_f32.c:436-455):
+ *   out = 0.5 * ( A + conj(B) - d.x * (tw.x, -tw.y) - d.y * (tw.y, tw.x) ),  d = (A.x - B.x, A.y + B.y) */
 FFT_HD cf32 rfft_merge(cf32 A, cf32 B, cf32 tw)
 {
-    float t1a = A.x - B.x, t1b = A.y + B.y;
-    float r = tw.x * t1a, s = tw.y * t1b, t = tw.y * t1a, u = tw.x * t1b;
-    return {0.5f * (A.x + B.x - r - s), 0.5f * (A.y - B.y + t - u)};
+    const cf32 s = cadd(A, cf32{B.x, -B.y});
+    const cf32 d = cadd(A, cf32{-B.x, B.y});
+    const cf32 t = caxpy(cf32{tw.y, tw.x}, -d.y, caxpy(cf32{tw.x, -tw.y}, -d.x, s));
+    return cscale(t, 0.5f);
 }
+/* twiddleCoef_rfft entry of bin k + e*NBF from the entry of bin k: the angle grows by
+ * e*pi/R = 2*pi*e*(64/R)/128, a compile-time rotation of the (sin, cos) pair */
+template <int R, int E_> FFT_HD cf32 rfft_tw_rot(cf32 tw)
+{
+    if (E_ == 0) return tw;
+    constexpr float c = cos128(E_ * (64 / R)), sn = sin128(E_ * (64 / R));
+    return caxpy(mul_mi(tw), sn, cscale(tw, c));       /* (s c + c' sn , c' c - s sn) with tw = (s, c') */
+}
+/* entry of bin Nh - k from the entry of bin k: (sin, cos)(pi - x) = (sin x, -cos x) */
+FFT_HD cf32 rfft_tw_mirror(cf32 tw) { return {tw.x, -tw.y}; }
 
-/* Requires: the pass next to the real side is a Mirror8 pass with 2 butterflies per thread
- * (E == 16), so thread i holds bins {j + t*NBF} and {NBF - j + t*NBF}: every (k, Nh-k) pair is
- * thread-local.  Slot m of butterfly 0 pairs with slot 15-m (thread 0: butterfly 0 pairs
- * t <-> 8-t with t = 0 the packed DC/Nyquist bin, butterfly 1 pairs t <-> 7-t). */
+/* Requires: the pass next to the real side is a Mirror pass, so thread i holds its butterflies
+ * in pairs (p, NBF - p): slot e of the first pairs with slot R-1-e of the second, i.e. every
+ * (k, Nh-k) pair is thread-local and shares one rfft twiddle (up to the mirror sign).  Pair 0 of
+ * thread 0 is (0, NBF/2): butterfly 0 pairs e <-> R-e (e = 0 is the packed DC/Nyquist bin,
+ * e = R/2 pairs with itself), butterfly NBF/2 pairs e <-> R-1-e.  One table entry is LOADED per
+ * butterfly pair; the entries of the other bins are compile-time rotations of it. */
 template <class PL, bool STAGED = false> struct RfftFwdBody {
     typedef Engine<PL> Eng;
     typedef typename Eng::Regs Regs;
     typedef cf32 elem;
-    static constexpr int NP = PL::NP, E = PL::E, N = PL::N;   /* N = complex length = real length / 2 */
+    static constexpr int NP = PL::NP, E = PL::E, N = PL::N, T = PL::T;   /* N = complex length = real length / 2 */
     static constexpr int kPhases = PhaseCount<NP>::value;
     typedef typename PassOf<PL, NP - 1>::type PL_LAST;
-    static_assert(PL_LAST::kMirror && E == 16, "forward rfft needs a trailing Mirror8 pass, 16 points per thread");
-    static constexpr int NBF = N / 8;
+    static constexpr int R = PL_LAST::R, NBF = N / R, NB = E / R;
+    static_assert(PL_LAST::kMirror && NB % 2 == 0, "forward rfft needs a trailing Mirror pass with an even number of butterflies per thread");
 
     struct Args {
         const cf32 *in;      /* real frame viewed as N complex */
@@ -189,28 +205,52 @@ template <class PL, bool STAGED = false> struct RfftFwdBody {
             for (int e = 0; e < PS::R; e++)
                 r.v[b * PS::R + e] = ld_in<STAGED>(a.in + Eng::template in_index<0>(i, b, e));
     }
+    template <int E0, int E1> static FFT_HD void pair_loop(const cf32 *A, const cf32 *B, const Args &a, int p, cf32 tw0)
+    {
+        /* bins k0 = p + e*NBF (in A) and Nh - k0 = (NBF - p) + (R-1-e)*NBF (in B), e = E0..E1-1 */
+        if constexpr (E0 < E1) {
+            const cf32 tw = rfft_tw_rot<R, E0>(tw0);
+            const int k0 = p + E0 * NBF;
+            st_stream(a.out + k0, rfft_split(A[E0], B[R - 1 - E0], tw));
+            st_stream(a.out + (N - k0), rfft_split(B[R - 1 - E0], A[E0], rfft_tw_mirror(tw)));
+            pair_loop<E0 + 1, E1>(A, B, a, p, tw0);
+        }
+    }
+    /* butterfly 0 of thread 0: bins e*NBF pair with (R-e)*NBF */
+    template <int E0> static FFT_HD void self_loop0(const cf32 *A, const Args &a, cf32 tw0)
+    {
+        if constexpr (E0 <= R / 2) {
+            const cf32 tw = rfft_tw_rot<R, E0>(tw0);
+            const int k0 = E0 * NBF;
+            st_stream(a.out + k0, rfft_split(A[E0], A[R - E0], tw));
+            if (E0 != R / 2) st_stream(a.out + (N - k0), rfft_split(A[R - E0], A[E0], rfft_tw_mirror(tw)));
+            self_loop0<E0 + 1>(A, a, tw0);
+        }
+    }
+    /* butterfly NBF/2 of thread 0: bins NBF/2 + e*NBF pair with NBF/2 + (R-1-e)*NBF */
+    template <int E0> static FFT_HD void self_loop1(const cf32 *B, const Args &a, cf32 tw0)
+    {
+        if constexpr (E0 < R / 2) {
+            const cf32 tw = rfft_tw_rot<R, E0>(tw0);
+            const int k0 = NBF / 2 + E0 * NBF;
+            st_stream(a.out + k0, rfft_split(B[E0], B[R - 1 - E0], tw));
+            st_stream(a.out + (N - k0), rfft_split(B[R - 1 - E0], B[E0], rfft_tw_mirror(tw)));
+            self_loop1<E0 + 1>(B, a, tw0);
+        }
+    }
     static FFT_HD void split_store(const Regs &r, const Args &a, int i)
     {
-        if (i != 0) {
-            const int j0 = i, j1 = NBF - i;
 #pragma unroll
-            for (int t = 0; t < 8; t++) {
-                const int k0 = j0 + t * NBF, k1 = j1 + t * NBF;
-                st_stream(a.out + k0, rfft_split(r.v[t], r.v[15 - t], a.twr[k0]));
-                st_stream(a.out + k1, rfft_split(r.v[8 + t], r.v[7 - t], a.twr[k1]));
-            }
-        } else {
-            const cf32 X0 = r.v[0];
-            st_stream(a.out + 0, cf32{X0.x + X0.y, X0.x - X0.y});       /* rfft_fast_f32.c:337-352 */
-#pragma unroll
-            for (int t = 1; t < 8; t++) {
-                const int k0 = t * NBF;
-                st_stream(a.out + k0, rfft_split(r.v[t], r.v[8 - t], a.twr[k0]));
-            }
-#pragma unroll
-            for (int t = 0; t < 8; t++) {
-                const int k1 = NBF / 2 + t * NBF;
-                st_stream(a.out + k1, rfft_split(r.v[8 + t], r.v[15 - t], a.twr[k1]));
+        for (int m = 0; m < NB / 2; m++) {
+            const int p = i + T * m;
+            const cf32 *A = &r.v[(2 * m) * R], *B = &r.v[(2 * m + 1) * R];
+            if (m != 0 || i != 0) {
+                pair_loop<0, R>(A, B, a, p, a.twr[p]);
+            } else {
+                const cf32 X0 = A[0];
+                st_stream(a.out + 0, cf32{X0.x + X0.y, X0.x - X0.y});       /* rfft_fast_f32.c:337-352 */
+                self_loop0<1>(A, a, a.twr[0]);
+                self_loop1<0>(B, a, a.twr[NBF / 2]);
             }
         }
     }
@@ -244,10 +284,10 @@ template <class PL, bool STAGED = false> struct RfftInvBody {
     typedef Engine<PL> Eng;
     typedef typename Eng::Regs Regs;
     typedef cf32 elem;
-    static constexpr int NP = PL::NP, E = PL::E, N = PL::N;
+    static constexpr int NP = PL::NP, E = PL::E, N = PL::N, T = PL::T;
     static constexpr int kPhases = PhaseCount<NP>::value;
-    static_assert(PL::P0::kMirror && E == 16, "inverse rfft needs a leading Mirror8 pass, 16 points per thread");
-    static constexpr int NBF = N / 8;
+    static constexpr int R = PL::P0::R, NBF = N / R, NB = E / R;
+    static_assert(PL::P0::kMirror && NB % 2 == 0, "inverse rfft needs a leading Mirror pass with an even number of butterflies per thread");
 
     struct Args {
         const cf32 *in;      /* packed spectrum, N complex */
@@ -268,32 +308,54 @@ template <class PL, bool STAGED = false> struct RfftInvBody {
     /* merge (rfft_fast_f32.c:405-462) then conjugate for the inverse CFFT (cfft_f32.c:1252-1261) */
     static FFT_HD cf32 mconj(cf32 z) { return {z.x, -z.y}; }
 
+    template <int E0, int E1> static FFT_HD void pair_loop(cf32 *A, cf32 *B, cf32 tw0)
+    {
+        if constexpr (E0 < E1) {
+            const cf32 tw = rfft_tw_rot<R, E0>(tw0);
+            const cf32 ga = A[E0], gb = B[R - 1 - E0];
+            A[E0] = mconj(rfft_merge(ga, gb, tw));
+            B[R - 1 - E0] = mconj(rfft_merge(gb, ga, rfft_tw_mirror(tw)));
+            pair_loop<E0 + 1, E1>(A, B, tw0);
+        }
+    }
+    template <int E0> static FFT_HD void self_loop0(cf32 *A, cf32 tw0)
+    {
+        if constexpr (E0 <= R / 2) {
+            const cf32 tw = rfft_tw_rot<R, E0>(tw0);
+            const cf32 ga = A[E0], gb = A[R - E0];
+            A[E0] = mconj(rfft_merge(ga, gb, tw));
+            if (E0 != R / 2) A[R - E0] = mconj(rfft_merge(gb, ga, rfft_tw_mirror(tw)));
+            self_loop0<E0 + 1>(A, tw0);
+        }
+    }
+    template <int E0> static FFT_HD void self_loop1(cf32 *B, cf32 tw0)
+    {
+        if constexpr (E0 < R / 2) {
+            const cf32 tw = rfft_tw_rot<R, E0>(tw0);
+            const cf32 ga = B[E0], gb = B[R - 1 - E0];
+            B[E0] = mconj(rfft_merge(ga, gb, tw));
+            B[R - 1 - E0] = mconj(rfft_merge(gb, ga, rfft_tw_mirror(tw)));
+            self_loop1<E0 + 1>(B, tw0);
+        }
+    }
     static FFT_HD void merge_load(Regs &r, const Args &a, int i)
     {
-        cf32 g[16];
-        if (i != 0) {
-            const int j0 = i, j1 = NBF - i;
 #pragma unroll
-            for (int t = 0; t < 8; t++) {
-                g[t] = ld_in<STAGED>(a.in + j0 + t * NBF);
-                g[8 + t] = ld_in<STAGED>(a.in + j1 + t * NBF);
+        for (int b = 0; b < NB; b++)
+#pragma unroll
+            for (int e = 0; e < R; e++) r.v[b * R + e] = ld_in<STAGED>(a.in + Eng::template in_index<0>(i, b, e));
+#pragma unroll
+        for (int m = 0; m < NB / 2; m++) {
+            const int p = i + T * m;
+            cf32 *A = &r.v[(2 * m) * R], *B = &r.v[(2 * m + 1) * R];
+            if (m != 0 || i != 0) {
+                pair_loop<0, R>(A, B, a.twr[p]);
+            } else {
+                const cf32 g0 = A[0];
+                A[0] = mconj(cf32{0.5f * (g0.x + g0.y), 0.5f * (g0.x - g0.y)});   /* :425-431 */
+                self_loop0<1>(A, a.twr[0]);
+                self_loop1<0>(B, a.twr[NBF / 2]);
             }
-#pragma unroll
-            for (int t = 0; t < 8; t++) {
-                r.v[t] = mconj(rfft_merge(g[t], g[15 - t], a.twr[j0 + t * NBF]));
-                r.v[8 + t] = mconj(rfft_merge(g[8 + t], g[7 - t], a.twr[j1 + t * NBF]));
-            }
-        } else {
-#pragma unroll
-            for (int t = 0; t < 8; t++) {
-                g[t] = ld_in<STAGED>(a.in + t * NBF);
-                g[8 + t] = ld_in<STAGED>(a.in + NBF / 2 + t * NBF);
-            }
-            r.v[0] = mconj(cf32{0.5f * (g[0].x + g[0].y), 0.5f * (g[0].x - g[0].y)});   /* :425-431 */
-#pragma unroll
-            for (int t = 1; t < 8; t++) r.v[t] = mconj(rfft_merge(g[t], g[8 - t], a.twr[t * NBF]));
-#pragma unroll
-            for (int t = 0; t < 8; t++) r.v[8 + t] = mconj(rfft_merge(g[8 + t], g[15 - t], a.twr[NBF / 2 + t * NBF]));
         }
     }
     static FFT_HD void gstore(const Regs &r, const Args &a, int i)

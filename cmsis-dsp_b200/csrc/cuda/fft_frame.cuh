@@ -35,36 +35,46 @@ namespace b200fft {
 
 /* ---------------------------------------------------------------- pass descriptors */
 
-/* f32 pass: true radix-R butterfly, external twiddles from the N-entry (cos,+sin) table */
+/* f32 pass: radix-R butterfly with the post-twiddle factored per radix-4 level (DftRec),
+ * twiddles from the N-entry (cos,+sin) table of the reference */
 template <int R_> struct PassF32 {
     static constexpr int R = R_;
     static constexpr bool kMirror = false;
     typedef cf32 telem;
     static FFT_HD int out_index(int e) { return e; }
     /* twiddle slots per butterfly in the pass-ordered table (none on the last pass: W^0) */
-    static constexpr int slots(bool lastPass) { return lastPass ? 0 : R - 1; }
-    /* slot t-1 of butterfly j = W_N^(s*p*t), p = j / S: entry s*p*t of the reference table */
+    static constexpr int slots(bool lastPass) { return lastPass ? 0 : dft_tw_slots(R); }
+    /* butterfly j, e = S*(j/S): level l reads W^(4^l e m), m = 1..3; the base level W^(4^L e t) */
     template <int N, int S> static void fill(const cf32 *base, cf32 *out, bool lastPass)
     {
         constexpr int NBF = N / R;
         if (lastPass) return;
-        for (int t = 1; t < R; t++)
-            for (int j = 0; j < NBF; j++) out[(t - 1) * NBF + j] = base[S * (j / S) * t];
+        for (int j = 0; j < NBF; j++) {
+            int s = 0, r = R;
+            long ec = (long)S * (j / S);
+            for (; r > 4; r /= 4, ec = (ec * 4) % N)
+                for (int m = 1; m <= 3; m++) out[(s++) * NBF + j] = base[(ec * m) % N];
+            for (int t = 1; t < r; t++) out[(s++) * NBF + j] = base[(ec * t) % N];
+        }
     }
     template <bool INV, int N, bool LASTPASS>
     static FFT_HD void compute(cf32 *x, const cf32 *__restrict__ twp, int j)
     {
         constexpr int NBF = N / R;
-        DftF32<R>::run(x);
-        if (!LASTPASS) {
+        if constexpr (LASTPASS) {
+            dft_f32<R, false>(x, nullptr);
+        } else {
+            cf32 w[dft_tw_slots(R)];
 #pragma unroll
-            for (int t = 1; t < R; t++) x[t] = mul_conj(x[t], twp[(t - 1) * NBF + j]);
+            for (int s = 0; s < dft_tw_slots(R); s++) w[s] = twp[s * NBF + j];
+            dft_f32<R, true>(x, w);
         }
     }
 };
-/* radix-8 f32 pass whose two butterflies per thread are a mirror pair (j, N/8 - j):
- * used next to the real side of arm_rfft_fast_f32 so split/merge stay thread-local */
-struct PassF32Mirror8 : PassF32<8> { static constexpr bool kMirror = true; };
+/* pass whose butterflies come in mirror pairs (j, N/R - j) per thread: used next to the real
+ * side of arm_rfft_fast_f32 so split/merge stay thread-local */
+template <int R_> struct PassF32Mirror : PassF32<R_> { static constexpr bool kMirror = true; };
+typedef PassF32Mirror<8> PassF32Mirror8;
 
 /* fixed-point pass: one or two of the reference's DIF stages, executed back to back on the
  * R = ra*rb points held by the thread. */
@@ -153,7 +163,12 @@ struct Plan {
     static_assert(E % P0::R == 0 && E % P1::R == 0 && E % P2::R == 0, "E must be a multiple of every radix");
     /* padded exchange layout: PADB extra elements after every 2^PADA elements */
     static FFT_HD int pad(int i) { return PADB_ ? (i + ((i >> PADA_) * PADB_)) : i; }
-    static constexpr int kFrameElems = PADB_ ? (N + ((N - 1) >> PADA_) * PADB_ + PADB_) : N;
+    static constexpr int kPadded = PADB_ ? (N + ((N - 1) >> PADA_) * PADB_ + PADB_) : N;
+    /* frames that share a shared-memory wavefront (T lanes each) start T elements apart modulo the
+     * wavefront width, so their lanes land in different banks */
+    static constexpr int kLanesPerWave = 128 / (int)sizeof(typename ARITH_::elem);
+    static constexpr int kFrameElems = (PADB_ && T_ < kLanesPerWave)
+        ? kPadded + ((T_ - kPadded % kLanesPerWave) + kLanesPerWave) % kLanesPerWave : kPadded;
     static constexpr int kSmemBytes = (NP > 1) ? F * kFrameElems * (int)sizeof(typename ARITH_::elem) : 0;
     static constexpr int kThreads = T * F;
     /* pass-ordered twiddle table: pass p owns slots_p * (N / R_p) entries starting at kTwOff<p> */
@@ -175,11 +190,13 @@ template <class PL> struct PassOf<PL, 0> { typedef typename PL::P0 type; static 
 template <class PL> struct PassOf<PL, 1> { typedef typename PL::P1 type; static constexpr int S = PL::S1, TWOFF = PL::kTw0; };
 template <class PL> struct PassOf<PL, 2> { typedef typename PL::P2 type; static constexpr int S = PL::S2, TWOFF = PL::kTw0 + PL::kTw1; };
 
-/* butterfly index handled by thread i as its b-th butterfly of a pass with NBF butterflies */
+/* butterfly index handled by thread i as its b-th butterfly of a pass with NBF butterflies.
+ * Mirror passes hand out PAIRS (p, NBF - p), p = i + T*(b/2) in [0, NBF/2); pair 0 is (0, NBF/2). */
 template <bool MIRROR, int T, int NBF> FFT_HD int bfly_index(int i, int b)
 {
     if (!MIRROR) return i + T * b;
-    return b == 0 ? i : (i == 0 ? NBF / 2 : NBF - i);
+    const int p = i + T * (b >> 1);
+    return (b & 1) ? (p == 0 ? NBF / 2 : NBF - p) : p;
 }
 
 /* ---------------------------------------------------------------- engine */

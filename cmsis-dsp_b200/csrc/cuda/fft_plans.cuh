@@ -24,40 +24,46 @@ typedef PassF32<2> F2;
 typedef PassF32<4> F4;
 typedef PassF32<8> F8;
 typedef PassF32<16> F16;
-typedef PassF32Mirror8 M8;
+typedef PassF32<32> F32;
+typedef PassF32<64> F64;
+typedef PassF32Mirror<8> M8;
+typedef PassF32Mirror<16> M16;
+typedef PassF32Mirror<32> M32;
 
-/* ---- f32 complex ---- */
+/* ---- f32 complex ----
+ * N >= 512: at most TWO passes (one shared-memory exchange): 32 or 64 points per thread, so a
+ * frame belongs to one warp (two for N = 4096) and the exchange needs only __syncwarp(). */
 template <int N> struct PlanCfftF32;
 template <> struct PlanCfftF32<16>   { typedef Plan<ArithF32, 16, 1, 128, 0, 0, F16> type; };
 template <> struct PlanCfftF32<32>   { typedef Plan<ArithF32, 32, 2, 64, 3, 1, F4, F8> type; };
 template <> struct PlanCfftF32<64>   { typedef Plan<ArithF32, 64, 4, 32, 3, 1, F8, F8> type; };
 template <> struct PlanCfftF32<128>  { typedef Plan<ArithF32, 128, 8, 16, 4, 1, F16, F8> type; };
 template <> struct PlanCfftF32<256>  { typedef Plan<ArithF32, 256, 16, 8, 4, 1, F16, F16> type; };
-template <> struct PlanCfftF32<512>  { typedef Plan<ArithF32, 512, 32, 4, 4, 1, F16, F8, F4> type; };
-template <> struct PlanCfftF32<1024> { typedef Plan<ArithF32, 1024, 64, 2, 4, 1, F16, F8, F8> type; };
-template <> struct PlanCfftF32<2048> { typedef Plan<ArithF32, 2048, 128, 1, 4, 1, F16, F16, F8> type; };
-template <> struct PlanCfftF32<4096> { typedef Plan<ArithF32, 4096, 256, 1, 4, 1, F16, F16, F16> type; };
+template <> struct PlanCfftF32<512>  { typedef Plan<ArithF32, 512, 16, 8, 5, 1, F32, F16> type; };
+template <> struct PlanCfftF32<1024> { typedef Plan<ArithF32, 1024, 32, 4, 5, 1, F32, F32> type; };
+template <> struct PlanCfftF32<2048> { typedef Plan<ArithF32, 2048, 32, 2, 6, 1, F64, F32> type; };
+template <> struct PlanCfftF32<4096> { typedef Plan<ArithF32, 4096, 64, 1, 6, 1, F64, F64> type; };
 
 /* ---- rfft_fast_f32: NC = complex length = real length / 2 ---- */
-template <int NC> struct PlanRfftFwd;   /* trailing Mirror8 */
+template <int NC> struct PlanRfftFwd;   /* trailing Mirror pass */
 template <> struct PlanRfftFwd<16>   { typedef Plan<ArithF32, 16, 1, 128, 0, 0, F2, M8> type; };
 template <> struct PlanRfftFwd<32>   { typedef Plan<ArithF32, 32, 2, 64, 3, 1, F4, M8> type; };
 template <> struct PlanRfftFwd<64>   { typedef Plan<ArithF32, 64, 4, 32, 3, 1, F8, M8> type; };
 template <> struct PlanRfftFwd<128>  { typedef Plan<ArithF32, 128, 8, 16, 4, 1, F16, M8> type; };
-template <> struct PlanRfftFwd<256>  { typedef Plan<ArithF32, 256, 16, 8, 4, 1, F4, F8, M8> type; };
-template <> struct PlanRfftFwd<512>  { typedef Plan<ArithF32, 512, 32, 4, 4, 1, F4, F16, M8> type; };
-template <> struct PlanRfftFwd<1024> { typedef Plan<ArithF32, 1024, 64, 2, 4, 1, F16, F8, M8> type; };
-template <> struct PlanRfftFwd<2048> { typedef Plan<ArithF32, 2048, 128, 1, 4, 1, F16, F16, M8> type; };
+template <> struct PlanRfftFwd<256>  { typedef Plan<ArithF32, 256, 8, 16, 4, 1, F16, M16> type; };
+template <> struct PlanRfftFwd<512>  { typedef Plan<ArithF32, 512, 16, 8, 5, 1, F32, M16> type; };
+template <> struct PlanRfftFwd<1024> { typedef Plan<ArithF32, 1024, 16, 4, 5, 1, F32, M32> type; };
+template <> struct PlanRfftFwd<2048> { typedef Plan<ArithF32, 2048, 32, 2, 6, 1, F64, M32> type; };
 
-template <int NC> struct PlanRfftInv;   /* leading Mirror8 */
+template <int NC> struct PlanRfftInv;   /* leading Mirror pass */
 template <> struct PlanRfftInv<16>   { typedef Plan<ArithF32, 16, 1, 128, 0, 0, M8, F2> type; };
 template <> struct PlanRfftInv<32>   { typedef Plan<ArithF32, 32, 2, 64, 3, 1, M8, F4> type; };
 template <> struct PlanRfftInv<64>   { typedef Plan<ArithF32, 64, 4, 32, 3, 1, M8, F8> type; };
 template <> struct PlanRfftInv<128>  { typedef Plan<ArithF32, 128, 8, 16, 4, 1, M8, F16> type; };
-template <> struct PlanRfftInv<256>  { typedef Plan<ArithF32, 256, 16, 8, 4, 1, M8, F8, F4> type; };
-template <> struct PlanRfftInv<512>  { typedef Plan<ArithF32, 512, 32, 4, 4, 1, M8, F16, F4> type; };
-template <> struct PlanRfftInv<1024> { typedef Plan<ArithF32, 1024, 64, 2, 4, 1, M8, F8, F16> type; };
-template <> struct PlanRfftInv<2048> { typedef Plan<ArithF32, 2048, 128, 1, 4, 1, M8, F16, F16> type; };
+template <> struct PlanRfftInv<256>  { typedef Plan<ArithF32, 256, 8, 16, 4, 1, M16, F16> type; };
+template <> struct PlanRfftInv<512>  { typedef Plan<ArithF32, 512, 16, 8, 4, 1, M16, F32> type; };
+template <> struct PlanRfftInv<1024> { typedef Plan<ArithF32, 1024, 16, 4, 5, 1, M32, F32> type; };
+template <> struct PlanRfftInv<2048> { typedef Plan<ArithF32, 2048, 32, 2, 5, 1, M32, F64> type; };
 
 /* ---- q31 / q15 ---- */
 template <class AR, int N> struct PlanCfftFix;

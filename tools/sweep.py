@@ -18,9 +18,9 @@ import torch  # noqa: E402
 import cmsisdsp_b200 as cd  # noqa: E402
 
 
-def timed(fn, reps, stream):
+def timed(fn, reps, stream, warm=3):
     cu = cd.cuda()
-    for _ in range(3):
+    for _ in range(warm):
         fn()
     torch.cuda.synchronize()
     t = C.c_void_p()
@@ -36,6 +36,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--mib", type=int, default=1024)
     ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--warm", type=int, default=3)
     ap.add_argument("--ops", default="cfft_f32,cfft_q31,cfft_q15,rfft_fwd,rfft_inv")
     ap.add_argument("--lens", default="16,32,64,128,256,512,1024,2048,4096")
     ap.add_argument("--json", default=None)
@@ -78,7 +79,7 @@ def main():
                 alg = 2 * B * N * 4
                 samples = B * N
                 info = cd.kernel_info(4 if inv else 3, N)
-            ms = timed(fn, args.reps, st)
+            ms = timed(fn, args.reps, st, args.warm)
             gbs = alg / ms / 1e6
             row = dict(op=op, N=N, frames=B, ms=ms, gsamples=samples / ms / 1e6, gbs=gbs, frac=gbs / peak, **info)
             rows.append(row)
