@@ -183,15 +183,27 @@ template <int OFF, int STR, bool TW> struct DftRec<1, OFF, STR, TW> {
 };
 
 /* natural-order radix-R butterfly: x[t] = DFT_R(x)[t] (* W^(e t) when TW) */
+template <int R, int T0> FFT_HD void dft_unpermute(const cf32 *x, cf32 *y)
+{
+    if constexpr (T0 < R) {
+        y[T0] = x[dft_pos(R, T0)];
+        dft_unpermute<R, T0 + 1>(x, y);
+    }
+}
+template <int R, int T0> FFT_HD void dft_copy(const cf32 *y, cf32 *x)
+{
+    if constexpr (T0 < R) {
+        x[T0] = y[T0];
+        dft_copy<R, T0 + 1>(y, x);
+    }
+}
 template <int R, bool TW> FFT_HD void dft_f32(cf32 *x, const cf32 *tw)
 {
     DftRec<R, 0, 1, TW>::run(x, tw);
-    if (R > 4) {
+    if constexpr (R > 4) {
         cf32 y[R];
-#pragma unroll
-        for (int t = 0; t < R; t++) y[t] = x[dft_pos(R, t)];
-#pragma unroll
-        for (int t = 0; t < R; t++) x[t] = y[t];
+        dft_unpermute<R, 0>(x, y);
+        dft_copy<R, 0>(y, x);
     }
 }
 

@@ -25,7 +25,14 @@ template <> FFT_HD ci16 ld_stream<ci16>(const ci16 *p) { short2 v = __ldcs(reint
 FFT_HD void st_stream(cf32 *p, cf32 v) { __stcs(reinterpret_cast<float2 *>(p), make_float2(v.x, v.y)); }
 FFT_HD void st_stream(ci32 *p, ci32 v) { __stcs(reinterpret_cast<int2 *>(p), make_int2(v.x, v.y)); }
 FFT_HD void st_stream(ci16 *p, ci16 v) { __stcs(reinterpret_cast<short2 *>(p), make_short2(v.x, v.y)); }
+/* predicated streaming store: no branch, so the surrounding straight-line code stays one block */
+FFT_HD void st_stream_if(bool pred, cf32 *p, cf32 v)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t@q st.global.cs.v2.f32 [%0], {%1, %2};\n\t}"
+                 ::"l"(p), "f"(v.x), "f"(v.y), "r"((int)pred) : "memory");
+}
 #else
+FFT_HD void st_stream_if(bool pred, cf32 *p, cf32 v) { if (pred) *p = v; }
 template <class V> FFT_HD V ld_stream(const V *p) { return *p; }
 template <class V> FFT_HD void st_stream(V *p, V v) { *p = v; }
 #endif
@@ -47,7 +54,10 @@ template <> struct IsF32<cf32> { static constexpr bool value = true; };
 
 /* ------------------------------------------------------------------ CFFT */
 
-template <class PL, bool INV, bool STAGED = false> struct CfftBody {
+/* PERM: bitReverseFlag == 0, results are scattered through the plan's output permutation
+ * (a compile-time flavour: a run-time test would put a predicated table load and its
+ * scoreboard wait in front of every store of the common natural-order case) */
+template <class PL, bool INV, bool PERM = false, bool STAGED = false> struct CfftBody {
     typedef Engine<PL> Eng;
     typedef typename Eng::A A;
     typedef typename A::elem elem;
@@ -61,7 +71,7 @@ template <class PL, bool INV, bool STAGED = false> struct CfftBody {
         const elem *in;          /* frame base (device or emulated) */
         elem *out;               /* may alias in */
         const elem *tw;          /* pass-ordered twiddle table of this plan (Plan::build_twiddles) */
-        const uint16_t *perm;    /* null => natural order; else destination position of X[k] */
+        const uint16_t *perm;    /* PERM only: destination position of X[k] */
         float scale;             /* f32 inverse: 1/N */
         int shl1;                /* fixed point, N = 2*4^m: final << 1 of every word */
     };
@@ -100,12 +110,48 @@ template <class PL, bool INV, bool STAGED = false> struct CfftBody {
                 } else if (a.shl1) {
                     w = A::shl1(w);                                  /* cfft_q31.c:803-820, cfft_q15.c:810-827 */
                 }
-                const int pos = a.perm ? (int)a.perm[k] : k;
+                int pos = k;
+                if constexpr (PERM) pos = (int)a.perm[k];
                 st_stream(a.out + pos, A::store(w));
             }
     }
     static FFT_HD cf32 scale_conj(cf32 w, float s) { return {w.x * s, -w.y * s}; }
     static FFT_HD ci32 scale_conj(ci32 w, float) { return w; }
+
+    /* phase 0 in two halves, for kernels whose input buffer doubles as the exchange buffer */
+    static constexpr bool kHasPre = false, kHasPost = false;
+    static FFT_HD void set_scratch(Args &, elem *) {}
+    static FFT_HD void pre(const Args &, elem *, int) {}
+    static FFT_HD void post(const Args &, elem *, int) {}
+    static FFT_HD void phase0_in(Regs &r, const Args &a, elem *, int i)
+    {
+        gload(r, a, i);
+        Eng::template compute<0, INV>(r, a.tw, i);
+    }
+    /* table values that do not depend on the frame: loaded before the wait for the frame data */
+    struct Hoist { typename Eng::template TwRegs<0> t0; };
+    static FFT_HD void hoist(Hoist &h, const Args &a, int i) { Eng::template load_tw<0>(h.t0, a.tw, i); }
+    static FFT_HD void phase0_in(Regs &r, const Args &a, elem *, int i, const Hoist &h)
+    {
+        gload(r, a, i);
+        Eng::template compute_pre<0, INV>(r, h.t0);
+    }
+    static FFT_HD void post(const Args &, elem *, int, const Hoist &) {}
+    static FFT_HD void pre(const Args &, elem *, int, const Hoist &) {}
+    static FFT_HD void last_out(Regs &r, const Args &a, int i, const Hoist &) { last_out(r, a, i); }
+    static FFT_HD void phase0_out(const Regs &r, elem *sm, int i) { Eng::template smem_store<0>(r, sm, i); }
+    /* last phase of a two-pass plan */
+    static FFT_HD void last_in(Regs &r, const elem *sm, int i) { Eng::template smem_load<1>(r, sm, i); }
+    static FFT_HD void last_out(Regs &r, const Args &a, int i)
+    {
+        Eng::template compute<1, INV>(r, a.tw, i);
+        gstore(r, a, i);
+    }
+    static FFT_HD void last(Regs &r, const Args &a, elem *sm, int i)
+    {
+        last_in(r, sm, i);
+        last_out(r, a, i);
+    }
 
     template <int PH> static FFT_HD void phase(Regs &r, const Args &a, elem *sm, int i)
     {
@@ -167,26 +213,35 @@ FFT_HD cf32 rfft_tw_mirror(cf32 tw) { return {tw.x, -tw.y}; }
 
 /* Requires: the pass next to the real side is a Mirror pass, so thread i holds its butterflies
  * in pairs (p, NBF - p): slot e of the first pairs with slot R-1-e of the second, i.e. every
- * (k, Nh-k) pair is thread-local and shares one rfft twiddle (up to the mirror sign).  Pair 0 of
- * thread 0 is (0, NBF/2): butterfly 0 pairs e <-> R-e (e = 0 is the packed DC/Nyquist bin,
- * e = R/2 pairs with itself), butterfly NBF/2 pairs e <-> R-1-e.  One table entry is LOADED per
- * butterfly pair; the entries of the other bins are compile-time rotations of it. */
+ * (k, Nh-k) pair is thread-local and shares one rfft twiddle (up to the mirror sign).  One table
+ * entry is LOADED per butterfly pair; the entries of the other bins are compile-time rotations.
+ *
+ * Pair 0 of thread 0 is the exception: it holds butterflies 0 and NBF/2, i.e. the 2R bins
+ * h*NBF/2, which pair among themselves (h <-> 2R-h; h = 0 is the packed DC/Nyquist bin, h = R
+ * pairs with itself).  Treating them inside thread 0 would make every warp that contains a
+ * thread 0 run a second, divergent copy of the whole epilogue, so these bins take a detour
+ * through a 2R-element scratch area behind the frame's exchange buffer and are split / merged
+ * by all T threads of the frame, a few bins each (phase 2 forward, phase 0 inverse). */
 template <class PL, bool STAGED = false> struct RfftFwdBody {
     typedef Engine<PL> Eng;
     typedef typename Eng::Regs Regs;
     typedef cf32 elem;
     static constexpr int NP = PL::NP, E = PL::E, N = PL::N, T = PL::T;   /* N = complex length = real length / 2 */
-    static constexpr int kPhases = PhaseCount<NP>::value;
+    static_assert(NP == 2, "rfft plans are two-pass plans");
+    static constexpr int kPhases = 3;
     typedef typename PassOf<PL, NP - 1>::type PL_LAST;
     static constexpr int R = PL_LAST::R, NBF = N / R, NB = E / R;
     static_assert(PL_LAST::kMirror && NB % 2 == 0, "forward rfft needs a trailing Mirror pass with an even number of butterflies per thread");
+    static_assert(PL::kSpecial == 2 * R, "plan must reserve the scratch area of the special bins");
 
     struct Args {
         const cf32 *in;      /* real frame viewed as N complex */
         cf32 *out;           /* packed spectrum: N complex = 2N floats */
         const cf32 *tw;      /* pass-ordered CFFT twiddles of this plan */
         const cf32 *twr;     /* twiddleCoef_rfft_(2N): (sin,cos)(2*pi*k/(2N)), k < N */
+        cf32 *scratch;       /* 2R elements of shared memory per frame (set by the kernel) */
     };
+    static FFT_HD void set_scratch(Args &a, cf32 *p) { a.scratch = p; }
     /* frame-local view of the batch arguments; with STAGED the kernel overrides `in` */
     static FFT_HD Args for_frame(Args a, uint64_t frame)
     {
@@ -205,77 +260,124 @@ template <class PL, bool STAGED = false> struct RfftFwdBody {
             for (int e = 0; e < PS::R; e++)
                 r.v[b * PS::R + e] = ld_in<STAGED>(a.in + Eng::template in_index<0>(i, b, e));
     }
-    template <int E0, int E1> static FFT_HD void pair_loop(const cf32 *A, const cf32 *B, const Args &a, int p, cf32 tw0)
+    template <int E0> static FFT_HD void pair_loop(const cf32 *A, const cf32 *B, const Args &a, int p, cf32 tw0, bool regular)
     {
-        /* bins k0 = p + e*NBF (in A) and Nh - k0 = (NBF - p) + (R-1-e)*NBF (in B), e = E0..E1-1 */
-        if constexpr (E0 < E1) {
+        /* bins k0 = p + e*NBF (in A) and Nh - k0 = (NBF - p) + (R-1-e)*NBF (in B) */
+        if constexpr (E0 < R) {
             const cf32 tw = rfft_tw_rot<R, E0>(tw0);
             const int k0 = p + E0 * NBF;
-            st_stream(a.out + k0, rfft_split(A[E0], B[R - 1 - E0], tw));
-            st_stream(a.out + (N - k0), rfft_split(B[R - 1 - E0], A[E0], rfft_tw_mirror(tw)));
-            pair_loop<E0 + 1, E1>(A, B, a, p, tw0);
+            const cf32 o0 = rfft_split(A[E0], B[R - 1 - E0], tw), o1 = rfft_split(B[R - 1 - E0], A[E0], rfft_tw_mirror(tw));
+            st_stream_if(regular, a.out + k0, o0);
+            st_stream_if(regular, a.out + (N - k0), o1);
+            pair_loop<E0 + 1>(A, B, a, p, tw0, regular);
         }
     }
-    /* butterfly 0 of thread 0: bins e*NBF pair with (R-e)*NBF */
-    template <int E0> static FFT_HD void self_loop0(const cf32 *A, const Args &a, cf32 tw0)
+    static FFT_HD void split_store(const Regs &r, const Args &a, cf32 *scratch, int i)
     {
-        if constexpr (E0 <= R / 2) {
-            const cf32 tw = rfft_tw_rot<R, E0>(tw0);
-            const int k0 = E0 * NBF;
-            st_stream(a.out + k0, rfft_split(A[E0], A[R - E0], tw));
-            if (E0 != R / 2) st_stream(a.out + (N - k0), rfft_split(A[R - E0], A[E0], rfft_tw_mirror(tw)));
-            self_loop0<E0 + 1>(A, a, tw0);
-        }
+        cf32 ptw[NB / 2];
+#pragma unroll
+        for (int m = 0; m < NB / 2; m++) ptw[m] = a.twr[i + T * m];
+        split_store(r, a, scratch, i, ptw);
     }
-    /* butterfly NBF/2 of thread 0: bins NBF/2 + e*NBF pair with NBF/2 + (R-1-e)*NBF */
-    template <int E0> static FFT_HD void self_loop1(const cf32 *B, const Args &a, cf32 tw0)
-    {
-        if constexpr (E0 < R / 2) {
-            const cf32 tw = rfft_tw_rot<R, E0>(tw0);
-            const int k0 = NBF / 2 + E0 * NBF;
-            st_stream(a.out + k0, rfft_split(B[E0], B[R - 1 - E0], tw));
-            st_stream(a.out + (N - k0), rfft_split(B[R - 1 - E0], B[E0], rfft_tw_mirror(tw)));
-            self_loop1<E0 + 1>(B, a, tw0);
-        }
-    }
-    static FFT_HD void split_store(const Regs &r, const Args &a, int i)
+    static FFT_HD void split_store(const Regs &r, const Args &a, cf32 *scratch, int i, const cf32 *ptw)
     {
 #pragma unroll
         for (int m = 0; m < NB / 2; m++) {
             const int p = i + T * m;
             const cf32 *A = &r.v[(2 * m) * R], *B = &r.v[(2 * m + 1) * R];
-            if (m != 0 || i != 0) {
-                pair_loop<0, R>(A, B, a, p, a.twr[p]);
-            } else {
-                const cf32 X0 = A[0];
-                st_stream(a.out + 0, cf32{X0.x + X0.y, X0.x - X0.y});       /* rfft_fast_f32.c:337-352 */
-                self_loop0<1>(A, a, a.twr[0]);
-                self_loop1<0>(B, a, a.twr[NBF / 2]);
+            pair_loop<0>(A, B, a, p, ptw[m], m != 0 || i != 0);
+            if (m == 0 && i == 0) {          /* X[h*NBF/2] -> scratch[h] */
+#pragma unroll
+                for (int e = 0; e < R; e++) {
+                    scratch[2 * e] = A[e];
+                    scratch[2 * e + 1] = B[e];
+                }
             }
         }
     }
+    /* rfft twiddles of the special bins this thread handles: h = i + T*q -> twr[h*NBF/2] (h = 0 -> twr[N/2]) */
+    static constexpr int kNS = (R + T - 1) / T;
+    static FFT_HD void load_special_tw(cf32 *stw, const Args &a, int i)
+    {
+#pragma unroll
+        for (int q = 0; q < kNS; q++) {
+            const int h = i + T * q;
+            stw[q] = a.twr[h == 0 ? N / 2 : (h < R ? h * (NBF / 2) : 0)];
+        }
+    }
+    static FFT_HD void special_bins(const Args &a, const cf32 *scratch, int i, const cf32 *stw)
+    {
+#pragma unroll
+        for (int q = 0; q < kNS; q++) {
+            const int h = i + T * q;
+            if (h >= R) break;
+            if (h == 0) {
+                const cf32 X0 = scratch[0], XR = scratch[R];
+                st_stream(a.out + 0, cf32{X0.x + X0.y, X0.x - X0.y});       /* rfft_fast_f32.c:337-352 */
+                st_stream(a.out + N / 2, rfft_split(XR, XR, stw[q]));
+            } else {
+                const int k = h * (NBF / 2);
+                const cf32 A = scratch[h], B = scratch[2 * R - h], tw = stw[q];
+                st_stream(a.out + k, rfft_split(A, B, tw));
+                st_stream(a.out + (N - k), rfft_split(B, A, rfft_tw_mirror(tw)));
+            }
+        }
+    }
+    static constexpr bool kHasPre = false, kHasPost = true;
+    static FFT_HD void pre(const Args &, cf32 *, int) {}
+    static FFT_HD void phase0_in(Regs &r, const Args &a, cf32 *, int i)
+    {
+        gload(r, a, i);
+        Eng::template compute<0, false>(r, a.tw, i);
+    }
+    static FFT_HD void phase0_out(const Regs &r, cf32 *sm, int i) { Eng::template smem_store<0>(r, sm, i); }
+    static FFT_HD void last_in(Regs &r, const cf32 *sm, int i) { Eng::template smem_load<1>(r, sm, i); }
+    static FFT_HD void last_out(Regs &r, const Args &a, int i)
+    {
+        Eng::template compute<1, false>(r, a.tw, i);
+        split_store(r, a, a.scratch, i);
+    }
+    static FFT_HD void last(Regs &r, const Args &a, cf32 *sm, int i)
+    {
+        last_in(r, sm, i);
+        last_out(r, a, i);
+    }
+    static FFT_HD void post(const Args &a, cf32 *, int i)
+    {
+        cf32 stw[kNS];
+        load_special_tw(stw, a, i);
+        special_bins(a, a.scratch, i, stw);
+    }
+    struct Hoist { typename Eng::template TwRegs<0> t0; cf32 stw[kNS]; cf32 ptw[NB / 2]; };
+    static FFT_HD void hoist(Hoist &h, const Args &a, int i)
+    {
+        Eng::template load_tw<0>(h.t0, a.tw, i);
+        load_special_tw(h.stw, a, i);
+#pragma unroll
+        for (int m = 0; m < NB / 2; m++) h.ptw[m] = a.twr[i + T * m];
+    }
+    static FFT_HD void pre(const Args &, cf32 *, int, const Hoist &) {}
+    static FFT_HD void phase0_in(Regs &r, const Args &a, cf32 *, int i, const Hoist &h)
+    {
+        gload(r, a, i);
+        Eng::template compute_pre<0, false>(r, h.t0);
+    }
+    static FFT_HD void post(const Args &a, cf32 *, int i, const Hoist &h) { special_bins(a, a.scratch, i, h.stw); }
+    static FFT_HD void last_out(Regs &r, const Args &a, int i, const Hoist &h)
+    {
+        Eng::template compute<1, false>(r, a.tw, i);
+        split_store(r, a, a.scratch, i, h.ptw);
+    }
+
     template <int PH> static FFT_HD void phase(Regs &r, const Args &a, cf32 *sm, int i)
     {
         if constexpr (PH == 0) {
-            gload(r, a, i);
-            Eng::template compute<0, false>(r, a.tw, i);
-            if constexpr (NP == 1) split_store(r, a, i);
-            else Eng::template smem_store<0>(r, sm, i);
-        } else if constexpr (NP == 2) {
-            Eng::template smem_load<1>(r, sm, i);
-            Eng::template compute<1, false>(r, a.tw, i);
-            split_store(r, a, i);
-        } else if constexpr (NP == 3) {
-            if constexpr (PH == 1) {
-                Eng::template smem_load<1>(r, sm, i);
-                Eng::template compute<1, false>(r, a.tw, i);
-            } else if constexpr (PH == 2) {
-                Eng::template smem_store<1>(r, sm, i);
-            } else {
-                Eng::template smem_load<2>(r, sm, i);
-                Eng::template compute<2, false>(r, a.tw, i);
-                split_store(r, a, i);
-            }
+            phase0_in(r, a, sm, i);
+            phase0_out(r, sm, i);
+        } else if constexpr (PH == 1) {
+            last(r, a, sm, i);
+        } else {
+            post(a, sm, i);
         }
     }
 };
@@ -285,9 +387,11 @@ template <class PL, bool STAGED = false> struct RfftInvBody {
     typedef typename Eng::Regs Regs;
     typedef cf32 elem;
     static constexpr int NP = PL::NP, E = PL::E, N = PL::N, T = PL::T;
-    static constexpr int kPhases = PhaseCount<NP>::value;
+    static_assert(NP == 2, "rfft plans are two-pass plans");
+    static constexpr int kPhases = 3;
     static constexpr int R = PL::P0::R, NBF = N / R, NB = E / R;
     static_assert(PL::P0::kMirror && NB % 2 == 0, "inverse rfft needs a leading Mirror pass with an even number of butterflies per thread");
+    static_assert(PL::kSpecial == 2 * R, "plan must reserve the scratch area of the special bins");
 
     struct Args {
         const cf32 *in;      /* packed spectrum, N complex */
@@ -295,7 +399,9 @@ template <class PL, bool STAGED = false> struct RfftInvBody {
         const cf32 *tw;
         const cf32 *twr;
         float scale;         /* 1/N */
+        cf32 *scratch;       /* 2R elements of shared memory per frame (set by the kernel) */
     };
+    static FFT_HD void set_scratch(Args &a, cf32 *p) { a.scratch = p; }
     /* frame-local view of the batch arguments; with STAGED the kernel overrides `in` */
     static FFT_HD Args for_frame(Args a, uint64_t frame)
     {
@@ -308,37 +414,52 @@ template <class PL, bool STAGED = false> struct RfftInvBody {
     /* merge (rfft_fast_f32.c:405-462) then conjugate for the inverse CFFT (cfft_f32.c:1252-1261) */
     static FFT_HD cf32 mconj(cf32 z) { return {z.x, -z.y}; }
 
-    template <int E0, int E1> static FFT_HD void pair_loop(cf32 *A, cf32 *B, cf32 tw0)
+    /* the 2R bins h*NBF/2 of butterflies 0 and NBF/2, merged by all threads of the frame */
+    static constexpr int kNS = (R + T - 1) / T;
+    static FFT_HD void load_special_tw(cf32 *stw, const Args &a, int i)
     {
-        if constexpr (E0 < E1) {
+#pragma unroll
+        for (int q = 0; q < kNS; q++) {
+            const int h = i + T * q;
+            stw[q] = a.twr[h == 0 ? N / 2 : (h < R ? h * (NBF / 2) : 0)];
+        }
+    }
+    static FFT_HD void special_merge(const Args &a, cf32 *scratch, int i, const cf32 *stw)
+    {
+#pragma unroll
+        for (int q = 0; q < kNS; q++) {
+            const int h = i + T * q;
+            if (h >= R) break;
+            if (h == 0) {
+                const cf32 g0 = ld_in<STAGED>(a.in), gR = ld_in<STAGED>(a.in + N / 2);
+                scratch[0] = mconj(cf32{0.5f * (g0.x + g0.y), 0.5f * (g0.x - g0.y)});   /* :425-431 */
+                scratch[R] = mconj(rfft_merge(gR, gR, stw[q]));
+            } else {
+                const int k = h * (NBF / 2);
+                const cf32 ga = ld_in<STAGED>(a.in + k), gb = ld_in<STAGED>(a.in + (N - k)), tw = stw[q];
+                scratch[h] = mconj(rfft_merge(ga, gb, tw));
+                scratch[2 * R - h] = mconj(rfft_merge(gb, ga, rfft_tw_mirror(tw)));
+            }
+        }
+    }
+    template <int E0> static FFT_HD void pair_loop(cf32 *A, cf32 *B, cf32 tw0)
+    {
+        if constexpr (E0 < R) {
             const cf32 tw = rfft_tw_rot<R, E0>(tw0);
             const cf32 ga = A[E0], gb = B[R - 1 - E0];
             A[E0] = mconj(rfft_merge(ga, gb, tw));
             B[R - 1 - E0] = mconj(rfft_merge(gb, ga, rfft_tw_mirror(tw)));
-            pair_loop<E0 + 1, E1>(A, B, tw0);
+            pair_loop<E0 + 1>(A, B, tw0);
         }
     }
-    template <int E0> static FFT_HD void self_loop0(cf32 *A, cf32 tw0)
+    static FFT_HD void merge_load(Regs &r, const Args &a, const cf32 *scratch, int i)
     {
-        if constexpr (E0 <= R / 2) {
-            const cf32 tw = rfft_tw_rot<R, E0>(tw0);
-            const cf32 ga = A[E0], gb = A[R - E0];
-            A[E0] = mconj(rfft_merge(ga, gb, tw));
-            if (E0 != R / 2) A[R - E0] = mconj(rfft_merge(gb, ga, rfft_tw_mirror(tw)));
-            self_loop0<E0 + 1>(A, tw0);
-        }
+        cf32 ptw[NB / 2];
+#pragma unroll
+        for (int m = 0; m < NB / 2; m++) ptw[m] = a.twr[i + T * m];
+        merge_load(r, a, scratch, i, ptw);
     }
-    template <int E0> static FFT_HD void self_loop1(cf32 *B, cf32 tw0)
-    {
-        if constexpr (E0 < R / 2) {
-            const cf32 tw = rfft_tw_rot<R, E0>(tw0);
-            const cf32 ga = B[E0], gb = B[R - 1 - E0];
-            B[E0] = mconj(rfft_merge(ga, gb, tw));
-            B[R - 1 - E0] = mconj(rfft_merge(gb, ga, rfft_tw_mirror(tw)));
-            self_loop1<E0 + 1>(B, tw0);
-        }
-    }
-    static FFT_HD void merge_load(Regs &r, const Args &a, int i)
+    static FFT_HD void merge_load(Regs &r, const Args &a, const cf32 *scratch, int i, const cf32 *ptw)
     {
 #pragma unroll
         for (int b = 0; b < NB; b++)
@@ -348,13 +469,14 @@ template <class PL, bool STAGED = false> struct RfftInvBody {
         for (int m = 0; m < NB / 2; m++) {
             const int p = i + T * m;
             cf32 *A = &r.v[(2 * m) * R], *B = &r.v[(2 * m + 1) * R];
-            if (m != 0 || i != 0) {
-                pair_loop<0, R>(A, B, a.twr[p]);
-            } else {
-                const cf32 g0 = A[0];
-                A[0] = mconj(cf32{0.5f * (g0.x + g0.y), 0.5f * (g0.x - g0.y)});   /* :425-431 */
-                self_loop0<1>(A, a.twr[0]);
-                self_loop1<0>(B, a.twr[NBF / 2]);
+            (void)p;
+            pair_loop<0>(A, B, ptw[m]);
+            if (m == 0 && i == 0) {          /* butterflies 0 and NBF/2 come merged from the scratch area */
+#pragma unroll
+                for (int e = 0; e < R; e++) {
+                    A[e] = scratch[2 * e];
+                    B[e] = scratch[2 * e + 1];
+                }
             }
         }
     }
@@ -366,32 +488,60 @@ template <class PL, bool STAGED = false> struct RfftInvBody {
 #pragma unroll
             for (int e = 0; e < PS::R; e++) {
                 const int k = Eng::template out_index<NP - 1>(i, b, e);
-                cf32 w = r.v[b * PS::R + e];
-                st_stream(a.out + k, cf32{w.x * a.scale, -w.y * a.scale});
+                st_stream(a.out + k, cscale(mconj(r.v[b * PS::R + e]), a.scale));
             }
     }
+    static constexpr bool kHasPre = true, kHasPost = false;
+    static FFT_HD void pre(const Args &a, cf32 *, int i)
+    {
+        cf32 stw[kNS];
+        load_special_tw(stw, a, i);
+        special_merge(a, a.scratch, i, stw);
+    }
+    static FFT_HD void post(const Args &, cf32 *, int) {}
+    static FFT_HD void phase0_in(Regs &r, const Args &a, cf32 *, int i)
+    {
+        merge_load(r, a, a.scratch, i);
+        Eng::template compute<0, false>(r, a.tw, i);
+    }
+    struct Hoist { typename Eng::template TwRegs<0> t0; cf32 stw[kNS]; cf32 ptw[NB / 2]; };
+    static FFT_HD void hoist(Hoist &h, const Args &a, int i)
+    {
+        Eng::template load_tw<0>(h.t0, a.tw, i);
+        load_special_tw(h.stw, a, i);
+#pragma unroll
+        for (int m = 0; m < NB / 2; m++) h.ptw[m] = a.twr[i + T * m];
+    }
+    static FFT_HD void pre(const Args &a, cf32 *, int i, const Hoist &h) { special_merge(a, a.scratch, i, h.stw); }
+    static FFT_HD void post(const Args &, cf32 *, int, const Hoist &) {}
+    static FFT_HD void last_out(Regs &r, const Args &a, int i, const Hoist &) { last_out(r, a, i); }
+    static FFT_HD void phase0_in(Regs &r, const Args &a, cf32 *, int i, const Hoist &h)
+    {
+        merge_load(r, a, a.scratch, i, h.ptw);
+        Eng::template compute_pre<0, false>(r, h.t0);
+    }
+    static FFT_HD void phase0_out(const Regs &r, cf32 *sm, int i) { Eng::template smem_store<0>(r, sm, i); }
+    static FFT_HD void last_in(Regs &r, const cf32 *sm, int i) { Eng::template smem_load<1>(r, sm, i); }
+    static FFT_HD void last_out(Regs &r, const Args &a, int i)
+    {
+        Eng::template compute<1, false>(r, a.tw, i);
+        gstore(r, a, i);
+    }
+    static FFT_HD void last(Regs &r, const Args &a, cf32 *sm, int i)
+    {
+        last_in(r, sm, i);
+        last_out(r, a, i);
+    }
+
     template <int PH> static FFT_HD void phase(Regs &r, const Args &a, cf32 *sm, int i)
     {
         if constexpr (PH == 0) {
-            merge_load(r, a, i);
-            Eng::template compute<0, false>(r, a.tw, i);
-            if constexpr (NP == 1) gstore(r, a, i);
-            else Eng::template smem_store<0>(r, sm, i);
-        } else if constexpr (NP == 2) {
-            Eng::template smem_load<1>(r, sm, i);
-            Eng::template compute<1, false>(r, a.tw, i);
-            gstore(r, a, i);
-        } else if constexpr (NP == 3) {
-            if constexpr (PH == 1) {
-                Eng::template smem_load<1>(r, sm, i);
-                Eng::template compute<1, false>(r, a.tw, i);
-            } else if constexpr (PH == 2) {
-                Eng::template smem_store<1>(r, sm, i);
-            } else {
-                Eng::template smem_load<2>(r, sm, i);
-                Eng::template compute<2, false>(r, a.tw, i);
-                gstore(r, a, i);
-            }
+            pre(a, sm, i);
+        } else if constexpr (PH == 1) {
+            phase0_in(r, a, sm, i);
+            phase0_out(r, sm, i);
+        } else {
+            last(r, a, sm, i);
         }
     }
 };

@@ -57,18 +57,23 @@ template <int R_> struct PassF32 {
             for (int t = 1; t < r; t++) out[(s++) * NBF + j] = base[(ec * t) % N];
         }
     }
+    /* the butterfly's twiddle values into registers / the butterfly on preloaded values */
+    template <int N, bool LASTPASS> static FFT_HD void load_tw(cf32 *w, const cf32 *__restrict__ twp, int j)
+    {
+        constexpr int NBF = N / R;
+#pragma unroll
+        for (int s = 0; s < slots(LASTPASS); s++) w[s] = twp[s * NBF + j];
+    }
+    template <bool INV, int N, bool LASTPASS> static FFT_HD void compute_w(cf32 *x, const cf32 *w)
+    {
+        dft_f32<R, !LASTPASS>(x, w);
+    }
     template <bool INV, int N, bool LASTPASS>
     static FFT_HD void compute(cf32 *x, const cf32 *__restrict__ twp, int j)
     {
-        constexpr int NBF = N / R;
-        if constexpr (LASTPASS) {
-            dft_f32<R, false>(x, nullptr);
-        } else {
-            cf32 w[dft_tw_slots(R)];
-#pragma unroll
-            for (int s = 0; s < dft_tw_slots(R); s++) w[s] = twp[s * NBF + j];
-            dft_f32<R, true>(x, w);
-        }
+        cf32 w[dft_tw_slots(R)];
+        load_tw<N, LASTPASS>(w, twp, j);
+        compute_w<INV, N, LASTPASS>(x, w);
     }
 };
 /* pass whose butterflies come in mirror pairs (j, N/R - j) per thread: used next to the real
@@ -164,13 +169,19 @@ struct Plan {
     /* padded exchange layout: PADB extra elements after every 2^PADA elements */
     static FFT_HD int pad(int i) { return PADB_ ? (i + ((i >> PADA_) * PADB_)) : i; }
     static constexpr int kPadded = PADB_ ? (N + ((N - 1) >> PADA_) * PADB_ + PADB_) : N;
+    /* scratch behind the exchange area for the 2R self-paired bins of an rfft Mirror pass (fft_body.cuh) */
+    static constexpr int kSpecial = P0_::kMirror ? 2 * P0_::R : (P1_::kMirror ? 2 * P1_::R : (P2_::kMirror ? 2 * P2_::R : 0));
     /* frames that share a shared-memory wavefront (T lanes each) start T elements apart modulo the
      * wavefront width, so their lanes land in different banks */
     static constexpr int kLanesPerWave = 128 / (int)sizeof(typename ARITH_::elem);
     static constexpr int kFrameElems = (PADB_ && T_ < kLanesPerWave)
         ? kPadded + ((T_ - kPadded % kLanesPerWave) + kLanesPerWave) % kLanesPerWave : kPadded;
-    static constexpr int kSmemBytes = (NP > 1) ? F * kFrameElems * (int)sizeof(typename ARITH_::elem) : 0;
+    /* CTA layout: F exchange areas of kFrameElems, then F scratch areas of kSpecial */
+    static constexpr int kSmemElems = F * (kFrameElems + kSpecial);
+    static constexpr int kSmemBytes = (NP > 1 || kSpecial) ? kSmemElems * (int)sizeof(typename ARITH_::elem) : 0;
     static constexpr int kThreads = T * F;
+    /* the same plan with another number of frames per CTA */
+    template <int F2> using with_frames = Plan<ARITH_, N_, T_, F2, PADA_, PADB_, P0_, P1_, P2_>;
     /* pass-ordered twiddle table: pass p owns slots_p * (N / R_p) entries starting at kTwOff<p> */
     static constexpr int kTw0 = P0::slots(NP == 1) * (N / P0::R);
     static constexpr int kTw1 = (NP > 1) ? P1::slots(NP == 2) * (N / P1::R) : 0;
@@ -252,6 +263,30 @@ template <class PL> struct Engine {
             const int j = bfly_index<PS::kMirror, T, NBF>(i, b);
             PS::template compute<INV, N, (P == NP - 1)>(&r.v[b * R], tw + PassOf<PL, P>::TWOFF, j);
         }
+    }
+
+    /* twiddles of pass P held in registers (f32 passes): lets a kernel issue the table loads
+     * before it starts waiting for the frame data */
+    template <int P> struct TwRegs {
+        typedef typename PassOf<PL, P>::type PS;
+        static constexpr int kSlots = PS::slots(P == NP - 1), kNB = E / PS::R;
+        typename PS::telem w[kNB * kSlots > 0 ? kNB * kSlots : 1];
+    };
+    template <int P, class TW> static FFT_HD void load_tw(TwRegs<P> &t, const TW *__restrict__ tw, int i)
+    {
+        typedef typename PassOf<PL, P>::type PS;
+        constexpr int NBF = N / PS::R;
+#pragma unroll
+        for (int b = 0; b < TwRegs<P>::kNB; b++)
+            PS::template load_tw<N, (P == NP - 1)>(&t.w[b * TwRegs<P>::kSlots], tw + PassOf<PL, P>::TWOFF,
+                                                   bfly_index<PS::kMirror, T, NBF>(i, b));
+    }
+    template <int P, bool INV> static FFT_HD void compute_pre(Regs &r, const TwRegs<P> &t)
+    {
+        typedef typename PassOf<PL, P>::type PS;
+#pragma unroll
+        for (int b = 0; b < TwRegs<P>::kNB; b++)
+            PS::template compute_w<INV, N, (P == NP - 1)>(&r.v[b * PS::R], &t.w[b * TwRegs<P>::kSlots]);
     }
 
     /* index (within the frame) of register slot (b, e) on the input side of pass P / output side */

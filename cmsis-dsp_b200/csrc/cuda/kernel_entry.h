@@ -1,0 +1,39 @@
+/*
+ * kernel_entry.h -- internal interface between the C-ABI shim (cmsisdsp_cuda.cu) and the
+ * per-(op, length) kernel objects (kernel_unit.cu compiled once per pair, in parallel).
+ * Not part of the public ABI.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace b200fft {
+
+enum KernelOp { OP_CFFT_F32 = 0, OP_CFFT_Q31 = 1, OP_CFFT_Q15 = 2, OP_RFFT_FWD = 3, OP_RFFT_INV = 4, OP_COUNT = 5 };
+
+struct KernelFacts { int threads, frames, smem, regs, ctasPerSm; };
+
+/* kernel flavours: KF_DIRECT = one CTA per frame group, loads straight into registers;
+ * KF_PIPE = persistent CTAs fed by bulk async copies (two-pass f32 plans only; falls back to
+ * KF_DIRECT when the flavour does not exist for the pair or the input is not 16-byte aligned) */
+enum KernelFlavour { KF_DIRECT = 0, KF_PIPE = 1 };
+
+struct KernelEntry {
+    /* cfft: in == out (in place), aux = output permutation (uint16, may be null), inv = ifftFlag,
+     *       shl1 = final << 1 (fixed point, N = 2*4^m)
+     * rfft: in -> out, aux = twiddleCoef_rfft table (device); direction is fixed by the op */
+    int (*launch)(const void *in, void *out, uint64_t nFrames, int inv, const void *tw, const void *aux, int shl1,
+                  int flavour, cudaStream_t st);
+    /* number of elements of the pass-ordered twiddle table (+1 pad); fills hostOut when non-null */
+    size_t (*twiddles)(const void *base, void *hostOut);
+    size_t elemBytes;
+    int (*facts)(KernelFacts *out, int flavour);
+    bool hasPipe;
+};
+
+/* defined in cmsisdsp_cuda.cu */
+int shim_fail(int code, const char *what, cudaError_t e);
+void shim_count_launch();
+
+}  // namespace b200fft

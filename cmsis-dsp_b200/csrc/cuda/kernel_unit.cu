@@ -1,0 +1,412 @@
+/*
+ * kernel_unit.cu -- ONE (op, length) pair of the batched FFT kernels, compiled once per pair
+ * (-DKU_OP=<KernelOp> -DKU_N=<complex length>) so that the 44 pairs build in parallel.
+ *
+ * One launch processes a whole batch of independent frames: a CTA holds PL::F frames,
+ * PL::T threads each (E = N/T points per thread, 16..64), and runs the phases of the plan's
+ * body (fft_body.cuh) with a barrier between them.  HBM is touched exactly once per point on
+ * the way in and once on the way out; the only other traffic is the shared-memory exchange(s).
+ */
+#include <cuda_runtime.h>
+#include <stdlib.h>
+
+#include "../../../include/cmsisdsp_cuda.h"
+#include "fft_plans.cuh"
+#include "kernel_entry.h"
+
+#if !defined(KU_OP) || !defined(KU_N)
+#error "compile with -DKU_OP=<0..4> -DKU_N=<length>"
+#endif
+
+using namespace b200fft;
+
+/* barrier between two phases of a frame: when a frame's T threads sit inside one warp the
+ * exchange is warp-private and __syncwarp() is enough (no CTA-wide stall) */
+template <class PL> __device__ __forceinline__ void frame_sync()
+{
+    if constexpr (PL::T <= 32) __syncwarp();
+    else __syncthreads();
+}
+
+template <class BODY, class PL>
+__global__ void __launch_bounds__(PL::kThreads) frame_kernel(typename BODY::Args base, uint64_t nFrames)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    typedef typename BODY::elem elem;
+    const int tid = threadIdx.x;
+    const int fl = tid / PL::T, i = tid % PL::T;
+    const uint64_t frame = (uint64_t)blockIdx.x * PL::F + fl;
+    const bool valid = frame < nFrames;
+    elem *sm = reinterpret_cast<elem *>(smem_raw) + fl * PL::kFrameElems;
+    typename BODY::Args a = BODY::for_frame(base, valid ? frame : 0);
+    BODY::set_scratch(a, reinterpret_cast<elem *>(smem_raw) + PL::F * PL::kFrameElems + fl * PL::kSpecial);
+    typename BODY::Regs r;
+
+    if (valid) BODY::template phase<0>(r, a, sm, i);
+    if constexpr (BODY::kPhases > 1) {
+        frame_sync<PL>();
+        if (valid) BODY::template phase<1>(r, a, sm, i);
+    }
+    if constexpr (BODY::kPhases > 2) {
+        frame_sync<PL>();
+        if (valid) BODY::template phase<2>(r, a, sm, i);
+    }
+    if constexpr (BODY::kPhases > 3) {
+        frame_sync<PL>();
+        if (valid) BODY::template phase<3>(r, a, sm, i);
+    }
+}
+
+/* ------------------------------------------------------------------ persistent TMA-fed kernel
+ *
+ * For the two-pass f32 plans (32/64 points per thread) a warp owns whole frames, so few warps
+ * fit on an SM and a warp that waits for its own global loads leaves HBM idle.  Here the loads
+ * are taken off the warps: a CTA (ONE warp, or two for N = 4096) loops over frame groups, and
+ * the group's ONE shared-memory buffer is, in turn,
+ *   1. the destination of a bulk async copy (cp.async.bulk = the 1-D TMA path, completion on an
+ *      mbarrier) of the group's frames, linear as in HBM,
+ *   2. once every thread holds its points in registers, the padded exchange buffer,
+ *   3. as soon as the exchange has been read back, the TMA destination of the NEXT group --
+ *      that copy flies while the second pass, the epilogue and the stores of this group run.
+ * Results leave through the registers (coalesced streaming stores). */
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+/* generic-proxy accesses to a buffer are ordered before the async-proxy (TMA) write that refills it */
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <class BODY, class PL> struct PipeSmem {
+    typedef typename PL::Arith::elem elem;
+    /* F*kFrameElems >= F*N: linear input, then padded exchange; + the scratch areas; + one mbarrier */
+    static constexpr int kBufBytes = (PL::kSmemElems * (int)sizeof(elem) + 15) & ~15;
+    static constexpr int kBytes = kBufBytes + 16;
+};
+
+template <class PL> __device__ __forceinline__ void cta_sync()
+{
+    if constexpr (PL::kThreads <= 32) __syncwarp();
+    else __syncthreads();
+}
+
+/* resident threads per SM the register allocation must leave room for: 384 (<= 168 registers)
+ * with 64 points per thread, 512 (<= 128 registers) with 32 */
+template <class PL> struct PipeBounds { static constexpr int kMinBlocks = (PL::E >= 64 ? 384 : 512) / PL::kThreads; };
+
+template <class BODY, class PL>
+__global__ void __launch_bounds__(PL::kThreads, PipeBounds<PL>::kMinBlocks) frame_kernel_pipe(typename BODY::Args base, uint64_t nFrames)
+{
+    static_assert(PL::NP == 2, "the pipelined kernel is written for two-pass plans");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    typedef typename BODY::elem elem;
+    typedef PipeSmem<BODY, PL> SM;
+    elem *buf = reinterpret_cast<elem *>(smem_raw);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + SM::kBufBytes);
+
+    const int tid = threadIdx.x;
+    const int fl = tid / PL::T, i = tid % PL::T;
+    const uint64_t nGroups = (nFrames + PL::F - 1) / PL::F;
+    constexpr uint32_t kGroupElems = PL::F * PL::N;
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto group_bytes = [&](uint64_t g) -> uint32_t {
+        const uint64_t left = nFrames - g * PL::F;
+        return (uint32_t)((left < (uint64_t)PL::F ? left : (uint64_t)PL::F) * PL::N * sizeof(elem));
+    };
+    auto fetch = [&](uint64_t g) {          /* one thread: start the copy of group g into the buffer */
+        const uint32_t bytes = group_bytes(g);
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(buf, base.in + g * (uint64_t)kGroupElems, bytes, bar);
+    };
+    uint64_t g = blockIdx.x;
+    if (tid == 0 && g < nGroups) fetch(g);
+    uint32_t parity = 0u;
+    elem *sm = buf + fl * PL::kFrameElems;                 /* exchange area of this thread's frame */
+    for (; g < nGroups; g += gridDim.x) {
+        const uint64_t frame = g * PL::F + fl;
+        const bool valid = frame < nFrames;
+        typename BODY::Args a = BODY::for_frame(base, valid ? frame : 0);
+        a.in = buf + fl * PL::N;                           /* the staged copy of this frame */
+        BODY::set_scratch(a, buf + PL::F * PL::kFrameElems + fl * PL::kSpecial);
+        typename BODY::Regs r;
+
+        const uint64_t gn = g + gridDim.x;
+        typename BODY::Hoist hz;
+        BODY::hoist(hz, a, i);                             /* table loads fly while we wait for the frame */
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+        if constexpr (BODY::kHasPre) {
+            if (valid) BODY::pre(a, sm, i, hz);
+            cta_sync<PL>();
+        }
+        if (valid) BODY::phase0_in(r, a, sm, i, hz);
+        cta_sync<PL>();                                    /* all inputs are in registers */
+        if (valid) BODY::phase0_out(r, sm, i);
+        cta_sync<PL>();
+        if (valid) BODY::last_in(r, sm, i);
+        cta_sync<PL>();                                    /* the exchange has been read back: the buffer is free */
+        if (tid == 0 && gn < nGroups) {
+            fence_proxy_async();
+            fetch(gn);
+        }
+        if (valid) BODY::last_out(r, a, i, hz);
+        if constexpr (BODY::kHasPost) {
+            cta_sync<PL>();
+            if (valid) BODY::post(a, sm, i, hz);
+        }
+    }
+}
+
+#define KU_TRY(call)                                                                  \
+    do {                                                                              \
+        cudaError_t e_ = (call);                                                      \
+        if (e_ != cudaSuccess) return shim_fail(CMSISDSP_CUDA_ERR_RUNTIME, #call, e_); \
+    } while (0)
+
+/* kernels that need more than the default 48 KiB of dynamic shared memory opt in once per device */
+template <class BODY, class PL> static int prepare()
+{
+    if (PL::kSmemBytes <= 48 * 1024) return CMSISDSP_CUDA_OK;
+    static bool done[64] = {};
+    int dev = 0;
+    KU_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return shim_fail(CMSISDSP_CUDA_ERR_NO_DEVICE, "device index out of range", cudaSuccess);
+    if (!done[dev]) {
+        KU_TRY(cudaFuncSetAttribute(frame_kernel<BODY, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, PL::kSmemBytes));
+        done[dev] = true;
+    }
+    return CMSISDSP_CUDA_OK;
+}
+
+template <class BODY, class PL>
+static int launch(const typename BODY::Args &args, uint64_t nFrames, cudaStream_t st)
+{
+    if (nFrames == 0) return CMSISDSP_CUDA_OK;
+    const uint64_t ctas = (nFrames + PL::F - 1) / PL::F;
+    if (ctas > 0x7fffffffull) return shim_fail(CMSISDSP_CUDA_ERR_ARGUMENT, "batch too large for one launch", cudaSuccess);
+    int rc = prepare<BODY, PL>();
+    if (rc) return rc;
+    frame_kernel<BODY, PL><<<(unsigned)ctas, PL::kThreads, PL::kSmemBytes, st>>>(args, nFrames);
+    shim_count_launch();
+    KU_TRY(cudaGetLastError());
+    return CMSISDSP_CUDA_OK;
+}
+
+template <class BODY, class PL> static int facts_of(KernelFacts *f)
+{
+    int rc = prepare<BODY, PL>();
+    if (rc) return rc;
+    cudaFuncAttributes fa;
+    KU_TRY(cudaFuncGetAttributes(&fa, frame_kernel<BODY, PL>));
+    int occ = 0;
+    KU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, frame_kernel<BODY, PL>, PL::kThreads, PL::kSmemBytes));
+    f->threads = PL::kThreads;
+    f->frames = PL::F;
+    f->smem = PL::kSmemBytes;
+    f->regs = fa.numRegs;
+    f->ctasPerSm = occ;
+    return CMSISDSP_CUDA_OK;
+}
+
+static int num_sms()
+{
+    static int n[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (!n[dev]) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        n[dev] = v;
+    }
+    return n[dev];
+}
+
+/* resident CTAs per SM of the pipelined kernel (also raises its dynamic shared memory limit once) */
+template <class BODY, class PL> static int pipe_occupancy(int *occOut)
+{
+    static int occ[64] = {};
+    int dev = 0;
+    KU_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return shim_fail(CMSISDSP_CUDA_ERR_NO_DEVICE, "device index out of range", cudaSuccess);
+    if (!occ[dev]) {
+        KU_TRY(cudaFuncSetAttribute(frame_kernel_pipe<BODY, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, PipeSmem<BODY, PL>::kBytes));
+        int o = 0;
+        KU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, frame_kernel_pipe<BODY, PL>, PL::kThreads, PipeSmem<BODY, PL>::kBytes));
+        if (o < 1) return shim_fail(CMSISDSP_CUDA_ERR_RUNTIME, "pipelined kernel does not fit on an SM", cudaSuccess);
+        occ[dev] = o;
+    }
+    *occOut = occ[dev];
+    return CMSISDSP_CUDA_OK;
+}
+
+template <class BODY, class PL>
+static int launch_pipe(const typename BODY::Args &args, uint64_t nFrames, cudaStream_t st)
+{
+    if (nFrames == 0) return CMSISDSP_CUDA_OK;
+    int occ = 0;
+    int rc = pipe_occupancy<BODY, PL>(&occ);
+    if (rc) return rc;
+    const uint64_t groups = (nFrames + PL::F - 1) / PL::F;
+    const uint64_t slots = (uint64_t)occ * (uint64_t)num_sms();
+    const unsigned grid = (unsigned)(groups < slots ? groups : slots);
+    frame_kernel_pipe<BODY, PL><<<grid, PL::kThreads, PipeSmem<BODY, PL>::kBytes, st>>>(args, nFrames);
+    shim_count_launch();
+    KU_TRY(cudaGetLastError());
+    return CMSISDSP_CUDA_OK;
+}
+
+template <class BODY, class PL> static int facts_of_pipe(KernelFacts *f)
+{
+    int occ = 0;
+    int rc = pipe_occupancy<BODY, PL>(&occ);
+    if (rc) return rc;
+    cudaFuncAttributes fa;
+    KU_TRY(cudaFuncGetAttributes(&fa, frame_kernel_pipe<BODY, PL>));
+    f->threads = PL::kThreads;
+    f->frames = PL::F;
+    f->smem = PipeSmem<BODY, PL>::kBytes;
+    f->regs = fa.numRegs;
+    f->ctasPerSm = occ;
+    return CMSISDSP_CUDA_OK;
+}
+
+template <class PL> static size_t twiddles_of(const void *base, void *hostOut)
+{
+    typedef typename PL::Arith::elem elem;
+    if (hostOut) PL::build_twiddles((const elem *)base, (elem *)hostOut);
+    return (size_t)PL::kTwEntries + 1;
+}
+
+/* ------------------------------------------------------------------ the pair of this unit */
+
+/* the pipelined flavour exists for the two-pass f32 plans; its CTA is one warp (T <= 32) or one frame */
+template <class P> struct PipeOf {
+    static constexpr bool kHas = (P::NP == 2) && (sizeof(typename P::Arith::elem) == 8) && (P::E >= 32);
+    typedef typename P::template with_frames<(P::T >= 32 ? 1 : 32 / P::T)> type;
+};
+static bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }   /* bulk copies need 16-byte aligned sources */
+
+#if KU_OP <= 2   /* complex FFT, in place */
+
+#if KU_OP == 0
+typedef ArithF32 AR;
+typedef PlanCfftF32<KU_N>::type PL;
+#elif KU_OP == 1
+typedef ArithQ31 AR;
+typedef PlanCfftFix<ArithQ31, KU_N>::type PL;
+#else
+typedef ArithQ15 AR;
+typedef PlanCfftFix<ArithQ15, KU_N>::type PL;
+#endif
+typedef PipeOf<PL> PIPE;
+
+template <bool INV, bool PERM>
+static int cfft_go(const void *in, void *out, uint64_t nFrames, const void *tw, const void *aux, int shl1, int flavour, cudaStream_t st)
+{
+    typedef AR::elem elem;
+    if constexpr (PIPE::kHas) {
+        if (flavour == KF_PIPE && aligned16(in)) {
+            typedef CfftBody<PIPE::type, INV, PERM, true> BODY;
+            typename BODY::Args a{(const elem *)in, (elem *)out, (const elem *)tw, (const uint16_t *)aux, 1.0f / (float)PL::N, shl1};
+            return launch_pipe<BODY, PIPE::type>(a, nFrames, st);
+        }
+    }
+    typedef CfftBody<PL, INV, PERM> BODY;
+    typename BODY::Args a{(const elem *)in, (elem *)out, (const elem *)tw, (const uint16_t *)aux, 1.0f / (float)PL::N, shl1};
+    return launch<BODY, PL>(a, nFrames, st);
+}
+static int ku_launch(const void *in, void *out, uint64_t nFrames, int inv, const void *tw, const void *aux, int shl1, int flavour, cudaStream_t st)
+{
+    if (inv) return aux ? cfft_go<true, true>(in, out, nFrames, tw, aux, shl1, flavour, st) : cfft_go<true, false>(in, out, nFrames, tw, aux, shl1, flavour, st);
+    return aux ? cfft_go<false, true>(in, out, nFrames, tw, aux, shl1, flavour, st) : cfft_go<false, false>(in, out, nFrames, tw, aux, shl1, flavour, st);
+}
+static int ku_facts(KernelFacts *f, int flavour)
+{
+    if constexpr (PIPE::kHas) {
+        if (flavour == KF_PIPE) return facts_of_pipe<CfftBody<PIPE::type, false, false, true>, PIPE::type>(f);
+    }
+    return facts_of<CfftBody<PL, false>, PL>(f);
+}
+
+#elif KU_OP == 3   /* arm_rfft_fast_f32 forward, KU_N = complex length */
+
+typedef PlanRfftFwd<KU_N>::type PL;
+typedef PipeOf<PL> PIPE;
+static int ku_launch(const void *in, void *out, uint64_t nFrames, int, const void *tw, const void *aux, int, int flavour, cudaStream_t st)
+{
+    if constexpr (PIPE::kHas) {
+        if (flavour == KF_PIPE && aligned16(in)) {
+            typedef RfftFwdBody<PIPE::type, true> BODY;
+            BODY::Args a{(const cf32 *)in, (cf32 *)out, (const cf32 *)tw, (const cf32 *)aux};
+            return launch_pipe<BODY, PIPE::type>(a, nFrames, st);
+        }
+    }
+    typedef RfftFwdBody<PL> BODY;
+    BODY::Args a{(const cf32 *)in, (cf32 *)out, (const cf32 *)tw, (const cf32 *)aux};
+    return launch<BODY, PL>(a, nFrames, st);
+}
+static int ku_facts(KernelFacts *f, int flavour)
+{
+    if constexpr (PIPE::kHas) {
+        if (flavour == KF_PIPE) return facts_of_pipe<RfftFwdBody<PIPE::type, true>, PIPE::type>(f);
+    }
+    return facts_of<RfftFwdBody<PL>, PL>(f);
+}
+
+#else              /* arm_rfft_fast_f32 inverse */
+
+typedef PlanRfftInv<KU_N>::type PL;
+typedef PipeOf<PL> PIPE;
+static int ku_launch(const void *in, void *out, uint64_t nFrames, int, const void *tw, const void *aux, int, int flavour, cudaStream_t st)
+{
+    if constexpr (PIPE::kHas) {
+        if (flavour == KF_PIPE && aligned16(in)) {
+            typedef RfftInvBody<PIPE::type, true> BODY;
+            BODY::Args a{(const cf32 *)in, (cf32 *)out, (const cf32 *)tw, (const cf32 *)aux, 1.0f / (float)PL::N};
+            return launch_pipe<BODY, PIPE::type>(a, nFrames, st);
+        }
+    }
+    typedef RfftInvBody<PL> BODY;
+    BODY::Args a{(const cf32 *)in, (cf32 *)out, (const cf32 *)tw, (const cf32 *)aux, 1.0f / (float)PL::N};
+    return launch<BODY, PL>(a, nFrames, st);
+}
+static int ku_facts(KernelFacts *f, int flavour)
+{
+    if constexpr (PIPE::kHas) {
+        if (flavour == KF_PIPE) return facts_of_pipe<RfftInvBody<PIPE::type, true>, PIPE::type>(f);
+    }
+    return facts_of<RfftInvBody<PL>, PL>(f);
+}
+
+#endif
+
+#define KU_CAT3(a, b, c) a##b##_##c
+#define KU_NAME(op, n) KU_CAT3(ku_entry_, op, n)
+namespace b200fft {
+extern const KernelEntry KU_NAME(KU_OP, KU_N);
+const KernelEntry KU_NAME(KU_OP, KU_N) = {ku_launch, twiddles_of<PL>, sizeof(PL::Arith::elem), ku_facts, PIPE::kHas};
+}

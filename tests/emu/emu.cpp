@@ -56,14 +56,17 @@ static void run_batch(uint64_t nFrames, MAKEARGS make)
 {
     typedef typename BODY::elem elem;
     constexpr int T = PL::T, F = PL::F;
-    std::vector<elem> smem((size_t)F * PL::kFrameElems + 16);
+    std::vector<elem> smem((size_t)PL::kSmemElems + 16);
     std::vector<typename BODY::Regs> regs((size_t)T * F);
     std::vector<typename BODY::Args> args(F);
     bool valid[F];
     for (uint64_t f0 = 0; f0 < nFrames; f0 += F) {
         for (int fl = 0; fl < F; fl++) {
             valid[fl] = (f0 + fl) < nFrames;
-            if (valid[fl]) args[fl] = make(f0 + fl);
+            if (valid[fl]) {
+                args[fl] = make(f0 + fl);
+                BODY::set_scratch(args[fl], smem.data() + (size_t)F * PL::kFrameElems + (size_t)fl * PL::kSpecial);
+            }
         }
         g_cta_base = (const char *)smem.data();
         PhaseRunner<BODY, 0>::run(regs, args.data(), smem.data(), T, F, PL::kFrameElems, valid);
@@ -71,10 +74,10 @@ static void run_batch(uint64_t nFrames, MAKEARGS make)
     }
 }
 
-template <class AR, class PL, bool INV>
-static void cfft_run(typename AR::elem *data, uint64_t nFrames, const void *tw, const uint16_t *perm, int shl1)
+template <class AR, class PL, bool INV, bool PERM>
+static void cfft_run_p(typename AR::elem *data, uint64_t nFrames, const void *tw, const uint16_t *perm, int shl1)
 {
-    typedef CfftBody<PL, INV> BODY;
+    typedef CfftBody<PL, INV, PERM> BODY;
     typedef typename AR::elem elem;
     std::vector<elem> ordered((size_t)PL::kTwEntries + 1);
     PL::build_twiddles((const elem *)tw, ordered.data());     /* same re-ordering the shim uploads */
@@ -88,6 +91,12 @@ static void cfft_run(typename AR::elem *data, uint64_t nFrames, const void *tw, 
         a.shl1 = shl1;
         return a;
     });
+}
+template <class AR, class PL, bool INV>
+static void cfft_run(typename AR::elem *data, uint64_t nFrames, const void *tw, const uint16_t *perm, int shl1)
+{
+    if (perm) cfft_run_p<AR, PL, INV, true>(data, nFrames, tw, perm, shl1);
+    else cfft_run_p<AR, PL, INV, false>(data, nFrames, tw, perm, shl1);
 }
 
 template <int N> static void cfft_f32_n(float *d, uint64_t n, int inv, const void *tw, const uint16_t *perm)
