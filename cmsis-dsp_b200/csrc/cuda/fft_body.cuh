@@ -61,6 +61,8 @@ template <class PL, bool INV, bool PERM = false, bool STAGED = false> struct Cff
     typedef Engine<PL> Eng;
     typedef typename Eng::A A;
     typedef typename A::elem elem;
+    typedef typename A::xelem xelem;
+    typedef typename A::telem telem;
     typedef typename A::work work;
     typedef typename Eng::Regs Regs;
     static constexpr int NP = PL::NP, E = PL::E, N = PL::N;
@@ -70,7 +72,7 @@ template <class PL, bool INV, bool PERM = false, bool STAGED = false> struct Cff
     struct Args {
         const elem *in;          /* frame base (device or emulated) */
         elem *out;               /* may alias in */
-        const elem *tw;          /* pass-ordered twiddle table of this plan (Plan::build_twiddles) */
+        const telem *tw;         /* pass-ordered twiddle table of this plan (Plan::build_twiddles) */
         const uint16_t *perm;    /* PERM only: destination position of X[k] */
         float scale;             /* f32 inverse: 1/N */
         int shl1;                /* fixed point, N = 2*4^m: final << 1 of every word */
@@ -120,10 +122,10 @@ template <class PL, bool INV, bool PERM = false, bool STAGED = false> struct Cff
 
     /* phase 0 in two halves, for kernels whose input buffer doubles as the exchange buffer */
     static constexpr bool kHasPre = false, kHasPost = false;
-    static FFT_HD void set_scratch(Args &, elem *) {}
-    static FFT_HD void pre(const Args &, elem *, int) {}
-    static FFT_HD void post(const Args &, elem *, int) {}
-    static FFT_HD void phase0_in(Regs &r, const Args &a, elem *, int i)
+    static FFT_HD void set_scratch(Args &, xelem *) {}
+    static FFT_HD void pre(const Args &, xelem *, int) {}
+    static FFT_HD void post(const Args &, xelem *, int) {}
+    static FFT_HD void phase0_in(Regs &r, const Args &a, xelem *, int i)
     {
         gload(r, a, i);
         Eng::template compute<0, INV>(r, a.tw, i);
@@ -131,29 +133,29 @@ template <class PL, bool INV, bool PERM = false, bool STAGED = false> struct Cff
     /* table values that do not depend on the frame: loaded before the wait for the frame data */
     struct Hoist { typename Eng::template TwRegs<0> t0; };
     static FFT_HD void hoist(Hoist &h, const Args &a, int i) { Eng::template load_tw<0>(h.t0, a.tw, i); }
-    static FFT_HD void phase0_in(Regs &r, const Args &a, elem *, int i, const Hoist &h)
+    static FFT_HD void phase0_in(Regs &r, const Args &a, xelem *, int i, const Hoist &h)
     {
         gload(r, a, i);
         Eng::template compute_pre<0, INV>(r, h.t0);
     }
-    static FFT_HD void post(const Args &, elem *, int, const Hoist &) {}
-    static FFT_HD void pre(const Args &, elem *, int, const Hoist &) {}
+    static FFT_HD void post(const Args &, xelem *, int, const Hoist &) {}
+    static FFT_HD void pre(const Args &, xelem *, int, const Hoist &) {}
     static FFT_HD void last_out(Regs &r, const Args &a, int i, const Hoist &) { last_out(r, a, i); }
-    static FFT_HD void phase0_out(const Regs &r, elem *sm, int i) { Eng::template smem_store<0>(r, sm, i); }
+    static FFT_HD void phase0_out(const Regs &r, xelem *sm, int i) { Eng::template smem_store<0>(r, sm, i); }
     /* last phase of a two-pass plan */
-    static FFT_HD void last_in(Regs &r, const elem *sm, int i) { Eng::template smem_load<1>(r, sm, i); }
+    static FFT_HD void last_in(Regs &r, const xelem *sm, int i) { Eng::template smem_load<1>(r, sm, i); }
     static FFT_HD void last_out(Regs &r, const Args &a, int i)
     {
         Eng::template compute<1, INV>(r, a.tw, i);
         gstore(r, a, i);
     }
-    static FFT_HD void last(Regs &r, const Args &a, elem *sm, int i)
+    static FFT_HD void last(Regs &r, const Args &a, xelem *sm, int i)
     {
         last_in(r, sm, i);
         last_out(r, a, i);
     }
 
-    template <int PH> static FFT_HD void phase(Regs &r, const Args &a, elem *sm, int i)
+    template <int PH> static FFT_HD void phase(Regs &r, const Args &a, xelem *sm, int i)
     {
         if constexpr (PH == 0) {
             gload(r, a, i);
@@ -226,6 +228,7 @@ template <class PL, bool STAGED = false> struct RfftFwdBody {
     typedef Engine<PL> Eng;
     typedef typename Eng::Regs Regs;
     typedef cf32 elem;
+    typedef cf32 xelem;
     static constexpr int NP = PL::NP, E = PL::E, N = PL::N, T = PL::T;   /* N = complex length = real length / 2 */
     static_assert(NP == 2, "rfft plans are two-pass plans");
     static constexpr int kPhases = 3;
@@ -386,6 +389,7 @@ template <class PL, bool STAGED = false> struct RfftInvBody {
     typedef Engine<PL> Eng;
     typedef typename Eng::Regs Regs;
     typedef cf32 elem;
+    typedef cf32 xelem;
     static constexpr int NP = PL::NP, E = PL::E, N = PL::N, T = PL::T;
     static_assert(NP == 2, "rfft plans are two-pass plans");
     static constexpr int kPhases = 3;

@@ -90,7 +90,8 @@ template <class ARITH, int KA, int KB = -1> struct PassFix {
     static constexpr bool kMirror = false;
     typedef typename ARITH::work work;
     typedef typename ARITH::twid twid;
-    typedef typename ARITH::elem telem;     /* twiddle tables use the storage element type */
+    typedef typename ARITH::telem telem;    /* device twiddle table element (q15: expanded to 32-bit pairs) */
+    typedef typename ARITH::elem selem;     /* element of the reference-layout source table */
 
     /* element e = w + rb*v holds residue v + ra*w after the pass */
     static FFT_HD int out_index(int e) { return (e / rb) + ra * (e % rb); }
@@ -102,14 +103,14 @@ template <class ARITH, int KA, int KB = -1> struct PassFix {
     /* pass-ordered table: slot (u*ta + m-1) of butterfly j = W^(m*(s*p + (N/R)*u)) for stage a,
      * slot (rb*ta + m-1) = W^(m*ra*s*p) for stage b -- the entries ia, 2ia, 3ia the reference
      * reads from twiddleCoef_N_q31/_q15 (arm_cfft_radix4_q31.c:229-266,307-317) */
-    template <int N, int S> static void fill(const telem *base, telem *out, bool)
+    template <int N, int S> static void fill(const selem *base, telem *out, bool)
     {
         constexpr int NBF = N / R;
         for (int j = 0; j < NBF; j++) {
             const int sp = S * (j / S);
             for (int u = 0; u < rb; u++)
-                for (int m = 1; m <= ta; m++) out[(u * ta + m - 1) * NBF + j] = base[m * (sp + (N / R) * u)];
-            for (int m = 1; m <= tb; m++) out[(rb * ta + m - 1) * NBF + j] = base[m * ra * sp];
+                for (int m = 1; m <= ta; m++) out[(u * ta + m - 1) * NBF + j] = ARITH::tw_expand(base[m * (sp + (N / R) * u)]);
+            for (int m = 1; m <= tb; m++) out[(rb * ta + m - 1) * NBF + j] = ARITH::tw_expand(base[m * ra * sp]);
         }
     }
 
@@ -120,8 +121,8 @@ template <class ARITH, int KA, int KB = -1> struct PassFix {
             twid z = {0, 0};
             ARITH::template bfly4<K, INV>(a, b, c, d, z, z, z);
         } else {
-            ARITH::template bfly4<K, INV>(a, b, c, d, ARITH::load(twp[slot * NBF + j]), ARITH::load(twp[(slot + 1) * NBF + j]),
-                                          ARITH::load(twp[(slot + 2) * NBF + j]));
+            ARITH::template bfly4<K, INV>(a, b, c, d, ARITH::tload(twp[slot * NBF + j]), ARITH::tload(twp[(slot + 1) * NBF + j]),
+                                          ARITH::tload(twp[(slot + 2) * NBF + j]));
         }
     }
 
@@ -133,7 +134,7 @@ template <class ARITH, int KA, int KB = -1> struct PassFix {
 #pragma unroll
         for (int u = 0; u < rb; u++) {
             if (KA == ST_PRE2)
-                ARITH::template bfly2<INV>(x[u], x[u + rb], ARITH::load(twp[u * NBF + j]));
+                ARITH::template bfly2<INV>(x[u], x[u + rb], ARITH::tload(twp[u * NBF + j]));
             else
                 stage4<KA, INV, NBF>(x[u], x[u + rb], x[u + 2 * rb], x[u + 3 * rb], twp, u * ta, j);
         }
@@ -173,12 +174,12 @@ struct Plan {
     static constexpr int kSpecial = P0_::kMirror ? 2 * P0_::R : (P1_::kMirror ? 2 * P1_::R : (P2_::kMirror ? 2 * P2_::R : 0));
     /* frames that share a shared-memory wavefront (T lanes each) start T elements apart modulo the
      * wavefront width, so their lanes land in different banks */
-    static constexpr int kLanesPerWave = 128 / (int)sizeof(typename ARITH_::elem);
+    static constexpr int kLanesPerWave = 128 / (int)sizeof(typename ARITH_::xelem);
     static constexpr int kFrameElems = (PADB_ && T_ < kLanesPerWave)
         ? kPadded + ((T_ - kPadded % kLanesPerWave) + kLanesPerWave) % kLanesPerWave : kPadded;
     /* CTA layout: F exchange areas of kFrameElems, then F scratch areas of kSpecial */
     static constexpr int kSmemElems = F * (kFrameElems + kSpecial);
-    static constexpr int kSmemBytes = (NP > 1 || kSpecial) ? kSmemElems * (int)sizeof(typename ARITH_::elem) : 0;
+    static constexpr int kSmemBytes = (NP > 1 || kSpecial) ? kSmemElems * (int)sizeof(typename ARITH_::xelem) : 0;
     static constexpr int kThreads = T * F;
     /* the same plan with another number of frames per CTA */
     template <int F2> using with_frames = Plan<ARITH_, N_, T_, F2, PADA_, PADB_, P0_, P1_, P2_>;
@@ -188,7 +189,7 @@ struct Plan {
     static constexpr int kTw2 = (NP > 2) ? P2::slots(true) * (N / P2::R) : 0;
     static constexpr int kTwEntries = kTw0 + kTw1 + kTw2;
     /* build the table from the reference-layout twiddles (N entries f32, 3N/4 entries q31/q15) */
-    static void build_twiddles(const typename ARITH_::elem *base, typename ARITH_::elem *out)
+    static void build_twiddles(const typename ARITH_::elem *base, typename ARITH_::telem *out)
     {
         P0::template fill<N, S0>(base, out, NP == 1);
         if constexpr (NP > 1) P1::template fill<N, S1>(base, out + kTw0, NP == 2);
@@ -215,13 +216,14 @@ template <bool MIRROR, int T, int NBF> FFT_HD int bfly_index(int i, int b)
 template <class PL> struct Engine {
     typedef typename PL::Arith A;
     typedef typename A::elem elem;
+    typedef typename A::xelem xelem;
     typedef typename A::work work;
     static constexpr int N = PL::N, T = PL::T, E = PL::E, NP = PL::NP;
 
     struct Regs { work v[E]; };
 
     /* ---- shared-memory exchange ---- */
-    template <int P> static FFT_HD void smem_store(const Regs &r, elem *sm, int i)
+    template <int P> static FFT_HD void smem_store(const Regs &r, xelem *sm, int i)
     {
         typedef typename PassOf<PL, P>::type PS;
         constexpr int R = PS::R, S = PassOf<PL, P>::S, NB = E / R, NBF = N / R;
@@ -232,12 +234,12 @@ template <class PL> struct Engine {
 #pragma unroll
             for (int e = 0; e < R; e++) {
                 const int idx = PL::pad(base + S * PS::out_index(e));
-                FFT_TRACE_SMEM(&sm[idx], (int)sizeof(elem), 1);
-                sm[idx] = A::store(r.v[b * R + e]);
+                FFT_TRACE_SMEM(&sm[idx], (int)sizeof(xelem), 1);
+                sm[idx] = A::xstore(r.v[b * R + e]);
             }
         }
     }
-    template <int P> static FFT_HD void smem_load(Regs &r, const elem *sm, int i)
+    template <int P> static FFT_HD void smem_load(Regs &r, const xelem *sm, int i)
     {
         typedef typename PassOf<PL, P>::type PS;
         constexpr int R = PS::R, NB = E / R, NBF = N / R;
@@ -247,8 +249,8 @@ template <class PL> struct Engine {
 #pragma unroll
             for (int e = 0; e < R; e++) {
                 const int idx = PL::pad(j + e * NBF);
-                FFT_TRACE_SMEM(&sm[idx], (int)sizeof(elem), 0);
-                r.v[b * R + e] = A::load(sm[idx]);
+                FFT_TRACE_SMEM(&sm[idx], (int)sizeof(xelem), 0);
+                r.v[b * R + e] = A::xload(sm[idx]);
             }
         }
     }

@@ -69,8 +69,8 @@ template <> struct PlanRfftInv<2048> { typedef Plan<ArithF32, 2048, 32, 2, 5, 1,
 template <class AR, int N> struct PlanCfftFix;
 #define FIXPLAN(N_, T_, F_, PA_, PB_, ...)                                                   \
     template <class AR> struct PlanCfftFix<AR, N_> {                                         \
-        /* 4-byte (q15) elements: one pad word per 32 elements; 8-byte (q31): per 16 */      \
-        typedef Plan<AR, N_, T_, F_, (PB_ && sizeof(typename AR::elem) == 4) ? 5 : PA_, PB_, __VA_ARGS__> type;                \
+        /* exchange elements are 8 bytes for both types (q15 travels sign-extended) */       \
+        typedef Plan<AR, N_, T_, F_, PA_, PB_, __VA_ARGS__> type;                            \
     };
 #define PF(...) PassFix<AR, __VA_ARGS__>
 FIXPLAN(16,   1,   128, 0, 0, PF(ST_FIRST4, ST_LAST4))

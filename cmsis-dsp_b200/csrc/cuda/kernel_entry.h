@@ -27,7 +27,7 @@ struct KernelEntry {
                   int flavour, cudaStream_t st);
     /* number of elements of the pass-ordered twiddle table (+1 pad); fills hostOut when non-null */
     size_t (*twiddles)(const void *base, void *hostOut);
-    size_t elemBytes;
+    size_t elemBytes;           /* bytes per entry of that table (Arith::telem) */
     int (*facts)(KernelFacts *out, int flavour);
     bool hasPipe;
 };

@@ -32,14 +32,14 @@ template <class BODY, class PL>
 __global__ void __launch_bounds__(PL::kThreads) frame_kernel(typename BODY::Args base, uint64_t nFrames)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    typedef typename BODY::elem elem;
+    typedef typename BODY::xelem xelem;                  /* shared-memory exchange element */
     const int tid = threadIdx.x;
     const int fl = tid / PL::T, i = tid % PL::T;
     const uint64_t frame = (uint64_t)blockIdx.x * PL::F + fl;
     const bool valid = frame < nFrames;
-    elem *sm = reinterpret_cast<elem *>(smem_raw) + fl * PL::kFrameElems;
+    xelem *sm = reinterpret_cast<xelem *>(smem_raw) + fl * PL::kFrameElems;
     typename BODY::Args a = BODY::for_frame(base, valid ? frame : 0);
-    BODY::set_scratch(a, reinterpret_cast<elem *>(smem_raw) + PL::F * PL::kFrameElems + fl * PL::kSpecial);
+    BODY::set_scratch(a, reinterpret_cast<xelem *>(smem_raw) + PL::F * PL::kFrameElems + fl * PL::kSpecial);
     typename BODY::Regs r;
 
     if (valid) BODY::template phase<0>(r, a, sm, i);
@@ -297,7 +297,8 @@ template <class BODY, class PL> static int facts_of_pipe(KernelFacts *f)
 template <class PL> static size_t twiddles_of(const void *base, void *hostOut)
 {
     typedef typename PL::Arith::elem elem;
-    if (hostOut) PL::build_twiddles((const elem *)base, (elem *)hostOut);
+    typedef typename PL::Arith::telem telem;
+    if (hostOut) PL::build_twiddles((const elem *)base, (telem *)hostOut);
     return (size_t)PL::kTwEntries + 1;
 }
 
@@ -331,12 +332,12 @@ static int cfft_go(const void *in, void *out, uint64_t nFrames, const void *tw, 
     if constexpr (PIPE::kHas) {
         if (flavour == KF_PIPE && aligned16(in)) {
             typedef CfftBody<PIPE::type, INV, PERM, true> BODY;
-            typename BODY::Args a{(const elem *)in, (elem *)out, (const elem *)tw, (const uint16_t *)aux, 1.0f / (float)PL::N, shl1};
+            typename BODY::Args a{(const elem *)in, (elem *)out, (const typename AR::telem *)tw, (const uint16_t *)aux, 1.0f / (float)PL::N, shl1};
             return launch_pipe<BODY, PIPE::type>(a, nFrames, st);
         }
     }
     typedef CfftBody<PL, INV, PERM> BODY;
-    typename BODY::Args a{(const elem *)in, (elem *)out, (const elem *)tw, (const uint16_t *)aux, 1.0f / (float)PL::N, shl1};
+    typename BODY::Args a{(const elem *)in, (elem *)out, (const typename AR::telem *)tw, (const uint16_t *)aux, 1.0f / (float)PL::N, shl1};
     return launch<BODY, PL>(a, nFrames, st);
 }
 static int ku_launch(const void *in, void *out, uint64_t nFrames, int inv, const void *tw, const void *aux, int shl1, int flavour, cudaStream_t st)
@@ -408,5 +409,5 @@ static int ku_facts(KernelFacts *f, int flavour)
 #define KU_NAME(op, n) KU_CAT3(ku_entry_, op, n)
 namespace b200fft {
 extern const KernelEntry KU_NAME(KU_OP, KU_N);
-const KernelEntry KU_NAME(KU_OP, KU_N) = {ku_launch, twiddles_of<PL>, sizeof(PL::Arith::elem), ku_facts, PIPE::kHas};
+const KernelEntry KU_NAME(KU_OP, KU_N) = {ku_launch, twiddles_of<PL>, sizeof(PL::Arith::telem), ku_facts, PIPE::kHas};
 }

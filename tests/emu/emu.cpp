@@ -54,7 +54,7 @@ template <class BODY, int PH> struct PhaseRunner {
 template <class PL, class BODY, class MAKEARGS>
 static void run_batch(uint64_t nFrames, MAKEARGS make)
 {
-    typedef typename BODY::elem elem;
+    typedef typename BODY::xelem elem;
     constexpr int T = PL::T, F = PL::F;
     std::vector<elem> smem((size_t)PL::kSmemElems + 16);
     std::vector<typename BODY::Regs> regs((size_t)T * F);
@@ -79,7 +79,7 @@ static void cfft_run_p(typename AR::elem *data, uint64_t nFrames, const void *tw
 {
     typedef CfftBody<PL, INV, PERM> BODY;
     typedef typename AR::elem elem;
-    std::vector<elem> ordered((size_t)PL::kTwEntries + 1);
+    std::vector<typename AR::telem> ordered((size_t)PL::kTwEntries + 1);
     PL::build_twiddles((const elem *)tw, ordered.data());     /* same re-ordering the shim uploads */
     run_batch<PL, BODY>(nFrames, [&](uint64_t f) {
         typename BODY::Args a;

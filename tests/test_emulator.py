@@ -85,12 +85,11 @@ def _trace(emu, run):
     return buf[:n]
 
 
-@pytest.mark.parametrize("kind,limit", [("f32", 1.0), ("q31", 1.0), ("q15", 2.0)])
+@pytest.mark.parametrize("kind,limit", [("f32", 1.0), ("q31", 1.0), ("q15", 1.0)])
 @pytest.mark.parametrize("N", [256, 512, 1024, 2048, 4096])
 def test_exchange_bank_conflicts(emu, kind, N, limit):
-    """wavefronts / ideal wavefronts of every exchange load/store.  f32 and q31 (8-byte
-    elements, pad 1 per 16) must be conflict-free for N >= 256; q15 (4-byte elements)
-    currently tolerates 2-way conflicts on one exchange."""
+    """wavefronts / ideal wavefronts of every exchange load/store: all three types exchange
+    8-byte elements (q15 travels sign-extended) and must be conflict-free for N >= 256."""
     tw, _ = product_tables(kind, N)
     y = np.zeros((8, 2 * N), dtype=cd.NP_DTYPE[kind])
     rows = _trace(emu, lambda: emu.emu_cfft(cd.TYPE_ID[kind], N, y.ctypes.data, 8, 0, 1, tw.ctypes.data, None))
