@@ -102,10 +102,26 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(sm), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
+def cpu_baseline_subprocess(frames):
+    """cpu_baseline_run in a fresh interpreter: the threads of a process that has initialised
+    torch/CUDA/NVML inherit a CPU affinity of one core on some boxes, which would make the
+    16-thread CPU baseline read 16x too low."""
+    out = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-baseline-only", str(frames)],
+                         capture_output=True, text=True, timeout=900)
+    for line in reversed(out.stdout.strip().splitlines()):
+        if line.startswith("{"):
+            return json.loads(line)
+    raise RuntimeError("cpu baseline subprocess failed: " + out.stderr[-400:])
+
+
 def cpu_baseline_run(frames, repeats=3, fast=True):
     """The reference's generic-C arm_rfft_fast_f32 forward+inverse on all host cores."""
     import numpy as np
     from oracle_lib import oracle, ref
+    try:
+        os.sched_setaffinity(0, set(range(os.cpu_count() or 1)))
+    except (AttributeError, OSError):
+        pass
     lib, kind = ref(fast=fast), "reference"
     if lib is None:
         lib, kind = oracle(), "port"
@@ -267,7 +283,7 @@ def run_cuda(args, rank, world, local_rank):
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu_baseline = cpu_baseline_run(FRAMES_PER_GPU // (4 if args.quick else 1))
+        cpu_baseline = cpu_baseline_subprocess(FRAMES_PER_GPU // (4 if args.quick else 1))
 
     if rank == 0:
         print(json.dumps({
@@ -294,7 +310,11 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--quick", action="store_true", help="smaller e2e / cpu samples (profiling runs)")
+    ap.add_argument("--cpu-baseline-only", type=int, default=0, help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.cpu_baseline_only:
+        print(json.dumps(cpu_baseline_run(args.cpu_baseline_only)))
+        return
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -63,8 +63,8 @@ static int len_index(uint32_t n)
     return -1;
 }
 
-/* kernel flavour (kernel_entry.h): the persistent TMA-fed kernel wherever the pair has one,
- * unless CMSISDSP_CUDA_KERNEL=direct|pipe forces a flavour (for A/B measurements) */
+/* kernel flavour (kernel_entry.h): the unit's measured preference, unless
+ * CMSISDSP_CUDA_KERNEL=direct|pipe forces a flavour (for A/B measurements) */
 static int choose_flavour(const KernelEntry *ke)
 {
     static int forced = -2;
@@ -73,7 +73,7 @@ static int choose_flavour(const KernelEntry *ke)
         forced = !e ? -1 : (!strcmp(e, "direct") ? KF_DIRECT : (!strcmp(e, "pipe") ? KF_PIPE : -1));
     }
     if (forced >= 0) return (forced == KF_PIPE && !ke->hasPipe) ? KF_DIRECT : forced;
-    return ke->hasPipe ? KF_PIPE : KF_DIRECT;
+    return ke->preferPipe ? KF_PIPE : KF_DIRECT;
 }
 
 /* ------------------------------------------------------------------ plan cache */

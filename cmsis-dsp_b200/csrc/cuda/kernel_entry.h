@@ -29,7 +29,8 @@ struct KernelEntry {
     size_t (*twiddles)(const void *base, void *hostOut);
     size_t elemBytes;           /* bytes per entry of that table (Arith::telem) */
     int (*facts)(KernelFacts *out, int flavour);
-    bool hasPipe;
+    bool hasPipe;               /* a KF_PIPE flavour exists for this pair */
+    bool preferPipe;            /* ... and measured faster than KF_DIRECT */
 };
 
 /* defined in cmsisdsp_cuda.cu */

@@ -307,6 +307,10 @@ template <class PL> static size_t twiddles_of(const void *base, void *hostOut)
 /* the pipelined flavour exists for the two-pass f32 plans; its CTA is one warp (T <= 32) or one frame */
 template <class P> struct PipeOf {
     static constexpr bool kHas = (P::NP == 2) && (sizeof(typename P::Arith::elem) == 8) && (P::E >= 32);
+    /* default flavour of this unit, from the A/B sweeps in profiles/ (CMSISDSP_CUDA_KERNEL overrides):
+     * cfft_f32 and the inverse rfft gain from the TMA-fed kernel wherever it exists; the forward
+     * rfft only at complex length 2048, and the inverse is better off direct at 512 */
+    static constexpr bool kPrefer = kHas && (KU_OP == 0 || (KU_OP == 3 && KU_N == 2048) || (KU_OP == 4 && KU_N != 512));
     typedef typename P::template with_frames<(P::T >= 32 ? 1 : 32 / P::T)> type;
 };
 static bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }   /* bulk copies need 16-byte aligned sources */
@@ -409,5 +413,5 @@ static int ku_facts(KernelFacts *f, int flavour)
 #define KU_NAME(op, n) KU_CAT3(ku_entry_, op, n)
 namespace b200fft {
 extern const KernelEntry KU_NAME(KU_OP, KU_N);
-const KernelEntry KU_NAME(KU_OP, KU_N) = {ku_launch, twiddles_of<PL>, sizeof(PL::Arith::telem), ku_facts, PIPE::kHas};
+const KernelEntry KU_NAME(KU_OP, KU_N) = {ku_launch, twiddles_of<PL>, sizeof(PL::Arith::telem), ku_facts, PIPE::kHas, PIPE::kPrefer};
 }

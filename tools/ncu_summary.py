@@ -7,8 +7,9 @@ import io
 import subprocess
 import sys
 
+UNIT = {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 WANT = [
-    ("gpu__time_duration.sum", "dur_us", 1e-3),
+    ("gpu__time_duration.sum", "dur_us", 1e6),       # scale applies after conversion to base units (s, byte)
     ("dram__bytes_read.sum", "dram_rd_MB", 1e-6),
     ("dram__bytes_write.sum", "dram_wr_MB", 1e-6),
     ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram_pct", 1),
@@ -50,6 +51,7 @@ def main():
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr = rows[0]
+    units = rows[1]
     col = {h: i for i, h in enumerate(hdr)}
     kcol = col["Kernel Name"]
     names = [n for n, _, _ in WANT if n in col]
@@ -62,7 +64,7 @@ def main():
                 continue
             v = r[col[n]].replace(",", "")
             try:
-                vals.append(f"{float(v) * sc:.4g}")
+                vals.append(f"{float(v) * UNIT.get(units[col[n]], 1.0) * sc:.4g}")
             except ValueError:
                 vals.append(v or "-")
         print(short(r[kcol]), r[col["Grid Size"]].replace(" ", ""), r[col["Block Size"]].replace(" ", ""), " ".join(vals))
