@@ -29,7 +29,7 @@ FFT_HD void st_stream(ci16 *p, ci16 v) { __stcs(reinterpret_cast<short2 *>(p), m
 FFT_HD void st_stream_if(bool pred, cf32 *p, cf32 v)
 {
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t@q st.global.cs.v2.f32 [%0], {%1, %2};\n\t}"
-                 ::"l"(p), "f"(v.x), "f"(v.y), "r"((int)pred) : "memory");
+                 ::"l"(p), "f"(v.x), "f"(v.y), "r"((int)pred));
 }
 #else
 FFT_HD void st_stream_if(bool pred, cf32 *p, cf32 v) { if (pred) *p = v; }
@@ -130,17 +130,23 @@ template <class PL, bool INV, bool PERM = false, bool STAGED = false> struct Cff
         gload(r, a, i);
         Eng::template compute<0, INV>(r, a.tw, i);
     }
-    /* table values that do not depend on the frame: loaded before the wait for the frame data */
+    /* Table values of this thread that do not depend on the frame (Hoist): the persistent kernel
+     * fetches them once and parks them in shared memory, column `pk` (stride PL::kThreads); the
+     * *_pk variants of the phases read them from there at the point of use. */
     struct Hoist { typename Eng::template TwRegs<0> t0; };
+    static constexpr int kH0 = (int)(sizeof(typename Eng::template TwRegs<0>) / sizeof(telem));
     static FFT_HD void hoist(Hoist &h, const Args &a, int i) { Eng::template load_tw<0>(h.t0, a.tw, i); }
-    static FFT_HD void phase0_in(Regs &r, const Args &a, xelem *, int i, const Hoist &h)
+    static FFT_HD void phase0_in_pk(Regs &r, const Args &a, xelem *, int i, const telem *pk)
     {
+        typename Eng::template TwRegs<0> t;
+#pragma unroll
+        for (int s = 0; s < kH0; s++) t.w[s] = pk[s * PL::kThreads];
         gload(r, a, i);
-        Eng::template compute_pre<0, INV>(r, h.t0);
+        Eng::template compute_pre<0, INV>(r, t);
     }
-    static FFT_HD void post(const Args &, xelem *, int, const Hoist &) {}
-    static FFT_HD void pre(const Args &, xelem *, int, const Hoist &) {}
-    static FFT_HD void last_out(Regs &r, const Args &a, int i, const Hoist &) { last_out(r, a, i); }
+    static FFT_HD void post_pk(const Args &, xelem *, int, const telem *) {}
+    static FFT_HD void pre_pk(const Args &, xelem *, int, const telem *) {}
+    static FFT_HD void last_out_pk(Regs &r, const Args &a, int i, const telem *) { last_out(r, a, i); }
     static FFT_HD void phase0_out(const Regs &r, xelem *sm, int i) { Eng::template smem_store<0>(r, sm, i); }
     /* last phase of a two-pass plan */
     static FFT_HD void last_in(Regs &r, const xelem *sm, int i) { Eng::template smem_load<1>(r, sm, i); }
@@ -352,6 +358,7 @@ template <class PL, bool STAGED = false> struct RfftFwdBody {
         special_bins(a, a.scratch, i, stw);
     }
     struct Hoist { typename Eng::template TwRegs<0> t0; cf32 stw[kNS]; cf32 ptw[NB / 2]; };
+    static constexpr int kH0 = (int)(sizeof(typename Eng::template TwRegs<0>) / sizeof(cf32));
     static FFT_HD void hoist(Hoist &h, const Args &a, int i)
     {
         Eng::template load_tw<0>(h.t0, a.tw, i);
@@ -359,17 +366,29 @@ template <class PL, bool STAGED = false> struct RfftFwdBody {
 #pragma unroll
         for (int m = 0; m < NB / 2; m++) h.ptw[m] = a.twr[i + T * m];
     }
-    static FFT_HD void pre(const Args &, cf32 *, int, const Hoist &) {}
-    static FFT_HD void phase0_in(Regs &r, const Args &a, cf32 *, int i, const Hoist &h)
+    static FFT_HD void pre_pk(const Args &, cf32 *, int, const cf32 *) {}
+    static FFT_HD void phase0_in_pk(Regs &r, const Args &a, cf32 *, int i, const cf32 *pk)
     {
+        typename Eng::template TwRegs<0> t;
+#pragma unroll
+        for (int s = 0; s < kH0; s++) t.w[s] = pk[s * PL::kThreads];
         gload(r, a, i);
-        Eng::template compute_pre<0, false>(r, h.t0);
+        Eng::template compute_pre<0, false>(r, t);
     }
-    static FFT_HD void post(const Args &a, cf32 *, int i, const Hoist &h) { special_bins(a, a.scratch, i, h.stw); }
-    static FFT_HD void last_out(Regs &r, const Args &a, int i, const Hoist &h)
+    static FFT_HD void last_out_pk(Regs &r, const Args &a, int i, const cf32 *pk)
     {
+        cf32 ptw[NB / 2];
+#pragma unroll
+        for (int m = 0; m < NB / 2; m++) ptw[m] = pk[(kH0 + kNS + m) * PL::kThreads];
         Eng::template compute<1, false>(r, a.tw, i);
-        split_store(r, a, a.scratch, i, h.ptw);
+        split_store(r, a, a.scratch, i, ptw);
+    }
+    static FFT_HD void post_pk(const Args &a, cf32 *, int i, const cf32 *pk)
+    {
+        cf32 stw[kNS];
+#pragma unroll
+        for (int q = 0; q < kNS; q++) stw[q] = pk[(kH0 + q) * PL::kThreads];
+        special_bins(a, a.scratch, i, stw);
     }
 
     template <int PH> static FFT_HD void phase(Regs &r, const Args &a, cf32 *sm, int i)
@@ -509,6 +528,7 @@ template <class PL, bool STAGED = false> struct RfftInvBody {
         Eng::template compute<0, false>(r, a.tw, i);
     }
     struct Hoist { typename Eng::template TwRegs<0> t0; cf32 stw[kNS]; cf32 ptw[NB / 2]; };
+    static constexpr int kH0 = (int)(sizeof(typename Eng::template TwRegs<0>) / sizeof(cf32));
     static FFT_HD void hoist(Hoist &h, const Args &a, int i)
     {
         Eng::template load_tw<0>(h.t0, a.tw, i);
@@ -516,13 +536,25 @@ template <class PL, bool STAGED = false> struct RfftInvBody {
 #pragma unroll
         for (int m = 0; m < NB / 2; m++) h.ptw[m] = a.twr[i + T * m];
     }
-    static FFT_HD void pre(const Args &a, cf32 *, int i, const Hoist &h) { special_merge(a, a.scratch, i, h.stw); }
-    static FFT_HD void post(const Args &, cf32 *, int, const Hoist &) {}
-    static FFT_HD void last_out(Regs &r, const Args &a, int i, const Hoist &) { last_out(r, a, i); }
-    static FFT_HD void phase0_in(Regs &r, const Args &a, cf32 *, int i, const Hoist &h)
+    static FFT_HD void pre_pk(const Args &a, cf32 *, int i, const cf32 *pk)
     {
-        merge_load(r, a, a.scratch, i, h.ptw);
-        Eng::template compute_pre<0, false>(r, h.t0);
+        cf32 stw[kNS];
+#pragma unroll
+        for (int q = 0; q < kNS; q++) stw[q] = pk[(kH0 + q) * PL::kThreads];
+        special_merge(a, a.scratch, i, stw);
+    }
+    static FFT_HD void post_pk(const Args &, cf32 *, int, const cf32 *) {}
+    static FFT_HD void last_out_pk(Regs &r, const Args &a, int i, const cf32 *) { last_out(r, a, i); }
+    static FFT_HD void phase0_in_pk(Regs &r, const Args &a, cf32 *, int i, const cf32 *pk)
+    {
+        cf32 ptw[NB / 2];
+#pragma unroll
+        for (int m = 0; m < NB / 2; m++) ptw[m] = pk[(kH0 + kNS + m) * PL::kThreads];
+        merge_load(r, a, a.scratch, i, ptw);
+        typename Eng::template TwRegs<0> t;
+#pragma unroll
+        for (int s = 0; s < kH0; s++) t.w[s] = pk[s * PL::kThreads];
+        Eng::template compute_pre<0, false>(r, t);
     }
     static FFT_HD void phase0_out(const Regs &r, cf32 *sm, int i) { Eng::template smem_store<0>(r, sm, i); }
     static FFT_HD void last_in(Regs &r, const cf32 *sm, int i) { Eng::template smem_load<1>(r, sm, i); }

@@ -95,41 +95,63 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 /* generic-proxy accesses to a buffer are ordered before the async-proxy (TMA) write that refills it */
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+/* A CTA of the pipelined kernel holds kUnits independent pipelines ("units": one warp, or the two
+ * warps of an N = 4096 frame), 128 threads in all.  They share only the read-only table values:
+ * what each thread needs from the twiddle tables does not depend on the frame, so it is fetched
+ * once per launch and parked in shared memory [value][thread of unit] -- with the carve-out this
+ * kernel needs there is next to no L1 left, and per-frame table loads were seen to miss it and
+ * stall every iteration on an L2 round trip (profiles/r1_ncu_hotspots_rfft_fwd_c.txt). */
 template <class BODY, class PL> struct PipeSmem {
     typedef typename PL::Arith::elem elem;
-    /* F*kFrameElems >= F*N: linear input, then padded exchange; + the scratch areas; + one mbarrier */
-    static constexpr int kBufBytes = (PL::kSmemElems * (int)sizeof(elem) + 15) & ~15;
-    static constexpr int kBytes = kBufBytes + 16;
+    static constexpr int kUnitThreads = PL::kThreads;
+    static constexpr int kUnits = 128 / kUnitThreads;
+    static constexpr int kCtaThreads = kUnits * kUnitThreads;
+    /* per unit: F*kFrameElems >= F*N (linear input, then padded exchange) + the scratch areas */
+    static constexpr int kBufBytes = (PL::kSmemElems * (int)sizeof(elem) + 127) & ~127;
+    static constexpr int kHoistVals = (int)(sizeof(typename BODY::Hoist) / sizeof(elem));
+    static constexpr int kHoistBytes = kHoistVals * kUnitThreads * (int)sizeof(elem);
+    static constexpr int kBytes = kUnits * kBufBytes + kHoistBytes + kUnits * 8;      /* + one mbarrier per unit */
+    /* register budget: three CTAs (384 threads, <= 168 registers) with 64 points per thread, four with 32 */
+    static constexpr int kMinBlocks = PL::E >= 64 ? 3 : 4;
 };
 
-template <class PL> __device__ __forceinline__ void cta_sync()
+/* barrier among the threads of one unit */
+template <class PL> __device__ __forceinline__ void unit_sync(int unit)
 {
     if constexpr (PL::kThreads <= 32) __syncwarp();
-    else __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(unit + 1), "r"(PL::kThreads) : "memory");
 }
 
-/* resident threads per SM the register allocation must leave room for: 384 (<= 168 registers)
- * with 64 points per thread, 512 (<= 128 registers) with 32 */
-template <class PL> struct PipeBounds { static constexpr int kMinBlocks = (PL::E >= 64 ? 384 : 512) / PL::kThreads; };
-
 template <class BODY, class PL>
-__global__ void __launch_bounds__(PL::kThreads, PipeBounds<PL>::kMinBlocks) frame_kernel_pipe(typename BODY::Args base, uint64_t nFrames)
+__global__ void __launch_bounds__(PipeSmem<BODY, PL>::kCtaThreads, PipeSmem<BODY, PL>::kMinBlocks)
+frame_kernel_pipe(typename BODY::Args base, uint64_t nFrames)
 {
     static_assert(PL::NP == 2, "the pipelined kernel is written for two-pass plans");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     typedef typename BODY::elem elem;
     typedef PipeSmem<BODY, PL> SM;
-    elem *buf = reinterpret_cast<elem *>(smem_raw);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + SM::kBufBytes);
+    static_assert(sizeof(typename BODY::Hoist) == SM::kHoistVals * sizeof(elem), "Hoist must be a flat set of table values");
 
-    const int tid = threadIdx.x;
-    const int fl = tid / PL::T, i = tid % PL::T;
+    const int unit = threadIdx.x / SM::kUnitThreads, ut = threadIdx.x % SM::kUnitThreads;
+    const int fl = ut / PL::T, i = ut % PL::T;
+    elem *buf = reinterpret_cast<elem *>(smem_raw + unit * SM::kBufBytes);
+    elem *parked = reinterpret_cast<elem *>(smem_raw + SM::kUnits * SM::kBufBytes);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + SM::kUnits * SM::kBufBytes + SM::kHoistBytes) + unit;
+
     const uint64_t nGroups = (nFrames + PL::F - 1) / PL::F;
+    const uint64_t stride = (uint64_t)gridDim.x * SM::kUnits;
     constexpr uint32_t kGroupElems = PL::F * PL::N;
 
-    if (tid == 0) {
+    if (ut == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (unit == 0) {
+        typename BODY::Hoist h0;
+        BODY::hoist(h0, base, i);
+        const elem *hp = reinterpret_cast<const elem *>(&h0);
+#pragma unroll
+        for (int s = 0; s < SM::kHoistVals; s++) parked[s * SM::kUnitThreads + ut] = hp[s];
     }
     __syncthreads();
 
@@ -137,16 +159,16 @@ __global__ void __launch_bounds__(PL::kThreads, PipeBounds<PL>::kMinBlocks) fram
         const uint64_t left = nFrames - g * PL::F;
         return (uint32_t)((left < (uint64_t)PL::F ? left : (uint64_t)PL::F) * PL::N * sizeof(elem));
     };
-    auto fetch = [&](uint64_t g) {          /* one thread: start the copy of group g into the buffer */
+    auto fetch = [&](uint64_t g) {          /* one thread: start the copy of group g into the unit's buffer */
         const uint32_t bytes = group_bytes(g);
         mbar_expect_tx(bar, bytes);
         bulk_g2s(buf, base.in + g * (uint64_t)kGroupElems, bytes, bar);
     };
-    uint64_t g = blockIdx.x;
-    if (tid == 0 && g < nGroups) fetch(g);
+    uint64_t g = (uint64_t)blockIdx.x * SM::kUnits + unit;
+    if (ut == 0 && g < nGroups) fetch(g);
     uint32_t parity = 0u;
     elem *sm = buf + fl * PL::kFrameElems;                 /* exchange area of this thread's frame */
-    for (; g < nGroups; g += gridDim.x) {
+    for (; g < nGroups; g += stride) {
         const uint64_t frame = g * PL::F + fl;
         const bool valid = frame < nFrames;
         typename BODY::Args a = BODY::for_frame(base, valid ? frame : 0);
@@ -154,29 +176,28 @@ __global__ void __launch_bounds__(PL::kThreads, PipeBounds<PL>::kMinBlocks) fram
         BODY::set_scratch(a, buf + PL::F * PL::kFrameElems + fl * PL::kSpecial);
         typename BODY::Regs r;
 
-        const uint64_t gn = g + gridDim.x;
-        typename BODY::Hoist hz;
-        BODY::hoist(hz, a, i);                             /* table loads fly while we wait for the frame */
+        const uint64_t gn = g + stride;
+        const elem *pk = parked + ut;                      /* this thread's column of parked table values */
         mbar_wait(bar, parity);
         parity ^= 1u;
         if constexpr (BODY::kHasPre) {
-            if (valid) BODY::pre(a, sm, i, hz);
-            cta_sync<PL>();
+            if (valid) BODY::pre_pk(a, sm, i, pk);
+            unit_sync<PL>(unit);
         }
-        if (valid) BODY::phase0_in(r, a, sm, i, hz);
-        cta_sync<PL>();                                    /* all inputs are in registers */
+        if (valid) BODY::phase0_in_pk(r, a, sm, i, pk);
+        unit_sync<PL>(unit);                               /* all inputs are in registers */
         if (valid) BODY::phase0_out(r, sm, i);
-        cta_sync<PL>();
+        unit_sync<PL>(unit);
         if (valid) BODY::last_in(r, sm, i);
-        cta_sync<PL>();                                    /* the exchange has been read back: the buffer is free */
-        if (tid == 0 && gn < nGroups) {
+        unit_sync<PL>(unit);                               /* the exchange has been read back: the buffer is free */
+        if (ut == 0 && gn < nGroups) {
             fence_proxy_async();
             fetch(gn);
         }
-        if (valid) BODY::last_out(r, a, i, hz);
+        if (valid) BODY::last_out_pk(r, a, i, pk);
         if constexpr (BODY::kHasPost) {
-            cta_sync<PL>();
-            if (valid) BODY::post(a, sm, i, hz);
+            unit_sync<PL>(unit);
+            if (valid) BODY::post_pk(a, sm, i, pk);
         }
     }
 }
@@ -255,7 +276,7 @@ template <class BODY, class PL> static int pipe_occupancy(int *occOut)
     if (!occ[dev]) {
         KU_TRY(cudaFuncSetAttribute(frame_kernel_pipe<BODY, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, PipeSmem<BODY, PL>::kBytes));
         int o = 0;
-        KU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, frame_kernel_pipe<BODY, PL>, PL::kThreads, PipeSmem<BODY, PL>::kBytes));
+        KU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, frame_kernel_pipe<BODY, PL>, PipeSmem<BODY, PL>::kCtaThreads, PipeSmem<BODY, PL>::kBytes));
         if (o < 1) return shim_fail(CMSISDSP_CUDA_ERR_RUNTIME, "pipelined kernel does not fit on an SM", cudaSuccess);
         occ[dev] = o;
     }
@@ -270,10 +291,12 @@ static int launch_pipe(const typename BODY::Args &args, uint64_t nFrames, cudaSt
     int occ = 0;
     int rc = pipe_occupancy<BODY, PL>(&occ);
     if (rc) return rc;
+    typedef PipeSmem<BODY, PL> SM;
     const uint64_t groups = (nFrames + PL::F - 1) / PL::F;
+    const uint64_t ctas = (groups + SM::kUnits - 1) / SM::kUnits;
     const uint64_t slots = (uint64_t)occ * (uint64_t)num_sms();
-    const unsigned grid = (unsigned)(groups < slots ? groups : slots);
-    frame_kernel_pipe<BODY, PL><<<grid, PL::kThreads, PipeSmem<BODY, PL>::kBytes, st>>>(args, nFrames);
+    const unsigned grid = (unsigned)(ctas < slots ? ctas : slots);
+    frame_kernel_pipe<BODY, PL><<<grid, SM::kCtaThreads, SM::kBytes, st>>>(args, nFrames);
     shim_count_launch();
     KU_TRY(cudaGetLastError());
     return CMSISDSP_CUDA_OK;
@@ -286,8 +309,8 @@ template <class BODY, class PL> static int facts_of_pipe(KernelFacts *f)
     if (rc) return rc;
     cudaFuncAttributes fa;
     KU_TRY(cudaFuncGetAttributes(&fa, frame_kernel_pipe<BODY, PL>));
-    f->threads = PL::kThreads;
-    f->frames = PL::F;
+    f->threads = PipeSmem<BODY, PL>::kCtaThreads;
+    f->frames = PL::F * PipeSmem<BODY, PL>::kUnits;
     f->smem = PipeSmem<BODY, PL>::kBytes;
     f->regs = fa.numRegs;
     f->ctasPerSm = occ;
