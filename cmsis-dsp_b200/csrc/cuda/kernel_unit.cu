@@ -111,8 +111,11 @@ template <class BODY, class PL> struct PipeSmem {
     static constexpr int kHoistVals = (int)(sizeof(typename BODY::Hoist) / sizeof(elem));
     static constexpr int kHoistBytes = kHoistVals * kUnitThreads * (int)sizeof(elem);
     static constexpr int kBytes = kUnits * kBufBytes + kHoistBytes + kUnits * 8;      /* + one mbarrier per unit */
-    /* register budget: three CTAs (384 threads, <= 168 registers) with 64 points per thread, four with 32 */
-    static constexpr int kMinBlocks = PL::E >= 64 ? 3 : 4;
+    /* Two CTAs (8 warps) per SM and up to 255 registers.  Measured: capping registers to fit three or
+     * four CTAs costs 5-30 % (the rfft epilogues want > 200 registers; a spill is ruinous here because
+     * with this kernel's shared-memory carve-out next to no L1 is left, so every reload is an L2 round
+     * trip), and the extra warps buy nothing once the loads are off the warps' critical path. */
+    static constexpr int kMinBlocks = 2;
 };
 
 /* barrier among the threads of one unit */
@@ -331,9 +334,8 @@ template <class PL> static size_t twiddles_of(const void *base, void *hostOut)
 template <class P> struct PipeOf {
     static constexpr bool kHas = (P::NP == 2) && (sizeof(typename P::Arith::elem) == 8) && (P::E >= 32);
     /* default flavour of this unit, from the A/B sweeps in profiles/ (CMSISDSP_CUDA_KERNEL overrides):
-     * cfft_f32 and the inverse rfft gain from the TMA-fed kernel wherever it exists; the forward
-     * rfft only at complex length 2048, and the inverse is better off direct at 512 */
-    static constexpr bool kPrefer = kHas && (KU_OP == 0 || (KU_OP == 3 && KU_N == 2048) || (KU_OP == 4 && KU_N != 512));
+     * the TMA-fed kernel wins wherever it exists, except the inverse rfft at complex length 512 */
+    static constexpr bool kPrefer = kHas && (KU_OP == 0 || KU_OP == 3 || (KU_OP == 4 && KU_N != 512));
     typedef typename P::template with_frames<(P::T >= 32 ? 1 : 32 / P::T)> type;
 };
 static bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }   /* bulk copies need 16-byte aligned sources */
