@@ -65,15 +65,23 @@ static int len_index(uint32_t n)
 
 /* kernel flavour (kernel_entry.h): the unit's measured preference, unless
  * CMSISDSP_CUDA_KERNEL=direct|pipe forces a flavour (for A/B measurements) */
+static std::atomic<int> g_flavour{-2};           /* -2: not read yet, -1: per-unit default, else forced */
 static int choose_flavour(const KernelEntry *ke)
 {
-    static int forced = -2;
+    int forced = g_flavour.load(std::memory_order_relaxed);
     if (forced == -2) {
         const char *e = getenv("CMSISDSP_CUDA_KERNEL");
         forced = !e ? -1 : (!strcmp(e, "direct") ? KF_DIRECT : (!strcmp(e, "pipe") ? KF_PIPE : -1));
+        g_flavour.store(forced, std::memory_order_relaxed);
     }
     if (forced >= 0) return (forced == KF_PIPE && !ke->hasPipe) ? KF_DIRECT : forced;
     return ke->preferPipe ? KF_PIPE : KF_DIRECT;
+}
+extern "C" int cmsisdsp_cuda_set_kernel_flavour(int flavour)
+{
+    if (flavour < -1 || flavour > KF_PIPE) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "set_kernel_flavour: -1 (default), 0 (direct) or 1 (pipelined)");
+    g_flavour.store(flavour, std::memory_order_relaxed);
+    return CMSISDSP_CUDA_OK;
 }
 
 /* ------------------------------------------------------------------ plan cache */

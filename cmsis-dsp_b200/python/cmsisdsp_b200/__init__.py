@@ -77,6 +77,7 @@ def cuda():
         "cmsisdsp_cuda_cfft_q15": ([vp, u32, u64, u8, u8, vp], i),
         "cmsisdsp_cuda_rfft_fast_f32": ([vp, vp, u32, u64, u8, vp], i),
         "cmsisdsp_cuda_last_error": ([], C.c_char_p), "cmsisdsp_cuda_launch_count": ([], u64),
+        "cmsisdsp_cuda_set_kernel_flavour": ([i], i),
         "cmsisdsp_cuda_kernel_info": ([i, u32] + [C.POINTER(i)] * 5, i),
     }
     for name, (args, res) in sig.items():

@@ -85,7 +85,12 @@ int  cmsisdsp_cuda_cfft_q15(void *d_p, uint32_t fftLen, uint64_t nFrames,
 int  cmsisdsp_cuda_rfft_fast_f32(const void *d_p, void *d_out, uint32_t fftLenReal, uint64_t nFrames,
                                  uint8_t ifftFlag, void *stream);
 
-/* ---- diagnostics ---- */
+/* ---- tuning / diagnostics ---- */
+/* Kernel flavour used by the transform entry points: -1 = the measured default of each (op, length),
+ * 0 = direct (one CTA per frame group, loads into registers), 1 = persistent TMA-fed kernel where the
+ * pair has one.  Both compute identical results; the switch exists for A/B measurements and tests
+ * (the environment variable CMSISDSP_CUDA_KERNEL=direct|pipe sets the initial value). */
+int  cmsisdsp_cuda_set_kernel_flavour(int flavour);
 const char *cmsisdsp_cuda_last_error(void);        /* thread-local, never NULL */
 uint64_t    cmsisdsp_cuda_launch_count(void);      /* kernels launched by this library so far */
 /* static facts about the kernel chosen for (op, fftLen): op 0 cfft_f32, 1 cfft_q31, 2 cfft_q15,

@@ -96,3 +96,22 @@ def test_exchange_bank_conflicts(emu, kind, N, limit):
     assert len(rows) > 0
     for ph, st, nbytes, req, ideal, wf in rows:
         assert wf <= limit * ideal, (kind, N, int(ph), "store" if st else "load", wf / ideal)
+
+
+@pytest.mark.parametrize("N", [512, 1024, 2048, 4096])
+@pytest.mark.parametrize("ifft", [0, 1])
+def test_rfft_exchange_bank_conflicts(emu, N, ifft):
+    """same for the rfft plans (mirror passes read / write the exchange in reversed lane order);
+    the scratch traffic of the 2R special bins (a few scattered 8-byte accesses) is exempt"""
+    tw, _ = cd.instance_tables(cd.cfft_instance("f32", N // 2), "f32")
+    S = cd.rfft_instance(N)
+    twr = np.ctypeslib.as_array(S.pTwiddleRFFT, shape=(N,)).copy()
+    x = np.zeros((8, N), dtype=np.float32)
+    y = np.zeros_like(x)
+    rows = _trace(emu, lambda: emu.emu_rfft(N, x.ctypes.data, y.ctypes.data, 8, ifft, tw.ctypes.data, twr.ctypes.data))
+    big = [r for r in rows if r[3] >= 8]          # the exchanges proper: many requests per phase
+    assert len(big) >= 2
+    for ph, st, nbytes, req, ideal, wf in big:
+        if (ifft == 0 and ph == 1 and st) or (ifft == 0 and ph == 2) or (ifft == 1 and ph == 0) or (ifft == 1 and ph == 1 and not st):
+            continue                              # phases that touch the scratch area
+        assert wf <= 1.0 * ideal, (N, ifft, int(ph), "store" if st else "load", wf / ideal)

@@ -267,3 +267,36 @@ def test_config5_length_sweep_f32_large_batches():
         idx = torch.arange(0, B, max(1, B // 512), device=dev)
         want = oracle().cfft("f32", N, x[idx].cpu().numpy(), 0, 1, threads=NT)
         assert relrms(fwd[idx].cpu().numpy(), want) <= F32_TOL, N
+
+
+# ------------------------------------------------------------------ kernel flavours
+
+def test_direct_and_pipelined_flavours_agree_bit_for_bit():
+    """The persistent TMA-fed kernels (two-pass f32 plans) run the same arithmetic as the direct
+    kernels: outputs must be identical, for ragged batch sizes too (partial last group, fewer
+    groups than resident CTAs)."""
+    cu = cd.cuda()
+    try:
+        for frames in (1, 3, 257, 5000):
+            for N in (512, 1024, 2048, 4096):
+                x = cfft_input("f32", N, frames=frames, seed=N + frames)
+                for ifft, bitrev in ((0, 1), (1, 0)):
+                    out = []
+                    for flavour in (0, 1):
+                        assert cu.cmsisdsp_cuda_set_kernel_flavour(flavour) == 0
+                        out.append(cd.cfft_batch("f32", N, x, ifft, bitrev))
+                    assert np.array_equal(out[0], out[1]), (N, frames, ifft, bitrev)
+                    assert relrms(out[1], oracle().cfft("f32", N, x, ifft, bitrev, threads=NT)) <= F32_TOL
+            for N in (512, 1024, 2048, 4096):
+                xr = rfft_input(N, frames=frames, seed=N + frames)
+                for ifft in (0, 1):
+                    src = xr if not ifft else oracle().rfft(N, xr, 0, threads=NT)
+                    out = []
+                    for flavour in (0, 1):
+                        assert cu.cmsisdsp_cuda_set_kernel_flavour(flavour) == 0
+                        out.append(cd.rfft_batch(N, src, ifft))
+                    assert np.array_equal(out[0], out[1]), (N, frames, ifft)
+                    assert relrms(out[1], oracle().rfft(N, src, ifft, threads=NT)) <= F32_TOL
+    finally:
+        cu.cmsisdsp_cuda_set_kernel_flavour(-1)
+    assert cu.cmsisdsp_cuda_set_kernel_flavour(7) != 0
