@@ -230,6 +230,22 @@ FFT_HD cf32 rfft_tw_mirror(cf32 tw) { return {tw.x, -tw.y}; }
  * thread 0 run a second, divergent copy of the whole epilogue, so these bins take a detour
  * through a 2R-element scratch area behind the frame's exchange buffer and are split / merged
  * by all T threads of the frame, a few bins each (phase 2 forward, phase 0 inverse). */
+struct RfftFwdArgs {
+    const cf32 *in;      /* real frame viewed as N complex */
+    cf32 *out;           /* packed spectrum: N complex = 2N floats */
+    const cf32 *tw;      /* pass-ordered CFFT twiddles of this plan */
+    const cf32 *twr;     /* twiddleCoef_rfft_(2N): (sin,cos)(2*pi*k/(2N)), k < N */
+    cf32 *scratch;       /* 2R elements of shared memory per frame (set by the kernel) */
+};
+struct RfftInvArgs {
+    const cf32 *in;      /* packed spectrum, N complex */
+    cf32 *out;           /* real frame viewed as N complex */
+    const cf32 *tw;
+    const cf32 *twr;
+    float scale;         /* 1/N */
+    cf32 *scratch;       /* 2R elements of shared memory per frame (set by the kernel) */
+};
+
 template <class PL, bool STAGED = false> struct RfftFwdBody {
     typedef Engine<PL> Eng;
     typedef typename Eng::Regs Regs;
@@ -243,13 +259,7 @@ template <class PL, bool STAGED = false> struct RfftFwdBody {
     static_assert(PL_LAST::kMirror && NB % 2 == 0, "forward rfft needs a trailing Mirror pass with an even number of butterflies per thread");
     static_assert(PL::kSpecial == 2 * R, "plan must reserve the scratch area of the special bins");
 
-    struct Args {
-        const cf32 *in;      /* real frame viewed as N complex */
-        cf32 *out;           /* packed spectrum: N complex = 2N floats */
-        const cf32 *tw;      /* pass-ordered CFFT twiddles of this plan */
-        const cf32 *twr;     /* twiddleCoef_rfft_(2N): (sin,cos)(2*pi*k/(2N)), k < N */
-        cf32 *scratch;       /* 2R elements of shared memory per frame (set by the kernel) */
-    };
+    typedef RfftFwdArgs Args;
     static FFT_HD void set_scratch(Args &a, cf32 *p) { a.scratch = p; }
     /* frame-local view of the batch arguments; with STAGED the kernel overrides `in` */
     static FFT_HD Args for_frame(Args a, uint64_t frame)
@@ -416,14 +426,7 @@ template <class PL, bool STAGED = false> struct RfftInvBody {
     static_assert(PL::P0::kMirror && NB % 2 == 0, "inverse rfft needs a leading Mirror pass with an even number of butterflies per thread");
     static_assert(PL::kSpecial == 2 * R, "plan must reserve the scratch area of the special bins");
 
-    struct Args {
-        const cf32 *in;      /* packed spectrum, N complex */
-        cf32 *out;           /* real frame viewed as N complex */
-        const cf32 *tw;
-        const cf32 *twr;
-        float scale;         /* 1/N */
-        cf32 *scratch;       /* 2R elements of shared memory per frame (set by the kernel) */
-    };
+    typedef RfftInvArgs Args;
     static FFT_HD void set_scratch(Args &a, cf32 *p) { a.scratch = p; }
     /* frame-local view of the batch arguments; with STAGED the kernel overrides `in` */
     static FFT_HD Args for_frame(Args a, uint64_t frame)
@@ -579,6 +582,161 @@ template <class PL, bool STAGED = false> struct RfftInvBody {
         } else {
             last(r, a, sm, i);
         }
+    }
+};
+
+/* ------------------------------------------------------------------ one thread per frame (N <= 64)
+ *
+ * Single-pass plans (T = 1, E = N): a thread transforms a whole frame in registers, no exchange.
+ * The frame is read and written with 16-byte vector accesses, which is what lets the kernel
+ * that feeds these bodies (frame_kernel_tiny: per-frame bulk copies into a padded shared-memory
+ * slot, and back) run conflict-free; in the emulator `in`/`out` are plain host frames. */
+
+template <class ELEM> struct alignas(16) Vec16 { ELEM e[16 / sizeof(ELEM)]; };
+
+template <class A, int N> struct TinyIO {
+    typedef typename A::elem elem;
+    typedef typename A::work work;
+    static constexpr int V = 16 / (int)sizeof(elem);
+    static FFT_HD void load(work *w, const elem *in)
+    {
+#pragma unroll
+        for (int m = 0; m < N / V; m++) {
+            const Vec16<elem> q = *reinterpret_cast<const Vec16<elem> *>(in + V * m);
+#pragma unroll
+            for (int u = 0; u < V; u++) w[V * m + u] = A::load(q.e[u]);
+        }
+    }
+    /* w[k] = value of position k */
+    static FFT_HD void store(const work *w, elem *out)
+    {
+#pragma unroll
+        for (int m = 0; m < N / V; m++) {
+            Vec16<elem> q;
+#pragma unroll
+            for (int u = 0; u < V; u++) q.e[u] = A::store(w[V * m + u]);
+            *reinterpret_cast<Vec16<elem> *>(out + V * m) = q;
+        }
+    }
+};
+
+template <class PL, bool INV, bool PERM = false> struct TinyCfftBody {
+    typedef CfftBody<PL, INV, PERM, true> Base;
+    typedef typename Base::Eng Eng;
+    typedef typename Base::A A;
+    typedef typename A::elem elem;
+    typedef typename A::xelem xelem;
+    typedef typename A::work work;
+    typedef typename Base::Regs Regs;
+    typedef typename Base::Args Args;
+    static constexpr int N = PL::N, kPhases = 1;
+    static constexpr bool kF32 = Base::kF32;
+    static_assert(PL::NP == 1 && PL::T == 1, "one thread per frame, one pass");
+    static FFT_HD Args for_frame(Args a, uint64_t frame) { return Base::for_frame(a, frame); }
+    static FFT_HD void set_scratch(Args &, xelem *) {}
+
+    template <int PH> static FFT_HD void phase(Regs &r, const Args &a, xelem *, int)
+    {
+        typedef typename PL::P0 PS;
+        TinyIO<A, N>::load(r.v, a.in);
+        if (kF32 && INV) {
+#pragma unroll
+            for (int k = 0; k < N; k++) r.v[k].y = -r.v[k].y;            /* cfft_f32.c:1252-1261 */
+        }
+        Eng::template compute<0, INV>(r, a.tw, 0);
+        work y[N];                                                        /* y[k] = X[k] */
+#pragma unroll
+        for (int e = 0; e < N; e++) {
+            work w = r.v[e];
+            if (kF32) {
+                if (INV) w = Base::scale_conj(w, a.scale);                /* cfft_f32.c:1285-1297 */
+            } else if (a.shl1) {
+                w = A::shl1(w);
+            }
+            y[PS::out_index(e)] = w;
+        }
+        if constexpr (PERM) {
+#pragma unroll
+            for (int k = 0; k < N; k++) a.out[a.perm[k]] = A::store(y[k]);
+        } else {
+            TinyIO<A, N>::store(y, a.out);
+        }
+    }
+};
+
+template <class PL> struct TinyRfftFwdBody {
+    typedef RfftFwdArgs Args;
+    typedef Engine<PL> Eng;
+    typedef typename Eng::Regs Regs;
+    typedef cf32 elem;
+    typedef cf32 xelem;
+    static constexpr int N = PL::N, kPhases = 1;       /* complex length */
+    static_assert(PL::NP == 1 && PL::T == 1, "one thread per frame, one pass");
+    static FFT_HD Args for_frame(Args a, uint64_t frame)
+    {
+        a.in += frame * (uint64_t)N;
+        a.out += frame * (uint64_t)N;
+        return a;
+    }
+    static FFT_HD void set_scratch(Args &, cf32 *) {}
+    template <int K> static FFT_HD void bins(const cf32 *X, cf32 *y, const cf32 *__restrict__ twr)
+    {
+        if constexpr (K < N / 2) {
+            const cf32 tw = twr[K];
+            y[K] = rfft_split(X[K], X[N - K], tw);
+            y[N - K] = rfft_split(X[N - K], X[K], rfft_tw_mirror(tw));
+            bins<K + 1>(X, y, twr);
+        }
+    }
+    template <int PH> static FFT_HD void phase(Regs &r, const Args &a, cf32 *, int)
+    {
+        TinyIO<ArithF32, N>::load(r.v, a.in);
+        Eng::template compute<0, false>(r, a.tw, 0);
+        cf32 y[N];
+        y[0] = cf32{r.v[0].x + r.v[0].y, r.v[0].x - r.v[0].y};            /* rfft_fast_f32.c:337-352 */
+        y[N / 2] = rfft_split(r.v[N / 2], r.v[N / 2], a.twr[N / 2]);
+        bins<1>(r.v, y, a.twr);
+        TinyIO<ArithF32, N>::store(y, a.out);
+    }
+};
+
+template <class PL> struct TinyRfftInvBody {
+    typedef RfftInvArgs Args;
+    typedef Engine<PL> Eng;
+    typedef typename Eng::Regs Regs;
+    typedef cf32 elem;
+    typedef cf32 xelem;
+    static constexpr int N = PL::N, kPhases = 1;
+    static_assert(PL::NP == 1 && PL::T == 1, "one thread per frame, one pass");
+    static FFT_HD Args for_frame(Args a, uint64_t frame)
+    {
+        a.in += frame * (uint64_t)N;
+        a.out += frame * (uint64_t)N;
+        return a;
+    }
+    static FFT_HD void set_scratch(Args &, cf32 *) {}
+    static FFT_HD cf32 mconj(cf32 z) { return {z.x, -z.y}; }
+    template <int K> static FFT_HD void bins(const cf32 *G, cf32 *x, const cf32 *__restrict__ twr)
+    {
+        if constexpr (K < N / 2) {
+            const cf32 tw = twr[K];
+            x[K] = mconj(rfft_merge(G[K], G[N - K], tw));
+            x[N - K] = mconj(rfft_merge(G[N - K], G[K], rfft_tw_mirror(tw)));
+            bins<K + 1>(G, x, twr);
+        }
+    }
+    template <int PH> static FFT_HD void phase(Regs &r, const Args &a, cf32 *, int)
+    {
+        cf32 g[N];
+        TinyIO<ArithF32, N>::load(g, a.in);
+        r.v[0] = mconj(cf32{0.5f * (g[0].x + g[0].y), 0.5f * (g[0].x - g[0].y)});   /* :425-431 */
+        r.v[N / 2] = mconj(rfft_merge(g[N / 2], g[N / 2], a.twr[N / 2]));
+        bins<1>(g, r.v, a.twr);
+        Eng::template compute<0, false>(r, a.tw, 0);
+        cf32 y[N];
+#pragma unroll
+        for (int k = 0; k < N; k++) y[k] = cscale(mconj(r.v[k]), a.scale);
+        TinyIO<ArithF32, N>::store(y, a.out);
     }
 };
 

@@ -81,36 +81,45 @@ template <int R_> struct PassF32 {
 template <int R_> struct PassF32Mirror : PassF32<R_> { static constexpr bool kMirror = true; };
 typedef PassF32Mirror<8> PassF32Mirror8;
 
-/* fixed-point pass: one or two of the reference's DIF stages, executed back to back on the
- * R = ra*rb points held by the thread. */
-template <class ARITH, int KA, int KB = -1> struct PassFix {
+/* fixed-point pass: one, two or three of the reference's DIF stages, executed back to back on
+ * the R = ra*rb*rc points held by the thread.  Point t = u + rc*(w + rb*v) (u < rc, w < rb,
+ * v < ra) sits at frame position j + t*N/R: stage a butterflies run over v, stage b over w,
+ * stage c over u -- spans N/ra, N/(ra rb), N/R of the reference's in-place passes. */
+template <class ARITH, int KA, int KB = -1, int KC = -1> struct PassFix {
     static constexpr int ra = (KA == ST_PRE2) ? 2 : 4;
     static constexpr int rb = (KB < 0) ? 1 : 4;
-    static constexpr int R = ra * rb;
+    static constexpr int rc = (KC < 0) ? 1 : 4;
+    static constexpr int R = ra * rb * rc;
     static constexpr bool kMirror = false;
     typedef typename ARITH::work work;
     typedef typename ARITH::twid twid;
     typedef typename ARITH::telem telem;    /* device twiddle table element (q15: expanded to 32-bit pairs) */
     typedef typename ARITH::elem selem;     /* element of the reference-layout source table */
 
-    /* element e = w + rb*v holds residue v + ra*w after the pass */
-    static FFT_HD int out_index(int e) { return (e / rb) + ra * (e % rb); }
+    /* element e = u + rc*(w + rb*v) holds residue v + ra*(w + rb*u) after the pass */
+    static FFT_HD int out_index(int e) { return (e / (rb * rc)) + ra * (((e / rc) % rb) + rb * (e % rc)); }
 
-    static constexpr int ta = (KA == ST_PRE2) ? 1 : (KA == ST_LAST4 ? 0 : 3);   /* twiddles per stage-a butterfly */
-    static constexpr int tb = (KB < 0 || KB == ST_LAST4) ? 0 : 3;
-    static constexpr int slots(bool) { return rb * ta + tb; }
+    static constexpr int tw_of(int K) { return K < 0 ? 0 : (K == ST_PRE2 ? 1 : (K == ST_LAST4 ? 0 : 3)); }
+    static constexpr int ta = tw_of(KA), tb = tw_of(KB), tc = tw_of(KC);   /* twiddles per butterfly of each stage */
+    static constexpr int kOffB = rb * rc * ta, kOffC = kOffB + rc * tb;
+    static constexpr int slots(bool) { return kOffC + tc; }
 
-    /* pass-ordered table: slot (u*ta + m-1) of butterfly j = W^(m*(s*p + (N/R)*u)) for stage a,
-     * slot (rb*ta + m-1) = W^(m*ra*s*p) for stage b -- the entries ia, 2ia, 3ia the reference
-     * reads from twiddleCoef_N_q31/_q15 (arm_cfft_radix4_q31.c:229-266,307-317) */
+    /* pass-ordered table of butterfly j, sp = S*(j/S):
+     *   stage a, sub-butterfly o < rb*rc : slots o*ta + m-1        = W^(m * (sp + (N/R) o))
+     *   stage b, sub-butterfly u < rc    : slots kOffB + u*tb + m-1 = W^(m * ra * (sp + (N/R) u))
+     *   stage c                          : slots kOffC + m-1        = W^(m * ra * rb * sp)
+     * i.e. the entries ia, 2ia, 3ia the reference reads from twiddleCoef_N_q31/_q15 with its
+     * twidCoefModifier (arm_cfft_radix4_q31.c:229-266,307-317; arm_cfft_q31.c:777-801) */
     template <int N, int S> static void fill(const selem *base, telem *out, bool)
     {
         constexpr int NBF = N / R;
         for (int j = 0; j < NBF; j++) {
             const int sp = S * (j / S);
-            for (int u = 0; u < rb; u++)
-                for (int m = 1; m <= ta; m++) out[(u * ta + m - 1) * NBF + j] = ARITH::tw_expand(base[m * (sp + (N / R) * u)]);
-            for (int m = 1; m <= tb; m++) out[(rb * ta + m - 1) * NBF + j] = ARITH::tw_expand(base[m * ra * sp]);
+            for (int o = 0; o < rb * rc; o++)
+                for (int m = 1; m <= ta; m++) out[(o * ta + m - 1) * NBF + j] = ARITH::tw_expand(base[m * (sp + (N / R) * o)]);
+            for (int u = 0; u < rc; u++)
+                for (int m = 1; m <= tb; m++) out[(kOffB + u * tb + m - 1) * NBF + j] = ARITH::tw_expand(base[m * ra * (sp + (N / R) * u)]);
+            for (int m = 1; m <= tc; m++) out[(kOffC + m - 1) * NBF + j] = ARITH::tw_expand(base[m * ra * rb * sp]);
         }
     }
 
@@ -129,20 +138,27 @@ template <class ARITH, int KA, int KB = -1> struct PassFix {
     template <bool INV, int N, bool LASTPASS>
     static FFT_HD void compute(work *x, const telem *__restrict__ twp, int j)
     {
-        constexpr int NBF = N / R;
-        /* stage a on elements t = u + rb*v  (u < rb, v < ra) */
+        constexpr int NBF = N / R, Q = rb * rc;
 #pragma unroll
-        for (int u = 0; u < rb; u++) {
+        for (int o = 0; o < Q; o++) {                 /* stage a */
             if (KA == ST_PRE2)
-                ARITH::template bfly2<INV>(x[u], x[u + rb], ARITH::tload(twp[u * NBF + j]));
+                ARITH::template bfly2<INV>(x[o], x[o + Q], ARITH::tload(twp[o * NBF + j]));
             else
-                stage4<KA, INV, NBF>(x[u], x[u + rb], x[u + 2 * rb], x[u + 3 * rb], twp, u * ta, j);
+                stage4<KA, INV, NBF>(x[o], x[o + Q], x[o + 2 * Q], x[o + 3 * Q], twp, o * ta, j);
         }
-        if (KB >= 0) {
-            /* stage b on elements u = 0..3 of each residue v */
+        if constexpr (KB >= 0) {                      /* stage b */
 #pragma unroll
             for (int v = 0; v < ra; v++)
-                stage4<KB, INV, NBF>(x[rb * v], x[rb * v + 1], x[rb * v + 2], x[rb * v + 3], twp, rb * ta, j);
+#pragma unroll
+                for (int u = 0; u < rc; u++) {
+                    const int base = u + Q * v;
+                    stage4<KB, INV, NBF>(x[base], x[base + rc], x[base + 2 * rc], x[base + 3 * rc], twp, kOffB + u * tb, j);
+                }
+        }
+        if constexpr (KC >= 0) {                      /* stage c */
+#pragma unroll
+            for (int g = 0; g < ra * rb; g++)
+                stage4<KC, INV, NBF>(x[4 * g], x[4 * g + 1], x[4 * g + 2], x[4 * g + 3], twp, kOffC, j);
         }
     }
 };

@@ -35,8 +35,8 @@ typedef PassF32Mirror<32> M32;
  * frame belongs to one warp (two for N = 4096) and the exchange needs only __syncwarp(). */
 template <int N> struct PlanCfftF32;
 template <> struct PlanCfftF32<16>   { typedef Plan<ArithF32, 16, 1, 128, 0, 0, F16> type; };
-template <> struct PlanCfftF32<32>   { typedef Plan<ArithF32, 32, 2, 64, 3, 1, F4, F8> type; };
-template <> struct PlanCfftF32<64>   { typedef Plan<ArithF32, 64, 4, 32, 3, 1, F8, F8> type; };
+template <> struct PlanCfftF32<32>   { typedef Plan<ArithF32, 32, 1, 128, 0, 0, F32> type; };
+template <> struct PlanCfftF32<64>   { typedef Plan<ArithF32, 64, 1, 128, 0, 0, F64> type; };
 template <> struct PlanCfftF32<128>  { typedef Plan<ArithF32, 128, 8, 16, 4, 1, F16, F8> type; };
 template <> struct PlanCfftF32<256>  { typedef Plan<ArithF32, 256, 16, 8, 4, 1, F16, F16> type; };
 template <> struct PlanCfftF32<512>  { typedef Plan<ArithF32, 512, 16, 8, 5, 1, F32, F16> type; };
@@ -74,8 +74,8 @@ template <class AR, int N> struct PlanCfftFix;
     };
 #define PF(...) PassFix<AR, __VA_ARGS__>
 FIXPLAN(16,   1,   128, 0, 0, PF(ST_FIRST4, ST_LAST4))
-FIXPLAN(32,   2,   64,  3, 1, PF(ST_PRE2, ST_FIRST4), PF(ST_LAST4))
-FIXPLAN(64,   4,   32,  4, 1, PF(ST_FIRST4, ST_MID4), PF(ST_LAST4))
+FIXPLAN(32,   1,   128, 0, 0, PF(ST_PRE2, ST_FIRST4, ST_LAST4))
+FIXPLAN(64,   1,   128, 0, 0, PF(ST_FIRST4, ST_MID4, ST_LAST4))
 FIXPLAN(128,  8,   16,  4, 1, PF(ST_PRE2, ST_FIRST4), PF(ST_MID4, ST_LAST4))
 FIXPLAN(256,  16,  8,   4, 1, PF(ST_FIRST4, ST_MID4), PF(ST_MID4, ST_LAST4))
 FIXPLAN(512,  32,  4,   4, 1, PF(ST_PRE2, ST_FIRST4), PF(ST_MID4, ST_MID4), PF(ST_LAST4))

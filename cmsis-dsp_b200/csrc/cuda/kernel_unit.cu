@@ -205,6 +205,70 @@ frame_kernel_pipe(typename BODY::Args base, uint64_t nFrames)
     }
 }
 
+/* ------------------------------------------------------------------ one thread per frame (N <= 64)
+ *
+ * For short frames no thread layout gives coalesced register loads (a thread owns at least a
+ * quarter of a 128..512-byte frame), so the TMA does the gather: every lane issues ONE bulk copy
+ * of its own frame into a padded shared-memory slot (slot stride = frame bytes + 16, which makes
+ * the 16-byte vector accesses of 8 consecutive lanes hit 32 different banks), transforms the frame
+ * in registers -- single pass, no exchange -- writes the result back into the slot and sends it
+ * home with one bulk store.  No LDG/STG at all on the data path. */
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+template <class PL> struct TinySmem {
+    typedef typename PL::Arith::elem elem;
+    static constexpr int kWarps = 4, kCtaThreads = 32 * kWarps, kFramesPerCta = kCtaThreads;
+    static constexpr int kFrameBytes = PL::N * (int)sizeof(elem);
+    static constexpr int kSlotBytes = kFrameBytes + 16;
+    static constexpr int kBytes = kCtaThreads * kSlotBytes + kWarps * 8;
+};
+
+template <class BODY, class PL>
+__global__ void __launch_bounds__(TinySmem<PL>::kCtaThreads) frame_kernel_tiny(typename BODY::Args base, uint64_t nFrames)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    typedef typename BODY::elem elem;
+    typedef TinySmem<PL> SM;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + SM::kCtaThreads * SM::kSlotBytes) + warp;
+    elem *slot = reinterpret_cast<elem *>(smem_raw + threadIdx.x * SM::kSlotBytes);
+    const uint64_t frame = (uint64_t)blockIdx.x * SM::kFramesPerCta + threadIdx.x;
+    const bool valid = frame < nFrames;
+
+    if (lane == 0) {
+        mbar_init(bar, 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    typename BODY::Args a = BODY::for_frame(base, valid ? frame : 0);
+    elem *home = a.out;
+    if (valid) {
+        mbar_expect_tx(bar, SM::kFrameBytes);                 /* arrive + this lane's bytes */
+        bulk_g2s(slot, a.in, SM::kFrameBytes, bar);
+    } else {
+        mbar_arrive(bar);
+    }
+    mbar_wait(bar, 0);
+    if (valid) {
+        a.in = slot;
+        a.out = slot;
+        typename BODY::Regs r;
+        BODY::template phase<0>(r, a, nullptr, 0);
+        fence_proxy_async();                                  /* the slot's generic-proxy writes -> visible to the TMA */
+        bulk_s2g(home, slot, SM::kFrameBytes);
+    }
+    bulk_wait_read_all();                                     /* shared memory must outlive the store's reads */
+}
+
 #define KU_TRY(call)                                                                  \
     do {                                                                              \
         cudaError_t e_ = (call);                                                      \
@@ -305,6 +369,50 @@ static int launch_pipe(const typename BODY::Args &args, uint64_t nFrames, cudaSt
     return CMSISDSP_CUDA_OK;
 }
 
+template <class BODY, class PL> static int tiny_prepare(int *occOut)
+{
+    static int occ[64] = {};
+    int dev = 0;
+    KU_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return shim_fail(CMSISDSP_CUDA_ERR_NO_DEVICE, "device index out of range", cudaSuccess);
+    if (!occ[dev]) {
+        KU_TRY(cudaFuncSetAttribute(frame_kernel_tiny<BODY, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, TinySmem<PL>::kBytes));
+        int o = 0;
+        KU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, frame_kernel_tiny<BODY, PL>, TinySmem<PL>::kCtaThreads, TinySmem<PL>::kBytes));
+        if (o < 1) return shim_fail(CMSISDSP_CUDA_ERR_RUNTIME, "thread-per-frame kernel does not fit on an SM", cudaSuccess);
+        occ[dev] = o;
+    }
+    if (occOut) *occOut = occ[dev];
+    return CMSISDSP_CUDA_OK;
+}
+template <class BODY, class PL>
+static int launch_tiny(const typename BODY::Args &args, uint64_t nFrames, cudaStream_t st)
+{
+    if (nFrames == 0) return CMSISDSP_CUDA_OK;
+    int rc = tiny_prepare<BODY, PL>(nullptr);
+    if (rc) return rc;
+    const uint64_t ctas = (nFrames + TinySmem<PL>::kFramesPerCta - 1) / TinySmem<PL>::kFramesPerCta;
+    if (ctas > 0x7fffffffull) return shim_fail(CMSISDSP_CUDA_ERR_ARGUMENT, "batch too large for one launch", cudaSuccess);
+    frame_kernel_tiny<BODY, PL><<<(unsigned)ctas, TinySmem<PL>::kCtaThreads, TinySmem<PL>::kBytes, st>>>(args, nFrames);
+    shim_count_launch();
+    KU_TRY(cudaGetLastError());
+    return CMSISDSP_CUDA_OK;
+}
+template <class BODY, class PL> static int facts_of_tiny(KernelFacts *f)
+{
+    int occ = 0;
+    int rc = tiny_prepare<BODY, PL>(&occ);
+    if (rc) return rc;
+    cudaFuncAttributes fa;
+    KU_TRY(cudaFuncGetAttributes(&fa, frame_kernel_tiny<BODY, PL>));
+    f->threads = TinySmem<PL>::kCtaThreads;
+    f->frames = TinySmem<PL>::kFramesPerCta;
+    f->smem = TinySmem<PL>::kBytes;
+    f->regs = fa.numRegs;
+    f->ctasPerSm = occ;
+    return CMSISDSP_CUDA_OK;
+}
+
 template <class BODY, class PL> static int facts_of_pipe(KernelFacts *f)
 {
     int occ = 0;
@@ -330,12 +438,16 @@ template <class PL> static size_t twiddles_of(const void *base, void *hostOut)
 
 /* ------------------------------------------------------------------ the pair of this unit */
 
-/* the pipelined flavour exists for the two-pass f32 plans; its CTA is one warp (T <= 32) or one frame */
+/* The TMA-fed flavour (KF_PIPE) of a unit is the persistent pipelined kernel for the two-pass f32
+ * plans (its CTA unit is one warp, T <= 32, or one frame) and the thread-per-frame kernel for the
+ * single-pass plans (N <= 64). */
 template <class P> struct PipeOf {
-    static constexpr bool kHas = (P::NP == 2) && (sizeof(typename P::Arith::elem) == 8) && (P::E >= 32);
+    static constexpr bool kTiny = (P::NP == 1) && (P::T == 1);
+    static constexpr bool kPipe = (P::NP == 2) && (sizeof(typename P::Arith::elem) == 8) && (P::E >= 32);
+    static constexpr bool kHas = kTiny || kPipe;
     /* default flavour of this unit, from the A/B sweeps in profiles/ (CMSISDSP_CUDA_KERNEL overrides):
-     * the TMA-fed kernel wins wherever it exists, except the inverse rfft at complex length 512 */
-    static constexpr bool kPrefer = kHas && (KU_OP == 0 || KU_OP == 3 || (KU_OP == 4 && KU_N != 512));
+     * the TMA-fed kernels win wherever they exist, except the inverse rfft at complex length 512 */
+    static constexpr bool kPrefer = kHas && !(KU_OP == 4 && KU_N == 512);
     typedef typename P::template with_frames<(P::T >= 32 ? 1 : 32 / P::T)> type;
 };
 static bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }   /* bulk copies need 16-byte aligned sources */
@@ -358,15 +470,23 @@ template <bool INV, bool PERM>
 static int cfft_go(const void *in, void *out, uint64_t nFrames, const void *tw, const void *aux, int shl1, int flavour, cudaStream_t st)
 {
     typedef AR::elem elem;
-    if constexpr (PIPE::kHas) {
+    typedef AR::telem telem;
+    if constexpr (PIPE::kTiny) {
+        if (flavour == KF_PIPE && aligned16(in)) {
+            typedef TinyCfftBody<PL, INV, PERM> BODY;
+            typename BODY::Args a{(const elem *)in, (elem *)out, (const telem *)tw, (const uint16_t *)aux, 1.0f / (float)PL::N, shl1};
+            return launch_tiny<BODY, PL>(a, nFrames, st);
+        }
+    }
+    if constexpr (PIPE::kPipe) {
         if (flavour == KF_PIPE && aligned16(in)) {
             typedef CfftBody<PIPE::type, INV, PERM, true> BODY;
-            typename BODY::Args a{(const elem *)in, (elem *)out, (const typename AR::telem *)tw, (const uint16_t *)aux, 1.0f / (float)PL::N, shl1};
+            typename BODY::Args a{(const elem *)in, (elem *)out, (const telem *)tw, (const uint16_t *)aux, 1.0f / (float)PL::N, shl1};
             return launch_pipe<BODY, PIPE::type>(a, nFrames, st);
         }
     }
     typedef CfftBody<PL, INV, PERM> BODY;
-    typename BODY::Args a{(const elem *)in, (elem *)out, (const typename AR::telem *)tw, (const uint16_t *)aux, 1.0f / (float)PL::N, shl1};
+    typename BODY::Args a{(const elem *)in, (elem *)out, (const telem *)tw, (const uint16_t *)aux, 1.0f / (float)PL::N, shl1};
     return launch<BODY, PL>(a, nFrames, st);
 }
 static int ku_launch(const void *in, void *out, uint64_t nFrames, int inv, const void *tw, const void *aux, int shl1, int flavour, cudaStream_t st)
@@ -376,61 +496,101 @@ static int ku_launch(const void *in, void *out, uint64_t nFrames, int inv, const
 }
 static int ku_facts(KernelFacts *f, int flavour)
 {
-    if constexpr (PIPE::kHas) {
+    if constexpr (PIPE::kTiny) {
+        if (flavour == KF_PIPE) return facts_of_tiny<TinyCfftBody<PL, false, false>, PL>(f);
+    }
+    if constexpr (PIPE::kPipe) {
         if (flavour == KF_PIPE) return facts_of_pipe<CfftBody<PIPE::type, false, false, true>, PIPE::type>(f);
     }
     return facts_of<CfftBody<PL, false>, PL>(f);
 }
+typedef PL TWPLAN;                 /* plan whose pass-ordered twiddle table the shim uploads */
 
 #elif KU_OP == 3   /* arm_rfft_fast_f32 forward, KU_N = complex length */
 
 typedef PlanRfftFwd<KU_N>::type PL;
+#if KU_N <= 64
+typedef PlanCfftF32<KU_N>::type TPL;   /* the single-pass complex plan of the thread-per-frame kernel (needs no twiddle table) */
+struct PIPE { static constexpr bool kHas = true, kPrefer = true; };
+#else
 typedef PipeOf<PL> PIPE;
+#endif
 static int ku_launch(const void *in, void *out, uint64_t nFrames, int, const void *tw, const void *aux, int, int flavour, cudaStream_t st)
 {
-    if constexpr (PIPE::kHas) {
+#if KU_N <= 64
+    if (flavour == KF_PIPE && aligned16(in) && aligned16(out)) {
+        typedef TinyRfftFwdBody<TPL> BODY;
+        BODY::Args a{(const cf32 *)in, (cf32 *)out, (const cf32 *)tw, (const cf32 *)aux};
+        return launch_tiny<BODY, TPL>(a, nFrames, st);
+    }
+#else
+    if constexpr (PIPE::kPipe) {
         if (flavour == KF_PIPE && aligned16(in)) {
             typedef RfftFwdBody<PIPE::type, true> BODY;
             BODY::Args a{(const cf32 *)in, (cf32 *)out, (const cf32 *)tw, (const cf32 *)aux};
             return launch_pipe<BODY, PIPE::type>(a, nFrames, st);
         }
     }
+#endif
     typedef RfftFwdBody<PL> BODY;
     BODY::Args a{(const cf32 *)in, (cf32 *)out, (const cf32 *)tw, (const cf32 *)aux};
     return launch<BODY, PL>(a, nFrames, st);
 }
 static int ku_facts(KernelFacts *f, int flavour)
 {
-    if constexpr (PIPE::kHas) {
+#if KU_N <= 64
+    if (flavour == KF_PIPE) return facts_of_tiny<TinyRfftFwdBody<TPL>, TPL>(f);
+#else
+    if constexpr (PIPE::kPipe) {
         if (flavour == KF_PIPE) return facts_of_pipe<RfftFwdBody<PIPE::type, true>, PIPE::type>(f);
     }
+#endif
     return facts_of<RfftFwdBody<PL>, PL>(f);
 }
+typedef PL TWPLAN;
 
 #else              /* arm_rfft_fast_f32 inverse */
 
 typedef PlanRfftInv<KU_N>::type PL;
+#if KU_N <= 64
+typedef PlanCfftF32<KU_N>::type TPL;
+struct PIPE { static constexpr bool kHas = true, kPrefer = true; };
+#else
 typedef PipeOf<PL> PIPE;
+#endif
 static int ku_launch(const void *in, void *out, uint64_t nFrames, int, const void *tw, const void *aux, int, int flavour, cudaStream_t st)
 {
-    if constexpr (PIPE::kHas) {
+#if KU_N <= 64
+    if (flavour == KF_PIPE && aligned16(in) && aligned16(out)) {
+        typedef TinyRfftInvBody<TPL> BODY;
+        BODY::Args a{(const cf32 *)in, (cf32 *)out, (const cf32 *)tw, (const cf32 *)aux, 1.0f / (float)PL::N};
+        return launch_tiny<BODY, TPL>(a, nFrames, st);
+    }
+#else
+    if constexpr (PIPE::kPipe) {
         if (flavour == KF_PIPE && aligned16(in)) {
             typedef RfftInvBody<PIPE::type, true> BODY;
             BODY::Args a{(const cf32 *)in, (cf32 *)out, (const cf32 *)tw, (const cf32 *)aux, 1.0f / (float)PL::N};
             return launch_pipe<BODY, PIPE::type>(a, nFrames, st);
         }
     }
+#endif
     typedef RfftInvBody<PL> BODY;
     BODY::Args a{(const cf32 *)in, (cf32 *)out, (const cf32 *)tw, (const cf32 *)aux, 1.0f / (float)PL::N};
     return launch<BODY, PL>(a, nFrames, st);
 }
 static int ku_facts(KernelFacts *f, int flavour)
 {
-    if constexpr (PIPE::kHas) {
+#if KU_N <= 64
+    if (flavour == KF_PIPE) return facts_of_tiny<TinyRfftInvBody<TPL>, TPL>(f);
+#else
+    if constexpr (PIPE::kPipe) {
         if (flavour == KF_PIPE) return facts_of_pipe<RfftInvBody<PIPE::type, true>, PIPE::type>(f);
     }
+#endif
     return facts_of<RfftInvBody<PL>, PL>(f);
 }
+typedef PL TWPLAN;
 
 #endif
 
@@ -438,5 +598,5 @@ static int ku_facts(KernelFacts *f, int flavour)
 #define KU_NAME(op, n) KU_CAT3(ku_entry_, op, n)
 namespace b200fft {
 extern const KernelEntry KU_NAME(KU_OP, KU_N);
-const KernelEntry KU_NAME(KU_OP, KU_N) = {ku_launch, twiddles_of<PL>, sizeof(PL::Arith::telem), ku_facts, PIPE::kHas, PIPE::kPrefer};
+const KernelEntry KU_NAME(KU_OP, KU_N) = {ku_launch, twiddles_of<TWPLAN>, sizeof(TWPLAN::Arith::telem), ku_facts, PIPE::kHas, PIPE::kPrefer};
 }

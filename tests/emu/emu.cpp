@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <type_traits>
 #include <vector>
 
 struct TraceRec { int phase, seq, tid, off, bytes, st; };
@@ -77,7 +78,8 @@ static void run_batch(uint64_t nFrames, MAKEARGS make)
 template <class AR, class PL, bool INV, bool PERM>
 static void cfft_run_p(typename AR::elem *data, uint64_t nFrames, const void *tw, const uint16_t *perm, int shl1)
 {
-    typedef CfftBody<PL, INV, PERM> BODY;
+    /* the body the product uses for this plan: one thread per frame for the single-pass plans */
+    typedef typename std::conditional<(PL::NP == 1 && PL::T == 1), TinyCfftBody<PL, INV, PERM>, CfftBody<PL, INV, PERM>>::type BODY;
     typedef typename AR::elem elem;
     std::vector<typename AR::telem> ordered((size_t)PL::kTwEntries + 1);
     PL::build_twiddles((const elem *)tw, ordered.data());     /* same re-ordering the shim uploads */
@@ -141,8 +143,8 @@ int emu_rfft(uint32_t Nreal, const float *in, float *out, uint64_t nFrames, int 
 #define CASE(nc)                                                                                     \
     case nc: {                                                                                       \
         if (!ifft) {                                                                                 \
-            typedef PlanRfftFwd<nc>::type PL;                                                        \
-            typedef RfftFwdBody<PL> BODY;                                                            \
+            typedef std::conditional<(nc <= 64), PlanCfftF32<(nc <= 64 ? nc : 16)>::type, PlanRfftFwd<nc>::type>::type PL; \
+            typedef std::conditional<(nc <= 64), TinyRfftFwdBody<PlanCfftF32<(nc <= 64 ? nc : 16)>::type>, RfftFwdBody<PlanRfftFwd<nc>::type>>::type BODY; \
             std::vector<cf32> ordered((size_t)PL::kTwEntries + 1);                                   \
             PL::build_twiddles((const cf32 *)tw, ordered.data());                                    \
             run_batch<PL, BODY>(nFrames, [&](uint64_t f) {                                           \
@@ -152,8 +154,8 @@ int emu_rfft(uint32_t Nreal, const float *in, float *out, uint64_t nFrames, int 
                 return a;                                                                            \
             });                                                                                      \
         } else {                                                                                     \
-            typedef PlanRfftInv<nc>::type PL;                                                        \
-            typedef RfftInvBody<PL> BODY;                                                            \
+            typedef std::conditional<(nc <= 64), PlanCfftF32<(nc <= 64 ? nc : 16)>::type, PlanRfftInv<nc>::type>::type PL; \
+            typedef std::conditional<(nc <= 64), TinyRfftInvBody<PlanCfftF32<(nc <= 64 ? nc : 16)>::type>, RfftInvBody<PlanRfftInv<nc>::type>>::type BODY; \
             std::vector<cf32> ordered((size_t)PL::kTwEntries + 1);                                   \
             PL::build_twiddles((const cf32 *)tw, ordered.data());                                    \
             run_batch<PL, BODY>(nFrames, [&](uint64_t f) {                                           \
