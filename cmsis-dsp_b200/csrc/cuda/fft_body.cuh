@@ -37,6 +37,21 @@ template <class V> FFT_HD V ld_stream(const V *p) { return *p; }
 template <class V> FFT_HD void st_stream(V *p, V v) { *p = v; }
 #endif
 
+/* frame output: STAGED = the result goes into the frame's image in shared memory (a bulk copy
+ * takes it home); otherwise straight to global memory with a streaming hint */
+template <bool STAGED, class V> FFT_HD void st_out(V *p, V v)
+{
+    if (STAGED) *p = v;
+    else st_stream(p, v);
+}
+template <bool STAGED> FFT_HD void st_out_if(bool pred, cf32 *p, cf32 v)
+{
+    if (STAGED) {
+        if (pred) *p = v;
+    } else {
+        st_stream_if(pred, p, v);
+    }
+}
 /* frame input: STAGED = the frame was brought into shared memory by a bulk (TMA) copy and `p`
  * points there; otherwise `p` is global memory and is read once with a streaming hint */
 template <bool STAGED, class V> FFT_HD V ld_in(const V *p)
@@ -122,6 +137,7 @@ template <class PL, bool INV, bool PERM = false, bool STAGED = false> struct Cff
 
     /* phase 0 in two halves, for kernels whose input buffer doubles as the exchange buffer */
     static constexpr bool kHasPre = false, kHasPost = false;
+    static constexpr bool kImageOut = false;     /* pipelined kernel: results leave through the registers */
     static FFT_HD void set_scratch(Args &, xelem *) {}
     static FFT_HD void pre(const Args &, xelem *, int) {}
     static FFT_HD void post(const Args &, xelem *, int) {}
@@ -286,8 +302,8 @@ template <class PL, bool STAGED = false> struct RfftFwdBody {
             const cf32 tw = rfft_tw_rot<R, E0>(tw0);
             const int k0 = p + E0 * NBF;
             const cf32 o0 = rfft_split(A[E0], B[R - 1 - E0], tw), o1 = rfft_split(B[R - 1 - E0], A[E0], rfft_tw_mirror(tw));
-            st_stream_if(regular, a.out + k0, o0);
-            st_stream_if(regular, a.out + (N - k0), o1);
+            st_out_if<STAGED>(regular, a.out + k0, o0);
+            st_out_if<STAGED>(regular, a.out + (N - k0), o1);
             pair_loop<E0 + 1>(A, B, a, p, tw0, regular);
         }
     }
@@ -332,17 +348,21 @@ template <class PL, bool STAGED = false> struct RfftFwdBody {
             if (h >= R) break;
             if (h == 0) {
                 const cf32 X0 = scratch[0], XR = scratch[R];
-                st_stream(a.out + 0, cf32{X0.x + X0.y, X0.x - X0.y});       /* rfft_fast_f32.c:337-352 */
-                st_stream(a.out + N / 2, rfft_split(XR, XR, stw[q]));
+                st_out<STAGED>(a.out + 0, cf32{X0.x + X0.y, X0.x - X0.y});       /* rfft_fast_f32.c:337-352 */
+                st_out<STAGED>(a.out + N / 2, rfft_split(XR, XR, stw[q]));
             } else {
                 const int k = h * (NBF / 2);
                 const cf32 A = scratch[h], B = scratch[2 * R - h], tw = stw[q];
-                st_stream(a.out + k, rfft_split(A, B, tw));
-                st_stream(a.out + (N - k), rfft_split(B, A, rfft_tw_mirror(tw)));
+                st_out<STAGED>(a.out + k, rfft_split(A, B, tw));
+                st_out<STAGED>(a.out + (N - k), rfft_split(B, A, rfft_tw_mirror(tw)));
             }
         }
     }
     static constexpr bool kHasPre = false, kHasPost = true;
+    /* pipelined kernel: the packed spectrum is assembled in shared memory (regular bins and the 2R
+     * special bins alike) and leaves with one bulk store -- full-line writes instead of 8-byte
+     * pieces with holes at the special bins */
+    static constexpr bool kImageOut = STAGED;
     static FFT_HD void pre(const Args &, cf32 *, int) {}
     static FFT_HD void phase0_in(Regs &r, const Args &a, cf32 *, int i)
     {
@@ -518,6 +538,7 @@ template <class PL, bool STAGED = false> struct RfftInvBody {
             }
     }
     static constexpr bool kHasPre = true, kHasPost = false;
+    static constexpr bool kImageOut = false;
     static FFT_HD void pre(const Args &a, cf32 *, int i)
     {
         cf32 stw[kNS];

@@ -92,6 +92,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
                      : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     } while (!done);
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 /* generic-proxy accesses to a buffer are ordered before the async-proxy (TMA) write that refills it */
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -176,6 +187,7 @@ frame_kernel_pipe(typename BODY::Args base, uint64_t nFrames)
         const bool valid = frame < nFrames;
         typename BODY::Args a = BODY::for_frame(base, valid ? frame : 0);
         a.in = buf + fl * PL::N;                           /* the staged copy of this frame */
+        if constexpr (BODY::kImageOut) a.out = buf + fl * PL::N;   /* ... and, at the end, the image of its result */
         BODY::set_scratch(a, buf + PL::F * PL::kFrameElems + fl * PL::kSpecial);
         typename BODY::Regs r;
 
@@ -193,14 +205,31 @@ frame_kernel_pipe(typename BODY::Args base, uint64_t nFrames)
         unit_sync<PL>(unit);
         if (valid) BODY::last_in(r, sm, i);
         unit_sync<PL>(unit);                               /* the exchange has been read back: the buffer is free */
-        if (ut == 0 && gn < nGroups) {
-            fence_proxy_async();
-            fetch(gn);
-        }
-        if (valid) BODY::last_out_pk(r, a, i, pk);
-        if constexpr (BODY::kHasPost) {
+        if constexpr (!BODY::kImageOut) {
+            /* results leave through the registers; the next group's copy flies meanwhile */
+            if (ut == 0 && gn < nGroups) {
+                fence_proxy_async();
+                fetch(gn);
+            }
+            if (valid) BODY::last_out_pk(r, a, i, pk);
+            if constexpr (BODY::kHasPost) {
+                unit_sync<PL>(unit);
+                if (valid) BODY::post_pk(a, sm, i, pk);
+            }
+        } else {
+            /* results are assembled as a frame image in the buffer and leave with one bulk store */
+            if (valid) BODY::last_out_pk(r, a, i, pk);
+            if constexpr (BODY::kHasPost) {
+                unit_sync<PL>(unit);
+                if (valid) BODY::post_pk(a, sm, i, pk);
+            }
+            fence_proxy_async();                           /* image writes (generic proxy) -> visible to the TMA */
             unit_sync<PL>(unit);
-            if (valid) BODY::post_pk(a, sm, i, pk);
+            if (ut == 0) {
+                bulk_s2g(base.out + g * (uint64_t)kGroupElems, buf, group_bytes(g));
+                bulk_wait_read_all();                      /* the store has read the image: the buffer is free again */
+                if (gn < nGroups) fetch(gn);
+            }
         }
     }
 }
@@ -213,17 +242,6 @@ frame_kernel_pipe(typename BODY::Args base, uint64_t nFrames)
  * the 16-byte vector accesses of 8 consecutive lanes hit 32 different banks), transforms the frame
  * in registers -- single pass, no exchange -- writes the result back into the slot and sends it
  * home with one bulk store.  No LDG/STG at all on the data path. */
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes)
-{
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-
 template <class PL> struct TinySmem {
     typedef typename PL::Arith::elem elem;
     static constexpr int kWarps = 4, kCtaThreads = 32 * kWarps, kFramesPerCta = kCtaThreads;
