@@ -208,6 +208,25 @@ static int get_plan(int type, uint32_t fftLen, DevPlan *out)
     return CMSISDSP_CUDA_OK;
 }
 
+namespace b200fft {
+int shim_rfft_tables(uint32_t fftLenReal, const void **twForward, const float **twRfft)
+{
+    const int li = len_index(fftLenReal);
+    if (li < 1) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "unsupported rfft length (32..4096, power of two)");
+    DevPlan pl;
+    int rc = get_plan(CMSISDSP_CUDA_F32, fftLenReal / 2, &pl);
+    if (rc) return rc;
+    int dev;
+    rc = cur_device(&dev);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_dev[dev].twr[li]) return fail(CMSISDSP_CUDA_ERR_NO_PLAN, "no rfft plan uploaded for this (device, fftLen)");
+    *twForward = pl.tw_rfwd;
+    *twRfft = g_dev[dev].twr[li];
+    return CMSISDSP_CUDA_OK;
+}
+}
+
 /* ------------------------------------------------------------------ transforms */
 
 static int cfft_any(int type, void *d_p, uint32_t fftLen, uint64_t nFrames, uint8_t ifftFlag, uint8_t bitReverseFlag, void *stream)

@@ -36,5 +36,8 @@ struct KernelEntry {
 /* defined in cmsisdsp_cuda.cu */
 int shim_fail(int code, const char *what, cudaError_t e);
 void shim_count_launch();
+/* device tables of the forward rfft plan of real length fftLenReal on the current device
+ * (CMSISDSP_CUDA_ERR_NO_PLAN when cmsisdsp_cuda_plan_upload / _rfft_plan_upload have not run) */
+int shim_rfft_tables(uint32_t fftLenReal, const void **twForward, const float **twRfft);
 
 }  // namespace b200fft

@@ -35,6 +35,8 @@ static __thread tls_ctx g_ctx = { -1, {0}, {{0}}, {{0}} };
 static __thread arm_status g_last = ARM_MATH_SUCCESS;
 
 arm_status arm_cuda_last_status(void) { return g_last; }
+/* used by the other exec files of this library (arm_mfcc.c) */
+arm_status arm_cuda_set_last_status(arm_status s) { g_last = s; return s; }
 
 static int ctx_ready(void)
 {

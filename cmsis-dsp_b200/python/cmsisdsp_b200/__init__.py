@@ -44,6 +44,13 @@ class arm_rfft_fast_instance_f32(C.Structure):
     _fields_ = [("Sint", arm_cfft_instance_f32), ("fftLenRFFT", C.c_uint16), ("pTwiddleRFFT", C.POINTER(C.c_float))]
 
 
+class arm_mfcc_instance_f32(C.Structure):
+    _fields_ = [("dctCoefs", C.POINTER(C.c_float)), ("filterCoefs", C.POINTER(C.c_float)),
+                ("windowCoefs", C.POINTER(C.c_float)), ("filterPos", C.POINTER(C.c_uint32)),
+                ("filterLengths", C.POINTER(C.c_uint32)), ("fftLen", C.c_uint32), ("nbMelFilters", C.c_uint32),
+                ("nbDctOutputs", C.c_uint32), ("rfft", arm_rfft_fast_instance_f32)]
+
+
 _libs = {}
 
 
@@ -78,6 +85,9 @@ def cuda():
         "cmsisdsp_cuda_rfft_fast_f32": ([vp, vp, u32, u64, u8, vp], i),
         "cmsisdsp_cuda_last_error": ([], C.c_char_p), "cmsisdsp_cuda_launch_count": ([], u64),
         "cmsisdsp_cuda_set_kernel_flavour": ([i], i),
+        "cmsisdsp_cuda_mfcc_plan_create": ([u32, u32, u32, vp, vp, vp, vp, vp, C.POINTER(vp)], i),
+        "cmsisdsp_cuda_mfcc_plan_destroy": ([vp], i),
+        "cmsisdsp_cuda_mfcc_f32": ([vp, vp, u64, vp, u64, vp], i),
         "cmsisdsp_cuda_kernel_info": ([i, u32] + [C.POINTER(i)] * 5, i),
     }
     for name, (args, res) in sig.items():
@@ -112,6 +122,13 @@ def lib():
     L.arm_rfft_fast_batch_f32.argtypes = [C.POINTER(arm_rfft_fast_instance_f32), C.c_void_p, C.c_void_p, u32, u8]
     L.arm_rfft_fast_batch_f32.restype = i
     L.arm_cuda_last_status.argtypes, L.arm_cuda_last_status.restype = [], i
+    mp = C.POINTER(arm_mfcc_instance_f32)
+    L.arm_mfcc_init_f32.argtypes, L.arm_mfcc_init_f32.restype = [mp, u32, u32, u32] + [C.c_void_p] * 5, i
+    for n in (32, 64, 128, 256, 512, 1024, 2048, 4096):
+        f = getattr(L, f"arm_mfcc_init_{n}_f32")
+        f.argtypes, f.restype = [mp, u32, u32] + [C.c_void_p] * 5, i
+    L.arm_mfcc_f32.argtypes, L.arm_mfcc_f32.restype = [mp, C.c_void_p, C.c_void_p, C.c_void_p], None
+    L.arm_mfcc_batch_f32.argtypes, L.arm_mfcc_batch_f32.restype = [mp, C.c_void_p, u32, C.c_void_p, u32], i
     _libs["front"] = L
     return L
 
@@ -178,6 +195,34 @@ def rfft_batch(N, x, ifft=0):
     if st != ARM_MATH_SUCCESS:
         raise RuntimeError(f"arm_rfft_fast_batch_f32 -> {st}: {last_error()}")
     return out
+
+
+class Mfcc:
+    """arm_mfcc_instance_f32 initialised from a config dict (fftLen, nbMel, nbDct, dct, pos, len, coefs,
+    window as numpy arrays); keeps the arrays alive, as a C caller would keep its coefficient tables."""
+
+    def __init__(self, cfg):
+        self.cfg = cfg
+        self.arrs = [np.ascontiguousarray(cfg["dct"], np.float32), np.ascontiguousarray(cfg["pos"], np.uint32),
+                     np.ascontiguousarray(cfg["len"], np.uint32), np.ascontiguousarray(cfg["coefs"], np.float32),
+                     np.ascontiguousarray(cfg["window"], np.float32)]
+        self.S = arm_mfcc_instance_f32()
+        st = lib().arm_mfcc_init_f32(C.byref(self.S), int(cfg["fftLen"]), int(cfg["nbMel"]), int(cfg["nbDct"]),
+                                     *[a.ctypes.data for a in self.arrs])
+        if st != ARM_MATH_SUCCESS:
+            raise ValueError(f"arm_mfcc_init_f32 -> {st}")
+
+    def batch(self, x, hop=None, frames=None):
+        """arm_mfcc_batch_f32 on a host signal x; returns [frames, nbDct]"""
+        n = int(self.cfg["fftLen"])
+        x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1)
+        hop = n if hop is None else int(hop)
+        frames = (x.size - n) // hop + 1 if frames is None else int(frames)
+        out = np.empty((frames, int(self.cfg["nbDct"])), dtype=np.float32)
+        st = lib().arm_mfcc_batch_f32(C.byref(self.S), x.ctypes.data, hop, out.ctypes.data, frames)
+        if st != ARM_MATH_SUCCESS:
+            raise RuntimeError(f"arm_mfcc_batch_f32 -> {st}: {last_error()}")
+        return out
 
 
 # ---------------------------------------------------------------- device-pointer API (shim)

@@ -85,6 +85,20 @@ int  cmsisdsp_cuda_cfft_q15(void *d_p, uint32_t fftLen, uint64_t nFrames,
 int  cmsisdsp_cuda_rfft_fast_f32(const void *d_p, void *d_out, uint32_t fftLenReal, uint64_t nFrames,
                                  uint8_t ifftFlag, void *stream);
 
+/* ---- arm_mfcc_f32 front end (Source/TransformFunctions/arm_mfcc_f32.c:88-174, arm_mfcc_init_f32.c:91-121) ----
+ * One fused kernel per frame batch: normalise, window, rfft, magnitude, mel filter bank, log, DCT.
+ * The plan keeps device copies of the caller's coefficient arrays (the arguments of arm_mfcc_init_f32);
+ * it needs the rfft plan of fftLen uploaded first (cmsisdsp_cuda_plan_upload for fftLen/2 +
+ * cmsisdsp_cuda_rfft_plan_upload).  fftLen in {256, 512, 1024, 2048, 4096}. */
+int  cmsisdsp_cuda_mfcc_plan_create(uint32_t fftLen, uint32_t nbMelFilters, uint32_t nbDctOutputs,
+                                    const float *dctCoefs, const uint32_t *filterPos, const uint32_t *filterLengths,
+                                    const float *filterCoefs, const float *windowCoefs, void **plan);
+int  cmsisdsp_cuda_mfcc_plan_destroy(void *plan);
+/* frame f = fftLen floats starting at d_src + f*strideFloats (strideFloats = fftLen: back to back;
+ * smaller: overlapping frames; must be even); d_dst: nFrames * nbDctOutputs floats.  d_src is not modified. */
+int  cmsisdsp_cuda_mfcc_f32(const void *plan, const void *d_src, uint64_t strideFloats, void *d_dst,
+                            uint64_t nFrames, void *stream);
+
 /* ---- tuning / diagnostics ---- */
 /* Kernel flavour used by the transform entry points: -1 = the measured default of each (op, length),
  * 0 = direct (one CTA per frame group, loads into registers), 1 = persistent TMA-fed kernel where the

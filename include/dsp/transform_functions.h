@@ -106,6 +106,57 @@ arm_status arm_rfft_fast_init_4096_f32(arm_rfft_fast_instance_f32 *S);
 arm_status arm_rfft_fast_init_f32(arm_rfft_fast_instance_f32 *S, uint16_t fftLen);
 void arm_rfft_fast_f32(const arm_rfft_fast_instance_f32 *S, float32_t *p, float32_t *pOut, uint8_t ifftFlag);
 
+/* ---------------------------------------------------------------- f32 MFCC (RFFT based)
+ * Instance and init are the reference's (Include/dsp/transform_functions.h:856-998, generic branch);
+ * supported fftLen here: 256, 512, 1024, 2048, 4096. */
+typedef struct
+{
+     const float32_t *dctCoefs;       /* DCT matrix, nbDctOutputs x nbMelFilters */
+     const float32_t *filterCoefs;    /* packed mel filter taps */
+     const float32_t *windowCoefs;    /* fftLen window coefficients */
+     const uint32_t  *filterPos;      /* first spectrum bin of each mel filter */
+     const uint32_t  *filterLengths;  /* number of taps of each mel filter */
+     uint32_t fftLen;
+     uint32_t nbMelFilters;
+     uint32_t nbDctOutputs;
+     arm_rfft_fast_instance_f32 rfft;
+} arm_mfcc_instance_f32;
+
+arm_status arm_mfcc_init_f32(arm_mfcc_instance_f32 *S, uint32_t fftLen, uint32_t nbMelFilters, uint32_t nbDctOutputs,
+                             const float32_t *dctCoefs, const uint32_t *filterPos, const uint32_t *filterLengths,
+                             const float32_t *filterCoefs, const float32_t *windowCoefs);
+arm_status arm_mfcc_init_32_f32(arm_mfcc_instance_f32 *S, uint32_t nbMelFilters, uint32_t nbDctOutputs,
+                             const float32_t *dctCoefs, const uint32_t *filterPos, const uint32_t *filterLengths,
+                             const float32_t *filterCoefs, const float32_t *windowCoefs);
+arm_status arm_mfcc_init_64_f32(arm_mfcc_instance_f32 *S, uint32_t nbMelFilters, uint32_t nbDctOutputs,
+                             const float32_t *dctCoefs, const uint32_t *filterPos, const uint32_t *filterLengths,
+                             const float32_t *filterCoefs, const float32_t *windowCoefs);
+arm_status arm_mfcc_init_128_f32(arm_mfcc_instance_f32 *S, uint32_t nbMelFilters, uint32_t nbDctOutputs,
+                             const float32_t *dctCoefs, const uint32_t *filterPos, const uint32_t *filterLengths,
+                             const float32_t *filterCoefs, const float32_t *windowCoefs);
+arm_status arm_mfcc_init_256_f32(arm_mfcc_instance_f32 *S, uint32_t nbMelFilters, uint32_t nbDctOutputs,
+                             const float32_t *dctCoefs, const uint32_t *filterPos, const uint32_t *filterLengths,
+                             const float32_t *filterCoefs, const float32_t *windowCoefs);
+arm_status arm_mfcc_init_512_f32(arm_mfcc_instance_f32 *S, uint32_t nbMelFilters, uint32_t nbDctOutputs,
+                             const float32_t *dctCoefs, const uint32_t *filterPos, const uint32_t *filterLengths,
+                             const float32_t *filterCoefs, const float32_t *windowCoefs);
+arm_status arm_mfcc_init_1024_f32(arm_mfcc_instance_f32 *S, uint32_t nbMelFilters, uint32_t nbDctOutputs,
+                             const float32_t *dctCoefs, const uint32_t *filterPos, const uint32_t *filterLengths,
+                             const float32_t *filterCoefs, const float32_t *windowCoefs);
+arm_status arm_mfcc_init_2048_f32(arm_mfcc_instance_f32 *S, uint32_t nbMelFilters, uint32_t nbDctOutputs,
+                             const float32_t *dctCoefs, const uint32_t *filterPos, const uint32_t *filterLengths,
+                             const float32_t *filterCoefs, const float32_t *windowCoefs);
+arm_status arm_mfcc_init_4096_f32(arm_mfcc_instance_f32 *S, uint32_t nbMelFilters, uint32_t nbDctOutputs,
+                             const float32_t *dctCoefs, const uint32_t *filterPos, const uint32_t *filterLengths,
+                             const float32_t *filterCoefs, const float32_t *windowCoefs);
+/* pSrc (fftLen samples) is destroyed like in the reference; pTmp (2*fftLen floats there) is not used */
+void arm_mfcc_f32(const arm_mfcc_instance_f32 *S, float32_t *pSrc, float32_t *pDst, float32_t *pTmp);
+/* B200 extension: nFrames frames taken every `hop` samples from pSrc (hop = fftLen: back to back; smaller:
+ * overlapping; must be even), nbDctOutputs coefficients per frame written to pDst.  pSrc is left untouched.
+ * Host or device pointers. */
+arm_status arm_mfcc_batch_f32(const arm_mfcc_instance_f32 *S, const float32_t *pSrc, uint32_t hop,
+                              float32_t *pDst, uint32_t nFrames);
+
 /* ---------------------------------------------------------------- B200 extension: batches
  *
  * nFrames frames stored back to back (frame stride 2*fftLen scalars for CFFT, fftLenRFFT

@@ -50,6 +50,13 @@ void orc_cfft_q31_batch(uint32_t N, int32_t *p, uint64_t nFrames, int ifft, int 
 void orc_cfft_q15_batch(uint32_t N, int16_t *p, uint64_t nFrames, int ifft, int bitrev, int nthreads);
 void orc_rfft_fast_f32_batch(uint32_t N, float *p, float *pOut, uint64_t nFrames, int ifft, int nthreads);
 
+/* ---- arm_mfcc_f32 (Source/TransformFunctions/arm_mfcc_f32.c:88-174), RFFT based ---- */
+void orc_mfcc_f32(uint32_t fftLen, uint32_t nbMel, uint32_t nbDct, const float *dct, const uint32_t *pos,
+                  const uint32_t *len, const float *coefs, const float *window, float *pSrc, float *pDst, float *pTmp);
+void orc_mfcc_f32_batch(uint32_t fftLen, uint32_t nbMel, uint32_t nbDct, const float *dct, const uint32_t *pos,
+                        const uint32_t *len, const float *coefs, const float *window, const float *src,
+                        uint64_t stride, float *dst, uint64_t nFrames, int nthreads);
+
 /* table digests used by the golden checks (FNV-1a 64 over the raw bytes) */
 uint64_t orc_fnv1a64(const void *data, uint64_t nbytes);
 

@@ -79,3 +79,46 @@ uint32_t ref_sizeof_cfft_instance_f32(void) { return (uint32_t)sizeof(arm_cfft_i
 uint32_t ref_sizeof_cfft_instance_q31(void) { return (uint32_t)sizeof(arm_cfft_instance_q31); }
 uint32_t ref_sizeof_cfft_instance_q15(void) { return (uint32_t)sizeof(arm_cfft_instance_q15); }
 uint32_t ref_sizeof_rfft_fast_instance_f32(void) { return (uint32_t)sizeof(arm_rfft_fast_instance_f32); }
+
+/* ---- arm_mfcc_f32 batch driver (frames start `stride` floats apart; src is left untouched) ---- */
+#include <string.h>
+typedef struct {
+    arm_mfcc_instance_f32 S; const float *src; uint64_t stride; float *dst; uint64_t f0, f1;
+} mjob_t;
+static void *mworker(void *arg)
+{
+    mjob_t *j = arg;
+    const uint32_t n = j->S.fftLen;
+    float *frame = malloc(sizeof(float) * n), *tmp = malloc(sizeof(float) * 2 * n);
+    for (uint64_t f = j->f0; f < j->f1; f++) {
+        memcpy(frame, j->src + f * j->stride, sizeof(float) * n);
+        arm_mfcc_f32(&j->S, frame, j->dst + f * j->S.nbDctOutputs, tmp);
+    }
+    free(frame); free(tmp);
+    return NULL;
+}
+int ref_mfcc_f32_batch(uint32_t fftLen, uint32_t nbMel, uint32_t nbDct, const float *dct, const uint32_t *pos,
+                       const uint32_t *len, const float *coefs, const float *window, const float *src,
+                       uint64_t stride, float *dst, uint64_t nFrames, int nthreads)
+{
+    arm_mfcc_instance_f32 S;
+    if (arm_mfcc_init_f32(&S, fftLen, nbMel, nbDct, dct, pos, len, coefs, window) != ARM_MATH_SUCCESS) return -1;
+    if (nthreads < 1) nthreads = 1;
+    if ((uint64_t)nthreads > nFrames) nthreads = nFrames ? (int)nFrames : 1;
+    pthread_t *th = malloc((size_t)nthreads * sizeof *th);
+    mjob_t *jobs = malloc((size_t)nthreads * sizeof *jobs);
+    uint64_t per = (nFrames + (uint64_t)nthreads - 1) / (uint64_t)nthreads;
+    for (int t = 0; t < nthreads; t++) {
+        uint64_t f0 = per * (uint64_t)t, f1 = f0 + per;
+        if (f0 > nFrames) f0 = nFrames;
+        if (f1 > nFrames) f1 = nFrames;
+        jobs[t] = (mjob_t){S, src, stride, dst, f0, f1};
+        if (nthreads == 1) mworker(&jobs[t]);
+        else pthread_create(&th[t], NULL, mworker, &jobs[t]);
+    }
+    if (nthreads > 1)
+        for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+    free(th); free(jobs);
+    return 0;
+}
+uint32_t ref_sizeof_mfcc_instance_f32(void) { return (uint32_t)sizeof(arm_mfcc_instance_f32); }

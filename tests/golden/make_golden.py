@@ -11,6 +11,9 @@ Outputs
         arrays keyed "<type>/<c|r>/<noisy|step>/<N>/<input|ref|ifft_input>".
   fft_bin_example.npz     Examples/ARM/arm_fft_bin_example/arm_fft_bin_data.c
         (testInput_f32_10khz; expected peak bin 213).
+  mfcc_patterns.npz       Testing/Source/Tests/mfccdata.c coefficient arrays (DCT 13x20, Hamming
+        windows, mel filter banks for 256/512/1024) and Testing/Patterns/DSP/Transform/MFCCF32/*
+        (noise / sine inputs with their float64-computed references).
   ref_digests.json        sha256 of the outputs of the COMPILED REFERENCE
         (oracle/_ref/libcmsisdsp_ref.so) on seeded inputs, per
         (type, N, ifft, bitrev) -- pins bits where the reference's own tests only
@@ -66,6 +69,30 @@ def main():
     assert vals.size == 2048, vals.size
     np.savez_compressed(os.path.join(HERE, "fft_bin_example.npz"), input=vals, ref_index=np.int32(213))
     print("fft_bin_example.npz:", vals.size, "floats")
+
+    # ---- MFCC: coefficient arrays of Testing/Source/Tests/mfccdata.c + the reference's patterns
+    src = open(os.path.join(REF, "Testing/Source/Tests/mfccdata.c")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+
+    def c_array(name, dtype):
+        m = re.search(name + r"\[[A-Z0-9_]+\]\s*=\s*\{(.*?)\};", src, flags=re.S)
+        toks = [t.strip().rstrip("f") for t in m.group(1).split(",") if t.strip()]
+        return np.array([float(t) if dtype == np.float32 else int(t) for t in toks], dtype=dtype)
+
+    mf = {"dct": c_array("mfcc_dct_coefs_config1_f32", np.float32)}
+    for cfg, n in ((1, 1024), (2, 512), (3, 256)):
+        mf[f"window/{n}"] = c_array(f"mfcc_window_coefs_config{cfg}_f32", np.float32)
+        mf[f"pos/{n}"] = c_array(f"mfcc_filter_pos_config{cfg}_f32", np.uint32)
+        mf[f"len/{n}"] = c_array(f"mfcc_filter_len_config{cfg}_f32", np.uint32)
+        mf[f"coefs/{n}"] = c_array(f"mfcc_filter_coefs_config{cfg}_f32", np.float32)
+        assert mf[f"window/{n}"].size == n and mf[f"coefs/{n}"].size == int(mf[f"len/{n}"].sum())
+        for sig in ("Noise", "Sine"):
+            for what in ("Input", "Ref"):
+                fn = os.path.join(PAT, "MFCCF32", f"MFCC{sig}{what}_{n}_1_f32.txt")
+                mf[f"{sig.lower()}/{n}/{what.lower()}"] = read_pattern(fn).view(np.float32)
+    assert mf["dct"].size == 260
+    np.savez_compressed(os.path.join(HERE, "mfcc_patterns.npz"), **mf)
+    print("mfcc_patterns.npz:", len(mf), "arrays")
 
     from oracle_lib import LENGTHS, RLENGTHS, ref
     from seeded_inputs import cfft_input, rfft_input

@@ -63,6 +63,24 @@ class _Lib:
         self._fn("rfft_fast_f32_batch")(N, p.ctypes.data, out.ctypes.data, p.size // N, int(ifft), int(threads))
         return (out, p) if return_clobbered else out
 
+    def mfcc(self, cfg, x, stride=None, frames=None, threads=1):
+        """arm_mfcc_f32 over frames taken from the 1-D signal x every `stride` samples.
+        cfg: dict(fftLen, nbMel, nbDct, dct, pos, len, coefs, window) of numpy arrays."""
+        n = int(cfg["fftLen"])
+        x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1)
+        stride = n if stride is None else int(stride)
+        frames = (x.size - n) // stride + 1 if frames is None else int(frames)
+        assert (frames - 1) * stride + n <= x.size
+        out = np.empty((frames, int(cfg["nbDct"])), dtype=np.float32)
+        arrs = [np.ascontiguousarray(cfg["dct"], np.float32), np.ascontiguousarray(cfg["pos"], np.uint32),
+                np.ascontiguousarray(cfg["len"], np.uint32), np.ascontiguousarray(cfg["coefs"], np.float32),
+                np.ascontiguousarray(cfg["window"], np.float32)]
+        fn = self._fn("mfcc_f32_batch")
+        fn.argtypes = [C.c_uint32] * 3 + [C.c_void_p] * 6 + [C.c_uint64, C.c_void_p, C.c_uint64, C.c_int]
+        fn(n, int(cfg["nbMel"]), int(cfg["nbDct"]), *[a.ctypes.data for a in arrs], x.ctypes.data, stride,
+           out.ctypes.data, frames, int(threads))
+        return out
+
     def table(self, name, N):
         n = {"twiddle_f32": 2 * N, "twiddle_q31": 3 * N // 2, "twiddle_q15": 3 * N // 2,
              "twiddle_rfft_f32": N}[name]
@@ -105,3 +123,11 @@ def perm_from_swaps(N, tab):
     for x, y in t:
         a[x], a[y] = a[y], a[x]
     return a
+
+
+def mfcc_config(n):
+    """The reference's own MFCC test configuration for fftLen n in {256, 512, 1024}
+    (Testing/Source/Tests/mfccdata.c via tests/golden/mfcc_patterns.npz): 20 mel filters, 13 DCT outputs."""
+    d = np.load(os.path.join(ROOT, "tests", "golden", "mfcc_patterns.npz"))
+    return dict(fftLen=n, nbMel=20, nbDct=13, dct=d["dct"], pos=d[f"pos/{n}"], len=d[f"len/{n}"],
+                coefs=d[f"coefs/{n}"], window=d[f"window/{n}"])

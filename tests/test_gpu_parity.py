@@ -300,3 +300,76 @@ def test_direct_and_pipelined_flavours_agree_bit_for_bit():
     finally:
         cu.cmsisdsp_cuda_set_kernel_flavour(-1)
     assert cu.cmsisdsp_cuda_set_kernel_flavour(7) != 0
+
+
+# ------------------------------------------------------------------ MFCC front end (BASELINE config 4)
+
+def _mfcc_ok(got, want):
+    """the reference's own MFCC thresholds (Testing/Source/Tests/MFCCF32.cpp:7-16)"""
+    got, want = got.astype(np.float64), want.astype(np.float64)
+    assert np.all(np.abs(got - want) <= 1e-5 + 1.2e-3 * np.abs(want)), float(np.abs(got - want).max())
+    snr = 10 * np.log10((want ** 2).sum() / max(((want - got) ** 2).sum(), 1e-300))
+    assert snr >= 115.0, snr
+
+
+@pytest.mark.parametrize("n", [256, 512, 1024])
+def test_mfcc_reference_patterns_and_oracle(n):
+    from oracle_lib import mfcc_config
+    d = np.load(os.path.join(HERE, "golden", "mfcc_patterns.npz"))
+    cfg = mfcc_config(n)
+    m = cd.Mfcc(cfg)
+    for sig in ("noise", "sine"):                                   # the reference's own vectors
+        _mfcc_ok(m.batch(d[f"{sig}/{n}/input"])[0], d[f"{sig}/{n}/ref"])
+    rng = np.random.default_rng(n)
+    t = np.arange(300 * n) / 16000.0
+    x = (0.5 * np.sin(2 * np.pi * 440 * t) + 0.3 * np.sin(2 * np.pi * 1300 * t) + 0.2 * np.sin(2 * np.pi * 3100 * t)
+         + 0.1 * rng.standard_normal(t.size)).astype(np.float32)
+    x[5 * n:6 * n] = 0.0                                            # an all-zero frame (maxValue == 0 branch)
+    for hop in (n, n // 4, 2 * n):                                  # back to back, overlapping, gapped
+        want = oracle().mfcc(cfg, x, stride=hop, threads=NT)
+        got = m.batch(x, hop=hop)
+        assert got.shape == want.shape and got.shape[0] >= 149
+        _mfcc_ok(got, want)
+    # legacy single-frame call: same numbers, pSrc may be clobbered
+    frame = x[:n].copy()
+    one = np.zeros(13, dtype=np.float32)
+    tmp = np.zeros(2 * n, dtype=np.float32)
+    cd.lib().arm_mfcc_f32(C.byref(m.S), frame.ctypes.data, one.ctypes.data, tmp.ctypes.data)
+    assert cd.lib().arm_cuda_last_status() == 0
+    _mfcc_ok(one, oracle().mfcc(cfg, x[:n])[0])
+
+
+def test_mfcc_config4_synthetic_audio_large_batch():
+    """BASELINE config 4 on one GPU: 16 kHz synthetic audio (3 sines + noise), 1024-sample frames, the
+    reference's 20-mel / 13-DCT / Hamming configuration; device-resident, 2^17 frames, stratified oracle check"""
+    torch = pytest.importorskip("torch")
+    from oracle_lib import mfcc_config
+    dev = torch.device("cuda", 0)
+    n, B = 1024, 1 << 17
+    cfg = mfcc_config(n)
+    m = cd.Mfcc(cfg)
+    g = torch.Generator(device=dev).manual_seed(4)
+    t = torch.arange(B * n, device=dev, dtype=torch.float64) / 16000.0
+    x = (0.5 * torch.sin(2 * np.pi * 440 * t) + 0.3 * torch.sin(2 * np.pi * 1300 * t) + 0.2 * torch.sin(2 * np.pi * 3100 * t)).float()
+    x += 0.1 * torch.randn(B * n, device=dev, generator=g)
+    out = torch.empty(B, 13, device=dev)
+    assert cd.lib().arm_mfcc_batch_f32(C.byref(m.S), x.data_ptr(), n, out.data_ptr(), B) == 0, cd.last_error()
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(out).all().item())
+    idx = np.arange(0, B, B // 2048)
+    xs = x.view(B, n)[torch.from_numpy(idx).to(dev)].cpu().numpy()
+    want = oracle().mfcc(cfg, xs.reshape(-1), threads=NT)
+    _mfcc_ok(out[torch.from_numpy(idx).to(dev)].cpu().numpy(), want)
+
+
+def test_mfcc_argument_errors():
+    from oracle_lib import mfcc_config
+    m = cd.Mfcc(mfcc_config(256))
+    x = np.zeros(1024, dtype=np.float32)
+    out = np.zeros(13 * 4, dtype=np.float32)
+    L = cd.lib()
+    assert L.arm_mfcc_batch_f32(C.byref(m.S), x.ctypes.data, 255, out.ctypes.data, 2) == cd.ARM_MATH_ARGUMENT_ERROR   # odd hop
+    assert L.arm_mfcc_batch_f32(C.byref(m.S), None, 256, out.ctypes.data, 2) == cd.ARM_MATH_ARGUMENT_ERROR
+    assert L.arm_mfcc_batch_f32(C.byref(m.S), x.ctypes.data, 256, out.ctypes.data, 0) == 0                            # empty batch
+    bad = cd.arm_mfcc_instance_f32()
+    assert L.arm_mfcc_init_f32(C.byref(bad), 100, 20, 13, *[a.ctypes.data for a in m.arrs]) == cd.ARM_MATH_ARGUMENT_ERROR

@@ -63,3 +63,21 @@ def test_digests_of_compiled_reference():
 def test_unsupported_length_is_noop():
     x = np.arange(2 * 24, dtype=np.float32)
     assert np.array_equal(oracle().cfft("f32", 24, x), x)
+
+
+# ------------------------------------------------------------------ MFCC (BASELINE config 4)
+
+@pytest.mark.parametrize("n", [256, 512, 1024])
+def test_mfcc_patterns(n):
+    """the reference's own MFCC vectors and thresholds (Testing/Source/Tests/MFCCF32.cpp:7-16:
+    SNR >= 115 dB, |err| <= 1e-5 + 1.2e-3 |ref|)"""
+    from oracle_lib import mfcc_config
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "mfcc_patterns.npz"))
+    cfg = mfcc_config(n)
+    for sig in ("noise", "sine"):
+        got = oracle().mfcc(cfg, d[f"{sig}/{n}/input"])[0].astype(np.float64)
+        ref = d[f"{sig}/{n}/ref"].astype(np.float64)
+        assert got.shape == ref.shape == (13,)
+        snr = 10 * np.log10((ref ** 2).sum() / ((ref - got) ** 2).sum())
+        assert snr >= 115.0, (n, sig, snr)
+        assert np.all(np.abs(got - ref) <= 1e-5 + 1.2e-3 * np.abs(ref)), (n, sig)

@@ -70,3 +70,19 @@ def test_threads_agree():
     x = rng.standard_normal((37, 2 * 256)).astype(np.float32)
     assert np.array_equal(oracle().cfft("f32", 256, x, threads=1), oracle().cfft("f32", 256, x, threads=5))
     assert np.array_equal(ref().cfft("f32", 256, x, threads=1), ref().cfft("f32", 256, x, threads=5))
+
+
+@pytest.mark.parametrize("n", [256, 512, 1024])
+def test_mfcc_bit_exact(n):
+    """oracle restatement of arm_mfcc_f32 == compiled reference, bit for bit, incl. overlapping frames"""
+    from oracle_lib import mfcc_config
+    cfg = mfcc_config(n)
+    rng = np.random.default_rng(n)
+    t = np.arange(40 * n) / 16000.0
+    x = (0.5 * np.sin(2 * np.pi * 440 * t) + 0.3 * np.sin(2 * np.pi * 1300 * t) + 0.1 * rng.standard_normal(t.size)).astype(np.float32)
+    x[3 * n:4 * n] = 0.0                                   # an all-zero frame: maxValue == 0 branch
+    for stride in (n, n // 4):
+        a = oracle().mfcc(cfg, x, stride=stride, threads=3)
+        b = ref().mfcc(cfg, x, stride=stride, threads=2)
+        assert a.shape == b.shape and a.shape[0] >= 37
+        assert np.array_equal(a, b), (n, stride, np.abs(a - b).max())

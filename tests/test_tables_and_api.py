@@ -85,7 +85,7 @@ def test_shared_objects_export_every_declared_symbol():
         assert hasattr(cu, name), name
     fr = cd.lib()
     names = _declared_functions(os.path.join(ROOT, "include", "dsp", "transform_functions.h"))
-    assert len(names) == 48      # 3x(9 per-length inits + init + exec) + rfft (8+1+1) + 4 batch + last_status
+    assert len(names) == 59      # 3x(9 per-length inits + init + exec) + rfft (8+1+1) + 4 batch + last_status + mfcc (8+1+1+1)
     for name in names:
         assert hasattr(fr, name), name
     for N in LENGTHS:
