@@ -47,12 +47,6 @@ template <int T> __device__ __forceinline__ float group_max(float v)
     for (int o = T / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
-template <int T> __device__ __forceinline__ float group_sum(float v)
-{
-#pragma unroll
-    for (int o = T / 2; o > 0; o >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
 
 template <int NC>
 __global__ void __launch_bounds__(128) mfcc_kernel(MfccArgs a, uint64_t nFrames)   /* every forward rfft plan has <= 128 threads per CTA */
@@ -89,23 +83,23 @@ __global__ void __launch_bounds__(128) mfcc_kernel(MfccArgs a, uint64_t nFrames)
         const float2 w = win[i + T * m];
         buf[i + T * m] = cf32{__fmul_rn(__fmul_rn(v[m].x, inv), w.x), __fmul_rn(__fmul_rn(v[m].y, inv), w.y)};
     }
-    __syncthreads();
+    __syncwarp();      /* a frame is private to its T lanes of one warp */
 
     /* 2. forward real FFT, shared memory to shared memory (arm_mfcc_f32.c:137) */
     typename BODY::Args ra{buf, buf, a.tw, a.twr, smem + F * PL::kFrameElems + fl * PL::kSpecial};
     {
         typename BODY::Regs r;
         BODY::phase0_in(r, ra, buf, i);
-        __syncthreads();
+        __syncwarp();      /* a frame is private to its T lanes of one warp */
         BODY::phase0_out(r, buf, i);
-        __syncthreads();
+        __syncwarp();      /* a frame is private to its T lanes of one warp */
         BODY::last_in(r, buf, i);
-        __syncthreads();
+        __syncwarp();      /* a frame is private to its T lanes of one warp */
         BODY::last_out(r, ra, i);                            /* regular bins -> packed spectrum in buf */
     }
-    __syncthreads();
+    __syncwarp();      /* a frame is private to its T lanes of one warp */
     BODY::post(ra, buf, i);                                  /* the 2R special bins */
-    __syncthreads();
+    __syncwarp();      /* a frame is private to its T lanes of one warp */
 
     /* 3. magnitudes of bins 0..NC-1, Nyquist (packed into bin 0) dropped, times max (:138-146) */
     float mag[E];
@@ -117,22 +111,22 @@ __global__ void __launch_bounds__(128) mfcc_kernel(MfccArgs a, uint64_t nFrames)
         const float s = sqrtf(__fadd_rn(__fmul_rn(z.x, z.x), __fmul_rn(z.y, z.y)));
         mag[m] = (mx != 0.0f) ? __fmul_rn(s, mx) : s;
     }
-    __syncthreads();
+    __syncwarp();      /* a frame is private to its T lanes of one warp */
     float *magbuf = reinterpret_cast<float *>(buf);
 #pragma unroll
     for (int m = 0; m < E; m++) magbuf[i + T * m] = mag[m];
-    __syncthreads();
+    __syncwarp();      /* a frame is private to its T lanes of one warp */
 
-    /* 4. mel filter bank, + 1e-6, log (:150-165); the T threads of the frame share each dot product */
-    for (uint32_t f = 0; f < a.nbMel; f++) {
-        const uint32_t p0 = a.pos[f], n = a.len[f];
-        const float *c = a.coefs + a.off[f];
+    /* 4. mel filter bank, + 1e-6, log (:150-165): a lane owns whole filters and sums their taps in the
+     * reference's order */
+    for (uint32_t f = i; f < a.nbMel; f += T) {
+        const uint32_t n = a.len[f];
+        const float *c = a.coefs + a.off[f], *mg = magbuf + a.pos[f];
         float s = 0.0f;
-        for (uint32_t t = i; t < n; t += T) s = __fadd_rn(s, __fmul_rn(magbuf[p0 + t], c[t]));
-        s = group_sum<T>(s);
-        if (i == 0) mel[f] = logf(__fadd_rn(s, 1.0e-6f));
+        for (uint32_t t = 0; t < n; t++) s = __fadd_rn(s, __fmul_rn(mg[t], c[t]));
+        mel[f] = logf(__fadd_rn(s, 1.0e-6f));
     }
-    __syncthreads();
+    __syncwarp();
 
     /* 5. DCT matrix (:167-171) */
     if (valid) {

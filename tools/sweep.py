@@ -54,6 +54,8 @@ def main():
         for N in [int(v) for v in args.lens.split(",")]:
             if op.startswith("rfft") and N < 32:
                 continue
+            if op == "mfcc" and N not in (256, 512, 1024):
+                continue
             nbytes = args.mib << 20
             if op.startswith("cfft"):
                 kind = op.split("_")[1]
@@ -69,6 +71,19 @@ def main():
                 alg = 2 * B * N * esz
                 samples = B * N
                 info = cd.kernel_info({"f32": 0, "q31": 1, "q15": 2}[kind], N)
+            elif op == "mfcc":
+                sys.path.insert(0, os.path.join(ROOT, "tests"))
+                from oracle_lib import mfcc_config
+                m = cd.Mfcc(mfcc_config(N))
+                B = nbytes // (4 * N)
+                a = torch.randn(B * N, device=dev)
+                b = torch.empty(B, 13, device=dev)
+                L = cd.lib()
+                fn = lambda: L.arm_mfcc_batch_f32(C.byref(m.S), a.data_ptr(), N, b.data_ptr(), B)
+                fn()                                   # creates the device plan
+                alg = B * (4 * N + 4 * 13)
+                samples = B * N
+                info = dict(threads_per_cta=0, frames_per_cta=0, smem_bytes=0, regs_per_thread=0, ctas_per_sm=0)
             else:
                 B = nbytes // (4 * N)
                 cd.ensure_rfft_plans(N)
