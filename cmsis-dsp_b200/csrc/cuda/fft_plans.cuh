@@ -78,6 +78,10 @@ FIXPLAN(32,   1,   128, 0, 0, PF(ST_PRE2, ST_FIRST4, ST_LAST4))
 FIXPLAN(64,   1,   128, 0, 0, PF(ST_FIRST4, ST_MID4, ST_LAST4))
 FIXPLAN(128,  8,   16,  4, 1, PF(ST_PRE2, ST_FIRST4), PF(ST_MID4, ST_LAST4))
 FIXPLAN(256,  16,  8,   4, 1, PF(ST_FIRST4, ST_MID4), PF(ST_MID4, ST_LAST4))
+/* N >= 512: three passes of 16 points per thread.  Two passes of 32/64 points per thread (the f32
+ * recipe) were measured 15-45 % SLOWER here: a fixed-point pass cannot factor its twiddles (the
+ * reference multiplies by specific table entries, truncating), so a radix-64 pass loads 63 of them
+ * per thread and the low-occupancy kernel waits on those loads */
 FIXPLAN(512,  32,  4,   4, 1, PF(ST_PRE2, ST_FIRST4), PF(ST_MID4, ST_MID4), PF(ST_LAST4))
 FIXPLAN(1024, 64,  2,   4, 1, PF(ST_FIRST4, ST_MID4), PF(ST_MID4, ST_MID4), PF(ST_LAST4))
 FIXPLAN(2048, 128, 1,   4, 1, PF(ST_PRE2, ST_FIRST4), PF(ST_MID4, ST_MID4), PF(ST_MID4, ST_LAST4))

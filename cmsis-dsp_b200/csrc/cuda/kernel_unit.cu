@@ -461,7 +461,7 @@ template <class PL> static size_t twiddles_of(const void *base, void *hostOut)
  * single-pass plans (N <= 64). */
 template <class P> struct PipeOf {
     static constexpr bool kTiny = (P::NP == 1) && (P::T == 1);
-    static constexpr bool kPipe = (P::NP == 2) && (sizeof(typename P::Arith::elem) == 8) && (P::E >= 32 || (KU_OP >= 3 && P::kSpecial > 0));
+    static constexpr bool kPipe = (P::NP == 2) && IsF32<typename P::Arith::elem>::value && (P::E >= 32 || (KU_OP >= 3 && P::kSpecial > 0));
     static constexpr bool kHas = kTiny || kPipe;
     /* default flavour of this unit, from the A/B sweeps in profiles/ (CMSISDSP_CUDA_KERNEL overrides):
      * the TMA-fed kernels win wherever they exist, except the inverse rfft at complex length 512 */
