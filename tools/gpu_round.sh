@@ -1,3 +1,8 @@
+#!/bin/bash
+# One GPU round: parity tests, the bench (both arms), the ncu launch list and one full capture of the
+# bench kernels, and the throughput sweep.  Run on a B200 box from the repo root:
+#     gpurun --timeout 1500 -- 'bash tools/gpu_round.sh'
+# then, back on the build box:  python tools/make_profiles.py <tag>   (writes profiles/<tag>_*)
 set -x
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 python bench.py > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; tail -c 2600 gpurun_out/bench_full.json
