@@ -66,7 +66,8 @@ static int len_index(uint32_t n)
 /* kernel flavour (kernel_entry.h): the unit's measured preference, unless
  * CMSISDSP_CUDA_KERNEL=direct|pipe forces a flavour (for A/B measurements) */
 static std::atomic<int> g_flavour{-2};           /* -2: not read yet, -1: per-unit default, else forced */
-static int choose_flavour(const KernelEntry *ke)
+namespace b200fft {
+int shim_forced_flavour()
 {
     int forced = g_flavour.load(std::memory_order_relaxed);
     if (forced == -2) {
@@ -74,6 +75,12 @@ static int choose_flavour(const KernelEntry *ke)
         forced = !e ? -1 : (!strcmp(e, "direct") ? KF_DIRECT : (!strcmp(e, "pipe") ? KF_PIPE : -1));
         g_flavour.store(forced, std::memory_order_relaxed);
     }
+    return forced;
+}
+}
+static int choose_flavour(const KernelEntry *ke)
+{
+    const int forced = shim_forced_flavour();
     if (forced >= 0) return (forced == KF_PIPE && !ke->hasPipe) ? KF_DIRECT : forced;
     return ke->preferPipe ? KF_PIPE : KF_DIRECT;
 }

@@ -295,16 +295,23 @@ template <class PL, bool STAGED = false> struct RfftFwdBody {
             for (int e = 0; e < PS::R; e++)
                 r.v[b * PS::R + e] = ld_in<STAGED>(a.in + Eng::template in_index<0>(i, b, e));
     }
-    template <int E0> static FFT_HD void pair_loop(const cf32 *A, const cf32 *B, const Args &a, int p, cf32 tw0, bool regular)
+    /* where a finished spectrum bin goes: by default into the packed spectrum at a.out (a fused
+     * consumer such as the MFCC kernel passes its own sink and never materialises the spectrum) */
+    struct SpectrumSink {
+        cf32 *out;
+        FFT_HD void put(int k, cf32 v, bool pred) const { st_out_if<STAGED>(pred, out + k, v); }
+        FFT_HD void put_dc_nyquist(cf32 v) const { st_out<STAGED>(out, v); }      /* bin 0 = (DC, Nyquist) */
+    };
+    template <int E0, class SINK> static FFT_HD void pair_loop(const cf32 *A, const cf32 *B, int p, cf32 tw0, bool regular, const SINK &sink)
     {
         /* bins k0 = p + e*NBF (in A) and Nh - k0 = (NBF - p) + (R-1-e)*NBF (in B) */
         if constexpr (E0 < R) {
             const cf32 tw = rfft_tw_rot<R, E0>(tw0);
             const int k0 = p + E0 * NBF;
             const cf32 o0 = rfft_split(A[E0], B[R - 1 - E0], tw), o1 = rfft_split(B[R - 1 - E0], A[E0], rfft_tw_mirror(tw));
-            st_out_if<STAGED>(regular, a.out + k0, o0);
-            st_out_if<STAGED>(regular, a.out + (N - k0), o1);
-            pair_loop<E0 + 1>(A, B, a, p, tw0, regular);
+            sink.put(k0, o0, regular);
+            sink.put(N - k0, o1, regular);
+            pair_loop<E0 + 1>(A, B, p, tw0, regular, sink);
         }
     }
     static FFT_HD void split_store(const Regs &r, const Args &a, cf32 *scratch, int i)
@@ -316,11 +323,15 @@ template <class PL, bool STAGED = false> struct RfftFwdBody {
     }
     static FFT_HD void split_store(const Regs &r, const Args &a, cf32 *scratch, int i, const cf32 *ptw)
     {
+        split_store(r, scratch, i, ptw, SpectrumSink{a.out});
+    }
+    template <class SINK> static FFT_HD void split_store(const Regs &r, cf32 *scratch, int i, const cf32 *ptw, const SINK &sink)
+    {
 #pragma unroll
         for (int m = 0; m < NB / 2; m++) {
             const int p = i + T * m;
             const cf32 *A = &r.v[(2 * m) * R], *B = &r.v[(2 * m + 1) * R];
-            pair_loop<0>(A, B, a, p, ptw[m], m != 0 || i != 0);
+            pair_loop<0>(A, B, p, ptw[m], m != 0 || i != 0, sink);
             if (m == 0 && i == 0) {          /* X[h*NBF/2] -> scratch[h] */
 #pragma unroll
                 for (int e = 0; e < R; e++) {
@@ -342,19 +353,23 @@ template <class PL, bool STAGED = false> struct RfftFwdBody {
     }
     static FFT_HD void special_bins(const Args &a, const cf32 *scratch, int i, const cf32 *stw)
     {
+        special_bins(scratch, i, stw, SpectrumSink{a.out});
+    }
+    template <class SINK> static FFT_HD void special_bins(const cf32 *scratch, int i, const cf32 *stw, const SINK &sink)
+    {
 #pragma unroll
         for (int q = 0; q < kNS; q++) {
             const int h = i + T * q;
             if (h >= R) break;
             if (h == 0) {
                 const cf32 X0 = scratch[0], XR = scratch[R];
-                st_out<STAGED>(a.out + 0, cf32{X0.x + X0.y, X0.x - X0.y});       /* rfft_fast_f32.c:337-352 */
-                st_out<STAGED>(a.out + N / 2, rfft_split(XR, XR, stw[q]));
+                sink.put_dc_nyquist(cf32{X0.x + X0.y, X0.x - X0.y});             /* rfft_fast_f32.c:337-352 */
+                sink.put(N / 2, rfft_split(XR, XR, stw[q]), true);
             } else {
                 const int k = h * (NBF / 2);
                 const cf32 A = scratch[h], B = scratch[2 * R - h], tw = stw[q];
-                st_out<STAGED>(a.out + k, rfft_split(A, B, tw));
-                st_out<STAGED>(a.out + (N - k), rfft_split(B, A, rfft_tw_mirror(tw)));
+                sink.put(k, rfft_split(A, B, tw), true);
+                sink.put(N - k, rfft_split(B, A, rfft_tw_mirror(tw)), true);
             }
         }
     }

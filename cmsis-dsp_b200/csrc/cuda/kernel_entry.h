@@ -39,5 +39,7 @@ void shim_count_launch();
 /* device tables of the forward rfft plan of real length fftLenReal on the current device
  * (CMSISDSP_CUDA_ERR_NO_PLAN when cmsisdsp_cuda_plan_upload / _rfft_plan_upload have not run) */
 int shim_rfft_tables(uint32_t fftLenReal, const void **twForward, const float **twRfft);
+/* flavour forced by cmsisdsp_cuda_set_kernel_flavour / CMSISDSP_CUDA_KERNEL: KF_DIRECT, KF_PIPE or -1 (per-kernel default) */
+int shim_forced_flavour();
 
 }  // namespace b200fft

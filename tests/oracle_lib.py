@@ -129,5 +129,28 @@ def mfcc_config(n):
     """The reference's own MFCC test configuration for fftLen n in {256, 512, 1024}
     (Testing/Source/Tests/mfccdata.c via tests/golden/mfcc_patterns.npz): 20 mel filters, 13 DCT outputs."""
     d = np.load(os.path.join(ROOT, "tests", "golden", "mfcc_patterns.npz"))
+    if n not in (256, 512, 1024):
+        return _mfcc_config_synth(n, d["dct"])
     return dict(fftLen=n, nbMel=20, nbDct=13, dct=d["dct"], pos=d[f"pos/{n}"], len=d[f"len/{n}"],
                 coefs=d[f"coefs/{n}"], window=d[f"window/{n}"])
+
+
+def _mfcc_config_synth(n, dct, fs=16000.0, fmin=64.0, fmax=8000.0, nb_mel=20):
+    """Same recipe as the reference's generator (cmsisdsp/mfcc.py:28-113: Hamming window, triangular
+    filters equally spaced on the mel scale, packed as pos/len/coefs) for lengths the reference ships
+    no test data for (2048, 4096)."""
+    mel = lambda f: 2595.0 * np.log10(1.0 + f / 700.0)
+    imel = lambda m: 700.0 * (10.0 ** (m / 2595.0) - 1.0)
+    edges = imel(np.linspace(mel(fmin), mel(fmax), nb_mel + 2))
+    freqs = np.arange(n // 2) * fs / n
+    pos, length, coefs = [], [], []
+    for k in range(nb_mel):
+        lo, ce, hi = edges[k], edges[k + 1], edges[k + 2]
+        w = np.maximum(0.0, np.minimum((freqs - lo) / (ce - lo), (hi - freqs) / (hi - ce)))
+        nz = np.nonzero(w)[0]
+        pos.append(int(nz[0])); length.append(int(nz[-1] - nz[0] + 1))
+        coefs.append(w[nz[0]:nz[-1] + 1])
+    window = 0.54 - 0.46 * np.cos(2 * np.pi * np.arange(n) / n)
+    return dict(fftLen=n, nbMel=nb_mel, nbDct=dct.shape[0] if dct.ndim == 2 else 13, dct=dct,
+                pos=np.asarray(pos, dtype=np.uint32), len=np.asarray(length, dtype=np.uint32),
+                coefs=np.concatenate(coefs).astype(np.float32), window=window.astype(np.float32))

@@ -325,7 +325,7 @@ def test_mfcc_reference_patterns_and_oracle(n):
     x = (0.5 * np.sin(2 * np.pi * 440 * t) + 0.3 * np.sin(2 * np.pi * 1300 * t) + 0.2 * np.sin(2 * np.pi * 3100 * t)
          + 0.1 * rng.standard_normal(t.size)).astype(np.float32)
     x[5 * n:6 * n] = 0.0                                            # an all-zero frame (maxValue == 0 branch)
-    for hop in (n, n // 4, 2 * n):                                  # back to back, overlapping, gapped
+    for hop in (n, n // 4, 2 * n, n // 2 + 2):                      # back to back, overlapping, gapped, not a multiple of 4 (direct kernel)
         want = oracle().mfcc(cfg, x, stride=hop, threads=NT)
         got = m.batch(x, hop=hop)
         assert got.shape == want.shape and got.shape[0] >= 149
@@ -337,6 +337,28 @@ def test_mfcc_reference_patterns_and_oracle(n):
     cd.lib().arm_mfcc_f32(C.byref(m.S), frame.ctypes.data, one.ctypes.data, tmp.ctypes.data)
     assert cd.lib().arm_cuda_last_status() == 0
     _mfcc_ok(one, oracle().mfcc(cfg, x[:n])[0])
+
+
+@pytest.mark.parametrize("n", [256, 512, 1024, 2048, 4096])
+def test_mfcc_both_kernels_ragged_batches(n):
+    """TMA-fed and direct MFCC kernels against the oracle for ragged frame counts (partial last group,
+    fewer groups than resident CTAs) and every supported fftLen (2048/4096 with a synthetic filter bank)."""
+    from oracle_lib import mfcc_config
+    cfg = mfcc_config(n)
+    m = cd.Mfcc(cfg)
+    cu = cd.cuda()
+    rng = np.random.default_rng(7 * n)
+    try:
+        for frames in (1, 3, 130, 1031):
+            x = rng.standard_normal((frames - 1) * (n // 2) + n).astype(np.float32)
+            want = oracle().mfcc(cfg, x, stride=n // 2, threads=NT)
+            for flavour in (0, 1):
+                assert cu.cmsisdsp_cuda_set_kernel_flavour(flavour) == 0
+                got = m.batch(x, hop=n // 2)
+                assert got.shape == want.shape == (frames, 13)
+                _mfcc_ok(got, want)
+    finally:
+        cu.cmsisdsp_cuda_set_kernel_flavour(-1)
 
 
 def test_mfcc_config4_synthetic_audio_large_batch():
