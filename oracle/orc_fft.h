@@ -2,8 +2,8 @@
  * oracle/orc_fft.h -- CPU ORACLE for the CMSIS-DSP FFT hot path.
  *
  * TEST INFRASTRUCTURE ONLY.  This is a plain-C restatement of the reference's
- * generic-C (non-DSP, non-Neon, non-MVE) algorithm for arm_cfft_{f32,q31,q15}
- * and arm_rfft_fast_f32.  Only tests/, __graft_entry__.smoke() and bench.py's
+ * generic-C (non-DSP, non-Neon, non-MVE) algorithm for arm_cfft_{f32,q31,q15},
+ * arm_rfft_fast_f32, arm_rfft_{q31,q15} and arm_mfcc_f32.  Only tests/, __graft_entry__.smoke() and bench.py's
  * cpu_baseline / --impl reference legs may load it.  The product library
  * (libcmsisdsp_cuda / libcmsisdsp_b200) never links or calls anything here.
  *
@@ -49,6 +49,16 @@ void orc_cfft_f32_batch(uint32_t N, float *p, uint64_t nFrames, int ifft, int bi
 void orc_cfft_q31_batch(uint32_t N, int32_t *p, uint64_t nFrames, int ifft, int bitrev, int nthreads);
 void orc_cfft_q15_batch(uint32_t N, int16_t *p, uint64_t nFrames, int ifft, int bitrev, int nthreads);
 void orc_rfft_fast_f32_batch(uint32_t N, float *p, float *pOut, uint64_t nFrames, int ifft, int nthreads);
+
+/* ---- fixed-point real FFT (orc_rfft_fix.c): arm_rfft_q31.c:145-181, arm_rfft_q15.c:148-182 ----
+ * N = real length 32..8192.  forward: pSrc N scalars (destroyed), pDst 2N scalars; inverse: pSrc bins
+ * 0..N/2 read (frames 2N scalars apart in the batch drivers), pDst N scalars. */
+const int32_t *orc_real_coef_q31(int b);                   /* realCoefAQ31 (b = 0) / realCoefBQ31 (b = 1), 8192 entries */
+const int16_t *orc_real_coef_q15(int b);
+void orc_rfft_q31(uint32_t N, int32_t *pSrc, int32_t *pDst, int ifftFlagR, int bitReverseFlagR);
+void orc_rfft_q15(uint32_t N, int16_t *pSrc, int16_t *pDst, int ifftFlagR, int bitReverseFlagR);
+void orc_rfft_q31_batch(uint32_t N, const int32_t *src, int32_t *dst, uint64_t nFrames, int ifft, int bitrev, int nthreads);
+void orc_rfft_q15_batch(uint32_t N, const int16_t *src, int16_t *dst, uint64_t nFrames, int ifft, int bitrev, int nthreads);
 
 /* ---- arm_mfcc_f32 (Source/TransformFunctions/arm_mfcc_f32.c:88-174), RFFT based ---- */
 void orc_mfcc_f32(uint32_t fftLen, uint32_t nbMel, uint32_t nbDct, const float *dct, const uint32_t *pos,

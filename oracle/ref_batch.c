@@ -9,6 +9,7 @@
 #include "arm_math_types.h"
 #include "dsp/transform_functions.h"
 #include "arm_const_structs.h"
+#include "arm_common_tables.h"
 #include <pthread.h>
 #include <stdlib.h>
 
@@ -122,3 +123,53 @@ int ref_mfcc_f32_batch(uint32_t fftLen, uint32_t nbMel, uint32_t nbDct, const fl
     return 0;
 }
 uint32_t ref_sizeof_mfcc_instance_f32(void) { return (uint32_t)sizeof(arm_mfcc_instance_f32); }
+
+/* ---- arm_rfft_q31 / arm_rfft_q15 batch drivers: forward frames N in -> 2N out, inverse frames 2N in -> N out;
+ * the source is copied per frame (the reference's forward transform destroys it) ---- */
+typedef struct { int q15; uint32_t N; const void *src; void *dst; uint64_t f0, f1; int ifft, bitrev; } rjob_t;
+static void *rworker(void *arg)
+{
+    rjob_t *j = arg;
+    const uint32_t N = j->N;
+    const uint64_t inStride = j->ifft ? 2ull * N : N, outStride = j->ifft ? N : 2ull * N;
+    arm_rfft_instance_q31 S31; arm_rfft_instance_q15 S15;
+    if (j->q15) { if (arm_rfft_init_q15(&S15, N, (uint32_t)j->ifft, (uint32_t)j->bitrev) != ARM_MATH_SUCCESS) return NULL; }
+    else        { if (arm_rfft_init_q31(&S31, N, (uint32_t)j->ifft, (uint32_t)j->bitrev) != ARM_MATH_SUCCESS) return NULL; }
+    void *tmp = malloc((j->q15 ? 2 : 4) * 2 * (size_t)N);
+    for (uint64_t f = j->f0; f < j->f1; f++) {
+        if (j->q15) {
+            memcpy(tmp, (const q15_t *)j->src + f * inStride, 2 * inStride);
+            arm_rfft_q15(&S15, (q15_t *)tmp, (q15_t *)j->dst + f * outStride);
+        } else {
+            memcpy(tmp, (const q31_t *)j->src + f * inStride, 4 * inStride);
+            arm_rfft_q31(&S31, (q31_t *)tmp, (q31_t *)j->dst + f * outStride);
+        }
+    }
+    free(tmp);
+    return NULL;
+}
+static void rrun(int q15, uint32_t N, const void *src, void *dst, uint64_t nFrames, int ifft, int bitrev, int nthreads)
+{
+    if (nthreads < 1) nthreads = 1;
+    if ((uint64_t)nthreads > nFrames) nthreads = nFrames ? (int)nFrames : 1;
+    pthread_t *th = malloc((size_t)nthreads * sizeof *th);
+    rjob_t *jobs = malloc((size_t)nthreads * sizeof *jobs);
+    uint64_t per = (nFrames + (uint64_t)nthreads - 1) / (uint64_t)nthreads;
+    for (int t = 0; t < nthreads; t++) {
+        uint64_t f0 = per * (uint64_t)t, f1 = f0 + per;
+        if (f0 > nFrames) f0 = nFrames;
+        if (f1 > nFrames) f1 = nFrames;
+        jobs[t] = (rjob_t){q15, N, src, dst, f0, f1, ifft, bitrev};
+        if (nthreads == 1) rworker(&jobs[t]);
+        else pthread_create(&th[t], NULL, rworker, &jobs[t]);
+    }
+    if (nthreads > 1)
+        for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+    free(th); free(jobs);
+}
+void ref_rfft_q31_batch(uint32_t N, const int32_t *src, int32_t *dst, uint64_t n, int ifft, int bitrev, int nt) { rrun(0, N, src, dst, n, ifft, bitrev, nt); }
+void ref_rfft_q15_batch(uint32_t N, const int16_t *src, int16_t *dst, uint64_t n, int ifft, int bitrev, int nt) { rrun(1, N, src, dst, n, ifft, bitrev, nt); }
+const int32_t *ref_real_coef_q31(int b) { return b ? realCoefBQ31 : realCoefAQ31; }
+const int16_t *ref_real_coef_q15(int b) { return b ? realCoefBQ15 : realCoefAQ15; }
+uint32_t ref_sizeof_rfft_instance_q31(void) { return (uint32_t)sizeof(arm_rfft_instance_q31); }
+uint32_t ref_sizeof_rfft_instance_q15(void) { return (uint32_t)sizeof(arm_rfft_instance_q15); }

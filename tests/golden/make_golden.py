@@ -46,6 +46,12 @@ def read_pattern(path):
 
 
 def main():
+    if "--digests-only" not in sys.argv:
+        patterns_main()
+    digests_main()
+
+
+def patterns_main():
     out = {}
     for tname, ext, view in (("F32", "f32", np.float32), ("Q31", "q31", np.int32), ("Q15", "q15", np.int16)):
         d = os.path.join(PAT, f"Transform{tname}")
@@ -94,7 +100,10 @@ def main():
     np.savez_compressed(os.path.join(HERE, "mfcc_patterns.npz"), **mf)
     print("mfcc_patterns.npz:", len(mf), "arrays")
 
-    from oracle_lib import LENGTHS, RLENGTHS, ref
+
+
+def digests_main():
+    from oracle_lib import LENGTHS, RFIX_LENGTHS, RLENGTHS, ref
     from seeded_inputs import cfft_input, rfft_input
     r = ref()
     dig = {}
@@ -110,6 +119,13 @@ def main():
         for ifft in (0, 1):
             y = r.rfft(N, x, ifft)
             dig[f"rfft_fast_f32/{N}/{ifft}"] = hashlib.sha256(y.tobytes()).hexdigest()
+    for kind in ("q31", "q15"):
+        for N in RFIX_LENGTHS:
+            x = cfft_input(kind, N // 2, frames=8, seed=3 * N)           # [8, N] real samples incl. full-scale frames
+            y = r.rfft_fix(kind, N, x, 0, 1)
+            dig[f"rfft_{kind}/{N}/0"] = hashlib.sha256(y.tobytes()).hexdigest()
+            z = r.rfft_fix(kind, N, np.concatenate([y, cfft_input(kind, N, frames=4, seed=5 * N)]), 1, 1)
+            dig[f"rfft_{kind}/{N}/1"] = hashlib.sha256(z.tobytes()).hexdigest()
     with open(os.path.join(HERE, "ref_digests.json"), "w") as f:
         json.dump(dig, f, indent=0, sort_keys=True)
     print("ref_digests.json:", len(dig), "digests")

@@ -14,6 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ODIR = os.path.join(ROOT, "oracle")
 LENGTHS = [16, 32, 64, 128, 256, 512, 1024, 2048, 4096]
 RLENGTHS = [32, 64, 128, 256, 512, 1024, 2048, 4096]
+RFIX_LENGTHS = [32, 64, 128, 256, 512, 1024, 2048, 4096, 8192]    # arm_rfft_q31 / arm_rfft_q15 real lengths
 
 _u16p = C.POINTER(C.c_uint16)
 
@@ -36,6 +37,13 @@ def _declare(lib, prefix):
         fn = f(lib, f"{prefix}_{name}")
         fn.argtypes = [C.c_uint32, _u16p]
         fn.restype = _u16p
+    for name, t in (("q31", C.c_int32), ("q15", C.c_int16)):
+        fn = f(lib, f"{prefix}_rfft_{name}_batch")
+        fn.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int]
+        fn.restype = None
+        fn = f(lib, f"{prefix}_real_coef_{name}")
+        fn.argtypes = [C.c_int]
+        fn.restype = C.POINTER(t)
 
 
 class _Lib:
@@ -62,6 +70,21 @@ class _Lib:
         out = np.empty_like(p)
         self._fn("rfft_fast_f32_batch")(N, p.ctypes.data, out.ctypes.data, p.size // N, int(ifft), int(threads))
         return (out, p) if return_clobbered else out
+
+    def rfft_fix(self, kind, N, x, ifft=0, bitrev=1, threads=1):
+        """arm_rfft_q31 / arm_rfft_q15.  forward: x [..., N] -> [..., 2N] (N complex bins, mirror included);
+        inverse: x [..., 2N] (bins 0..N/2 are read) -> [..., N]."""
+        dt = {"q31": np.int32, "q15": np.int16}[kind]
+        src = np.ascontiguousarray(x, dtype=dt)
+        per = 2 * N if ifft else N
+        assert src.size % per == 0
+        frames = src.size // per
+        out = np.empty(frames * (N if ifft else 2 * N), dtype=dt)
+        self._fn(f"rfft_{kind}_batch")(N, src.ctypes.data, out.ctypes.data, frames, int(ifft), int(bitrev), int(threads))
+        return out.reshape(frames, -1)
+
+    def real_coef(self, kind, b):
+        return np.ctypeslib.as_array(self._fn(f"real_coef_{kind}")(int(b)), shape=(8192,)).copy()
 
     def mfcc(self, cfg, x, stride=None, frames=None, threads=1):
         """arm_mfcc_f32 over frames taken from the 1-D signal x every `stride` samples.

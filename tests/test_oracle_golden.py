@@ -6,8 +6,9 @@ import hashlib
 import numpy as np
 import pytest
 
-from golden_checks import assert_like_reference, golden_cases, ref_digests
-from oracle_lib import LENGTHS, RLENGTHS, oracle
+from golden_checks import (assert_like_reference, assert_rfft_fix_like_reference, golden_cases, golden_rfft_fix_cases,
+                           ref_digests, rfft_fix_threshold_applies)
+from oracle_lib import LENGTHS, RFIX_LENGTHS, RLENGTHS, oracle
 from seeded_inputs import cfft_input, rfft_input
 import os
 
@@ -31,6 +32,19 @@ def test_rfft_patterns():
         assert_like_reference("f32", "r", out, ref, N, ifft)
         n += 1
     assert n == 32          # 8 lengths x {noisy, step} x {fwd, inv}
+
+
+@pytest.mark.parametrize("kind", ["q31", "q15"])
+def test_rfft_fixed_point_patterns(kind):
+    n = 0
+    for N, sig, ifft, x, ref in golden_rfft_fix_cases(kind):
+        if not rfft_fix_threshold_applies(kind, N, sig, ifft):
+            continue
+        out = oracle().rfft_fix(kind, N, x, ifft, 1)
+        snr, want = assert_rfft_fix_like_reference(kind, N, ifft, out, ref)
+        assert want is None or snr >= want, (kind, N, sig, ifft, snr)
+        n += 1
+    assert n == {"q31": 24, "q15": 22}[kind]
 
 
 def test_fft_bin_example_known_answer():
@@ -58,6 +72,13 @@ def test_digests_of_compiled_reference():
         for ifft in (0, 1):
             y = o.rfft(N, x, ifft)
             assert hashlib.sha256(y.tobytes()).hexdigest() == dig[f"rfft_fast_f32/{N}/{ifft}"], (N, ifft)
+    for kind in ("q31", "q15"):
+        for N in RFIX_LENGTHS:
+            x = cfft_input(kind, N // 2, frames=8, seed=3 * N)
+            y = o.rfft_fix(kind, N, x, 0, 1)
+            assert hashlib.sha256(y.tobytes()).hexdigest() == dig[f"rfft_{kind}/{N}/0"], (kind, N, 0)
+            z = o.rfft_fix(kind, N, np.concatenate([y, cfft_input(kind, N, frames=4, seed=5 * N)]), 1, 1)
+            assert hashlib.sha256(z.tobytes()).hexdigest() == dig[f"rfft_{kind}/{N}/1"], (kind, N, 1)
 
 
 def test_unsupported_length_is_noop():

@@ -4,7 +4,7 @@ every transform bit for bit, f32 included (both are built -ffp-contract=off)."""
 import numpy as np
 import pytest
 
-from oracle_lib import LENGTHS, RLENGTHS, oracle, ref
+from oracle_lib import LENGTHS, RFIX_LENGTHS, RLENGTHS, oracle, ref
 
 pytestmark = pytest.mark.skipif(ref() is None, reason="oracle/_ref not built (needs /root/reference)")
 
@@ -63,6 +63,27 @@ def test_rfft_bit_exact(N):
         b, pb = ref().rfft(N, x, ifft, return_clobbered=True)
         assert np.array_equal(bits(a), bits(b)), (N, ifft)
         assert np.array_equal(bits(pa), bits(pb)), ("clobbered input", N, ifft)
+
+
+@pytest.mark.parametrize("kind", ["q31", "q15"])
+def test_real_coef_tables_identical(kind):
+    for b in (0, 1):
+        assert np.array_equal(oracle().real_coef(kind, b), ref().real_coef(kind, b)), (kind, b)
+
+
+@pytest.mark.parametrize("kind", ["q31", "q15"])
+@pytest.mark.parametrize("N", RFIX_LENGTHS)
+def test_rfft_fixed_point_bit_exact(kind, N):
+    """arm_rfft_q31 / arm_rfft_q15, forward and inverse, incl. full-scale frames (wrap / saturation paths)"""
+    rng = np.random.default_rng(3000 + N)
+    x = _inputs(kind, N // 2, rng)                                  # [frames, N] real samples
+    a = oracle().rfft_fix(kind, N, x, 0, 1, threads=2)
+    b = ref().rfft_fix(kind, N, x, 0, 1, threads=3)
+    assert a.shape == (x.shape[0], 2 * N) and np.array_equal(a, b), (kind, N, "forward")
+    spec = np.concatenate([a, _inputs(kind, N, rng)], axis=0)       # genuine spectra and arbitrary full-scale bins
+    c = oracle().rfft_fix(kind, N, spec, 1, 1, threads=2)
+    d = ref().rfft_fix(kind, N, spec, 1, 1, threads=3)
+    assert c.shape == (spec.shape[0], N) and np.array_equal(c, d), (kind, N, "inverse")
 
 
 def test_threads_agree():
