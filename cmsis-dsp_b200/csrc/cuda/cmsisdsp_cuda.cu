@@ -47,12 +47,14 @@ void shim_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 #define DECL(op, n) extern const KernelEntry ku_entry_##op##_##n;
 namespace b200fft {
 FOR_ALL_N(DECL, 0) FOR_ALL_N(DECL, 1) FOR_ALL_N(DECL, 2) FOR_RFFT_NC(DECL, 3) FOR_RFFT_NC(DECL, 4)
+FOR_ALL_N(DECL, 5) FOR_ALL_N(DECL, 6) FOR_ALL_N(DECL, 7) FOR_ALL_N(DECL, 8)
 }
 #undef DECL
 #define REF(op, n) &ku_entry_##op##_##n,
 /* [op][index of the COMPLEX length 16..4096]; the rfft ops have no 4096-point complex plan */
 static const KernelEntry *const kEntries[OP_COUNT][9] = {
-    {FOR_ALL_N(REF, 0)}, {FOR_ALL_N(REF, 1)}, {FOR_ALL_N(REF, 2)}, {FOR_RFFT_NC(REF, 3) nullptr}, {FOR_RFFT_NC(REF, 4) nullptr}};
+    {FOR_ALL_N(REF, 0)}, {FOR_ALL_N(REF, 1)}, {FOR_ALL_N(REF, 2)}, {FOR_RFFT_NC(REF, 3) nullptr}, {FOR_RFFT_NC(REF, 4) nullptr},
+    {FOR_ALL_N(REF, 5)}, {FOR_ALL_N(REF, 6)}, {FOR_ALL_N(REF, 7)}, {FOR_ALL_N(REF, 8)}};
 #undef REF
 
 static const uint32_t kLens[9] = {16, 32, 64, 128, 256, 512, 1024, 2048, 4096};
@@ -102,6 +104,7 @@ struct DevPlan {
 struct DevState {
     DevPlan plan[3][9];
     float *twr[9] = {};           /* rfft twiddles, indexed by len_index(real length) */
+    void *rcoef[3][9] = {};       /* q31 / q15 real FFT: split coefficients (ci32x4 per bin), indexed by len_index(fftLenReal / 2) */
 };
 static const int kMaxDev = 64;
 static DevState g_dev[kMaxDev];
@@ -202,6 +205,46 @@ extern "C" int cmsisdsp_cuda_rfft_plan_ready(uint32_t fftLenReal)
     return g_dev[dev].twr[li] != nullptr && g_dev[dev].plan[0][li - 1].tw != nullptr;
 }
 
+extern "C" int cmsisdsp_cuda_rfft_fix_plan_upload(int type, uint32_t fftLenReal, const void *pTwiddleAReal,
+                                                  const void *pTwiddleBReal, uint32_t twidCoefRModifier)
+{
+    const int li = len_index(fftLenReal / 2);
+    if ((type != CMSISDSP_CUDA_Q31 && type != CMSISDSP_CUDA_Q15) || (fftLenReal & 1u) || li < 0 || !pTwiddleAReal || !pTwiddleBReal ||
+        twidCoefRModifier == 0 || (uint64_t)twidCoefRModifier * fftLenReal > 8192u)
+        return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "rfft_fix_plan_upload: bad type / length / pointer / modifier");
+    int dev;
+    int rc = cur_device(&dev);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_dev[dev].rcoef[type][li]) return CMSISDSP_CUDA_OK;
+    /* bin k reads entries 2*k*modifier and 2*k*modifier + 1 of both tables (arm_rfft_q31.c:272-273,333-334) */
+    const uint32_t L2 = fftLenReal / 2;
+    std::vector<int32_t> coef((size_t)L2 * 4);
+    for (uint32_t k = 0; k < L2; k++) {
+        const size_t e = (size_t)2 * k * twidCoefRModifier;
+        if (type == CMSISDSP_CUDA_Q31) {
+            const int32_t *A = (const int32_t *)pTwiddleAReal, *B = (const int32_t *)pTwiddleBReal;
+            coef[4 * k] = A[e]; coef[4 * k + 1] = A[e + 1]; coef[4 * k + 2] = B[e]; coef[4 * k + 3] = B[e + 1];
+        } else {
+            const int16_t *A = (const int16_t *)pTwiddleAReal, *B = (const int16_t *)pTwiddleBReal;
+            coef[4 * k] = A[e]; coef[4 * k + 1] = A[e + 1]; coef[4 * k + 2] = B[e]; coef[4 * k + 3] = B[e + 1];
+        }
+    }
+    void *d = nullptr;
+    CU_TRY(cudaMalloc(&d, coef.size() * sizeof(int32_t)));
+    CU_TRY(cudaMemcpy(d, coef.data(), coef.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    g_dev[dev].rcoef[type][li] = d;
+    return CMSISDSP_CUDA_OK;
+}
+extern "C" int cmsisdsp_cuda_rfft_fix_plan_ready(int type, uint32_t fftLenReal)
+{
+    const int li = len_index(fftLenReal / 2);
+    int dev;
+    if ((type != CMSISDSP_CUDA_Q31 && type != CMSISDSP_CUDA_Q15) || li < 0 || cur_device(&dev)) return 0;
+    std::lock_guard<std::mutex> lk(g_mu);
+    return g_dev[dev].rcoef[type][li] != nullptr && g_dev[dev].plan[type][li].tw != nullptr;
+}
+
 static int get_plan(int type, uint32_t fftLen, DevPlan *out)
 {
     const int li = len_index(fftLen);
@@ -280,9 +323,36 @@ extern "C" int cmsisdsp_cuda_rfft_fast_f32(const void *d_p, void *d_out, uint32_
                       (cudaStream_t)stream);
 }
 
+static int rfft_fix(int type, const void *d_src, void *d_dst, uint32_t fftLenReal, uint64_t nFrames, uint8_t ifftFlagR, void *stream)
+{
+    if ((!d_src || !d_dst) && nFrames) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "null data pointer");
+    if (d_src == d_dst && nFrames) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "rfft: pSrc and pDst must not alias");
+    const int li = (fftLenReal & 1u) ? -1 : len_index(fftLenReal / 2);
+    if (li < 0) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "unsupported fixed-point rfft length (32..8192, power of two)");
+    DevPlan pl;
+    int rc = get_plan(type, fftLenReal / 2, &pl);
+    if (rc) return rc;
+    int dev;
+    rc = cur_device(&dev);
+    if (rc) return rc;
+    const void *coef;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        coef = g_dev[dev].rcoef[type][li];
+    }
+    if (!coef) return fail(CMSISDSP_CUDA_ERR_NO_PLAN, "no fixed-point rfft plan uploaded for this (device, type, fftLenReal)");
+    const int op = (type == CMSISDSP_CUDA_Q31 ? OP_RFFT_Q31_FWD : OP_RFFT_Q15_FWD) + (ifftFlagR ? 1 : 0);
+    const KernelEntry *ke = kEntries[op][li];
+    return ke->launch(d_src, d_dst, nFrames, ifftFlagR != 0, pl.tw, coef, (li + 4) & 1, KF_DIRECT, (cudaStream_t)stream);
+}
+extern "C" int cmsisdsp_cuda_rfft_q31(const void *d_src, void *d_dst, uint32_t fftLenReal, uint64_t nFrames, uint8_t ifftFlagR, void *stream)
+{ return rfft_fix(CMSISDSP_CUDA_Q31, d_src, d_dst, fftLenReal, nFrames, ifftFlagR, stream); }
+extern "C" int cmsisdsp_cuda_rfft_q15(const void *d_src, void *d_dst, uint32_t fftLenReal, uint64_t nFrames, uint8_t ifftFlagR, void *stream)
+{ return rfft_fix(CMSISDSP_CUDA_Q15, d_src, d_dst, fftLenReal, nFrames, ifftFlagR, stream); }
+
 extern "C" int cmsisdsp_cuda_kernel_info(int op, uint32_t fftLen, int *threads, int *frames, int *smem, int *regs, int *ctasPerSm)
 {
-    const int li = len_index((op >= 3) ? fftLen / 2 : fftLen);
+    const int li = len_index((op >= 3) ? fftLen / 2 : fftLen);       /* ops 3..8 take the real length */
     if (op < 0 || op >= OP_COUNT || li < 0 || !kEntries[op][li]) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "kernel_info: unsupported (op, fftLen)");
     KernelFacts f;
     int rc = kEntries[op][li]->facts(&f, choose_flavour(kEntries[op][li]));

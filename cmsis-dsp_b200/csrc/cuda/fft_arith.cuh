@@ -28,6 +28,9 @@ namespace b200fft {
 struct alignas(8) cf32 { float x, y; };
 struct alignas(8) ci32 { int32_t x, y; };
 struct alignas(4) ci16 { int16_t x, y; };
+/* split-stage coefficients of one bin of the fixed-point real FFT: realCoefA[2k], realCoefA[2k+1],
+ * realCoefB[2k], realCoefB[2k+1] at the instance's twidCoefRModifier, 32-bit (q15 sign-extended) */
+struct alignas(16) ci32x4 { int32_t a0, a1, b0, b1; };
 
 /* ------------------------------------------------------------------ f32
  *
@@ -311,6 +314,40 @@ struct ArithQ31 {
         else      { p0 = rhi32_sub(p0, yt, w.y); p1 = rhi32_acc(p1, xt, w.y); }
         B = {wshl1(p0), wshl1(p1)};
     }
+
+    /* ---- real FFT (arm_rfft_q31.c): S1 = X[k], S2 = X[L2-k]; the reference's exact sequence of rounding
+     * multiply-accumulates, which reads only A[2k], A[2k+1] and B[2k] (B[2k+1] == -A[2k+1]) ---- */
+    static FFT_HD work split_fwd(work s1, work s2, ci32x4 c)          /* arm_split_rfft_q31, :290-325 */
+    {
+        int32_t r = rhi32(s1.x, c.a0), i = rhi32(s1.x, c.a1);
+        r = rhi32_sub(r, s1.y, c.a1);
+        i = rhi32_acc(i, s1.y, c.a0);
+        r = rhi32_sub(r, s2.y, c.a1);
+        i = rhi32_sub(i, s2.y, c.b0);
+        r = rhi32_acc(r, s2.x, c.b0);
+        i = rhi32_sub(i, s2.x, c.a1);
+        return {r, i};
+    }
+    static FFT_HD work split_inv(work s1, work s2, ci32x4 c)          /* arm_split_rifft_q31, :438-466 */
+    {
+        int32_t r = rhi32(s1.x, c.a0), i = rhi32(s1.x, wsub(0, c.a1));
+        r = rhi32_acc(r, s1.y, c.a1);
+        i = rhi32_acc(i, s1.y, c.a0);
+        r = rhi32_acc(r, s2.y, c.a1);
+        i = rhi32_sub(i, s2.y, c.b0);
+        r = rhi32_acc(r, s2.x, c.b0);
+        i = rhi32_acc(i, s2.x, c.a1);
+        return {r, i};
+    }
+    static FFT_HD work split_dc(work x0) { return {wadd(x0.x, x0.y) >> 1, 0}; }       /* :339-340 */
+    static FFT_HD work split_nyquist(work x0) { return {wsub(x0.x, x0.y) >> 1, 0}; }  /* :336-337 */
+    static FFT_HD work mirror(work o) { return {o.x, wsub(0, o.y)}; }                 /* :327-329 */
+    static FFT_HD work sat_shl1(work w)                                               /* arm_shift_q31(.., 1, ..) */
+    {
+        const int64_t x = (int64_t)w.x * 2, y = (int64_t)w.y * 2;
+        return {x > INT32_MAX ? INT32_MAX : (x < INT32_MIN ? INT32_MIN : (int32_t)x),
+                y > INT32_MAX ? INT32_MAX : (y < INT32_MIN ? INT32_MIN : (int32_t)y)};
+    }
 };
 
 /* ------------------------------------------------------------------ q15
@@ -428,6 +465,27 @@ struct ArithQ15 {
         if (!INV) B = {((xt * w.x) >> 16) + ((yt * w.y) >> 16), ((yt * w.x) >> 16) - ((xt * w.y) >> 16)};
         else      B = {((xt * w.x) >> 16) - ((yt * w.y) >> 16), ((yt * w.x) >> 16) + ((xt * w.y) >> 16)};
     }
+
+    /* ---- real FFT (arm_rfft_q15.c generic branch): 32-bit wrap-around sums of q15 x q15 products, >> 16;
+     * the results fit int16, the negated mirror is truncated by store() ---- */
+    static FFT_HD int32_t sum4(int32_t p, int32_t q, int32_t u, int32_t v)
+    {
+        return (int32_t)((uint32_t)p + (uint32_t)q + (uint32_t)u + (uint32_t)v) >> 16;
+    }
+    static FFT_HD work split_fwd(work s1, work s2, ci32x4 c)          /* arm_split_rfft_q15, :364-383 */
+    {
+        return {sum4(s1.x * c.a0, -(s1.y * c.a1), s2.x * c.b0, s2.y * c.b1),
+                sum4(s2.x * c.b1, -(s2.y * c.b0), s1.y * c.a0, s1.x * c.a1)};
+    }
+    static FFT_HD work split_inv(work s1, work s2, ci32x4 c)          /* arm_split_rifft_q15, :554-562 */
+    {
+        return {sum4(s2.x * c.b0, -(s2.y * c.b1), s1.x * c.a0, s1.y * c.a1),
+                sum4(s1.y * c.a0, -(s1.x * c.a1), -(s2.x * c.b1), -(s2.y * c.b0))};
+    }
+    static FFT_HD work split_dc(work x0) { return {(x0.x + x0.y) >> 1, 0}; }          /* :403-404 */
+    static FFT_HD work split_nyquist(work x0) { return {(x0.x - x0.y) >> 1, 0}; }     /* :400-401 */
+    static FFT_HD work mirror(work o) { return {o.x, -o.y}; }                         /* :393-394 */
+    static FFT_HD work sat_shl1(work w) { return {sat16(w.x * 2), sat16(w.y * 2)}; }  /* arm_shift_q15(.., 1, ..) */
 };
 
 }  // namespace b200fft

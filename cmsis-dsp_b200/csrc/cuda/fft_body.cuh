@@ -72,7 +72,10 @@ template <> struct IsF32<cf32> { static constexpr bool value = true; };
 /* PERM: bitReverseFlag == 0, results are scattered through the plan's output permutation
  * (a compile-time flavour: a run-time test would put a predicated table load and its
  * scoreboard wait in front of every store of the common natural-order case) */
-template <class PL, bool INV, bool PERM = false, bool STAGED = false> struct CfftBody {
+/* RIFFT: the body is the core of the fixed-point inverse real FFT (arm_rfft_q31.c:160-167,
+ * arm_rfft_q15.c:162-169): the load is the merge stage arm_split_rifft_* applied to the bins
+ * X[k], X[N-k] of a 2N-bin spectrum frame, the store ends with arm_shift_*(.., 1, ..) */
+template <class PL, bool INV, bool PERM = false, bool STAGED = false, bool RIFFT = false> struct CfftBody {
     typedef Engine<PL> Eng;
     typedef typename Eng::A A;
     typedef typename A::elem elem;
@@ -91,11 +94,12 @@ template <class PL, bool INV, bool PERM = false, bool STAGED = false> struct Cff
         const uint16_t *perm;    /* PERM only: destination position of X[k] */
         float scale;             /* f32 inverse: 1/N */
         int shl1;                /* fixed point, N = 2*4^m: final << 1 of every word */
+        const ci32x4 *coef;      /* RIFFT only: split-stage coefficients of bins 0..N-1 */
     };
     /* frame-local view of the batch arguments; with STAGED the kernel overrides `in` */
     static FFT_HD Args for_frame(Args a, uint64_t frame)
     {
-        a.in += frame * (uint64_t)N;
+        a.in += frame * (uint64_t)(RIFFT ? 2 * N : N);
         a.out += frame * (uint64_t)N;
         return a;
     }
@@ -108,7 +112,14 @@ template <class PL, bool INV, bool PERM = false, bool STAGED = false> struct Cff
         for (int b = 0; b < E / PS::R; b++)
 #pragma unroll
             for (int e = 0; e < PS::R; e++) {
-                work w = A::load(ld_in<STAGED>(a.in + Eng::template in_index<0>(i, b, e)));
+                const int idx = Eng::template in_index<0>(i, b, e);
+                work w;
+                if constexpr (RIFFT) {
+                    /* every bin is read twice (as X[k] and as X[N-k]): plain cached loads */
+                    w = A::split_inv(A::load(a.in[idx]), A::load(a.in[N - idx]), a.coef[idx]);
+                } else {
+                    w = A::load(ld_in<STAGED>(a.in + idx));
+                }
                 if (kF32 && INV) w.y = -w.y;                       /* conjugate input (cfft_f32.c:1252-1261) */
                 r.v[b * PS::R + e] = w;
             }
@@ -127,6 +138,7 @@ template <class PL, bool INV, bool PERM = false, bool STAGED = false> struct Cff
                 } else if (a.shl1) {
                     w = A::shl1(w);                                  /* cfft_q31.c:803-820, cfft_q15.c:810-827 */
                 }
+                if constexpr (RIFFT) w = A::sat_shl1(w);
                 int pos = k;
                 if constexpr (PERM) pos = (int)a.perm[k];
                 st_stream(a.out + pos, A::store(w));
@@ -177,17 +189,21 @@ template <class PL, bool INV, bool PERM = false, bool STAGED = false> struct Cff
         last_out(r, a, i);
     }
 
-    template <int PH> static FFT_HD void phase(Regs &r, const Args &a, xelem *sm, int i)
+    /* HOLD: the results of the last pass stay in the registers (no store): a fused epilogue follows */
+    template <int PH, bool HOLD = false> static FFT_HD void phase(Regs &r, const Args &a, xelem *sm, int i)
     {
         if constexpr (PH == 0) {
             gload(r, a, i);
             Eng::template compute<0, INV>(r, a.tw, i);
-            if constexpr (NP == 1) gstore(r, a, i);
-            else Eng::template smem_store<0>(r, sm, i);
+            if constexpr (NP == 1) {
+                if constexpr (!HOLD) gstore(r, a, i);
+            } else {
+                Eng::template smem_store<0>(r, sm, i);
+            }
         } else if constexpr (NP == 2) {
             Eng::template smem_load<1>(r, sm, i);
             Eng::template compute<1, INV>(r, a.tw, i);
-            gstore(r, a, i);
+            if constexpr (!HOLD) gstore(r, a, i);
         } else if constexpr (NP == 3) {
             if constexpr (PH == 1) {
                 Eng::template smem_load<1>(r, sm, i);
@@ -197,7 +213,100 @@ template <class PL, bool INV, bool PERM = false, bool STAGED = false> struct Cff
             } else {
                 Eng::template smem_load<2>(r, sm, i);
                 Eng::template compute<2, INV>(r, a.tw, i);
-                gstore(r, a, i);
+                if constexpr (!HOLD) gstore(r, a, i);
+            }
+        }
+    }
+};
+
+/* ------------------------------------------------------------------ fixed-point real FFT, forward
+ *
+ * arm_rfft_q31 / arm_rfft_q15 with ifftFlagR = 0 (arm_rfft_q31.c:169-178, arm_rfft_q15.c:171-180): the
+ * N-point CFFT of the frame (N = fftLenReal / 2) and arm_split_rfft_* fused: the last pass leaves X in
+ * the frame's exchange buffer in natural order, then every thread splits E bins, reading X[k] and X[N-k]
+ * from shared memory and writing bin k and its conjugate mirror 2N-k (the reference writes the mirror
+ * explicitly, :327-329).  HBM: N elements in, 2N elements out, once.  The inverse direction is
+ * CfftBody<.., RIFFT = true>. */
+template <class PL> struct RfftFixFwdBody {
+    typedef CfftBody<PL, false> C;
+    typedef typename C::Eng Eng;
+    typedef typename C::A A;
+    typedef typename A::elem elem;
+    typedef typename A::xelem xelem;
+    typedef typename A::telem telem;
+    typedef typename A::work work;
+    typedef typename Eng::Regs Regs;
+    static constexpr int NP = PL::NP, E = PL::E, N = PL::N, T = PL::T;
+    static constexpr int kCfftPhases = PhaseCount<NP>::value;
+    static constexpr int kPhases = (NP == 1) ? 1 : kCfftPhases + 2;
+    static_assert(NP > 1 || T == 1, "single-pass plans are one thread per frame");
+
+    struct Args {
+        const elem *in;          /* N complex = fftLenReal scalars */
+        elem *out;               /* 2N complex */
+        const telem *tw;         /* pass-ordered twiddles of the N-point CFFT plan */
+        const ci32x4 *coef;      /* split-stage coefficients of bins 0..N-1 */
+        int shl1;
+    };
+    static FFT_HD Args for_frame(Args a, uint64_t frame)
+    {
+        a.in += frame * (uint64_t)N;
+        a.out += frame * (uint64_t)(2 * N);
+        return a;
+    }
+    static FFT_HD void set_scratch(Args &, xelem *) {}
+    static FFT_HD typename C::Args cfft_args(const Args &a) { return typename C::Args{a.in, nullptr, a.tw, nullptr, 0.0f, a.shl1, nullptr}; }
+
+    static FFT_HD void put_bin0(const Args &a, work x0)
+    {
+        st_stream(a.out, A::store(A::split_dc(x0)));
+        st_stream(a.out + N, A::store(A::split_nyquist(x0)));
+    }
+    static FFT_HD void put_bin(const Args &a, int k, work s1, work s2)
+    {
+        const work o = A::split_fwd(s1, s2, a.coef[k]);
+        st_stream(a.out + k, A::store(o));
+        st_stream(a.out + (2 * N - k), A::store(A::mirror(o)));
+    }
+    template <int K> static FFT_HD void bins_in_regs(const Args &a, const work *y)
+    {
+        if constexpr (K < N) {
+            put_bin(a, K, y[K], y[N - K]);
+            bins_in_regs<K + 1>(a, y);
+        }
+    }
+
+    template <int PH> static FFT_HD void phase(Regs &r, const Args &a, xelem *sm, int i)
+    {
+        typedef typename PassOf<PL, NP - 1>::type PSL;
+        if constexpr (NP == 1) {
+            C::template phase<0, true>(r, cfft_args(a), sm, i);
+            work y[N];                                                /* y[k] = X[k] */
+#pragma unroll
+            for (int e = 0; e < N; e++) y[PSL::out_index(e)] = a.shl1 ? A::shl1(r.v[e]) : r.v[e];
+            put_bin0(a, y[0]);
+            bins_in_regs<1>(a, y);
+        } else if constexpr (PH < kCfftPhases) {
+            C::template phase<PH, true>(r, cfft_args(a), sm, i);
+        } else if constexpr (PH == kCfftPhases) {
+#pragma unroll
+            for (int b = 0; b < E / PSL::R; b++)
+#pragma unroll
+                for (int e = 0; e < PSL::R; e++) {
+                    const int k = Eng::template out_index<NP - 1>(i, b, e);
+                    const work w = r.v[b * PSL::R + e];
+                    /* natural order, NOT padded: lanes store / load runs of consecutive bins in both directions */
+                    FFT_TRACE_SMEM(&sm[k], (int)sizeof(xelem), 1);
+                    sm[k] = A::xstore(a.shl1 ? A::shl1(w) : w);               /* cfft_q31.c:803-820, cfft_q15.c:810-827 */
+                }
+        } else {
+#pragma unroll
+            for (int m = 0; m < E; m++) {
+                const int k = i + T * m;
+                FFT_TRACE_SMEM(&sm[k], (int)sizeof(xelem), 0);
+                FFT_TRACE_SMEM(&sm[k ? N - k : 0], (int)sizeof(xelem), 0);
+                if (m == 0 && i == 0) put_bin0(a, A::xload(sm[0]));
+                else put_bin(a, k, A::xload(sm[k]), A::xload(sm[N - k]));
             }
         }
     }

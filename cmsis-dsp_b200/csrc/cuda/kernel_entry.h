@@ -10,7 +10,8 @@
 
 namespace b200fft {
 
-enum KernelOp { OP_CFFT_F32 = 0, OP_CFFT_Q31 = 1, OP_CFFT_Q15 = 2, OP_RFFT_FWD = 3, OP_RFFT_INV = 4, OP_COUNT = 5 };
+enum KernelOp { OP_CFFT_F32 = 0, OP_CFFT_Q31 = 1, OP_CFFT_Q15 = 2, OP_RFFT_FWD = 3, OP_RFFT_INV = 4,
+                OP_RFFT_Q31_FWD = 5, OP_RFFT_Q31_INV = 6, OP_RFFT_Q15_FWD = 7, OP_RFFT_Q15_INV = 8, OP_COUNT = 9 };
 
 struct KernelFacts { int threads, frames, smem, regs, ctasPerSm; };
 
@@ -22,7 +23,9 @@ enum KernelFlavour { KF_DIRECT = 0, KF_PIPE = 1 };
 struct KernelEntry {
     /* cfft: in == out (in place), aux = output permutation (uint16, may be null), inv = ifftFlag,
      *       shl1 = final << 1 (fixed point, N = 2*4^m)
-     * rfft: in -> out, aux = twiddleCoef_rfft table (device); direction is fixed by the op */
+     * rfft: in -> out, aux = twiddleCoef_rfft table (device); direction is fixed by the op
+     * rfft q31/q15: in -> out, tw = twiddles of the cfft plan of the same type and complex length,
+     *       aux = split coefficients (ci32x4 per bin), shl1 as for cfft */
     int (*launch)(const void *in, void *out, uint64_t nFrames, int inv, const void *tw, const void *aux, int shl1,
                   int flavour, cudaStream_t st);
     /* number of elements of the pass-ordered twiddle table (+1 pad); fills hostOut when non-null */

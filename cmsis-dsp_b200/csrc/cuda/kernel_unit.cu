@@ -16,7 +16,7 @@
 #include "bulk_copy.cuh"
 
 #if !defined(KU_OP) || !defined(KU_N)
-#error "compile with -DKU_OP=<0..4> -DKU_N=<length>"
+#error "compile with -DKU_OP=<0..8> -DKU_N=<length>"
 #endif
 
 using namespace b200fft;
@@ -27,6 +27,17 @@ template <class PL> __device__ __forceinline__ void frame_sync()
 {
     if constexpr (PL::T <= 32) __syncwarp();
     else __syncthreads();
+}
+
+/* the phases of a body, a frame barrier between two of them */
+template <class BODY, class PL, int PH>
+__device__ __forceinline__ void run_phases(typename BODY::Regs &r, const typename BODY::Args &a, typename BODY::xelem *sm, int i, bool valid)
+{
+    if (valid) BODY::template phase<PH>(r, a, sm, i);
+    if constexpr (PH + 1 < BODY::kPhases) {
+        frame_sync<PL>();
+        run_phases<BODY, PL, PH + 1>(r, a, sm, i, valid);
+    }
 }
 
 template <class BODY, class PL>
@@ -43,19 +54,7 @@ __global__ void __launch_bounds__(PL::kThreads) frame_kernel(typename BODY::Args
     BODY::set_scratch(a, reinterpret_cast<xelem *>(smem_raw) + PL::F * PL::kFrameElems + fl * PL::kSpecial);
     typename BODY::Regs r;
 
-    if (valid) BODY::template phase<0>(r, a, sm, i);
-    if constexpr (BODY::kPhases > 1) {
-        frame_sync<PL>();
-        if (valid) BODY::template phase<1>(r, a, sm, i);
-    }
-    if constexpr (BODY::kPhases > 2) {
-        frame_sync<PL>();
-        if (valid) BODY::template phase<2>(r, a, sm, i);
-    }
-    if constexpr (BODY::kPhases > 3) {
-        frame_sync<PL>();
-        if (valid) BODY::template phase<3>(r, a, sm, i);
-    }
+    run_phases<BODY, PL, 0>(r, a, sm, i, valid);
 }
 
 /* ------------------------------------------------------------------ persistent TMA-fed kernel
@@ -532,7 +531,7 @@ static int ku_facts(KernelFacts *f, int flavour)
 }
 typedef PL TWPLAN;
 
-#else              /* arm_rfft_fast_f32 inverse */
+#elif KU_OP == 4   /* arm_rfft_fast_f32 inverse */
 
 typedef PlanRfftInv<KU_N>::type PL;
 #if KU_N <= 64
@@ -573,6 +572,36 @@ static int ku_facts(KernelFacts *f, int flavour)
 #endif
     return facts_of<RfftInvBody<PL>, PL>(f);
 }
+typedef PL TWPLAN;
+
+#else              /* arm_rfft_q31 (5 forward, 6 inverse) / arm_rfft_q15 (7, 8); KU_N = complex length = fftLenReal / 2 */
+
+#if KU_OP <= 6
+typedef ArithQ31 AR;
+#else
+typedef ArithQ15 AR;
+#endif
+typedef PlanCfftFix<AR, KU_N>::type PL;
+struct PIPE { static constexpr bool kHas = false, kPrefer = false; };
+#if KU_OP == 5 || KU_OP == 7
+typedef RfftFixFwdBody<PL> BODY;
+static BODY::Args ku_args(const void *in, void *out, const void *tw, const void *aux, int shl1)
+{
+    return BODY::Args{(const AR::elem *)in, (AR::elem *)out, (const AR::telem *)tw, (const ci32x4 *)aux, shl1};
+}
+#else
+typedef CfftBody<PL, true, false, false, true> BODY;
+static BODY::Args ku_args(const void *in, void *out, const void *tw, const void *aux, int shl1)
+{
+    return BODY::Args{(const AR::elem *)in, (AR::elem *)out, (const AR::telem *)tw, nullptr, 0.0f, shl1, (const ci32x4 *)aux};
+}
+#endif
+/* in -> out (never aliased), tw = the pass-ordered twiddles of the KU_N-point CFFT plan, aux = split coefficients */
+static int ku_launch(const void *in, void *out, uint64_t nFrames, int, const void *tw, const void *aux, int shl1, int, cudaStream_t st)
+{
+    return launch<BODY, PL>(ku_args(in, out, tw, aux, shl1), nFrames, st);
+}
+static int ku_facts(KernelFacts *f, int) { return facts_of<BODY, PL>(f); }
 typedef PL TWPLAN;
 
 #endif

@@ -3,6 +3,7 @@
  *
  *   arm_cfft_f32 / q31 / q15   reference: arm_cfft_f32.c:1243-1298, arm_cfft_q31.c:704-755, arm_cfft_q15.c:671-722
  *   arm_rfft_fast_f32          reference: arm_rfft_fast_f32.c:675-699
+ *   arm_rfft_q31 / q15         reference: arm_rfft_q31.c:145-181, arm_rfft_q15.c:148-182
  *   arm_*_batch_*              B200 extension (include/dsp/transform_functions.h)
  *
  * Data may live in host or device memory.  Host buffers are streamed through the device
@@ -207,3 +208,77 @@ void arm_rfft_fast_f32(const arm_rfft_fast_instance_f32 *S, float32_t *p, float3
 {
     g_last = rfft_batch(S, p, pOut, 1, ifftFlag, 1);
 }
+
+/* ---- fixed-point real FFT ---- */
+
+typedef int (*rfix_fn)(const void *, void *, uint32_t, uint64_t, uint8_t, void *);
+
+/* clobber != 0: a forward transform also leaves the fftLenReal/2-point CFFT in pSrc, the side effect of the
+ * reference's in-place CFFT on the source buffer (arm_rfft_q31.c:174, arm_rfft_q15.c:176) */
+static arm_status rfix_batch(int type, rfix_fn fn, cfft_fn cfn, size_t scalarBytes, uint32_t N, uint8_t ifftFlagR,
+                             uint8_t bitReverseFlagR, uint32_t modifier, const void *coefA, const void *coefB,
+                             const void *cfftTw, const uint16_t *br, uint16_t brLen, uint32_t cfftLen,
+                             void *pSrc, void *pDst, uint64_t nFrames, int clobber)
+{
+    if (!pSrc || !pDst || pSrc == pDst || !coefA || !coefB || !cfftTw) return ARM_MATH_ARGUMENT_ERROR;
+    if (N < 32 || N > 8192 || (N & (N - 1)) != 0 || cfftLen != N / 2 || bitReverseFlagR != 1) return ARM_MATH_ARGUMENT_ERROR;
+    if (nFrames == 0) return ARM_MATH_SUCCESS;
+    if (ctx_ready()) return ARM_MATH_ARGUMENT_ERROR;
+    if (ensure_plan(type, N / 2, cfftTw, br, brLen)) return ARM_MATH_ARGUMENT_ERROR;
+    if (!cmsisdsp_cuda_rfft_fix_plan_ready(type, N) && cmsisdsp_cuda_rfft_fix_plan_upload(type, N, coefA, coefB, modifier))
+        return ARM_MATH_ARGUMENT_ERROR;
+
+    const size_t inBytes = (size_t)(ifftFlagR ? 2 * N : N) * scalarBytes, outBytes = (size_t)(ifftFlagR ? N : 2 * N) * scalarBytes;
+    const int inDev = cmsisdsp_cuda_is_device_pointer(pSrc), outDev = cmsisdsp_cuda_is_device_pointer(pDst);
+    if (inDev < 0 || outDev < 0 || inDev != outDev) return ARM_MATH_ARGUMENT_ERROR;
+    if (inDev) {
+        if (fn(pSrc, pDst, N, nFrames, ifftFlagR, g_ctx.stream[0])) return ARM_MATH_ARGUMENT_ERROR;
+        if (clobber && !ifftFlagR && cfn(pSrc, N / 2, nFrames, 0, 1, g_ctx.stream[0])) return ARM_MATH_ARGUMENT_ERROR;
+        return cmsisdsp_cuda_stream_synchronize(g_ctx.stream[0]) ? ARM_MATH_ARGUMENT_ERROR : ARM_MATH_SUCCESS;
+    }
+    uint64_t perChunk = CHUNK_BYTES / (inBytes > outBytes ? inBytes : outBytes);
+    if (perChunk == 0) perChunk = 1;
+    int rc = 0, s = 0;
+    for (uint64_t f = 0; f < nFrames && !rc; f += perChunk, s = (s + 1) % NSTREAM) {
+        const uint64_t n = (nFrames - f < perChunk) ? nFrames - f : perChunk;
+        char *hin = (char *)pSrc + f * inBytes, *hout = (char *)pDst + f * outBytes;
+        void *din, *dout;
+        if ((rc = staging(s, 0, (size_t)perChunk * inBytes, &din))) break;
+        if ((rc = staging(s, 1, (size_t)perChunk * outBytes, &dout))) break;
+        if ((rc = cmsisdsp_cuda_memcpy_h2d(din, hin, (size_t)n * inBytes, g_ctx.stream[s]))) break;
+        if ((rc = fn(din, dout, N, n, ifftFlagR, g_ctx.stream[s]))) break;
+        if ((rc = cmsisdsp_cuda_memcpy_d2h(hout, dout, (size_t)n * outBytes, g_ctx.stream[s]))) break;
+        if (clobber && !ifftFlagR) {
+            if ((rc = cfn(din, N / 2, n, 0, 1, g_ctx.stream[s]))) break;
+            rc = cmsisdsp_cuda_memcpy_d2h(hin, din, (size_t)n * inBytes, g_ctx.stream[s]);
+        }
+    }
+    for (int i = 0; i < NSTREAM; i++)
+        if (cmsisdsp_cuda_stream_synchronize(g_ctx.stream[i])) rc = rc ? rc : -1;
+    return rc ? ARM_MATH_ARGUMENT_ERROR : ARM_MATH_SUCCESS;
+}
+
+static arm_status rfix_q31(const arm_rfft_instance_q31 *S, q31_t *pSrc, q31_t *pDst, uint64_t nFrames, int clobber)
+{
+    if (!S || !S->pCfft) return ARM_MATH_ARGUMENT_ERROR;
+    return rfix_batch(CMSISDSP_CUDA_Q31, cmsisdsp_cuda_rfft_q31, cmsisdsp_cuda_cfft_q31, sizeof(q31_t), S->fftLenReal, S->ifftFlagR,
+                      S->bitReverseFlagR, S->twidCoefRModifier, S->pTwiddleAReal, S->pTwiddleBReal, S->pCfft->pTwiddle,
+                      S->pCfft->pBitRevTable, S->pCfft->bitRevLength, S->pCfft->fftLen, pSrc, pDst, nFrames, clobber);
+}
+static arm_status rfix_q15(const arm_rfft_instance_q15 *S, q15_t *pSrc, q15_t *pDst, uint64_t nFrames, int clobber)
+{
+    if (!S || !S->pCfft) return ARM_MATH_ARGUMENT_ERROR;
+    return rfix_batch(CMSISDSP_CUDA_Q15, cmsisdsp_cuda_rfft_q15, cmsisdsp_cuda_cfft_q15, sizeof(q15_t), S->fftLenReal, S->ifftFlagR,
+                      S->bitReverseFlagR, S->twidCoefRModifier, S->pTwiddleAReal, S->pTwiddleBReal, S->pCfft->pTwiddle,
+                      S->pCfft->pBitRevTable, S->pCfft->bitRevLength, S->pCfft->fftLen, pSrc, pDst, nFrames, clobber);
+}
+arm_status arm_rfft_batch_q31(const arm_rfft_instance_q31 *S, const q31_t *pSrc, q31_t *pDst, uint32_t nFrames)
+{
+    return rfix_q31(S, (q31_t *)pSrc, pDst, nFrames, 0);
+}
+arm_status arm_rfft_batch_q15(const arm_rfft_instance_q15 *S, const q15_t *pSrc, q15_t *pDst, uint32_t nFrames)
+{
+    return rfix_q15(S, (q15_t *)pSrc, pDst, nFrames, 0);
+}
+void arm_rfft_q31(const arm_rfft_instance_q31 *S, q31_t *pSrc, q31_t *pDst) { g_last = rfix_q31(S, pSrc, pDst, 1, 1); }
+void arm_rfft_q15(const arm_rfft_instance_q15 *S, q15_t *pSrc, q15_t *pDst) { g_last = rfix_q15(S, pSrc, pDst, 1, 1); }

@@ -6,6 +6,7 @@
  *   arm_cfft_init_f32 / _N_f32     Source/TransformFunctions/arm_cfft_init_f32.c:116-136,291-354
  *   arm_cfft_init_q31 / q15        Source/TransformFunctions/arm_cfft_init_q31.c, arm_cfft_init_q15.c:116-138,283-345
  *   arm_rfft_fast_init_f32 / _N    Source/TransformFunctions/arm_rfft_fast_init_f32.c:83-99,331-371
+ *   arm_rfft_init_q31 / q15 / _N   Source/TransformFunctions/arm_rfft_init_q31.c:97-127,395-470, arm_rfft_init_q15.c
  */
 #include "arm_const_structs.h"
 
@@ -74,3 +75,38 @@ arm_status arm_rfft_fast_init_f32(arm_rfft_fast_instance_f32 *S, uint16_t fftLen
     default:    return ARM_MATH_ARGUMENT_ERROR;
     }
 }
+
+/* fixed-point real FFT: fftLenReal, its complex half, the stride through the 8192-entry realCoef tables */
+#define RFIX_INIT_N(EXT, TAB, N, H, MOD)                                                                        \
+    arm_status arm_rfft_init_##N##_##EXT(arm_rfft_instance_##EXT *S, uint32_t ifftFlagR, uint32_t bitReverseFlag) \
+    {                                                                                                           \
+        S->fftLenReal = (uint16_t)N;                                                                            \
+        S->pTwiddleAReal = realCoefA##TAB;                                                                      \
+        S->pTwiddleBReal = realCoefB##TAB;                                                                      \
+        S->ifftFlagR = (uint8_t)ifftFlagR;                                                                      \
+        S->bitReverseFlagR = (uint8_t)bitReverseFlag;                                                           \
+        S->twidCoefRModifier = MOD##U;                                                                          \
+        S->pCfft = &arm_cfft_sR_##EXT##_len##H;                                                                 \
+        return ARM_MATH_SUCCESS;                                                                                \
+    }
+#define RFIX_ALL(EXT, TAB)                                                                                      \
+    RFIX_INIT_N(EXT, TAB, 8192, 4096, 1) RFIX_INIT_N(EXT, TAB, 4096, 2048, 2) RFIX_INIT_N(EXT, TAB, 2048, 1024, 4) \
+    RFIX_INIT_N(EXT, TAB, 1024, 512, 8) RFIX_INIT_N(EXT, TAB, 512, 256, 16) RFIX_INIT_N(EXT, TAB, 256, 128, 32)  \
+    RFIX_INIT_N(EXT, TAB, 128, 64, 64) RFIX_INIT_N(EXT, TAB, 64, 32, 128) RFIX_INIT_N(EXT, TAB, 32, 16, 256)     \
+    arm_status arm_rfft_init_##EXT(arm_rfft_instance_##EXT *S, uint32_t fftLenReal, uint32_t ifftFlagR, uint32_t bitReverseFlag) \
+    {                                                                                                           \
+        switch (fftLenReal) {                                                                                   \
+        case 8192U: return arm_rfft_init_8192_##EXT(S, ifftFlagR, bitReverseFlag);                              \
+        case 4096U: return arm_rfft_init_4096_##EXT(S, ifftFlagR, bitReverseFlag);                              \
+        case 2048U: return arm_rfft_init_2048_##EXT(S, ifftFlagR, bitReverseFlag);                              \
+        case 1024U: return arm_rfft_init_1024_##EXT(S, ifftFlagR, bitReverseFlag);                              \
+        case 512U:  return arm_rfft_init_512_##EXT(S, ifftFlagR, bitReverseFlag);                               \
+        case 256U:  return arm_rfft_init_256_##EXT(S, ifftFlagR, bitReverseFlag);                               \
+        case 128U:  return arm_rfft_init_128_##EXT(S, ifftFlagR, bitReverseFlag);                               \
+        case 64U:   return arm_rfft_init_64_##EXT(S, ifftFlagR, bitReverseFlag);                                \
+        case 32U:   return arm_rfft_init_32_##EXT(S, ifftFlagR, bitReverseFlag);                                \
+        default:    return ARM_MATH_ARGUMENT_ERROR;                                                             \
+        }                                                                                                       \
+    }
+RFIX_ALL(q31, Q31)
+RFIX_ALL(q15, Q15)

@@ -20,6 +20,7 @@ LIBDIR = os.path.normpath(os.path.join(_HERE, "..", "..", "lib"))
 
 LENGTHS = [16, 32, 64, 128, 256, 512, 1024, 2048, 4096]
 RLENGTHS = [32, 64, 128, 256, 512, 1024, 2048, 4096]
+RFIX_LENGTHS = [32, 64, 128, 256, 512, 1024, 2048, 4096, 8192]      # arm_rfft_q31 / arm_rfft_q15
 ARM_MATH_SUCCESS = 0
 ARM_MATH_ARGUMENT_ERROR = -1
 TYPE_ID = {"f32": 0, "q31": 1, "q15": 2}
@@ -42,6 +43,19 @@ CFFT_INSTANCE = {"f32": arm_cfft_instance_f32, "q31": arm_cfft_instance_q31, "q1
 
 class arm_rfft_fast_instance_f32(C.Structure):
     _fields_ = [("Sint", arm_cfft_instance_f32), ("fftLenRFFT", C.c_uint16), ("pTwiddleRFFT", C.POINTER(C.c_float))]
+
+
+def _mk_rfft_fix_instance(scalar, cfft):
+    class Inst(C.Structure):
+        _fields_ = [("fftLenReal", C.c_uint32), ("ifftFlagR", C.c_uint8), ("bitReverseFlagR", C.c_uint8),
+                    ("twidCoefRModifier", C.c_uint32), ("pTwiddleAReal", C.POINTER(scalar)),
+                    ("pTwiddleBReal", C.POINTER(scalar)), ("pCfft", C.POINTER(cfft))]
+    return Inst
+
+
+arm_rfft_instance_q31 = _mk_rfft_fix_instance(C.c_int32, arm_cfft_instance_q31)
+arm_rfft_instance_q15 = _mk_rfft_fix_instance(C.c_int16, arm_cfft_instance_q15)
+RFIX_INSTANCE = {"q31": arm_rfft_instance_q31, "q15": arm_rfft_instance_q15}
 
 
 class arm_mfcc_instance_f32(C.Structure):
@@ -83,6 +97,8 @@ def cuda():
         "cmsisdsp_cuda_cfft_q31": ([vp, u32, u64, u8, u8, vp], i),
         "cmsisdsp_cuda_cfft_q15": ([vp, u32, u64, u8, u8, vp], i),
         "cmsisdsp_cuda_rfft_fast_f32": ([vp, vp, u32, u64, u8, vp], i),
+        "cmsisdsp_cuda_rfft_fix_plan_upload": ([i, u32, vp, vp, u32], i), "cmsisdsp_cuda_rfft_fix_plan_ready": ([i, u32], i),
+        "cmsisdsp_cuda_rfft_q31": ([vp, vp, u32, u64, u8, vp], i), "cmsisdsp_cuda_rfft_q15": ([vp, vp, u32, u64, u8, vp], i),
         "cmsisdsp_cuda_last_error": ([], C.c_char_p), "cmsisdsp_cuda_launch_count": ([], u64),
         "cmsisdsp_cuda_set_kernel_flavour": ([i], i),
         "cmsisdsp_cuda_mfcc_plan_create": ([u32, u32, u32, vp, vp, vp, vp, vp, C.POINTER(vp)], i),
@@ -122,6 +138,16 @@ def lib():
     L.arm_rfft_fast_batch_f32.argtypes = [C.POINTER(arm_rfft_fast_instance_f32), C.c_void_p, C.c_void_p, u32, u8]
     L.arm_rfft_fast_batch_f32.restype = i
     L.arm_cuda_last_status.argtypes, L.arm_cuda_last_status.restype = [], i
+    for k, inst in RFIX_INSTANCE.items():
+        f = getattr(L, f"arm_rfft_init_{k}")
+        f.argtypes, f.restype = [C.POINTER(inst), u32, u32, u32], i
+        for n in RFIX_LENGTHS:
+            f = getattr(L, f"arm_rfft_init_{n}_{k}")
+            f.argtypes, f.restype = [C.POINTER(inst), u32, u32], i
+        f = getattr(L, f"arm_rfft_{k}")
+        f.argtypes, f.restype = [C.POINTER(inst), C.c_void_p, C.c_void_p], None
+        f = getattr(L, f"arm_rfft_batch_{k}")
+        f.argtypes, f.restype = [C.POINTER(inst), C.c_void_p, C.c_void_p, u32], i
     mp = C.POINTER(arm_mfcc_instance_f32)
     L.arm_mfcc_init_f32.argtypes, L.arm_mfcc_init_f32.restype = [mp, u32, u32, u32] + [C.c_void_p] * 5, i
     for n in (32, 64, 128, 256, 512, 1024, 2048, 4096):
@@ -197,6 +223,28 @@ def rfft_batch(N, x, ifft=0):
     return out
 
 
+def rfft_fix_instance(kind, N, ifft=0, bitrev=1):
+    S = RFIX_INSTANCE[kind]()
+    st = getattr(lib(), f"arm_rfft_init_{kind}")(C.byref(S), N, int(ifft), int(bitrev))
+    if st != ARM_MATH_SUCCESS:
+        raise ValueError(f"arm_rfft_init_{kind}({N}) -> {st}")
+    return S
+
+
+def rfft_fix_batch(kind, N, x, ifft=0):
+    """arm_rfft_batch_<q31|q15> on a host array: forward [..., N] -> [frames, 2N]; inverse [..., 2N] -> [frames, N]."""
+    src = np.ascontiguousarray(x, dtype=NP_DTYPE[kind])
+    per = 2 * N if ifft else N
+    assert src.size % per == 0
+    frames = src.size // per
+    out = np.empty((frames, N if ifft else 2 * N), dtype=NP_DTYPE[kind])
+    S = rfft_fix_instance(kind, N, ifft, 1)
+    st = getattr(lib(), f"arm_rfft_batch_{kind}")(C.byref(S), src.ctypes.data, out.ctypes.data, frames)
+    if st != ARM_MATH_SUCCESS:
+        raise RuntimeError(f"arm_rfft_batch_{kind} -> {st}: {last_error()}")
+    return out
+
+
 class Mfcc:
     """arm_mfcc_instance_f32 initialised from a config dict (fftLen, nbMel, nbDct, dct, pos, len, coefs,
     window as numpy arrays); keeps the arrays alive, as a C caller would keep its coefficient tables."""
@@ -241,6 +289,21 @@ def ensure_rfft_plans(N):
     rc = cuda().cmsisdsp_cuda_rfft_plan_upload(N, C.cast(S.pTwiddleRFFT, C.c_void_p))
     if rc:
         raise RuntimeError(f"rfft_plan_upload({N}) -> {rc}: {last_error()}")
+
+
+def ensure_rfft_fix_plans(kind, N):
+    ensure_plans(kind, N // 2)
+    S = rfft_fix_instance(kind, N)
+    rc = cuda().cmsisdsp_cuda_rfft_fix_plan_upload(TYPE_ID[kind], N, C.cast(S.pTwiddleAReal, C.c_void_p),
+                                                   C.cast(S.pTwiddleBReal, C.c_void_p), S.twidCoefRModifier)
+    if rc:
+        raise RuntimeError(f"rfft_fix_plan_upload({kind},{N}) -> {rc}: {last_error()}")
+
+
+def rfft_fix_device(kind, N, d_in, d_out, n_frames, ifft=0, stream=0):
+    rc = getattr(cuda(), f"cmsisdsp_cuda_rfft_{kind}")(d_in, d_out, N, n_frames, int(ifft), stream)
+    if rc:
+        raise RuntimeError(f"cmsisdsp_cuda_rfft_{kind} -> {rc}: {last_error()}")
 
 
 def cfft_device(kind, N, dptr, n_frames, ifft=0, bitrev=1, stream=0):

@@ -71,6 +71,12 @@ extern const uint16_t armBitRevIndexTable_fixed_1024[ARMBITREVINDEXTABLE_FIXED_1
 extern const uint16_t armBitRevIndexTable_fixed_2048[ARMBITREVINDEXTABLE_FIXED_2048_TABLE_LENGTH];
 extern const uint16_t armBitRevIndexTable_fixed_4096[ARMBITREVINDEXTABLE_FIXED_4096_TABLE_LENGTH];
 
+/* split-stage coefficients of arm_rfft_q31 / arm_rfft_q15 (Include/arm_common_tables.h:241-245) */
+extern const q31_t realCoefAQ31[8192];
+extern const q31_t realCoefBQ31[8192];
+extern const q15_t realCoefAQ15[8192];
+extern const q15_t realCoefBQ15[8192];
+
 #ifdef __cplusplus
 }
 #endif

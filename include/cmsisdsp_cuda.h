@@ -85,6 +85,22 @@ int  cmsisdsp_cuda_cfft_q15(void *d_p, uint32_t fftLen, uint64_t nFrames,
 int  cmsisdsp_cuda_rfft_fast_f32(const void *d_p, void *d_out, uint32_t fftLenReal, uint64_t nFrames,
                                  uint8_t ifftFlag, void *stream);
 
+/* ---- arm_rfft_q31 / arm_rfft_q15 (Source/TransformFunctions/arm_rfft_q31.c:145-181, arm_rfft_q15.c:148-182) ----
+ * fftLenReal in {32..8192}; bitReverseFlagR = 1 (natural-order spectrum).  The plan is the cfft plan of the
+ * same type and length fftLenReal/2 (cmsisdsp_cuda_plan_upload) plus the split-stage coefficients: the
+ * instance's pTwiddleAReal / pTwiddleBReal (realCoefA/B, read at twidCoefRModifier), compacted on upload.
+ * forward (ifftFlagR = 0): d_src nFrames*fftLenReal scalars (left untouched), d_dst nFrames*2*fftLenReal
+ *     scalars = fftLenReal complex bins per frame, conjugate mirror included, as the reference writes them;
+ * inverse (ifftFlagR = 1): d_src frames 2*fftLenReal scalars apart, bins 0..fftLenReal/2 are read;
+ *     d_dst nFrames*fftLenReal scalars.  d_src and d_dst must not alias. */
+int  cmsisdsp_cuda_rfft_fix_plan_upload(int type, uint32_t fftLenReal, const void *pTwiddleAReal,
+                                        const void *pTwiddleBReal, uint32_t twidCoefRModifier);
+int  cmsisdsp_cuda_rfft_fix_plan_ready(int type, uint32_t fftLenReal);
+int  cmsisdsp_cuda_rfft_q31(const void *d_src, void *d_dst, uint32_t fftLenReal, uint64_t nFrames,
+                            uint8_t ifftFlagR, void *stream);
+int  cmsisdsp_cuda_rfft_q15(const void *d_src, void *d_dst, uint32_t fftLenReal, uint64_t nFrames,
+                            uint8_t ifftFlagR, void *stream);
+
 /* ---- arm_mfcc_f32 front end (Source/TransformFunctions/arm_mfcc_f32.c:88-174, arm_mfcc_init_f32.c:91-121) ----
  * One fused kernel per frame batch: normalise, window, rfft, magnitude, mel filter bank, log, DCT.
  * The plan keeps device copies of the caller's coefficient arrays (the arguments of arm_mfcc_init_f32);
@@ -108,7 +124,8 @@ int  cmsisdsp_cuda_set_kernel_flavour(int flavour);
 const char *cmsisdsp_cuda_last_error(void);        /* thread-local, never NULL */
 uint64_t    cmsisdsp_cuda_launch_count(void);      /* kernels launched by this library so far */
 /* static facts about the kernel chosen for (op, fftLen): op 0 cfft_f32, 1 cfft_q31, 2 cfft_q15,
- * 3 rfft forward, 4 rfft inverse (fftLen = real length for 3/4).  Any out pointer may be NULL. */
+ * 3 rfft forward, 4 rfft inverse, 5/6 rfft_q31 forward/inverse, 7/8 rfft_q15 forward/inverse (fftLen = real
+ * length for 3..8).  Any out pointer may be NULL. */
 int  cmsisdsp_cuda_kernel_info(int op, uint32_t fftLen, int *threadsPerCta, int *framesPerCta,
                                int *smemBytes, int *regsPerThread, int *ctasPerSm);
 

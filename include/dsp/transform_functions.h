@@ -3,7 +3,8 @@
  *
  * Instance structs, init and exec prototypes are those of the reference's generic
  * (non-Neon, non-MVE) branch, field for field and argument for argument
- * (Include/dsp/transform_functions.h:282-331 q15, :347-394 q31, :410-460 f32, :813-849 rfft_fast),
+ * (Include/dsp/transform_functions.h:282-331 q15, :347-394 q31, :410-460 f32, :813-849 rfft_fast,
+ * :508-617 rfft_q15, :655-760 rfft_q31),
  * so existing callers re-link without source changes.  The `*_batch_*` functions at the end
  * are the B200 extension: the same transform over nFrames contiguous frames in one call.
  *
@@ -106,6 +107,48 @@ arm_status arm_rfft_fast_init_4096_f32(arm_rfft_fast_instance_f32 *S);
 arm_status arm_rfft_fast_init_f32(arm_rfft_fast_instance_f32 *S, uint16_t fftLen);
 void arm_rfft_fast_f32(const arm_rfft_fast_instance_f32 *S, float32_t *p, float32_t *pOut, uint8_t ifftFlag);
 
+/* ---------------------------------------------------------------- q15 / q31 RFFT
+ * Instance, init and exec are the reference's generic (non-Neon, non-MVE) branch
+ * (Include/dsp/transform_functions.h:508-521,566-617 q15, :655-668,694-745 q31).  fftLenReal in {32..8192}.
+ * Buffers as in the reference: forward reads fftLenReal scalars and writes 2*fftLenReal (all fftLenReal
+ * complex bins, conjugate half included); inverse reads bins 0..fftLenReal/2 and writes fftLenReal scalars.
+ * bitReverseFlagR = 1 is the supported mode (natural-order spectrum); with 0 the exec functions do nothing
+ * and report ARM_MATH_ARGUMENT_ERROR through arm_cuda_last_status(). */
+typedef struct
+{
+          uint32_t fftLenReal;                /* length of the real FFT */
+          uint8_t  ifftFlagR;                 /* 0: forward, 1: inverse */
+          uint8_t  bitReverseFlagR;           /* 1: output in natural order */
+          uint32_t twidCoefRModifier;         /* stride through the 8192-entry coefficient tables */
+    const q15_t   *pTwiddleAReal;             /* realCoefAQ15 */
+    const q15_t   *pTwiddleBReal;             /* realCoefBQ15 */
+    const arm_cfft_instance_q15 *pCfft;       /* complex FFT instance of length fftLenReal/2 */
+} arm_rfft_instance_q15;
+
+typedef struct
+{
+          uint32_t fftLenReal;
+          uint8_t  ifftFlagR;
+          uint8_t  bitReverseFlagR;
+          uint32_t twidCoefRModifier;
+    const q31_t   *pTwiddleAReal;             /* realCoefAQ31 */
+    const q31_t   *pTwiddleBReal;             /* realCoefBQ31 */
+    const arm_cfft_instance_q31 *pCfft;
+} arm_rfft_instance_q31;
+
+#define CMSISDSP_B200_DECL_RFFT_FIX(N)                                                                             \
+    arm_status arm_rfft_init_##N##_q15(arm_rfft_instance_q15 *S, uint32_t ifftFlagR, uint32_t bitReverseFlag);   \
+    arm_status arm_rfft_init_##N##_q31(arm_rfft_instance_q31 *S, uint32_t ifftFlagR, uint32_t bitReverseFlag);
+CMSISDSP_B200_DECL_RFFT_FIX(32) CMSISDSP_B200_DECL_RFFT_FIX(64) CMSISDSP_B200_DECL_RFFT_FIX(128)
+CMSISDSP_B200_DECL_RFFT_FIX(256) CMSISDSP_B200_DECL_RFFT_FIX(512) CMSISDSP_B200_DECL_RFFT_FIX(1024)
+CMSISDSP_B200_DECL_RFFT_FIX(2048) CMSISDSP_B200_DECL_RFFT_FIX(4096) CMSISDSP_B200_DECL_RFFT_FIX(8192)
+#undef CMSISDSP_B200_DECL_RFFT_FIX
+arm_status arm_rfft_init_q15(arm_rfft_instance_q15 *S, uint32_t fftLenReal, uint32_t ifftFlagR, uint32_t bitReverseFlag);
+arm_status arm_rfft_init_q31(arm_rfft_instance_q31 *S, uint32_t fftLenReal, uint32_t ifftFlagR, uint32_t bitReverseFlag);
+/* pSrc is modified by the forward transform like in the reference (it then holds the fftLenReal/2-point CFFT) */
+void arm_rfft_q15(const arm_rfft_instance_q15 *S, q15_t *pSrc, q15_t *pDst);
+void arm_rfft_q31(const arm_rfft_instance_q31 *S, q31_t *pSrc, q31_t *pDst);
+
 /* ---------------------------------------------------------------- f32 MFCC (RFFT based)
  * Instance and init are the reference's (Include/dsp/transform_functions.h:856-998, generic branch);
  * supported fftLen here: 256, 512, 1024, 2048, 4096. */
@@ -173,6 +216,11 @@ arm_status arm_cfft_batch_q15(const arm_cfft_instance_q15 *S, q15_t *p, uint32_t
                               uint8_t ifftFlag, uint8_t bitReverseFlag);
 arm_status arm_rfft_fast_batch_f32(const arm_rfft_fast_instance_f32 *S, float32_t *p, float32_t *pOut,
                                    uint32_t nFrames, uint8_t ifftFlag);
+/* Fixed-point real FFT over nFrames frames; direction = S->ifftFlagR.  forward: pSrc frames fftLenReal
+ * scalars apart, pDst frames 2*fftLenReal apart; inverse: pSrc frames 2*fftLenReal apart (bins
+ * 0..fftLenReal/2 are read), pDst frames fftLenReal apart.  pSrc is left untouched. */
+arm_status arm_rfft_batch_q31(const arm_rfft_instance_q31 *S, const q31_t *pSrc, q31_t *pDst, uint32_t nFrames);
+arm_status arm_rfft_batch_q15(const arm_rfft_instance_q15 *S, const q15_t *pSrc, q15_t *pDst, uint32_t nFrames);
 /* status of the most recent legacy (void) exec call on this thread */
 arm_status arm_cuda_last_status(void);
 

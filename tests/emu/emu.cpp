@@ -173,6 +173,54 @@ int emu_rfft(uint32_t Nreal, const float *in, float *out, uint64_t nFrames, int 
     }
 }
 
+/* arm_rfft_q31 (type 1) / arm_rfft_q15 (type 2): Nreal = real length 32..8192; forward frames Nreal
+ * scalars in -> 2*Nreal scalars out, inverse frames 2*Nreal scalars in -> Nreal out.  tw = the
+ * reference-layout twiddles of the Nreal/2-point CFFT, coefA/B = realCoefA/B tables (8192 entries). */
+int emu_rfft_fix(int type, uint32_t Nreal, const void *in, void *out, uint64_t nFrames, int ifft, const void *tw,
+                 const void *coefA, const void *coefB)
+{
+    const uint32_t L2 = Nreal / 2, mod = 8192u / Nreal;
+    std::vector<ci32x4> coef(L2);
+    for (uint32_t k = 0; k < L2; k++) {
+        if (type == 1) {
+            const int32_t *A = (const int32_t *)coefA, *B = (const int32_t *)coefB;
+            coef[k] = ci32x4{A[2 * k * mod], A[2 * k * mod + 1], B[2 * k * mod], B[2 * k * mod + 1]};
+        } else {
+            const int16_t *A = (const int16_t *)coefA, *B = (const int16_t *)coefB;
+            coef[k] = ci32x4{A[2 * k * mod], A[2 * k * mod + 1], B[2 * k * mod], B[2 * k * mod + 1]};
+        }
+    }
+    const int shl1 = __builtin_ctz(L2) & 1;
+    switch (L2) {
+#define RUN(AR, n)                                                                                   \
+    {                                                                                                \
+        typedef PlanCfftFix<AR, n>::type PL;                                                         \
+        typedef AR::elem elem;                                                                       \
+        std::vector<AR::telem> ordered((size_t)PL::kTwEntries + 1);                                  \
+        PL::build_twiddles((const elem *)tw, ordered.data());                                        \
+        if (!ifft) {                                                                                 \
+            typedef RfftFixFwdBody<PL> BODY;                                                         \
+            run_batch<PL, BODY>(nFrames, [&](uint64_t f) {                                           \
+                return BODY::Args{(const elem *)in + f * n, (elem *)out + f * 2 * n, ordered.data(), coef.data(), shl1}; \
+            });                                                                                      \
+        } else {                                                                                     \
+            typedef CfftBody<PL, true, false, false, true> BODY;                                     \
+            run_batch<PL, BODY>(nFrames, [&](uint64_t f) {                                           \
+                return BODY::Args{(const elem *)in + f * 2 * n, (elem *)out + f * n, ordered.data(), nullptr, 0.0f, shl1, coef.data()}; \
+            });                                                                                      \
+        }                                                                                            \
+    }
+#define CASE(n)                                                     \
+    case n:                                                         \
+        if (type == 1) RUN(ArithQ31, n) else RUN(ArithQ15, n)       \
+        return 0;
+        FOR_ALL_N(CASE)
+#undef CASE
+#undef RUN
+    default: return -1;
+    }
+}
+
 void emu_trace_begin(void) { g_trace.clear(); g_trace_on = true; }
 
 /* Per (phase, is_store): number of warp-level requests and the shared-memory wavefronts they

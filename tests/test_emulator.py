@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 import cmsisdsp_b200 as cd
-from oracle_lib import LENGTHS, RLENGTHS, oracle, perm_from_swaps
+from oracle_lib import LENGTHS, RFIX_LENGTHS, RLENGTHS, oracle, perm_from_swaps
 from seeded_inputs import cfft_input, rfft_input
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -29,6 +29,7 @@ def emu():
     L.emu_cfft.argtypes = [C.c_int, C.c_uint32, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.emu_rfft.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
     L.emu_trace_stats.argtypes = [C.c_void_p, C.c_int]
+    L.emu_rfft_fix.argtypes = [C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     return L
 
 
@@ -115,3 +116,35 @@ def test_rfft_exchange_bank_conflicts(emu, N, ifft):
         if (ifft == 0 and ph == 1 and st) or (ifft == 0 and ph == 2) or (ifft == 1 and ph == 0) or (ifft == 1 and ph == 1 and not st):
             continue                              # phases that touch the scratch area
         assert wf <= 1.0 * ideal, (N, ifft, int(ph), "store" if st else "load", wf / ideal)
+
+
+@pytest.mark.parametrize("kind", ["q31", "q15"])
+@pytest.mark.parametrize("N", RFIX_LENGTHS)
+def test_rfft_fixed_point_bodies(emu, kind, N):
+    """RfftFixFwdBody (CFFT + split stage fused) and CfftBody<.., RIFFT> (merge stage fused into the load, final
+    saturating << 1) against the oracle, bit for bit, with the product's own tables; ragged last CTA; full-scale
+    frames (wrap-around sums, saturation); no bank conflicts in the extra exchange of the forward body"""
+    S = cd.rfft_fix_instance(kind, N)
+    A = np.ctypeslib.as_array(S.pTwiddleAReal, shape=(8192,))
+    B = np.ctypeslib.as_array(S.pTwiddleBReal, shape=(8192,))
+    tw, _ = cd.instance_tables(S.pCfft.contents, kind)
+    frames = 2 * {16: 128, 32: 64, 64: 32, 128: 16, 256: 8, 512: 4, 1024: 2}.get(N // 2, 1) + 3
+    x = cfft_input(kind, N // 2, frames=max(frames, 6), seed=7 * N)                 # [frames, N] real samples
+    want = oracle().rfft_fix(kind, N, x, 0, 1)
+    got = np.zeros_like(want)
+    emu.emu_trace_begin()
+    assert emu.emu_rfft_fix(cd.TYPE_ID[kind], N, x.ctypes.data, got.ctypes.data, x.shape[0], 0, tw.ctypes.data,
+                            A.ctypes.data, B.ctypes.data) == 0
+    assert np.array_equal(got, want), (kind, N, "forward")
+    rows = np.zeros((64, 6), dtype=np.int64)
+    n = emu.emu_trace_stats(rows.ctypes.data, 64)
+    first_new = 2 if N // 2 <= 256 else 4          # the phases the fused split adds behind the CFFT's own (2- / 3-pass plans)
+    for ph, st, nbytes, req, ideal, wf in rows[:n]:
+        if N // 2 >= 256 and ph >= first_new:
+            assert wf == ideal, f"{kind} N={N} phase {ph} {'store' if st else 'load'}: {wf} wavefronts for {ideal} ideal"
+    spec = np.concatenate([want, cfft_input(kind, N, frames=6, seed=11 * N)])       # genuine spectra + arbitrary bins
+    want = oracle().rfft_fix(kind, N, spec, 1, 1)
+    got = np.zeros_like(want)
+    assert emu.emu_rfft_fix(cd.TYPE_ID[kind], N, spec.ctypes.data, got.ctypes.data, spec.shape[0], 1, tw.ctypes.data,
+                            A.ctypes.data, B.ctypes.data) == 0
+    assert np.array_equal(got, want), (kind, N, "inverse")

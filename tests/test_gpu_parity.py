@@ -13,8 +13,9 @@ import numpy as np
 import pytest
 
 import cmsisdsp_b200 as cd
-from golden_checks import assert_like_reference, golden_cases, ref_digests
-from oracle_lib import LENGTHS, RLENGTHS, oracle
+from golden_checks import (assert_like_reference, assert_rfft_fix_like_reference, golden_cases, golden_rfft_fix_cases,
+                           ref_digests, rfft_fix_threshold_applies)
+from oracle_lib import LENGTHS, RFIX_LENGTHS, RLENGTHS, oracle
 from seeded_inputs import cfft_input, rfft_input
 
 pytestmark = pytest.mark.gpu
@@ -300,6 +301,91 @@ def test_direct_and_pipelined_flavours_agree_bit_for_bit():
     finally:
         cu.cmsisdsp_cuda_set_kernel_flavour(-1)
     assert cu.cmsisdsp_cuda_set_kernel_flavour(7) != 0
+
+
+# ------------------------------------------------------------------ arm_rfft_q31 / arm_rfft_q15
+
+@pytest.mark.parametrize("kind", ["q31", "q15"])
+@pytest.mark.parametrize("N", RFIX_LENGTHS)
+def test_rfft_fixed_point_bit_exact(kind, N):
+    """forward and inverse through arm_rfft_batch_*, host buffers, ragged batch, full-scale frames: memcmp-identical
+    to the oracle; digests of the compiled reference; pSrc left untouched by the batched call"""
+    x = cfft_input(kind, N // 2, frames=203, seed=N)                # [203, N] real samples
+    xin = x.copy()
+    spec = cd.rfft_fix_batch(kind, N, xin, 0)
+    assert np.array_equal(xin, x)
+    assert spec.shape == (203, 2 * N)
+    assert np.array_equal(spec, oracle().rfft_fix(kind, N, x, 0, 1, threads=NT)), (kind, N, "forward")
+    src = np.concatenate([spec, cfft_input(kind, N, frames=37, seed=2 * N)])
+    back = cd.rfft_fix_batch(kind, N, src, 1)
+    assert np.array_equal(back, oracle().rfft_fix(kind, N, src, 1, 1, threads=NT)), (kind, N, "inverse")
+    dig = ref_digests()
+    x8 = cfft_input(kind, N // 2, frames=8, seed=3 * N)
+    y = cd.rfft_fix_batch(kind, N, x8, 0)
+    assert hashlib.sha256(y.tobytes()).hexdigest() == dig[f"rfft_{kind}/{N}/0"]
+    z = cd.rfft_fix_batch(kind, N, np.concatenate([y, cfft_input(kind, N, frames=4, seed=5 * N)]), 1)
+    assert hashlib.sha256(z.tobytes()).hexdigest() == dig[f"rfft_{kind}/{N}/1"]
+
+
+@pytest.mark.parametrize("kind", ["q31", "q15"])
+def test_rfft_fixed_point_reference_patterns_and_legacy_call(kind):
+    n = 0
+    for N, sig, ifft, x, ref in golden_rfft_fix_cases(kind):
+        if not rfft_fix_threshold_applies(kind, N, sig, ifft):
+            continue
+        snr, want = assert_rfft_fix_like_reference(kind, N, ifft, cd.rfft_fix_batch(kind, N, x, ifft), ref)
+        assert want is None or snr >= want, (kind, N, sig, ifft, snr)
+        n += 1
+    assert n == {"q31": 24, "q15": 22}[kind]
+    # legacy single-frame call (arm_rfft_q31.c:145-181): same bits, and pSrc ends up holding the N/2-point CFFT
+    N = 256
+    L = cd.lib()
+    x = cfft_input(kind, N // 2, frames=1, seed=77).reshape(-1)
+    p, out = x.copy(), np.zeros(2 * N, dtype=x.dtype)
+    S = cd.rfft_fix_instance(kind, N, 0, 1)
+    getattr(L, f"arm_rfft_{kind}")(C.byref(S), p.ctypes.data, out.ctypes.data)
+    assert L.arm_cuda_last_status() == 0, cd.last_error()
+    assert np.array_equal(out, oracle().rfft_fix(kind, N, x, 0, 1)[0])
+    assert np.array_equal(p, oracle().cfft(kind, N // 2, x, 0, 1).reshape(-1))
+    Si = cd.rfft_fix_instance(kind, N, 1, 1)
+    back = np.zeros(N, dtype=x.dtype)
+    spec = out.copy()
+    getattr(L, f"arm_rfft_{kind}")(C.byref(Si), spec.ctypes.data, back.ctypes.data)
+    assert L.arm_cuda_last_status() == 0
+    assert np.array_equal(back, oracle().rfft_fix(kind, N, out, 1, 1)[0]) and np.array_equal(spec, out)
+    # unsupported mode / arguments
+    S0 = cd.rfft_fix_instance(kind, N, 0, 0)
+    assert getattr(L, f"arm_rfft_batch_{kind}")(C.byref(S0), p.ctypes.data, out.ctypes.data, 1) == cd.ARM_MATH_ARGUMENT_ERROR
+    assert getattr(L, f"arm_rfft_batch_{kind}")(C.byref(S), p.ctypes.data, p.ctypes.data, 1) == cd.ARM_MATH_ARGUMENT_ERROR
+    assert getattr(L, f"arm_rfft_batch_{kind}")(C.byref(S), p.ctypes.data, out.ctypes.data, 0) == 0
+
+
+@pytest.mark.parametrize("kind", ["q31", "q15"])
+def test_rfft_fixed_point_large_batch_device_pointers(kind):
+    """2^16 frames of N = 1024 resident on the device, forward then inverse through the shim; stratified oracle check"""
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda", 0)
+    N, B = 1024, 1 << 16
+    tdt = torch.int32 if kind == "q31" else torch.int16
+    info = np.iinfo(cd.NP_DTYPE[kind])
+    g = torch.Generator(device=dev).manual_seed(9)
+    x = torch.randint(info.min // 2, info.max // 2, (B, N), device=dev, dtype=tdt, generator=g)
+    spec = torch.empty(B, 2 * N, device=dev, dtype=tdt)
+    back = torch.empty(B, N, device=dev, dtype=tdt)
+    cd.ensure_rfft_fix_plans(kind, N)
+    st = torch.cuda.current_stream().cuda_stream
+    cd.rfft_fix_device(kind, N, x.data_ptr(), spec.data_ptr(), B, 0, st)
+    cd.rfft_fix_device(kind, N, spec.data_ptr(), back.data_ptr(), B, 1, st)
+    torch.cuda.synchronize()
+    idx = torch.arange(0, B, B // 512, device=dev)
+    xs = x[idx].cpu().numpy()
+    want = oracle().rfft_fix(kind, N, xs, 0, 1, threads=NT)
+    assert np.array_equal(spec[idx].cpu().numpy(), want)
+    assert np.array_equal(back[idx].cpu().numpy(), oracle().rfft_fix(kind, N, want, 1, 1, threads=NT))
+    # conjugate symmetry of every frame's spectrum (size-independent property): bin N-k == conj(bin k)
+    sp = spec.view(B, N, 2)
+    assert bool((sp[:, 1:N // 2, 0] == sp[:, N // 2 + 1:, 0].flip(1)).all().item())
+    assert bool((sp[:, 1:N // 2, 1] == -sp[:, N // 2 + 1:, 1].flip(1)).all().item())
 
 
 # ------------------------------------------------------------------ MFCC front end (BASELINE config 4)

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import cmsisdsp_b200 as cd
-from oracle_lib import LENGTHS, RLENGTHS, oracle, ref
+from oracle_lib import LENGTHS, RFIX_LENGTHS, RLENGTHS, oracle, ref
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -36,6 +36,31 @@ def test_generated_tables_match_oracle_and_reference(N):
                 assert np.array_equal(bits(twr), bits(chk.table("twiddle_rfft_f32", N)))
 
 
+@pytest.mark.parametrize("kind", ["q31", "q15"])
+def test_real_coef_tables_and_rfft_fix_instances(kind):
+    """realCoefA/B tables generated at build time == oracle == compiled reference; the instance fields are the
+    reference's (arm_rfft_init_q31.c:97-127: modifier = 8192 / fftLenReal, pCfft = preset of half the length)"""
+    checkers = [oracle()] + ([ref()] if ref() is not None else [])
+    for N in RFIX_LENGTHS:
+        for ifft in (0, 1):
+            S = cd.rfft_fix_instance(kind, N, ifft, 1)
+            assert (S.fftLenReal, S.ifftFlagR, S.bitReverseFlagR, S.twidCoefRModifier) == (N, ifft, 1, 8192 // N)
+            assert S.pCfft.contents.fftLen == N // 2
+            assert bytes(S.pCfft.contents) == bytes(cd.preset(kind, N // 2))
+    S = cd.rfft_fix_instance(kind, 8192)
+    A = np.ctypeslib.as_array(S.pTwiddleAReal, shape=(8192,)).copy()
+    B = np.ctypeslib.as_array(S.pTwiddleBReal, shape=(8192,)).copy()
+    for chk in checkers:
+        assert np.array_equal(A, chk.real_coef(kind, 0)) and np.array_equal(B, chk.real_coef(kind, 1))
+    L = cd.lib()
+    for bad in (0, 16, 48, 16384):
+        assert getattr(L, f"arm_rfft_init_{kind}")(C.byref(S), bad, 0, 1) == cd.ARM_MATH_ARGUMENT_ERROR
+    for N in RFIX_LENGTHS:
+        S2 = cd.RFIX_INSTANCE[kind]()
+        assert getattr(L, f"arm_rfft_init_{N}_{kind}")(C.byref(S2), 1, 1) == cd.ARM_MATH_SUCCESS
+        assert bytes(S2) == bytes(cd.rfft_fix_instance(kind, N, 1, 1))
+
+
 def test_struct_layouts_match_reference():
     # SURVEY.md section 8(a) A1/A2/A15: 32 / 32 / 32 / 48 bytes on LP64
     assert C.sizeof(cd.arm_cfft_instance_f32) == 32
@@ -45,7 +70,8 @@ def test_struct_layouts_match_reference():
     if ref() is not None:
         L = ref().lib
         for name, t in (("cfft_instance_f32", cd.arm_cfft_instance_f32), ("cfft_instance_q31", cd.arm_cfft_instance_q31),
-                        ("cfft_instance_q15", cd.arm_cfft_instance_q15), ("rfft_fast_instance_f32", cd.arm_rfft_fast_instance_f32)):
+                        ("cfft_instance_q15", cd.arm_cfft_instance_q15), ("rfft_fast_instance_f32", cd.arm_rfft_fast_instance_f32),
+                        ("rfft_instance_q31", cd.arm_rfft_instance_q31), ("rfft_instance_q15", cd.arm_rfft_instance_q15)):
             fn = getattr(L, f"ref_sizeof_{name}")
             fn.restype = C.c_uint32
             assert fn() == C.sizeof(t)
@@ -85,9 +111,14 @@ def test_shared_objects_export_every_declared_symbol():
         assert hasattr(cu, name), name
     fr = cd.lib()
     names = _declared_functions(os.path.join(ROOT, "include", "dsp", "transform_functions.h"))
-    assert len(names) == 59      # 3x(9 per-length inits + init + exec) + rfft (8+1+1) + 4 batch + last_status + mfcc (8+1+1+1)
+    # 3x(9 per-length inits + init + exec) + rfft (8+1+1) + 4 batch + last_status + mfcc (8+1+1+1)
+    # + rfft_q31/q15 (init, exec, batch each; their per-length inits are declared through a macro)
+    assert len(names) == 65
     for name in names:
         assert hasattr(fr, name), name
+    for N in RFIX_LENGTHS:
+        for kind in ("q31", "q15"):
+            assert hasattr(fr, f"arm_rfft_init_{N}_{kind}")
     for N in LENGTHS:
         for kind in ("f32", "q31", "q15"):
             cd.preset(kind, N)

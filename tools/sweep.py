@@ -52,7 +52,7 @@ def main():
     rows = []
     for op in args.ops.split(","):
         for N in [int(v) for v in args.lens.split(",")]:
-            if op.startswith("rfft") and N < 32:
+            if op.startswith("rfft_") and N < 32:
                 continue
             if op == "mfcc" and N not in (256, 512, 1024):
                 continue
@@ -84,6 +84,22 @@ def main():
                 alg = B * (4 * N + 4 * 13)
                 samples = B * N
                 info = dict(threads_per_cta=0, frames_per_cta=0, smem_bytes=0, regs_per_thread=0, ctas_per_sm=0)
+            elif op.startswith("rfftq"):
+                # rfftq31_fwd / rfftq31_inv / rfftq15_fwd / rfftq15_inv; N = real length; algorithmic bytes:
+                # forward N in + 2N out scalars, inverse N+2 in (bins 0..N/2) + N out
+                kind, inv = ("q31" if "31" in op else "q15"), int(op.endswith("inv"))
+                if N < 32:
+                    continue
+                esz = 4 if kind == "q31" else 2
+                B = nbytes // (2 * N * esz)
+                cd.ensure_rfft_fix_plans(kind, N)
+                tdt = torch.int32 if kind == "q31" else torch.int16
+                a = torch.randint(-2**13, 2**13, (B, 2 * N if inv else N), device=dev, dtype=tdt)
+                b = torch.empty(B, N if inv else 2 * N, device=dev, dtype=tdt)
+                fn = lambda: cd.rfft_fix_device(kind, N, a.data_ptr(), b.data_ptr(), B, inv, st)
+                alg = B * esz * ((N + 2 + N) if inv else 3 * N)
+                samples = B * N
+                info = cd.kernel_info((5 if kind == "q31" else 7) + inv, N)
             else:
                 B = nbytes // (4 * N)
                 cd.ensure_rfft_plans(N)
