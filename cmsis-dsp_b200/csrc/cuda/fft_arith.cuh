@@ -233,7 +233,14 @@ FFT_HD int32_t wsub(int32_t a, int32_t b) { return (int32_t)((uint32_t)a - (uint
 FFT_HD int32_t wshl1(int32_t a) { return (int32_t)((uint32_t)a << 1); }
 FFT_HD int32_t hi32(int32_t a, int32_t b)
 {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && !defined(FFT_HI32_MULHI)
+    /* the 64-bit product on the FMA pipe (IMAD.WIDE), upper register taken as is: __mulhi compiles to
+     * IMAD.HI, which sm_100 executes on the quarter-rate XU pipe -- at 12 of them per point it, not HBM,
+     * bounded the q31 kernels (profiles/r1_e: XU pipe 55 % busy at N = 4096) */
+    int32_t hi;
+    asm("{\n\t.reg .b64 t;\n\t.reg .b32 lo;\n\tmul.wide.s32 t, %1, %2;\n\tmov.b64 {lo, %0}, t;\n\t}" : "=r"(hi) : "r"(a), "r"(b));
+    return hi;
+#elif defined(__CUDA_ARCH__)
     return __mulhi(a, b);
 #else
     return (int32_t)(((int64_t)a * b) >> 32);
@@ -393,6 +400,9 @@ FFT_HD int32_t sat_sub16(int32_t a, int32_t b)
 }
 FFT_HD int32_t q15w(int32_t v) { return (int32_t)(int16_t)(uint16_t)(uint32_t)v; }   /* wrap to int16, keep in a register */
 
+/* Measured and rejected: twiddles pre-shifted by 16 and the sum taken as the upper word of two wide
+ * products (no shift on the ALU pipe, which bounds this kernel).  ptxas ends such a pair with IMAD.HI, an
+ * XU-pipe instruction on sm_100, and the kernels lost 5-10 % (profiles/r1_e_notes.md). */
 template <bool INV> FFT_HD ci32 rot_q15(int32_t x, int32_t y, ci32 w)
 {
     if (!INV) return {(w.x * x + w.y * y) >> 16, (w.x * y - w.y * x) >> 16};
