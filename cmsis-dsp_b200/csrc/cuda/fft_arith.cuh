@@ -231,21 +231,36 @@ struct ArithF32 {
 FFT_HD int32_t wadd(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
 FFT_HD int32_t wsub(int32_t a, int32_t b) { return (int32_t)((uint32_t)a - (uint32_t)b); }
 FFT_HD int32_t wshl1(int32_t a) { return (int32_t)((uint32_t)a << 1); }
-FFT_HD int32_t hi32(int32_t a, int32_t b)
+/* truncating high product hi32(a*b), two spellings for the two pipes that can produce it on sm_100:
+ *   hi32_xu   __mulhi -> IMAD.HI, executed by the XU pipe (one warp instruction per 8 cycles per scheduler)
+ *   hi32_fma  64-bit product -> IMAD.WIDE on the FMA pipe, upper register taken as is
+ * A q31 butterfly needs 12 of them per 4 points; all on the XU pipe that pipe bounds the kernel (55 % busy at
+ * 60 % of the HBM peak, profiles/r1_e_ncu_q31.txt).  Measured (profiles/r1_e_notes.md): all on the FMA pipe is
+ * the fastest for every length but 32 (+4..12 points of HBM peak at N = 64, 256, 2048, 4096); half and half
+ * performs like all-XU.  N = 32 keeps IMAD.HI: the wide products cost it 15 registers and one resident CTA. */
+FFT_HD int32_t hi32_xu(int32_t a, int32_t b)
 {
-#if defined(__CUDA_ARCH__) && !defined(FFT_HI32_MULHI)
-    /* the 64-bit product on the FMA pipe (IMAD.WIDE), upper register taken as is: __mulhi compiles to
-     * IMAD.HI, which sm_100 executes on the quarter-rate XU pipe -- at 12 of them per point it, not HBM,
-     * bounded the q31 kernels (profiles/r1_e: XU pipe 55 % busy at N = 4096) */
-    int32_t hi;
-    asm("{\n\t.reg .b64 t;\n\t.reg .b32 lo;\n\tmul.wide.s32 t, %1, %2;\n\tmov.b64 {lo, %0}, t;\n\t}" : "=r"(hi) : "r"(a), "r"(b));
-    return hi;
-#elif defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__)
     return __mulhi(a, b);
 #else
     return (int32_t)(((int64_t)a * b) >> 32);
 #endif
 }
+FFT_HD int32_t hi32_fma(int32_t a, int32_t b)
+{
+#if defined(__CUDA_ARCH__)
+    int32_t hi;
+    asm("{\n\t.reg .b64 t;\n\t.reg .b32 lo;\n\tmul.wide.s32 t, %1, %2;\n\tmov.b64 {lo, %0}, t;\n\t}" : "=r"(hi) : "r"(a), "r"(b));
+    return hi;
+#else
+    return (int32_t)(((int64_t)a * b) >> 32);
+#endif
+}
+#if defined(FFT_HI32_XU)
+FFT_HD int32_t hi32(int32_t a, int32_t b) { return hi32_xu(a, b); }
+#else
+FFT_HD int32_t hi32(int32_t a, int32_t b) { return hi32_fma(a, b); }
+#endif
 /* SMMULR / SMMLAR / SMMLSR (none.h:185-194) */
 FFT_HD int32_t rhi32(int32_t x, int32_t y) { return (int32_t)(((int64_t)x * y + 0x80000000LL) >> 32); }
 FFT_HD int32_t rhi32_acc(int32_t a, int32_t x, int32_t y)

@@ -10,6 +10,9 @@
 #include <cuda_runtime.h>
 #include <stdlib.h>
 
+#if defined(KU_N) && KU_N == 32
+#define FFT_HI32_XU 1        /* q31 high products as IMAD.HI for this length (fft_arith.cuh: hi32) */
+#endif
 #include "../../../include/cmsisdsp_cuda.h"
 #include "fft_plans.cuh"
 #include "kernel_entry.h"
