@@ -172,6 +172,16 @@ def run_cuda(args, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # keep this rank's host thread (and so its pinned buffers, first touch) on the NUMA node of its GPU: with
+    # several ranks streaming host buffers at once, remote-node memory halves the end-to-end rate
+    numa_bound = False
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        numa_bound = True
+    except Exception:
+        pass
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -279,6 +289,7 @@ def run_cuda(args, rank, world, local_rank):
         e2e = {"value": world * Be * N_REAL / float(dt.item()) / 1e6, "unit": UNIT,
                "h2d_bytes_per_step": 2 * Be * N_REAL * 4, "d2h_bytes_per_step": 2 * Be * N_REAL * 4,
                "frames": Be, "api": "arm_rfft_fast_batch_f32 (host pointers, pinned), forward then inverse",
+               "host_thread_bound_to_gpu_numa_node": numa_bound,
                "roundtrip_relrms": ert}
 
     cpu_baseline = None

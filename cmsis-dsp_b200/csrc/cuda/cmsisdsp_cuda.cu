@@ -47,14 +47,14 @@ void shim_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 #define DECL(op, n) extern const KernelEntry ku_entry_##op##_##n;
 namespace b200fft {
 FOR_ALL_N(DECL, 0) FOR_ALL_N(DECL, 1) FOR_ALL_N(DECL, 2) FOR_RFFT_NC(DECL, 3) FOR_RFFT_NC(DECL, 4)
-FOR_ALL_N(DECL, 5) FOR_ALL_N(DECL, 6) FOR_ALL_N(DECL, 7) FOR_ALL_N(DECL, 8)
+FOR_ALL_N(DECL, 5) FOR_ALL_N(DECL, 6) FOR_ALL_N(DECL, 7) FOR_ALL_N(DECL, 8) FOR_ALL_N(DECL, 9)
 }
 #undef DECL
 #define REF(op, n) &ku_entry_##op##_##n,
 /* [op][index of the COMPLEX length 16..4096]; the rfft ops have no 4096-point complex plan */
 static const KernelEntry *const kEntries[OP_COUNT][9] = {
     {FOR_ALL_N(REF, 0)}, {FOR_ALL_N(REF, 1)}, {FOR_ALL_N(REF, 2)}, {FOR_RFFT_NC(REF, 3) nullptr}, {FOR_RFFT_NC(REF, 4) nullptr},
-    {FOR_ALL_N(REF, 5)}, {FOR_ALL_N(REF, 6)}, {FOR_ALL_N(REF, 7)}, {FOR_ALL_N(REF, 8)}};
+    {FOR_ALL_N(REF, 5)}, {FOR_ALL_N(REF, 6)}, {FOR_ALL_N(REF, 7)}, {FOR_ALL_N(REF, 8)}, {FOR_ALL_N(REF, 9)}};
 #undef REF
 
 static const uint32_t kLens[9] = {16, 32, 64, 128, 256, 512, 1024, 2048, 4096};
@@ -323,6 +323,25 @@ extern "C" int cmsisdsp_cuda_rfft_fast_f32(const void *d_p, void *d_out, uint32_
                       (cudaStream_t)stream);
 }
 
+/* arm_cfft_f32 + spectrum epilogue: mode 0 magnitudes, 1 squared magnitudes (d_out: fftLen floats per frame),
+ * 2 peak (d_out: one value, d_aux: one uint32 index per frame) */
+static int cfft_spectrum(const void *d_src, void *d_out, void *d_aux, uint32_t fftLen, uint64_t nFrames, uint8_t ifftFlag, int mode, void *stream)
+{
+    if ((!d_src || !d_out || (mode == 2 && !d_aux)) && nFrames) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "null data pointer");
+    if (d_src == d_out && nFrames) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "spectrum epilogue: source and destination must not alias");
+    DevPlan pl;
+    int rc = get_plan(CMSISDSP_CUDA_F32, fftLen, &pl);
+    if (rc) return rc;
+    const KernelEntry *ke = kEntries[OP_CFFT_MAG_F32][len_index(fftLen)];
+    return ke->launch(d_src, d_out, nFrames, ifftFlag == 1, pl.tw, d_aux, mode, choose_flavour(ke), (cudaStream_t)stream);
+}
+extern "C" int cmsisdsp_cuda_cfft_mag_f32(const void *d_src, void *d_mag, uint32_t fftLen, uint64_t nFrames, uint8_t ifftFlag,
+                                          uint8_t squared, void *stream)
+{ return cfft_spectrum(d_src, d_mag, nullptr, fftLen, nFrames, ifftFlag, squared ? 1 : 0, stream); }
+extern "C" int cmsisdsp_cuda_cfft_peak_f32(const void *d_src, void *d_val, void *d_idx, uint32_t fftLen, uint64_t nFrames,
+                                           uint8_t ifftFlag, void *stream)
+{ return cfft_spectrum(d_src, d_val, d_idx, fftLen, nFrames, ifftFlag, 2, stream); }
+
 static int rfft_fix(int type, const void *d_src, void *d_dst, uint32_t fftLenReal, uint64_t nFrames, uint8_t ifftFlagR, void *stream)
 {
     if ((!d_src || !d_dst) && nFrames) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "null data pointer");
@@ -352,7 +371,7 @@ extern "C" int cmsisdsp_cuda_rfft_q15(const void *d_src, void *d_dst, uint32_t f
 
 extern "C" int cmsisdsp_cuda_kernel_info(int op, uint32_t fftLen, int *threads, int *frames, int *smem, int *regs, int *ctasPerSm)
 {
-    const int li = len_index((op >= 3) ? fftLen / 2 : fftLen);       /* ops 3..8 take the real length */
+    const int li = len_index((op >= 3 && op <= 8) ? fftLen / 2 : fftLen);       /* ops 3..8 take the real length */
     if (op < 0 || op >= OP_COUNT || li < 0 || !kEntries[op][li]) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "kernel_info: unsupported (op, fftLen)");
     KernelFacts f;
     int rc = kEntries[op][li]->facts(&f, choose_flavour(kEntries[op][li]));

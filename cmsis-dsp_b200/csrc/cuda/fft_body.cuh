@@ -13,6 +13,7 @@
  * the CPU emulator (tests/emu) runs each phase for every thread in turn.
  */
 #pragma once
+#include <math.h>
 #include "fft_frame.cuh"
 
 namespace b200fft {
@@ -215,6 +216,136 @@ template <class PL, bool INV, bool PERM = false, bool STAGED = false, bool RIFFT
                 Eng::template compute<2, INV>(r, a.tw, i);
                 if constexpr (!HOLD) gstore(r, a, i);
             }
+        }
+    }
+};
+
+/* ------------------------------------------------------------------ CFFT with a fused spectrum epilogue (f32)
+ *
+ * arm_cfft_f32 followed by arm_cmplx_mag_f32 / arm_cmplx_mag_squared_f32 (ComplexMathFunctions/arm_cmplx_mag_f32.c:
+ * 252-264, arm_cmplx_mag_squared_f32.c) and, for SPEC_PEAK, arm_max_f32 (StatisticsFunctions/arm_max_f32.c: the first
+ * maximum wins) -- the pipeline of Examples/ARM/arm_fft_bin_example/arm_fft_bin_example_f32.c:141-149.  The spectrum
+ * never reaches HBM: a frame costs 8N bytes in and 4N bytes (magnitudes) or 8 bytes (peak value and index) out. */
+enum SpectrumMode { SPEC_MAG = 0, SPEC_MAG_SQUARED = 1, SPEC_PEAK = 2 };
+
+#if defined(__CUDA_ARCH__)
+FFT_HD void st_stream(float *p, float v) { __stcs(p, v); }
+FFT_HD float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+FFT_HD float add_rn(float a, float b) { return __fadd_rn(a, b); }
+#else
+FFT_HD void st_stream(float *p, float v) { *p = v; }
+FFT_HD float mul_rn(float a, float b) { return a * b; }
+FFT_HD float add_rn(float a, float b) { return a + b; }
+#endif
+
+template <class PL, bool INV, int MODE, bool STAGED = false> struct CfftMagBody : CfftBody<PL, INV, false, STAGED> {
+    typedef CfftBody<PL, INV, false, STAGED> C;
+    typedef typename C::Eng Eng;
+    typedef typename C::Regs Regs;
+    typedef cf32 elem;
+    typedef cf32 xelem;
+    typedef cf32 telem;
+    static constexpr int NP = PL::NP, E = PL::E, N = PL::N, T = PL::T;
+    static_assert(IsF32<typename PL::Arith::elem>::value, "spectrum epilogues are f32");
+    /* SPEC_PEAK with a frame that spans several warps: the warps' partial peaks meet in the exchange buffer */
+    static constexpr bool kCross = (MODE == SPEC_PEAK) && (T > 32);
+    static constexpr int kCfftPhases = PhaseCount<NP>::value;
+    static constexpr int kPhases = kCfftPhases + (kCross ? 2 : 0);
+
+    struct Args : C::Args {
+        float *mag;              /* SPEC_MAG / SPEC_MAG_SQUARED: N floats per frame */
+        float *peakVal;          /* SPEC_PEAK: one value and one index per frame */
+        uint32_t *peakIdx;
+    };
+    static FFT_HD Args for_frame(Args a, uint64_t frame)
+    {
+        a.in += frame * (uint64_t)N;
+        if (MODE == SPEC_PEAK) {
+            a.peakVal += frame;
+            a.peakIdx += frame;
+        } else {
+            a.mag += frame * (uint64_t)N;
+        }
+        return a;
+    }
+    static FFT_HD void set_scratch(Args &, xelem *) {}
+
+    static FFT_HD float magnitude(cf32 w, float scale)
+    {
+        if (INV) w = cf32{w.x * scale, -w.y * scale};                       /* cfft_f32.c:1285-1297 */
+        const float s = add_rn(mul_rn(w.x, w.x), mul_rn(w.y, w.y));         /* (real * real) + (imag * imag), no contraction */
+        if (MODE == SPEC_MAG_SQUARED) return s;
+#if defined(__CUDA_ARCH__)
+        return __fsqrt_rn(s);
+#else
+        return sqrtf(s);
+#endif
+    }
+    static FFT_HD bool better(float v1, int k1, float v2, int k2) { return v1 > v2 || (v1 == v2 && k1 < k2); }
+
+    /* the registers hold the results of the last pass */
+    static FFT_HD void epilogue(Regs &r, const Args &a, int i)
+    {
+        typedef typename PassOf<PL, NP - 1>::type PS;
+        float bv = 0.0f;
+        int bk = 0x7fffffff;
+#pragma unroll
+        for (int b = 0; b < E / PS::R; b++)
+#pragma unroll
+            for (int e = 0; e < PS::R; e++) {
+                const int k = Eng::template out_index<NP - 1>(i, b, e);
+                const float m = magnitude(r.v[b * PS::R + e], a.scale);
+                if (MODE == SPEC_PEAK) {
+                    if ((b == 0 && e == 0) || better(m, k, bv, bk)) { bv = m; bk = k; }
+                } else {
+                    st_stream(a.mag + k, m);
+                }
+            }
+        if (MODE == SPEC_PEAK) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+            for (int o = (T < 32 ? T : 32) / 2; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+                if (better(ov, ok, bv, bk)) { bv = ov; bk = ok; }
+            }
+            if (kCross) {
+                r.v[0] = cf32{bv, __int_as_float(bk)};                      /* the warp's partial, for the two extra phases */
+            } else if (i == 0) {
+                *a.peakVal = bv;
+                *a.peakIdx = (uint32_t)bk;
+            }
+#else
+            (void)bv; (void)bk;                                             /* the peak reduction uses warp shuffles: device only */
+#endif
+        }
+    }
+    static FFT_HD void last_out(Regs &r, const Args &a, int i)
+    {
+        Eng::template compute<1, INV>(r, a.tw, i);
+        epilogue(r, a, i);
+    }
+    static FFT_HD void last_out_pk(Regs &r, const Args &a, int i, const telem *) { last_out(r, a, i); }
+
+    template <int PH> static FFT_HD void phase(Regs &r, const Args &a, xelem *sm, int i)
+    {
+        if constexpr (PH < kCfftPhases) {
+            C::template phase<PH, true>(r, a, sm, i);
+            if constexpr (PH == kCfftPhases - 1) epilogue(r, a, i);
+        } else if constexpr (PH == kCfftPhases) {
+            if ((i & 31) == 0) sm[i >> 5] = r.v[0];
+        } else {
+#if defined(__CUDA_ARCH__)
+            if (i == 0) {
+                float bv = sm[0].x;
+                int bk = __float_as_int(sm[0].y);
+#pragma unroll
+                for (int w = 1; w < T / 32; w++)
+                    if (better(sm[w].x, __float_as_int(sm[w].y), bv, bk)) { bv = sm[w].x; bk = __float_as_int(sm[w].y); }
+                *a.peakVal = bv;
+                *a.peakIdx = (uint32_t)bk;
+            }
+#endif
         }
     }
 };

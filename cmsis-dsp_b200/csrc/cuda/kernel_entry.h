@@ -11,7 +11,8 @@
 namespace b200fft {
 
 enum KernelOp { OP_CFFT_F32 = 0, OP_CFFT_Q31 = 1, OP_CFFT_Q15 = 2, OP_RFFT_FWD = 3, OP_RFFT_INV = 4,
-                OP_RFFT_Q31_FWD = 5, OP_RFFT_Q31_INV = 6, OP_RFFT_Q15_FWD = 7, OP_RFFT_Q15_INV = 8, OP_COUNT = 9 };
+                OP_RFFT_Q31_FWD = 5, OP_RFFT_Q31_INV = 6, OP_RFFT_Q15_FWD = 7, OP_RFFT_Q15_INV = 8, OP_CFFT_MAG_F32 = 9,
+                OP_COUNT = 10 };
 
 struct KernelFacts { int threads, frames, smem, regs, ctasPerSm; };
 
@@ -25,7 +26,9 @@ struct KernelEntry {
      *       shl1 = final << 1 (fixed point, N = 2*4^m)
      * rfft: in -> out, aux = twiddleCoef_rfft table (device); direction is fixed by the op
      * rfft q31/q15: in -> out, tw = twiddles of the cfft plan of the same type and complex length,
-     *       aux = split coefficients (ci32x4 per bin), shl1 as for cfft */
+     *       aux = split coefficients (ci32x4 per bin), shl1 as for cfft
+     * cfft + spectrum epilogue (f32): in -> out = magnitudes, or out = peak values and aux = peak indices; tw = the
+     *       cfft plan's twiddles; the shl1 slot carries the SpectrumMode (0 mag, 1 mag squared, 2 peak) */
     int (*launch)(const void *in, void *out, uint64_t nFrames, int inv, const void *tw, const void *aux, int shl1,
                   int flavour, cudaStream_t st);
     /* number of elements of the pass-ordered twiddle table (+1 pad); fills hostOut when non-null */

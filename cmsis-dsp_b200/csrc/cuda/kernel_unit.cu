@@ -19,7 +19,7 @@
 #include "bulk_copy.cuh"
 
 #if !defined(KU_OP) || !defined(KU_N)
-#error "compile with -DKU_OP=<0..8> -DKU_N=<length>"
+#error "compile with -DKU_OP=<0..9> -DKU_N=<length>"
 #endif
 
 using namespace b200fft;
@@ -574,6 +574,51 @@ static int ku_facts(KernelFacts *f, int flavour)
     }
 #endif
     return facts_of<RfftInvBody<PL>, PL>(f);
+}
+typedef PL TWPLAN;
+
+#elif KU_OP == 9   /* arm_cfft_f32 with a fused spectrum epilogue: out = magnitudes (shl1 = SpectrumMode 0 / 1) or
+                    * out = peak values, aux = peak indices (shl1 = SPEC_PEAK) */
+
+typedef PlanCfftF32<KU_N>::type PL;
+typedef PipeOf<PL> PIPEOF;
+struct PIPE { static constexpr bool kHas = PIPEOF::kPipe, kPrefer = PIPEOF::kPipe; };
+
+template <bool INV, int MODE>
+static int mag_go(const void *in, void *out, uint64_t nFrames, const void *tw, const void *aux, int flavour, cudaStream_t st)
+{
+    if constexpr (PIPEOF::kPipe) {
+        typedef CfftMagBody<PIPEOF::type, INV, MODE, true> BODY;
+        if constexpr (!BODY::kCross) {          /* a frame wider than a warp meets through the exchange buffer: direct kernel */
+            if (flavour == KF_PIPE && aligned16(in)) {
+                typename BODY::Args a{};
+                a.in = (const cf32 *)in; a.tw = (const cf32 *)tw; a.scale = 1.0f / (float)PL::N;
+                a.mag = (float *)out; a.peakVal = (float *)out; a.peakIdx = (uint32_t *)aux;
+                return launch_pipe<BODY, PIPEOF::type>(a, nFrames, st);
+            }
+        }
+    }
+    typedef CfftMagBody<PL, INV, MODE> BODY;
+    typename BODY::Args a{};
+    a.in = (const cf32 *)in; a.tw = (const cf32 *)tw; a.scale = 1.0f / (float)PL::N;
+    a.mag = (float *)out; a.peakVal = (float *)out; a.peakIdx = (uint32_t *)aux;
+    return launch<BODY, PL>(a, nFrames, st);
+}
+static int ku_launch(const void *in, void *out, uint64_t nFrames, int inv, const void *tw, const void *aux, int mode, int flavour, cudaStream_t st)
+{
+    switch (mode) {
+    case SPEC_MAG: return inv ? mag_go<true, SPEC_MAG>(in, out, nFrames, tw, aux, flavour, st) : mag_go<false, SPEC_MAG>(in, out, nFrames, tw, aux, flavour, st);
+    case SPEC_MAG_SQUARED: return inv ? mag_go<true, SPEC_MAG_SQUARED>(in, out, nFrames, tw, aux, flavour, st) : mag_go<false, SPEC_MAG_SQUARED>(in, out, nFrames, tw, aux, flavour, st);
+    case SPEC_PEAK: return inv ? mag_go<true, SPEC_PEAK>(in, out, nFrames, tw, aux, flavour, st) : mag_go<false, SPEC_PEAK>(in, out, nFrames, tw, aux, flavour, st);
+    }
+    return shim_fail(CMSISDSP_CUDA_ERR_ARGUMENT, "spectrum mode must be 0 (mag), 1 (mag squared) or 2 (peak)", cudaSuccess);
+}
+static int ku_facts(KernelFacts *f, int flavour)
+{
+    if constexpr (PIPEOF::kPipe) {
+        if (flavour == KF_PIPE) return facts_of_pipe<CfftMagBody<PIPEOF::type, false, SPEC_MAG, true>, PIPEOF::type>(f);
+    }
+    return facts_of<CfftMagBody<PL, false, SPEC_MAG>, PL>(f);
 }
 typedef PL TWPLAN;
 

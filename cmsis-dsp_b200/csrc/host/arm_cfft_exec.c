@@ -282,3 +282,61 @@ arm_status arm_rfft_batch_q15(const arm_rfft_instance_q15 *S, const q15_t *pSrc,
 }
 void arm_rfft_q31(const arm_rfft_instance_q31 *S, q31_t *pSrc, q31_t *pDst) { g_last = rfix_q31(S, pSrc, pDst, 1, 1); }
 void arm_rfft_q15(const arm_rfft_instance_q15 *S, q15_t *pSrc, q15_t *pDst) { g_last = rfix_q15(S, pSrc, pDst, 1, 1); }
+
+/* ---- arm_cfft_f32 fused with arm_cmplx_mag[_squared]_f32 (mode 0 / 1) or with arm_cmplx_mag_f32 + arm_max_f32 (mode 2) ---- */
+static arm_status spectrum_batch(const arm_cfft_instance_f32 *S, const float32_t *pSrc, void *pOut, uint32_t *pIndex,
+                                 uint64_t nFrames, uint8_t ifftFlag, int mode)
+{
+    if (!S || !pSrc || !pOut || (mode == 2 && !pIndex) || !S->pTwiddle || (const void *)pSrc == pOut) return ARM_MATH_ARGUMENT_ERROR;
+    const uint32_t N = S->fftLen;
+    if (!valid_len(N)) return ARM_MATH_ARGUMENT_ERROR;
+    if (nFrames == 0) return ARM_MATH_SUCCESS;
+    if (ctx_ready()) return ARM_MATH_ARGUMENT_ERROR;
+    if (ensure_plan(CMSISDSP_CUDA_F32, N, S->pTwiddle, S->pBitRevTable, S->bitRevLength)) return ARM_MATH_ARGUMENT_ERROR;
+    const size_t inBytes = (size_t)2 * N * sizeof(float32_t), outBytes = (mode == 2) ? sizeof(float32_t) : (size_t)N * sizeof(float32_t);
+    const int inDev = cmsisdsp_cuda_is_device_pointer(pSrc), outDev = cmsisdsp_cuda_is_device_pointer(pOut);
+    const int idxDev = (mode == 2) ? cmsisdsp_cuda_is_device_pointer(pIndex) : outDev;
+    if (inDev < 0 || outDev < 0 || inDev != outDev || idxDev != outDev) return ARM_MATH_ARGUMENT_ERROR;
+    if (inDev) {
+        int rc = (mode == 2) ? cmsisdsp_cuda_cfft_peak_f32(pSrc, pOut, pIndex, N, nFrames, ifftFlag, g_ctx.stream[0])
+                             : cmsisdsp_cuda_cfft_mag_f32(pSrc, pOut, N, nFrames, ifftFlag, (uint8_t)mode, g_ctx.stream[0]);
+        if (rc) return ARM_MATH_ARGUMENT_ERROR;
+        return cmsisdsp_cuda_stream_synchronize(g_ctx.stream[0]) ? ARM_MATH_ARGUMENT_ERROR : ARM_MATH_SUCCESS;
+    }
+    uint64_t perChunk = CHUNK_BYTES / inBytes;
+    if (perChunk == 0) perChunk = 1;
+    int rc = 0, s = 0;
+    for (uint64_t f = 0; f < nFrames && !rc; f += perChunk, s = (s + 1) % NSTREAM) {
+        const uint64_t n = (nFrames - f < perChunk) ? nFrames - f : perChunk;
+        void *din, *dout;
+        /* staging [1] holds the magnitudes, or the peak values followed by the peak indices */
+        if ((rc = staging(s, 0, (size_t)perChunk * inBytes, &din))) break;
+        if ((rc = staging(s, 1, (size_t)perChunk * (mode == 2 ? 8 : outBytes), &dout))) break;
+        if ((rc = cmsisdsp_cuda_memcpy_h2d(din, (const char *)pSrc + f * inBytes, (size_t)n * inBytes, g_ctx.stream[s]))) break;
+        if (mode == 2) {
+            void *didx = (char *)dout + (size_t)perChunk * 4;
+            if ((rc = cmsisdsp_cuda_cfft_peak_f32(din, dout, didx, N, n, ifftFlag, g_ctx.stream[s]))) break;
+            if ((rc = cmsisdsp_cuda_memcpy_d2h((float32_t *)pOut + f, dout, (size_t)n * 4, g_ctx.stream[s]))) break;
+            rc = cmsisdsp_cuda_memcpy_d2h(pIndex + f, didx, (size_t)n * 4, g_ctx.stream[s]);
+        } else {
+            if ((rc = cmsisdsp_cuda_cfft_mag_f32(din, dout, N, n, ifftFlag, (uint8_t)mode, g_ctx.stream[s]))) break;
+            rc = cmsisdsp_cuda_memcpy_d2h((char *)pOut + f * outBytes, dout, (size_t)n * outBytes, g_ctx.stream[s]);
+        }
+    }
+    for (int i = 0; i < NSTREAM; i++)
+        if (cmsisdsp_cuda_stream_synchronize(g_ctx.stream[i])) rc = rc ? rc : -1;
+    return rc ? ARM_MATH_ARGUMENT_ERROR : ARM_MATH_SUCCESS;
+}
+arm_status arm_cfft_mag_batch_f32(const arm_cfft_instance_f32 *S, const float32_t *pSrc, float32_t *pMag, uint32_t nFrames, uint8_t ifftFlag)
+{
+    return spectrum_batch(S, pSrc, pMag, 0, nFrames, ifftFlag, 0);
+}
+arm_status arm_cfft_mag_squared_batch_f32(const arm_cfft_instance_f32 *S, const float32_t *pSrc, float32_t *pMag, uint32_t nFrames, uint8_t ifftFlag)
+{
+    return spectrum_batch(S, pSrc, pMag, 0, nFrames, ifftFlag, 1);
+}
+arm_status arm_cfft_peak_batch_f32(const arm_cfft_instance_f32 *S, const float32_t *pSrc, float32_t *pResult, uint32_t *pIndex,
+                                   uint32_t nFrames, uint8_t ifftFlag)
+{
+    return spectrum_batch(S, pSrc, pResult, pIndex, nFrames, ifftFlag, 2);
+}

@@ -99,6 +99,7 @@ def cuda():
         "cmsisdsp_cuda_rfft_fast_f32": ([vp, vp, u32, u64, u8, vp], i),
         "cmsisdsp_cuda_rfft_fix_plan_upload": ([i, u32, vp, vp, u32], i), "cmsisdsp_cuda_rfft_fix_plan_ready": ([i, u32], i),
         "cmsisdsp_cuda_rfft_q31": ([vp, vp, u32, u64, u8, vp], i), "cmsisdsp_cuda_rfft_q15": ([vp, vp, u32, u64, u8, vp], i),
+        "cmsisdsp_cuda_cfft_mag_f32": ([vp, vp, u32, u64, u8, u8, vp], i), "cmsisdsp_cuda_cfft_peak_f32": ([vp, vp, vp, u32, u64, u8, vp], i),
         "cmsisdsp_cuda_last_error": ([], C.c_char_p), "cmsisdsp_cuda_launch_count": ([], u64),
         "cmsisdsp_cuda_set_kernel_flavour": ([i], i),
         "cmsisdsp_cuda_mfcc_plan_create": ([u32, u32, u32, vp, vp, vp, vp, vp, C.POINTER(vp)], i),
@@ -138,6 +139,11 @@ def lib():
     L.arm_rfft_fast_batch_f32.argtypes = [C.POINTER(arm_rfft_fast_instance_f32), C.c_void_p, C.c_void_p, u32, u8]
     L.arm_rfft_fast_batch_f32.restype = i
     L.arm_cuda_last_status.argtypes, L.arm_cuda_last_status.restype = [], i
+    for name in ("arm_cfft_mag_batch_f32", "arm_cfft_mag_squared_batch_f32"):
+        f = getattr(L, name)
+        f.argtypes, f.restype = [C.POINTER(arm_cfft_instance_f32), C.c_void_p, C.c_void_p, u32, u8], i
+    L.arm_cfft_peak_batch_f32.argtypes = [C.POINTER(arm_cfft_instance_f32), C.c_void_p, C.c_void_p, C.c_void_p, u32, u8]
+    L.arm_cfft_peak_batch_f32.restype = i
     for k, inst in RFIX_INSTANCE.items():
         f = getattr(L, f"arm_rfft_init_{k}")
         f.argtypes, f.restype = [C.POINTER(inst), u32, u32, u32], i
@@ -221,6 +227,33 @@ def rfft_batch(N, x, ifft=0):
     if st != ARM_MATH_SUCCESS:
         raise RuntimeError(f"arm_rfft_fast_batch_f32 -> {st}: {last_error()}")
     return out
+
+
+def cfft_mag_batch(N, x, ifft=0, squared=False):
+    """arm_cfft_mag[_squared]_batch_f32 on a host array [..., 2N]; returns [frames, N] magnitudes."""
+    src = np.ascontiguousarray(x, dtype=np.float32)
+    assert src.size % (2 * N) == 0
+    frames = src.size // (2 * N)
+    out = np.empty((frames, N), dtype=np.float32)
+    S = cfft_instance("f32", N)
+    fn = lib().arm_cfft_mag_squared_batch_f32 if squared else lib().arm_cfft_mag_batch_f32
+    st = fn(C.byref(S), src.ctypes.data, out.ctypes.data, frames, int(ifft))
+    if st != ARM_MATH_SUCCESS:
+        raise RuntimeError(f"arm_cfft_mag_batch_f32 -> {st}: {last_error()}")
+    return out
+
+
+def cfft_peak_batch(N, x, ifft=0):
+    """arm_cfft_peak_batch_f32 on a host array [..., 2N]; returns (values [frames], indices [frames])."""
+    src = np.ascontiguousarray(x, dtype=np.float32)
+    assert src.size % (2 * N) == 0
+    frames = src.size // (2 * N)
+    val, idx = np.empty(frames, dtype=np.float32), np.empty(frames, dtype=np.uint32)
+    S = cfft_instance("f32", N)
+    st = lib().arm_cfft_peak_batch_f32(C.byref(S), src.ctypes.data, val.ctypes.data, idx.ctypes.data, frames, int(ifft))
+    if st != ARM_MATH_SUCCESS:
+        raise RuntimeError(f"arm_cfft_peak_batch_f32 -> {st}: {last_error()}")
+    return val, idx
 
 
 def rfft_fix_instance(kind, N, ifft=0, bitrev=1):

@@ -85,6 +85,16 @@ int  cmsisdsp_cuda_cfft_q15(void *d_p, uint32_t fftLen, uint64_t nFrames,
 int  cmsisdsp_cuda_rfft_fast_f32(const void *d_p, void *d_out, uint32_t fftLenReal, uint64_t nFrames,
                                  uint8_t ifftFlag, void *stream);
 
+/* ---- arm_cfft_f32 with a fused spectrum epilogue (the spectrum itself is never written) ----
+ * = arm_cfft_f32(.., ifftFlag, 1) + arm_cmplx_mag_f32 / arm_cmplx_mag_squared_f32 (ComplexMathFunctions/
+ * arm_cmplx_mag_f32.c:252-264) [+ arm_max_f32, the first maximum wins]: Examples/ARM/arm_fft_bin_example/
+ * arm_fft_bin_example_f32.c:141-149.  d_src: nFrames*2*fftLen floats, left untouched; d_mag: nFrames*fftLen floats;
+ * d_val / d_idx: nFrames floats / uint32.  Needs the cfft plan of (f32, fftLen). */
+int  cmsisdsp_cuda_cfft_mag_f32(const void *d_src, void *d_mag, uint32_t fftLen, uint64_t nFrames, uint8_t ifftFlag,
+                                uint8_t squared, void *stream);
+int  cmsisdsp_cuda_cfft_peak_f32(const void *d_src, void *d_val, void *d_idx, uint32_t fftLen, uint64_t nFrames,
+                                 uint8_t ifftFlag, void *stream);
+
 /* ---- arm_rfft_q31 / arm_rfft_q15 (Source/TransformFunctions/arm_rfft_q31.c:145-181, arm_rfft_q15.c:148-182) ----
  * fftLenReal in {32..8192}; bitReverseFlagR = 1 (natural-order spectrum).  The plan is the cfft plan of the
  * same type and length fftLenReal/2 (cmsisdsp_cuda_plan_upload) plus the split-stage coefficients: the
@@ -125,7 +135,7 @@ const char *cmsisdsp_cuda_last_error(void);        /* thread-local, never NULL *
 uint64_t    cmsisdsp_cuda_launch_count(void);      /* kernels launched by this library so far */
 /* static facts about the kernel chosen for (op, fftLen): op 0 cfft_f32, 1 cfft_q31, 2 cfft_q15,
  * 3 rfft forward, 4 rfft inverse, 5/6 rfft_q31 forward/inverse, 7/8 rfft_q15 forward/inverse (fftLen = real
- * length for 3..8).  Any out pointer may be NULL. */
+ * length for 3..8), 9 cfft_f32 + magnitude epilogue.  Any out pointer may be NULL. */
 int  cmsisdsp_cuda_kernel_info(int op, uint32_t fftLen, int *threadsPerCta, int *framesPerCta,
                                int *smemBytes, int *regsPerThread, int *ctasPerSm);
 

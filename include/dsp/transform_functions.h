@@ -216,6 +216,17 @@ arm_status arm_cfft_batch_q15(const arm_cfft_instance_q15 *S, q15_t *p, uint32_t
                               uint8_t ifftFlag, uint8_t bitReverseFlag);
 arm_status arm_rfft_fast_batch_f32(const arm_rfft_fast_instance_f32 *S, float32_t *p, float32_t *pOut,
                                    uint32_t nFrames, uint8_t ifftFlag);
+/* arm_cfft_f32(S, p, ifftFlag, 1) fused with its usual consumers; pSrc (nFrames * 2*fftLen floats) is left untouched and
+ * the spectrum itself is never written:
+ *   _mag_ / _mag_squared_   + arm_cmplx_mag_f32 / arm_cmplx_mag_squared_f32: pMag receives fftLen floats per frame
+ *   _peak_                  + arm_cmplx_mag_f32 + arm_max_f32: one (value, index) per frame, the first maximum wins
+ * (Examples/ARM/arm_fft_bin_example/arm_fft_bin_example_f32.c:141-149).  Host or device pointers. */
+arm_status arm_cfft_mag_batch_f32(const arm_cfft_instance_f32 *S, const float32_t *pSrc, float32_t *pMag,
+                                  uint32_t nFrames, uint8_t ifftFlag);
+arm_status arm_cfft_mag_squared_batch_f32(const arm_cfft_instance_f32 *S, const float32_t *pSrc, float32_t *pMag,
+                                          uint32_t nFrames, uint8_t ifftFlag);
+arm_status arm_cfft_peak_batch_f32(const arm_cfft_instance_f32 *S, const float32_t *pSrc, float32_t *pResult,
+                                   uint32_t *pIndex, uint32_t nFrames, uint8_t ifftFlag);
 /* Fixed-point real FFT over nFrames frames; direction = S->ifftFlagR.  forward: pSrc frames fftLenReal
  * scalars apart, pDst frames 2*fftLenReal apart; inverse: pSrc frames 2*fftLenReal apart (bins
  * 0..fftLenReal/2 are read), pDst frames fftLenReal apart.  pSrc is left untouched. */

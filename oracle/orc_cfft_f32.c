@@ -242,3 +242,43 @@ void orc_cfft_f32(uint32_t N, float *p, int ifftFlag, int bitReverseFlag)
         }
     }
 }
+
+/* ------------------------------------------------------------------ spectrum epilogues
+ * arm_cfft_f32 followed by arm_cmplx_mag_f32 (Source/ComplexMathFunctions/arm_cmplx_mag_f32.c:252-264:
+ * sqrtf(re*re + im*im) through arm_sqrt_f32, Include/dsp/fast_math_functions.h:234-292) or
+ * arm_cmplx_mag_squared_f32 (arm_cmplx_mag_squared_f32.c: re*re + im*im), and arm_max_f32
+ * (Source/StatisticsFunctions/arm_max_f32.c generic loop: the FIRST maximum wins) -- the pipeline of
+ * Examples/ARM/arm_fft_bin_example/arm_fft_bin_example_f32.c:141-149.  p is transformed in place. */
+#include <math.h>
+#include <stdlib.h>
+void orc_cfft_mag_f32(uint32_t N, float *p, float *mag, int ifftFlag, int squared)
+{
+    orc_cfft_f32(N, p, ifftFlag, 1);
+    for (uint32_t k = 0; k < N; k++) {
+        const float re = p[2 * k], im = p[2 * k + 1];
+        const float s = (re * re) + (im * im);
+        mag[k] = squared ? s : (s >= 0.0f ? sqrtf(s) : 0.0f);
+    }
+}
+void orc_max_f32(const float *src, uint32_t n, float *val, uint32_t *idx)
+{
+    float out = src[0];
+    uint32_t outIndex = 0;
+    for (uint32_t k = 1; k < n; k++)
+        if (out < src[k]) { out = src[k]; outIndex = k; }
+    *val = out;
+    *idx = outIndex;
+}
+/* batch: src nFrames*2N floats (untouched), mag nFrames*N floats (may be NULL), val/idx nFrames (may be NULL) */
+void orc_cfft_mag_f32_batch(uint32_t N, const float *src, float *mag, float *val, uint32_t *idx, uint64_t nFrames,
+                            int ifftFlag, int squared)
+{
+    float *p = malloc(sizeof(float) * 2 * N), *m = malloc(sizeof(float) * N);
+    for (uint64_t f = 0; f < nFrames; f++) {
+        for (uint32_t k = 0; k < 2 * N; k++) p[k] = src[f * 2 * N + k];
+        orc_cfft_mag_f32(N, p, m, ifftFlag, squared);
+        if (mag) for (uint32_t k = 0; k < N; k++) mag[f * N + k] = m[k];
+        if (val && idx) orc_max_f32(m, N, val + f, idx + f);
+    }
+    free(p); free(m);
+}

@@ -50,6 +50,12 @@ void orc_cfft_q31_batch(uint32_t N, int32_t *p, uint64_t nFrames, int ifft, int 
 void orc_cfft_q15_batch(uint32_t N, int16_t *p, uint64_t nFrames, int ifft, int bitrev, int nthreads);
 void orc_rfft_fast_f32_batch(uint32_t N, float *p, float *pOut, uint64_t nFrames, int ifft, int nthreads);
 
+/* ---- spectrum epilogues: arm_cfft_f32 + arm_cmplx_mag[_squared]_f32 (+ arm_max_f32), orc_cfft_f32.c ---- */
+void orc_cfft_mag_f32(uint32_t N, float *p, float *mag, int ifftFlag, int squared);
+void orc_max_f32(const float *src, uint32_t n, float *val, uint32_t *idx);
+void orc_cfft_mag_f32_batch(uint32_t N, const float *src, float *mag, float *val, uint32_t *idx, uint64_t nFrames,
+                            int ifftFlag, int squared);
+
 /* ---- fixed-point real FFT (orc_rfft_fix.c): arm_rfft_q31.c:145-181, arm_rfft_q15.c:148-182 ----
  * N = real length 32..8192.  forward: pSrc N scalars (destroyed), pDst 2N scalars; inverse: pSrc bins
  * 0..N/2 read (frames 2N scalars apart in the batch drivers), pDst N scalars. */

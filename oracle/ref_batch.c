@@ -173,3 +173,23 @@ const int32_t *ref_real_coef_q31(int b) { return b ? realCoefBQ31 : realCoefAQ31
 const int16_t *ref_real_coef_q15(int b) { return b ? realCoefBQ15 : realCoefAQ15; }
 uint32_t ref_sizeof_rfft_instance_q31(void) { return (uint32_t)sizeof(arm_rfft_instance_q31); }
 uint32_t ref_sizeof_rfft_instance_q15(void) { return (uint32_t)sizeof(arm_rfft_instance_q15); }
+
+/* ---- arm_cfft_f32 + arm_cmplx_mag[_squared]_f32 (+ arm_max_f32): the reference's own functions, frame by frame ---- */
+#include "dsp/complex_math_functions.h"
+#include "dsp/statistics_functions.h"
+void ref_cfft_mag_f32_batch(uint32_t N, const float *src, float *mag, float *val, uint32_t *idx, uint64_t nFrames,
+                            int ifftFlag, int squared)
+{
+    arm_cfft_instance_f32 S;
+    if (arm_cfft_init_f32(&S, (uint16_t)N) != ARM_MATH_SUCCESS) return;
+    float *p = malloc(sizeof(float) * 2 * N), *m = malloc(sizeof(float) * N);
+    for (uint64_t f = 0; f < nFrames; f++) {
+        memcpy(p, src + f * 2 * N, sizeof(float) * 2 * N);
+        arm_cfft_f32(&S, p, (uint8_t)ifftFlag, 1);
+        if (squared) arm_cmplx_mag_squared_f32(p, m, N);
+        else arm_cmplx_mag_f32(p, m, N);
+        if (mag) memcpy(mag + f * N, m, sizeof(float) * N);
+        if (val && idx) arm_max_f32(m, N, val + f, idx + f);
+    }
+    free(p); free(m);
+}

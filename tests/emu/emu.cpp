@@ -221,6 +221,36 @@ int emu_rfft_fix(int type, uint32_t Nreal, const void *in, void *out, uint64_t n
     }
 }
 
+/* arm_cfft_f32 + arm_cmplx_mag[_squared]_f32 fused (CfftMagBody, modes 0 / 1; the peak mode reduces with warp
+ * shuffles and is exercised on the device only) */
+int emu_cfft_mag(uint32_t N, const float *in, float *mag, uint64_t nFrames, int ifft, int squared, const void *tw)
+{
+    switch (N) {
+#define RUNM(n, INV, MODE)                                                                         \
+    {                                                                                              \
+        typedef PlanCfftF32<n>::type PL;                                                           \
+        typedef CfftMagBody<PL, INV, MODE> BODY;                                                   \
+        std::vector<cf32> ordered((size_t)PL::kTwEntries + 1);                                     \
+        PL::build_twiddles((const cf32 *)tw, ordered.data());                                      \
+        run_batch<PL, BODY>(nFrames, [&](uint64_t f) {                                             \
+            BODY::Args a{};                                                                        \
+            a.in = (const cf32 *)in + f * n; a.tw = ordered.data(); a.scale = 1.0f / (float)n;     \
+            a.mag = mag + f * n;                                                                   \
+            return a;                                                                              \
+        });                                                                                        \
+    }
+#define CASE(n)                                                                                    \
+    case n:                                                                                        \
+        if (ifft) { if (squared) RUNM(n, true, SPEC_MAG_SQUARED) else RUNM(n, true, SPEC_MAG) }    \
+        else      { if (squared) RUNM(n, false, SPEC_MAG_SQUARED) else RUNM(n, false, SPEC_MAG) }  \
+        return 0;
+        FOR_ALL_N(CASE)
+#undef CASE
+#undef RUNM
+    default: return -1;
+    }
+}
+
 void emu_trace_begin(void) { g_trace.clear(); g_trace_on = true; }
 
 /* Per (phase, is_store): number of warp-level requests and the shared-memory wavefronts they

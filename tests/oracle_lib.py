@@ -83,6 +83,20 @@ class _Lib:
         self._fn(f"rfft_{kind}_batch")(N, src.ctypes.data, out.ctypes.data, frames, int(ifft), int(bitrev), int(threads))
         return out.reshape(frames, -1)
 
+    def cfft_mag(self, N, x, ifft=0, squared=False, peak=False):
+        """arm_cfft_f32 + arm_cmplx_mag[_squared]_f32 (+ arm_max_f32) per frame: returns mags [frames, N], or
+        (values [frames], indices [frames]) with peak=True."""
+        src = np.ascontiguousarray(x, dtype=np.float32)
+        assert src.size % (2 * N) == 0
+        frames = src.size // (2 * N)
+        mag = np.empty((frames, N), dtype=np.float32)
+        val, idx = np.empty(frames, dtype=np.float32), np.empty(frames, dtype=np.uint32)
+        fn = self._fn("cfft_mag_f32_batch")
+        fn.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int]
+        fn.restype = None
+        fn(N, src.ctypes.data, mag.ctypes.data, val.ctypes.data, idx.ctypes.data, frames, int(ifft), int(squared))
+        return (val, idx) if peak else mag
+
     def real_coef(self, kind, b):
         return np.ctypeslib.as_array(self._fn(f"real_coef_{kind}")(int(b)), shape=(8192,)).copy()
 

@@ -29,6 +29,7 @@ def emu():
     L.emu_cfft.argtypes = [C.c_int, C.c_uint32, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.emu_rfft.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
     L.emu_trace_stats.argtypes = [C.c_void_p, C.c_int]
+    L.emu_cfft_mag.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p]
     L.emu_rfft_fix.argtypes = [C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     return L
 
@@ -148,3 +149,20 @@ def test_rfft_fixed_point_bodies(emu, kind, N):
     assert emu.emu_rfft_fix(cd.TYPE_ID[kind], N, spec.ctypes.data, got.ctypes.data, spec.shape[0], 1, tw.ctypes.data,
                             A.ctypes.data, B.ctypes.data) == 0
     assert np.array_equal(got, want), (kind, N, "inverse")
+
+
+@pytest.mark.parametrize("N", LENGTHS)
+def test_cfft_magnitude_epilogue_body(emu, N):
+    """CfftMagBody (magnitude / squared magnitude fused behind the last pass) against the oracle's
+    arm_cfft_f32 + arm_cmplx_mag[_squared]_f32, north_star tolerance"""
+    tw, _ = product_tables("f32", N)
+    frames = 2 * {16: 128, 32: 64, 64: 32, 128: 16, 256: 8, 512: 4, 1024: 2}.get(N, 1) + 3
+    x = cfft_input("f32", N, frames=frames, seed=13 * N)
+    for ifft in (0, 1):
+        for sq in (0, 1):
+            want = oracle().cfft_mag(N, x, ifft, bool(sq))
+            got = np.zeros_like(want)
+            xin = x.copy()
+            assert emu.emu_cfft_mag(N, xin.ctypes.data, got.ctypes.data, frames, ifft, sq, tw.ctypes.data) == 0
+            assert np.array_equal(xin, x)
+            assert relrms(got, want) <= (4e-6 if sq else 2e-6), (N, ifft, sq)

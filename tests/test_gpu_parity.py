@@ -303,6 +303,82 @@ def test_direct_and_pipelined_flavours_agree_bit_for_bit():
     assert cu.cmsisdsp_cuda_set_kernel_flavour(7) != 0
 
 
+# ------------------------------------------------------------------ fused spectrum epilogues
+
+@pytest.mark.parametrize("N", LENGTHS)
+def test_cfft_magnitude_and_peak_epilogues(N):
+    """arm_cfft_mag[_squared]_batch_f32 / arm_cfft_peak_batch_f32 against arm_cfft_f32 + arm_cmplx_mag[_squared]_f32 +
+    arm_max_f32 of the oracle; both kernel flavours; ragged batches; the source is left untouched"""
+    cu = cd.cuda()
+    rng = np.random.default_rng(17 * N)
+    frames = 301
+    k0 = rng.integers(1, N - 1, size=frames)
+    n = np.arange(N)
+    tone = np.exp(2j * np.pi * k0[:, None] * n[None, :] / N) * (0.5 + rng.random((frames, 1)))
+    z = tone + 0.05 * (rng.standard_normal((frames, N)) + 1j * rng.standard_normal((frames, N)))
+    x = np.empty((frames, 2 * N), dtype=np.float32)
+    x[:, 0::2], x[:, 1::2] = z.real, z.imag
+    x[7] = 0.0                                                       # all-zero frame: every bin ties, index 0 must win
+    try:
+        for flavour in (0, 1):
+            assert cu.cmsisdsp_cuda_set_kernel_flavour(flavour) == 0
+            for ifft in (0, 1):
+                xin = x.copy()
+                for sq in (False, True):
+                    want = oracle().cfft_mag(N, x, ifft, sq)
+                    got = cd.cfft_mag_batch(N, xin, ifft, sq)
+                    assert np.array_equal(xin, x)
+                    assert relrms(got, want) <= (2 * F32_TOL if sq else F32_TOL), (N, flavour, ifft, sq)
+                wv, wi = oracle().cfft_mag(N, x, ifft, peak=True)
+                gv, gi = cd.cfft_peak_batch(N, xin, ifft)
+                assert gi[7] == 0 and gv[7] == 0.0
+                # a clear tone: the peak bin is unambiguous (forward: k0; inverse: N - k0)
+                assert np.array_equal(gi, wi), (N, flavour, ifft, np.flatnonzero(gi != wi)[:5])
+                assert np.all(np.abs(gv - wv) <= 4e-6 * np.abs(wv)), (N, flavour, ifft)
+                if not ifft:
+                    keep = np.arange(frames) != 7
+                    assert np.array_equal(gi[keep], k0[keep].astype(np.uint32))
+    finally:
+        cu.cmsisdsp_cuda_set_kernel_flavour(-1)
+
+
+def test_fft_bin_example_fused_peak():
+    """Examples/ARM/arm_fft_bin_example: the 10 kHz tone must peak at bin 213, now in ONE fused call"""
+    d = np.load(os.path.join(HERE, "golden", "fft_bin_example.npz"))
+    val, idx = cd.cfft_peak_batch(1024, d["input"], 0)
+    assert int(idx[0]) == int(d["ref_index"]) == 213
+    wv, wi = oracle().cfft_mag(1024, d["input"], 0, peak=True)
+    assert int(wi[0]) == 213 and abs(float(val[0]) - float(wv[0])) <= 4e-6 * float(wv[0])
+
+
+def test_spectrum_epilogues_device_pointers_large_batch():
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda", 0)
+    N, B = 1024, 1 << 16
+    g = torch.Generator(device=dev).manual_seed(21)
+    x = torch.randn(B, 2 * N, device=dev, generator=g)
+    x0 = x.clone()
+    mag = torch.empty(B, N, device=dev)
+    val = torch.empty(B, device=dev)
+    idx = torch.empty(B, device=dev, dtype=torch.int32)
+    S = cd.cfft_instance("f32", N)
+    L = cd.lib()
+    assert L.arm_cfft_mag_batch_f32(C.byref(S), x.data_ptr(), mag.data_ptr(), B, 0) == 0, cd.last_error()
+    assert L.arm_cfft_peak_batch_f32(C.byref(S), x.data_ptr(), val.data_ptr(), idx.data_ptr(), B, 0) == 0, cd.last_error()
+    torch.cuda.synchronize()
+    assert bool((x == x0).all().item())
+    # size-independent properties: the peak is the maximum of the magnitudes, at the first index that holds it;
+    # Parseval: sum |X|^2 = N sum |x|^2
+    mx, am = mag.max(dim=1)
+    assert bool((val == mx).all().item()) and bool((idx.long() == am).all().item() or (mag.gather(1, idx.long()[:, None])[:, 0] == mx).all().item())
+    e_t = x.double().pow(2).sum(1) * N
+    e_f = mag.double().pow(2).sum(1)
+    assert float(((e_f - e_t).abs() / e_t).max()) < 1e-5
+    sel = torch.arange(0, B, B // 256, device=dev)
+    want = oracle().cfft_mag(N, x[sel].cpu().numpy(), 0, False)
+    assert relrms(mag[sel].cpu().numpy(), want) <= F32_TOL
+
+
 # ------------------------------------------------------------------ arm_rfft_q31 / arm_rfft_q15 (SURVEY 8(f) rank 2)
 
 @pytest.mark.parametrize("kind", ["q31", "q15"])

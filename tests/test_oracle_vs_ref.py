@@ -86,6 +86,20 @@ def test_rfft_fixed_point_bit_exact(kind, N):
     assert c.shape == (spec.shape[0], N) and np.array_equal(c, d), (kind, N, "inverse")
 
 
+@pytest.mark.parametrize("N", [16, 128, 1024, 4096])
+def test_cfft_mag_and_peak_bit_exact(N):
+    """arm_cfft_f32 + arm_cmplx_mag[_squared]_f32 + arm_max_f32 restated == the compiled reference's own functions"""
+    rng = np.random.default_rng(4000 + N)
+    x = rng.standard_normal((7, 2 * N)).astype(np.float32)
+    x[3] = 0.0
+    x[4, 0::2] = 1.0; x[4, 1::2] = 0.0                               # constant frame: every bin but DC ties at ~0
+    for ifft in (0, 1):
+        for sq in (False, True):
+            assert np.array_equal(bits(oracle().cfft_mag(N, x, ifft, sq)), bits(ref().cfft_mag(N, x, ifft, sq)))
+        (v0, i0), (v1, i1) = oracle().cfft_mag(N, x, ifft, peak=True), ref().cfft_mag(N, x, ifft, peak=True)
+        assert np.array_equal(bits(v0), bits(v1)) and np.array_equal(i0, i1)
+
+
 def test_threads_agree():
     rng = np.random.default_rng(7)
     x = rng.standard_normal((37, 2 * 256)).astype(np.float32)

@@ -113,7 +113,8 @@ def test_shared_objects_export_every_declared_symbol():
     names = _declared_functions(os.path.join(ROOT, "include", "dsp", "transform_functions.h"))
     # 3x(9 per-length inits + init + exec) + rfft (8+1+1) + 4 batch + last_status + mfcc (8+1+1+1)
     # + rfft_q31/q15 (init, exec, batch each; their per-length inits are declared through a macro)
-    assert len(names) == 65
+    # + 3 fused spectrum epilogues (mag, mag squared, peak)
+    assert len(names) == 68
     for name in names:
         assert hasattr(fr, name), name
     for N in RFIX_LENGTHS:

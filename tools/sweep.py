@@ -57,7 +57,7 @@ def main():
             if op == "mfcc" and N not in (256, 512, 1024):
                 continue
             nbytes = args.mib << 20
-            if op.startswith("cfft"):
+            if op.startswith("cfft") and op not in ("cfft_mag", "cfft_peak"):
                 kind = op.split("_")[1]
                 esz = {"f32": 8, "q31": 8, "q15": 4}[kind]
                 B = nbytes // (esz * N)
@@ -84,6 +84,20 @@ def main():
                 alg = B * (4 * N + 4 * 13)
                 samples = B * N
                 info = dict(threads_per_cta=0, frames_per_cta=0, smem_bytes=0, regs_per_thread=0, ctas_per_sm=0)
+            elif op in ("cfft_mag", "cfft_peak"):
+                B = nbytes // (8 * N)
+                cd.ensure_plans("f32", N)
+                a = torch.randn(B, 2 * N, device=dev)
+                b = torch.empty(B, N if op == "cfft_mag" else 2, device=dev)
+                cu = cd.cuda()
+                if op == "cfft_mag":
+                    fn = lambda: cu.cmsisdsp_cuda_cfft_mag_f32(a.data_ptr(), b.data_ptr(), N, B, 0, 0, st)
+                    alg = B * N * 12
+                else:
+                    fn = lambda: cu.cmsisdsp_cuda_cfft_peak_f32(a.data_ptr(), b.data_ptr(), b.data_ptr() + 4 * B, N, B, 0, st)
+                    alg = B * (N * 8 + 8)
+                samples = B * N
+                info = cd.kernel_info(9, N)
             elif op.startswith("rfftq"):
                 # rfftq31_fwd / rfftq31_inv / rfftq15_fwd / rfftq15_inv; N = real length; algorithmic bytes:
                 # forward N in + 2N out scalars, inverse N+2 in (bins 0..N/2) + N out
