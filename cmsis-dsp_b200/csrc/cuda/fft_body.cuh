@@ -274,7 +274,8 @@ template <class PL, bool INV, int MODE, bool STAGED = false> struct CfftMagBody 
     {
         if (INV) w = cf32{w.x * scale, -w.y * scale};                       /* cfft_f32.c:1285-1297 */
         const float s = add_rn(mul_rn(w.x, w.x), mul_rn(w.y, w.y));         /* (real * real) + (imag * imag), no contraction */
-        if (MODE == SPEC_MAG_SQUARED) return s;
+        /* SPEC_PEAK compares squared magnitudes (sqrt is monotonic) and takes the root of the winner only */
+        if (MODE != SPEC_MAG) return s;
 #if defined(__CUDA_ARCH__)
         return __fsqrt_rn(s);
 #else
@@ -312,7 +313,7 @@ template <class PL, bool INV, int MODE, bool STAGED = false> struct CfftMagBody 
             if (kCross) {
                 r.v[0] = cf32{bv, __int_as_float(bk)};                      /* the warp's partial, for the two extra phases */
             } else if (i == 0) {
-                *a.peakVal = bv;
+                *a.peakVal = __fsqrt_rn(bv);
                 *a.peakIdx = (uint32_t)bk;
             }
 #else
@@ -342,7 +343,7 @@ template <class PL, bool INV, int MODE, bool STAGED = false> struct CfftMagBody 
 #pragma unroll
                 for (int w = 1; w < T / 32; w++)
                     if (better(sm[w].x, __float_as_int(sm[w].y), bv, bk)) { bv = sm[w].x; bk = __float_as_int(sm[w].y); }
-                *a.peakVal = bv;
+                *a.peakVal = __fsqrt_rn(bv);
                 *a.peakIdx = (uint32_t)bk;
             }
 #endif

@@ -343,12 +343,16 @@ def test_cfft_magnitude_and_peak_epilogues(N):
 
 
 def test_fft_bin_example_fused_peak():
-    """Examples/ARM/arm_fft_bin_example: the 10 kHz tone must peak at bin 213, now in ONE fused call"""
+    """Examples/ARM/arm_fft_bin_example: the 10 kHz tone peaks at bin 213, now in ONE fused call.  The example's input
+    is a real signal (imaginary parts zero), so bins 213 and 1024 - 213 tie mathematically and only rounding separates
+    them: the reference's own arithmetic happens to favour 213, any other correctly rounded FFT may favour either."""
     d = np.load(os.path.join(HERE, "golden", "fft_bin_example.npz"))
     val, idx = cd.cfft_peak_batch(1024, d["input"], 0)
-    assert int(idx[0]) == int(d["ref_index"]) == 213
+    assert int(d["ref_index"]) == 213 and int(idx[0]) in (213, 1024 - 213)
     wv, wi = oracle().cfft_mag(1024, d["input"], 0, peak=True)
     assert int(wi[0]) == 213 and abs(float(val[0]) - float(wv[0])) <= 4e-6 * float(wv[0])
+    mag = cd.cfft_mag_batch(1024, d["input"], 0)[0]
+    assert int(np.argmax(mag[:512])) == 213                        # the known answer on the non-redundant half
 
 
 def test_spectrum_epilogues_device_pointers_large_batch():
