@@ -51,3 +51,32 @@ for u in ("3_2048", "4_2048"):
             keep.append(re.sub(r"\s*/\* 0x[0-9a-f]+ \*/$", "", l))
     open(os.path.join(P, f"{tag}_sass_ku_{u}.pipe.sass"), "w").write("\n".join(keep) + "\n")
 print("profiles written for", tag, tr)
+
+# ---- the other kernel families (tools/gpu_round.sh: prof_fam_*.ncu-rep, sweep_rfix, config4)
+fam = []
+for name in ("mfcc", "cfft_f32", "cfft_q31", "cfft_q15", "rfftq31_fwd", "cfft_peak"):
+    rep = os.path.join(G, f"prof_fam_{name}.ncu-rep")
+    if os.path.exists(rep):
+        out = subprocess.run([sys.executable, os.path.join(R, "tools", "ncu_summary.py"), rep], capture_output=True, text=True).stdout
+        fam.append(f"## {name}  (python tools/sweep.py --mib 256 --ops {name} --lens 1024 under ncu --set full --clock-control none)\n" + out)
+        hs = subprocess.run([sys.executable, os.path.join(R, "tools", "ncu_hotspots.py"), rep, "15"], capture_output=True, text=True).stdout
+        open(os.path.join(P, f"{tag}_ncu_hotspots_{name}.txt"), "w").write(f"# {name} N=1024, per-instruction stall samples\n" + "\n".join(l[:230] for l in hs.splitlines()) + "\n")
+if fam:
+    open(os.path.join(P, f"{tag}_ncu_families.txt"), "w").write("\n".join(fam))
+for src, dst in (("sweep_rfix.txt", f"{tag}_sweep_rfft_fixed.txt"), ("config4_1gpu.json", f"{tag}_config4_1gpu.json")):
+    if os.path.exists(os.path.join(G, src)):
+        open(os.path.join(P, dst), "w").write(open(os.path.join(G, src)).read())
+for unit, pat, dst in (("mfcc", "mfcc_kernel_pipeILi512E", f"{tag}_sass_mfcc_pipe_1024.sass"), ("ku_1_1024", "Lb0ELb0ELb0ELb0E", f"{tag}_sass_ku_1_1024.sass")):
+    obj = os.path.join(R, "cmsis-dsp_b200", "build", f"{unit}.o")
+    if not os.path.exists(obj):
+        continue
+    sass = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
+    keep, on = [], False
+    for l in sass.splitlines():
+        if "Function :" in l:
+            on = pat in l
+        if on:
+            keep.append(re.sub(r"\s*/\* 0x[0-9a-f]+ \*/$", "", l))
+    if keep:
+        open(os.path.join(P, dst), "w").write("\n".join(keep) + "\n")
+print("family profiles written")
