@@ -172,8 +172,8 @@ def run_cuda(args, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    # keep this rank's host thread (and so its pinned buffers, first touch) on the NUMA node of its GPU: with
-    # several ranks streaming host buffers at once, remote-node memory halves the end-to-end rate
+    # keep this rank's host thread (and so its pinned buffers, first touch) on the NUMA node of its GPU
+    # (matters on multi-socket hosts when several ranks stream host buffers at once; a no-op on one node)
     numa_bound = False
     try:
         import pynvml
