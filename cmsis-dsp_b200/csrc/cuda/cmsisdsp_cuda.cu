@@ -393,7 +393,16 @@ extern "C" int cmsisdsp_cuda_device_count(void)
     return n;
 }
 extern "C" int cmsisdsp_cuda_set_device(int device) { CU_TRY(cudaSetDevice(device)); return 0; }
-extern "C" int cmsisdsp_cuda_get_device(void) { int d = -1; if (cudaGetDevice(&d) != cudaSuccess) return -1; return d; }
+extern "C" int cmsisdsp_cuda_get_device(void)
+{
+    int d = -1;
+    const cudaError_t e = cudaGetDevice(&d);
+    if (e != cudaSuccess) {
+        fail(CMSISDSP_CUDA_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback): cudaGetDevice", e);
+        return -1;
+    }
+    return d;
+}
 extern "C" int cmsisdsp_cuda_malloc(void **p, size_t bytes) { if (!p) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "null"); CU_TRY(cudaMalloc(p, bytes)); return 0; }
 extern "C" int cmsisdsp_cuda_free(void *p) { CU_TRY(cudaFree(p)); return 0; }
 extern "C" int cmsisdsp_cuda_host_alloc(void **p, size_t bytes) { if (!p) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "null"); CU_TRY(cudaHostAlloc(p, bytes, cudaHostAllocDefault)); return 0; }

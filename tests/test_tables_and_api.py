@@ -132,3 +132,34 @@ def test_shard_partition():
             assert parts[0][0] == 0 and parts[-1][1] == B
             for (a, b), (c, d) in zip(parts, parts[1:]):
                 assert b == c and a <= b and c <= d
+
+
+def test_no_cpu_fallback_without_a_device():
+    """Without a CUDA device every exec entry point must FAIL (ARM_MATH_ARGUMENT_ERROR / a latched status), never
+    compute on the CPU: the buffers stay untouched.  Skipped where a GPU is visible."""
+    cu, L = cd.cuda(), cd.lib()
+    if cu.cmsisdsp_cuda_device_count() > 0:
+        pytest.skip("a CUDA device is visible")
+    x = np.arange(2 * 64, dtype=np.float32)
+    x0 = x.copy()
+    S = cd.cfft_instance("f32", 64)
+    assert L.arm_cfft_batch_f32(C.byref(S), x.ctypes.data, 1, 0, 1) == cd.ARM_MATH_ARGUMENT_ERROR
+    L.arm_cfft_f32(C.byref(S), x.ctypes.data, 0, 1)
+    assert L.arm_cuda_last_status() == cd.ARM_MATH_ARGUMENT_ERROR and np.array_equal(x, x0)
+    out = np.zeros(64, dtype=np.float32)
+    R = cd.rfft_instance(64)
+    assert L.arm_rfft_fast_batch_f32(C.byref(R), x.ctypes.data, out.ctypes.data, 1, 0) == cd.ARM_MATH_ARGUMENT_ERROR
+    assert L.arm_cfft_mag_batch_f32(C.byref(S), x.ctypes.data, out.ctypes.data, 1, 0) == cd.ARM_MATH_ARGUMENT_ERROR
+    idx = np.zeros(1, dtype=np.uint32)
+    assert L.arm_cfft_peak_batch_f32(C.byref(S), x.ctypes.data, out.ctypes.data, idx.ctypes.data, 1, 0) == cd.ARM_MATH_ARGUMENT_ERROR
+    for kind in ("q31", "q15"):
+        xi = np.arange(2 * 64, dtype=cd.NP_DTYPE[kind])
+        Si = cd.cfft_instance(kind, 64)
+        assert getattr(L, f"arm_cfft_batch_{kind}")(C.byref(Si), xi.ctypes.data, 1, 0, 1) == cd.ARM_MATH_ARGUMENT_ERROR
+        Sr = cd.rfft_fix_instance(kind, 64)
+        oi = np.zeros(128, dtype=cd.NP_DTYPE[kind])
+        assert getattr(L, f"arm_rfft_batch_{kind}")(C.byref(Sr), xi.ctypes.data, oi.ctypes.data, 1) == cd.ARM_MATH_ARGUMENT_ERROR
+        assert not oi.any()
+    assert not out.any() and np.array_equal(x, x0)
+    assert cd.last_error() != ""
+    assert cu.cmsisdsp_cuda_launch_count() == 0
