@@ -362,7 +362,7 @@ static int rfft_fix(int type, const void *d_src, void *d_dst, uint32_t fftLenRea
     if (!coef) return fail(CMSISDSP_CUDA_ERR_NO_PLAN, "no fixed-point rfft plan uploaded for this (device, type, fftLenReal)");
     const int op = (type == CMSISDSP_CUDA_Q31 ? OP_RFFT_Q31_FWD : OP_RFFT_Q15_FWD) + (ifftFlagR ? 1 : 0);
     const KernelEntry *ke = kEntries[op][li];
-    return ke->launch(d_src, d_dst, nFrames, ifftFlagR != 0, pl.tw, coef, (li + 4) & 1, KF_DIRECT, (cudaStream_t)stream);
+    return ke->launch(d_src, d_dst, nFrames, ifftFlagR != 0, pl.tw, coef, (li + 4) & 1, choose_flavour(ke), (cudaStream_t)stream);
 }
 extern "C" int cmsisdsp_cuda_rfft_q31(const void *d_src, void *d_dst, uint32_t fftLenReal, uint64_t nFrames, uint8_t ifftFlagR, void *stream)
 { return rfft_fix(CMSISDSP_CUDA_Q31, d_src, d_dst, fftLenReal, nFrames, ifftFlagR, stream); }

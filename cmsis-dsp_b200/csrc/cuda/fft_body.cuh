@@ -1017,4 +1017,159 @@ template <class PL> struct TinyRfftInvBody {
     }
 };
 
+/* ------------------------------------------------------------------ thread per frame: the fused entry points
+ *
+ * Same data path as TinyCfftBody (the kernel brings the lane's frame into its padded slot with one bulk copy and
+ * sends the slot home with another), for bodies whose input and output differ in size: kTinyInBytes / kTinyOutBytes,
+ * tiny_home (where the slot goes) and tiny_bind (point the arguments at the slot).  Slots are read and written with
+ * 16-byte vectors only (conflict-free across the lanes of a warp). */
+
+template <class A, int COUNT> struct VecOut {
+    typedef typename A::elem elem;
+    typedef typename A::work work;
+    static constexpr int V = 16 / (int)sizeof(elem);
+    /* store z[G*V .. G*V+V-1] as one vector */
+    template <int G> static FFT_HD void group(const work *z, elem *out)
+    {
+        Vec16<elem> q;
+#pragma unroll
+        for (int u = 0; u < V; u++) q.e[u] = A::store(z[G * V + u]);
+        *reinterpret_cast<Vec16<elem> *>(out + G * V) = q;
+    }
+};
+
+/* arm_rfft_q31 / arm_rfft_q15, complex length N <= 64 (real length <= 128) */
+template <class PL, bool INV> struct TinyRfftFixBody {
+    typedef typename PL::Arith A;
+    typedef typename A::elem elem;
+    typedef typename A::xelem xelem;
+    typedef typename A::telem telem;
+    typedef typename A::work work;
+    typedef Engine<PL> Eng;
+    typedef typename Eng::Regs Regs;
+    typedef typename PL::P0 PS;
+    static constexpr int N = PL::N, kPhases = 1, V = 16 / (int)sizeof(elem);
+    static_assert(PL::NP == 1 && PL::T == 1, "one thread per frame, one pass");
+    struct Args {
+        const elem *in;
+        elem *out;
+        const telem *tw;
+        const ci32x4 *coef;
+        int shl1;
+    };
+    static FFT_HD Args for_frame(Args a, uint64_t frame)
+    {
+        a.in += frame * (uint64_t)(INV ? 2 * N : N);
+        a.out += frame * (uint64_t)(INV ? N : 2 * N);
+        return a;
+    }
+    static FFT_HD void set_scratch(Args &, xelem *) {}
+    /* inverse: bins 0..N of the 2N-bin spectrum frame, rounded up to whole vectors (the frame is longer than that) */
+    static constexpr int kInElems = INV ? ((N + 1 + V - 1) / V) * V : N;
+    static constexpr int kTinyInBytes = kInElems * (int)sizeof(elem), kTinyOutBytes = (INV ? N : 2 * N) * (int)sizeof(elem);
+    static FFT_HD void *tiny_home(const Args &a) { return a.out; }
+    static FFT_HD void tiny_bind(Args &a, void *slot) { a.in = reinterpret_cast<const elem *>(slot); a.out = reinterpret_cast<elem *>(slot); }
+
+    /* forward: bins k = K and 2N-K; a vector leaves as soon as its last element exists */
+    template <int K> static FFT_HD void fwd_bins(const Args &a, const work *y, work *z)
+    {
+        if constexpr (K < N) {
+            const work o = A::split_fwd(y[K], y[N - K], a.coef[K]);
+            z[K] = o;
+            z[2 * N - K] = A::mirror(o);
+            if constexpr (K % V == V - 1) VecOut<A, 2 * N>::template group<K / V>(z, a.out);
+            if constexpr ((2 * N - K) % V == 0) VecOut<A, 2 * N>::template group<(2 * N - K) / V>(z, a.out);
+            fwd_bins<K + 1>(a, y, z);
+        }
+    }
+    template <int G> static FFT_HD void out_groups(const work *y, elem *out)
+    {
+        if constexpr (G < N / V) {
+            VecOut<A, N>::template group<G>(y, out);
+            out_groups<G + 1>(y, out);
+        }
+    }
+    template <int PH> static FFT_HD void phase(Regs &r, const Args &a, xelem *, int)
+    {
+        if constexpr (!INV) {
+            TinyIO<A, N>::load(r.v, a.in);
+            Eng::template compute<0, false>(r, a.tw, 0);
+            work y[N];                                                 /* y[k] = X[k] */
+#pragma unroll
+            for (int e = 0; e < N; e++) y[PS::out_index(e)] = a.shl1 ? A::shl1(r.v[e]) : r.v[e];
+            work z[2 * N];
+            z[0] = A::split_dc(y[0]);
+            z[N] = A::split_nyquist(y[0]);
+            fwd_bins<1>(a, y, z);
+            VecOut<A, 2 * N>::template group<N / V>(z, a.out);        /* the vector that starts with bin N (Nyquist) */
+        } else {
+            work g[kInElems];
+            TinyIO<A, kInElems>::load(g, a.in);
+#pragma unroll
+            for (int b = 0; b < N / PS::R; b++)
+#pragma unroll
+                for (int e = 0; e < PS::R; e++) {
+                    const int idx = Eng::template in_index<0>(0, b, e);
+                    r.v[b * PS::R + e] = A::split_inv(g[idx], g[N - idx], a.coef[idx]);
+                }
+            Eng::template compute<0, true>(r, a.tw, 0);
+            work y[N];
+#pragma unroll
+            for (int e = 0; e < N; e++) {
+                work w = r.v[e];
+                if (a.shl1) w = A::shl1(w);
+                y[PS::out_index(e)] = A::sat_shl1(w);
+            }
+            out_groups<0>(y, a.out);
+        }
+    }
+};
+
+/* arm_cfft_f32 + magnitude / peak, N <= 64 */
+template <class PL, bool INV, int MODE> struct TinyCfftMagBody {
+    typedef CfftMagBody<PL, INV, MODE, true> M;
+    typedef typename M::Args Args;
+    typedef typename M::Eng Eng;
+    typedef typename M::Regs Regs;
+    typedef cf32 elem;
+    typedef cf32 xelem;
+    typedef typename PL::P0 PS;
+    static constexpr int N = PL::N, kPhases = 1;
+    static_assert(PL::NP == 1 && PL::T == 1, "one thread per frame, one pass");
+    static FFT_HD Args for_frame(Args a, uint64_t frame) { return M::for_frame(a, frame); }
+    static FFT_HD void set_scratch(Args &, xelem *) {}
+    static constexpr int kTinyInBytes = N * (int)sizeof(cf32), kTinyOutBytes = (MODE == SPEC_PEAK) ? 0 : N * (int)sizeof(float);
+    static FFT_HD void *tiny_home(const Args &a) { return a.mag; }
+    static FFT_HD void tiny_bind(Args &a, void *slot)
+    {
+        a.in = reinterpret_cast<const cf32 *>(slot);
+        if (MODE != SPEC_PEAK) a.mag = reinterpret_cast<float *>(slot);
+    }
+    template <int PH> static FFT_HD void phase(Regs &r, const Args &a, xelem *, int)
+    {
+        TinyIO<ArithF32, N>::load(r.v, a.in);
+        if (INV) {
+#pragma unroll
+            for (int k = 0; k < N; k++) r.v[k].y = -r.v[k].y;                /* cfft_f32.c:1252-1261 */
+        }
+        Eng::template compute<0, INV>(r, a.tw, 0);
+        float m[N];                                                           /* m[k] = |X[k]| (squared for SPEC_MAG_SQUARED / SPEC_PEAK) */
+#pragma unroll
+        for (int e = 0; e < N; e++) m[PS::out_index(e)] = M::magnitude(r.v[e], a.scale);
+        if (MODE == SPEC_PEAK) {
+            float bv = m[0];
+            int bk = 0;
+#pragma unroll
+            for (int k = 1; k < N; k++)
+                if (m[k] > bv) { bv = m[k]; bk = k; }                        /* the first maximum wins */
+            *a.peakVal = sqrtf(bv);
+            *a.peakIdx = (uint32_t)bk;
+        } else {
+#pragma unroll
+            for (int g = 0; g < N / 4; g++)
+                *reinterpret_cast<Vec16<float> *>(a.mag + 4 * g) = Vec16<float>{{m[4 * g], m[4 * g + 1], m[4 * g + 2], m[4 * g + 3]}};
+        }
+    }
+};
+
 }  // namespace b200fft

@@ -10,6 +10,8 @@
 #include <cuda_runtime.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #if defined(KU_N) && KU_N == 32
 #define FFT_HI32_XU 1        /* q31 high products as IMAD.HI for this length (fft_arith.cuh: hi32) */
 #endif
@@ -209,23 +211,43 @@ frame_kernel_pipe(typename BODY::Args base, uint64_t nFrames)
  * the 16-byte vector accesses of 8 consecutive lanes hit 32 different banks), transforms the frame
  * in registers -- single pass, no exchange -- writes the result back into the slot and sends it
  * home with one bulk store.  No LDG/STG at all on the data path. */
-template <class PL> struct TinySmem {
+/* bytes a thread-per-frame body brings in / sends home per frame, where its result goes, and how its arguments
+ * are pointed at the slot (defaults: a frame of N elements in place of itself) */
+template <class BODY, class PL, class = void> struct TinyTraits {
     typedef typename PL::Arith::elem elem;
-    static constexpr int kWarps = 4, kCtaThreads = 32 * kWarps, kFramesPerCta = kCtaThreads;
-    static constexpr int kFrameBytes = PL::N * (int)sizeof(elem);
-    static constexpr int kSlotBytes = kFrameBytes + 16;
+    static constexpr int kIn = PL::N * (int)sizeof(elem), kOut = kIn;
+    static __device__ __forceinline__ void *home(const typename BODY::Args &a) { return a.out; }
+    static __device__ __forceinline__ void bind(typename BODY::Args &a, void *slot)
+    {
+        a.in = reinterpret_cast<const elem *>(slot);
+        a.out = reinterpret_cast<elem *>(slot);
+    }
+};
+template <class BODY, class PL> struct TinyTraits<BODY, PL, std::void_t<decltype(BODY::kTinyInBytes)>> {
+    static constexpr int kIn = BODY::kTinyInBytes, kOut = BODY::kTinyOutBytes;     /* kOut = 0: the body stores its (tiny) result itself */
+    static __device__ __forceinline__ void *home(const typename BODY::Args &a) { return BODY::tiny_home(a); }
+    static __device__ __forceinline__ void bind(typename BODY::Args &a, void *slot) { BODY::tiny_bind(a, slot); }
+};
+
+template <class BODY, class PL> struct TinySmem {
+    typedef TinyTraits<BODY, PL> TT;
+    static_assert(TT::kIn % 16 == 0 && TT::kOut % 16 == 0, "bulk copies move multiples of 16 bytes");
+    static constexpr int kSlotBytes = (TT::kIn > TT::kOut ? TT::kIn : TT::kOut) + 16;
+    /* as many warps per CTA as keep the CTA's slots around 110 KB (two CTAs per SM) */
+    static constexpr int kWarps = (kSlotBytes * 128 <= 112 * 1024) ? 4 : ((kSlotBytes * 64 <= 112 * 1024) ? 2 : 1);
+    static constexpr int kCtaThreads = 32 * kWarps, kFramesPerCta = kCtaThreads;
     static constexpr int kBytes = kCtaThreads * kSlotBytes + kWarps * 8;
 };
 
 template <class BODY, class PL>
-__global__ void __launch_bounds__(TinySmem<PL>::kCtaThreads) frame_kernel_tiny(typename BODY::Args base, uint64_t nFrames)
+__global__ void __launch_bounds__(TinySmem<BODY, PL>::kCtaThreads) frame_kernel_tiny(typename BODY::Args base, uint64_t nFrames)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    typedef typename BODY::elem elem;
-    typedef TinySmem<PL> SM;
+    typedef TinySmem<BODY, PL> SM;
+    typedef typename SM::TT TT;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + SM::kCtaThreads * SM::kSlotBytes) + warp;
-    elem *slot = reinterpret_cast<elem *>(smem_raw + threadIdx.x * SM::kSlotBytes);
+    void *slot = smem_raw + threadIdx.x * SM::kSlotBytes;
     const uint64_t frame = (uint64_t)blockIdx.x * SM::kFramesPerCta + threadIdx.x;
     const bool valid = frame < nFrames;
 
@@ -235,21 +257,22 @@ __global__ void __launch_bounds__(TinySmem<PL>::kCtaThreads) frame_kernel_tiny(t
     }
     __syncwarp();
     typename BODY::Args a = BODY::for_frame(base, valid ? frame : 0);
-    elem *home = a.out;
+    void *home = TT::home(a);
     if (valid) {
-        mbar_expect_tx(bar, SM::kFrameBytes);                 /* arrive + this lane's bytes */
-        bulk_g2s(slot, a.in, SM::kFrameBytes, bar);
+        mbar_expect_tx(bar, TT::kIn);                         /* arrive + this lane's bytes */
+        bulk_g2s(slot, a.in, TT::kIn, bar);
     } else {
         mbar_arrive(bar);
     }
     mbar_wait(bar, 0);
     if (valid) {
-        a.in = slot;
-        a.out = slot;
+        TT::bind(a, slot);
         typename BODY::Regs r;
         BODY::template phase<0>(r, a, nullptr, 0);
-        fence_proxy_async();                                  /* the slot's generic-proxy writes -> visible to the TMA */
-        bulk_s2g(home, slot, SM::kFrameBytes);
+        if constexpr (TT::kOut > 0) {
+            fence_proxy_async();                              /* the slot's generic-proxy writes -> visible to the TMA */
+            bulk_s2g(home, slot, TT::kOut);
+        }
     }
     bulk_wait_read_all();                                     /* shared memory must outlive the store's reads */
 }
@@ -361,9 +384,9 @@ template <class BODY, class PL> static int tiny_prepare(int *occOut)
     KU_TRY(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) return shim_fail(CMSISDSP_CUDA_ERR_NO_DEVICE, "device index out of range", cudaSuccess);
     if (!occ[dev]) {
-        KU_TRY(cudaFuncSetAttribute(frame_kernel_tiny<BODY, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, TinySmem<PL>::kBytes));
+        KU_TRY(cudaFuncSetAttribute(frame_kernel_tiny<BODY, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, TinySmem<BODY, PL>::kBytes));
         int o = 0;
-        KU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, frame_kernel_tiny<BODY, PL>, TinySmem<PL>::kCtaThreads, TinySmem<PL>::kBytes));
+        KU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, frame_kernel_tiny<BODY, PL>, TinySmem<BODY, PL>::kCtaThreads, TinySmem<BODY, PL>::kBytes));
         if (o < 1) return shim_fail(CMSISDSP_CUDA_ERR_RUNTIME, "thread-per-frame kernel does not fit on an SM", cudaSuccess);
         occ[dev] = o;
     }
@@ -376,9 +399,9 @@ static int launch_tiny(const typename BODY::Args &args, uint64_t nFrames, cudaSt
     if (nFrames == 0) return CMSISDSP_CUDA_OK;
     int rc = tiny_prepare<BODY, PL>(nullptr);
     if (rc) return rc;
-    const uint64_t ctas = (nFrames + TinySmem<PL>::kFramesPerCta - 1) / TinySmem<PL>::kFramesPerCta;
+    const uint64_t ctas = (nFrames + TinySmem<BODY, PL>::kFramesPerCta - 1) / TinySmem<BODY, PL>::kFramesPerCta;
     if (ctas > 0x7fffffffull) return shim_fail(CMSISDSP_CUDA_ERR_ARGUMENT, "batch too large for one launch", cudaSuccess);
-    frame_kernel_tiny<BODY, PL><<<(unsigned)ctas, TinySmem<PL>::kCtaThreads, TinySmem<PL>::kBytes, st>>>(args, nFrames);
+    frame_kernel_tiny<BODY, PL><<<(unsigned)ctas, TinySmem<BODY, PL>::kCtaThreads, TinySmem<BODY, PL>::kBytes, st>>>(args, nFrames);
     shim_count_launch();
     KU_TRY(cudaGetLastError());
     return CMSISDSP_CUDA_OK;
@@ -390,9 +413,9 @@ template <class BODY, class PL> static int facts_of_tiny(KernelFacts *f)
     if (rc) return rc;
     cudaFuncAttributes fa;
     KU_TRY(cudaFuncGetAttributes(&fa, frame_kernel_tiny<BODY, PL>));
-    f->threads = TinySmem<PL>::kCtaThreads;
-    f->frames = TinySmem<PL>::kFramesPerCta;
-    f->smem = TinySmem<PL>::kBytes;
+    f->threads = TinySmem<BODY, PL>::kCtaThreads;
+    f->frames = TinySmem<BODY, PL>::kFramesPerCta;
+    f->smem = TinySmem<BODY, PL>::kBytes;
     f->regs = fa.numRegs;
     f->ctasPerSm = occ;
     return CMSISDSP_CUDA_OK;
@@ -582,11 +605,20 @@ typedef PL TWPLAN;
 
 typedef PlanCfftF32<KU_N>::type PL;
 typedef PipeOf<PL> PIPEOF;
-struct PIPE { static constexpr bool kHas = PIPEOF::kPipe, kPrefer = PIPEOF::kPipe; };
+struct PIPE { static constexpr bool kHas = PIPEOF::kHas, kPrefer = PIPEOF::kHas; };
 
 template <bool INV, int MODE>
 static int mag_go(const void *in, void *out, uint64_t nFrames, const void *tw, const void *aux, int flavour, cudaStream_t st)
 {
+    if constexpr (PIPEOF::kTiny) {
+        if (flavour == KF_PIPE && aligned16(in) && (MODE == SPEC_PEAK || aligned16(out))) {
+            typedef TinyCfftMagBody<PL, INV, MODE> BODY;
+            typename BODY::Args a{};
+            a.in = (const cf32 *)in; a.tw = (const cf32 *)tw; a.scale = 1.0f / (float)PL::N;
+            a.mag = (float *)out; a.peakVal = (float *)out; a.peakIdx = (uint32_t *)aux;
+            return launch_tiny<BODY, PL>(a, nFrames, st);
+        }
+    }
     if constexpr (PIPEOF::kPipe) {
         typedef CfftMagBody<PIPEOF::type, INV, MODE, true> BODY;
         if constexpr (!BODY::kCross) {          /* a frame wider than a warp meets through the exchange buffer: direct kernel */
@@ -615,6 +647,9 @@ static int ku_launch(const void *in, void *out, uint64_t nFrames, int inv, const
 }
 static int ku_facts(KernelFacts *f, int flavour)
 {
+    if constexpr (PIPEOF::kTiny) {
+        if (flavour == KF_PIPE) return facts_of_tiny<TinyCfftMagBody<PL, false, SPEC_MAG>, PL>(f);
+    }
     if constexpr (PIPEOF::kPipe) {
         if (flavour == KF_PIPE) return facts_of_pipe<CfftMagBody<PIPEOF::type, false, SPEC_MAG, true>, PIPEOF::type>(f);
     }
@@ -630,14 +665,17 @@ typedef ArithQ31 AR;
 typedef ArithQ15 AR;
 #endif
 typedef PlanCfftFix<AR, KU_N>::type PL;
-struct PIPE { static constexpr bool kHas = false, kPrefer = false; };
+/* the TMA-fed flavour of these units is the thread-per-frame kernel (complex length <= 64) */
+struct PIPE { static constexpr bool kHas = (PL::NP == 1 && PL::T == 1), kPrefer = kHas; };
 #if KU_OP == 5 || KU_OP == 7
+static constexpr bool kKuInverse = false;
 typedef RfftFixFwdBody<PL> BODY;
 static BODY::Args ku_args(const void *in, void *out, const void *tw, const void *aux, int shl1)
 {
     return BODY::Args{(const AR::elem *)in, (AR::elem *)out, (const AR::telem *)tw, (const ci32x4 *)aux, shl1};
 }
 #else
+static constexpr bool kKuInverse = true;
 typedef CfftBody<PL, true, false, false, true> BODY;
 static BODY::Args ku_args(const void *in, void *out, const void *tw, const void *aux, int shl1)
 {
@@ -645,11 +683,30 @@ static BODY::Args ku_args(const void *in, void *out, const void *tw, const void 
 }
 #endif
 /* in -> out (never aliased), tw = the pass-ordered twiddles of the KU_N-point CFFT plan, aux = split coefficients */
-static int ku_launch(const void *in, void *out, uint64_t nFrames, int, const void *tw, const void *aux, int shl1, int, cudaStream_t st)
+/* (templates on the direction only so that the thread-per-frame body is not instantiated for the longer plans) */
+template <bool KI>
+static int fix_go(const void *in, void *out, uint64_t nFrames, const void *tw, const void *aux, int shl1, int flavour, cudaStream_t st)
 {
+    if constexpr (PIPE::kHas) {
+        if (flavour == KF_PIPE && aligned16(in) && aligned16(out)) {
+            typedef TinyRfftFixBody<PL, KI> TBODY;
+            return launch_tiny<TBODY, PL>(typename TBODY::Args{(const AR::elem *)in, (AR::elem *)out, (const AR::telem *)tw, (const ci32x4 *)aux, shl1}, nFrames, st);
+        }
+    }
     return launch<BODY, PL>(ku_args(in, out, tw, aux, shl1), nFrames, st);
 }
-static int ku_facts(KernelFacts *f, int) { return facts_of<BODY, PL>(f); }
+template <bool KI> static int fix_facts(KernelFacts *f, int flavour)
+{
+    if constexpr (PIPE::kHas) {
+        if (flavour == KF_PIPE) return facts_of_tiny<TinyRfftFixBody<PL, KI>, PL>(f);
+    }
+    return facts_of<BODY, PL>(f);
+}
+static int ku_launch(const void *in, void *out, uint64_t nFrames, int, const void *tw, const void *aux, int shl1, int flavour, cudaStream_t st)
+{
+    return fix_go<kKuInverse>(in, out, nFrames, tw, aux, shl1, flavour, st);
+}
+static int ku_facts(KernelFacts *f, int flavour) { return fix_facts<kKuInverse>(f, flavour); }
 typedef PL TWPLAN;
 
 #endif

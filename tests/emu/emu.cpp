@@ -115,6 +115,40 @@ template <class AR, int N> static void cfft_fix_n(void *d, uint64_t n, int inv, 
     else cfft_run<AR, PL, false>((typename AR::elem *)d, n, tw, perm, shl1);
 }
 
+
+/* the body the product uses by default for (type, complex length n): thread per frame for n <= 64 */
+template <class AR, int n>
+static void rfft_fix_run(const void *in, void *out, uint64_t nFrames, int ifft, const void *tw, const ci32x4 *coef, int shl1)
+{
+    typedef typename PlanCfftFix<AR, n>::type PL;
+    typedef typename AR::elem elem;
+    std::vector<typename AR::telem> ordered((size_t)PL::kTwEntries + 1);
+    PL::build_twiddles((const elem *)tw, ordered.data());
+    if constexpr (PL::NP == 1 && PL::T == 1) {
+        if (!ifft) {
+            typedef TinyRfftFixBody<PL, false> BODY;
+            run_batch<PL, BODY>(nFrames, [&](uint64_t f) {
+                return typename BODY::Args{(const elem *)in + f * n, (elem *)out + f * 2 * n, ordered.data(), coef, shl1};
+            });
+        } else {
+            typedef TinyRfftFixBody<PL, true> BODY;
+            run_batch<PL, BODY>(nFrames, [&](uint64_t f) {
+                return typename BODY::Args{(const elem *)in + f * 2 * n, (elem *)out + f * n, ordered.data(), coef, shl1};
+            });
+        }
+    } else if (!ifft) {
+        typedef RfftFixFwdBody<PL> BODY;
+        run_batch<PL, BODY>(nFrames, [&](uint64_t f) {
+            return typename BODY::Args{(const elem *)in + f * n, (elem *)out + f * 2 * n, ordered.data(), coef, shl1};
+        });
+    } else {
+        typedef CfftBody<PL, true, false, false, true> BODY;
+        run_batch<PL, BODY>(nFrames, [&](uint64_t f) {
+            return typename BODY::Args{(const elem *)in + f * 2 * n, (elem *)out + f * n, ordered.data(), nullptr, 0.0f, shl1, coef};
+        });
+    }
+}
+
 #define FOR_ALL_N(X) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096)
 #define FOR_RFFT_NC(X) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048)
 
@@ -192,31 +226,13 @@ int emu_rfft_fix(int type, uint32_t Nreal, const void *in, void *out, uint64_t n
     }
     const int shl1 = __builtin_ctz(L2) & 1;
     switch (L2) {
-#define RUN(AR, n)                                                                                   \
-    {                                                                                                \
-        typedef PlanCfftFix<AR, n>::type PL;                                                         \
-        typedef AR::elem elem;                                                                       \
-        std::vector<AR::telem> ordered((size_t)PL::kTwEntries + 1);                                  \
-        PL::build_twiddles((const elem *)tw, ordered.data());                                        \
-        if (!ifft) {                                                                                 \
-            typedef RfftFixFwdBody<PL> BODY;                                                         \
-            run_batch<PL, BODY>(nFrames, [&](uint64_t f) {                                           \
-                return BODY::Args{(const elem *)in + f * n, (elem *)out + f * 2 * n, ordered.data(), coef.data(), shl1}; \
-            });                                                                                      \
-        } else {                                                                                     \
-            typedef CfftBody<PL, true, false, false, true> BODY;                                     \
-            run_batch<PL, BODY>(nFrames, [&](uint64_t f) {                                           \
-                return BODY::Args{(const elem *)in + f * 2 * n, (elem *)out + f * n, ordered.data(), nullptr, 0.0f, shl1, coef.data()}; \
-            });                                                                                      \
-        }                                                                                            \
-    }
 #define CASE(n)                                                     \
     case n:                                                         \
-        if (type == 1) RUN(ArithQ31, n) else RUN(ArithQ15, n)       \
+        if (type == 1) rfft_fix_run<ArithQ31, n>(in, out, nFrames, ifft, tw, coef.data(), shl1); \
+        else rfft_fix_run<ArithQ15, n>(in, out, nFrames, ifft, tw, coef.data(), shl1);           \
         return 0;
         FOR_ALL_N(CASE)
 #undef CASE
-#undef RUN
     default: return -1;
     }
 }
@@ -229,7 +245,7 @@ int emu_cfft_mag(uint32_t N, const float *in, float *mag, uint64_t nFrames, int 
 #define RUNM(n, INV, MODE)                                                                         \
     {                                                                                              \
         typedef PlanCfftF32<n>::type PL;                                                           \
-        typedef CfftMagBody<PL, INV, MODE> BODY;                                                   \
+        typedef std::conditional<(PL::NP == 1 && PL::T == 1), TinyCfftMagBody<PL, INV, MODE>, CfftMagBody<PL, INV, MODE>>::type BODY; \
         std::vector<cf32> ordered((size_t)PL::kTwEntries + 1);                                     \
         PL::build_twiddles((const cf32 *)tw, ordered.data());                                      \
         run_batch<PL, BODY>(nFrames, [&](uint64_t f) {                                             \
