@@ -81,7 +81,9 @@ FIXPLAN(256,  16,  8,   4, 1, PF(ST_FIRST4, ST_MID4), PF(ST_MID4, ST_LAST4))
 /* N >= 512: three passes of 16 points per thread.  Two passes of 32/64 points per thread (the f32
  * recipe) were measured 15-45 % SLOWER here: a fixed-point pass cannot factor its twiddles (the
  * reference multiplies by specific table entries, truncating), so a radix-64 pass loads 63 of them
- * per thread and the low-occupancy kernel waits on those loads */
+ * per thread and the low-occupancy kernel waits on those loads.  Three passes with 32 points per thread (half the
+ * threads and barriers: T = 32 / 64 / 128 for N = 1024 / 2048 / 4096) were also measured slower, by 8-25 %
+ * (profiles/r1_e_notes.md): occupancy, not barrier count, is what these kernels live on */
 FIXPLAN(512,  32,  4,   4, 1, PF(ST_PRE2, ST_FIRST4), PF(ST_MID4, ST_MID4), PF(ST_LAST4))
 FIXPLAN(1024, 64,  2,   4, 1, PF(ST_FIRST4, ST_MID4), PF(ST_MID4, ST_MID4), PF(ST_LAST4))
 FIXPLAN(2048, 128, 1,   4, 1, PF(ST_PRE2, ST_FIRST4), PF(ST_MID4, ST_MID4), PF(ST_MID4, ST_LAST4))
