@@ -104,7 +104,7 @@ template <class PL, bool INV, bool PERM = false, bool STAGED = false, bool RIFFT
         a.out += frame * (uint64_t)N;
         return a;
     }
-    static constexpr bool kStaged = STAGED;
+    static constexpr bool kStaged = STAGED, kInv = INV;
 
     static FFT_HD void gload(Regs &r, const Args &a, int i)
     {

@@ -15,6 +15,19 @@
 #if defined(KU_N) && KU_N == 32
 #define FFT_HI32_XU 1        /* q31 high products as IMAD.HI for this length (fft_arith.cuh: hi32) */
 #endif
+/* Launch bounds of the direct kernel: (threads, 1) lets ptxas spend registers (12-60 more) instead of chasing resident
+ * CTAs; (threads, 0) = no second bound = its occupancy heuristic.  Chosen per (op, length) from an A/B sweep of all
+ * units (profiles/r1_e_notes.md): free registers win for the f32 units, cfft_q31 up to N = 2048 (+12 points at 512),
+ * rfft_q31 forward up to complex 256 and rfft_q31 inverse; they lose 2-13 points for the 256-thread CTAs of N = 4096
+ * and for the q15 real FFT, and are neutral for cfft_q15. */
+#ifndef KU_MINB
+#if KU_OP == 0 || KU_OP == 3 || KU_OP == 4 || KU_OP == 9 || KU_OP == 6 || (KU_OP == 1 && KU_N <= 2048) || (KU_OP == 5 && KU_N <= 256)
+#define KU_MINB 1
+#else
+#define KU_MINB 0
+#endif
+#endif
+
 #include "../../../include/cmsisdsp_cuda.h"
 #include "fft_plans.cuh"
 #include "kernel_entry.h"
@@ -46,7 +59,7 @@ __device__ __forceinline__ void run_phases(typename BODY::Regs &r, const typenam
 }
 
 template <class BODY, class PL>
-__global__ void __launch_bounds__(PL::kThreads) frame_kernel(typename BODY::Args base, uint64_t nFrames)
+__global__ void __launch_bounds__(PL::kThreads, KU_MINB) frame_kernel(typename BODY::Args base, uint64_t nFrames)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typedef typename BODY::xelem xelem;                  /* shared-memory exchange element */

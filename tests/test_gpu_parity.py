@@ -288,6 +288,14 @@ def test_direct_and_pipelined_flavours_agree_bit_for_bit():
                         out.append(cd.cfft_batch("f32", N, x, ifft, bitrev))
                     assert np.array_equal(out[0], out[1]), (N, frames, ifft, bitrev)
                     assert relrms(out[1], oracle().cfft("f32", N, x, ifft, bitrev, threads=NT)) <= F32_TOL
+            for kind in ("q31", "q15"):                      # fixed point: persistent TMA-fed flavour of the multi-pass plans
+                for N in (128, 256, 512, 1024, 2048, 4096):
+                    xi = cfft_input(kind, N, frames=max(frames, 6), seed=N + frames)[:max(frames, 1)] if frames >= 6 else cfft_input(kind, N, frames=6, seed=N)[:frames]
+                    for ifft, bitrev in ((0, 1), (1, 0)):
+                        want = oracle().cfft(kind, N, xi, ifft, bitrev, threads=NT)
+                        for flavour in (0, 1):
+                            assert cu.cmsisdsp_cuda_set_kernel_flavour(flavour) == 0
+                            assert np.array_equal(cd.cfft_batch(kind, N, xi, ifft, bitrev), want), (kind, N, frames, ifft, bitrev, flavour)
             for N in (512, 1024, 2048, 4096):
                 xr = rfft_input(N, frames=frames, seed=N + frames)
                 for ifft in (0, 1):
