@@ -58,6 +58,21 @@ arm_rfft_instance_q15 = _mk_rfft_fix_instance(C.c_int16, arm_cfft_instance_q15)
 RFIX_INSTANCE = {"q31": arm_rfft_instance_q31, "q15": arm_rfft_instance_q15}
 
 
+def _mk_radix_instance(scalar, with_oneby):
+    class Inst(C.Structure):
+        _fields_ = [("fftLen", C.c_uint16), ("ifftFlag", C.c_uint8), ("bitReverseFlag", C.c_uint8),
+                    ("pTwiddle", C.POINTER(scalar)), ("pBitRevTable", C.POINTER(C.c_uint16)),
+                    ("twidCoefModifier", C.c_uint16), ("bitRevFactor", C.c_uint16)] + ([("onebyfftLen", C.c_float)] if with_oneby else [])
+    return Inst
+
+
+# deprecated radix-4 / radix-2 instance API (arm_cfft_radix2_instance_f32 has the same fields as the radix-4 one)
+arm_cfft_radix4_instance_f32 = _mk_radix_instance(C.c_float, True)
+arm_cfft_radix4_instance_q31 = _mk_radix_instance(C.c_int32, False)
+arm_cfft_radix4_instance_q15 = _mk_radix_instance(C.c_int16, False)
+RADIX_INSTANCE = {"f32": arm_cfft_radix4_instance_f32, "q31": arm_cfft_radix4_instance_q31, "q15": arm_cfft_radix4_instance_q15}
+
+
 class arm_mfcc_instance_f32(C.Structure):
     _fields_ = [("dctCoefs", C.POINTER(C.c_float)), ("filterCoefs", C.POINTER(C.c_float)),
                 ("windowCoefs", C.POINTER(C.c_float)), ("filterPos", C.POINTER(C.c_uint32)),
@@ -144,6 +159,14 @@ def lib():
         f.argtypes, f.restype = [C.POINTER(arm_cfft_instance_f32), C.c_void_p, C.c_void_p, u32, u8], i
     L.arm_cfft_peak_batch_f32.argtypes = [C.POINTER(arm_cfft_instance_f32), C.c_void_p, C.c_void_p, C.c_void_p, u32, u8]
     L.arm_cfft_peak_batch_f32.restype = i
+    for name, k in (("radix4", "f32"), ("radix4", "q31"), ("radix4", "q15"), ("radix2", "f32")):
+        inst = RADIX_INSTANCE[k]
+        f = getattr(L, f"arm_cfft_{name}_init_{k}")
+        f.argtypes, f.restype = [C.POINTER(inst), u16, u8, u8], i
+        f = getattr(L, f"arm_cfft_{name}_{k}")
+        f.argtypes, f.restype = [C.POINTER(inst), C.c_void_p], None
+        f = getattr(L, f"arm_cfft_{name}_batch_{k}")
+        f.argtypes, f.restype = [C.POINTER(inst), C.c_void_p, u32], i
     for k, inst in RFIX_INSTANCE.items():
         f = getattr(L, f"arm_rfft_init_{k}")
         f.argtypes, f.restype = [C.POINTER(inst), u32, u32, u32], i
@@ -254,6 +277,20 @@ def cfft_peak_batch(N, x, ifft=0):
     if st != ARM_MATH_SUCCESS:
         raise RuntimeError(f"arm_cfft_peak_batch_f32 -> {st}: {last_error()}")
     return val, idx
+
+
+def cfft_radix_batch(kind, radix, N, x, ifft=0, bitrev=1):
+    """deprecated arm_cfft_radix{4,2}_* instance API, batched: x [..., 2N] -> transformed copy"""
+    y = np.ascontiguousarray(x, dtype=NP_DTYPE[kind]).copy()
+    assert y.size % (2 * N) == 0
+    S = RADIX_INSTANCE[kind]()
+    st = getattr(lib(), f"arm_cfft_radix{radix}_init_{kind}")(C.byref(S), N, int(ifft), int(bitrev))
+    if st != ARM_MATH_SUCCESS:
+        raise ValueError(f"arm_cfft_radix{radix}_init_{kind}({N}) -> {st}")
+    st = getattr(lib(), f"arm_cfft_radix{radix}_batch_{kind}")(C.byref(S), y.ctypes.data, y.size // (2 * N))
+    if st != ARM_MATH_SUCCESS:
+        raise RuntimeError(f"arm_cfft_radix{radix}_batch_{kind} -> {st}: {last_error()}")
+    return y
 
 
 def rfft_fix_instance(kind, N, ifft=0, bitrev=1):

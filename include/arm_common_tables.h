@@ -71,6 +71,11 @@ extern const uint16_t armBitRevIndexTable_fixed_1024[ARMBITREVINDEXTABLE_FIXED_1
 extern const uint16_t armBitRevIndexTable_fixed_2048[ARMBITREVINDEXTABLE_FIXED_2048_TABLE_LENGTH];
 extern const uint16_t armBitRevIndexTable_fixed_4096[ARMBITREVINDEXTABLE_FIXED_4096_TABLE_LENGTH];
 
+/* deprecated radix-2 / radix-4 instance API: one bit reversal table for every length, the 4096-point twiddles
+ * read with a stride (Include/arm_common_tables.h:52,78) */
+extern const uint16_t armBitRevTable[1024];
+#define twiddleCoef twiddleCoef_4096
+
 /* split-stage coefficients of arm_rfft_q31 / arm_rfft_q15 (Include/arm_common_tables.h:241-245) */
 extern const q31_t realCoefAQ31[8192];
 extern const q31_t realCoefBQ31[8192];

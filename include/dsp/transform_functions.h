@@ -107,6 +107,61 @@ arm_status arm_rfft_fast_init_4096_f32(arm_rfft_fast_instance_f32 *S);
 arm_status arm_rfft_fast_init_f32(arm_rfft_fast_instance_f32 *S, uint16_t fftLen);
 void arm_rfft_fast_f32(const arm_rfft_fast_instance_f32 *S, float32_t *p, float32_t *pOut, uint8_t ifftFlag);
 
+/* ---------------------------------------------------------------- deprecated radix-4 / radix-2 instance API
+ * (Include/dsp/transform_functions.h:107-266; direction and bit-reversal flag live in the instance).  Thin adapters
+ * over the same kernels: the reference's arm_cfft_radix4_q31 / _q15 ARE arm_cfft_q31 / _q15 for fftLen = 4^m (same
+ * butterflies, same table values read with a stride: bit-identical, checked against the compiled reference), and the
+ * f32 variants compute the same DFT (relative RMS vs the reference's radix-4 / radix-2 code <= 2e-6).
+ * Lengths: radix-4 16, 64, 256, 1024, 4096; radix-2 f32 16..4096.  The f32 adapters need bitReverseFlag = 1 (the raw
+ * order of a radix-4 / radix-2 pass differs from arm_cfft_f32's).  The fixed-point radix-2 functions are a different
+ * algorithm (other per-stage scaling) and are not provided. */
+typedef struct
+{
+          uint16_t  fftLen;
+          uint8_t   ifftFlag;
+          uint8_t   bitReverseFlag;
+    const q15_t    *pTwiddle;            /* twiddleCoef_4096_q15, read with stride twidCoefModifier */
+    const uint16_t *pBitRevTable;        /* &armBitRevTable[bitRevFactor - 1] */
+          uint16_t  twidCoefModifier;
+          uint16_t  bitRevFactor;
+} arm_cfft_radix4_instance_q15;
+typedef struct
+{
+          uint16_t  fftLen;
+          uint8_t   ifftFlag;
+          uint8_t   bitReverseFlag;
+    const q31_t    *pTwiddle;
+    const uint16_t *pBitRevTable;
+          uint16_t  twidCoefModifier;
+          uint16_t  bitRevFactor;
+} arm_cfft_radix4_instance_q31;
+typedef struct
+{
+          uint16_t   fftLen;
+          uint8_t    ifftFlag;
+          uint8_t    bitReverseFlag;
+    const float32_t *pTwiddle;
+    const uint16_t  *pBitRevTable;
+          uint16_t   twidCoefModifier;
+          uint16_t   bitRevFactor;
+          float32_t  onebyfftLen;
+} arm_cfft_radix4_instance_f32;
+typedef arm_cfft_radix4_instance_f32 arm_cfft_radix2_instance_f32;     /* same fields (transform_functions.h:215-225) */
+
+arm_status arm_cfft_radix4_init_q15(arm_cfft_radix4_instance_q15 *S, uint16_t fftLen, uint8_t ifftFlag, uint8_t bitReverseFlag);
+arm_status arm_cfft_radix4_init_q31(arm_cfft_radix4_instance_q31 *S, uint16_t fftLen, uint8_t ifftFlag, uint8_t bitReverseFlag);
+arm_status arm_cfft_radix4_init_f32(arm_cfft_radix4_instance_f32 *S, uint16_t fftLen, uint8_t ifftFlag, uint8_t bitReverseFlag);
+arm_status arm_cfft_radix2_init_f32(arm_cfft_radix2_instance_f32 *S, uint16_t fftLen, uint8_t ifftFlag, uint8_t bitReverseFlag);
+void arm_cfft_radix4_q15(const arm_cfft_radix4_instance_q15 *S, q15_t *pSrc);
+void arm_cfft_radix4_q31(const arm_cfft_radix4_instance_q31 *S, q31_t *pSrc);
+void arm_cfft_radix4_f32(const arm_cfft_radix4_instance_f32 *S, float32_t *pSrc);
+void arm_cfft_radix2_f32(const arm_cfft_radix2_instance_f32 *S, float32_t *pSrc);
+/* B200 extension: nFrames contiguous frames */
+arm_status arm_cfft_radix4_batch_q15(const arm_cfft_radix4_instance_q15 *S, q15_t *p, uint32_t nFrames);
+arm_status arm_cfft_radix4_batch_q31(const arm_cfft_radix4_instance_q31 *S, q31_t *p, uint32_t nFrames);
+arm_status arm_cfft_radix4_batch_f32(const arm_cfft_radix4_instance_f32 *S, float32_t *p, uint32_t nFrames);
+arm_status arm_cfft_radix2_batch_f32(const arm_cfft_radix2_instance_f32 *S, float32_t *p, uint32_t nFrames);
+
 /* ---------------------------------------------------------------- q15 / q31 RFFT
  * Instance, init and exec are the reference's generic (non-Neon, non-MVE) branch
  * (Include/dsp/transform_functions.h:508-521,566-617 q15, :655-668,694-745 q31).  fftLenReal in {32..8192}.

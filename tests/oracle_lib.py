@@ -97,6 +97,16 @@ class _Lib:
         fn(N, src.ctypes.data, mag.ctypes.data, val.ctypes.data, idx.ctypes.data, frames, int(ifft), int(squared))
         return (val, idx) if peak else mag
 
+    def cfft_radix(self, kind, radix, N, x, ifft=0, bitrev=1):
+        """the reference's deprecated arm_cfft_radix{4,2}_* (compiled reference only)"""
+        dt = {"f32": np.float32, "q31": np.int32, "q15": np.int16}[kind]
+        y = np.ascontiguousarray(x, dtype=dt).copy()
+        fn = self._fn("cfft_radix_batch")
+        fn.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_uint64, C.c_int, C.c_int]
+        fn.restype = C.c_int
+        assert fn({"f32": 0, "q31": 1, "q15": 2}[kind], radix, N, y.ctypes.data, y.size // (2 * N), int(ifft), int(bitrev)) == 0
+        return y
+
     def real_coef(self, kind, b):
         return np.ctypeslib.as_array(self._fn(f"real_coef_{kind}")(int(b)), shape=(8192,)).copy()
 

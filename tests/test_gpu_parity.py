@@ -311,6 +311,37 @@ def test_direct_and_pipelined_flavours_agree_bit_for_bit():
     assert cu.cmsisdsp_cuda_set_kernel_flavour(7) != 0
 
 
+# ------------------------------------------------------------------ deprecated radix-4 / radix-2 instance API
+
+def test_deprecated_radix_api_against_the_compiled_reference():
+    """arm_cfft_radix4_{q31,q15}: memcmp-identical to the reference's own deprecated functions (both flags, both
+    directions); arm_cfft_radix4_f32 / arm_cfft_radix2_f32: relative RMS <= 2e-6; f32 with bitReverseFlag = 0 refused"""
+    from oracle_lib import ref
+    if ref() is None:
+        pytest.skip("oracle/_ref not built")
+    for kind in ("q31", "q15"):
+        for N in (16, 64, 256, 1024, 4096):
+            x = cfft_input(kind, N, frames=41, seed=N)
+            for ifft in (0, 1):
+                for bitrev in (1, 0):
+                    assert np.array_equal(cd.cfft_radix_batch(kind, 4, N, x, ifft, bitrev), ref().cfft_radix(kind, 4, N, x, ifft, bitrev)), (kind, N, ifft, bitrev)
+    for radix, lens in ((4, (16, 64, 256, 1024, 4096)), (2, LENGTHS)):
+        for N in lens:
+            x = cfft_input("f32", N, frames=41, seed=N)
+            for ifft in (0, 1):
+                assert relrms(cd.cfft_radix_batch("f32", radix, N, x, ifft, 1), ref().cfft_radix("f32", radix, N, x, ifft, 1)) <= F32_TOL, (radix, N, ifft)
+    with pytest.raises(RuntimeError):
+        cd.cfft_radix_batch("f32", 4, 64, np.zeros(128, dtype=np.float32), 0, 0)
+    # legacy single-frame call
+    S = cd.arm_cfft_radix4_instance_q15()
+    L = cd.lib()
+    assert L.arm_cfft_radix4_init_q15(C.byref(S), 256, 0, 1) == 0
+    x = cfft_input("q15", 256, frames=1, seed=5).reshape(-1)
+    y = x.copy()
+    L.arm_cfft_radix4_q15(C.byref(S), y.ctypes.data)
+    assert L.arm_cuda_last_status() == 0 and np.array_equal(y, oracle().cfft("q15", 256, x, 0, 1).reshape(-1))
+
+
 # ------------------------------------------------------------------ fused spectrum epilogues (SURVEY 8(f) rank 3)
 
 @pytest.mark.parametrize("N", LENGTHS)

@@ -61,6 +61,37 @@ def test_real_coef_tables_and_rfft_fix_instances(kind):
         assert bytes(S2) == bytes(cd.rfft_fix_instance(kind, N, 1, 1))
 
 
+def test_deprecated_radix_api_instances():
+    """arm_cfft_radix4_init_* / arm_cfft_radix2_init_f32 fill the instance like the reference (strided 4096-point twiddles,
+    one shared bit reversal table); armBitRevTable generated == the compiled reference's"""
+    L = cd.lib()
+    tab = np.ctypeslib.as_array((C.c_uint16 * 1024).in_dll(L, "armBitRevTable")).copy()
+    if ref() is not None:
+        fn = ref().lib.ref_arm_bit_rev_table
+        fn.restype = C.POINTER(C.c_uint16)
+        assert np.array_equal(tab, np.ctypeslib.as_array(fn(), shape=(1024,)))
+        for name, t in (("cfft_radix4_instance_f32", cd.arm_cfft_radix4_instance_f32), ("cfft_radix4_instance_q31", cd.arm_cfft_radix4_instance_q31),
+                        ("cfft_radix4_instance_q15", cd.arm_cfft_radix4_instance_q15)):
+            f = getattr(ref().lib, f"ref_sizeof_{name}")
+            f.restype = C.c_uint32
+            assert f() == C.sizeof(t)
+    for name, kind, lens in (("radix4", "f32", (16, 64, 256, 1024, 4096)), ("radix4", "q31", (16, 64, 256, 1024, 4096)),
+                             ("radix4", "q15", (16, 64, 256, 1024, 4096)), ("radix2", "f32", LENGTHS)):
+        init = getattr(L, f"arm_cfft_{name}_init_{kind}")
+        for N in lens:
+            S = cd.RADIX_INSTANCE[kind]()
+            assert init(C.byref(S), N, 1, 0) == cd.ARM_MATH_SUCCESS
+            assert (S.fftLen, S.ifftFlag, S.bitReverseFlag, S.twidCoefModifier, S.bitRevFactor) == (N, 1, 0, 4096 // N, 4096 // N)
+            assert S.pBitRevTable[0] == tab[4096 // N - 1]
+            big = cd.preset(kind, 4096)
+            assert C.addressof(S.pTwiddle.contents) == C.addressof(big.pTwiddle.contents)
+            if kind == "f32":
+                assert S.onebyfftLen == np.float32(1.0 / N)
+        S = cd.RADIX_INSTANCE[kind]()
+        for bad in (0, 8, 24, 8192) + ((32, 128, 2048) if name == "radix4" else ()):
+            assert init(C.byref(S), bad, 0, 1) == cd.ARM_MATH_ARGUMENT_ERROR
+
+
 def test_struct_layouts_match_reference():
     # SURVEY.md section 8(a) A1/A2/A15: 32 / 32 / 32 / 48 bytes on LP64
     assert C.sizeof(cd.arm_cfft_instance_f32) == 32
@@ -113,8 +144,8 @@ def test_shared_objects_export_every_declared_symbol():
     names = _declared_functions(os.path.join(ROOT, "include", "dsp", "transform_functions.h"))
     # 3x(9 per-length inits + init + exec) + rfft (8+1+1) + 4 batch + last_status + mfcc (8+1+1+1)
     # + rfft_q31/q15 (init, exec, batch each; their per-length inits are declared through a macro)
-    # + 3 fused spectrum epilogues (mag, mag squared, peak)
-    assert len(names) == 68
+    # + 3 fused spectrum epilogues (mag, mag squared, peak) + deprecated radix-4/2 API (4 x (init, exec, batch))
+    assert len(names) == 80
     for name in names:
         assert hasattr(fr, name), name
     for N in RFIX_LENGTHS:
