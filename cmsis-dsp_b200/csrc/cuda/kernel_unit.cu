@@ -33,6 +33,18 @@
 #include "kernel_entry.h"
 #include "bulk_copy.cuh"
 
+/* Resident CTAs per SM the pipelined kernel's register allocation aims at.  Three (a cap of 168 registers, no spills)
+ * pays where the kernel is not HBM-bound at 8 warps per SM: the magnitude / peak epilogues at N >= 2048 (+5..8 points)
+ * and the forward rfft of complex length 1024 (79 -> 84 %); the plain cfft_f32 at those lengths is HBM-bound either way
+ * (N = 4096: 91.6 -> 89.0 %, kept at two). */
+#ifndef KU_PIPE_MINB
+#if (KU_OP == 9 && KU_N >= 2048) || (KU_OP == 3 && KU_N == 1024)
+#define KU_PIPE_MINB 3
+#else
+#define KU_PIPE_MINB 2
+#endif
+#endif
+
 #if !defined(KU_OP) || !defined(KU_N)
 #error "compile with -DKU_OP=<0..9> -DKU_N=<length>"
 #endif
@@ -108,7 +120,7 @@ template <class BODY, class PL> struct PipeSmem {
      * four CTAs costs 5-30 % (the rfft epilogues want > 200 registers; a spill is ruinous here because
      * with this kernel's shared-memory carve-out next to no L1 is left, so every reload is an L2 round
      * trip), and the extra warps buy nothing once the loads are off the warps' critical path. */
-    static constexpr int kMinBlocks = 2;
+    static constexpr int kMinBlocks = KU_PIPE_MINB;
 };
 
 /* barrier among the threads of one unit */

@@ -311,6 +311,43 @@ def test_direct_and_pipelined_flavours_agree_bit_for_bit():
     assert cu.cmsisdsp_cuda_set_kernel_flavour(7) != 0
 
 
+# ------------------------------------------------------------------ call-compatible Python surface
+
+def test_python_wrapper_compatible_surface():
+    """`import cmsisdsp_b200.compat as dsp` takes the call sequences written for the reference's PythonWrapper
+    (cmsisdsp_transform.c:2074-2545): instance(), init(S, ...), exec(S, x, ...) -> array"""
+    import cmsisdsp_b200.compat as dsp
+    from oracle_lib import mfcc_config
+    x = cfft_input("f32", 256, frames=3, seed=1)
+    S = dsp.arm_cfft_instance_f32()
+    assert dsp.arm_cfft_init_f32(S, 256) == 0 and dsp.arm_cfft_init_f32(dsp.arm_cfft_instance_f32(), 100) == cd.ARM_MATH_ARGUMENT_ERROR
+    assert relrms(dsp.arm_cfft_f32(S, x[0], 0, 1), oracle().cfft("f32", 256, x[0], 0, 1).reshape(-1)) <= F32_TOL   # one frame
+    assert relrms(dsp.arm_cfft_f32(S, x, 1, 1), oracle().cfft("f32", 256, x, 1, 1).reshape(-1)) <= F32_TOL    # three frames, one call
+    for kind in ("q31", "q15"):
+        Si = getattr(dsp, f"arm_cfft_instance_{kind}")()
+        assert getattr(dsp, f"arm_cfft_init_{kind}")(Si, 1024) == 0
+        xi = cfft_input(kind, 1024, frames=7, seed=2)
+        assert np.array_equal(getattr(dsp, f"arm_cfft_{kind}")(Si, xi, 0, 1), oracle().cfft(kind, 1024, xi, 0, 1).reshape(-1))
+        Sr = getattr(dsp, f"arm_rfft_instance_{kind}")()
+        assert getattr(dsp, f"arm_rfft_init_{kind}")(Sr, 512, 0, 1) == 0
+        xr = cfft_input(kind, 256, frames=6, seed=3)
+        spec = getattr(dsp, f"arm_rfft_{kind}")(Sr, xr)
+        assert np.array_equal(spec, oracle().rfft_fix(kind, 512, xr, 0, 1).reshape(-1))
+        Sv = getattr(dsp, f"arm_rfft_instance_{kind}")()
+        assert getattr(dsp, f"arm_rfft_init_{kind}")(Sv, 512, 1, 1) == 0
+        one = spec[:2 * 512]
+        assert np.array_equal(getattr(dsp, f"arm_rfft_{kind}")(Sv, one[:512 + 2]), oracle().rfft_fix(kind, 512, one, 1, 1).reshape(-1))
+    R = dsp.arm_rfft_fast_instance_f32()
+    assert dsp.arm_rfft_fast_init_f32(R, 1024) == 0
+    xr = rfft_input(1024, frames=5, seed=4)
+    assert relrms(dsp.arm_rfft_fast_f32(R, xr, 0), oracle().rfft(1024, xr, 0).reshape(-1)) <= F32_TOL
+    cfg = mfcc_config(512)
+    M = dsp.arm_mfcc_instance_f32()
+    assert dsp.arm_mfcc_init_f32(M, 512, 20, 13, cfg["dct"], cfg["pos"], cfg["len"], cfg["coefs"], cfg["window"]) == 0
+    sig = rfft_input(512, frames=9, seed=5).reshape(-1)
+    _mfcc_ok(dsp.arm_mfcc_f32(M, sig, None).reshape(9, 13), oracle().mfcc(cfg, sig))
+
+
 # ------------------------------------------------------------------ deprecated radix-4 / radix-2 instance API (SURVEY 8(f) rank 4)
 
 def test_deprecated_radix_api_against_the_compiled_reference():
