@@ -33,12 +33,17 @@
 #include "kernel_entry.h"
 #include "bulk_copy.cuh"
 
-/* Resident CTAs per SM the pipelined kernel's register allocation aims at.  Three (a cap of 168 registers, no spills)
- * pays where the kernel is not HBM-bound at 8 warps per SM: the magnitude / peak epilogues at N >= 2048 (+5..8 points)
- * and the forward rfft of complex length 1024 (79 -> 84 %); the plain cfft_f32 at those lengths is HBM-bound either way
- * (N = 4096: 91.6 -> 89.0 %, kept at two). */
+/* Resident CTAs per SM the pipelined kernel's register allocation aims at (the second launch bound; it changes ptxas'
+ * register budget AND its schedule).  Chosen per (op, length) from an A/B/C sweep of 2 / 3 / 4 over every pipelined unit
+ * (profiles/r1_e_notes.md).  Default two: the rfft epilogues want > 200 registers and the plain cfft_f32 is HBM-bound
+ * either way.  Three: forward rfft of complex length 2048 -- the bench kernel: same 3 CTAs/SM and 168 instead of 167
+ * registers, but 0.380 -> 0.345 ms (86.5 -> 95.2 % of the HBM peak) -- and 1024 (79 -> 84 %), magnitude / peak epilogues at
+ * N >= 2048 (+5..8 points).  Four: forward rfft of complex length 256 (89.8 -> 94.0 %), epilogues at N = 1024 (peak
+ * 71.5 -> 75.9 %).  Four at N >= 2048 spills and loses 30-40 points. */
 #ifndef KU_PIPE_MINB
-#if (KU_OP == 9 && KU_N >= 2048) || (KU_OP == 3 && KU_N == 1024)
+#if (KU_OP == 3 && KU_N == 256) || (KU_OP == 9 && KU_N == 1024)
+#define KU_PIPE_MINB 4
+#elif (KU_OP == 3 && KU_N >= 1024) || (KU_OP == 9 && KU_N >= 2048)
 #define KU_PIPE_MINB 3
 #else
 #define KU_PIPE_MINB 2

@@ -16,7 +16,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIBDIR = os.path.normpath(os.path.join(_HERE, "..", "..", "lib"))
+# CMSISDSP_B200_LIBDIR: an alternative build of the two libraries (A/B measurements of compile-time choices)
+LIBDIR = os.environ.get("CMSISDSP_B200_LIBDIR") or os.path.normpath(os.path.join(_HERE, "..", "..", "lib"))
 
 LENGTHS = [16, 32, 64, 128, 256, 512, 1024, 2048, 4096]
 RLENGTHS = [32, 64, 128, 256, 512, 1024, 2048, 4096]
