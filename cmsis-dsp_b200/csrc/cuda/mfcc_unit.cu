@@ -204,7 +204,7 @@ template <int NC> struct MfccPipe {
     static constexpr int kQuad = (T >= 4) ? 4 : 1;                                         /* lanes summed by shuffles before a partial sum is stored */
     static constexpr int kPartStride = T / kQuad + 1;                                      /* per-filter partial sums, conflict-free both ways */
     /* resident CTAs per SM the register allocation aims at (E <= 32: 4 CTAs = 16 warps; above: shared memory allows 2) */
-    static constexpr int kMinBlocks = (E <= 32) ? 4 : 2;
+    static constexpr int kMinBlocks = (E <= 32) ? (NC >= 256 ? 3 : 4) : 2;      /* measured: 3 is 2.5 % faster than 4 at fftLen 512 / 1024 (same 128 registers) */
     static constexpr int kHoistVals = (int)(sizeof(typename BODY::Hoist) / sizeof(cf32));
     /* byte offsets inside the CTA's dynamic shared memory */
     static constexpr int oBuf = 0;
