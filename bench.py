@@ -56,6 +56,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.stop_flag = index, threading.Event()
         self.sm, self.sm_max, self.reasons = [], None, set()
+        self.mem, self.power = [], []
         self.nvml = None
         try:
             import pynvml
@@ -69,6 +70,11 @@ class ClockSampler(threading.Thread):
     def _sample_nvml(self):
         n = self.nvml
         self.sm.append(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+        try:                                          # HBM clock and board power: the bench is HBM-bound
+            self.mem.append(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_MEM))
+            self.power.append(n.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+        except Exception:
+            pass
         r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
         for name, bit in (("hw_slowdown", n.nvmlClocksThrottleReasonHwSlowdown),
                           ("hw_thermal_slowdown", n.nvmlClocksThrottleReasonHwThermalSlowdown),
@@ -98,8 +104,10 @@ class ClockSampler(threading.Thread):
 
     def summary(self):
         sm = sorted(self.sm)
+        mem = sorted(self.mem)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.sm_max,
-                "reasons": sorted(self.reasons), "samples": len(sm), "source": "nvml" if self.nvml else "nvidia-smi"}
+                "reasons": sorted(self.reasons), "samples": len(sm), "source": "nvml" if self.nvml else "nvidia-smi",
+                "mem_mhz": mem[len(mem) // 2] if mem else None, "power_w_max": max(self.power) if self.power else None}
 
 
 def cpu_baseline_subprocess(frames):
