@@ -262,6 +262,26 @@ def run_cuda(args, rank, world, local_rank):
                 "fwd_ms": fwd_ms, "inv_ms": inv_ms,
                 "fwd_gbs": bytes_per_launch / (fwd_ms * 1e-3) / 1e9, "inv_gbs": bytes_per_launch / (inv_ms * 1e-3) / 1e9,
                 "algorithmic_bytes_per_launch": bytes_per_launch}
+    # the same number of back-to-back launches of a plain device copy of the same size, timed the same way: what the
+    # memory system sustains over a region this long (MEASURED_PEAKS.json's figure is a best-of-10 burst)
+    try:
+        ca, cb = x.view(-1), y.view(-1)
+        for _ in range(3):
+            cb.copy_(ca)
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(2 * args.steps):
+            cb.copy_(ca)
+        c1.record()
+        torch.cuda.synchronize()
+        copy_gbs = 2 * args.steps * 2 * ca.numel() * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9
+        roofline["sustained_copy_gbs"] = copy_gbs
+        roofline["frac_of_sustained_copy"] = achieved / copy_gbs
+        roofline["sustained_copy_how"] = f"{2 * args.steps} back-to-back torch copy_ launches of 1 GiB f32 (read + write bytes), CUDA events"
+    except Exception as e:                                # diagnostic only
+        roofline["sustained_copy_gbs"] = None
+        roofline["sustained_copy_how"] = f"failed: {e}"
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
         with open(tr) as f:
@@ -323,7 +343,7 @@ def run_cuda(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
