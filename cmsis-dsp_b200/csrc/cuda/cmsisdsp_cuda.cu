@@ -47,14 +47,14 @@ void shim_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 #define DECL(op, n) extern const KernelEntry ku_entry_##op##_##n;
 namespace b200fft {
 FOR_ALL_N(DECL, 0) FOR_ALL_N(DECL, 1) FOR_ALL_N(DECL, 2) FOR_RFFT_NC(DECL, 3) FOR_RFFT_NC(DECL, 4)
-FOR_ALL_N(DECL, 5) FOR_ALL_N(DECL, 6) FOR_ALL_N(DECL, 7) FOR_ALL_N(DECL, 8) FOR_ALL_N(DECL, 9)
+FOR_ALL_N(DECL, 5) FOR_ALL_N(DECL, 6) FOR_ALL_N(DECL, 7) FOR_ALL_N(DECL, 8) FOR_ALL_N(DECL, 9) FOR_ALL_N(DECL, 10)
 }
 #undef DECL
 #define REF(op, n) &ku_entry_##op##_##n,
 /* [op][index of the COMPLEX length 16..4096]; the rfft ops have no 4096-point complex plan */
 static const KernelEntry *const kEntries[OP_COUNT][9] = {
     {FOR_ALL_N(REF, 0)}, {FOR_ALL_N(REF, 1)}, {FOR_ALL_N(REF, 2)}, {FOR_RFFT_NC(REF, 3) nullptr}, {FOR_RFFT_NC(REF, 4) nullptr},
-    {FOR_ALL_N(REF, 5)}, {FOR_ALL_N(REF, 6)}, {FOR_ALL_N(REF, 7)}, {FOR_ALL_N(REF, 8)}, {FOR_ALL_N(REF, 9)}};
+    {FOR_ALL_N(REF, 5)}, {FOR_ALL_N(REF, 6)}, {FOR_ALL_N(REF, 7)}, {FOR_ALL_N(REF, 8)}, {FOR_ALL_N(REF, 9)}, {FOR_ALL_N(REF, 10)}};
 #undef REF
 
 static const uint32_t kLens[9] = {16, 32, 64, 128, 256, 512, 1024, 2048, 4096};
@@ -102,7 +102,7 @@ struct DevPlan {
     uint16_t *perm = nullptr;     /* destination position of X[k] when bitReverseFlag == 0 */
 };
 struct DevState {
-    DevPlan plan[3][9];
+    DevPlan plan[4][9];           /* [CMSISDSP_CUDA_F32 / Q31 / Q15 / F64][length] */
     float *twr[9] = {};           /* rfft twiddles, indexed by len_index(real length) */
     void *rcoef[3][9] = {};       /* q31 / q15 real FFT: split coefficients (ci32x4 per bin), indexed by len_index(fftLenReal / 2) */
 };
@@ -131,9 +131,12 @@ static int upload_pass_ordered(const KernelEntry *ke, const void *base, void **d
     return CMSISDSP_CUDA_OK;
 }
 
+/* kernel op of the complex FFT of a data type */
+static int cfft_op(int type) { return type == CMSISDSP_CUDA_F64 ? OP_CFFT_F64 : type; }
+
 static int build_tables(int type, int li, const void *base, DevPlan &p)
 {
-    int rc = upload_pass_ordered(kEntries[type][li], base, &p.tw);
+    int rc = upload_pass_ordered(kEntries[cfft_op(type)][li], base, &p.tw);
     if (rc || type != CMSISDSP_CUDA_F32 || !kEntries[OP_RFFT_FWD][li]) return rc;
     rc = upload_pass_ordered(kEntries[OP_RFFT_FWD][li], base, &p.tw_rfwd);
     if (!rc) rc = upload_pass_ordered(kEntries[OP_RFFT_INV][li], base, &p.tw_rinv);
@@ -144,7 +147,7 @@ extern "C" int cmsisdsp_cuda_plan_upload(int type, uint32_t fftLen, const void *
                                          const uint16_t *pBitRevTable, uint16_t bitRevLength)
 {
     const int li = len_index(fftLen);
-    if (type < 0 || type > 2 || li < 0 || !pTwiddle || (!pBitRevTable && bitRevLength))
+    if (type < 0 || type > CMSISDSP_CUDA_F64 || li < 0 || !pTwiddle || (!pBitRevTable && bitRevLength))
         return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "plan_upload: bad type / length / pointer");
     int dev;
     int rc = cur_device(&dev);
@@ -192,7 +195,7 @@ extern "C" int cmsisdsp_cuda_plan_ready(int type, uint32_t fftLen)
 {
     const int li = len_index(fftLen);
     int dev;
-    if (type < 0 || type > 2 || li < 0 || cur_device(&dev)) return 0;
+    if (type < 0 || type > CMSISDSP_CUDA_F64 || li < 0 || cur_device(&dev)) return 0;
     std::lock_guard<std::mutex> lk(g_mu);
     return g_dev[dev].plan[type][li].tw != nullptr;
 }
@@ -287,8 +290,9 @@ static int cfft_any(int type, void *d_p, uint32_t fftLen, uint64_t nFrames, uint
     if (rc) return rc;
     const int li = len_index(fftLen);
     /* N = 2*4^m: final << 1 (fixed point only; arm_cfft_q31.c:803-820, arm_cfft_q15.c:810-827) */
-    const int shl1 = (type != CMSISDSP_CUDA_F32) ? ((li + 4) & 1) : 0;
-    const KernelEntry *ke = kEntries[type][li];
+    const int shl1 = (type == CMSISDSP_CUDA_Q31 || type == CMSISDSP_CUDA_Q15) ? ((li + 4) & 1) : 0;
+    if (type == CMSISDSP_CUDA_F64 && ((uintptr_t)d_p & 15u)) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "cfft_f64: data must be 16-byte aligned");
+    const KernelEntry *ke = kEntries[cfft_op(type)][li];
     return ke->launch(d_p, d_p, nFrames, ifftFlag == 1, pl.tw, bitReverseFlag ? nullptr : pl.perm, shl1, choose_flavour(ke),
                       (cudaStream_t)stream);
 }
@@ -299,6 +303,9 @@ extern "C" int cmsisdsp_cuda_cfft_q31(void *d_p, uint32_t fftLen, uint64_t nFram
 { return cfft_any(CMSISDSP_CUDA_Q31, d_p, fftLen, nFrames, ifftFlag, bitReverseFlag, stream); }
 extern "C" int cmsisdsp_cuda_cfft_q15(void *d_p, uint32_t fftLen, uint64_t nFrames, uint8_t ifftFlag, uint8_t bitReverseFlag, void *stream)
 { return cfft_any(CMSISDSP_CUDA_Q15, d_p, fftLen, nFrames, ifftFlag, bitReverseFlag, stream); }
+
+extern "C" int cmsisdsp_cuda_cfft_f64(void *d_p, uint32_t fftLen, uint64_t nFrames, uint8_t ifftFlag, uint8_t bitReverseFlag, void *stream)
+{ return cfft_any(CMSISDSP_CUDA_F64, d_p, fftLen, nFrames, ifftFlag, bitReverseFlag, stream); }
 
 extern "C" int cmsisdsp_cuda_rfft_fast_f32(const void *d_p, void *d_out, uint32_t fftLenReal, uint64_t nFrames, uint8_t ifftFlag, void *stream)
 {

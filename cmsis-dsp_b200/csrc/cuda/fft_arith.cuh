@@ -28,6 +28,7 @@ namespace b200fft {
 struct alignas(8) cf32 { float x, y; };
 struct alignas(8) ci32 { int32_t x, y; };
 struct alignas(4) ci16 { int16_t x, y; };
+struct alignas(16) cf64 { double x, y; };
 /* split-stage coefficients of one bin of the fixed-point real FFT: realCoefA[2k], realCoefA[2k+1],
  * realCoefB[2k], realCoefB[2k+1] at the instance's twidCoefRModifier, 32-bit (q15 sign-extended) */
 struct alignas(16) ci32x4 { int32_t a0, a1, b0, b1; };
@@ -511,6 +512,73 @@ struct ArithQ15 {
     static FFT_HD work split_nyquist(work x0) { return {(x0.x - x0.y) >> 1, 0}; }     /* :400-401 */
     static FFT_HD work mirror(work o) { return {o.x, -o.y}; }                         /* :393-394 */
     static FFT_HD work sat_shl1(work w) { return {sat16(w.x * 2), sat16(w.y * 2)}; }  /* arm_shift_q15(.., 1, ..) */
+};
+
+/* ------------------------------------------------------------------ f64
+ *
+ * arm_cfft_f64 (Source/TransformFunctions/arm_cfft_f64.c) is a radix-4 DIF transform with the stage
+ * structure of the fixed-point path -- arm_radix4_butterfly_f64 (:58-183) for N = 4^m, one radix-2
+ * pre-pass and two half-size radix-4 transforms for N = 2*4^m (arm_cfft_radix4by2_f64, :193-239), results
+ * in binary bit-reversed order (its armBitRevIndexTableF64_N are the fixed-point swap lists) -- and no
+ * scaling, so it runs on the PassFix passes with this Arith: the reference's butterfly, operation for
+ * operation: same operand order, and products rounded on their own (__dmul_rn: no FMA contraction), so
+ * that with the same twiddle values the results are bit-identical to the reference's generic-C build
+ * (-ffp-contract=off) -- the f64 kernels have the arithmetic headroom (16 bytes per point).  The inverse is conjugate -> forward -> conjugate / N (:262-312), done by CfftBody at the load and
+ * the store like f32, so the butterflies have no inverse variant. */
+struct ArithF64 {
+    typedef cf64 elem;
+    typedef cf64 work;
+    typedef cf64 twid;
+    typedef cf64 xelem;
+    typedef cf64 telem;
+    static FFT_HD work load(elem e) { return e; }
+    static FFT_HD elem store(work w) { return w; }
+    static FFT_HD work xload(xelem e) { return e; }
+    static FFT_HD xelem xstore(work w) { return w; }
+    static FFT_HD telem tw_expand(elem e) { return e; }
+    static FFT_HD twid tload(telem e) { return e; }
+    static FFT_HD work shl1(work w) { return w; }
+    static FFT_HD double mul(double a, double b)
+    {
+#if defined(__CUDA_ARCH__)
+        return __dmul_rn(a, b);
+#else
+        return a * b;
+#endif
+    }
+    /* (r, s) * conj(W), W = (cos, +sin): arm_cfft_f64.c:139-143 */
+    static FFT_HD work rot(double r, double s, twid w) { return {mul(r, w.x) + mul(s, w.y), mul(s, w.x) - mul(r, w.y)}; }
+
+    /* outputs in residue order (a', b'[W^1], c'[W^2], d'[W^3]); arm_cfft_f64.c:108-170.  The last stage's
+     * twiddles are W^0 = (1, 0) (:94-99 with ia1 = 0): the products are skipped. */
+    template <int KIND, bool INV>
+    static FFT_HD void bfly4(work &A, work &B, work &C, work &D, twid w1, twid w2, twid w3)
+    {
+        double r1 = A.x + C.x, r2 = A.x - C.x, s1 = A.y + C.y, s2 = A.y - C.y;
+        double t1 = B.x + D.x;
+        const double ax = r1 + t1;
+        r1 = r1 - t1;
+        double t2 = B.y + D.y;
+        const double ay = s1 + t2;
+        s1 = s1 - t2;
+        t1 = B.y - D.y;
+        t2 = B.x - D.x;
+        const work oc = (KIND == ST_LAST4) ? work{r1, s1} : rot(r1, s1, w2);
+        r1 = r2 + t1;
+        r2 = r2 - t1;
+        s1 = s2 - t2;
+        s2 = s2 + t2;
+        const work ob = (KIND == ST_LAST4) ? work{r1, s1} : rot(r1, s1, w1);
+        const work od = (KIND == ST_LAST4) ? work{r2, s2} : rot(r2, s2, w3);
+        A = {ax, ay}; B = ob; C = oc; D = od;
+    }
+    /* radix-2 pre-pass of the N = 2*4^m lengths (arm_cfft_f64.c:205-230) */
+    template <bool INV> static FFT_HD void bfly2(work &A, work &B, twid w)
+    {
+        const double a0 = A.x + B.x, xt = A.x - B.x, yt = A.y - B.y, a1 = B.y + A.y;
+        A = {a0, a1};
+        B = rot(xt, yt, w);
+    }
 };
 
 }  // namespace b200fft

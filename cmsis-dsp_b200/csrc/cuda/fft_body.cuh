@@ -23,7 +23,9 @@ template <class V> FFT_HD V ld_stream(const V *p);
 template <> FFT_HD cf32 ld_stream<cf32>(const cf32 *p) { float2 v = __ldcs(reinterpret_cast<const float2 *>(p)); return {v.x, v.y}; }
 template <> FFT_HD ci32 ld_stream<ci32>(const ci32 *p) { int2 v = __ldcs(reinterpret_cast<const int2 *>(p)); return {v.x, v.y}; }
 template <> FFT_HD ci16 ld_stream<ci16>(const ci16 *p) { short2 v = __ldcs(reinterpret_cast<const short2 *>(p)); return {v.x, v.y}; }
+template <> FFT_HD cf64 ld_stream<cf64>(const cf64 *p) { double2 v = __ldcs(reinterpret_cast<const double2 *>(p)); return {v.x, v.y}; }
 FFT_HD void st_stream(cf32 *p, cf32 v) { __stcs(reinterpret_cast<float2 *>(p), make_float2(v.x, v.y)); }
+FFT_HD void st_stream(cf64 *p, cf64 v) { __stcs(reinterpret_cast<double2 *>(p), make_double2(v.x, v.y)); }
 FFT_HD void st_stream(ci32 *p, ci32 v) { __stcs(reinterpret_cast<int2 *>(p), make_int2(v.x, v.y)); }
 FFT_HD void st_stream(ci16 *p, ci16 v) { __stcs(reinterpret_cast<short2 *>(p), make_short2(v.x, v.y)); }
 /* predicated streaming store: no branch, so the surrounding straight-line code stays one block */
@@ -67,6 +69,9 @@ template <int NP> struct PhaseCount { static constexpr int value = (NP == 1) ? 1
 
 template <class T> struct IsF32 { static constexpr bool value = false; };
 template <> struct IsF32<cf32> { static constexpr bool value = true; };
+/* floating-point element: the inverse is conjugate -> forward -> conjugate / N, no fixed-point << 1 */
+template <class T> struct IsFloat { static constexpr bool value = IsF32<T>::value; };
+template <> struct IsFloat<cf64> { static constexpr bool value = true; };
 
 /* ------------------------------------------------------------------ CFFT */
 
@@ -86,7 +91,7 @@ template <class PL, bool INV, bool PERM = false, bool STAGED = false, bool RIFFT
     typedef typename Eng::Regs Regs;
     static constexpr int NP = PL::NP, E = PL::E, N = PL::N;
     static constexpr int kPhases = PhaseCount<NP>::value;
-    static constexpr bool kF32 = IsF32<elem>::value;
+    static constexpr bool kF32 = IsFloat<elem>::value;      /* f32 or f64 */
 
     struct Args {
         const elem *in;          /* frame base (device or emulated) */
@@ -146,6 +151,7 @@ template <class PL, bool INV, bool PERM = false, bool STAGED = false, bool RIFFT
             }
     }
     static FFT_HD cf32 scale_conj(cf32 w, float s) { return {w.x * s, -w.y * s}; }
+    static FFT_HD cf64 scale_conj(cf64 w, float s) { return {w.x * (double)s, -w.y * (double)s}; }   /* cfft_f64.c:298-310 */
     static FFT_HD ci32 scale_conj(ci32 w, float) { return w; }
 
     /* phase 0 in two halves, for kernels whose input buffer doubles as the exchange buffer */

@@ -91,4 +91,20 @@ FIXPLAN(4096, 256, 1,   4, 1, PF(ST_FIRST4, ST_MID4), PF(ST_MID4, ST_MID4), PF(S
 #undef PF
 #undef FIXPLAN
 
+/* ---- f64 complex (arm_cfft_f64.c: the fixed-point stage structure, 16-byte points) ----
+ * 16 points (64 registers) per thread from N = 64 up; the short lengths use 4 threads per frame so that a
+ * frame's loads stay 64-byte pieces (one thread per frame would read 16-byte pieces 16 N bytes apart). */
+template <int N> struct PlanCfftF64;
+#define PD(...) PassFix<ArithF64, __VA_ARGS__>
+template <> struct PlanCfftF64<16>   { typedef Plan<ArithF64, 16,   4,   32, 4, 1, PD(ST_FIRST4), PD(ST_LAST4)> type; };
+template <> struct PlanCfftF64<32>   { typedef Plan<ArithF64, 32,   4,   32, 4, 1, PD(ST_PRE2, ST_FIRST4), PD(ST_LAST4)> type; };
+template <> struct PlanCfftF64<64>   { typedef Plan<ArithF64, 64,   4,   32, 4, 1, PD(ST_FIRST4, ST_MID4), PD(ST_LAST4)> type; };
+template <> struct PlanCfftF64<128>  { typedef Plan<ArithF64, 128,  8,   16, 4, 1, PD(ST_PRE2, ST_FIRST4), PD(ST_MID4, ST_LAST4)> type; };
+template <> struct PlanCfftF64<256>  { typedef Plan<ArithF64, 256,  16,  8,  4, 1, PD(ST_FIRST4, ST_MID4), PD(ST_MID4, ST_LAST4)> type; };
+template <> struct PlanCfftF64<512>  { typedef Plan<ArithF64, 512,  32,  4,  4, 1, PD(ST_PRE2, ST_FIRST4), PD(ST_MID4, ST_MID4), PD(ST_LAST4)> type; };
+template <> struct PlanCfftF64<1024> { typedef Plan<ArithF64, 1024, 64,  2,  4, 1, PD(ST_FIRST4, ST_MID4), PD(ST_MID4, ST_MID4), PD(ST_LAST4)> type; };
+template <> struct PlanCfftF64<2048> { typedef Plan<ArithF64, 2048, 128, 1,  4, 1, PD(ST_PRE2, ST_FIRST4), PD(ST_MID4, ST_MID4), PD(ST_MID4, ST_LAST4)> type; };
+template <> struct PlanCfftF64<4096> { typedef Plan<ArithF64, 4096, 256, 1,  4, 1, PD(ST_FIRST4, ST_MID4), PD(ST_MID4, ST_MID4), PD(ST_MID4, ST_LAST4)> type; };
+#undef PD
+
 }  // namespace b200fft

@@ -21,7 +21,7 @@
  * rfft_q31 forward up to complex 256 and rfft_q31 inverse; they lose 2-13 points for the 256-thread CTAs of N = 4096
  * and for the q15 real FFT, and are neutral for cfft_q15. */
 #ifndef KU_MINB
-#if KU_OP == 0 || KU_OP == 3 || KU_OP == 4 || KU_OP == 9 || KU_OP == 6 || (KU_OP == 1 && KU_N <= 2048) || (KU_OP == 5 && KU_N <= 256)
+#if KU_OP == 0 || KU_OP == 3 || KU_OP == 4 || KU_OP == 9 || KU_OP == 6 || (KU_OP == 10 && KU_N <= 1024) || (KU_OP == 1 && KU_N <= 2048) || (KU_OP == 5 && KU_N <= 256)
 #define KU_MINB 1
 #else
 #define KU_MINB 0
@@ -51,7 +51,7 @@
 #endif
 
 #if !defined(KU_OP) || !defined(KU_N)
-#error "compile with -DKU_OP=<0..9> -DKU_N=<length>"
+#error "compile with -DKU_OP=<0..10> -DKU_N=<length>"
 #endif
 
 using namespace b200fft;
@@ -490,9 +490,12 @@ template <class P> struct PipeOf {
 };
 static bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }   /* bulk copies need 16-byte aligned sources */
 
-#if KU_OP <= 2   /* complex FFT, in place */
+#if KU_OP <= 2 || KU_OP == 10   /* complex FFT, in place */
 
-#if KU_OP == 0
+#if KU_OP == 10
+typedef ArithF64 AR;
+typedef PlanCfftF64<KU_N>::type PL;
+#elif KU_OP == 0
 typedef ArithF32 AR;
 typedef PlanCfftF32<KU_N>::type PL;
 #elif KU_OP == 1

@@ -2,6 +2,7 @@
  * arm_cfft_exec.c -- exec functions of the FFT path: thin C over libcmsisdsp_cuda.
  *
  *   arm_cfft_f32 / q31 / q15   reference: arm_cfft_f32.c:1243-1298, arm_cfft_q31.c:704-755, arm_cfft_q15.c:671-722
+ *   arm_cfft_f64               reference: arm_cfft_f64.c:262-312
  *   arm_rfft_fast_f32          reference: arm_rfft_fast_f32.c:675-699
  *   arm_rfft_q31 / q15         reference: arm_rfft_q31.c:145-181, arm_rfft_q15.c:148-182
  *   arm_*_batch_*              B200 extension (include/dsp/transform_functions.h)
@@ -134,6 +135,13 @@ arm_status arm_cfft_batch_q15(const arm_cfft_instance_q15 *S, q15_t *p, uint32_t
                       S->pBitRevTable, S->bitRevLength, p, nFrames, ifftFlag, bitReverseFlag);
 }
 
+arm_status arm_cfft_batch_f64(const arm_cfft_instance_f64 *S, float64_t *p, uint32_t nFrames, uint8_t ifftFlag, uint8_t bitReverseFlag)
+{
+    if (!S) return ARM_MATH_ARGUMENT_ERROR;
+    return cfft_batch(CMSISDSP_CUDA_F64, cmsisdsp_cuda_cfft_f64, sizeof(float64_t), S->fftLen, S->pTwiddle,
+                      S->pBitRevTable, S->bitRevLength, p, nFrames, ifftFlag, bitReverseFlag);
+}
+
 /* clobber != 0: also leave the N/2-point CFFT in p after a forward transform, the
  * side effect of the reference's in-place CFFT on the input buffer (rfft_fast_f32.c:694) */
 static arm_status rfft_batch(const arm_rfft_fast_instance_f32 *S, float32_t *p, float32_t *pOut,
@@ -193,6 +201,11 @@ void arm_cfft_f32(const arm_cfft_instance_f32 *S, float32_t *p1, uint8_t ifftFla
 {
     if (!legacy_len_ok(S->fftLen)) { g_last = ARM_MATH_SUCCESS; return; }
     g_last = arm_cfft_batch_f32(S, p1, 1, ifftFlag, bitReverseFlag);
+}
+void arm_cfft_f64(const arm_cfft_instance_f64 *S, float64_t *p1, uint8_t ifftFlag, uint8_t bitReverseFlag)
+{
+    if (!legacy_len_ok(S->fftLen)) { g_last = ARM_MATH_SUCCESS; return; }
+    g_last = arm_cfft_batch_f64(S, p1, 1, ifftFlag, bitReverseFlag);
 }
 void arm_cfft_q31(const arm_cfft_instance_q31 *S, q31_t *p1, uint8_t ifftFlag, uint8_t bitReverseFlag)
 {

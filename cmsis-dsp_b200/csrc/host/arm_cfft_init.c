@@ -5,6 +5,7 @@
  * the first exec call on each device).
  *   arm_cfft_init_f32 / _N_f32     Source/TransformFunctions/arm_cfft_init_f32.c:116-136,291-354
  *   arm_cfft_init_q31 / q15        Source/TransformFunctions/arm_cfft_init_q31.c, arm_cfft_init_q15.c:116-138,283-345
+ *   arm_cfft_init_f64 / _N_f64     Source/TransformFunctions/arm_cfft_init_f64.c:58-72,205-277
  *   arm_rfft_fast_init_f32 / _N    Source/TransformFunctions/arm_rfft_fast_init_f32.c:83-99,331-371
  *   arm_rfft_init_q31 / q15 / _N   Source/TransformFunctions/arm_rfft_init_q31.c:97-127,395-470, arm_rfft_init_q15.c
  */
@@ -22,9 +23,11 @@
 #define INIT_F32(N) INIT_N(f32, N)
 #define INIT_Q31(N) INIT_N(q31, N)
 #define INIT_Q15(N) INIT_N(q15, N)
+#define INIT_F64(N) INIT_N(f64, N)
 CMSISDSP_B200_FOR_EACH_LEN(INIT_F32)
 CMSISDSP_B200_FOR_EACH_LEN(INIT_Q31)
 CMSISDSP_B200_FOR_EACH_LEN(INIT_Q15)
+CMSISDSP_B200_FOR_EACH_LEN(INIT_F64)
 
 #define CASE_N(EXT, N) case N##U: return arm_cfft_init_##N##_##EXT(S);
 #define INIT_ANY(EXT)                                                               \
@@ -40,6 +43,7 @@ CMSISDSP_B200_FOR_EACH_LEN(INIT_Q15)
 INIT_ANY(f32)
 INIT_ANY(q31)
 INIT_ANY(q15)
+INIT_ANY(f64)
 
 #define RINIT_N(N, H)                                                               \
     arm_status arm_rfft_fast_init_##N##_f32(arm_rfft_fast_instance_f32 *S)          \

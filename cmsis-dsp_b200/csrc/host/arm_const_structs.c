@@ -1,6 +1,6 @@
 /*
  * arm_const_structs.c -- constant preset instances (reference:
- * Source/CommonTables/arm_const_structs.c:79-114 f32, :132-166 q31, :172-206 q15, :265-311 rfft).
+ * Source/CommonTables/arm_const_structs.c:39-73 f64, :79-114 f32, :132-166 q31, :172-206 q15, :265-311 rfft).
  * Table data comes from the build-time generator (csrc/tables/gen_tables.c).
  */
 #include "arm_const_structs.h"
@@ -12,7 +12,11 @@
 #define SR_Q15(N) \
     const arm_cfft_instance_q15 arm_cfft_sR_q15_len##N = { N, twiddleCoef_##N##_q15, armBitRevIndexTable_fixed_##N, ARMBITREVINDEXTABLE_FIXED_##N##_TABLE_LENGTH };
 
+#define SR_F64(N) \
+    const arm_cfft_instance_f64 arm_cfft_sR_f64_len##N = { N, (const float64_t *)twiddleCoefF64_##N, armBitRevIndexTableF64_##N, ARMBITREVINDEXTABLEF64_##N##_TABLE_LENGTH };
+
 CMSISDSP_B200_FOR_EACH_LEN(SR_F32)
+CMSISDSP_B200_FOR_EACH_LEN(SR_F64)
 CMSISDSP_B200_FOR_EACH_LEN(SR_Q31)
 CMSISDSP_B200_FOR_EACH_LEN(SR_Q15)
 

@@ -15,6 +15,11 @@
  *   armBitRevIndexTableN     ordered swap list of the (r0,8,8,..) digit reversal,
  *                            entries are complex index * 8                          (:25057-26040)
  *   armBitRevIndexTable_fixed_N  swap list of the binary bit reversal               (:26042-26700)
+ *   twiddleCoefF64_N         (cos, +sin)(2 pi i / N) as IEEE-754 double bit patterns, i < N: first-quadrant sines in
+ *                            double precision, the other quadrants by symmetry (:191-8506).  NOT value-identical:
+ *                            the reference's literals are not reproducible by a rule; 15-20 % of them differ from
+ *                            these by 1 ulp (none by more), which is inside the f64 parity bar (rel-RMS 1e-15)
+ *   armBitRevIndexTableF64_N the fixed-point swap lists under their f64 names    (:24404-25050)
  *   armBitRevTable           (12-bit reversal of l) >> 1, l = 1..1024 (deprecated radix-2/4 API)   (:41-67)
  *   realCoefAQ31 / realCoefBQ31 / realCoefAQ15 / realCoefBQ15   split-stage coefficients of arm_rfft_q31 / _q15,
  *                            n = 4096: A = 0.5 (1 - sin, -cos), B = 0.5 (1 + sin, cos)(2 pi i / 2n),
@@ -28,6 +33,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 static const unsigned kLen[9] = {16, 32, 64, 128, 256, 512, 1024, 2048, 4096};
 static const double kTwoPi = 6.283185307179586476925286766559;
@@ -89,6 +95,16 @@ static void exchange_neighbours(unsigned N, unsigned *tab)
     }
 }
 
+/* sin(2 pi i / N) for 0 <= i <= N/4; -0.0 never appears (the reference's tables hold +0) */
+static double quarter_sin(unsigned i, unsigned N) { return sin(kTwoPi * (double)i / (double)N); }
+static unsigned long long dbits(double v)
+{
+    unsigned long long u;
+    if (v == 0.0) v = 0.0;
+    memcpy(&u, &v, sizeof u);
+    return u;
+}
+
 static void emit_u16(const char *name, unsigned N, const unsigned *tab, unsigned n)
 {
     printf("const uint16_t %s%u[%u] = {", name, N, n);
@@ -142,6 +158,22 @@ int main(void)
         for (unsigned k = 0; k < N; k++) P[k] = bit_reverse(lg, k);
         n = swap_list(N, P, tab);
         emit_u16("armBitRevIndexTable_fixed_", N, tab, n);
+        emit_u16("armBitRevIndexTableF64_", N, tab, n);      /* the reference's f64 lists are the fixed-point ones */
+        /* f64 twiddles as bit patterns: first-quadrant sines, the rest by symmetry (exact 0 / 1 on the axes) */
+        printf("const uint64_t twiddleCoefF64_%u[%u] = {", N, 2 * N);
+        for (unsigned i = 0; i < N; i++) {
+            const unsigned q = N / 4, quad = i / q, r = i % q;
+            const double sr = quarter_sin(r, N), cr = quarter_sin(q - r, N);
+            double c, sn;
+            switch (quad) {
+            case 0: c = cr; sn = sr; break;
+            case 1: c = -sr; sn = cr; break;
+            case 2: c = -cr; sn = -sr; break;
+            default: c = sr; sn = -cr; break;
+            }
+            printf("%s0x%016llxull,0x%016llxull,", (i % 4) ? "" : "\n  ", dbits(c), dbits(sn));
+        }
+        printf("\n};\n");
         printf("const uint16_t cmsisdsp_b200_bitrev_len_fixed_%u = %u;\n\n", N, n);
         free(P); free(tab);
     }

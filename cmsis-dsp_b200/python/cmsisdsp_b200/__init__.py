@@ -24,9 +24,9 @@ RLENGTHS = [32, 64, 128, 256, 512, 1024, 2048, 4096]
 RFIX_LENGTHS = [32, 64, 128, 256, 512, 1024, 2048, 4096, 8192]      # arm_rfft_q31 / arm_rfft_q15
 ARM_MATH_SUCCESS = 0
 ARM_MATH_ARGUMENT_ERROR = -1
-TYPE_ID = {"f32": 0, "q31": 1, "q15": 2}
-NP_DTYPE = {"f32": np.float32, "q31": np.int32, "q15": np.int16}
-C_SCALAR = {"f32": C.c_float, "q31": C.c_int32, "q15": C.c_int16}
+TYPE_ID = {"f32": 0, "q31": 1, "q15": 2, "f64": 3}
+NP_DTYPE = {"f32": np.float32, "q31": np.int32, "q15": np.int16, "f64": np.float64}
+C_SCALAR = {"f32": C.c_float, "q31": C.c_int32, "q15": C.c_int16, "f64": C.c_double}
 
 
 def _mk_cfft_instance(scalar):
@@ -39,7 +39,9 @@ def _mk_cfft_instance(scalar):
 arm_cfft_instance_f32 = _mk_cfft_instance(C.c_float)
 arm_cfft_instance_q31 = _mk_cfft_instance(C.c_int32)
 arm_cfft_instance_q15 = _mk_cfft_instance(C.c_int16)
-CFFT_INSTANCE = {"f32": arm_cfft_instance_f32, "q31": arm_cfft_instance_q31, "q15": arm_cfft_instance_q15}
+arm_cfft_instance_f64 = _mk_cfft_instance(C.c_double)
+CFFT_INSTANCE = {"f32": arm_cfft_instance_f32, "q31": arm_cfft_instance_q31, "q15": arm_cfft_instance_q15,
+                 "f64": arm_cfft_instance_f64}
 
 
 class arm_rfft_fast_instance_f32(C.Structure):
@@ -112,6 +114,7 @@ def cuda():
         "cmsisdsp_cuda_cfft_f32": ([vp, u32, u64, u8, u8, vp], i),
         "cmsisdsp_cuda_cfft_q31": ([vp, u32, u64, u8, u8, vp], i),
         "cmsisdsp_cuda_cfft_q15": ([vp, u32, u64, u8, u8, vp], i),
+        "cmsisdsp_cuda_cfft_f64": ([vp, u32, u64, u8, u8, vp], i),
         "cmsisdsp_cuda_rfft_fast_f32": ([vp, vp, u32, u64, u8, vp], i),
         "cmsisdsp_cuda_rfft_fix_plan_upload": ([i, u32, vp, vp, u32], i), "cmsisdsp_cuda_rfft_fix_plan_ready": ([i, u32], i),
         "cmsisdsp_cuda_rfft_q31": ([vp, vp, u32, u64, u8, vp], i), "cmsisdsp_cuda_rfft_q15": ([vp, vp, u32, u64, u8, vp], i),
@@ -221,7 +224,7 @@ def rfft_instance(N):
 def instance_tables(S, kind):
     """numpy copies of (twiddle table, bit-reversal swap list) an instance points at."""
     n = int(S.fftLen)
-    ntw = 2 * n if kind == "f32" else 3 * n // 2
+    ntw = 2 * n if kind in ("f32", "f64") else 3 * n // 2
     tw = np.ctypeslib.as_array(S.pTwiddle, shape=(ntw,)).copy()
     br = np.ctypeslib.as_array(S.pBitRevTable, shape=(int(S.bitRevLength),)).copy()
     return tw, br

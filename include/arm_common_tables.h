@@ -22,6 +22,24 @@ extern "C" {
 CMSISDSP_B200_FOR_EACH_LEN(CMSISDSP_B200_DECL_TW)
 #undef CMSISDSP_B200_DECL_TW
 
+/* f64 complex FFT (Include/arm_common_tables.h:43-59,153-178): twiddles stored as IEEE-754 bit patterns like the
+ * reference's; generated values are within 1 ulp of the reference's literals (see gen_tables.c).  The bit reversal
+ * tables are the fixed-point (binary) swap lists, as in the reference. */
+#define CMSISDSP_B200_DECL_TW64(N)                       \
+    extern const uint64_t twiddleCoefF64_##N[(N) * 2];   \
+    extern const uint16_t armBitRevIndexTableF64_##N[];
+CMSISDSP_B200_FOR_EACH_LEN(CMSISDSP_B200_DECL_TW64)
+#undef CMSISDSP_B200_DECL_TW64
+#define ARMBITREVINDEXTABLEF64_16_TABLE_LENGTH   ((uint16_t)12)
+#define ARMBITREVINDEXTABLEF64_32_TABLE_LENGTH   ((uint16_t)24)
+#define ARMBITREVINDEXTABLEF64_64_TABLE_LENGTH   ((uint16_t)56)
+#define ARMBITREVINDEXTABLEF64_128_TABLE_LENGTH  ((uint16_t)112)
+#define ARMBITREVINDEXTABLEF64_256_TABLE_LENGTH  ((uint16_t)240)
+#define ARMBITREVINDEXTABLEF64_512_TABLE_LENGTH  ((uint16_t)480)
+#define ARMBITREVINDEXTABLEF64_1024_TABLE_LENGTH ((uint16_t)992)
+#define ARMBITREVINDEXTABLEF64_2048_TABLE_LENGTH ((uint16_t)1984)
+#define ARMBITREVINDEXTABLEF64_4096_TABLE_LENGTH ((uint16_t)4032)
+
 extern const float32_t twiddleCoef_rfft_32[32];
 extern const float32_t twiddleCoef_rfft_64[64];
 extern const float32_t twiddleCoef_rfft_128[128];

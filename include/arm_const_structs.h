@@ -1,6 +1,6 @@
 /*
  * arm_const_structs.h -- ready-made constant CFFT instances, usable without calling the
- * init functions (reference: Include/arm_const_structs.h:50-78,
+ * init functions (reference: Include/arm_const_structs.h:41-78,
  * Source/CommonTables/arm_const_structs.c:79-114,132-206,265-311).
  */
 #ifndef ARM_CONST_STRUCTS_H
@@ -17,7 +17,8 @@ extern "C" {
 #define CMSISDSP_B200_DECL_SR(N)                                  \
     extern const arm_cfft_instance_f32 arm_cfft_sR_f32_len##N;    \
     extern const arm_cfft_instance_q31 arm_cfft_sR_q31_len##N;    \
-    extern const arm_cfft_instance_q15 arm_cfft_sR_q15_len##N;
+    extern const arm_cfft_instance_q15 arm_cfft_sR_q15_len##N;    \
+    extern const arm_cfft_instance_f64 arm_cfft_sR_f64_len##N;
 CMSISDSP_B200_FOR_EACH_LEN(CMSISDSP_B200_DECL_SR)
 #undef CMSISDSP_B200_DECL_SR
 

@@ -14,6 +14,7 @@
  *                                 arm_bitreversal2.c:84-108), looped over nFrames frames
  *   cmsisdsp_cuda_cfft_q31        Source/TransformFunctions/arm_cfft_q31.c:704-755 (+ arm_cfft_radix4_q31.c:153-834)
  *   cmsisdsp_cuda_cfft_q15        Source/TransformFunctions/arm_cfft_q15.c:671-722 (+ arm_cfft_radix4_q15.c:572-970,1434-1813)
+ *   cmsisdsp_cuda_cfft_f64        Source/TransformFunctions/arm_cfft_f64.c:262-312 (+ :58-239, arm_bitreversal2.c:45-70)
  *   cmsisdsp_cuda_rfft_fast_f32   Source/TransformFunctions/arm_rfft_fast_f32.c:675-699 (+ :316-462)
  *   cmsisdsp_cuda_plan_upload     the residency of Source/CommonTables/arm_common_tables.c twiddle / bit-reversal
  *                                 tables (:8523-26700) reached through arm_cfft_instance_* (transform_functions.h:282-424)
@@ -32,7 +33,8 @@ extern "C" {
 enum {
     CMSISDSP_CUDA_F32 = 0,
     CMSISDSP_CUDA_Q31 = 1,
-    CMSISDSP_CUDA_Q15 = 2
+    CMSISDSP_CUDA_Q15 = 2,
+    CMSISDSP_CUDA_F64 = 3
 };
 
 enum {
@@ -63,7 +65,7 @@ int  cmsisdsp_cuda_timer_begin(void **timer, void *stream);
 int  cmsisdsp_cuda_timer_end(void *timer, void *stream, float *elapsedMs);
 
 /* ---- plans: device-resident tables, keyed by (device, type, fftLen) ---- */
-/* pTwiddle: f32 -> 2*fftLen floats (cos,+sin); q31/q15 -> 3*fftLen/2 values (3N/4 pairs).
+/* pTwiddle: f32 -> 2*fftLen floats (cos,+sin); f64 -> 2*fftLen doubles; q31/q15 -> 3*fftLen/2 values (3N/4 pairs).
  * pBitRevTable/bitRevLength: the ordered swap list of the instance struct; it is expanded to the
  * output permutation used when bitReverseFlag == 0.  Idempotent. */
 int  cmsisdsp_cuda_plan_upload(int type, uint32_t fftLen, const void *pTwiddle,
@@ -79,6 +81,9 @@ int  cmsisdsp_cuda_cfft_f32(void *d_p, uint32_t fftLen, uint64_t nFrames,
 int  cmsisdsp_cuda_cfft_q31(void *d_p, uint32_t fftLen, uint64_t nFrames,
                             uint8_t ifftFlag, uint8_t bitReverseFlag, void *stream);
 int  cmsisdsp_cuda_cfft_q15(void *d_p, uint32_t fftLen, uint64_t nFrames,
+                            uint8_t ifftFlag, uint8_t bitReverseFlag, void *stream);
+/* d_p: nFrames*2*fftLen doubles, 16-byte aligned */
+int  cmsisdsp_cuda_cfft_f64(void *d_p, uint32_t fftLen, uint64_t nFrames,
                             uint8_t ifftFlag, uint8_t bitReverseFlag, void *stream);
 /* d_p: nFrames*fftLenReal floats, left untouched (the reference clobbers it);
  * d_out: nFrames*fftLenReal floats, packed {DC, Nyquist, Re1, Im1, ...}.  d_p and d_out must not alias. */
@@ -135,7 +140,7 @@ const char *cmsisdsp_cuda_last_error(void);        /* thread-local, never NULL *
 uint64_t    cmsisdsp_cuda_launch_count(void);      /* kernels launched by this library so far */
 /* static facts about the kernel chosen for (op, fftLen): op 0 cfft_f32, 1 cfft_q31, 2 cfft_q15,
  * 3 rfft forward, 4 rfft inverse, 5/6 rfft_q31 forward/inverse, 7/8 rfft_q15 forward/inverse (fftLen = real
- * length for 3..8), 9 cfft_f32 + magnitude epilogue.  Any out pointer may be NULL. */
+ * length for 3..8), 9 cfft_f32 + magnitude epilogue, 10 cfft_f64.  Any out pointer may be NULL. */
 int  cmsisdsp_cuda_kernel_info(int op, uint32_t fftLen, int *threadsPerCta, int *framesPerCta,
                                int *smemBytes, int *regsPerThread, int *ctasPerSm);
 

@@ -88,6 +88,28 @@ arm_status arm_cfft_init_16_f32(arm_cfft_instance_f32 *S);
 arm_status arm_cfft_init_f32(arm_cfft_instance_f32 *S, uint16_t fftLen);
 void arm_cfft_f32(const arm_cfft_instance_f32 *S, float32_t *p1, uint8_t ifftFlag, uint8_t bitReverseFlag);
 
+/* ---------------------------------------------------------------- f64 CFFT
+ * (Include/dsp/transform_functions.h:466-493; arm_cfft_f64.c:262-312) */
+typedef struct
+{
+          uint16_t   fftLen;
+    const float64_t *pTwiddle;
+    const uint16_t  *pBitRevTable;
+          uint16_t   bitRevLength;
+} arm_cfft_instance_f64;
+
+arm_status arm_cfft_init_4096_f64(arm_cfft_instance_f64 *S);
+arm_status arm_cfft_init_2048_f64(arm_cfft_instance_f64 *S);
+arm_status arm_cfft_init_1024_f64(arm_cfft_instance_f64 *S);
+arm_status arm_cfft_init_512_f64(arm_cfft_instance_f64 *S);
+arm_status arm_cfft_init_256_f64(arm_cfft_instance_f64 *S);
+arm_status arm_cfft_init_128_f64(arm_cfft_instance_f64 *S);
+arm_status arm_cfft_init_64_f64(arm_cfft_instance_f64 *S);
+arm_status arm_cfft_init_32_f64(arm_cfft_instance_f64 *S);
+arm_status arm_cfft_init_16_f64(arm_cfft_instance_f64 *S);
+arm_status arm_cfft_init_f64(arm_cfft_instance_f64 *S, uint16_t fftLen);
+void arm_cfft_f64(const arm_cfft_instance_f64 *S, float64_t *p1, uint8_t ifftFlag, uint8_t bitReverseFlag);
+
 /* ---------------------------------------------------------------- f32 fast RFFT */
 typedef struct
 {
@@ -268,6 +290,9 @@ arm_status arm_cfft_batch_f32(const arm_cfft_instance_f32 *S, float32_t *p, uint
 arm_status arm_cfft_batch_q31(const arm_cfft_instance_q31 *S, q31_t *p, uint32_t nFrames,
                               uint8_t ifftFlag, uint8_t bitReverseFlag);
 arm_status arm_cfft_batch_q15(const arm_cfft_instance_q15 *S, q15_t *p, uint32_t nFrames,
+                              uint8_t ifftFlag, uint8_t bitReverseFlag);
+/* device pointers must be 16-byte aligned (host buffers are staged) */
+arm_status arm_cfft_batch_f64(const arm_cfft_instance_f64 *S, float64_t *p, uint32_t nFrames,
                               uint8_t ifftFlag, uint8_t bitReverseFlag);
 arm_status arm_rfft_fast_batch_f32(const arm_rfft_fast_instance_f32 *S, float32_t *p, float32_t *pOut,
                                    uint32_t nFrames, uint8_t ifftFlag);

@@ -216,3 +216,16 @@ const uint16_t *ref_arm_bit_rev_table(void) { return armBitRevTable; }
 uint32_t ref_sizeof_cfft_radix4_instance_f32(void) { return (uint32_t)sizeof(arm_cfft_radix4_instance_f32); }
 uint32_t ref_sizeof_cfft_radix4_instance_q31(void) { return (uint32_t)sizeof(arm_cfft_radix4_instance_q31); }
 uint32_t ref_sizeof_cfft_radix4_instance_q15(void) { return (uint32_t)sizeof(arm_cfft_radix4_instance_q15); }
+
+/* ---- arm_cfft_f64, frame by frame (single thread: used for parity only) ---- */
+int ref_cfft_f64_batch(uint32_t N, double *p, uint64_t nFrames, int ifft, int bitrev)
+{
+    arm_cfft_instance_f64 S;
+    if (arm_cfft_init_f64(&S, (uint16_t)N) != ARM_MATH_SUCCESS) return -1;
+    for (uint64_t f = 0; f < nFrames; f++) arm_cfft_f64(&S, p + 2ull * N * f, (uint8_t)ifft, (uint8_t)bitrev);
+    return 0;
+}
+const double *ref_twiddle_f64(uint32_t N) { arm_cfft_instance_f64 S; return arm_cfft_init_f64(&S, (uint16_t)N) ? 0 : S.pTwiddle; }
+const uint16_t *ref_bitrev_f64(uint32_t N, uint16_t *len)
+{ arm_cfft_instance_f64 S; if (arm_cfft_init_f64(&S, (uint16_t)N)) return 0; *len = S.bitRevLength; return S.pBitRevTable; }
+uint32_t ref_sizeof_cfft_instance_f64(void) { return (uint32_t)sizeof(arm_cfft_instance_f64); }

@@ -107,6 +107,12 @@ template <int N> static void cfft_f32_n(float *d, uint64_t n, int inv, const voi
     if (inv) cfft_run<ArithF32, PL, true>((cf32 *)d, n, tw, perm, 0);
     else cfft_run<ArithF32, PL, false>((cf32 *)d, n, tw, perm, 0);
 }
+template <int N> static void cfft_f64_n(double *d, uint64_t n, int inv, const void *tw, const uint16_t *perm)
+{
+    typedef typename PlanCfftF64<N>::type PL;
+    if (inv) cfft_run<ArithF64, PL, true>((cf64 *)d, n, tw, perm, 0);
+    else cfft_run<ArithF64, PL, false>((cf64 *)d, n, tw, perm, 0);
+}
 template <class AR, int N> static void cfft_fix_n(void *d, uint64_t n, int inv, const void *tw, const uint16_t *perm)
 {
     typedef typename PlanCfftFix<AR, N>::type PL;
@@ -163,6 +169,7 @@ int emu_cfft(int type, uint32_t N, void *data, uint64_t nFrames, int ifft, int b
     case n:                                                                          \
         if (type == 0) cfft_f32_n<n>((float *)data, nFrames, inv, tw, pp);          \
         else if (type == 1) cfft_fix_n<ArithQ31, n>(data, nFrames, inv, tw, pp);    \
+        else if (type == 3) cfft_f64_n<n>((double *)data, nFrames, inv, tw, pp);    \
         else cfft_fix_n<ArithQ15, n>(data, nFrames, inv, tw, pp);                   \
         return 0;
         FOR_ALL_N(CASE)

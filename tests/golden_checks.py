@@ -19,6 +19,7 @@ THRESH = {
     ("f32", "r"): dict(snr=120.0, abs=5.0e-5, rel=1.0e-5),
     ("q31", "c"): dict(snr=90.0, near=53),
     ("q15", "c"): dict(snr=30.0, near=15),
+    ("f64", "c"): dict(snr=250.0, abs=2.0e-13, rel=1.0e-13),       # Testing/Source/Tests/TransformCF64.cpp:6-8
 }
 
 
@@ -26,6 +27,7 @@ def patterns():
     global _pat
     if _pat is None:
         _pat = dict(np.load(os.path.join(HERE, "golden", "transform_patterns.npz")))
+        _pat.update(np.load(os.path.join(HERE, "golden", "transform_patterns_f64.npz")))
     return _pat
 
 
@@ -95,7 +97,7 @@ def golden_cases(kind, cr):
             yield N, sig, 0, cut(pat[base + "input"]), cut(pat[base + "ref"])
         if base + "ifft_input" in pat:
             ref = cut(pat[base + "input"])
-            if kind != "f32":
+            if kind not in ("f32", "f64"):
                 ref = ref >> int(np.log2(N))
             yield N, sig, 1, cut(pat[base + "ifft_input"]), ref
 

@@ -64,6 +64,30 @@ class _Lib:
         self._fn(f"cfft_{kind}_batch")(N, y.ctypes.data, y.size // (2 * N), int(ifft), int(bitrev), int(threads))
         return y
 
+    def cfft_f64(self, N, x, ifft=0, bitrev=1, twiddle=None, threads=1):
+        """arm_cfft_f64 on x [..., 2N] float64; returns a transformed copy.  twiddle (oracle only): the table to
+        use instead of the oracle's generated one (e.g. the compiled reference's twiddleCoefF64_N)."""
+        y = np.ascontiguousarray(x, dtype=np.float64).copy()
+        assert y.size % (2 * N) == 0
+        fn = self._fn("cfft_f64_batch")
+        if self.prefix == "orc":
+            tw = None if twiddle is None else np.ascontiguousarray(twiddle, dtype=np.float64)
+            fn.argtypes = [C.c_uint32, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_int]
+            fn.restype = None
+            fn(N, y.ctypes.data, y.size // (2 * N), int(ifft), int(bitrev), None if tw is None else tw.ctypes.data, int(threads))
+        else:
+            assert twiddle is None
+            fn.argtypes = [C.c_uint32, C.c_void_p, C.c_uint64, C.c_int, C.c_int]
+            fn.restype = C.c_int
+            assert fn(N, y.ctypes.data, y.size // (2 * N), int(ifft), int(bitrev)) == 0
+        return y
+
+    def twiddle_f64(self, N):
+        fn = self._fn("twiddle_f64")
+        fn.argtypes = [C.c_uint32]
+        fn.restype = C.POINTER(C.c_double)
+        return np.ctypeslib.as_array(fn(N), shape=(2 * N,)).copy()
+
     def rfft(self, N, x, ifft=0, threads=1, return_clobbered=False):
         p = np.ascontiguousarray(x, dtype=np.float32).copy()
         assert p.size % N == 0

@@ -64,6 +64,21 @@ def test_cfft_bodies(emu, kind, N):
                 assert np.array_equal(got, want), (kind, N, ifft, bitrev)  # bit-exact
 
 
+@pytest.mark.parametrize("N", LENGTHS)
+def test_cfft_f64_bodies(emu, N):
+    """the f64 butterflies run in the reference's operation order: bit-identical to the oracle on the same table"""
+    tw, perm = product_tables("f64", N)
+    assert np.array_equal(tw, oracle().twiddle_f64(N))
+    rng = np.random.default_rng(N)
+    x = rng.standard_normal((2 * {16: 32, 32: 32, 64: 32, 128: 16, 256: 8, 512: 4, 1024: 2}.get(N, 1) + 3, 2 * N))
+    for ifft in (0, 1):
+        for bitrev in (0, 1):
+            want = oracle().cfft_f64(N, x, ifft, bitrev)
+            got = x.copy()
+            assert emu.emu_cfft(cd.TYPE_ID["f64"], N, got.ctypes.data, got.shape[0], ifft, bitrev, tw.ctypes.data, perm.ctypes.data) == 0
+            assert np.array_equal(got.view(np.uint64), want.view(np.uint64)), (N, ifft, bitrev)
+
+
 @pytest.mark.parametrize("N", RLENGTHS)
 def test_rfft_bodies(emu, N):
     tw, _ = cd.instance_tables(cd.cfft_instance("f32", N // 2), "f32")

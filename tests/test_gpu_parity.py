@@ -117,6 +117,65 @@ def test_fft_bin_example_known_answer():
 
 # ------------------------------------------------------------------ API behaviour
 
+# ------------------------------------------------------------------ arm_cfft_f64
+F64_TOL = 1e-15         # relative RMS against the compiled reference (its twiddle literals differ from ours by <= 1 ulp)
+
+
+@pytest.mark.parametrize("N", LENGTHS)
+def test_cfft_f64_all_modes(N):
+    """Bit-identical to the oracle (same operation order, no FMA contraction, same table); relative RMS <= 1e-15 per
+    frame against the reference's own build, whose table differs in the last place."""
+    from oracle_lib import ref
+    rng = np.random.default_rng(7000 + N)
+    x = rng.standard_normal((301, 2 * N))
+    x[1] *= 1e-6
+    x[2] *= 1e9
+    for ifft in (0, 1):
+        for bitrev in (0, 1):
+            want = oracle().cfft_f64(N, x, ifft, bitrev, threads=NT)
+            got = cd.cfft_batch("f64", N, x, ifft, bitrev)
+            assert np.array_equal(got.view(np.uint64), want.view(np.uint64)), (N, ifft, bitrev)
+            if ref() is not None:
+                r = ref().cfft_f64(N, x[:40], ifft, bitrev)
+                per_frame = np.sqrt(((got[:40] - r) ** 2).sum(1) / (r ** 2).sum(1))
+                assert per_frame.max() <= F64_TOL, (N, ifft, bitrev, per_frame.max())
+
+
+def test_cfft_f64_reference_patterns_legacy_call_and_device_pointers():
+    torch = pytest.importorskip("torch")
+    L = cd.lib()
+    n = 0
+    for N, sig, ifft, x, refv in golden_cases("f64", "c"):          # TransformCF64.cpp thresholds (SNR 250 dB)
+        buf = np.ascontiguousarray(x, dtype=np.float64).copy()
+        S = cd.cfft_instance("f64", N)
+        L.arm_cfft_f64(C.byref(S), buf.ctypes.data, ifft, 1)         # the reference's single-frame signature
+        assert L.arm_cuda_last_status() == 0
+        assert_like_reference("f64", "c", buf, refv, N, ifft)
+        n += 1
+    assert n == 36
+    dev = torch.device("cuda", 0)
+    for N, frames in ((16, 100003), (64, 4099), (1024, 2049), (4096, 1025)):
+        x = np.random.default_rng(N).standard_normal((frames, 2 * N))
+        cd.ensure_plans("f64", N)
+        t = torch.from_numpy(x).to(dev)
+        cd.cfft_device("f64", N, t.data_ptr(), frames, 0, 1, torch.cuda.current_stream().cuda_stream)
+        spec = t.cpu().numpy()
+        z = np.fft.fft(x[:, 0::2] + 1j * x[:, 1::2], axis=1)         # an independent DFT
+        assert relrms(spec[:, 0::2] + 1j * spec[:, 1::2], z) <= 1e-15 * np.log2(N)
+        sub = slice(0, 64)
+        assert np.array_equal(spec[sub], oracle().cfft_f64(N, x[sub], 0, 1))
+        cd.cfft_device("f64", N, t.data_ptr(), frames, 1, 1, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert relrms(t.cpu().numpy(), x) <= 1e-15 * np.log2(N)      # round trip
+        # misaligned device pointer: refused, not mangled
+        assert cd.cuda().cmsisdsp_cuda_cfft_f64(t.data_ptr() + 8, N, 1, 0, 1, 0) == -1
+    S = cd.cfft_instance("f64", 64)
+    assert L.arm_cfft_batch_f64(None, None, 1, 0, 1) == cd.ARM_MATH_ARGUMENT_ERROR
+    assert L.arm_cfft_batch_f64(C.byref(S), None, 1, 0, 1) == cd.ARM_MATH_ARGUMENT_ERROR
+    one = np.zeros(128)
+    assert L.arm_cfft_batch_f64(C.byref(S), one.ctypes.data, 0, 0, 1) == 0
+
+
 def test_legacy_single_frame_signatures():
     L = cd.lib()
     for kind in ("f32", "q31", "q15"):

@@ -25,6 +25,16 @@ def test_cfft_patterns(kind):
     assert n == 36          # 9 lengths x {noisy, step} x {fwd, inv}
 
 
+def test_cfft_f64_patterns():
+    """Testing/Patterns/DSP/Transform/TransformF64 with the thresholds of TransformCF64.cpp:6-8 (SNR 250 dB)."""
+    n = 0
+    for N, sig, ifft, x, ref in golden_cases("f64", "c"):
+        out = oracle().cfft_f64(N, x, ifft, 1).reshape(-1)
+        assert_like_reference("f64", "c", out, ref, N, ifft)
+        n += 1
+    assert n == 36
+
+
 def test_rfft_patterns():
     n = 0
     for N, sig, ifft, x, ref in golden_cases("f32", "r"):

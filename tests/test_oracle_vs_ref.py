@@ -121,3 +121,38 @@ def test_mfcc_bit_exact(n):
         b = ref().mfcc(cfg, x, stride=stride, threads=2)
         assert a.shape == b.shape and a.shape[0] >= 37
         assert np.array_equal(a, b), (n, stride, np.abs(a - b).max())
+
+
+# ------------------------------------------------------------------ arm_cfft_f64
+def test_f64_tables_within_one_ulp_of_the_reference():
+    """The reference's twiddleCoefF64_N literals follow no reproducible rule: the generated table may differ by one
+    unit in the last place, never more; the bit-reversal lists are the fixed-point ones (identical)."""
+    o, r = oracle(), ref()
+    for N in LENGTHS:
+        a, b = o.twiddle_f64(N), r.twiddle_f64(N)
+        d = np.abs(a.view(np.int64) - b.view(np.int64))
+        assert d.max() <= 1 and (d != 0).mean() <= 0.2, (N, int(d.max()), float((d != 0).mean()))
+        assert not np.signbit(a[a == 0]).any()
+        ln = np.zeros(1, dtype=np.uint16)
+        fn = r._fn("bitrev_f64")
+        import ctypes as C
+        fn.argtypes, fn.restype = [C.c_uint32, C.c_void_p], C.POINTER(C.c_uint16)
+        tab = np.ctypeslib.as_array(fn(N, ln.ctypes.data), shape=(int(ln[0]),))
+        assert np.array_equal(tab, o.bitrev("fixed", N))
+
+
+@pytest.mark.parametrize("N", LENGTHS)
+def test_cfft_f64_bit_exact_on_the_reference_table_and_1e15_on_the_generated_one(N):
+    rng = np.random.default_rng(3000 + N)
+    x = rng.standard_normal((6, 2 * N))
+    x[1] *= 1e-6
+    x[2] *= 1e9
+    tw = ref().twiddle_f64(N)
+    for ifft in (0, 1):
+        for bitrev in (0, 1):
+            b = ref().cfft_f64(N, x, ifft, bitrev)
+            a = oracle().cfft_f64(N, x, ifft, bitrev, twiddle=tw)
+            assert np.array_equal(a.view(np.uint64), b.view(np.uint64)), (N, ifft, bitrev)
+            g = oracle().cfft_f64(N, x, ifft, bitrev)
+            for f in range(x.shape[0]):
+                assert np.sqrt(((g[f] - b[f]) ** 2).sum() / (b[f] ** 2).sum()) <= 1e-15, (N, ifft, bitrev, f)

@@ -28,6 +28,15 @@ def test_generated_tables_match_oracle_and_reference(N):
             for chk in checkers:
                 assert np.array_equal(bits(tw), bits(chk.table(f"twiddle_{kind}", N))), (kind, N)
                 assert np.array_equal(br, chk.bitrev(which, N)), (kind, N)
+    # f64: the generated twiddles are the oracle's (within 1 ulp of the reference's literals, which follow no rule:
+    # test_oracle_vs_ref.py); the swap lists are the reference's own (its fixed-point lists)
+    for S in (cd.cfft_instance("f64", N), cd.preset("f64", N)):
+        tw, br = cd.instance_tables(S, "f64")
+        assert np.array_equal(tw.view(np.uint64), oracle().twiddle_f64(N).view(np.uint64))
+        for chk in checkers:
+            assert np.array_equal(br, chk.bitrev("fixed", N))
+        if ref() is not None:
+            assert np.abs(tw.view(np.int64) - ref().twiddle_f64(N).view(np.int64)).max() <= 1
     if N >= 32:
         for S in (cd.rfft_instance(N), cd.rfft_preset(N)):
             assert S.fftLenRFFT == N and S.Sint.fftLen == N // 2
@@ -101,7 +110,7 @@ def test_struct_layouts_match_reference():
     if ref() is not None:
         L = ref().lib
         for name, t in (("cfft_instance_f32", cd.arm_cfft_instance_f32), ("cfft_instance_q31", cd.arm_cfft_instance_q31),
-                        ("cfft_instance_q15", cd.arm_cfft_instance_q15), ("rfft_fast_instance_f32", cd.arm_rfft_fast_instance_f32),
+                        ("cfft_instance_q15", cd.arm_cfft_instance_q15), ("cfft_instance_f64", cd.arm_cfft_instance_f64), ("rfft_fast_instance_f32", cd.arm_rfft_fast_instance_f32),
                         ("rfft_instance_q31", cd.arm_rfft_instance_q31), ("rfft_instance_q15", cd.arm_rfft_instance_q15)):
             fn = getattr(L, f"ref_sizeof_{name}")
             fn.restype = C.c_uint32
@@ -142,17 +151,17 @@ def test_shared_objects_export_every_declared_symbol():
         assert hasattr(cu, name), name
     fr = cd.lib()
     names = _declared_functions(os.path.join(ROOT, "include", "dsp", "transform_functions.h"))
-    # 3x(9 per-length inits + init + exec) + rfft (8+1+1) + 4 batch + last_status + mfcc (8+1+1+1)
+    # 4x(9 per-length inits + init + exec) [f32, q31, q15, f64] + rfft (8+1+1) + 5 batch + last_status + mfcc (8+1+1+1)
     # + rfft_q31/q15 (init, exec, batch each; their per-length inits are declared through a macro)
     # + 3 fused spectrum epilogues (mag, mag squared, peak) + deprecated radix-4/2 API (4 x (init, exec, batch))
-    assert len(names) == 80
+    assert len(names) == 92
     for name in names:
         assert hasattr(fr, name), name
     for N in RFIX_LENGTHS:
         for kind in ("q31", "q15"):
             assert hasattr(fr, f"arm_rfft_init_{N}_{kind}")
     for N in LENGTHS:
-        for kind in ("f32", "q31", "q15"):
+        for kind in ("f32", "q31", "q15", "f64"):
             cd.preset(kind, N)
 
 
@@ -191,6 +200,11 @@ def test_no_cpu_fallback_without_a_device():
         oi = np.zeros(128, dtype=cd.NP_DTYPE[kind])
         assert getattr(L, f"arm_rfft_batch_{kind}")(C.byref(Sr), xi.ctypes.data, oi.ctypes.data, 1) == cd.ARM_MATH_ARGUMENT_ERROR
         assert not oi.any()
+    xd = np.arange(2 * 64, dtype=np.float64)
+    Sd = cd.cfft_instance("f64", 64)
+    assert L.arm_cfft_batch_f64(C.byref(Sd), xd.ctypes.data, 1, 0, 1) == cd.ARM_MATH_ARGUMENT_ERROR
+    L.arm_cfft_f64(C.byref(Sd), xd.ctypes.data, 0, 1)
+    assert L.arm_cuda_last_status() == cd.ARM_MATH_ARGUMENT_ERROR and np.array_equal(xd, np.arange(2 * 64, dtype=np.float64))
     assert not out.any() and np.array_equal(x, x0)
     assert cd.last_error() != ""
     assert cu.cmsisdsp_cuda_launch_count() == 0

@@ -59,18 +59,20 @@ def main():
             nbytes = args.mib << 20
             if op.startswith("cfft") and op not in ("cfft_mag", "cfft_peak"):
                 kind = op.split("_")[1]
-                esz = {"f32": 8, "q31": 8, "q15": 4}[kind]
+                esz = {"f32": 8, "q31": 8, "q15": 4, "f64": 16}[kind]
                 B = nbytes // (esz * N)
                 cd.ensure_plans(kind, N)
                 buf = torch.zeros(B * N * esz // 4, dtype=torch.int32, device=dev)
                 if kind == "f32":
                     buf.view(torch.float32).normal_()
+                elif kind == "f64":
+                    buf.view(torch.float64).normal_()
                 else:
                     buf.random_(-2**20, 2**20)
                 fn = lambda: cd.cfft_device(kind, N, buf.data_ptr(), B, 0, 1, st)
                 alg = 2 * B * N * esz
                 samples = B * N
-                info = cd.kernel_info({"f32": 0, "q31": 1, "q15": 2}[kind], N)
+                info = cd.kernel_info({"f32": 0, "q31": 1, "q15": 2, "f64": 10}[kind], N)
             elif op == "mfcc":
                 sys.path.insert(0, os.path.join(ROOT, "tests"))
                 from oracle_lib import mfcc_config
