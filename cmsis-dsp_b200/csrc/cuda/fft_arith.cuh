@@ -214,6 +214,8 @@ template <int R, bool TW> FFT_HD void dft_f32(cf32 *x, const cf32 *tw)
 /* An Arith names four representations of a complex point: elem (HBM), work (registers),
  * xelem (shared-memory exchange) and telem (device twiddle table). */
 struct ArithF32 {
+    static constexpr bool kDirectTw = false;
+    static constexpr int kTableNum = 1, kTableDen = 1;
     typedef cf32 elem;
     typedef cf32 work;
     typedef cf32 twid;
@@ -281,7 +283,14 @@ template <bool INV> FFT_HD ci32 rot_q31(int32_t R, int32_t S, ci32 w)
     return {wsub(hi32(R, w.x), hi32(S, w.y)), wadd(hi32(S, w.x), hi32(R, w.y))};
 }
 
+#if defined(FFT_FIX_DIRECT_TW)
+#define FFT_FIX_DIRECT_TW_VALUE true
+#else
+#define FFT_FIX_DIRECT_TW_VALUE false
+#endif
 struct ArithQ31 {
+    static constexpr bool kDirectTw = FFT_FIX_DIRECT_TW_VALUE;     /* fft_frame.cuh: PassFix::kDirect */
+    static constexpr int kTableNum = 3, kTableDen = 4;        /* reference table: 3N/4 entries */
     typedef ci32 elem;      /* storage element */
     typedef ci32 work;      /* register element */
     typedef ci32 twid;
@@ -426,6 +435,8 @@ template <bool INV> FFT_HD ci32 rot_q15(int32_t x, int32_t y, ci32 w)
 }
 
 struct ArithQ15 {
+    static constexpr bool kDirectTw = FFT_FIX_DIRECT_TW_VALUE;
+    static constexpr int kTableNum = 3, kTableDen = 4;
     typedef ci16 elem;
     typedef ci32 work;      /* int16 values carried sign-extended in 32-bit registers */
     typedef ci32 twid;
@@ -526,6 +537,8 @@ struct ArithQ15 {
  * (-ffp-contract=off) -- the f64 kernels have the arithmetic headroom (16 bytes per point).  The inverse is conjugate -> forward -> conjugate / N (:262-312), done by CfftBody at the load and
  * the store like f32, so the butterflies have no inverse variant. */
 struct ArithF64 {
+    static constexpr bool kDirectTw = false;
+    static constexpr int kTableNum = 1, kTableDen = 1;        /* reference table: N entries */
     typedef cf64 elem;
     typedef cf64 work;
     typedef cf64 twid;
@@ -579,6 +592,19 @@ struct ArithF64 {
         A = {a0, a1};
         B = rot(xt, yt, w);
     }
+};
+
+/* the same arithmetic reading the reference-layout twiddle table (PassFix::kDirect, fft_frame.cuh): used for
+ * N >= 2048, where the pass-ordered copy (16-byte entries) no longer fits next to the exchange buffers in L1.
+ * Measured on B200 (profiles/r1_f_notes.md): N = 2048 68.6 -> 84.4 %, N = 4096 56.5 -> 68.7 % of the HBM peak;
+ * N <= 1024 is 0-2 points faster with the pass-ordered copy.  The same switch for q31 / q15 (FFT_FIX_DIRECT_TW,
+ * 8-byte entries, tables a third the size) measured 1-4 points SLOWER at every length and stays off. */
+struct ArithF64D : ArithF64 {
+#if defined(FFT_F64_ORDERED_TW)
+    static constexpr bool kDirectTw = false;
+#else
+    static constexpr bool kDirectTw = true;
+#endif
 };
 
 }  // namespace b200fft

@@ -40,6 +40,7 @@ namespace b200fft {
 template <int R_> struct PassF32 {
     static constexpr int R = R_;
     static constexpr bool kMirror = false;
+    static constexpr bool kDirect = false;
     typedef cf32 telem;
     static FFT_HD int out_index(int e) { return e; }
     /* twiddle slots per butterfly in the pass-ordered table (none on the last pass: W^0) */
@@ -102,7 +103,12 @@ template <class ARITH, int KA, int KB = -1, int KC = -1> struct PassFix {
     static constexpr int tw_of(int K) { return K < 0 ? 0 : (K == ST_PRE2 ? 1 : (K == ST_LAST4 ? 0 : 3)); }
     static constexpr int ta = tw_of(KA), tb = tw_of(KB), tc = tw_of(KC);   /* twiddles per butterfly of each stage */
     static constexpr int kOffB = rb * rc * ta, kOffC = kOffB + rc * tb;
-    static constexpr int slots(bool) { return kOffC + tc; }
+    /* kDirect (Arith::kDirectTw): the pass reads the REFERENCE-layout table at the reference's own indices
+     * (compute_direct) instead of a pass-ordered copy.  The pass-ordered copy makes every warp load contiguous
+     * but is ~3 N entries per plan; with 16-byte entries (f64, N = 4096: 184 KiB against a 64 KiB table) it
+     * falls out of L1 and every frame re-reads it from L2 -- more bytes than the frame itself. */
+    static constexpr bool kDirect = ARITH::kDirectTw;
+    static constexpr int slots(bool) { return kDirect ? 0 : kOffC + tc; }
 
     /* pass-ordered table of butterfly j, sp = S*(j/S):
      *   stage a, sub-butterfly o < rb*rc : slots o*ta + m-1        = W^(m * (sp + (N/R) o))
@@ -113,7 +119,7 @@ template <class ARITH, int KA, int KB = -1, int KC = -1> struct PassFix {
     template <int N, int S> static void fill(const selem *base, telem *out, bool)
     {
         constexpr int NBF = N / R;
-        for (int j = 0; j < NBF; j++) {
+        for (int j = 0; j < (kDirect ? 0 : NBF); j++) {
             const int sp = S * (j / S);
             for (int o = 0; o < rb * rc; o++)
                 for (int m = 1; m <= ta; m++) out[(o * ta + m - 1) * NBF + j] = ARITH::tw_expand(base[m * (sp + (N / R) * o)]);
@@ -132,6 +138,47 @@ template <class ARITH, int KA, int KB = -1, int KC = -1> struct PassFix {
         } else {
             ARITH::template bfly4<K, INV>(a, b, c, d, ARITH::tload(twp[slot * NBF + j]), ARITH::tload(twp[(slot + 1) * NBF + j]),
                                           ARITH::tload(twp[(slot + 2) * NBF + j]));
+        }
+    }
+
+    /* radix-4 stage on the reference-layout table: W^1, W^2, W^3 at ia, 2 ia, 3 ia (arm_cfft_radix4_q31.c:229-266) */
+    template <int K, bool INV>
+    static FFT_HD void stage4d(work &a, work &b, work &c, work &d, const telem *__restrict__ tw, int ia)
+    {
+        if (K == ST_LAST4) {
+            twid z = {0, 0};
+            ARITH::template bfly4<K, INV>(a, b, c, d, z, z, z);
+        } else {
+            ARITH::template bfly4<K, INV>(a, b, c, d, ARITH::tload(tw[ia]), ARITH::tload(tw[2 * ia]), ARITH::tload(tw[3 * ia]));
+        }
+    }
+    /* same butterflies as compute(), twiddle indices as in fill(): S = product of the radices of the earlier passes */
+    template <bool INV, int N, int S>
+    static FFT_HD void compute_direct(work *x, const telem *__restrict__ tw, int j)
+    {
+        constexpr int NBF = N / R, Q = rb * rc;
+        const int sp = S * (j / S);
+#pragma unroll
+        for (int o = 0; o < Q; o++) {                 /* stage a */
+            const int ia = sp + NBF * o;
+            if (KA == ST_PRE2)
+                ARITH::template bfly2<INV>(x[o], x[o + Q], ARITH::tload(tw[ia]));
+            else
+                stage4d<KA, INV>(x[o], x[o + Q], x[o + 2 * Q], x[o + 3 * Q], tw, ia);
+        }
+        if constexpr (KB >= 0) {                      /* stage b */
+#pragma unroll
+            for (int v = 0; v < ra; v++)
+#pragma unroll
+                for (int u = 0; u < rc; u++) {
+                    const int base = u + Q * v;
+                    stage4d<KB, INV>(x[base], x[base + rc], x[base + 2 * rc], x[base + 3 * rc], tw, ra * (sp + NBF * u));
+                }
+        }
+        if constexpr (KC >= 0) {                      /* stage c */
+#pragma unroll
+            for (int g = 0; g < ra * rb; g++)
+                stage4d<KC, INV>(x[4 * g], x[4 * g + 1], x[4 * g + 2], x[4 * g + 3], tw, ra * rb * sp);
         }
     }
 
@@ -168,8 +215,12 @@ template <class ARITH, int KA, int KB = -1, int KC = -1> struct PassFix {
 struct NoPass {
     static constexpr int R = 1;
     static constexpr bool kMirror = false;
+    static constexpr bool kDirect = false;
     static constexpr int slots(bool) { return 0; }
 };
+
+/* entries of the reference-layout twiddle table of an Arith with direct passes */
+template <class A, int N> constexpr int direct_entries() { return A::kDirectTw ? A::kTableNum * N / A::kTableDen : 0; }
 
 template <class ARITH_, int N_, int T_, int F_, int PADA_, int PADB_, class P0_, class P1_ = NoPass, class P2_ = NoPass>
 struct Plan {
@@ -203,10 +254,17 @@ struct Plan {
     static constexpr int kTw0 = P0::slots(NP == 1) * (N / P0::R);
     static constexpr int kTw1 = (NP > 1) ? P1::slots(NP == 2) * (N / P1::R) : 0;
     static constexpr int kTw2 = (NP > 2) ? P2::slots(true) * (N / P2::R) : 0;
-    static constexpr int kTwEntries = kTw0 + kTw1 + kTw2;
-    /* build the table from the reference-layout twiddles (N entries f32, 3N/4 entries q31/q15) */
+    /* direct passes (PassFix::kDirect) share one copy of the reference-layout table */
+    static constexpr bool kDirectTw = P0::kDirect;
+    static_assert((P1::R == 1 || P1::kDirect == kDirectTw) && (P2::R == 1 || P2::kDirect == kDirectTw), "all passes alike");
+    static constexpr int kTwEntries = kDirectTw ? direct_entries<ARITH_, N>() : kTw0 + kTw1 + kTw2;
+    /* build the table from the reference-layout twiddles (N entries f32 / f64, 3N/4 entries q31/q15) */
     static void build_twiddles(const typename ARITH_::elem *base, typename ARITH_::telem *out)
     {
+        if constexpr (kDirectTw) {
+            for (int i = 0; i < kTwEntries; i++) out[i] = ARITH_::tw_expand(base[i]);
+            return;
+        }
         P0::template fill<N, S0>(base, out, NP == 1);
         if constexpr (NP > 1) P1::template fill<N, S1>(base, out + kTw0, NP == 2);
         if constexpr (NP > 2) P2::template fill<N, S2>(base, out + kTw0 + kTw1, true);
@@ -279,7 +337,8 @@ template <class PL> struct Engine {
 #pragma unroll
         for (int b = 0; b < NB; b++) {
             const int j = bfly_index<PS::kMirror, T, NBF>(i, b);
-            PS::template compute<INV, N, (P == NP - 1)>(&r.v[b * R], tw + PassOf<PL, P>::TWOFF, j);
+            if constexpr (PS::kDirect) PS::template compute_direct<INV, N, S>(&r.v[b * R], tw, j);
+            else PS::template compute<INV, N, (P == NP - 1)>(&r.v[b * R], tw + PassOf<PL, P>::TWOFF, j);
         }
     }
 

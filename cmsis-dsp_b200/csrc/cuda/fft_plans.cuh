@@ -93,18 +93,22 @@ FIXPLAN(4096, 256, 1,   4, 1, PF(ST_FIRST4, ST_MID4), PF(ST_MID4, ST_MID4), PF(S
 
 /* ---- f64 complex (arm_cfft_f64.c: the fixed-point stage structure, 16-byte points) ----
  * 16 points (64 registers) per thread from N = 64 up; the short lengths use 4 threads per frame so that a
- * frame's loads stay 64-byte pieces (one thread per frame would read 16-byte pieces 16 N bytes apart). */
+ * frame's loads stay 64-byte pieces (one thread per frame would read 16-byte pieces 16 N bytes apart).
+ * Exchange padding: one element after every 2^PADA, chosen so that every exchange is conflict-free for 16-byte
+ * elements (tests/test_emulator.py::test_f64_exchange_bank_conflicts): 8 where the first pass is radix 8. */
 template <int N> struct PlanCfftF64;
 #define PD(...) PassFix<ArithF64, __VA_ARGS__>
-template <> struct PlanCfftF64<16>   { typedef Plan<ArithF64, 16,   4,   32, 4, 1, PD(ST_FIRST4), PD(ST_LAST4)> type; };
-template <> struct PlanCfftF64<32>   { typedef Plan<ArithF64, 32,   4,   32, 4, 1, PD(ST_PRE2, ST_FIRST4), PD(ST_LAST4)> type; };
+template <> struct PlanCfftF64<16>   { typedef Plan<ArithF64, 16,   4,   32, 2, 1, PD(ST_FIRST4), PD(ST_LAST4)> type; };
+template <> struct PlanCfftF64<32>   { typedef Plan<ArithF64, 32,   4,   32, 3, 1, PD(ST_PRE2, ST_FIRST4), PD(ST_LAST4)> type; };
 template <> struct PlanCfftF64<64>   { typedef Plan<ArithF64, 64,   4,   32, 4, 1, PD(ST_FIRST4, ST_MID4), PD(ST_LAST4)> type; };
-template <> struct PlanCfftF64<128>  { typedef Plan<ArithF64, 128,  8,   16, 4, 1, PD(ST_PRE2, ST_FIRST4), PD(ST_MID4, ST_LAST4)> type; };
+template <> struct PlanCfftF64<128>  { typedef Plan<ArithF64, 128,  8,   16, 3, 1, PD(ST_PRE2, ST_FIRST4), PD(ST_MID4, ST_LAST4)> type; };
 template <> struct PlanCfftF64<256>  { typedef Plan<ArithF64, 256,  16,  8,  4, 1, PD(ST_FIRST4, ST_MID4), PD(ST_MID4, ST_LAST4)> type; };
-template <> struct PlanCfftF64<512>  { typedef Plan<ArithF64, 512,  32,  4,  4, 1, PD(ST_PRE2, ST_FIRST4), PD(ST_MID4, ST_MID4), PD(ST_LAST4)> type; };
+template <> struct PlanCfftF64<512>  { typedef Plan<ArithF64, 512,  32,  4,  3, 1, PD(ST_PRE2, ST_FIRST4), PD(ST_MID4, ST_MID4), PD(ST_LAST4)> type; };
 template <> struct PlanCfftF64<1024> { typedef Plan<ArithF64, 1024, 64,  2,  4, 1, PD(ST_FIRST4, ST_MID4), PD(ST_MID4, ST_MID4), PD(ST_LAST4)> type; };
-template <> struct PlanCfftF64<2048> { typedef Plan<ArithF64, 2048, 128, 1,  4, 1, PD(ST_PRE2, ST_FIRST4), PD(ST_MID4, ST_MID4), PD(ST_MID4, ST_LAST4)> type; };
-template <> struct PlanCfftF64<4096> { typedef Plan<ArithF64, 4096, 256, 1,  4, 1, PD(ST_FIRST4, ST_MID4), PD(ST_MID4, ST_MID4), PD(ST_MID4, ST_LAST4)> type; };
+#define PDD(...) PassFix<ArithF64D, __VA_ARGS__>       /* twiddles from the reference-layout table (ArithF64D) */
+template <> struct PlanCfftF64<2048> { typedef Plan<ArithF64D, 2048, 128, 1, 3, 1, PDD(ST_PRE2, ST_FIRST4), PDD(ST_MID4, ST_MID4), PDD(ST_MID4, ST_LAST4)> type; };
+template <> struct PlanCfftF64<4096> { typedef Plan<ArithF64D, 4096, 256, 1, 4, 1, PDD(ST_FIRST4, ST_MID4), PDD(ST_MID4, ST_MID4), PDD(ST_MID4, ST_LAST4)> type; };
+#undef PDD
 #undef PD
 
 }  // namespace b200fft

@@ -21,7 +21,12 @@
  * rfft_q31 forward up to complex 256 and rfft_q31 inverse; they lose 2-13 points for the 256-thread CTAs of N = 4096
  * and for the q15 real FFT, and are neutral for cfft_q15. */
 #ifndef KU_MINB
-#if KU_OP == 0 || KU_OP == 3 || KU_OP == 4 || KU_OP == 9 || KU_OP == 6 || (KU_OP == 10 && KU_N <= 1024) || (KU_OP == 1 && KU_N <= 2048) || (KU_OP == 5 && KU_N <= 256)
+#if KU_OP == 10 && (KU_N == 1024 || KU_N == 2048)
+/* cfft_f64: 128 registers / 4 CTAs at N = 1024 (92.1 vs 91.1 % of the HBM peak with free registers), 96 / 5 CTAs at
+ * N = 2048 (84.9 vs 84.3 %); N = 4096 stays on ptxas' own choice (128 registers, 2 CTAs of 256 threads: a third CTA
+ * needs 80 registers, spills, 68.5 -> 48.8 %) */
+#define KU_MINB (KU_N == 1024 ? 4 : 5)
+#elif KU_OP == 0 || KU_OP == 3 || KU_OP == 4 || KU_OP == 9 || KU_OP == 6 || (KU_OP == 10 && KU_N <= 512) || (KU_OP == 1 && KU_N <= 2048) || (KU_OP == 5 && KU_N <= 256)
 #define KU_MINB 1
 #else
 #define KU_MINB 0
@@ -493,8 +498,8 @@ static bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }   /* 
 #if KU_OP <= 2 || KU_OP == 10   /* complex FFT, in place */
 
 #if KU_OP == 10
-typedef ArithF64 AR;
 typedef PlanCfftF64<KU_N>::type PL;
+typedef PL::Arith AR;
 #elif KU_OP == 0
 typedef ArithF32 AR;
 typedef PlanCfftF32<KU_N>::type PL;

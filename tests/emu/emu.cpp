@@ -110,8 +110,8 @@ template <int N> static void cfft_f32_n(float *d, uint64_t n, int inv, const voi
 template <int N> static void cfft_f64_n(double *d, uint64_t n, int inv, const void *tw, const uint16_t *perm)
 {
     typedef typename PlanCfftF64<N>::type PL;
-    if (inv) cfft_run<ArithF64, PL, true>((cf64 *)d, n, tw, perm, 0);
-    else cfft_run<ArithF64, PL, false>((cf64 *)d, n, tw, perm, 0);
+    if (inv) cfft_run<typename PL::Arith, PL, true>((cf64 *)d, n, tw, perm, 0);
+    else cfft_run<typename PL::Arith, PL, false>((cf64 *)d, n, tw, perm, 0);
 }
 template <class AR, int N> static void cfft_fix_n(void *d, uint64_t n, int inv, const void *tw, const uint16_t *perm)
 {

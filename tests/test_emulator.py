@@ -115,6 +115,17 @@ def test_exchange_bank_conflicts(emu, kind, N, limit):
         assert wf <= limit * ideal, (kind, N, int(ph), "store" if st else "load", wf / ideal)
 
 
+@pytest.mark.parametrize("N", LENGTHS)
+def test_f64_exchange_bank_conflicts(emu, N):
+    """16-byte exchange elements (a quarter warp per wavefront): every f64 plan is conflict-free"""
+    tw, _ = product_tables("f64", N)
+    y = np.zeros((64, 2 * N))
+    rows = _trace(emu, lambda: emu.emu_cfft(cd.TYPE_ID["f64"], N, y.ctypes.data, 64, 0, 1, tw.ctypes.data, None))
+    assert len(rows) > 0
+    for ph, st, nbytes, req, ideal, wf in rows:
+        assert nbytes == 16 and wf == ideal, (N, int(ph), "store" if st else "load", wf / ideal)
+
+
 @pytest.mark.parametrize("N", [512, 1024, 2048, 4096])
 @pytest.mark.parametrize("ifft", [0, 1])
 def test_rfft_exchange_bank_conflicts(emu, N, ifft):
