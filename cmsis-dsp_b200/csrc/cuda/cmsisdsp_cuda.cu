@@ -104,6 +104,7 @@ struct DevPlan {
 struct DevState {
     DevPlan plan[4][9];           /* [CMSISDSP_CUDA_F32 / Q31 / Q15 / F64][length] */
     float *twr[9] = {};           /* rfft twiddles, indexed by len_index(real length) */
+    double *twr64[9] = {};        /* arm_rfft_fast_f64: twiddleCoefF64_rfft_N, same index */
     void *rcoef[3][9] = {};       /* q31 / q15 real FFT: split coefficients (ci32x4 per bin), indexed by len_index(fftLenReal / 2) */
 };
 static const int kMaxDev = 64;
@@ -282,18 +283,25 @@ int shim_rfft_tables(uint32_t fftLenReal, const void **twForward, const float **
 
 /* ------------------------------------------------------------------ transforms */
 
+static int cfft_io(int type, const void *d_in, void *d_p, uint32_t fftLen, uint64_t nFrames, uint8_t ifftFlag, uint8_t bitReverseFlag, void *stream);
 static int cfft_any(int type, void *d_p, uint32_t fftLen, uint64_t nFrames, uint8_t ifftFlag, uint8_t bitReverseFlag, void *stream)
 {
-    if (!d_p && nFrames) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "null data pointer");
+    return cfft_io(type, d_p, d_p, fftLen, nFrames, ifftFlag, bitReverseFlag, stream);
+}
+/* d_in == d_p: in place; otherwise frames are read from d_in and written to d_p (the direct kernels never read a
+ * frame after they started to write it, so the two may also be distinct buffers) */
+static int cfft_io(int type, const void *d_in, void *d_p, uint32_t fftLen, uint64_t nFrames, uint8_t ifftFlag, uint8_t bitReverseFlag, void *stream)
+{
+    if ((!d_p || !d_in) && nFrames) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "null data pointer");
     DevPlan pl;
     int rc = get_plan(type, fftLen, &pl);
     if (rc) return rc;
     const int li = len_index(fftLen);
     /* N = 2*4^m: final << 1 (fixed point only; arm_cfft_q31.c:803-820, arm_cfft_q15.c:810-827) */
     const int shl1 = (type == CMSISDSP_CUDA_Q31 || type == CMSISDSP_CUDA_Q15) ? ((li + 4) & 1) : 0;
-    if (type == CMSISDSP_CUDA_F64 && ((uintptr_t)d_p & 15u)) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "cfft_f64: data must be 16-byte aligned");
+    if (type == CMSISDSP_CUDA_F64 && (((uintptr_t)d_p | (uintptr_t)d_in) & 15u)) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "cfft_f64: data must be 16-byte aligned");
     const KernelEntry *ke = kEntries[cfft_op(type)][li];
-    return ke->launch(d_p, d_p, nFrames, ifftFlag == 1, pl.tw, bitReverseFlag ? nullptr : pl.perm, shl1, choose_flavour(ke),
+    return ke->launch(d_in, d_p, nFrames, ifftFlag == 1, pl.tw, bitReverseFlag ? nullptr : pl.perm, shl1, choose_flavour(ke),
                       (cudaStream_t)stream);
 }
 
@@ -328,6 +336,110 @@ extern "C" int cmsisdsp_cuda_rfft_fast_f32(const void *d_p, void *d_out, uint32_
     const KernelEntry *ke = kEntries[ifftFlag ? OP_RFFT_INV : OP_RFFT_FWD][li - 1];
     return ke->launch(d_p, d_out, nFrames, ifftFlag != 0, ifftFlag ? pl.tw_rinv : pl.tw_rfwd, twr, 0, choose_flavour(ke),
                       (cudaStream_t)stream);
+}
+
+/* ------------------------------------------------------------------ arm_rfft_fast_f64 (arm_rfft_fast_f64.c:207-233)
+ *
+ * An adapter over the f64 complex kernels, not a fused kernel: forward = N/2-point CFFT written
+ * to d_out, then the split stage in place on d_out; inverse = merge stage d_p -> d_out, then the inverse CFFT in place.
+ * One thread owns the bin pair (k, L - k), so the stages can run in place.  The arithmetic follows stage_rfft_f64
+ * (:30-118) and merge_rfft_f64 (:121-181) operation for operation, products rounded on their own. */
+extern "C" int cmsisdsp_cuda_rfft_f64_plan_upload(uint32_t fftLenReal, const double *pTwiddleRFFT)
+{
+    const int li = len_index(fftLenReal);
+    if (li < 1 || !pTwiddleRFFT) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "rfft_f64_plan_upload: bad length / pointer");
+    int dev;
+    int rc = cur_device(&dev);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_dev[dev].twr64[li]) return CMSISDSP_CUDA_OK;
+    double *d = nullptr;
+    CU_TRY(cudaMalloc((void **)&d, fftLenReal * sizeof(double)));
+    CU_TRY(cudaMemcpy(d, pTwiddleRFFT, fftLenReal * sizeof(double), cudaMemcpyHostToDevice));
+    g_dev[dev].twr64[li] = d;
+    return CMSISDSP_CUDA_OK;
+}
+extern "C" int cmsisdsp_cuda_rfft_f64_plan_ready(uint32_t fftLenReal)
+{
+    const int li = len_index(fftLenReal);
+    int dev;
+    if (li < 1 || cur_device(&dev)) return 0;
+    std::lock_guard<std::mutex> lk(g_mu);
+    return g_dev[dev].twr64[li] != nullptr && g_dev[dev].plan[CMSISDSP_CUDA_F64][li - 1].tw != nullptr;
+}
+
+/* split: X = CFFT of the packed frame (L complex bins) -> packed real spectrum; both in `x` */
+static __device__ __forceinline__ double2 rfft64_split(double2 a, double2 b, double2 tw)       /* :102-115 */
+{
+    const double t1a = b.x - a.x, t1b = b.y + a.y;
+    const double p0 = __dmul_rn(tw.x, t1a), p1 = __dmul_rn(tw.y, t1a), p2 = __dmul_rn(tw.x, t1b), p3 = __dmul_rn(tw.y, t1b);
+    return make_double2(__dmul_rn(0.5, ((a.x + b.x) + p0) + p3), __dmul_rn(0.5, ((a.y - b.y) + p1) - p2));
+}
+static __device__ __forceinline__ double2 rfft64_merge(double2 a, double2 b, double2 tw)       /* :159-177 */
+{
+    const double t1a = a.x - b.x, t1b = a.y + b.y;
+    const double r = __dmul_rn(tw.x, t1a), s = __dmul_rn(tw.y, t1b), t = __dmul_rn(tw.y, t1a), u = __dmul_rn(tw.x, t1b);
+    return make_double2(__dmul_rn(0.5, ((a.x + b.x) - r) - s), __dmul_rn(0.5, ((a.y - b.y) + t) - u));
+}
+template <bool MERGE>
+__global__ void __launch_bounds__(256) rfft64_stage_kernel(const double2 *__restrict__ src, double2 *dst, const double2 *__restrict__ twr,
+                                                           uint32_t L, uint64_t nFrames)
+{
+    const uint32_t per = L / 2 + 1;                         /* bin pairs (k, L - k), k = 0 .. L/2 */
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nFrames * per) return;
+    const uint64_t frame = idx / per;
+    const uint32_t k = (uint32_t)(idx % per);
+    const double2 *x = src + frame * L;
+    double2 *y = dst + frame * L;
+    if (k == 0) {
+        const double2 a = x[0];
+        if (MERGE) y[0] = make_double2(__dmul_rn(0.5, a.x + a.y), __dmul_rn(0.5, a.x - a.y));             /* :143-144 */
+        else { const double t1a = a.x + a.x, t1b = a.y + a.y; y[0] = make_double2(__dmul_rn(0.5, t1a + t1b), __dmul_rn(0.5, t1a - t1b)); }   /* :56-65 */
+        return;
+    }
+    const double2 a = x[k], b = x[L - k];
+    const double2 oa = MERGE ? rfft64_merge(a, b, twr[k]) : rfft64_split(a, b, twr[k]);
+    if (2 * k != L) {
+        const double2 ob = MERGE ? rfft64_merge(b, a, twr[L - k]) : rfft64_split(b, a, twr[L - k]);
+        y[L - k] = ob;
+    }
+    y[k] = oa;
+}
+
+extern "C" int cmsisdsp_cuda_rfft_fast_f64(const void *d_p, void *d_out, uint32_t fftLenReal, uint64_t nFrames, uint8_t ifftFlag, void *stream)
+{
+    if ((!d_p || !d_out) && nFrames) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "null data pointer");
+    if (d_p == d_out && nFrames) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "rfft_fast_f64: p and pOut must not alias");
+    if (((uintptr_t)d_p | (uintptr_t)d_out) & 15u) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "rfft_fast_f64: data must be 16-byte aligned");
+    const int li = len_index(fftLenReal);
+    if (li < 1) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "unsupported rfft length (32..4096, power of two)");
+    int dev;
+    int rc = cur_device(&dev);
+    if (rc) return rc;
+    const double *twr;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        twr = g_dev[dev].twr64[li];
+    }
+    if (!twr) return fail(CMSISDSP_CUDA_ERR_NO_PLAN, "no f64 rfft plan uploaded for this (device, fftLen)");
+    if (nFrames == 0) return CMSISDSP_CUDA_OK;
+    const uint32_t L = fftLenReal / 2;
+    const uint64_t items = nFrames * (uint64_t)(L / 2 + 1), blocks = (items + 255) / 256;
+    if (blocks > 0x7fffffffull) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "batch too large for one launch");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!ifftFlag) {
+        rc = cfft_io(CMSISDSP_CUDA_F64, d_p, d_out, L, nFrames, 0, 1, stream);
+        if (rc) return rc;
+        rfft64_stage_kernel<false><<<(unsigned)blocks, 256, 0, st>>>((const double2 *)d_out, (double2 *)d_out, (const double2 *)twr, L, nFrames);
+        shim_count_launch();
+        CU_TRY(cudaGetLastError());
+        return CMSISDSP_CUDA_OK;
+    }
+    rfft64_stage_kernel<true><<<(unsigned)blocks, 256, 0, st>>>((const double2 *)d_p, (double2 *)d_out, (const double2 *)twr, L, nFrames);
+    shim_count_launch();
+    CU_TRY(cudaGetLastError());
+    return cfft_any(CMSISDSP_CUDA_F64, d_out, L, nFrames, 1, 1, stream);
 }
 
 /* arm_cfft_f32 + spectrum epilogue: mode 0 magnitudes, 1 squared magnitudes (d_out: fftLen floats per frame),

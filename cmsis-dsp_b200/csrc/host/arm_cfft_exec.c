@@ -193,6 +193,57 @@ arm_status arm_rfft_fast_batch_f32(const arm_rfft_fast_instance_f32 *S, float32_
     return rfft_batch(S, p, pOut, nFrames, ifftFlag, 0);
 }
 
+/* arm_rfft_fast_f64: same contract as rfft_batch above, 8-byte scalars, the f64 shim entry */
+static arm_status rfft64_batch(const arm_rfft_fast_instance_f64 *S, float64_t *p, float64_t *pOut,
+                               uint64_t nFrames, uint8_t ifftFlag, int clobber)
+{
+    if (!S || !p || !pOut || p == pOut || !S->pTwiddleRFFT || !S->Sint.pTwiddle) return ARM_MATH_ARGUMENT_ERROR;
+    const uint32_t N = S->fftLenRFFT;
+    if (N < 32 || !valid_len(N)) return ARM_MATH_ARGUMENT_ERROR;
+    if (nFrames == 0) return ARM_MATH_SUCCESS;
+    if (ctx_ready()) return ARM_MATH_ARGUMENT_ERROR;
+    if (ensure_plan(CMSISDSP_CUDA_F64, N / 2, S->Sint.pTwiddle, S->Sint.pBitRevTable, S->Sint.bitRevLength))
+        return ARM_MATH_ARGUMENT_ERROR;
+    if (!cmsisdsp_cuda_rfft_f64_plan_ready(N) && cmsisdsp_cuda_rfft_f64_plan_upload(N, S->pTwiddleRFFT))
+        return ARM_MATH_ARGUMENT_ERROR;
+
+    const size_t frameBytes = (size_t)N * sizeof(float64_t);
+    const int inDev = cmsisdsp_cuda_is_device_pointer(p), outDev = cmsisdsp_cuda_is_device_pointer(pOut);
+    if (inDev < 0 || outDev < 0 || inDev != outDev) return ARM_MATH_ARGUMENT_ERROR;
+    if (inDev) {
+        if (cmsisdsp_cuda_rfft_fast_f64(p, pOut, N, nFrames, ifftFlag, g_ctx.stream[0])) return ARM_MATH_ARGUMENT_ERROR;
+        if (clobber && !ifftFlag && cmsisdsp_cuda_cfft_f64(p, N / 2, nFrames, 0, 1, g_ctx.stream[0])) return ARM_MATH_ARGUMENT_ERROR;
+        return cmsisdsp_cuda_stream_synchronize(g_ctx.stream[0]) ? ARM_MATH_ARGUMENT_ERROR : ARM_MATH_SUCCESS;
+    }
+    uint64_t perChunk = CHUNK_BYTES / frameBytes;
+    if (perChunk == 0) perChunk = 1;
+    int rc = 0, s = 0;
+    for (uint64_t f = 0; f < nFrames && !rc; f += perChunk, s = (s + 1) % NSTREAM) {
+        const uint64_t n = (nFrames - f < perChunk) ? nFrames - f : perChunk;
+        char *hin = (char *)p + f * frameBytes, *hout = (char *)pOut + f * frameBytes;
+        void *din, *dout;
+        if ((rc = staging(s, 0, (size_t)perChunk * frameBytes, &din))) break;
+        if ((rc = staging(s, 1, (size_t)perChunk * frameBytes, &dout))) break;
+        if ((rc = cmsisdsp_cuda_memcpy_h2d(din, hin, (size_t)n * frameBytes, g_ctx.stream[s]))) break;
+        if ((rc = cmsisdsp_cuda_rfft_fast_f64(din, dout, N, n, ifftFlag, g_ctx.stream[s]))) break;
+        if ((rc = cmsisdsp_cuda_memcpy_d2h(hout, dout, (size_t)n * frameBytes, g_ctx.stream[s]))) break;
+        if (clobber && !ifftFlag) {
+            if ((rc = cmsisdsp_cuda_cfft_f64(din, N / 2, n, 0, 1, g_ctx.stream[s]))) break;
+            rc = cmsisdsp_cuda_memcpy_d2h(hin, din, (size_t)n * frameBytes, g_ctx.stream[s]);
+        }
+    }
+    for (int i = 0; i < NSTREAM; i++)
+        if (cmsisdsp_cuda_stream_synchronize(g_ctx.stream[i])) rc = rc ? rc : -1;
+    return rc ? ARM_MATH_ARGUMENT_ERROR : ARM_MATH_SUCCESS;
+}
+
+arm_status arm_rfft_fast_batch_f64(const arm_rfft_fast_instance_f64 *S, float64_t *p, float64_t *pOut,
+                                   uint32_t nFrames, uint8_t ifftFlag)
+{
+    if (S && S->Sint.fftLen != S->fftLenRFFT / 2) return ARM_MATH_ARGUMENT_ERROR;
+    return rfft64_batch(S, p, pOut, nFrames, ifftFlag, 0);
+}
+
 /* ---- legacy single-frame signatures ---- */
 
 static int legacy_len_ok(uint32_t n) { return valid_len(n); }
@@ -206,6 +257,13 @@ void arm_cfft_f64(const arm_cfft_instance_f64 *S, float64_t *p1, uint8_t ifftFla
 {
     if (!legacy_len_ok(S->fftLen)) { g_last = ARM_MATH_SUCCESS; return; }
     g_last = arm_cfft_batch_f64(S, p1, 1, ifftFlag, bitReverseFlag);
+}
+/* arm_rfft_fast_f64.c:207-233: sets Sint.fftLen like the reference; the forward call leaves the N/2-point CFFT in p */
+void arm_rfft_fast_f64(arm_rfft_fast_instance_f64 *S, float64_t *p, float64_t *pOut, uint8_t ifftFlag)
+{
+    S->Sint.fftLen = S->fftLenRFFT / 2;
+    if (S->fftLenRFFT < 32 || !legacy_len_ok(S->fftLenRFFT)) { g_last = ARM_MATH_SUCCESS; return; }
+    g_last = rfft64_batch(S, p, pOut, 1, ifftFlag, 1);
 }
 void arm_cfft_q31(const arm_cfft_instance_q31 *S, q31_t *p1, uint8_t ifftFlag, uint8_t bitReverseFlag)
 {

@@ -65,6 +65,42 @@ RINIT_N(1024, 512)
 RINIT_N(2048, 1024)
 RINIT_N(4096, 2048)
 
+/* arm_rfft_fast_init_f64.c:44-70 (per length), :282-321 */
+#define RINIT64_N(N, H)                                                             \
+    arm_status arm_rfft_fast_init_##N##_f64(arm_rfft_fast_instance_f64 *S)          \
+    {                                                                               \
+        arm_status status;                                                          \
+        if (!S) return ARM_MATH_ARGUMENT_ERROR;                                     \
+        status = arm_cfft_init_##H##_f64(&(S->Sint));                               \
+        if (status != ARM_MATH_SUCCESS) return status;                              \
+        S->fftLenRFFT = N##U;                                                       \
+        S->pTwiddleRFFT = (const float64_t *)twiddleCoefF64_rfft_##N;               \
+        return ARM_MATH_SUCCESS;                                                    \
+    }
+RINIT64_N(32, 16)
+RINIT64_N(64, 32)
+RINIT64_N(128, 64)
+RINIT64_N(256, 128)
+RINIT64_N(512, 256)
+RINIT64_N(1024, 512)
+RINIT64_N(2048, 1024)
+RINIT64_N(4096, 2048)
+
+arm_status arm_rfft_fast_init_f64(arm_rfft_fast_instance_f64 *S, uint16_t fftLen)
+{
+    switch (fftLen) {
+    case 4096U: return arm_rfft_fast_init_4096_f64(S);
+    case 2048U: return arm_rfft_fast_init_2048_f64(S);
+    case 1024U: return arm_rfft_fast_init_1024_f64(S);
+    case 512U:  return arm_rfft_fast_init_512_f64(S);
+    case 256U:  return arm_rfft_fast_init_256_f64(S);
+    case 128U:  return arm_rfft_fast_init_128_f64(S);
+    case 64U:   return arm_rfft_fast_init_64_f64(S);
+    case 32U:   return arm_rfft_fast_init_32_f64(S);
+    default:    return ARM_MATH_ARGUMENT_ERROR;
+    }
+}
+
 arm_status arm_rfft_fast_init_f32(arm_rfft_fast_instance_f32 *S, uint16_t fftLen)
 {
     switch (fftLen) {

@@ -174,6 +174,16 @@ int main(void)
             printf("%s0x%016llxull,0x%016llxull,", (i % 4) ? "" : "\n  ", dbits(c), dbits(sn));
         }
         printf("\n};\n");
+        if (N >= 32) {      /* twiddleCoefF64_rfft_N: (sin, cos)(2 pi i / N), i < N/2, same rule (arm_common_tables.c:26703-30810) */
+            printf("const uint64_t twiddleCoefF64_rfft_%u[%u] = {", N, N);
+            for (unsigned i = 0; i < N / 2; i++) {
+                const unsigned q = N / 4;
+                const double sn = (i < q) ? quarter_sin(i, N) : quarter_sin(2 * q - i, N);
+                const double c = (i < q) ? quarter_sin(q - i, N) : -quarter_sin(i - q, N);
+                printf("%s0x%016llxull,0x%016llxull,", (i % 4) ? "" : "\n  ", dbits(sn), dbits(c));
+            }
+            printf("\n};\n");
+        }
         printf("const uint16_t cmsisdsp_b200_bitrev_len_fixed_%u = %u;\n\n", N, n);
         free(P); free(tab);
     }

@@ -48,6 +48,10 @@ class arm_rfft_fast_instance_f32(C.Structure):
     _fields_ = [("Sint", arm_cfft_instance_f32), ("fftLenRFFT", C.c_uint16), ("pTwiddleRFFT", C.POINTER(C.c_float))]
 
 
+class arm_rfft_fast_instance_f64(C.Structure):
+    _fields_ = [("Sint", arm_cfft_instance_f64), ("fftLenRFFT", C.c_uint16), ("pTwiddleRFFT", C.POINTER(C.c_double))]
+
+
 def _mk_rfft_fix_instance(scalar, cfft):
     class Inst(C.Structure):
         _fields_ = [("fftLenReal", C.c_uint32), ("ifftFlagR", C.c_uint8), ("bitReverseFlagR", C.c_uint8),
@@ -116,6 +120,8 @@ def cuda():
         "cmsisdsp_cuda_cfft_q15": ([vp, u32, u64, u8, u8, vp], i),
         "cmsisdsp_cuda_cfft_f64": ([vp, u32, u64, u8, u8, vp], i),
         "cmsisdsp_cuda_rfft_fast_f32": ([vp, vp, u32, u64, u8, vp], i),
+        "cmsisdsp_cuda_rfft_fast_f64": ([vp, vp, u32, u64, u8, vp], i),
+        "cmsisdsp_cuda_rfft_f64_plan_upload": ([u32, vp], i), "cmsisdsp_cuda_rfft_f64_plan_ready": ([u32], i),
         "cmsisdsp_cuda_rfft_fix_plan_upload": ([i, u32, vp, vp, u32], i), "cmsisdsp_cuda_rfft_fix_plan_ready": ([i, u32], i),
         "cmsisdsp_cuda_rfft_q31": ([vp, vp, u32, u64, u8, vp], i), "cmsisdsp_cuda_rfft_q15": ([vp, vp, u32, u64, u8, vp], i),
         "cmsisdsp_cuda_cfft_mag_f32": ([vp, vp, u32, u64, u8, u8, vp], i), "cmsisdsp_cuda_cfft_peak_f32": ([vp, vp, vp, u32, u64, u8, vp], i),
@@ -157,6 +163,13 @@ def lib():
     L.arm_rfft_fast_f32.argtypes, L.arm_rfft_fast_f32.restype = [C.POINTER(arm_rfft_fast_instance_f32), C.c_void_p, C.c_void_p, u8], None
     L.arm_rfft_fast_batch_f32.argtypes = [C.POINTER(arm_rfft_fast_instance_f32), C.c_void_p, C.c_void_p, u32, u8]
     L.arm_rfft_fast_batch_f32.restype = i
+    L.arm_rfft_fast_init_f64.argtypes, L.arm_rfft_fast_init_f64.restype = [C.POINTER(arm_rfft_fast_instance_f64), u16], i
+    for n in RLENGTHS:
+        f = getattr(L, f"arm_rfft_fast_init_{n}_f64")
+        f.argtypes, f.restype = [C.POINTER(arm_rfft_fast_instance_f64)], i
+    L.arm_rfft_fast_f64.argtypes, L.arm_rfft_fast_f64.restype = [C.POINTER(arm_rfft_fast_instance_f64), C.c_void_p, C.c_void_p, u8], None
+    L.arm_rfft_fast_batch_f64.argtypes = [C.POINTER(arm_rfft_fast_instance_f64), C.c_void_p, C.c_void_p, u32, u8]
+    L.arm_rfft_fast_batch_f64.restype = i
     L.arm_cuda_last_status.argtypes, L.arm_cuda_last_status.restype = [], i
     for name in ("arm_cfft_mag_batch_f32", "arm_cfft_mag_squared_batch_f32"):
         f = getattr(L, name)
@@ -221,6 +234,14 @@ def rfft_instance(N):
     return S
 
 
+def rfft_f64_instance(N):
+    S = arm_rfft_fast_instance_f64()
+    st = lib().arm_rfft_fast_init_f64(C.byref(S), N)
+    if st != ARM_MATH_SUCCESS:
+        raise ValueError(f"arm_rfft_fast_init_f64({N}) -> {st}")
+    return S
+
+
 def instance_tables(S, kind):
     """numpy copies of (twiddle table, bit-reversal swap list) an instance points at."""
     n = int(S.fftLen)
@@ -253,6 +274,18 @@ def rfft_batch(N, x, ifft=0):
     st = lib().arm_rfft_fast_batch_f32(C.byref(S), p.ctypes.data, out.ctypes.data, p.size // N, int(ifft))
     if st != ARM_MATH_SUCCESS:
         raise RuntimeError(f"arm_rfft_fast_batch_f32 -> {st}: {last_error()}")
+    return out
+
+
+def rfft_f64_batch(N, x, ifft=0):
+    """arm_rfft_fast_batch_f64 on a host array [..., N] of float64; returns the transformed array."""
+    p = np.ascontiguousarray(x, dtype=np.float64)
+    assert p.size % N == 0
+    out = np.empty_like(p)
+    S = rfft_f64_instance(N)
+    st = lib().arm_rfft_fast_batch_f64(C.byref(S), p.ctypes.data, out.ctypes.data, p.size // N, int(ifft))
+    if st != ARM_MATH_SUCCESS:
+        raise RuntimeError(f"arm_rfft_fast_batch_f64 -> {st}: {last_error()}")
     return out
 
 
@@ -384,6 +417,20 @@ def cfft_device(kind, N, dptr, n_frames, ifft=0, bitrev=1, stream=0):
     rc = getattr(cuda(), f"cmsisdsp_cuda_cfft_{kind}")(dptr, N, n_frames, int(ifft), int(bitrev), stream)
     if rc:
         raise RuntimeError(f"cmsisdsp_cuda_cfft_{kind} -> {rc}: {last_error()}")
+
+
+def ensure_rfft_f64_plans(N):
+    ensure_plans("f64", N // 2)
+    S = rfft_f64_instance(N)
+    rc = cuda().cmsisdsp_cuda_rfft_f64_plan_upload(N, C.cast(S.pTwiddleRFFT, C.c_void_p))
+    if rc:
+        raise RuntimeError(f"rfft_f64_plan_upload({N}) -> {rc}: {last_error()}")
+
+
+def rfft_f64_device(N, d_in, d_out, n_frames, ifft=0, stream=0):
+    rc = cuda().cmsisdsp_cuda_rfft_fast_f64(d_in, d_out, N, n_frames, int(ifft), stream)
+    if rc:
+        raise RuntimeError(f"cmsisdsp_cuda_rfft_fast_f64 -> {rc}: {last_error()}")
 
 
 def rfft_device(N, d_in, d_out, n_frames, ifft=0, stream=0):

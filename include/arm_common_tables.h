@@ -30,6 +30,14 @@ CMSISDSP_B200_FOR_EACH_LEN(CMSISDSP_B200_DECL_TW)
     extern const uint16_t armBitRevIndexTableF64_##N[];
 CMSISDSP_B200_FOR_EACH_LEN(CMSISDSP_B200_DECL_TW64)
 #undef CMSISDSP_B200_DECL_TW64
+extern const uint64_t twiddleCoefF64_rfft_32[32];
+extern const uint64_t twiddleCoefF64_rfft_64[64];
+extern const uint64_t twiddleCoefF64_rfft_128[128];
+extern const uint64_t twiddleCoefF64_rfft_256[256];
+extern const uint64_t twiddleCoefF64_rfft_512[512];
+extern const uint64_t twiddleCoefF64_rfft_1024[1024];
+extern const uint64_t twiddleCoefF64_rfft_2048[2048];
+extern const uint64_t twiddleCoefF64_rfft_4096[4096];
 #define ARMBITREVINDEXTABLEF64_16_TABLE_LENGTH   ((uint16_t)12)
 #define ARMBITREVINDEXTABLEF64_32_TABLE_LENGTH   ((uint16_t)24)
 #define ARMBITREVINDEXTABLEF64_64_TABLE_LENGTH   ((uint16_t)56)

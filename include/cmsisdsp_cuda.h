@@ -85,6 +85,14 @@ int  cmsisdsp_cuda_cfft_q15(void *d_p, uint32_t fftLen, uint64_t nFrames,
 /* d_p: nFrames*2*fftLen doubles, 16-byte aligned */
 int  cmsisdsp_cuda_cfft_f64(void *d_p, uint32_t fftLen, uint64_t nFrames,
                             uint8_t ifftFlag, uint8_t bitReverseFlag, void *stream);
+/* arm_rfft_fast_f64 (Source/TransformFunctions/arm_rfft_fast_f64.c:207-233): an adapter over cmsisdsp_cuda_cfft_f64
+ * (complex transform, then the split stage in place on d_out; inverse: merge stage, then the inverse transform).
+ * Needs the f64 plan of fftLenReal/2 and pTwiddleRFFT = fftLenReal doubles ((sin,cos) pairs).  d_p is left untouched;
+ * d_p and d_out: nFrames*fftLenReal doubles, 16-byte aligned, not aliased. */
+int  cmsisdsp_cuda_rfft_f64_plan_upload(uint32_t fftLenReal, const double *pTwiddleRFFT);
+int  cmsisdsp_cuda_rfft_f64_plan_ready(uint32_t fftLenReal);
+int  cmsisdsp_cuda_rfft_fast_f64(const void *d_p, void *d_out, uint32_t fftLenReal, uint64_t nFrames,
+                                 uint8_t ifftFlag, void *stream);
 /* d_p: nFrames*fftLenReal floats, left untouched (the reference clobbers it);
  * d_out: nFrames*fftLenReal floats, packed {DC, Nyquist, Re1, Im1, ...}.  d_p and d_out must not alias. */
 int  cmsisdsp_cuda_rfft_fast_f32(const void *d_p, void *d_out, uint32_t fftLenReal, uint64_t nFrames,

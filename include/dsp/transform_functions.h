@@ -110,6 +110,26 @@ arm_status arm_cfft_init_16_f64(arm_cfft_instance_f64 *S);
 arm_status arm_cfft_init_f64(arm_cfft_instance_f64 *S, uint16_t fftLen);
 void arm_cfft_f64(const arm_cfft_instance_f64 *S, float64_t *p1, uint8_t ifftFlag, uint8_t bitReverseFlag);
 
+/* ---------------------------------------------------------------- f64 fast RFFT
+ * (Include/dsp/transform_functions.h:770-794; arm_rfft_fast_f64.c:207-233).  S is not const, as in the reference. */
+typedef struct
+{
+          arm_cfft_instance_f64 Sint;     /* internal CFFT structure (length fftLenRFFT/2) */
+          uint16_t   fftLenRFFT;          /* length of the real sequence */
+    const float64_t *pTwiddleRFFT;        /* twiddle factors of the real stage */
+} arm_rfft_fast_instance_f64;
+
+arm_status arm_rfft_fast_init_32_f64(arm_rfft_fast_instance_f64 *S);
+arm_status arm_rfft_fast_init_64_f64(arm_rfft_fast_instance_f64 *S);
+arm_status arm_rfft_fast_init_128_f64(arm_rfft_fast_instance_f64 *S);
+arm_status arm_rfft_fast_init_256_f64(arm_rfft_fast_instance_f64 *S);
+arm_status arm_rfft_fast_init_512_f64(arm_rfft_fast_instance_f64 *S);
+arm_status arm_rfft_fast_init_1024_f64(arm_rfft_fast_instance_f64 *S);
+arm_status arm_rfft_fast_init_2048_f64(arm_rfft_fast_instance_f64 *S);
+arm_status arm_rfft_fast_init_4096_f64(arm_rfft_fast_instance_f64 *S);
+arm_status arm_rfft_fast_init_f64(arm_rfft_fast_instance_f64 *S, uint16_t fftLen);
+void arm_rfft_fast_f64(arm_rfft_fast_instance_f64 *S, float64_t *p, float64_t *pOut, uint8_t ifftFlag);
+
 /* ---------------------------------------------------------------- f32 fast RFFT */
 typedef struct
 {
@@ -295,6 +315,10 @@ arm_status arm_cfft_batch_q15(const arm_cfft_instance_q15 *S, q15_t *p, uint32_t
 arm_status arm_cfft_batch_f64(const arm_cfft_instance_f64 *S, float64_t *p, uint32_t nFrames,
                               uint8_t ifftFlag, uint8_t bitReverseFlag);
 arm_status arm_rfft_fast_batch_f32(const arm_rfft_fast_instance_f32 *S, float32_t *p, float32_t *pOut,
+                                   uint32_t nFrames, uint8_t ifftFlag);
+/* leaves p untouched in both directions, like arm_rfft_fast_batch_f32 (the single-frame forward call keeps the
+ * reference's side effect: p then holds the N/2-point CFFT) */
+arm_status arm_rfft_fast_batch_f64(const arm_rfft_fast_instance_f64 *S, float64_t *p, float64_t *pOut,
                                    uint32_t nFrames, uint8_t ifftFlag);
 /* arm_cfft_f32(S, p, ifftFlag, 1) fused with its usual consumers; pSrc (nFrames * 2*fftLen floats) is left untouched and
  * the spectrum itself is never written:

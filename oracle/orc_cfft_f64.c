@@ -175,3 +175,84 @@ void orc_cfft_f64_batch(uint32_t N, double *p, uint64_t nFrames, int ifft, int b
         for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
     free(th); free(jobs);
 }
+
+/* ------------------------------------------------------------------ arm_rfft_fast_f64
+ *   arm_rfft_fast_f64   Source/TransformFunctions/arm_rfft_fast_f64.c:207-233
+ *   stage_rfft_f64      arm_rfft_fast_f64.c:30-118     (split after the forward N/2-point CFFT, which runs in place on p)
+ *   merge_rfft_f64      arm_rfft_fast_f64.c:121-181    (merge into pOut before the inverse CFFT, in place on pOut)
+ * Real-stage table: (sin, cos)(2 pi k / N), k < N/2 -- the reference's twiddleCoefF64_rfft_N literals
+ * (arm_common_tables.c:26703-30810) are within 1 ulp of the generated one, like the complex table. */
+static double *g_twr[9];
+static pthread_once_t g_once_r = PTHREAD_ONCE_INIT;
+static void build_rfft_tables(void)
+{
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int li = 1; li < 9; li++) {
+        const uint32_t N = k_len[li], q = N / 4;
+        double *qs = malloc((q + 1) * sizeof *qs), *t = malloc(N * sizeof *t);
+        for (uint32_t i = 0; i <= q; i++) qs[i] = sin(two_pi * (double)i / (double)N);
+        for (uint32_t i = 0; i < N / 2; i++) {
+            const double s = (i < q) ? qs[i] : qs[2 * q - i], c = (i < q) ? qs[q - i] : -qs[i - q];
+            t[2 * i] = (s == 0.0) ? 0.0 : s;
+            t[2 * i + 1] = (c == 0.0) ? 0.0 : c;
+        }
+        free(qs);
+        g_twr[li] = t;
+    }
+}
+const double *orc_twiddle_rfft_f64(uint32_t N)
+{
+    pthread_once(&g_once_r, build_rfft_tables);
+    for (int li = 1; li < 9; li++)
+        if (k_len[li] == N) return g_twr[li];
+    return NULL;
+}
+
+void orc_rfft_fast_f64(uint32_t N, double *p, double *pOut, int ifftFlag, const double *twiddleC, const double *twiddleR)
+{
+    const uint32_t L = N / 2;
+    const cf64_t *tw = (const cf64_t *)(twiddleR ? twiddleR : orc_twiddle_rfft_f64(N));
+    if (!tw) return;
+    if (ifftFlag) {
+        const cf64_t *x = (const cf64_t *)p;
+        cf64_t *y = (cf64_t *)pOut;
+        y[0].re = 0.5 * (x[0].re + x[0].im);
+        y[0].im = 0.5 * (x[0].re - x[0].im);
+        for (uint32_t k = 1; k < L; k++) {
+            const cf64_t a = x[k], b = x[L - k];
+            const double t1a = a.re - b.re, t1b = a.im + b.im;
+            const double r = tw[k].re * t1a, s = tw[k].im * t1b, t = tw[k].im * t1a, u = tw[k].re * t1b;
+            y[k].re = 0.5 * (a.re + b.re - r - s);
+            y[k].im = 0.5 * (a.im - b.im + t - u);
+        }
+        orc_cfft_f64(L, pOut, 1, 1, twiddleC);
+        return;
+    }
+    orc_cfft_f64(L, p, 0, 1, twiddleC);
+    const cf64_t *x = (const cf64_t *)p;
+    cf64_t *y = (cf64_t *)pOut;
+    {
+        const double t1a = x[0].re + x[0].re, t1b = x[0].im + x[0].im;
+        y[0].re = 0.5 * (t1a + t1b);
+        y[0].im = 0.5 * (t1a - t1b);
+    }
+    for (uint32_t k = 1; k < L; k++) {
+        const cf64_t a = x[k], b = x[L - k];
+        const double t1a = b.re - a.re, t1b = b.im + a.im;
+        const double p0 = tw[k].re * t1a, p1 = tw[k].im * t1a, p2 = tw[k].re * t1b, p3 = tw[k].im * t1b;
+        y[k].re = 0.5 * (a.re + b.re + p0 + p3);
+        y[k].im = 0.5 * (a.im - b.im + p1 - p2);
+    }
+}
+
+/* p is copied per frame (the forward transform destroys it); single thread: parity only */
+void orc_rfft_fast_f64_batch(uint32_t N, const double *p, double *pOut, uint64_t nFrames, int ifft, const double *twiddleC,
+                             const double *twiddleR)
+{
+    double *tmp = malloc(N * sizeof *tmp);
+    for (uint64_t f = 0; f < nFrames; f++) {
+        for (uint32_t i = 0; i < N; i++) tmp[i] = p[f * N + i];
+        orc_rfft_fast_f64(N, tmp, pOut + f * N, ifft, twiddleC, twiddleR);
+    }
+    free(tmp);
+}

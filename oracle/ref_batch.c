@@ -229,3 +229,19 @@ const double *ref_twiddle_f64(uint32_t N) { arm_cfft_instance_f64 S; return arm_
 const uint16_t *ref_bitrev_f64(uint32_t N, uint16_t *len)
 { arm_cfft_instance_f64 S; if (arm_cfft_init_f64(&S, (uint16_t)N)) return 0; *len = S.bitRevLength; return S.pBitRevTable; }
 uint32_t ref_sizeof_cfft_instance_f64(void) { return (uint32_t)sizeof(arm_cfft_instance_f64); }
+
+/* ---- arm_rfft_fast_f64, frame by frame; the source is copied per frame (the forward transform destroys it) ---- */
+int ref_rfft_fast_f64_batch(uint32_t N, const double *p, double *pOut, uint64_t nFrames, int ifft)
+{
+    arm_rfft_fast_instance_f64 S;
+    if (arm_rfft_fast_init_f64(&S, (uint16_t)N) != ARM_MATH_SUCCESS) return -1;
+    double *tmp = malloc(sizeof(double) * N);
+    for (uint64_t f = 0; f < nFrames; f++) {
+        memcpy(tmp, p + f * N, sizeof(double) * N);
+        arm_rfft_fast_f64(&S, tmp, pOut + f * N, (uint8_t)ifft);
+    }
+    free(tmp);
+    return 0;
+}
+const double *ref_twiddle_rfft_f64(uint32_t N) { arm_rfft_fast_instance_f64 S; return arm_rfft_fast_init_f64(&S, (uint16_t)N) ? 0 : S.pTwiddleRFFT; }
+uint32_t ref_sizeof_rfft_fast_instance_f64(void) { return (uint32_t)sizeof(arm_rfft_fast_instance_f64); }

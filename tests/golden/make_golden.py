@@ -9,7 +9,7 @@ Outputs
         (Testing/Patterns/DSP/Transform/Transform{F32,Q31,Q15}/*.txt, written by
         Testing/PatternGeneration/Transform.py from scipy.fftpack), re-packed as
         arrays keyed "<type>/<c|r>/<noisy|step>/<N>/<input|ref|ifft_input>".
-  transform_patterns_f64.npz  same for Testing/Patterns/DSP/Transform/TransformF64/Complex*.txt (arm_cfft_f64).
+  transform_patterns_f64.npz  same for Testing/Patterns/DSP/Transform/TransformF64/*.txt (arm_cfft_f64, arm_rfft_fast_f64).
   fft_bin_example.npz     Examples/ARM/arm_fft_bin_example/arm_fft_bin_data.c
         (testInput_f32_10khz; expected peak bin 213).
   mfcc_patterns.npz       Testing/Source/Tests/mfccdata.c coefficient arrays (DCT 13x20, Hamming
@@ -55,16 +55,16 @@ def main():
 
 
 def f64_patterns_main():
-    """transform_patterns_f64.npz: the complex-FFT vectors of Testing/Patterns/DSP/Transform/TransformF64 (arm_cfft_f64)."""
+    """transform_patterns_f64.npz: the vectors of Testing/Patterns/DSP/Transform/TransformF64 (arm_cfft_f64, arm_rfft_fast_f64)."""
     out = {}
     d = os.path.join(PAT, "TransformF64")
     for fn in sorted(os.listdir(d)):
-        m = re.match(r"Complex(InputSamples|FFTSamples|InputIFFTSamples)_(Noisy|Step)_(\d+)_\d+_f64\.txt$", fn)
+        m = re.match(r"(Complex|Real)(InputSamples|FFTSamples|InputIFFTSamples)_(Noisy|Step)_(\d+)_\d+_f64\.txt$", fn)
         if not m:
             continue
-        what, sig, n = m.groups()
+        cr, what, sig, n = m.groups()
         what = {"InputSamples": "input", "FFTSamples": "ref", "InputIFFTSamples": "ifft_input"}[what]
-        out[f"f64/c/{sig.lower()}/{n}/{what}"] = read_pattern(os.path.join(d, fn)).view(np.float64)
+        out[f"f64/{'c' if cr == 'Complex' else 'r'}/{sig.lower()}/{n}/{what}"] = read_pattern(os.path.join(d, fn)).view(np.float64)
     np.savez_compressed(os.path.join(HERE, "transform_patterns_f64.npz"), **out)
     print("transform_patterns_f64.npz:", len(out), "arrays")
 

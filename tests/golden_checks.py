@@ -20,6 +20,7 @@ THRESH = {
     ("q31", "c"): dict(snr=90.0, near=53),
     ("q15", "c"): dict(snr=30.0, near=15),
     ("f64", "c"): dict(snr=250.0, abs=2.0e-13, rel=1.0e-13),       # Testing/Source/Tests/TransformCF64.cpp:6-8
+    ("f64", "r"): dict(snr=250.0, abs=2.0e-13, rel=3.0e-15),       # Testing/Source/Tests/TransformRF64.cpp:7-9
 }
 
 

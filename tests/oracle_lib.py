@@ -82,6 +82,32 @@ class _Lib:
             assert fn(N, y.ctypes.data, y.size // (2 * N), int(ifft), int(bitrev)) == 0
         return y
 
+    def rfft_f64(self, N, x, ifft=0, twiddle_c=None, twiddle_r=None):
+        """arm_rfft_fast_f64 on x [..., N] float64 (copied: the reference's forward transform destroys its input)."""
+        src = np.ascontiguousarray(x, dtype=np.float64)
+        assert src.size % N == 0
+        out = np.empty_like(src)
+        fn = self._fn("rfft_fast_f64_batch")
+        if self.prefix == "orc":
+            tc = None if twiddle_c is None else np.ascontiguousarray(twiddle_c, dtype=np.float64)
+            tr = None if twiddle_r is None else np.ascontiguousarray(twiddle_r, dtype=np.float64)
+            fn.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
+            fn.restype = None
+            fn(N, src.ctypes.data, out.ctypes.data, src.size // N, int(ifft), None if tc is None else tc.ctypes.data,
+               None if tr is None else tr.ctypes.data)
+        else:
+            assert twiddle_c is None and twiddle_r is None
+            fn.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
+            fn.restype = C.c_int
+            assert fn(N, src.ctypes.data, out.ctypes.data, src.size // N, int(ifft)) == 0
+        return out
+
+    def twiddle_rfft_f64(self, N):
+        fn = self._fn("twiddle_rfft_f64")
+        fn.argtypes = [C.c_uint32]
+        fn.restype = C.POINTER(C.c_double)
+        return np.ctypeslib.as_array(fn(N), shape=(N,)).copy()
+
     def twiddle_f64(self, N):
         fn = self._fn("twiddle_f64")
         fn.argtypes = [C.c_uint32]

@@ -177,6 +177,59 @@ def test_cfft_f64_reference_patterns_legacy_call_and_device_pointers():
     assert L.arm_cfft_batch_f64(C.byref(S), one.ctypes.data, 0, 0, 1) == 0
 
 
+@pytest.mark.parametrize("N", RLENGTHS)
+def test_rfft_fast_f64_both_directions(N):
+    """arm_rfft_fast_f64 (adapter: complex kernel + split / merge stage): bit-identical to the oracle on the product's
+    tables, <= 1e-15 against the compiled reference, the reference's golden vectors, the legacy call's side effect."""
+    from oracle_lib import ref
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(8000 + N)
+    x = rng.standard_normal((301, N))
+    want = oracle().rfft_f64(N, x, 0)
+    spec = cd.rfft_f64_batch(N, x, 0)
+    assert np.array_equal(spec.view(np.uint64), want.view(np.uint64))
+    back = cd.rfft_f64_batch(N, spec, 1)
+    assert np.array_equal(back.view(np.uint64), oracle().rfft_f64(N, spec, 1).view(np.uint64))
+    assert relrms(back, x) <= 1e-15 * np.log2(N)
+    if ref() is not None:
+        assert relrms(spec[:40], ref().rfft_f64(N, x[:40], 0)) <= F64_TOL
+        assert relrms(back[:40], ref().rfft_f64(N, spec[:40], 1)) <= F64_TOL
+    # numpy's rfft as an independent check of the packing {DC, Nyquist, Re1, Im1, ...}
+    z = np.fft.rfft(x, axis=1)
+    packed = np.empty_like(x)
+    packed[:, 0], packed[:, 1] = z[:, 0].real, z[:, N // 2].real
+    packed[:, 2::2], packed[:, 3::2] = z[:, 1:N // 2].real, z[:, 1:N // 2].imag
+    assert relrms(spec, packed) <= 1e-15 * np.log2(N)
+    # the reference's single-frame signature: forward leaves the N/2-point CFFT in p, inverse leaves p alone
+    L = cd.lib()
+    S = cd.rfft_f64_instance(N)
+    p, out = x[:1].copy(), np.zeros((1, N))
+    L.arm_rfft_fast_f64(C.byref(S), p.ctypes.data, out.ctypes.data, 0)
+    assert L.arm_cuda_last_status() == 0
+    assert np.array_equal(out, want[:1]) and np.array_equal(p, oracle().cfft_f64(N // 2, x[:1], 0, 1))
+    p2, out2 = want[:1].copy(), np.zeros((1, N))
+    L.arm_rfft_fast_f64(C.byref(S), p2.ctypes.data, out2.ctypes.data, 1)
+    assert np.array_equal(p2, want[:1]) and relrms(out2, x[:1]) <= 1e-15 * np.log2(N)
+    # device pointers: source left untouched
+    dev = torch.device("cuda", 0)
+    cd.ensure_rfft_f64_plans(N)
+    a = torch.from_numpy(x).to(dev)
+    b = torch.empty_like(a)
+    cd.rfft_f64_device(N, a.data_ptr(), b.data_ptr(), x.shape[0], 0, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(b.cpu().numpy(), spec) and np.array_equal(a.cpu().numpy(), x)
+    assert L.arm_rfft_fast_batch_f64(C.byref(S), a.data_ptr(), a.data_ptr(), 1, 0) == cd.ARM_MATH_ARGUMENT_ERROR    # aliasing
+
+
+def test_rfft_fast_f64_reference_patterns():
+    n = 0
+    for N, sig, ifft, x, refv in golden_cases("f64", "r"):           # TransformRF64.cpp thresholds
+        out = cd.rfft_f64_batch(N, x, ifft).reshape(-1)
+        assert_like_reference("f64", "r", out, refv, N, ifft)
+        n += 1
+    assert n == 32
+
+
 def test_legacy_single_frame_signatures():
     L = cd.lib()
     for kind in ("f32", "q31", "q15"):

@@ -35,6 +35,16 @@ def test_cfft_f64_patterns():
     assert n == 36
 
 
+def test_rfft_fast_f64_patterns():
+    """Real-FFT vectors of TransformF64 with the thresholds of TransformRF64.cpp:7-9."""
+    n = 0
+    for N, sig, ifft, x, ref in golden_cases("f64", "r"):
+        out = oracle().rfft_f64(N, x, ifft).reshape(-1)
+        assert_like_reference("f64", "r", out, ref, N, ifft)
+        n += 1
+    assert n == 32
+
+
 def test_rfft_patterns():
     n = 0
     for N, sig, ifft, x, ref in golden_cases("f32", "r"):

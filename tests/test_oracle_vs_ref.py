@@ -156,3 +156,17 @@ def test_cfft_f64_bit_exact_on_the_reference_table_and_1e15_on_the_generated_one
             g = oracle().cfft_f64(N, x, ifft, bitrev)
             for f in range(x.shape[0]):
                 assert np.sqrt(((g[f] - b[f]) ** 2).sum() / (b[f] ** 2).sum()) <= 1e-15, (N, ifft, bitrev, f)
+
+
+@pytest.mark.parametrize("N", RLENGTHS)
+def test_rfft_fast_f64_bit_exact_on_the_reference_tables(N):
+    rng = np.random.default_rng(4000 + N)
+    x = rng.standard_normal((5, N))
+    tc, tr = ref().twiddle_f64(N // 2), ref().twiddle_rfft_f64(N)
+    d = np.abs(oracle().twiddle_rfft_f64(N).view(np.int64) - tr.view(np.int64))
+    assert d.max() <= 1 and (d != 0).mean() <= 0.2
+    for ifft in (0, 1):
+        b = ref().rfft_f64(N, x, ifft)
+        assert np.array_equal(oracle().rfft_f64(N, x, ifft, tc, tr).view(np.uint64), b.view(np.uint64)), (N, ifft)
+        g = oracle().rfft_f64(N, x, ifft)
+        assert np.sqrt(((g - b) ** 2).sum() / (b ** 2).sum()) <= 1e-15, (N, ifft)

@@ -38,6 +38,12 @@ def test_generated_tables_match_oracle_and_reference(N):
         if ref() is not None:
             assert np.abs(tw.view(np.int64) - ref().twiddle_f64(N).view(np.int64)).max() <= 1
     if N >= 32:
+        S = cd.rfft_f64_instance(N)
+        assert S.fftLenRFFT == N and S.Sint.fftLen == N // 2
+        assert bytes(S.Sint) == bytes(cd.cfft_instance("f64", N // 2))
+        twr64 = np.ctypeslib.as_array(S.pTwiddleRFFT, shape=(N,)).copy()
+        assert np.array_equal(twr64.view(np.uint64), oracle().twiddle_rfft_f64(N).view(np.uint64))
+    if N >= 32:
         for S in (cd.rfft_instance(N), cd.rfft_preset(N)):
             assert S.fftLenRFFT == N and S.Sint.fftLen == N // 2
             twr = np.ctypeslib.as_array(S.pTwiddleRFFT, shape=(N,)).copy()
@@ -110,7 +116,7 @@ def test_struct_layouts_match_reference():
     if ref() is not None:
         L = ref().lib
         for name, t in (("cfft_instance_f32", cd.arm_cfft_instance_f32), ("cfft_instance_q31", cd.arm_cfft_instance_q31),
-                        ("cfft_instance_q15", cd.arm_cfft_instance_q15), ("cfft_instance_f64", cd.arm_cfft_instance_f64), ("rfft_fast_instance_f32", cd.arm_rfft_fast_instance_f32),
+                        ("cfft_instance_q15", cd.arm_cfft_instance_q15), ("cfft_instance_f64", cd.arm_cfft_instance_f64), ("rfft_fast_instance_f64", cd.arm_rfft_fast_instance_f64), ("rfft_fast_instance_f32", cd.arm_rfft_fast_instance_f32),
                         ("rfft_instance_q31", cd.arm_rfft_instance_q31), ("rfft_instance_q15", cd.arm_rfft_instance_q15)):
             fn = getattr(L, f"ref_sizeof_{name}")
             fn.restype = C.c_uint32
@@ -151,10 +157,10 @@ def test_shared_objects_export_every_declared_symbol():
         assert hasattr(cu, name), name
     fr = cd.lib()
     names = _declared_functions(os.path.join(ROOT, "include", "dsp", "transform_functions.h"))
-    # 4x(9 per-length inits + init + exec) [f32, q31, q15, f64] + rfft (8+1+1) + 5 batch + last_status + mfcc (8+1+1+1)
+    # 4x(9 per-length inits + init + exec) [f32, q31, q15, f64] + 2 x rfft (8+1+1) [f32, f64] + 6 batch + last_status + mfcc (8+1+1+1)
     # + rfft_q31/q15 (init, exec, batch each; their per-length inits are declared through a macro)
     # + 3 fused spectrum epilogues (mag, mag squared, peak) + deprecated radix-4/2 API (4 x (init, exec, batch))
-    assert len(names) == 92
+    assert len(names) == 103
     for name in names:
         assert hasattr(fr, name), name
     for N in RFIX_LENGTHS:
@@ -205,6 +211,13 @@ def test_no_cpu_fallback_without_a_device():
     assert L.arm_cfft_batch_f64(C.byref(Sd), xd.ctypes.data, 1, 0, 1) == cd.ARM_MATH_ARGUMENT_ERROR
     L.arm_cfft_f64(C.byref(Sd), xd.ctypes.data, 0, 1)
     assert L.arm_cuda_last_status() == cd.ARM_MATH_ARGUMENT_ERROR and np.array_equal(xd, np.arange(2 * 64, dtype=np.float64))
+    Rd = cd.rfft_f64_instance(64)
+    od = np.zeros(64)
+    assert L.arm_rfft_fast_batch_f64(C.byref(Rd), xd.ctypes.data, od.ctypes.data, 1, 0) == cd.ARM_MATH_ARGUMENT_ERROR and not od.any()
+    bad64 = cd.arm_rfft_fast_instance_f64()
+    for badlen in (0, 16, 48, 8192):
+        assert L.arm_rfft_fast_init_f64(C.byref(bad64), badlen) == cd.ARM_MATH_ARGUMENT_ERROR
+    assert L.arm_rfft_fast_init_1024_f64(None) == cd.ARM_MATH_ARGUMENT_ERROR
     assert not out.any() and np.array_equal(x, x0)
     assert cd.last_error() != ""
     assert cu.cmsisdsp_cuda_launch_count() == 0
