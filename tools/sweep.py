@@ -52,7 +52,7 @@ def main():
     rows = []
     for op in args.ops.split(","):
         for N in [int(v) for v in args.lens.split(",")]:
-            if op.startswith("rfft_") and N < 32:
+            if op.startswith("rfft") and N < 32:
                 continue
             if op == "mfcc" and N not in (256, 512, 1024):
                 continue
@@ -100,6 +100,19 @@ def main():
                     alg = B * (N * 8 + 8)
                 samples = B * N
                 info = cd.kernel_info(9, N)
+            elif op.startswith("rfft64"):
+                # arm_rfft_fast_f64 (adapter: two launches); algorithmic bytes as for the f32 real FFT: N in + N out doubles
+                if N < 32:
+                    continue
+                B = nbytes // (8 * N)
+                cd.ensure_rfft_f64_plans(N)
+                a = torch.randn(B, N, device=dev, dtype=torch.float64)
+                b = torch.empty_like(a)
+                inv = int(op.endswith("inv"))
+                fn = lambda: cd.rfft_f64_device(N, a.data_ptr(), b.data_ptr(), B, inv, st)
+                alg = 2 * B * N * 8
+                samples = B * N
+                info = cd.kernel_info(10, N // 2)
             elif op.startswith("rfftq"):
                 # rfftq31_fwd / rfftq31_inv / rfftq15_fwd / rfftq15_inv; N = real length; algorithmic bytes:
                 # forward N in + 2N out scalars, inverse N+2 in (bins 0..N/2) + N out
