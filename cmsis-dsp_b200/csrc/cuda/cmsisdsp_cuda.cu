@@ -424,22 +424,38 @@ extern "C" int cmsisdsp_cuda_rfft_fast_f64(const void *d_p, void *d_out, uint32_
     }
     if (!twr) return fail(CMSISDSP_CUDA_ERR_NO_PLAN, "no f64 rfft plan uploaded for this (device, fftLen)");
     if (nFrames == 0) return CMSISDSP_CUDA_OK;
+    /* Measured and rejected as a default (profiles/r1_f_notes.md): running the two launches of a direction over
+     * L2-sized CHUNKS of the batch, so that the second finds the first's output in L2.  With separate launches the
+     * per-chunk launch cost and drain outweigh the saved HBM round trip at every chunk size (1 GiB batches, N = 1024:
+     * whole batch 49.9 %, 64 MiB chunks 39.5 %, 16 MiB 27.6 %, 4 MiB 12.2 % of the HBM peak).  The knob stays for
+     * re-measurement: CMSISDSP_CUDA_RFFT64_CHUNK_MIB (0 = the whole batch per launch, the default). */
+    static const long chunkMiB = [] { const char *e = getenv("CMSISDSP_CUDA_RFFT64_CHUNK_MIB"); return e ? atol(e) : 0L; }();
     const uint32_t L = fftLenReal / 2;
-    const uint64_t items = nFrames * (uint64_t)(L / 2 + 1), blocks = (items + 255) / 256;
-    if (blocks > 0x7fffffffull) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "batch too large for one launch");
+    const uint64_t frameBytes = (uint64_t)fftLenReal * sizeof(double);
+    uint64_t perChunk = chunkMiB > 0 ? ((uint64_t)chunkMiB << 20) / frameBytes : nFrames;
+    if (perChunk == 0) perChunk = 1;
     cudaStream_t st = (cudaStream_t)stream;
-    if (!ifftFlag) {
-        rc = cfft_io(CMSISDSP_CUDA_F64, d_p, d_out, L, nFrames, 0, 1, stream);
-        if (rc) return rc;
-        rfft64_stage_kernel<false><<<(unsigned)blocks, 256, 0, st>>>((const double2 *)d_out, (double2 *)d_out, (const double2 *)twr, L, nFrames);
-        shim_count_launch();
-        CU_TRY(cudaGetLastError());
-        return CMSISDSP_CUDA_OK;
+    for (uint64_t f = 0; f < nFrames; f += perChunk) {
+        const uint64_t n = (nFrames - f < perChunk) ? nFrames - f : perChunk;
+        const char *src = (const char *)d_p + f * frameBytes;
+        char *dst = (char *)d_out + f * frameBytes;
+        const uint64_t items = n * (uint64_t)(L / 2 + 1), blocks = (items + 255) / 256;
+        if (blocks > 0x7fffffffull) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "batch too large for one launch");
+        if (!ifftFlag) {
+            rc = cfft_io(CMSISDSP_CUDA_F64, src, dst, L, n, 0, 1, stream);
+            if (rc) return rc;
+            rfft64_stage_kernel<false><<<(unsigned)blocks, 256, 0, st>>>((const double2 *)dst, (double2 *)dst, (const double2 *)twr, L, n);
+            shim_count_launch();
+            CU_TRY(cudaGetLastError());
+        } else {
+            rfft64_stage_kernel<true><<<(unsigned)blocks, 256, 0, st>>>((const double2 *)src, (double2 *)dst, (const double2 *)twr, L, n);
+            shim_count_launch();
+            CU_TRY(cudaGetLastError());
+            rc = cfft_any(CMSISDSP_CUDA_F64, dst, L, n, 1, 1, stream);
+            if (rc) return rc;
+        }
     }
-    rfft64_stage_kernel<true><<<(unsigned)blocks, 256, 0, st>>>((const double2 *)d_p, (double2 *)d_out, (const double2 *)twr, L, nFrames);
-    shim_count_launch();
-    CU_TRY(cudaGetLastError());
-    return cfft_any(CMSISDSP_CUDA_F64, d_out, L, nFrames, 1, 1, stream);
+    return CMSISDSP_CUDA_OK;
 }
 
 /* arm_cfft_f32 + spectrum epilogue: mode 0 magnitudes, 1 squared magnitudes (d_out: fftLen floats per frame),

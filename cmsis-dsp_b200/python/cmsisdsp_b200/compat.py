@@ -6,7 +6,7 @@ PythonWrapper/cmsisdsp_pkg/src/cmsisdsp_transform.c:2074-2545) over the B200 lib
     status = dsp.arm_cfft_init_f32(S, 1024)
     y = dsp.arm_cfft_f32(S, x, 0, 1)              # returns the transformed array, like the reference's wrapper
 
-Same names, argument order and return conventions for the FFT path (cfft f32/q31/q15, rfft_fast_f32, rfft q31/q15,
+Same names, argument order and return conventions for the FFT path (cfft f32/q31/q15/f64, rfft_fast_f32/f64, rfft q31/q15,
 mfcc f32).  One extension: an input holding several frames back to back is transformed as a batch in ONE call
 (the reference's wrapper takes exactly one frame).  A binding, not an implementation: everything goes through the
 C ABI; errors raise RuntimeError with the shim's message.
@@ -16,7 +16,7 @@ import ctypes as C
 import numpy as np
 
 from . import (ARM_MATH_SUCCESS, CFFT_INSTANCE, NP_DTYPE, RFIX_INSTANCE, arm_mfcc_instance_f32 as _mfcc_struct,
-               arm_rfft_fast_instance_f32 as _rfft_struct, last_error, lib)
+               arm_rfft_fast_instance_f32 as _rfft_struct, arm_rfft_fast_instance_f64 as _rfft64_struct, last_error, lib)
 
 
 def _check(st, what):
@@ -49,7 +49,21 @@ arm_cfft_instance_f32, arm_cfft_init_f32, arm_cfft_f32 = _mk_cfft("f32")
 arm_cfft_instance_q31, arm_cfft_init_q31, arm_cfft_q31 = _mk_cfft("q31")
 arm_cfft_instance_q15, arm_cfft_init_q15, arm_cfft_q15 = _mk_cfft("q15")
 
+arm_cfft_instance_f64, arm_cfft_init_f64, arm_cfft_f64 = _mk_cfft("f64")
+
 arm_rfft_fast_instance_f32 = _rfft_struct
+arm_rfft_fast_instance_f64 = _rfft64_struct
+
+
+def arm_rfft_fast_init_f64(S, fftLen):
+    return int(lib().arm_rfft_fast_init_f64(C.byref(S), int(fftLen)))
+
+
+def arm_rfft_fast_f64(S, p, ifftFlag):
+    src, n = _frames(p, np.float64, S.fftLenRFFT)
+    out = np.empty_like(src)
+    _check(lib().arm_rfft_fast_batch_f64(C.byref(S), src.ctypes.data, out.ctypes.data, n, int(ifftFlag)), "arm_rfft_fast_f64")
+    return out
 
 
 def arm_rfft_fast_init_f32(S, fftLen):

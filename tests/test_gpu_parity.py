@@ -454,6 +454,14 @@ def test_python_wrapper_compatible_surface():
     assert dsp.arm_rfft_fast_init_f32(R, 1024) == 0
     xr = rfft_input(1024, frames=5, seed=4)
     assert relrms(dsp.arm_rfft_fast_f32(R, xr, 0), oracle().rfft(1024, xr, 0).reshape(-1)) <= F32_TOL
+    D = dsp.arm_cfft_instance_f64()
+    assert dsp.arm_cfft_init_f64(D, 256) == 0 and dsp.arm_cfft_init_f64(D, 100) == cd.ARM_MATH_ARGUMENT_ERROR
+    assert dsp.arm_cfft_init_f64(D, 256) == 0
+    xd = np.random.default_rng(9).standard_normal(3 * 512)
+    assert np.array_equal(dsp.arm_cfft_f64(D, xd, 0, 1), oracle().cfft_f64(256, xd, 0, 1))
+    RD = dsp.arm_rfft_fast_instance_f64()
+    assert dsp.arm_rfft_fast_init_f64(RD, 512) == 0
+    assert np.array_equal(dsp.arm_rfft_fast_f64(RD, xd, 0), oracle().rfft_f64(512, xd, 0))
     cfg = mfcc_config(512)
     M = dsp.arm_mfcc_instance_f32()
     assert dsp.arm_mfcc_init_f32(M, 512, 20, 13, cfg["dct"], cfg["pos"], cfg["len"], cfg["coefs"], cfg["window"]) == 0
