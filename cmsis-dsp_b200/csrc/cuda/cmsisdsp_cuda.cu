@@ -48,13 +48,14 @@ void shim_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 namespace b200fft {
 FOR_ALL_N(DECL, 0) FOR_ALL_N(DECL, 1) FOR_ALL_N(DECL, 2) FOR_RFFT_NC(DECL, 3) FOR_RFFT_NC(DECL, 4)
 FOR_ALL_N(DECL, 5) FOR_ALL_N(DECL, 6) FOR_ALL_N(DECL, 7) FOR_ALL_N(DECL, 8) FOR_ALL_N(DECL, 9) FOR_ALL_N(DECL, 10)
+FOR_RFFT_NC(DECL, 11) FOR_RFFT_NC(DECL, 12)
 }
 #undef DECL
 #define REF(op, n) &ku_entry_##op##_##n,
 /* [op][index of the COMPLEX length 16..4096]; the rfft ops have no 4096-point complex plan */
 static const KernelEntry *const kEntries[OP_COUNT][9] = {
     {FOR_ALL_N(REF, 0)}, {FOR_ALL_N(REF, 1)}, {FOR_ALL_N(REF, 2)}, {FOR_RFFT_NC(REF, 3) nullptr}, {FOR_RFFT_NC(REF, 4) nullptr},
-    {FOR_ALL_N(REF, 5)}, {FOR_ALL_N(REF, 6)}, {FOR_ALL_N(REF, 7)}, {FOR_ALL_N(REF, 8)}, {FOR_ALL_N(REF, 9)}, {FOR_ALL_N(REF, 10)}};
+    {FOR_ALL_N(REF, 5)}, {FOR_ALL_N(REF, 6)}, {FOR_ALL_N(REF, 7)}, {FOR_ALL_N(REF, 8)}, {FOR_ALL_N(REF, 9)}, {FOR_ALL_N(REF, 10)}, {FOR_RFFT_NC(REF, 11) nullptr}, {FOR_RFFT_NC(REF, 12) nullptr}};
 #undef REF
 
 static const uint32_t kLens[9] = {16, 32, 64, 128, 256, 512, 1024, 2048, 4096};
@@ -340,10 +341,10 @@ extern "C" int cmsisdsp_cuda_rfft_fast_f32(const void *d_p, void *d_out, uint32_
 
 /* ------------------------------------------------------------------ arm_rfft_fast_f64 (arm_rfft_fast_f64.c:207-233)
  *
- * An adapter over the f64 complex kernels, not a fused kernel: forward = N/2-point CFFT written
- * to d_out, then the split stage in place on d_out; inverse = merge stage d_p -> d_out, then the inverse CFFT in place.
- * One thread owns the bin pair (k, L - k), so the stages can run in place.  The arithmetic follows stage_rfft_f64
- * (:30-118) and merge_rfft_f64 (:121-181) operation for operation, products rounded on their own. */
+ * One fused kernel per direction (fft_body.cuh: RfftF64FwdBody / RfftF64InvBody; units ku_11_L / ku_12_L): the L-point
+ * f64 CFFT with stage_rfft_f64 (:30-118) as its epilogue, merge_rfft_f64 (:121-181) as the load of the inverse.  The
+ * first form of this entry point was an adapter -- complex kernel, then a stage kernel in place, two passes over HBM:
+ * 45-52 % of the HBM peak (profiles/r1_f_notes.md). */
 extern "C" int cmsisdsp_cuda_rfft_f64_plan_upload(uint32_t fftLenReal, const double *pTwiddleRFFT)
 {
     const int li = len_index(fftLenReal);
@@ -368,45 +369,6 @@ extern "C" int cmsisdsp_cuda_rfft_f64_plan_ready(uint32_t fftLenReal)
     return g_dev[dev].twr64[li] != nullptr && g_dev[dev].plan[CMSISDSP_CUDA_F64][li - 1].tw != nullptr;
 }
 
-/* split: X = CFFT of the packed frame (L complex bins) -> packed real spectrum; both in `x` */
-static __device__ __forceinline__ double2 rfft64_split(double2 a, double2 b, double2 tw)       /* :102-115 */
-{
-    const double t1a = b.x - a.x, t1b = b.y + a.y;
-    const double p0 = __dmul_rn(tw.x, t1a), p1 = __dmul_rn(tw.y, t1a), p2 = __dmul_rn(tw.x, t1b), p3 = __dmul_rn(tw.y, t1b);
-    return make_double2(__dmul_rn(0.5, ((a.x + b.x) + p0) + p3), __dmul_rn(0.5, ((a.y - b.y) + p1) - p2));
-}
-static __device__ __forceinline__ double2 rfft64_merge(double2 a, double2 b, double2 tw)       /* :159-177 */
-{
-    const double t1a = a.x - b.x, t1b = a.y + b.y;
-    const double r = __dmul_rn(tw.x, t1a), s = __dmul_rn(tw.y, t1b), t = __dmul_rn(tw.y, t1a), u = __dmul_rn(tw.x, t1b);
-    return make_double2(__dmul_rn(0.5, ((a.x + b.x) - r) - s), __dmul_rn(0.5, ((a.y - b.y) + t) - u));
-}
-template <bool MERGE>
-__global__ void __launch_bounds__(256) rfft64_stage_kernel(const double2 *__restrict__ src, double2 *dst, const double2 *__restrict__ twr,
-                                                           uint32_t L, uint64_t nFrames)
-{
-    const uint32_t per = L / 2 + 1;                         /* bin pairs (k, L - k), k = 0 .. L/2 */
-    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= nFrames * per) return;
-    const uint64_t frame = idx / per;
-    const uint32_t k = (uint32_t)(idx % per);
-    const double2 *x = src + frame * L;
-    double2 *y = dst + frame * L;
-    if (k == 0) {
-        const double2 a = x[0];
-        if (MERGE) y[0] = make_double2(__dmul_rn(0.5, a.x + a.y), __dmul_rn(0.5, a.x - a.y));             /* :143-144 */
-        else { const double t1a = a.x + a.x, t1b = a.y + a.y; y[0] = make_double2(__dmul_rn(0.5, t1a + t1b), __dmul_rn(0.5, t1a - t1b)); }   /* :56-65 */
-        return;
-    }
-    const double2 a = x[k], b = x[L - k];
-    const double2 oa = MERGE ? rfft64_merge(a, b, twr[k]) : rfft64_split(a, b, twr[k]);
-    if (2 * k != L) {
-        const double2 ob = MERGE ? rfft64_merge(b, a, twr[L - k]) : rfft64_split(b, a, twr[L - k]);
-        y[L - k] = ob;
-    }
-    y[k] = oa;
-}
-
 extern "C" int cmsisdsp_cuda_rfft_fast_f64(const void *d_p, void *d_out, uint32_t fftLenReal, uint64_t nFrames, uint8_t ifftFlag, void *stream)
 {
     if ((!d_p || !d_out) && nFrames) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "null data pointer");
@@ -423,39 +385,11 @@ extern "C" int cmsisdsp_cuda_rfft_fast_f64(const void *d_p, void *d_out, uint32_
         twr = g_dev[dev].twr64[li];
     }
     if (!twr) return fail(CMSISDSP_CUDA_ERR_NO_PLAN, "no f64 rfft plan uploaded for this (device, fftLen)");
-    if (nFrames == 0) return CMSISDSP_CUDA_OK;
-    /* Measured and rejected as a default (profiles/r1_f_notes.md): running the two launches of a direction over
-     * L2-sized CHUNKS of the batch, so that the second finds the first's output in L2.  With separate launches the
-     * per-chunk launch cost and drain outweigh the saved HBM round trip at every chunk size (1 GiB batches, N = 1024:
-     * whole batch 49.9 %, 64 MiB chunks 39.5 %, 16 MiB 27.6 %, 4 MiB 12.2 % of the HBM peak).  The knob stays for
-     * re-measurement: CMSISDSP_CUDA_RFFT64_CHUNK_MIB (0 = the whole batch per launch, the default). */
-    static const long chunkMiB = [] { const char *e = getenv("CMSISDSP_CUDA_RFFT64_CHUNK_MIB"); return e ? atol(e) : 0L; }();
-    const uint32_t L = fftLenReal / 2;
-    const uint64_t frameBytes = (uint64_t)fftLenReal * sizeof(double);
-    uint64_t perChunk = chunkMiB > 0 ? ((uint64_t)chunkMiB << 20) / frameBytes : nFrames;
-    if (perChunk == 0) perChunk = 1;
-    cudaStream_t st = (cudaStream_t)stream;
-    for (uint64_t f = 0; f < nFrames; f += perChunk) {
-        const uint64_t n = (nFrames - f < perChunk) ? nFrames - f : perChunk;
-        const char *src = (const char *)d_p + f * frameBytes;
-        char *dst = (char *)d_out + f * frameBytes;
-        const uint64_t items = n * (uint64_t)(L / 2 + 1), blocks = (items + 255) / 256;
-        if (blocks > 0x7fffffffull) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "batch too large for one launch");
-        if (!ifftFlag) {
-            rc = cfft_io(CMSISDSP_CUDA_F64, src, dst, L, n, 0, 1, stream);
-            if (rc) return rc;
-            rfft64_stage_kernel<false><<<(unsigned)blocks, 256, 0, st>>>((const double2 *)dst, (double2 *)dst, (const double2 *)twr, L, n);
-            shim_count_launch();
-            CU_TRY(cudaGetLastError());
-        } else {
-            rfft64_stage_kernel<true><<<(unsigned)blocks, 256, 0, st>>>((const double2 *)src, (double2 *)dst, (const double2 *)twr, L, n);
-            shim_count_launch();
-            CU_TRY(cudaGetLastError());
-            rc = cfft_any(CMSISDSP_CUDA_F64, dst, L, n, 1, 1, stream);
-            if (rc) return rc;
-        }
-    }
-    return CMSISDSP_CUDA_OK;
+    DevPlan pl;
+    rc = get_plan(CMSISDSP_CUDA_F64, fftLenReal / 2, &pl);
+    if (rc) return rc;
+    const KernelEntry *ke = kEntries[ifftFlag ? OP_RFFT_F64_INV : OP_RFFT_F64_FWD][li - 1];
+    return ke->launch(d_p, d_out, nFrames, ifftFlag != 0, pl.tw, twr, 0, KF_DIRECT, (cudaStream_t)stream);
 }
 
 /* arm_cfft_f32 + spectrum epilogue: mode 0 magnitudes, 1 squared magnitudes (d_out: fftLen floats per frame),
@@ -506,7 +440,7 @@ extern "C" int cmsisdsp_cuda_rfft_q15(const void *d_src, void *d_dst, uint32_t f
 
 extern "C" int cmsisdsp_cuda_kernel_info(int op, uint32_t fftLen, int *threads, int *frames, int *smem, int *regs, int *ctasPerSm)
 {
-    const int li = len_index((op >= 3 && op <= 8) ? fftLen / 2 : fftLen);       /* ops 3..8 take the real length */
+    const int li = len_index(((op >= 3 && op <= 8) || op == OP_RFFT_F64_FWD || op == OP_RFFT_F64_INV) ? fftLen / 2 : fftLen);   /* real length */
     if (op < 0 || op >= OP_COUNT || li < 0 || !kEntries[op][li]) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "kernel_info: unsupported (op, fftLen)");
     KernelFacts f;
     int rc = kEntries[op][li]->facts(&f, choose_flavour(kEntries[op][li]));

@@ -450,6 +450,140 @@ template <class PL> struct RfftFixFwdBody {
     }
 };
 
+/* ------------------------------------------------------------------ arm_rfft_fast_f64, fused
+ *
+ * Forward (arm_rfft_fast_f64.c:224-231): the L-point CFFT of the frame (L = fftLenRFFT / 2 = PL::N) and
+ * stage_rfft_f64 (:30-118) in one kernel, the way RfftFixFwdBody does it for the fixed-point types: the last pass
+ * leaves X in the exchange buffer in natural order, then every thread splits E bins from X[k] and X[L-k] and writes
+ * the packed spectrum {DC, Nyquist, Re1, Im1, ...}.  Inverse (:215-222): merge_rfft_f64 (:121-181) is the load of the
+ * inverse CFFT.  HBM: 16 L bytes in, 16 L bytes out, once.  Products are rounded on their own (ArithF64::mul) and sums
+ * run left to right as in the reference, so the results are bit-identical to the two-kernel adapter and the oracle. */
+FFT_HD cf64 rfft64_split(cf64 a, cf64 b, cf64 tw)          /* a = X[k], b = X[L-k], tw = (twR, twI) = coef[2k], coef[2k+1] */
+{
+    const double t1a = b.x - a.x, t1b = b.y + a.y;
+    const double p0 = ArithF64::mul(tw.x, t1a), p1 = ArithF64::mul(tw.y, t1a), p2 = ArithF64::mul(tw.x, t1b), p3 = ArithF64::mul(tw.y, t1b);
+    return {ArithF64::mul(0.5, ((a.x + b.x) + p0) + p3), ArithF64::mul(0.5, ((a.y - b.y) + p1) - p2)};
+}
+FFT_HD cf64 rfft64_merge(cf64 a, cf64 b, cf64 tw)
+{
+    const double t1a = a.x - b.x, t1b = a.y + b.y;
+    const double r = ArithF64::mul(tw.x, t1a), s = ArithF64::mul(tw.y, t1b), t = ArithF64::mul(tw.y, t1a), u = ArithF64::mul(tw.x, t1b);
+    return {ArithF64::mul(0.5, ((a.x + b.x) - r) - s), ArithF64::mul(0.5, ((a.y - b.y) + t) - u)};
+}
+FFT_HD cf64 rfft64_split0(cf64 a)                          /* :47-65 */
+{
+    const double t1a = a.x + a.x, t1b = a.y + a.y;
+    return {ArithF64::mul(0.5, t1a + t1b), ArithF64::mul(0.5, t1a - t1b)};
+}
+FFT_HD cf64 rfft64_merge0(cf64 a) { return {ArithF64::mul(0.5, a.x + a.y), ArithF64::mul(0.5, a.x - a.y)}; }   /* :138-144 */
+
+template <class PL> struct RfftF64FwdBody {
+    typedef CfftBody<PL, false> C;
+    typedef typename C::Eng Eng;
+    typedef typename C::A A;
+    typedef cf64 elem;
+    typedef cf64 xelem;
+    typedef cf64 telem;
+    typedef cf64 work;
+    typedef typename Eng::Regs Regs;
+    static constexpr int NP = PL::NP, E = PL::E, N = PL::N, T = PL::T;
+    static constexpr int kCfftPhases = PhaseCount<NP>::value;
+    static constexpr int kPhases = kCfftPhases + 2;
+    static_assert(NP > 1, "the f64 plans have at least one exchange");
+
+    struct Args {
+        const cf64 *in;          /* L complex = fftLenRFFT doubles */
+        cf64 *out;               /* L complex: packed spectrum */
+        const cf64 *tw;          /* twiddles of the L-point CFFT plan */
+        const cf64 *twr;         /* twiddleCoefF64_rfft: (sin, cos) pairs, L entries */
+    };
+    static FFT_HD Args for_frame(Args a, uint64_t frame)
+    {
+        a.in += frame * (uint64_t)N;
+        a.out += frame * (uint64_t)N;
+        return a;
+    }
+    static FFT_HD void set_scratch(Args &, xelem *) {}
+    static FFT_HD typename C::Args cfft_args(const Args &a) { return typename C::Args{a.in, nullptr, a.tw, nullptr, 0.0f, 0, nullptr}; }
+
+    template <int PH> static FFT_HD void phase(Regs &r, const Args &a, xelem *sm, int i)
+    {
+        typedef typename PassOf<PL, NP - 1>::type PSL;
+        if constexpr (PH < kCfftPhases) {
+            C::template phase<PH, true>(r, cfft_args(a), sm, i);
+        } else if constexpr (PH == kCfftPhases) {
+#pragma unroll
+            for (int b = 0; b < E / PSL::R; b++)
+#pragma unroll
+                for (int e = 0; e < PSL::R; e++) {
+                    const int k = Eng::template out_index<NP - 1>(i, b, e);
+                    FFT_TRACE_SMEM(&sm[k], (int)sizeof(xelem), 1);
+                    sm[k] = r.v[b * PSL::R + e];                      /* natural order, not padded */
+                }
+        } else {
+#pragma unroll
+            for (int m = 0; m < E; m++) {
+                const int k = i + T * m;
+                FFT_TRACE_SMEM(&sm[k], (int)sizeof(xelem), 0);
+                FFT_TRACE_SMEM(&sm[k ? N - k : 0], (int)sizeof(xelem), 0);
+                if (m == 0 && i == 0) st_stream(a.out, rfft64_split0(sm[0]));
+                else st_stream(a.out + k, rfft64_split(sm[k], sm[N - k], a.twr[k]));
+            }
+        }
+    }
+};
+
+template <class PL> struct RfftF64InvBody {
+    typedef CfftBody<PL, true> C;
+    typedef typename C::Eng Eng;
+    typedef typename C::A A;
+    typedef cf64 elem;
+    typedef cf64 xelem;
+    typedef cf64 telem;
+    typedef cf64 work;
+    typedef typename Eng::Regs Regs;
+    static constexpr int NP = PL::NP, E = PL::E, N = PL::N, T = PL::T;
+    static constexpr int kPhases = PhaseCount<NP>::value;
+    static_assert(NP > 1, "the f64 plans have at least one exchange");
+
+    struct Args {
+        const cf64 *in;          /* packed spectrum, L complex */
+        cf64 *out;               /* L complex = fftLenRFFT doubles */
+        const cf64 *tw;
+        const cf64 *twr;
+        float scale;             /* 1 / L */
+    };
+    static FFT_HD Args for_frame(Args a, uint64_t frame)
+    {
+        a.in += frame * (uint64_t)N;
+        a.out += frame * (uint64_t)N;
+        return a;
+    }
+    static FFT_HD void set_scratch(Args &, xelem *) {}
+    static FFT_HD typename C::Args cfft_args(const Args &a) { return typename C::Args{a.in, a.out, a.tw, nullptr, a.scale, 0, nullptr}; }
+
+    template <int PH> static FFT_HD void phase(Regs &r, const Args &a, xelem *sm, int i)
+    {
+        if constexpr (PH == 0) {
+            typedef typename PL::P0 PS;
+#pragma unroll
+            for (int b = 0; b < E / PS::R; b++)
+#pragma unroll
+                for (int e = 0; e < PS::R; e++) {
+                    const int idx = Eng::template in_index<0>(i, b, e);
+                    /* every bin is read twice (as X[k] and as X[L-k]): plain cached loads */
+                    work w = idx ? rfft64_merge(a.in[idx], a.in[N - idx], a.twr[idx]) : rfft64_merge0(a.in[0]);
+                    w.y = -w.y;                                           /* conjugate input (arm_cfft_f64.c:262-272) */
+                    r.v[b * PS::R + e] = w;
+                }
+            Eng::template compute<0, true>(r, a.tw, i);
+            Eng::template smem_store<0>(r, sm, i);
+        } else {
+            C::template phase<PH>(r, cfft_args(a), sm, i);
+        }
+    }
+};
+
 /* ------------------------------------------------------------------ RFFT (f32 only) */
 
 /* split stage for one bin: A = X[k], B = X[Nh-k], tw = twiddleCoef_rfft[k] = (sin,cos)

@@ -12,7 +12,7 @@ namespace b200fft {
 
 enum KernelOp { OP_CFFT_F32 = 0, OP_CFFT_Q31 = 1, OP_CFFT_Q15 = 2, OP_RFFT_FWD = 3, OP_RFFT_INV = 4,
                 OP_RFFT_Q31_FWD = 5, OP_RFFT_Q31_INV = 6, OP_RFFT_Q15_FWD = 7, OP_RFFT_Q15_INV = 8, OP_CFFT_MAG_F32 = 9,
-                OP_CFFT_F64 = 10, OP_COUNT = 11 };
+                OP_CFFT_F64 = 10, OP_RFFT_F64_FWD = 11, OP_RFFT_F64_INV = 12, OP_COUNT = 13 };
 
 struct KernelFacts { int threads, frames, smem, regs, ctasPerSm; };
 

@@ -56,7 +56,7 @@
 #endif
 
 #if !defined(KU_OP) || !defined(KU_N)
-#error "compile with -DKU_OP=<0..10> -DKU_N=<length>"
+#error "compile with -DKU_OP=<0..12> -DKU_N=<length>"
 #endif
 
 using namespace b200fft;
@@ -693,6 +693,28 @@ static int ku_facts(KernelFacts *f, int flavour)
     }
     return facts_of<CfftMagBody<PL, false, SPEC_MAG>, PL>(f);
 }
+typedef PL TWPLAN;
+
+#elif KU_OP == 11 || KU_OP == 12   /* arm_rfft_fast_f64 forward (11) / inverse (12), KU_N = complex length = fftLenRFFT / 2 */
+
+typedef PlanCfftF64<KU_N>::type PL;
+struct PIPE { static constexpr bool kHas = false, kPrefer = false; };
+#if KU_OP == 11
+typedef RfftF64FwdBody<PL> BODY;
+#else
+typedef RfftF64InvBody<PL> BODY;
+#endif
+/* in -> out (never aliased), tw = the twiddles of the KU_N-point f64 CFFT plan, aux = twiddleCoefF64_rfft (device) */
+static int ku_launch(const void *in, void *out, uint64_t nFrames, int, const void *tw, const void *aux, int, int, cudaStream_t st)
+{
+#if KU_OP == 11
+    BODY::Args a{(const cf64 *)in, (cf64 *)out, (const cf64 *)tw, (const cf64 *)aux};
+#else
+    BODY::Args a{(const cf64 *)in, (cf64 *)out, (const cf64 *)tw, (const cf64 *)aux, 1.0f / (float)PL::N};
+#endif
+    return launch<BODY, PL>(a, nFrames, st);
+}
+static int ku_facts(KernelFacts *f, int) { return facts_of<BODY, PL>(f); }
 typedef PL TWPLAN;
 
 #else              /* arm_rfft_q31 (5 forward, 6 inverse) / arm_rfft_q15 (7, 8); KU_N = complex length = fftLenReal / 2 */

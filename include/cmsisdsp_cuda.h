@@ -85,8 +85,8 @@ int  cmsisdsp_cuda_cfft_q15(void *d_p, uint32_t fftLen, uint64_t nFrames,
 /* d_p: nFrames*2*fftLen doubles, 16-byte aligned */
 int  cmsisdsp_cuda_cfft_f64(void *d_p, uint32_t fftLen, uint64_t nFrames,
                             uint8_t ifftFlag, uint8_t bitReverseFlag, void *stream);
-/* arm_rfft_fast_f64 (Source/TransformFunctions/arm_rfft_fast_f64.c:207-233): an adapter over cmsisdsp_cuda_cfft_f64
- * (complex transform, then the split stage in place on d_out; inverse: merge stage, then the inverse transform).
+/* arm_rfft_fast_f64 (Source/TransformFunctions/arm_rfft_fast_f64.c:207-233): one fused kernel per direction (the
+ * N/2-point f64 transform with the split stage as its epilogue / the merge stage as the load of the inverse).
  * Needs the f64 plan of fftLenReal/2 and pTwiddleRFFT = fftLenReal doubles ((sin,cos) pairs).  d_p is left untouched;
  * d_p and d_out: nFrames*fftLenReal doubles, 16-byte aligned, not aliased. */
 int  cmsisdsp_cuda_rfft_f64_plan_upload(uint32_t fftLenReal, const double *pTwiddleRFFT);
@@ -148,7 +148,7 @@ const char *cmsisdsp_cuda_last_error(void);        /* thread-local, never NULL *
 uint64_t    cmsisdsp_cuda_launch_count(void);      /* kernels launched by this library so far */
 /* static facts about the kernel chosen for (op, fftLen): op 0 cfft_f32, 1 cfft_q31, 2 cfft_q15,
  * 3 rfft forward, 4 rfft inverse, 5/6 rfft_q31 forward/inverse, 7/8 rfft_q15 forward/inverse (fftLen = real
- * length for 3..8), 9 cfft_f32 + magnitude epilogue, 10 cfft_f64.  Any out pointer may be NULL. */
+ * length for 3..8), 9 cfft_f32 + magnitude epilogue, 10 cfft_f64, 11/12 rfft_fast_f64 forward/inverse (real length).  Any out pointer may be NULL. */
 int  cmsisdsp_cuda_kernel_info(int op, uint32_t fftLen, int *threadsPerCta, int *framesPerCta,
                                int *smemBytes, int *regsPerThread, int *ctasPerSm);
 

@@ -274,6 +274,33 @@ int emu_cfft_mag(uint32_t N, const float *in, float *mag, uint64_t nFrames, int 
     }
 }
 
+int emu_rfft64(uint32_t Nreal, const double *in, double *out, uint64_t nFrames, int ifft, const void *tw, const void *twr)
+{
+    switch (Nreal / 2) {
+#define CASE(nc)                                                                                     \
+    case nc: {                                                                                       \
+        typedef PlanCfftF64<nc>::type PL;                                                            \
+        std::vector<cf64> ordered((size_t)PL::kTwEntries + 1);                                       \
+        PL::build_twiddles((const cf64 *)tw, ordered.data());                                        \
+        if (!ifft) {                                                                                 \
+            typedef RfftF64FwdBody<PL> BODY;                                                         \
+            run_batch<PL, BODY>(nFrames, [&](uint64_t f) {                                           \
+                return BODY::Args{(const cf64 *)in + f * nc, (cf64 *)out + f * nc, ordered.data(), (const cf64 *)twr}; \
+            });                                                                                      \
+        } else {                                                                                     \
+            typedef RfftF64InvBody<PL> BODY;                                                         \
+            run_batch<PL, BODY>(nFrames, [&](uint64_t f) {                                           \
+                return BODY::Args{(const cf64 *)in + f * nc, (cf64 *)out + f * nc, ordered.data(), (const cf64 *)twr, 1.0f / (float)nc}; \
+            });                                                                                      \
+        }                                                                                            \
+        return 0;                                                                                    \
+    }
+        FOR_RFFT_NC(CASE)
+#undef CASE
+    default: return -1;
+    }
+}
+
 void emu_trace_begin(void) { g_trace.clear(); g_trace_on = true; }
 
 /* Per (phase, is_store): number of warp-level requests and the shared-memory wavefronts they

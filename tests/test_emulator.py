@@ -30,6 +30,7 @@ def emu():
     L.emu_rfft.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
     L.emu_trace_stats.argtypes = [C.c_void_p, C.c_int]
     L.emu_cfft_mag.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p]
+    L.emu_rfft64.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
     L.emu_rfft_fix.argtypes = [C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     return L
 
@@ -113,6 +114,24 @@ def test_exchange_bank_conflicts(emu, kind, N, limit):
     assert len(rows) > 0
     for ph, st, nbytes, req, ideal, wf in rows:
         assert wf <= limit * ideal, (kind, N, int(ph), "store" if st else "load", wf / ideal)
+
+
+@pytest.mark.parametrize("N", RLENGTHS)
+def test_rfft_fast_f64_bodies(emu, N):
+    """fused f64 real FFT (CFFT + split epilogue / merge prologue): bit-identical to the oracle, input untouched,
+    every exchange (the natural-order one of the split stage included) conflict-free"""
+    tw, _ = cd.instance_tables(cd.cfft_instance("f64", N // 2), "f64")
+    S = cd.rfft_f64_instance(N)
+    twr = np.ctypeslib.as_array(S.pTwiddleRFFT, shape=(N,)).copy()
+    x = np.random.default_rng(N).standard_normal((67, N))
+    for ifft in (0, 1):
+        want = oracle().rfft_f64(N, x, ifft)
+        got, xin = np.zeros_like(x), x.copy()
+        rows = _trace(emu, lambda: emu.emu_rfft64(N, xin.ctypes.data, got.ctypes.data, x.shape[0], ifft, tw.ctypes.data, twr.ctypes.data))
+        assert np.array_equal(xin, x)
+        assert np.array_equal(got.view(np.uint64), want.view(np.uint64)), (N, ifft)
+        for ph, st, nbytes, req, ideal, wf in rows:
+            assert wf == ideal, (N, ifft, int(ph), "store" if st else "load", wf / ideal)
 
 
 @pytest.mark.parametrize("N", LENGTHS)

@@ -101,7 +101,7 @@ def main():
                 samples = B * N
                 info = cd.kernel_info(9, N)
             elif op.startswith("rfft64"):
-                # arm_rfft_fast_f64 (adapter: two launches); algorithmic bytes as for the f32 real FFT: N in + N out doubles
+                # arm_rfft_fast_f64 (fused kernels); algorithmic bytes as for the f32 real FFT: N in + N out doubles
                 if N < 32:
                     continue
                 B = nbytes // (8 * N)
@@ -112,7 +112,7 @@ def main():
                 fn = lambda: cd.rfft_f64_device(N, a.data_ptr(), b.data_ptr(), B, inv, st)
                 alg = 2 * B * N * 8
                 samples = B * N
-                info = cd.kernel_info(10, N // 2)
+                info = cd.kernel_info(12 if inv else 11, N)
             elif op.startswith("rfftq"):
                 # rfftq31_fwd / rfftq31_inv / rfftq15_fwd / rfftq15_inv; N = real length; algorithmic bytes:
                 # forward N in + 2N out scalars, inverse N+2 in (bins 0..N/2) + N out
