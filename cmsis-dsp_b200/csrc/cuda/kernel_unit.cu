@@ -19,14 +19,16 @@
  * CTAs; (threads, 0) = no second bound = its occupancy heuristic.  Chosen per (op, length) from an A/B sweep of all
  * units (profiles/r1_e_notes.md): free registers win for the f32 units, cfft_q31 up to N = 2048 (+12 points at 512),
  * rfft_q31 forward up to complex 256 and rfft_q31 inverse; they lose 2-13 points for the 256-thread CTAs of N = 4096
- * and for the q15 real FFT, and are neutral for cfft_q15. */
+ * and for the q15 real FFT, and are neutral for cfft_q15.  Fused rfft_fast_f64 (profiles/r1_f_notes.md): free registers win
+ * for the forward units at every length (+1..22 points: real N = 256 62.9 -> 84.9 %, 1024 60.7 -> 73.9 %) and lose 1-15
+ * points for the inverse ones except the shortest. */
 #ifndef KU_MINB
 #if KU_OP == 10 && (KU_N == 1024 || KU_N == 2048)
 /* cfft_f64: 128 registers / 4 CTAs at N = 1024 (92.1 vs 91.1 % of the HBM peak with free registers), 96 / 5 CTAs at
  * N = 2048 (84.9 vs 84.3 %); N = 4096 stays on ptxas' own choice (128 registers, 2 CTAs of 256 threads: a third CTA
  * needs 80 registers, spills, 68.5 -> 48.8 %) */
 #define KU_MINB (KU_N == 1024 ? 4 : 5)
-#elif KU_OP == 0 || KU_OP == 3 || KU_OP == 4 || KU_OP == 9 || KU_OP == 6 || (KU_OP == 10 && KU_N <= 512) || (KU_OP == 1 && KU_N <= 2048) || (KU_OP == 5 && KU_N <= 256)
+#elif KU_OP == 0 || KU_OP == 3 || KU_OP == 4 || KU_OP == 9 || KU_OP == 6 || (KU_OP == 10 && KU_N <= 512) || KU_OP == 11 || (KU_OP == 12 && KU_N == 16) || (KU_OP == 1 && KU_N <= 2048) || (KU_OP == 5 && KU_N <= 256)
 #define KU_MINB 1
 #else
 #define KU_MINB 0
