@@ -520,6 +520,11 @@ template <class PL> struct RfftF64FwdBody {
                     FFT_TRACE_SMEM(&sm[k], (int)sizeof(xelem), 1);
                     sm[k] = r.v[b * PSL::R + e];                      /* natural order, not padded */
                 }
+            /* the registers are free now: fetch this thread's real-stage twiddles so that the loads fly across the
+             * barrier (loaded at the point of use they serialised on one register pair: 16 L2 latencies per thread,
+             * the largest stall of the kernel, profiles/r1_f_ncu_hotspots_rfft_f64_fwd_4096.txt) */
+#pragma unroll
+            for (int m = 0; m < E; m++) r.v[m] = a.twr[i + T * m];
         } else {
 #pragma unroll
             for (int m = 0; m < E; m++) {
@@ -527,7 +532,7 @@ template <class PL> struct RfftF64FwdBody {
                 FFT_TRACE_SMEM(&sm[k], (int)sizeof(xelem), 0);
                 FFT_TRACE_SMEM(&sm[k ? N - k : 0], (int)sizeof(xelem), 0);
                 if (m == 0 && i == 0) st_stream(a.out, rfft64_split0(sm[0]));
-                else st_stream(a.out + k, rfft64_split(sm[k], sm[N - k], a.twr[k]));
+                else st_stream(a.out + k, rfft64_split(sm[k], sm[N - k], r.v[m]));
             }
         }
     }
