@@ -284,6 +284,13 @@ int shim_rfft_tables(uint32_t fftLenReal, const void **twForward, const float **
 
 /* ------------------------------------------------------------------ transforms */
 
+/* Device buffers must be aligned to one complex element (the kernels move whole complex points: 8 bytes for
+ * f32 / q31, 4 for q15, 16 for f64).  The reference takes any scalar-aligned buffer; the C front library's
+ * host-pointer path always satisfies this (its staging buffers are cudaMalloc'ed), a device-pointer caller
+ * with an odd scalar offset gets ERR_ARGUMENT instead of a misaligned-address fault. */
+static int elem_align(int type) { return type == CMSISDSP_CUDA_F64 ? 16 : (type == CMSISDSP_CUDA_Q15 ? 4 : 8); }
+static bool misaligned(const void *p, int a) { return ((uintptr_t)p & (uintptr_t)(a - 1)) != 0; }
+
 static int cfft_io(int type, const void *d_in, void *d_p, uint32_t fftLen, uint64_t nFrames, uint8_t ifftFlag, uint8_t bitReverseFlag, void *stream);
 static int cfft_any(int type, void *d_p, uint32_t fftLen, uint64_t nFrames, uint8_t ifftFlag, uint8_t bitReverseFlag, void *stream)
 {
@@ -300,7 +307,8 @@ static int cfft_io(int type, const void *d_in, void *d_p, uint32_t fftLen, uint6
     const int li = len_index(fftLen);
     /* N = 2*4^m: final << 1 (fixed point only; arm_cfft_q31.c:803-820, arm_cfft_q15.c:810-827) */
     const int shl1 = (type == CMSISDSP_CUDA_Q31 || type == CMSISDSP_CUDA_Q15) ? ((li + 4) & 1) : 0;
-    if (type == CMSISDSP_CUDA_F64 && (((uintptr_t)d_p | (uintptr_t)d_in) & 15u)) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "cfft_f64: data must be 16-byte aligned");
+    if (misaligned(d_p, elem_align(type)) || misaligned(d_in, elem_align(type)))
+        return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "cfft: device data must be aligned to one complex element (8 bytes f32/q31, 4 q15, 16 f64)");
     const KernelEntry *ke = kEntries[cfft_op(type)][li];
     return ke->launch(d_in, d_p, nFrames, ifftFlag == 1, pl.tw, bitReverseFlag ? nullptr : pl.perm, shl1, choose_flavour(ke),
                       (cudaStream_t)stream);
@@ -320,6 +328,7 @@ extern "C" int cmsisdsp_cuda_rfft_fast_f32(const void *d_p, void *d_out, uint32_
 {
     if ((!d_p || !d_out) && nFrames) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "null data pointer");
     if (d_p == d_out && nFrames) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "rfft_fast: p and pOut must not alias");
+    if (misaligned(d_p, 8) || misaligned(d_out, 8)) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "rfft_fast: device data must be 8-byte aligned");
     const int li = len_index(fftLenReal);
     if (li < 1) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "unsupported rfft length (32..4096, power of two)");
     DevPlan pl;
@@ -398,6 +407,8 @@ static int cfft_spectrum(const void *d_src, void *d_out, void *d_aux, uint32_t f
 {
     if ((!d_src || !d_out || (mode == 2 && !d_aux)) && nFrames) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "null data pointer");
     if (d_src == d_out && nFrames) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "spectrum epilogue: source and destination must not alias");
+    if (misaligned(d_src, 8) || misaligned(d_out, 4) || misaligned(d_aux, 4))
+        return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "spectrum epilogue: source must be 8-byte, destinations 4-byte aligned");
     DevPlan pl;
     int rc = get_plan(CMSISDSP_CUDA_F32, fftLen, &pl);
     if (rc) return rc;
@@ -415,6 +426,8 @@ static int rfft_fix(int type, const void *d_src, void *d_dst, uint32_t fftLenRea
 {
     if ((!d_src || !d_dst) && nFrames) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "null data pointer");
     if (d_src == d_dst && nFrames) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "rfft: pSrc and pDst must not alias");
+    if (misaligned(d_src, elem_align(type)) || misaligned(d_dst, elem_align(type)))
+        return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "rfft: device data must be aligned to one complex element (8 bytes q31, 4 q15)");
     const int li = (fftLenReal & 1u) ? -1 : len_index(fftLenReal / 2);
     if (li < 0) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "unsupported fixed-point rfft length (32..8192, power of two)");
     DevPlan pl;

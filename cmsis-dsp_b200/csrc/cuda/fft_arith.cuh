@@ -214,6 +214,7 @@ template <int R, bool TW> FFT_HD void dft_f32(cf32 *x, const cf32 *tw)
 /* An Arith names four representations of a complex point: elem (HBM), work (registers),
  * xelem (shared-memory exchange) and telem (device twiddle table). */
 struct ArithF32 {
+    static constexpr bool kPreShift = false;     /* see ArithQ15::load_shifted */
     static constexpr bool kDirectTw = false;
     static constexpr int kTableNum = 1, kTableDen = 1;
     typedef cf32 elem;
@@ -289,6 +290,7 @@ template <bool INV> FFT_HD ci32 rot_q31(int32_t R, int32_t S, ci32 w)
 #define FFT_FIX_DIRECT_TW_VALUE false
 #endif
 struct ArithQ31 {
+    static constexpr bool kPreShift = false;     /* see ArithQ15::load_shifted */
     static constexpr bool kDirectTw = FFT_FIX_DIRECT_TW_VALUE;     /* fft_frame.cuh: PassFix::kDirect */
     static constexpr int kTableNum = 3, kTableDen = 4;        /* reference table: 3N/4 entries */
     typedef ci32 elem;      /* storage element */
@@ -306,7 +308,7 @@ struct ArithQ31 {
 
     /* radix-4 DIF stage butterfly; outputs in residue order (a', b'[W^1], c'[W^2], d'[W^3]).
      * w1/w2/w3 = table entries (cos,+sin) of W^1, W^2, W^3 for this butterfly. */
-    template <int KIND, bool INV>
+    template <int KIND, bool INV, bool TAIL = false, bool PRE = false>
     static FFT_HD void bfly4(work &A, work &B, work &C, work &D, twid w1, twid w2, twid w3)
     {
         work a = A, b = B, c = C, e = D;
@@ -336,7 +338,7 @@ struct ArithQ31 {
         A = oa; B = ob; C = oc; D = od;
     }
     /* radix-2 pre-pass of the N = 2*4^m lengths (arm_cfft_q31.c:777-797 / :838-856) */
-    template <bool INV> static FFT_HD void bfly2(work &A, work &B, twid w)
+    template <bool INV, bool PRE = false> static FFT_HD void bfly2(work &A, work &B, twid w)
     {
         work a = A, b = B;
         int32_t xt = wsub(a.x >> 2, b.x >> 2), yt = wsub(a.y >> 2, b.y >> 2);
@@ -399,6 +401,21 @@ struct ArithQ31 {
  * as VIADDMNMX + VIMNMX.  tests/test_emulator.py and the GPU parity tests compare against the
  * oracle on full-scale inputs (all 0x8000 / 0x7FFF / alternating) where those fire. */
 
+/* Arithmetic right shifts on the FMA pipe.  The q15 kernels are bound by the ALU pipe (shifts, min/max, byte
+ * permutes: one warp instruction per two cycles per scheduler) while the FMA pipe, just as wide, runs at a quarter
+ * of that.  x >> k is the upper word of the 64-bit product x * 2^(32-k), an IMAD.WIDE -- provided the factor is not
+ * a compile-time constant (the compiler turns it back into a shift), so it lives in constant memory. */
+#if defined(__CUDACC__)
+static __constant__ int32_t g_shr_mul[3] = {1 << 16, 1 << 30, (int32_t)0x80000000u};   /* >> 16, >> 2, and -(x) >> 1 */
+#endif
+#if !defined(__CUDA_ARCH__)
+/* host (the kernel emulator of the CPU tests): the same factors, so the emulator checks these very formulas */
+static const int32_t g_shr_mul_host[3] = {1 << 16, 1 << 30, (int32_t)0x80000000u};
+#define g_shr_mul g_shr_mul_host
+#endif
+FFT_HD int32_t shr16_fma(int32_t v) { return hi32_fma(v, g_shr_mul[0]); }
+FFT_HD int32_t shr2_fma(int32_t v) { return hi32_fma(v, g_shr_mul[1]); }
+
 FFT_HD int32_t sat16(int32_t v)
 {
 #if defined(__CUDA_ARCH__)
@@ -423,18 +440,61 @@ FFT_HD int32_t sat_sub16(int32_t a, int32_t b)
     return sat16(a - b);
 #endif
 }
+/* A value the optimiser knows nothing about.  int16 data sign-extended into 32-bit registers keeps its 16-bit range
+ * in LLVM's eyes, which then narrows the butterfly arithmetic to i16 and legalises every step with a sign-extending
+ * PRMT and register moves (seen in the first stage: ~80 extra instructions per 16 points).  The mov is free. */
+FFT_HD int32_t opaque32(int32_t v)
+{
+#if defined(__CUDA_ARCH__)
+    int32_t r;
+    asm("mov.b32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+#else
+    return v;
+#endif
+}
+/* sat16(a + b) >> 1 and sat16(a - b) >> 1, the head of every middle / last stage butterfly (arm_cfft_radix4_q15.c:
+ * 803-846).  The difference is taken NEGATED, clamp(b - a, -32767, 32768) = -sat16(a - b) (the operand negation is free
+ * in VIADDMNMX, for one operand only), because floor(s / 2) = upper word of (-s) * -2^31: the halving of the four
+ * differences of a butterfly moves to the FMA pipe as an IMAD.WIDE (2^31 itself does not fit the signed factor). */
+FFT_HD int32_t half_sat_add16(int32_t a, int32_t b) { return sat_add16(a, b) >> 1; }
+#ifndef FFT_Q15_DIFF_HALVE_FMA
+#define FFT_Q15_DIFF_HALVE_FMA 1
+#endif
+FFT_HD int32_t half_sat_sub16(int32_t a, int32_t b)
+{
+    if (FFT_Q15_DIFF_HALVE_FMA) {
+#if defined(__CUDA_ARCH__)
+        const int32_t n = max(__viaddmin_s32(b, -a, 32768), -32767);
+#else
+        const int32_t n = (b - a) > 32768 ? 32768 : ((b - a) < -32767 ? -32767 : (b - a));
+#endif
+        return hi32_fma(n, g_shr_mul[2]);
+    }
+    return sat_sub16(a, b) >> 1;
+}
 FFT_HD int32_t q15w(int32_t v) { return (int32_t)(int16_t)(uint16_t)(uint32_t)v; }   /* wrap to int16, keep in a register */
 
 /* Measured and rejected: twiddles pre-shifted by 16 and the sum taken as the upper word of two wide
  * products (no shift on the ALU pipe, which bounds this kernel).  ptxas ends such a pair with IMAD.HI, an
  * XU-pipe instruction on sm_100, and the kernels lost 5-10 % (profiles/r1_e_notes.md). */
-template <bool INV> FFT_HD ci32 rot_q15(int32_t x, int32_t y, ci32 w)
+/* ALUSHIFT: plain shifts (results that go to memory next: an IMAD.WIDE leaves its upper word in the odd register of
+ * a pair, and a 64-bit shared-memory store wants (x, y) in an aligned pair -- the moves cost more than the shift) */
+template <bool INV, bool ALUSHIFT> FFT_HD ci32 rot_q15(int32_t x, int32_t y, ci32 w)
 {
-    if (!INV) return {(w.x * x + w.y * y) >> 16, (w.x * y - w.y * x) >> 16};
-    return {(w.x * x - w.y * y) >> 16, (w.y * x + w.x * y) >> 16};
+    if (ALUSHIFT) {
+        if (!INV) return {(w.x * x + w.y * y) >> 16, (w.x * y - w.y * x) >> 16};
+        return {(w.x * x - w.y * y) >> 16, (w.y * x + w.x * y) >> 16};
+    }
+    if (!INV) return {shr16_fma(w.x * x + w.y * y), shr16_fma(w.x * y - w.y * x)};
+    return {shr16_fma(w.x * x - w.y * y), shr16_fma(w.y * x + w.x * y)};
 }
 
+#ifndef FFT_Q15_SHIFT_MODE
+#define FFT_Q15_SHIFT_MODE 1     /* 0: every rot shift on the ALU pipe, 1: FMA pipe except at the end of a pass, 2: FMA pipe always */
+#endif
 struct ArithQ15 {
+    static constexpr bool kAluShift(bool tail) { return FFT_Q15_SHIFT_MODE == 0 || (FFT_Q15_SHIFT_MODE == 1 && tail); }
     static constexpr bool kDirectTw = FFT_FIX_DIRECT_TW_VALUE;
     static constexpr int kTableNum = 3, kTableDen = 4;
     typedef ci16 elem;
@@ -442,7 +502,16 @@ struct ArithQ15 {
     typedef ci32 twid;
     typedef ci32 xelem;
     typedef ci32 telem;
-    static FFT_HD work load(elem e) { return {(int32_t)e.x, (int32_t)e.y}; }
+    static FFT_HD work load(elem e) { return {opaque32((int32_t)e.x), opaque32((int32_t)e.y)}; }
+    /* A frame's first stage shifts every input right (>> 2 radix-4, >> 1 radix-2 pre-pass): taken straight from the
+     * packed 32-bit word {x, y} that shift is also the unpacking -- y >> SH = word >> (16 + SH), x >> SH =
+     * (word << 16) >> (16 + SH) -- three instructions per point instead of two sign extensions and two shifts.
+     * The stage is then told that its inputs are already shifted (PRE). */
+    static constexpr bool kPreShift = true;
+    template <int SH> static FFT_HD work load_shifted(uint32_t u)      /* u = the point as one little-endian word */
+    {
+        return {opaque32((int32_t)opaque32((int32_t)(u << 16)) >> (16 + SH)), opaque32((int32_t)u >> (16 + SH))};
+    }
     static FFT_HD elem store(work w) { return {(int16_t)w.x, (int16_t)w.y}; }
     static FFT_HD work xload(xelem e) { return e; }
     static FFT_HD xelem xstore(work w) { return w; }
@@ -450,53 +519,54 @@ struct ArithQ15 {
     static FFT_HD twid tload(telem e) { return e; }
     static FFT_HD work shl1(work w) { return {q15w((int32_t)((uint32_t)w.x << 1)), q15w((int32_t)((uint32_t)w.y << 1))}; }
 
-    template <int KIND, bool INV>
+    template <int KIND, bool INV, bool TAIL = false, bool PRE = false>
     static FFT_HD void bfly4(work &A, work &B, work &C, work &D, twid w1, twid w2, twid w3)
     {
         if (KIND == ST_FIRST4) {
             /* inputs >> 2: nothing below can saturate or wrap (see the header of this section) */
-            const int32_t T0 = A.x >> 2, T1 = A.y >> 2, C0 = C.x >> 2, C1 = C.y >> 2;
-            const int32_t B0 = B.x >> 2, B1 = B.y >> 2, U0 = D.x >> 2, U1 = D.y >> 2;
+            const int32_t T0 = PRE ? A.x : A.x >> 2, T1 = PRE ? A.y : A.y >> 2, C0 = PRE ? C.x : C.x >> 2, C1 = PRE ? C.y : C.y >> 2;
+            const int32_t B0 = PRE ? B.x : B.x >> 2, B1 = PRE ? B.y : B.y >> 2, U0 = PRE ? D.x : D.x >> 2, U1 = PRE ? D.y : D.y >> 2;
             const int32_t R0 = T0 + C0, R1 = T1 + C1, S0 = T0 - C0, S1 = T1 - C1;
             const int32_t V0 = B0 + U0, V1 = B1 + U1, D0 = B0 - U0, D1 = B1 - U1;
             A = {(R0 >> 1) + (V0 >> 1), (R1 >> 1) + (V1 >> 1)};
-            C = rot_q15<INV>(R0 - V0, R1 - V1, w2);
+            C = rot_q15<INV, kAluShift(TAIL)>(R0 - V0, R1 - V1, w2);
             if (!INV) {
-                B = rot_q15<INV>(S0 + D1, S1 - D0, w1);
-                D = rot_q15<INV>(S0 - D1, S1 + D0, w3);
+                B = rot_q15<INV, kAluShift(TAIL)>(S0 + D1, S1 - D0, w1);
+                D = rot_q15<INV, kAluShift(TAIL)>(S0 - D1, S1 + D0, w3);
             } else {
-                B = rot_q15<INV>(S0 - D1, S1 + D0, w1);
-                D = rot_q15<INV>(S0 + D1, S1 - D0, w3);
+                B = rot_q15<INV, kAluShift(TAIL)>(S0 - D1, S1 + D0, w1);
+                D = rot_q15<INV, kAluShift(TAIL)>(S0 + D1, S1 - D0, w3);
             }
             return;
         }
         /* middle and last stages: saturating pair sums, then everything on halved operands */
-        const int32_t R0 = sat_add16(A.x, C.x) >> 1, R1 = sat_add16(A.y, C.y) >> 1;
-        const int32_t S0 = sat_sub16(A.x, C.x) >> 1, S1 = sat_sub16(A.y, C.y) >> 1;
-        const int32_t V0 = sat_add16(B.x, D.x) >> 1, V1 = sat_add16(B.y, D.y) >> 1;
-        const int32_t D0 = sat_sub16(B.x, D.x) >> 1, D1 = sat_sub16(B.y, D.y) >> 1;
+        const int32_t S0 = half_sat_sub16(A.x, C.x), S1 = half_sat_sub16(A.y, C.y);
+        const int32_t V0 = half_sat_add16(B.x, D.x), V1 = half_sat_add16(B.y, D.y);
+        const int32_t D0 = half_sat_sub16(B.x, D.x), D1 = half_sat_sub16(B.y, D.y);
+        const int32_t R0 = half_sat_add16(A.x, C.x), R1 = half_sat_add16(A.y, C.y);
+        const int32_t RpV0 = R0 + V0, RpV1 = R1 + V1, RmV0 = R0 - V0, RmV1 = R1 - V1;
         if (KIND == ST_MID4) {
-            A = {(R0 + V0) >> 1, (R1 + V1) >> 1};
-            C = rot_q15<INV>(R0 - V0, R1 - V1, w2);
+            A = {RpV0 >> 1, RpV1 >> 1};
+            C = rot_q15<INV, kAluShift(TAIL)>(RmV0, RmV1, w2);
             if (!INV) {
-                B = rot_q15<INV>(S0 + D1, S1 - D0, w1);
-                D = rot_q15<INV>(S0 - D1, S1 + D0, w3);
+                B = rot_q15<INV, kAluShift(TAIL)>(S0 + D1, S1 - D0, w1);
+                D = rot_q15<INV, kAluShift(TAIL)>(S0 - D1, S1 + D0, w3);
             } else {
-                B = rot_q15<INV>(S0 - D1, S1 + D0, w1);
-                D = rot_q15<INV>(S0 + D1, S1 - D0, w3);
+                B = rot_q15<INV, kAluShift(TAIL)>(S0 - D1, S1 + D0, w1);
+                D = rot_q15<INV, kAluShift(TAIL)>(S0 + D1, S1 - D0, w3);
             }
         } else {
-            A = {R0 + V0, R1 + V1};
-            C = {R0 - V0, R1 - V1};
+            A = {RpV0, RpV1};
+            C = {RmV0, RmV1};
             const work p = {S0 + D1, S1 - D0}, q = {S0 - D1, S1 + D0};
             B = INV ? q : p;
             D = INV ? p : q;
         }
     }
     /* arm_cfft_q15.c:782-800 / :881-899 */
-    template <bool INV> static FFT_HD void bfly2(work &A, work &B, twid w)
+    template <bool INV, bool PRE = false> static FFT_HD void bfly2(work &A, work &B, twid w)
     {
-        const int32_t ax = A.x >> 1, ay = A.y >> 1, bx = B.x >> 1, by = B.y >> 1;
+        const int32_t ax = PRE ? A.x : A.x >> 1, ay = PRE ? A.y : A.y >> 1, bx = PRE ? B.x : B.x >> 1, by = PRE ? B.y : B.y >> 1;
         const int32_t xt = ax - bx, yt = ay - by;
         A = {(ax + bx) >> 1, (ay + by) >> 1};
         if (!INV) B = {((xt * w.x) >> 16) + ((yt * w.y) >> 16), ((yt * w.x) >> 16) - ((xt * w.y) >> 16)};
@@ -537,6 +607,7 @@ struct ArithQ15 {
  * (-ffp-contract=off) -- the f64 kernels have the arithmetic headroom (16 bytes per point).  The inverse is conjugate -> forward -> conjugate / N (:262-312), done by CfftBody at the load and
  * the store like f32, so the butterflies have no inverse variant. */
 struct ArithF64 {
+    static constexpr bool kPreShift = false;     /* see ArithQ15::load_shifted */
     static constexpr bool kDirectTw = false;
     static constexpr int kTableNum = 1, kTableDen = 1;        /* reference table: N entries */
     typedef cf64 elem;
@@ -564,7 +635,7 @@ struct ArithF64 {
 
     /* outputs in residue order (a', b'[W^1], c'[W^2], d'[W^3]); arm_cfft_f64.c:108-170.  The last stage's
      * twiddles are W^0 = (1, 0) (:94-99 with ia1 = 0): the products are skipped. */
-    template <int KIND, bool INV>
+    template <int KIND, bool INV, bool TAIL = false, bool PRE = false>
     static FFT_HD void bfly4(work &A, work &B, work &C, work &D, twid w1, twid w2, twid w3)
     {
         double r1 = A.x + C.x, r2 = A.x - C.x, s1 = A.y + C.y, s2 = A.y - C.y;
@@ -586,7 +657,7 @@ struct ArithF64 {
         A = {ax, ay}; B = ob; C = oc; D = od;
     }
     /* radix-2 pre-pass of the N = 2*4^m lengths (arm_cfft_f64.c:205-230) */
-    template <bool INV> static FFT_HD void bfly2(work &A, work &B, twid w)
+    template <bool INV, bool PRE = false> static FFT_HD void bfly2(work &A, work &B, twid w)
     {
         const double a0 = A.x + B.x, xt = A.x - B.x, yt = A.y - B.y, a1 = B.y + A.y;
         A = {a0, a1};

@@ -40,6 +40,17 @@ template <class V> FFT_HD V ld_stream(const V *p) { return *p; }
 template <class V> FFT_HD void st_stream(V *p, V v) { *p = v; }
 #endif
 
+/* a q15 point as one 32-bit word {x, y} (ArithQ15::load_shifted) */
+FFT_HD uint32_t ld_word(const ci16 *p)
+{
+#if defined(__CUDA_ARCH__)
+    return __ldcs(reinterpret_cast<const unsigned int *>(p));
+#else
+    return (uint32_t)(uint16_t)p->x | ((uint32_t)(uint16_t)p->y << 16);
+#endif
+}
+template <class V> FFT_HD uint32_t ld_word(const V *) { return 0; }     /* other element types never take this path */
+
 /* frame output: STAGED = the result goes into the frame's image in shared memory (a bulk copy
  * takes it home); otherwise straight to global memory with a streaming hint */
 template <bool STAGED, class V> FFT_HD void st_out(V *p, V v)
@@ -92,6 +103,8 @@ template <class PL, bool INV, bool PERM = false, bool STAGED = false, bool RIFFT
     static constexpr int NP = PL::NP, E = PL::E, N = PL::N;
     static constexpr int kPhases = PhaseCount<NP>::value;
     static constexpr bool kF32 = IsFloat<elem>::value;      /* f32 or f64 */
+    /* q15: the first stage's input shift is taken while unpacking the loaded word (ArithQ15::load_shifted) */
+    static constexpr bool kPre = A::kPreShift && !RIFFT;
 
     struct Args {
         const elem *in;          /* frame base (device or emulated) */
@@ -99,7 +112,7 @@ template <class PL, bool INV, bool PERM = false, bool STAGED = false, bool RIFFT
         const telem *tw;         /* pass-ordered twiddle table of this plan (Plan::build_twiddles) */
         const uint16_t *perm;    /* PERM only: destination position of X[k] */
         float scale;             /* f32 inverse: 1/N */
-        int shl1;                /* fixed point, N = 2*4^m: final << 1 of every word */
+        int shl1;                /* fixed point, N = 2*4^m: final << 1 of every word (== PL::kOddLog2: the kernels use the constant) */
         const ci32x4 *coef;      /* RIFFT only: split-stage coefficients of bins 0..N-1 */
     };
     /* frame-local view of the batch arguments; with STAGED the kernel overrides `in` */
@@ -123,6 +136,8 @@ template <class PL, bool INV, bool PERM = false, bool STAGED = false, bool RIFFT
                 if constexpr (RIFFT) {
                     /* every bin is read twice (as X[k] and as X[N-k]): plain cached loads */
                     w = A::split_inv(A::load(a.in[idx]), A::load(a.in[N - idx]), a.coef[idx]);
+                } else if constexpr (kPre) {
+                    w = A::template load_shifted<PS::kInShift>(ld_word(a.in + idx));
                 } else {
                     w = A::load(ld_in<STAGED>(a.in + idx));
                 }
@@ -141,7 +156,7 @@ template <class PL, bool INV, bool PERM = false, bool STAGED = false, bool RIFFT
                 work w = r.v[b * PS::R + e];
                 if (kF32) {
                     if (INV) w = scale_conj(w, a.scale);             /* cfft_f32.c:1285-1297 */
-                } else if (a.shl1) {
+                } else if (PL::kOddLog2) {
                     w = A::shl1(w);                                  /* cfft_q31.c:803-820, cfft_q15.c:810-827 */
                 }
                 if constexpr (RIFFT) w = A::sat_shl1(w);
@@ -163,7 +178,7 @@ template <class PL, bool INV, bool PERM = false, bool STAGED = false, bool RIFFT
     static FFT_HD void phase0_in(Regs &r, const Args &a, xelem *, int i)
     {
         gload(r, a, i);
-        Eng::template compute<0, INV>(r, a.tw, i);
+        Eng::template compute<0, INV, kPre>(r, a.tw, i);
     }
     /* Table values of this thread that do not depend on the frame (Hoist): the persistent kernel
      * fetches them once and parks them in shared memory, column `pk` (stride PL::kThreads); the
@@ -201,7 +216,7 @@ template <class PL, bool INV, bool PERM = false, bool STAGED = false, bool RIFFT
     {
         if constexpr (PH == 0) {
             gload(r, a, i);
-            Eng::template compute<0, INV>(r, a.tw, i);
+            Eng::template compute<0, INV, kPre>(r, a.tw, i);
             if constexpr (NP == 1) {
                 if constexpr (!HOLD) gstore(r, a, i);
             } else {
@@ -421,7 +436,7 @@ template <class PL> struct RfftFixFwdBody {
             C::template phase<0, true>(r, cfft_args(a), sm, i);
             work y[N];                                                /* y[k] = X[k] */
 #pragma unroll
-            for (int e = 0; e < N; e++) y[PSL::out_index(e)] = a.shl1 ? A::shl1(r.v[e]) : r.v[e];
+            for (int e = 0; e < N; e++) y[PSL::out_index(e)] = PL::kOddLog2 ? A::shl1(r.v[e]) : r.v[e];
             put_bin0(a, y[0]);
             bins_in_regs<1>(a, y);
         } else if constexpr (PH < kCfftPhases) {
@@ -435,7 +450,7 @@ template <class PL> struct RfftFixFwdBody {
                     const work w = r.v[b * PSL::R + e];
                     /* natural order, NOT padded: lanes store / load runs of consecutive bins in both directions */
                     FFT_TRACE_SMEM(&sm[k], (int)sizeof(xelem), 1);
-                    sm[k] = A::xstore(a.shl1 ? A::shl1(w) : w);               /* cfft_q31.c:803-820, cfft_q15.c:810-827 */
+                    sm[k] = A::xstore(PL::kOddLog2 ? A::shl1(w) : w);               /* cfft_q31.c:803-820, cfft_q15.c:810-827 */
                 }
         } else {
 #pragma unroll
@@ -1072,7 +1087,7 @@ template <class PL, bool INV, bool PERM = false> struct TinyCfftBody {
             work w = r.v[e];
             if (kF32) {
                 if (INV) w = Base::scale_conj(w, a.scale);                /* cfft_f32.c:1285-1297 */
-            } else if (a.shl1) {
+            } else if (PL::kOddLog2) {
                 w = A::shl1(w);
             }
             y[PS::out_index(e)] = w;
@@ -1241,7 +1256,7 @@ template <class PL, bool INV> struct TinyRfftFixBody {
             Eng::template compute<0, false>(r, a.tw, 0);
             work y[N];                                                 /* y[k] = X[k] */
 #pragma unroll
-            for (int e = 0; e < N; e++) y[PS::out_index(e)] = a.shl1 ? A::shl1(r.v[e]) : r.v[e];
+            for (int e = 0; e < N; e++) y[PS::out_index(e)] = PL::kOddLog2 ? A::shl1(r.v[e]) : r.v[e];
             work z[2 * N];
             z[0] = A::split_dc(y[0]);
             z[N] = A::split_nyquist(y[0]);
@@ -1262,7 +1277,7 @@ template <class PL, bool INV> struct TinyRfftFixBody {
 #pragma unroll
             for (int e = 0; e < N; e++) {
                 work w = r.v[e];
-                if (a.shl1) w = A::shl1(w);
+                if (PL::kOddLog2) w = A::shl1(w);
                 y[PS::out_index(e)] = A::sat_shl1(w);
             }
             out_groups<0>(y, a.out);

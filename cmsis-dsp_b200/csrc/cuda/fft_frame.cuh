@@ -42,7 +42,7 @@ template <int R_> struct PassF32 {
     static constexpr bool kMirror = false;
     static constexpr bool kDirect = false;
     typedef cf32 telem;
-    static FFT_HD int out_index(int e) { return e; }
+    static FFT_HD constexpr int out_index(int e) { return e; }
     /* twiddle slots per butterfly in the pass-ordered table (none on the last pass: W^0) */
     static constexpr int slots(bool lastPass) { return lastPass ? 0 : dft_tw_slots(R); }
     /* butterfly j, e = S*(j/S): level l reads W^(4^l e m), m = 1..3; the base level W^(4^L e t) */
@@ -91,6 +91,7 @@ template <class ARITH, int KA, int KB = -1, int KC = -1> struct PassFix {
     static constexpr int rb = (KB < 0) ? 1 : 4;
     static constexpr int rc = (KC < 0) ? 1 : 4;
     static constexpr int R = ra * rb * rc;
+    static constexpr int kInShift = (KA == ST_PRE2) ? 1 : ((KA == ST_FIRST4) ? 2 : 0);   /* q15: input shift of stage a */
     static constexpr bool kMirror = false;
     typedef typename ARITH::work work;
     typedef typename ARITH::twid twid;
@@ -98,7 +99,7 @@ template <class ARITH, int KA, int KB = -1, int KC = -1> struct PassFix {
     typedef typename ARITH::elem selem;     /* element of the reference-layout source table */
 
     /* element e = u + rc*(w + rb*v) holds residue v + ra*(w + rb*u) after the pass */
-    static FFT_HD int out_index(int e) { return (e / (rb * rc)) + ra * (((e / rc) % rb) + rb * (e % rc)); }
+    static FFT_HD constexpr int out_index(int e) { return (e / (rb * rc)) + ra * (((e / rc) % rb) + rb * (e % rc)); }
 
     static constexpr int tw_of(int K) { return K < 0 ? 0 : (K == ST_PRE2 ? 1 : (K == ST_LAST4 ? 0 : 3)); }
     static constexpr int ta = tw_of(KA), tb = tw_of(KB), tc = tw_of(KC);   /* twiddles per butterfly of each stage */
@@ -129,31 +130,32 @@ template <class ARITH, int KA, int KB = -1, int KC = -1> struct PassFix {
         }
     }
 
-    template <int K, bool INV, int NBF>
+    /* TAIL: the stage is the last one of its pass (its results go to shared or global memory next) */
+    template <int K, bool INV, int NBF, bool TAIL, bool PRE = false>
     static FFT_HD void stage4(work &a, work &b, work &c, work &d, const telem *__restrict__ twp, int slot, int j)
     {
         if (K == ST_LAST4) {
             twid z = {0, 0};
-            ARITH::template bfly4<K, INV>(a, b, c, d, z, z, z);
+            ARITH::template bfly4<K, INV, TAIL>(a, b, c, d, z, z, z);
         } else {
-            ARITH::template bfly4<K, INV>(a, b, c, d, ARITH::tload(twp[slot * NBF + j]), ARITH::tload(twp[(slot + 1) * NBF + j]),
+            ARITH::template bfly4<K, INV, TAIL, PRE>(a, b, c, d, ARITH::tload(twp[slot * NBF + j]), ARITH::tload(twp[(slot + 1) * NBF + j]),
                                           ARITH::tload(twp[(slot + 2) * NBF + j]));
         }
     }
 
     /* radix-4 stage on the reference-layout table: W^1, W^2, W^3 at ia, 2 ia, 3 ia (arm_cfft_radix4_q31.c:229-266) */
-    template <int K, bool INV>
+    template <int K, bool INV, bool TAIL, bool PRE = false>
     static FFT_HD void stage4d(work &a, work &b, work &c, work &d, const telem *__restrict__ tw, int ia)
     {
         if (K == ST_LAST4) {
             twid z = {0, 0};
-            ARITH::template bfly4<K, INV>(a, b, c, d, z, z, z);
+            ARITH::template bfly4<K, INV, TAIL>(a, b, c, d, z, z, z);
         } else {
-            ARITH::template bfly4<K, INV>(a, b, c, d, ARITH::tload(tw[ia]), ARITH::tload(tw[2 * ia]), ARITH::tload(tw[3 * ia]));
+            ARITH::template bfly4<K, INV, TAIL, PRE>(a, b, c, d, ARITH::tload(tw[ia]), ARITH::tload(tw[2 * ia]), ARITH::tload(tw[3 * ia]));
         }
     }
     /* same butterflies as compute(), twiddle indices as in fill(): S = product of the radices of the earlier passes */
-    template <bool INV, int N, int S>
+    template <bool INV, int N, int S, bool PRE = false>
     static FFT_HD void compute_direct(work *x, const telem *__restrict__ tw, int j)
     {
         constexpr int NBF = N / R, Q = rb * rc;
@@ -162,9 +164,9 @@ template <class ARITH, int KA, int KB = -1, int KC = -1> struct PassFix {
         for (int o = 0; o < Q; o++) {                 /* stage a */
             const int ia = sp + NBF * o;
             if (KA == ST_PRE2)
-                ARITH::template bfly2<INV>(x[o], x[o + Q], ARITH::tload(tw[ia]));
+                ARITH::template bfly2<INV, PRE>(x[o], x[o + Q], ARITH::tload(tw[ia]));
             else
-                stage4d<KA, INV>(x[o], x[o + Q], x[o + 2 * Q], x[o + 3 * Q], tw, ia);
+                stage4d<KA, INV, (KB < 0), PRE>(x[o], x[o + Q], x[o + 2 * Q], x[o + 3 * Q], tw, ia);
         }
         if constexpr (KB >= 0) {                      /* stage b */
 #pragma unroll
@@ -172,26 +174,27 @@ template <class ARITH, int KA, int KB = -1, int KC = -1> struct PassFix {
 #pragma unroll
                 for (int u = 0; u < rc; u++) {
                     const int base = u + Q * v;
-                    stage4d<KB, INV>(x[base], x[base + rc], x[base + 2 * rc], x[base + 3 * rc], tw, ra * (sp + NBF * u));
+                    stage4d<KB, INV, (KC < 0)>(x[base], x[base + rc], x[base + 2 * rc], x[base + 3 * rc], tw, ra * (sp + NBF * u));
                 }
         }
         if constexpr (KC >= 0) {                      /* stage c */
 #pragma unroll
             for (int g = 0; g < ra * rb; g++)
-                stage4d<KC, INV>(x[4 * g], x[4 * g + 1], x[4 * g + 2], x[4 * g + 3], tw, ra * rb * sp);
+                stage4d<KC, INV, true>(x[4 * g], x[4 * g + 1], x[4 * g + 2], x[4 * g + 3], tw, ra * rb * sp);
         }
     }
 
-    template <bool INV, int N, bool LASTPASS>
+    /* PRE: the inputs of stage a carry that stage's input shift already (Arith::load_shifted) */
+    template <bool INV, int N, bool LASTPASS, bool PRE = false>
     static FFT_HD void compute(work *x, const telem *__restrict__ twp, int j)
     {
         constexpr int NBF = N / R, Q = rb * rc;
 #pragma unroll
         for (int o = 0; o < Q; o++) {                 /* stage a */
             if (KA == ST_PRE2)
-                ARITH::template bfly2<INV>(x[o], x[o + Q], ARITH::tload(twp[o * NBF + j]));
+                ARITH::template bfly2<INV, PRE>(x[o], x[o + Q], ARITH::tload(twp[o * NBF + j]));
             else
-                stage4<KA, INV, NBF>(x[o], x[o + Q], x[o + 2 * Q], x[o + 3 * Q], twp, o * ta, j);
+                stage4<KA, INV, NBF, (KB < 0), PRE>(x[o], x[o + Q], x[o + 2 * Q], x[o + 3 * Q], twp, o * ta, j);
         }
         if constexpr (KB >= 0) {                      /* stage b */
 #pragma unroll
@@ -199,13 +202,13 @@ template <class ARITH, int KA, int KB = -1, int KC = -1> struct PassFix {
 #pragma unroll
                 for (int u = 0; u < rc; u++) {
                     const int base = u + Q * v;
-                    stage4<KB, INV, NBF>(x[base], x[base + rc], x[base + 2 * rc], x[base + 3 * rc], twp, kOffB + u * tb, j);
+                    stage4<KB, INV, NBF, (KC < 0)>(x[base], x[base + rc], x[base + 2 * rc], x[base + 3 * rc], twp, kOffB + u * tb, j);
                 }
         }
         if constexpr (KC >= 0) {                      /* stage c */
 #pragma unroll
             for (int g = 0; g < ra * rb; g++)
-                stage4<KC, INV, NBF>(x[4 * g], x[4 * g + 1], x[4 * g + 2], x[4 * g + 3], twp, kOffC, j);
+                stage4<KC, INV, NBF, true>(x[4 * g], x[4 * g + 1], x[4 * g + 2], x[4 * g + 3], twp, kOffC, j);
         }
     }
 };
@@ -231,11 +234,22 @@ struct Plan {
     static constexpr int F = F_;          /* frames per CTA */
     static constexpr int E = N / T;       /* points per thread */
     static constexpr int NP = (P1::R == 1) ? 1 : ((P2::R == 1) ? 2 : 3);
+    /* N = 2*4^m: the fixed-point transforms start with a radix-2 stage and end with << 1 (arm_cfft_q31.c:803-820) */
+    static constexpr bool kOddLog2 = (N_ & 0xAAAAAAAA) != 0;
     static constexpr int S0 = 1, S1 = P0::R, S2 = P0::R * P1::R;
     static_assert(P0::R * P1::R * P2::R == N, "radices must multiply to N");
     static_assert(E % P0::R == 0 && E % P1::R == 0 && E % P2::R == 0, "E must be a multiple of every radix");
     /* padded exchange layout: PADB extra elements after every 2^PADA elements */
     static FFT_HD int pad(int i) { return PADB_ ? (i + ((i >> PADA_) * PADB_)) : i; }
+    /* pad(base + off) for a compile-time `off`: when off is a multiple of the padding period the padding of the two
+     * terms adds up, so a thread's accesses are ONE padded base plus immediate offsets (the compiler does not
+     * discover this by itself: it rebuilt every padded index from scratch, ~6 instructions per point on q15) */
+    template <int OFF> static FFT_HD int pad_at(int base, int paddedBase)
+    {
+        if constexpr (PADB_ == 0) return base + OFF;
+        else if constexpr (OFF % (1 << PADA_) == 0) return paddedBase + OFF + (OFF >> PADA_) * PADB_;
+        else return pad(base + OFF);
+    }
     static constexpr int kPadded = PADB_ ? (N + ((N - 1) >> PADA_) * PADB_ + PADB_) : N;
     /* scratch behind the exchange area for the 2R self-paired bins of an rfft Mirror pass (fft_body.cuh) */
     static constexpr int kSpecial = P0_::kMirror ? 2 * P0_::R : (P1_::kMirror ? 2 * P1_::R : (P2_::kMirror ? 2 * P2_::R : 0));
@@ -297,48 +311,68 @@ template <class PL> struct Engine {
     struct Regs { work v[E]; };
 
     /* ---- shared-memory exchange ---- */
-    template <int P> static FFT_HD void smem_store(const Regs &r, xelem *sm, int i)
+    template <int P, int B0, int E0> static FFT_HD void store_elems(const Regs &r, xelem *sm, int base, int pbase)
+    {
+        typedef typename PassOf<PL, P>::type PS;
+        constexpr int R = PS::R, S = PassOf<PL, P>::S;
+        if constexpr (E0 < R) {
+            const int idx = PL::template pad_at<S * PS::out_index(E0)>(base, pbase);
+            FFT_TRACE_SMEM(&sm[idx], (int)sizeof(xelem), 1);
+            sm[idx] = A::xstore(r.v[B0 * R + E0]);
+            store_elems<P, B0, E0 + 1>(r, sm, base, pbase);
+        }
+    }
+    template <int P, int B0> static FFT_HD void store_bflies(const Regs &r, xelem *sm, int i)
     {
         typedef typename PassOf<PL, P>::type PS;
         constexpr int R = PS::R, S = PassOf<PL, P>::S, NB = E / R, NBF = N / R;
-#pragma unroll
-        for (int b = 0; b < NB; b++) {
-            const int j = bfly_index<PS::kMirror, T, NBF>(i, b);
+        if constexpr (B0 < NB) {
+            const int j = bfly_index<PS::kMirror, T, NBF>(i, B0);
             const int base = (j % S) + S * R * (j / S);
-#pragma unroll
-            for (int e = 0; e < R; e++) {
-                const int idx = PL::pad(base + S * PS::out_index(e));
-                FFT_TRACE_SMEM(&sm[idx], (int)sizeof(xelem), 1);
-                sm[idx] = A::xstore(r.v[b * R + e]);
-            }
+            store_elems<P, B0, 0>(r, sm, base, PL::pad(base));
+            store_bflies<P, B0 + 1>(r, sm, i);
         }
     }
-    template <int P> static FFT_HD void smem_load(Regs &r, const xelem *sm, int i)
+    template <int P> static FFT_HD void smem_store(const Regs &r, xelem *sm, int i) { store_bflies<P, 0>(r, sm, i); }
+
+    template <int P, int B0, int E0> static FFT_HD void load_elems(Regs &r, const xelem *sm, int j, int pj)
+    {
+        typedef typename PassOf<PL, P>::type PS;
+        constexpr int R = PS::R, NBF = N / R;
+        if constexpr (E0 < R) {
+            const int idx = PL::template pad_at<E0 * NBF>(j, pj);
+            FFT_TRACE_SMEM(&sm[idx], (int)sizeof(xelem), 0);
+            r.v[B0 * R + E0] = A::xload(sm[idx]);
+            load_elems<P, B0, E0 + 1>(r, sm, j, pj);
+        }
+    }
+    template <int P, int B0> static FFT_HD void load_bflies(Regs &r, const xelem *sm, int i)
     {
         typedef typename PassOf<PL, P>::type PS;
         constexpr int R = PS::R, NB = E / R, NBF = N / R;
-#pragma unroll
-        for (int b = 0; b < NB; b++) {
-            const int j = bfly_index<PS::kMirror, T, NBF>(i, b);
-#pragma unroll
-            for (int e = 0; e < R; e++) {
-                const int idx = PL::pad(j + e * NBF);
-                FFT_TRACE_SMEM(&sm[idx], (int)sizeof(xelem), 0);
-                r.v[b * R + e] = A::xload(sm[idx]);
-            }
+        if constexpr (B0 < NB) {
+            const int j = bfly_index<PS::kMirror, T, NBF>(i, B0);
+            load_elems<P, B0, 0>(r, sm, j, PL::pad(j));
+            load_bflies<P, B0 + 1>(r, sm, i);
         }
     }
+    template <int P> static FFT_HD void smem_load(Regs &r, const xelem *sm, int i) { load_bflies<P, 0>(r, sm, i); }
 
     /* ---- butterflies of pass P on the registers ---- */
-    template <int P, bool INV, class TW> static FFT_HD void compute(Regs &r, const TW *__restrict__ tw, int i)
+    template <int P, bool INV, bool PRE = false, class TW> static FFT_HD void compute(Regs &r, const TW *__restrict__ tw, int i)
     {
         typedef typename PassOf<PL, P>::type PS;
         constexpr int R = PS::R, S = PassOf<PL, P>::S, NB = E / R, NBF = N / R;
 #pragma unroll
         for (int b = 0; b < NB; b++) {
             const int j = bfly_index<PS::kMirror, T, NBF>(i, b);
-            if constexpr (PS::kDirect) PS::template compute_direct<INV, N, S>(&r.v[b * R], tw, j);
-            else PS::template compute<INV, N, (P == NP - 1)>(&r.v[b * R], tw + PassOf<PL, P>::TWOFF, j);
+            if constexpr (PRE) {
+                if constexpr (PS::kDirect) PS::template compute_direct<INV, N, S, true>(&r.v[b * R], tw, j);
+                else PS::template compute<INV, N, (P == NP - 1), true>(&r.v[b * R], tw + PassOf<PL, P>::TWOFF, j);
+            } else {
+                if constexpr (PS::kDirect) PS::template compute_direct<INV, N, S>(&r.v[b * R], tw, j);
+                else PS::template compute<INV, N, (P == NP - 1)>(&r.v[b * R], tw + PassOf<PL, P>::TWOFF, j);
+            }
         }
     }
 

@@ -573,7 +573,8 @@ static int ku_launch(const void *in, void *out, uint64_t nFrames, int, const voi
     }
 #else
     if constexpr (PIPE::kPipe) {
-        if (flavour == KF_PIPE && aligned16(in)) {
+        /* kImageOut: the spectrum leaves with a bulk store, which needs a 16-byte aligned destination too */
+        if (flavour == KF_PIPE && aligned16(in) && aligned16(out)) {
             typedef RfftFwdBody<PIPE::type, true> BODY;
             BODY::Args a{(const cf32 *)in, (cf32 *)out, (const cf32 *)tw, (const cf32 *)aux};
             return launch_pipe<BODY, PIPE::type>(a, nFrames, st);
