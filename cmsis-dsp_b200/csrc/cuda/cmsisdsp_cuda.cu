@@ -94,23 +94,70 @@ extern "C" int cmsisdsp_cuda_set_kernel_flavour(int flavour)
     return CMSISDSP_CUDA_OK;
 }
 
-/* ------------------------------------------------------------------ plan cache */
+/* ------------------------------------------------------------------ plan cache
+ *
+ * Device-resident tables, keyed by (device, table kind, length) AND by the CONTENT of the caller's host tables: an
+ * instance is plain data that may point at any table (the reference reads whatever the struct points at), so a second
+ * instance with other values for the same length gets its own device copy instead of silently running on the first
+ * one's.  Up to kSlots distinct tables per key.  Recognising a table costs a pointer compare plus a 32-sample
+ * fingerprint; the full 64-bit hash is taken only when the pointer or the fingerprint is new.  Which slot a thread's
+ * next transform uses is thread-local (set by the upload call that precedes it), so two host threads with different
+ * tables for the same length do not disturb each other.  Device copies are never freed: they live as long as the
+ * process (a kernel of another thread may still be reading them). */
+
+static const int kSlots = 4;
+static const int kMaxDev = 64;
+
+static uint64_t fnv1a(const void *data, size_t bytes, uint64_t h = 1469598103934665603ull)
+{
+    const unsigned char *p = (const unsigned char *)data;
+    size_t i = 0;
+    for (; i + 8 <= bytes; i += 8) {
+        uint64_t w;
+        memcpy(&w, p + i, 8);
+        h = (h ^ w) * 1099511628211ull;
+    }
+    for (; i < bytes; i++) h = (h ^ p[i]) * 1099511628211ull;
+    return h;
+}
+/* 32 four-byte samples spread over the table (tables are at least 64 bytes) */
+static uint32_t fingerprint(const void *data, size_t bytes)
+{
+    const unsigned char *p = (const unsigned char *)data;
+    const size_t words = bytes / 4, step = words >= 32 ? words / 32 : 1;
+    uint32_t h = 2166136261u;
+    for (size_t i = 0; i < words; i += step) {
+        uint32_t w;
+        memcpy(&w, p + 4 * i, 4);
+        h = (h ^ w) * 16777619u;
+    }
+    return h ^ (uint32_t)bytes;
+}
 
 struct DevPlan {
     void *tw = nullptr;           /* pass-ordered twiddles of the cfft plan (Plan::build_twiddles) */
     void *tw_rfwd = nullptr;      /* f32 only: same for the rfft forward / inverse plans of complex length N */
     void *tw_rinv = nullptr;
     uint16_t *perm = nullptr;     /* destination position of X[k] when bitReverseFlag == 0 */
+    bool permIsBitrev = false;    /* ... and it is the plain binary bit reversal (every fixed-point preset) */
 };
+struct Slot {
+    bool used = false;
+    const void *host[2] = {nullptr, nullptr};   /* the caller's tables this slot was built from */
+    uint32_t extra = 0;                         /* further key material (bitRevLength, twidCoefRModifier) */
+    uint32_t fp = 0;
+    uint64_t hash = 0;
+    DevPlan plan;                               /* cfft kinds */
+    void *table = nullptr;                      /* rfft twiddles / split coefficients */
+};
+enum TableKind { TK_PLAN_F32 = 0, TK_PLAN_Q31, TK_PLAN_Q15, TK_PLAN_F64, TK_TWR_F32, TK_TWR_F64, TK_RCOEF_Q31, TK_RCOEF_Q15, TK_COUNT };
 struct DevState {
-    DevPlan plan[4][9];           /* [CMSISDSP_CUDA_F32 / Q31 / Q15 / F64][length] */
-    float *twr[9] = {};           /* rfft twiddles, indexed by len_index(real length) */
-    double *twr64[9] = {};        /* arm_rfft_fast_f64: twiddleCoefF64_rfft_N, same index */
-    void *rcoef[3][9] = {};       /* q31 / q15 real FFT: split coefficients (ci32x4 per bin), indexed by len_index(fftLenReal / 2) */
+    Slot slot[TK_COUNT][9][kSlots];
+    uint16_t *bitrev[9] = {};     /* plain binary bit reversal of 0..N-1 (cfft_f32 in bit-reversed output order) */
 };
-static const int kMaxDev = 64;
 static DevState g_dev[kMaxDev];
 static std::mutex g_mu;
+static thread_local uint8_t t_cur[kMaxDev][TK_COUNT][9];     /* slot the calling thread's transforms use */
 
 static int cur_device(int *dev)
 {
@@ -118,6 +165,38 @@ static int cur_device(int *dev)
     if (e != cudaSuccess) return fail(CMSISDSP_CUDA_ERR_NO_DEVICE, "cudaGetDevice", e);
     if (*dev < 0 || *dev >= kMaxDev) return fail(CMSISDSP_CUDA_ERR_NO_DEVICE, "device index out of range");
     return CMSISDSP_CUDA_OK;
+}
+
+/* Find the slot built from these host tables, or claim a free one.  Returns the slot index (>= 0) with *fresh = true
+ * when the caller has to build it, or a negative error.  Call with g_mu held. */
+static int find_slot(Slot *slots, const void *h0, size_t bytes0, const void *h1, size_t bytes1, uint32_t extra, bool *fresh,
+                     uint32_t *fpOut, uint64_t *hashOut)
+{
+    const uint32_t fp = fingerprint(h0, bytes0);
+    *fresh = false;
+    for (int s = 0; s < kSlots; s++)
+        if (slots[s].used && slots[s].host[0] == h0 && slots[s].host[1] == h1 && slots[s].extra == extra && slots[s].fp == fp) return s;
+    uint64_t h = fnv1a(h0, bytes0);
+    if (h1 && bytes1) h = fnv1a(h1, bytes1, h);
+    h = (h ^ extra) * 1099511628211ull;
+    for (int s = 0; s < kSlots; s++)
+        if (slots[s].used && slots[s].hash == h) {           /* same content at another address */
+            slots[s].host[0] = h0; slots[s].host[1] = h1; slots[s].extra = extra; slots[s].fp = fp;
+            return s;
+        }
+    for (int s = 0; s < kSlots; s++)
+        if (!slots[s].used) {
+            *fresh = true;
+            *fpOut = fp;
+            *hashOut = h;
+            return s;
+        }
+    return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "more than 4 distinct tables for one (device, type, length)");
+}
+static void claim(Slot &sl, const void *h0, const void *h1, uint32_t extra, uint32_t fp, uint64_t hash)
+{
+    sl.host[0] = h0; sl.host[1] = h1; sl.extra = extra; sl.fp = fp; sl.hash = hash;
+    sl.used = true;
 }
 
 /* re-order the reference-layout twiddles into the plan's pass order and upload them */
@@ -128,9 +207,30 @@ static int upload_pass_ordered(const KernelEntry *ke, const void *base, void **d
     ke->twiddles(base, host.data());
     void *d = nullptr;
     CU_TRY(cudaMalloc(&d, host.size()));
-    CU_TRY(cudaMemcpy(d, host.data(), host.size(), cudaMemcpyHostToDevice));
+    const cudaError_t e = cudaMemcpy(d, host.data(), host.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(d);
+        return fail(CMSISDSP_CUDA_ERR_RUNTIME, "cudaMemcpy (twiddles)", e);
+    }
     *dOut = d;
     return CMSISDSP_CUDA_OK;
+}
+static int upload_raw(const void *host, size_t bytes, void **dOut)
+{
+    void *d = nullptr;
+    CU_TRY(cudaMalloc(&d, bytes));
+    const cudaError_t e = cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(d);
+        return fail(CMSISDSP_CUDA_ERR_RUNTIME, "cudaMemcpy (table)", e);
+    }
+    *dOut = d;
+    return CMSISDSP_CUDA_OK;
+}
+static void free_plan(DevPlan &p)
+{
+    cudaFree(p.tw); cudaFree(p.tw_rfwd); cudaFree(p.tw_rinv); cudaFree(p.perm);
+    p = DevPlan();
 }
 
 /* kernel op of the complex FFT of a data type */
@@ -144,6 +244,22 @@ static int build_tables(int type, int li, const void *base, DevPlan &p)
     if (!rc) rc = upload_pass_ordered(kEntries[OP_RFFT_INV][li], base, &p.tw_rinv);
     return rc;
 }
+static uint32_t bitrev_of(uint32_t k, uint32_t n)
+{
+    uint32_t r = 0;
+    for (uint32_t m = n >> 1; m; m >>= 1, k >>= 1) r = (r << 1) | (k & 1u);
+    return r;
+}
+/* bytes of the reference-layout twiddle table of (type, fftLen) */
+static size_t twiddle_bytes(int type, uint32_t n)
+{
+    switch (type) {
+    case CMSISDSP_CUDA_F32: return (size_t)2 * n * sizeof(float);
+    case CMSISDSP_CUDA_F64: return (size_t)2 * n * sizeof(double);
+    case CMSISDSP_CUDA_Q31: return (size_t)(3 * n / 2) * sizeof(int32_t);
+    default: return (size_t)(3 * n / 2) * sizeof(int16_t);
+    }
+}
 
 extern "C" int cmsisdsp_cuda_plan_upload(int type, uint32_t fftLen, const void *pTwiddle,
                                          const uint16_t *pBitRevTable, uint16_t bitRevLength)
@@ -155,8 +271,15 @@ extern "C" int cmsisdsp_cuda_plan_upload(int type, uint32_t fftLen, const void *
     int rc = cur_device(&dev);
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(g_mu);
-    DevPlan &p = g_dev[dev].plan[type][li];
-    if (p.tw) return CMSISDSP_CUDA_OK;
+    Slot *slots = g_dev[dev].slot[TK_PLAN_F32 + type][li];
+    bool fresh;
+    uint32_t fp = 0;
+    uint64_t hash = 0;
+    const int s = find_slot(slots, pTwiddle, twiddle_bytes(type, fftLen), pBitRevTable, (size_t)bitRevLength * sizeof(uint16_t),
+                            bitRevLength, &fresh, &fp, &hash);
+    if (s < 0) return s;
+    t_cur[dev][TK_PLAN_F32 + type][li] = (uint8_t)s;
+    if (!fresh) return CMSISDSP_CUDA_OK;
 
     /* out[k] = scrambled[P[k]] after the swap list  =>  X[k] lives at scrambled position P[k] */
     std::vector<uint16_t> perm(fftLen);
@@ -166,48 +289,68 @@ extern "C" int cmsisdsp_cuda_plan_upload(int type, uint32_t fftLen, const void *
         if (a >= fftLen || b >= fftLen) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "plan_upload: bit-reversal entry out of range");
         const uint16_t t = perm[a]; perm[a] = perm[b]; perm[b] = t;
     }
-    uint16_t *dperm = nullptr;
-    CU_TRY(cudaMalloc((void **)&dperm, fftLen * sizeof(uint16_t)));
-    CU_TRY(cudaMemcpy(dperm, perm.data(), fftLen * sizeof(uint16_t), cudaMemcpyHostToDevice));
     DevPlan np;
-    np.perm = dperm;
-    rc = build_tables(type, li, pTwiddle, np);
-    if (rc) return rc;
-    p = np;
+    np.permIsBitrev = true;
+    for (uint32_t k = 0; k < fftLen; k++) np.permIsBitrev = np.permIsBitrev && perm[k] == bitrev_of(k, fftLen);
+    rc = upload_raw(perm.data(), fftLen * sizeof(uint16_t), (void **)&np.perm);
+    if (!rc) rc = build_tables(type, li, pTwiddle, np);
+    if (rc) {
+        free_plan(np);
+        return rc;
+    }
+    slots[s].plan = np;
+    claim(slots[s], pTwiddle, pBitRevTable, bitRevLength, fp, hash);
     return CMSISDSP_CUDA_OK;
+}
+
+/* a raw table (rfft twiddles): upload once per content, select for the calling thread */
+static int table_upload(int kind, int li, const void *host, size_t bytes)
+{
+    int dev;
+    int rc = cur_device(&dev);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(g_mu);
+    Slot *slots = g_dev[dev].slot[kind][li];
+    bool fresh;
+    uint32_t fp = 0;
+    uint64_t hash = 0;
+    const int s = find_slot(slots, host, bytes, nullptr, 0, 0, &fresh, &fp, &hash);
+    if (s < 0) return s;
+    t_cur[dev][kind][li] = (uint8_t)s;
+    if (!fresh) return CMSISDSP_CUDA_OK;
+    rc = upload_raw(host, bytes, &slots[s].table);
+    if (rc) return rc;
+    claim(slots[s], host, nullptr, 0, fp, hash);
+    return CMSISDSP_CUDA_OK;
+}
+/* the calling thread's current slot of (kind, li) on the current device; null when nothing was uploaded */
+static const Slot *cur_slot(int kind, int li)
+{
+    int dev;
+    if (cur_device(&dev)) return nullptr;
+    std::lock_guard<std::mutex> lk(g_mu);
+    const Slot *sl = &g_dev[dev].slot[kind][li][t_cur[dev][kind][li]];
+    return sl->used ? sl : nullptr;
 }
 
 extern "C" int cmsisdsp_cuda_rfft_plan_upload(uint32_t fftLenReal, const float *pTwiddleRFFT)
 {
     const int li = len_index(fftLenReal);
     if (li < 1 || !pTwiddleRFFT) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "rfft_plan_upload: bad length / pointer");
-    int dev;
-    int rc = cur_device(&dev);
-    if (rc) return rc;
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (g_dev[dev].twr[li]) return CMSISDSP_CUDA_OK;
-    float *d = nullptr;
-    CU_TRY(cudaMalloc((void **)&d, fftLenReal * sizeof(float)));
-    CU_TRY(cudaMemcpy(d, pTwiddleRFFT, fftLenReal * sizeof(float), cudaMemcpyHostToDevice));
-    g_dev[dev].twr[li] = d;
-    return CMSISDSP_CUDA_OK;
+    return table_upload(TK_TWR_F32, li, pTwiddleRFFT, fftLenReal * sizeof(float));
 }
 
 extern "C" int cmsisdsp_cuda_plan_ready(int type, uint32_t fftLen)
 {
     const int li = len_index(fftLen);
-    int dev;
-    if (type < 0 || type > CMSISDSP_CUDA_F64 || li < 0 || cur_device(&dev)) return 0;
-    std::lock_guard<std::mutex> lk(g_mu);
-    return g_dev[dev].plan[type][li].tw != nullptr;
+    if (type < 0 || type > CMSISDSP_CUDA_F64 || li < 0) return 0;
+    return cur_slot(TK_PLAN_F32 + type, li) != nullptr;
 }
 extern "C" int cmsisdsp_cuda_rfft_plan_ready(uint32_t fftLenReal)
 {
     const int li = len_index(fftLenReal);
-    int dev;
-    if (li < 1 || cur_device(&dev)) return 0;
-    std::lock_guard<std::mutex> lk(g_mu);
-    return g_dev[dev].twr[li] != nullptr && g_dev[dev].plan[0][li - 1].tw != nullptr;
+    if (li < 1) return 0;
+    return cur_slot(TK_TWR_F32, li) != nullptr && cur_slot(TK_PLAN_F32, li - 1) != nullptr;
 }
 
 extern "C" int cmsisdsp_cuda_rfft_fix_plan_upload(int type, uint32_t fftLenReal, const void *pTwiddleAReal,
@@ -220,10 +363,21 @@ extern "C" int cmsisdsp_cuda_rfft_fix_plan_upload(int type, uint32_t fftLenReal,
     int dev;
     int rc = cur_device(&dev);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (g_dev[dev].rcoef[type][li]) return CMSISDSP_CUDA_OK;
-    /* bin k reads entries 2*k*modifier and 2*k*modifier + 1 of both tables (arm_rfft_q31.c:272-273,333-334) */
+    const int kind = type == CMSISDSP_CUDA_Q31 ? TK_RCOEF_Q31 : TK_RCOEF_Q15;
+    const size_t scalar = type == CMSISDSP_CUDA_Q31 ? 4 : 2;
+    /* bin k reads entries 2*k*modifier and 2*k*modifier + 1 of both tables (arm_rfft_q31.c:272-273,333-334):
+     * the tables are hashed over the span that is read */
     const uint32_t L2 = fftLenReal / 2;
+    const size_t span = ((size_t)2 * (L2 - 1) * twidCoefRModifier + 2) * scalar;
+    std::lock_guard<std::mutex> lk(g_mu);
+    Slot *slots = g_dev[dev].slot[kind][li];
+    bool fresh;
+    uint32_t fp = 0;
+    uint64_t hash = 0;
+    const int s = find_slot(slots, pTwiddleAReal, span, pTwiddleBReal, span, twidCoefRModifier, &fresh, &fp, &hash);
+    if (s < 0) return s;
+    t_cur[dev][kind][li] = (uint8_t)s;
+    if (!fresh) return CMSISDSP_CUDA_OK;
     std::vector<int32_t> coef((size_t)L2 * 4);
     for (uint32_t k = 0; k < L2; k++) {
         const size_t e = (size_t)2 * k * twidCoefRModifier;
@@ -235,19 +389,16 @@ extern "C" int cmsisdsp_cuda_rfft_fix_plan_upload(int type, uint32_t fftLenReal,
             coef[4 * k] = A[e]; coef[4 * k + 1] = A[e + 1]; coef[4 * k + 2] = B[e]; coef[4 * k + 3] = B[e + 1];
         }
     }
-    void *d = nullptr;
-    CU_TRY(cudaMalloc(&d, coef.size() * sizeof(int32_t)));
-    CU_TRY(cudaMemcpy(d, coef.data(), coef.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-    g_dev[dev].rcoef[type][li] = d;
+    rc = upload_raw(coef.data(), coef.size() * sizeof(int32_t), &slots[s].table);
+    if (rc) return rc;
+    claim(slots[s], pTwiddleAReal, pTwiddleBReal, twidCoefRModifier, fp, hash);
     return CMSISDSP_CUDA_OK;
 }
 extern "C" int cmsisdsp_cuda_rfft_fix_plan_ready(int type, uint32_t fftLenReal)
 {
     const int li = len_index(fftLenReal / 2);
-    int dev;
-    if ((type != CMSISDSP_CUDA_Q31 && type != CMSISDSP_CUDA_Q15) || li < 0 || cur_device(&dev)) return 0;
-    std::lock_guard<std::mutex> lk(g_mu);
-    return g_dev[dev].rcoef[type][li] != nullptr && g_dev[dev].plan[type][li].tw != nullptr;
+    if ((type != CMSISDSP_CUDA_Q31 && type != CMSISDSP_CUDA_Q15) || li < 0) return 0;
+    return cur_slot(type == CMSISDSP_CUDA_Q31 ? TK_RCOEF_Q31 : TK_RCOEF_Q15, li) != nullptr && cur_slot(TK_PLAN_F32 + type, li) != nullptr;
 }
 
 static int get_plan(int type, uint32_t fftLen, DevPlan *out)
@@ -257,9 +408,16 @@ static int get_plan(int type, uint32_t fftLen, DevPlan *out)
     int dev;
     int rc = cur_device(&dev);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(g_mu);
-    *out = g_dev[dev].plan[type][li];
-    if (!out->tw) return fail(CMSISDSP_CUDA_ERR_NO_PLAN, "no plan uploaded for this (device, type, fftLen)");
+    const Slot *sl = cur_slot(TK_PLAN_F32 + type, li);
+    if (!sl) return fail(CMSISDSP_CUDA_ERR_NO_PLAN, "no plan uploaded for this (device, type, fftLen)");
+    *out = sl->plan;
+    return CMSISDSP_CUDA_OK;
+}
+static int get_table(int kind, int li, const void **out, const char *what)
+{
+    const Slot *sl = cur_slot(kind, li);
+    if (!sl) return fail(CMSISDSP_CUDA_ERR_NO_PLAN, what);
+    *out = sl->table;
     return CMSISDSP_CUDA_OK;
 }
 
@@ -271,13 +429,11 @@ int shim_rfft_tables(uint32_t fftLenReal, const void **twForward, const float **
     DevPlan pl;
     int rc = get_plan(CMSISDSP_CUDA_F32, fftLenReal / 2, &pl);
     if (rc) return rc;
-    int dev;
-    rc = cur_device(&dev);
+    const void *twr = nullptr;
+    rc = get_table(TK_TWR_F32, li, &twr, "no rfft plan uploaded for this (device, fftLen)");
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (!g_dev[dev].twr[li]) return fail(CMSISDSP_CUDA_ERR_NO_PLAN, "no rfft plan uploaded for this (device, fftLen)");
     *twForward = pl.tw_rfwd;
-    *twRfft = g_dev[dev].twr[li];
+    *twRfft = (const float *)twr;
     return CMSISDSP_CUDA_OK;
 }
 }
@@ -291,14 +447,31 @@ int shim_rfft_tables(uint32_t fftLenReal, const void **twForward, const float **
 static int elem_align(int type) { return type == CMSISDSP_CUDA_F64 ? 16 : (type == CMSISDSP_CUDA_Q15 ? 4 : 8); }
 static bool misaligned(const void *p, int a) { return ((uintptr_t)p & (uintptr_t)(a - 1)) != 0; }
 
-static int cfft_io(int type, const void *d_in, void *d_p, uint32_t fftLen, uint64_t nFrames, uint8_t ifftFlag, uint8_t bitReverseFlag, void *stream);
-static int cfft_any(int type, void *d_p, uint32_t fftLen, uint64_t nFrames, uint8_t ifftFlag, uint8_t bitReverseFlag, void *stream)
+enum OutputOrder { ORDER_NATURAL = 0, ORDER_INSTANCE = 1, ORDER_BITREV = 2 };
+/* plain binary bit reversal of 0..N-1 on the current device (built on first use) */
+static int bitrev_table(int li, const uint16_t **out)
 {
-    return cfft_io(type, d_p, d_p, fftLen, nFrames, ifftFlag, bitReverseFlag, stream);
+    int dev;
+    int rc = cur_device(&dev);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_dev[dev].bitrev[li]) {
+        const uint32_t n = kLens[li];
+        std::vector<uint16_t> t(n);
+        for (uint32_t k = 0; k < n; k++) t[k] = (uint16_t)bitrev_of(k, n);
+        rc = upload_raw(t.data(), n * sizeof(uint16_t), (void **)&g_dev[dev].bitrev[li]);
+        if (rc) return rc;
+    }
+    *out = g_dev[dev].bitrev[li];
+    return CMSISDSP_CUDA_OK;
 }
+
 /* d_in == d_p: in place; otherwise frames are read from d_in and written to d_p (the direct kernels never read a
- * frame after they started to write it, so the two may also be distinct buffers) */
-static int cfft_io(int type, const void *d_in, void *d_p, uint32_t fftLen, uint64_t nFrames, uint8_t ifftFlag, uint8_t bitReverseFlag, void *stream)
+ * frame after they started to write it, so the two may also be distinct buffers).
+ * order: ORDER_NATURAL (bitReverseFlag = 1), ORDER_INSTANCE (bitReverseFlag = 0: the order the instance's own swap list
+ * leaves behind), ORDER_BITREV (plain binary bit-reversed order: the deprecated radix-4 / radix-2 f32 functions with
+ * bitReverseFlag = 0, arm_cfft_radix4_f32.c:81, arm_cfft_radix2_f32.c) */
+static int cfft_io(int type, const void *d_in, void *d_p, uint32_t fftLen, uint64_t nFrames, uint8_t ifftFlag, int order, void *stream)
 {
     if ((!d_p || !d_in) && nFrames) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "null data pointer");
     DevPlan pl;
@@ -309,9 +482,15 @@ static int cfft_io(int type, const void *d_in, void *d_p, uint32_t fftLen, uint6
     const int shl1 = (type == CMSISDSP_CUDA_Q31 || type == CMSISDSP_CUDA_Q15) ? ((li + 4) & 1) : 0;
     if (misaligned(d_p, elem_align(type)) || misaligned(d_in, elem_align(type)))
         return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "cfft: device data must be aligned to one complex element (8 bytes f32/q31, 4 q15, 16 f64)");
+    const uint16_t *perm = nullptr;
+    if (order == ORDER_INSTANCE) perm = pl.perm;
+    else if (order == ORDER_BITREV && (rc = bitrev_table(li, &perm))) return rc;
     const KernelEntry *ke = kEntries[cfft_op(type)][li];
-    return ke->launch(d_in, d_p, nFrames, ifftFlag == 1, pl.tw, bitReverseFlag ? nullptr : pl.perm, shl1, choose_flavour(ke),
-                      (cudaStream_t)stream);
+    return ke->launch(d_in, d_p, nFrames, ifftFlag == 1, pl.tw, perm, nullptr, shl1, choose_flavour(ke), (cudaStream_t)stream);
+}
+static int cfft_any(int type, void *d_p, uint32_t fftLen, uint64_t nFrames, uint8_t ifftFlag, uint8_t bitReverseFlag, void *stream)
+{
+    return cfft_io(type, d_p, d_p, fftLen, nFrames, ifftFlag, bitReverseFlag ? ORDER_NATURAL : ORDER_INSTANCE, stream);
 }
 
 extern "C" int cmsisdsp_cuda_cfft_f32(void *d_p, uint32_t fftLen, uint64_t nFrames, uint8_t ifftFlag, uint8_t bitReverseFlag, void *stream)
@@ -320,9 +499,10 @@ extern "C" int cmsisdsp_cuda_cfft_q31(void *d_p, uint32_t fftLen, uint64_t nFram
 { return cfft_any(CMSISDSP_CUDA_Q31, d_p, fftLen, nFrames, ifftFlag, bitReverseFlag, stream); }
 extern "C" int cmsisdsp_cuda_cfft_q15(void *d_p, uint32_t fftLen, uint64_t nFrames, uint8_t ifftFlag, uint8_t bitReverseFlag, void *stream)
 { return cfft_any(CMSISDSP_CUDA_Q15, d_p, fftLen, nFrames, ifftFlag, bitReverseFlag, stream); }
-
 extern "C" int cmsisdsp_cuda_cfft_f64(void *d_p, uint32_t fftLen, uint64_t nFrames, uint8_t ifftFlag, uint8_t bitReverseFlag, void *stream)
 { return cfft_any(CMSISDSP_CUDA_F64, d_p, fftLen, nFrames, ifftFlag, bitReverseFlag, stream); }
+extern "C" int cmsisdsp_cuda_cfft_f32_bitrev_order(void *d_p, uint32_t fftLen, uint64_t nFrames, uint8_t ifftFlag, void *stream)
+{ return cfft_io(CMSISDSP_CUDA_F32, d_p, d_p, fftLen, nFrames, ifftFlag, ORDER_BITREV, stream); }
 
 extern "C" int cmsisdsp_cuda_rfft_fast_f32(const void *d_p, void *d_out, uint32_t fftLenReal, uint64_t nFrames, uint8_t ifftFlag, void *stream)
 {
@@ -334,17 +514,11 @@ extern "C" int cmsisdsp_cuda_rfft_fast_f32(const void *d_p, void *d_out, uint32_
     DevPlan pl;
     int rc = get_plan(CMSISDSP_CUDA_F32, fftLenReal / 2, &pl);
     if (rc) return rc;
-    int dev;
-    rc = cur_device(&dev);
+    const void *twr = nullptr;
+    rc = get_table(TK_TWR_F32, li, &twr, "no rfft plan uploaded for this (device, fftLen)");
     if (rc) return rc;
-    const float *twr;
-    {
-        std::lock_guard<std::mutex> lk(g_mu);
-        twr = g_dev[dev].twr[li];
-    }
-    if (!twr) return fail(CMSISDSP_CUDA_ERR_NO_PLAN, "no rfft plan uploaded for this (device, fftLen)");
     const KernelEntry *ke = kEntries[ifftFlag ? OP_RFFT_INV : OP_RFFT_FWD][li - 1];
-    return ke->launch(d_p, d_out, nFrames, ifftFlag != 0, ifftFlag ? pl.tw_rinv : pl.tw_rfwd, twr, 0, choose_flavour(ke),
+    return ke->launch(d_p, d_out, nFrames, ifftFlag != 0, ifftFlag ? pl.tw_rinv : pl.tw_rfwd, twr, nullptr, 0, choose_flavour(ke),
                       (cudaStream_t)stream);
 }
 
@@ -358,24 +532,13 @@ extern "C" int cmsisdsp_cuda_rfft_f64_plan_upload(uint32_t fftLenReal, const dou
 {
     const int li = len_index(fftLenReal);
     if (li < 1 || !pTwiddleRFFT) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "rfft_f64_plan_upload: bad length / pointer");
-    int dev;
-    int rc = cur_device(&dev);
-    if (rc) return rc;
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (g_dev[dev].twr64[li]) return CMSISDSP_CUDA_OK;
-    double *d = nullptr;
-    CU_TRY(cudaMalloc((void **)&d, fftLenReal * sizeof(double)));
-    CU_TRY(cudaMemcpy(d, pTwiddleRFFT, fftLenReal * sizeof(double), cudaMemcpyHostToDevice));
-    g_dev[dev].twr64[li] = d;
-    return CMSISDSP_CUDA_OK;
+    return table_upload(TK_TWR_F64, li, pTwiddleRFFT, fftLenReal * sizeof(double));
 }
 extern "C" int cmsisdsp_cuda_rfft_f64_plan_ready(uint32_t fftLenReal)
 {
     const int li = len_index(fftLenReal);
-    int dev;
-    if (li < 1 || cur_device(&dev)) return 0;
-    std::lock_guard<std::mutex> lk(g_mu);
-    return g_dev[dev].twr64[li] != nullptr && g_dev[dev].plan[CMSISDSP_CUDA_F64][li - 1].tw != nullptr;
+    if (li < 1) return 0;
+    return cur_slot(TK_TWR_F64, li) != nullptr && cur_slot(TK_PLAN_F64, li - 1) != nullptr;
 }
 
 extern "C" int cmsisdsp_cuda_rfft_fast_f64(const void *d_p, void *d_out, uint32_t fftLenReal, uint64_t nFrames, uint8_t ifftFlag, void *stream)
@@ -385,20 +548,14 @@ extern "C" int cmsisdsp_cuda_rfft_fast_f64(const void *d_p, void *d_out, uint32_
     if (((uintptr_t)d_p | (uintptr_t)d_out) & 15u) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "rfft_fast_f64: data must be 16-byte aligned");
     const int li = len_index(fftLenReal);
     if (li < 1) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "unsupported rfft length (32..4096, power of two)");
-    int dev;
-    int rc = cur_device(&dev);
+    const void *twr = nullptr;
+    int rc = get_table(TK_TWR_F64, li, &twr, "no f64 rfft plan uploaded for this (device, fftLen)");
     if (rc) return rc;
-    const double *twr;
-    {
-        std::lock_guard<std::mutex> lk(g_mu);
-        twr = g_dev[dev].twr64[li];
-    }
-    if (!twr) return fail(CMSISDSP_CUDA_ERR_NO_PLAN, "no f64 rfft plan uploaded for this (device, fftLen)");
     DevPlan pl;
     rc = get_plan(CMSISDSP_CUDA_F64, fftLenReal / 2, &pl);
     if (rc) return rc;
     const KernelEntry *ke = kEntries[ifftFlag ? OP_RFFT_F64_INV : OP_RFFT_F64_FWD][li - 1];
-    return ke->launch(d_p, d_out, nFrames, ifftFlag != 0, pl.tw, twr, 0, KF_DIRECT, (cudaStream_t)stream);
+    return ke->launch(d_p, d_out, nFrames, ifftFlag != 0, pl.tw, twr, nullptr, 0, KF_DIRECT, (cudaStream_t)stream);
 }
 
 /* arm_cfft_f32 + spectrum epilogue: mode 0 magnitudes, 1 squared magnitudes (d_out: fftLen floats per frame),
@@ -413,7 +570,7 @@ static int cfft_spectrum(const void *d_src, void *d_out, void *d_aux, uint32_t f
     int rc = get_plan(CMSISDSP_CUDA_F32, fftLen, &pl);
     if (rc) return rc;
     const KernelEntry *ke = kEntries[OP_CFFT_MAG_F32][len_index(fftLen)];
-    return ke->launch(d_src, d_out, nFrames, ifftFlag == 1, pl.tw, d_aux, mode, choose_flavour(ke), (cudaStream_t)stream);
+    return ke->launch(d_src, d_out, nFrames, ifftFlag == 1, pl.tw, d_aux, nullptr, mode, choose_flavour(ke), (cudaStream_t)stream);
 }
 extern "C" int cmsisdsp_cuda_cfft_mag_f32(const void *d_src, void *d_mag, uint32_t fftLen, uint64_t nFrames, uint8_t ifftFlag,
                                           uint8_t squared, void *stream)
@@ -422,7 +579,12 @@ extern "C" int cmsisdsp_cuda_cfft_peak_f32(const void *d_src, void *d_val, void 
                                            uint8_t ifftFlag, void *stream)
 { return cfft_spectrum(d_src, d_val, d_idx, fftLen, nFrames, ifftFlag, 2, stream); }
 
-static int rfft_fix(int type, const void *d_src, void *d_dst, uint32_t fftLenReal, uint64_t nFrames, uint8_t ifftFlagR, void *stream)
+/* bitReverseFlagR = 0 (arm_rfft_q31.c:164,173 hand the flag to arm_cfft_q31): the complex transform inside leaves its
+ * result in the instance's unordered layout -- forward, the split stage then runs over that layout as if it were
+ * natural order; inverse, the result stays unordered.  Supported for instances whose unordered layout is the plain
+ * binary bit reversal (every preset). */
+static int rfft_fix(int type, const void *d_src, void *d_dst, uint32_t fftLenReal, uint64_t nFrames, uint8_t ifftFlagR,
+                    uint8_t bitReverseFlagR, void *stream)
 {
     if ((!d_src || !d_dst) && nFrames) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "null data pointer");
     if (d_src == d_dst && nFrames) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "rfft: pSrc and pDst must not alias");
@@ -433,23 +595,23 @@ static int rfft_fix(int type, const void *d_src, void *d_dst, uint32_t fftLenRea
     DevPlan pl;
     int rc = get_plan(type, fftLenReal / 2, &pl);
     if (rc) return rc;
-    int dev;
-    rc = cur_device(&dev);
+    const void *coef = nullptr;
+    rc = get_table(type == CMSISDSP_CUDA_Q31 ? TK_RCOEF_Q31 : TK_RCOEF_Q15, li, &coef,
+                   "no fixed-point rfft plan uploaded for this (device, type, fftLenReal)");
     if (rc) return rc;
-    const void *coef;
-    {
-        std::lock_guard<std::mutex> lk(g_mu);
-        coef = g_dev[dev].rcoef[type][li];
-    }
-    if (!coef) return fail(CMSISDSP_CUDA_ERR_NO_PLAN, "no fixed-point rfft plan uploaded for this (device, type, fftLenReal)");
+    if (!bitReverseFlagR && !pl.permIsBitrev)
+        return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "rfft with bitReverseFlagR = 0 needs the standard (binary) bit-reversal table");
     const int op = (type == CMSISDSP_CUDA_Q31 ? OP_RFFT_Q31_FWD : OP_RFFT_Q15_FWD) + (ifftFlagR ? 1 : 0);
     const KernelEntry *ke = kEntries[op][li];
-    return ke->launch(d_src, d_dst, nFrames, ifftFlagR != 0, pl.tw, coef, (li + 4) & 1, choose_flavour(ke), (cudaStream_t)stream);
+    return ke->launch(d_src, d_dst, nFrames, ifftFlagR != 0, pl.tw, coef, bitReverseFlagR ? nullptr : pl.perm, (li + 4) & 1,
+                      choose_flavour(ke), (cudaStream_t)stream);
 }
-extern "C" int cmsisdsp_cuda_rfft_q31(const void *d_src, void *d_dst, uint32_t fftLenReal, uint64_t nFrames, uint8_t ifftFlagR, void *stream)
-{ return rfft_fix(CMSISDSP_CUDA_Q31, d_src, d_dst, fftLenReal, nFrames, ifftFlagR, stream); }
-extern "C" int cmsisdsp_cuda_rfft_q15(const void *d_src, void *d_dst, uint32_t fftLenReal, uint64_t nFrames, uint8_t ifftFlagR, void *stream)
-{ return rfft_fix(CMSISDSP_CUDA_Q15, d_src, d_dst, fftLenReal, nFrames, ifftFlagR, stream); }
+extern "C" int cmsisdsp_cuda_rfft_q31(const void *d_src, void *d_dst, uint32_t fftLenReal, uint64_t nFrames, uint8_t ifftFlagR,
+                                      uint8_t bitReverseFlagR, void *stream)
+{ return rfft_fix(CMSISDSP_CUDA_Q31, d_src, d_dst, fftLenReal, nFrames, ifftFlagR, bitReverseFlagR, stream); }
+extern "C" int cmsisdsp_cuda_rfft_q15(const void *d_src, void *d_dst, uint32_t fftLenReal, uint64_t nFrames, uint8_t ifftFlagR,
+                                      uint8_t bitReverseFlagR, void *stream)
+{ return rfft_fix(CMSISDSP_CUDA_Q15, d_src, d_dst, fftLenReal, nFrames, ifftFlagR, bitReverseFlagR, stream); }
 
 extern "C" int cmsisdsp_cuda_kernel_info(int op, uint32_t fftLen, int *threads, int *frames, int *smem, int *regs, int *ctasPerSm)
 {
@@ -498,6 +660,14 @@ extern "C" int cmsisdsp_cuda_stream_create(void **stream)
 extern "C" int cmsisdsp_cuda_stream_destroy(void *stream) { CU_TRY(cudaStreamDestroy((cudaStream_t)stream)); return 0; }
 extern "C" int cmsisdsp_cuda_stream_synchronize(void *stream) { CU_TRY(cudaStreamSynchronize((cudaStream_t)stream)); return 0; }
 
+/* device ordinal that owns ptr (device or managed memory), -1 for host memory, < -1 on error */
+extern "C" int cmsisdsp_cuda_pointer_device(const void *ptr)
+{
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, ptr);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); fail(CMSISDSP_CUDA_ERR_RUNTIME, "cudaPointerGetAttributes", e); return -2; }
+    return (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) ? at.device : -1;
+}
 extern "C" int cmsisdsp_cuda_is_device_pointer(const void *ptr)
 {
     cudaPointerAttributes at;

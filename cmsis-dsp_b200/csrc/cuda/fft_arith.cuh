@@ -214,6 +214,7 @@ template <int R, bool TW> FFT_HD void dft_f32(cf32 *x, const cf32 *tw)
 /* An Arith names four representations of a complex point: elem (HBM), work (registers),
  * xelem (shared-memory exchange) and telem (device twiddle table). */
 struct ArithF32 {
+    static constexpr bool kBiased = false;       /* see ArithQ15::bfly4 */
     static constexpr bool kPreShift = false;     /* see ArithQ15::load_shifted */
     static constexpr bool kDirectTw = false;
     static constexpr int kTableNum = 1, kTableDen = 1;
@@ -290,6 +291,7 @@ template <bool INV> FFT_HD ci32 rot_q31(int32_t R, int32_t S, ci32 w)
 #define FFT_FIX_DIRECT_TW_VALUE false
 #endif
 struct ArithQ31 {
+    static constexpr bool kBiased = false;       /* see ArithQ15::bfly4 */
     static constexpr bool kPreShift = false;     /* see ArithQ15::load_shifted */
     static constexpr bool kDirectTw = FFT_FIX_DIRECT_TW_VALUE;     /* fft_frame.cuh: PassFix::kDirect */
     static constexpr int kTableNum = 3, kTableDen = 4;        /* reference table: 3N/4 entries */
@@ -309,7 +311,7 @@ struct ArithQ31 {
     /* radix-4 DIF stage butterfly; outputs in residue order (a', b'[W^1], c'[W^2], d'[W^3]).
      * w1/w2/w3 = table entries (cos,+sin) of W^1, W^2, W^3 for this butterfly. */
     template <int KIND, bool INV, bool TAIL = false, bool PRE = false>
-    static FFT_HD void bfly4(work &A, work &B, work &C, work &D, twid w1, twid w2, twid w3)
+    static FFT_HD void bfly4(work &A, work &B, work &C, work &D, twid w1, twid w2, twid w3, int32_t = 0)
     {
         work a = A, b = B, c = C, e = D;
         if (KIND == ST_FIRST4) {
@@ -454,44 +456,47 @@ FFT_HD int32_t opaque32(int32_t v)
 #endif
 }
 /* sat16(a + b) >> 1 and sat16(a - b) >> 1, the head of every middle / last stage butterfly (arm_cfft_radix4_q15.c:
- * 803-846).  The difference is taken NEGATED, clamp(b - a, -32767, 32768) = -sat16(a - b) (the operand negation is free
- * in VIADDMNMX, for one operand only), because floor(s / 2) = upper word of (-s) * -2^31: the halving of the four
- * differences of a butterfly moves to the FMA pipe as an IMAD.WIDE (2^31 itself does not fit the signed factor). */
-FFT_HD int32_t half_sat_add16(int32_t a, int32_t b) { return sat_add16(a, b) >> 1; }
-#ifndef FFT_Q15_DIFF_HALVE_FMA
-#define FFT_Q15_DIFF_HALVE_FMA 1
-#endif
-FFT_HD int32_t half_sat_sub16(int32_t a, int32_t b)
+ * 803-846), in TWO instructions each instead of three (add-and-min, max, shift).  Between stages the first operand of
+ * each pair (points a and b of a butterfly; c and d are the second operands) is carried with a bias of +32768:
+ *     relu(min(a' + c, 65535)) = sat16(a + c) + 32768   and   relu(min(a' - c, 65535)) = sat16(a - c) + 32768
+ * are single VIADDMNMX.RELU instructions (clamp to [0, 65535] = both saturation bounds at once), and
+ *     ((s + 32768) >> 1) - 16384 = s >> 1        (32768 is even: exact)
+ * is one shift-and-add (LEA.HI.SX32).  The producer of a point adds the bias for free: its last instruction is a shift
+ * followed by nothing ((acc >> 16) becomes (acc >> 16) + bias, again one LEA.HI.SX32).  Which points are a / b of
+ * their next butterfly is a compile-time fact inside a pass and a per-thread constant across an exchange
+ * (PassFix::compute, Engine::compute). */
+FFT_HD int32_t relu_add_min16(int32_t a, int32_t b)          /* clamp(a + b, 0, 65535) */
 {
-    if (FFT_Q15_DIFF_HALVE_FMA) {
 #if defined(__CUDA_ARCH__)
-        const int32_t n = max(__viaddmin_s32(b, -a, 32768), -32767);
+    return __viaddmin_s32_relu(a, b, 65535);
 #else
-        const int32_t n = (b - a) > 32768 ? 32768 : ((b - a) < -32767 ? -32767 : (b - a));
+    const int32_t v = a + b;
+    return v > 65535 ? 65535 : (v < 0 ? 0 : v);
 #endif
-        return hi32_fma(n, g_shr_mul[2]);
-    }
-    return sat_sub16(a, b) >> 1;
 }
+/* ab = a + 32768 (biased), c plain */
+FFT_HD int32_t half_sat_add16(int32_t ab, int32_t c) { return (relu_add_min16(ab, c) >> 1) - 16384; }
+FFT_HD int32_t half_sat_sub16(int32_t ab, int32_t c) { return (relu_add_min16(ab, -c) >> 1) - 16384; }
 FFT_HD int32_t q15w(int32_t v) { return (int32_t)(int16_t)(uint16_t)(uint32_t)v; }   /* wrap to int16, keep in a register */
 
 /* Measured and rejected: twiddles pre-shifted by 16 and the sum taken as the upper word of two wide
  * products (no shift on the ALU pipe, which bounds this kernel).  ptxas ends such a pair with IMAD.HI, an
  * XU-pipe instruction on sm_100, and the kernels lost 5-10 % (profiles/r1_e_notes.md). */
-/* ALUSHIFT: plain shifts (results that go to memory next: an IMAD.WIDE leaves its upper word in the odd register of
- * a pair, and a 64-bit shared-memory store wants (x, y) in an aligned pair -- the moves cost more than the shift) */
-template <bool INV, bool ALUSHIFT> FFT_HD ci32 rot_q15(int32_t x, int32_t y, ci32 w)
+/* (r, s) * conj(W) >> 16 (forward) / (r, s) * W >> 16 (inverse), + ob: the bias the result carries into its next
+ * butterfly (0 or 32768; shift and add are one instruction).  ALUSHIFT is kept for A/B runs: the other spelling
+ * takes the shift as the upper word of a product by 2^16 on the FMA pipe (IMAD.WIDE), which measured SLOWER --
+ * IMAD.WIDE issues at half the rate of IMAD (tools/probes/probe_dpx.cu, profiles/r2_notes.md). */
+template <bool INV, bool ALUSHIFT> FFT_HD ci32 rot_q15(int32_t x, int32_t y, ci32 w, int32_t ob)
 {
     if (ALUSHIFT) {
-        if (!INV) return {(w.x * x + w.y * y) >> 16, (w.x * y - w.y * x) >> 16};
-        return {(w.x * x - w.y * y) >> 16, (w.y * x + w.x * y) >> 16};
+        if (!INV) return {((w.x * x + w.y * y) >> 16) + ob, ((w.x * y - w.y * x) >> 16) + ob};
+        return {((w.x * x - w.y * y) >> 16) + ob, ((w.y * x + w.x * y) >> 16) + ob};
     }
-    if (!INV) return {shr16_fma(w.x * x + w.y * y), shr16_fma(w.x * y - w.y * x)};
-    return {shr16_fma(w.x * x - w.y * y), shr16_fma(w.y * x + w.x * y)};
+    if (!INV) return {shr16_fma(w.x * x + w.y * y) + ob, shr16_fma(w.x * y - w.y * x) + ob};
+    return {shr16_fma(w.x * x - w.y * y) + ob, shr16_fma(w.y * x + w.x * y) + ob};
 }
-
 #ifndef FFT_Q15_SHIFT_MODE
-#define FFT_Q15_SHIFT_MODE 1     /* 0: every rot shift on the ALU pipe, 1: FMA pipe except at the end of a pass, 2: FMA pipe always */
+#define FFT_Q15_SHIFT_MODE 0     /* 0: every rot shift on the ALU pipe (measured best), 1: FMA pipe except at the end of a pass, 2: FMA pipe always */
 #endif
 struct ArithQ15 {
     static constexpr bool kAluShift(bool tail) { return FFT_Q15_SHIFT_MODE == 0 || (FFT_Q15_SHIFT_MODE == 1 && tail); }
@@ -519,45 +524,47 @@ struct ArithQ15 {
     static FFT_HD twid tload(telem e) { return e; }
     static FFT_HD work shl1(work w) { return {q15w((int32_t)((uint32_t)w.x << 1)), q15w((int32_t)((uint32_t)w.y << 1))}; }
 
+    static constexpr bool kBiased = true;      /* points a, b of a middle / last stage butterfly carry +32768 (see half_sat_add16) */
+    /* ob: the bias (0 or 32768) every output of this butterfly carries (the outputs of one butterfly always play the
+     * same part in their next butterflies); 0 for the last stage */
     template <int KIND, bool INV, bool TAIL = false, bool PRE = false>
-    static FFT_HD void bfly4(work &A, work &B, work &C, work &D, twid w1, twid w2, twid w3)
+    static FFT_HD void bfly4(work &A, work &B, work &C, work &D, twid w1, twid w2, twid w3, int32_t ob = 0)
     {
         if (KIND == ST_FIRST4) {
-            /* inputs >> 2: nothing below can saturate or wrap (see the header of this section) */
+            /* inputs >> 2 (plain, unbiased): nothing below can saturate or wrap (see the header of this section) */
             const int32_t T0 = PRE ? A.x : A.x >> 2, T1 = PRE ? A.y : A.y >> 2, C0 = PRE ? C.x : C.x >> 2, C1 = PRE ? C.y : C.y >> 2;
             const int32_t B0 = PRE ? B.x : B.x >> 2, B1 = PRE ? B.y : B.y >> 2, U0 = PRE ? D.x : D.x >> 2, U1 = PRE ? D.y : D.y >> 2;
             const int32_t R0 = T0 + C0, R1 = T1 + C1, S0 = T0 - C0, S1 = T1 - C1;
             const int32_t V0 = B0 + U0, V1 = B1 + U1, D0 = B0 - U0, D1 = B1 - U1;
-            A = {(R0 >> 1) + (V0 >> 1), (R1 >> 1) + (V1 >> 1)};
-            C = rot_q15<INV, kAluShift(TAIL)>(R0 - V0, R1 - V1, w2);
+            A = {(R0 >> 1) + (V0 >> 1) + ob, (R1 >> 1) + (V1 >> 1) + ob};
+            C = rot_q15<INV, kAluShift(TAIL)>(R0 - V0, R1 - V1, w2, ob);
             if (!INV) {
-                B = rot_q15<INV, kAluShift(TAIL)>(S0 + D1, S1 - D0, w1);
-                D = rot_q15<INV, kAluShift(TAIL)>(S0 - D1, S1 + D0, w3);
+                B = rot_q15<INV, kAluShift(TAIL)>(S0 + D1, S1 - D0, w1, ob);
+                D = rot_q15<INV, kAluShift(TAIL)>(S0 - D1, S1 + D0, w3, ob);
             } else {
-                B = rot_q15<INV, kAluShift(TAIL)>(S0 - D1, S1 + D0, w1);
-                D = rot_q15<INV, kAluShift(TAIL)>(S0 + D1, S1 - D0, w3);
+                B = rot_q15<INV, kAluShift(TAIL)>(S0 - D1, S1 + D0, w1, ob);
+                D = rot_q15<INV, kAluShift(TAIL)>(S0 + D1, S1 - D0, w3, ob);
             }
             return;
         }
-        /* middle and last stages: saturating pair sums, then everything on halved operands */
+        /* middle and last stages: saturating pair sums (A, B biased; C, D plain), then everything on halved operands */
+        const int32_t R0 = half_sat_add16(A.x, C.x), R1 = half_sat_add16(A.y, C.y);
         const int32_t S0 = half_sat_sub16(A.x, C.x), S1 = half_sat_sub16(A.y, C.y);
         const int32_t V0 = half_sat_add16(B.x, D.x), V1 = half_sat_add16(B.y, D.y);
         const int32_t D0 = half_sat_sub16(B.x, D.x), D1 = half_sat_sub16(B.y, D.y);
-        const int32_t R0 = half_sat_add16(A.x, C.x), R1 = half_sat_add16(A.y, C.y);
-        const int32_t RpV0 = R0 + V0, RpV1 = R1 + V1, RmV0 = R0 - V0, RmV1 = R1 - V1;
         if (KIND == ST_MID4) {
-            A = {RpV0 >> 1, RpV1 >> 1};
-            C = rot_q15<INV, kAluShift(TAIL)>(RmV0, RmV1, w2);
+            A = {((R0 + V0) >> 1) + ob, ((R1 + V1) >> 1) + ob};
+            C = rot_q15<INV, kAluShift(TAIL)>(R0 - V0, R1 - V1, w2, ob);
             if (!INV) {
-                B = rot_q15<INV, kAluShift(TAIL)>(S0 + D1, S1 - D0, w1);
-                D = rot_q15<INV, kAluShift(TAIL)>(S0 - D1, S1 + D0, w3);
+                B = rot_q15<INV, kAluShift(TAIL)>(S0 + D1, S1 - D0, w1, ob);
+                D = rot_q15<INV, kAluShift(TAIL)>(S0 - D1, S1 + D0, w3, ob);
             } else {
-                B = rot_q15<INV, kAluShift(TAIL)>(S0 - D1, S1 + D0, w1);
-                D = rot_q15<INV, kAluShift(TAIL)>(S0 + D1, S1 - D0, w3);
+                B = rot_q15<INV, kAluShift(TAIL)>(S0 - D1, S1 + D0, w1, ob);
+                D = rot_q15<INV, kAluShift(TAIL)>(S0 + D1, S1 - D0, w3, ob);
             }
         } else {
-            A = {RpV0, RpV1};
-            C = {RmV0, RmV1};
+            A = {R0 + V0, R1 + V1};
+            C = {R0 - V0, R1 - V1};
             const work p = {S0 + D1, S1 - D0}, q = {S0 - D1, S1 + D0};
             B = INV ? q : p;
             D = INV ? p : q;
@@ -607,6 +614,7 @@ struct ArithQ15 {
  * (-ffp-contract=off) -- the f64 kernels have the arithmetic headroom (16 bytes per point).  The inverse is conjugate -> forward -> conjugate / N (:262-312), done by CfftBody at the load and
  * the store like f32, so the butterflies have no inverse variant. */
 struct ArithF64 {
+    static constexpr bool kBiased = false;       /* see ArithQ15::bfly4 */
     static constexpr bool kPreShift = false;     /* see ArithQ15::load_shifted */
     static constexpr bool kDirectTw = false;
     static constexpr int kTableNum = 1, kTableDen = 1;        /* reference table: N entries */
@@ -636,7 +644,7 @@ struct ArithF64 {
     /* outputs in residue order (a', b'[W^1], c'[W^2], d'[W^3]); arm_cfft_f64.c:108-170.  The last stage's
      * twiddles are W^0 = (1, 0) (:94-99 with ia1 = 0): the products are skipped. */
     template <int KIND, bool INV, bool TAIL = false, bool PRE = false>
-    static FFT_HD void bfly4(work &A, work &B, work &C, work &D, twid w1, twid w2, twid w3)
+    static FFT_HD void bfly4(work &A, work &B, work &C, work &D, twid w1, twid w2, twid w3, int32_t = 0)
     {
         double r1 = A.x + C.x, r2 = A.x - C.x, s1 = A.y + C.y, s2 = A.y - C.y;
         double t1 = B.x + D.x;

@@ -74,6 +74,14 @@ template <bool STAGED, class V> FFT_HD V ld_in(const V *p)
     return ld_stream(p);
 }
 
+/* plain binary bit reversal of k, 0 <= k < n (n a power of two) */
+FFT_HD constexpr int bitrev_const(int k, int n)
+{
+    int r = 0;
+    for (int m = n >> 1; m; m >>= 1, k >>= 1) r = (r << 1) | (k & 1);
+    return r;
+}
+
 /* number of phases for a plan with NP passes: 1 -> 1, 2 -> 2, 3 -> 4 (the middle pass is split
  * into load+compute / store so the single exchange buffer can be reused) */
 template <int NP> struct PhaseCount { static constexpr int value = (NP == 1) ? 1 : (NP == 2 ? 2 : 4); };
@@ -380,7 +388,9 @@ template <class PL, bool INV, int MODE, bool STAGED = false> struct CfftMagBody 
  * from shared memory and writing bin k and its conjugate mirror 2N-k (the reference writes the mirror
  * explicitly, :327-329).  HBM: N elements in, 2N elements out, once.  The inverse direction is
  * CfftBody<.., RIFFT = true>. */
-template <class PL> struct RfftFixFwdBody {
+/* PERM: bitReverseFlagR = 0 -- the complex transform's result is laid out in the unordered (bit-reversed) order
+ * before the split stage reads it as if it were natural order (arm_rfft_q31.c:173-176 with the flag passed on) */
+template <class PL, bool PERM = false> struct RfftFixFwdBody {
     typedef CfftBody<PL, false> C;
     typedef typename C::Eng Eng;
     typedef typename C::A A;
@@ -400,6 +410,7 @@ template <class PL> struct RfftFixFwdBody {
         const telem *tw;         /* pass-ordered twiddles of the N-point CFFT plan */
         const ci32x4 *coef;      /* split-stage coefficients of bins 0..N-1 */
         int shl1;
+        const uint16_t *perm;    /* PERM: position of X[k] in the unordered layout */
     };
     static FFT_HD Args for_frame(Args a, uint64_t frame)
     {
@@ -436,7 +447,7 @@ template <class PL> struct RfftFixFwdBody {
             C::template phase<0, true>(r, cfft_args(a), sm, i);
             work y[N];                                                /* y[k] = X[k] */
 #pragma unroll
-            for (int e = 0; e < N; e++) y[PSL::out_index(e)] = PL::kOddLog2 ? A::shl1(r.v[e]) : r.v[e];
+            for (int e = 0; e < N; e++) y[PERM ? bitrev_const(PSL::out_index(e), N) : PSL::out_index(e)] = PL::kOddLog2 ? A::shl1(r.v[e]) : r.v[e];
             put_bin0(a, y[0]);
             bins_in_regs<1>(a, y);
         } else if constexpr (PH < kCfftPhases) {
@@ -449,8 +460,10 @@ template <class PL> struct RfftFixFwdBody {
                     const int k = Eng::template out_index<NP - 1>(i, b, e);
                     const work w = r.v[b * PSL::R + e];
                     /* natural order, NOT padded: lanes store / load runs of consecutive bins in both directions */
-                    FFT_TRACE_SMEM(&sm[k], (int)sizeof(xelem), 1);
-                    sm[k] = A::xstore(PL::kOddLog2 ? A::shl1(w) : w);               /* cfft_q31.c:803-820, cfft_q15.c:810-827 */
+                    int pos = k;
+                    if constexpr (PERM) pos = (int)a.perm[k];
+                    FFT_TRACE_SMEM(&sm[pos], (int)sizeof(xelem), 1);
+                    sm[pos] = A::xstore(PL::kOddLog2 ? A::shl1(w) : w);             /* cfft_q31.c:803-820, cfft_q15.c:810-827 */
                 }
         } else {
 #pragma unroll
@@ -1199,7 +1212,7 @@ template <class A, int COUNT> struct VecOut {
 };
 
 /* arm_rfft_q31 / arm_rfft_q15, complex length N <= 64 (real length <= 128) */
-template <class PL, bool INV> struct TinyRfftFixBody {
+template <class PL, bool INV, bool PERM = false> struct TinyRfftFixBody {
     typedef typename PL::Arith A;
     typedef typename A::elem elem;
     typedef typename A::xelem xelem;
@@ -1256,7 +1269,7 @@ template <class PL, bool INV> struct TinyRfftFixBody {
             Eng::template compute<0, false>(r, a.tw, 0);
             work y[N];                                                 /* y[k] = X[k] */
 #pragma unroll
-            for (int e = 0; e < N; e++) y[PS::out_index(e)] = PL::kOddLog2 ? A::shl1(r.v[e]) : r.v[e];
+            for (int e = 0; e < N; e++) y[PERM ? bitrev_const(PS::out_index(e), N) : PS::out_index(e)] = PL::kOddLog2 ? A::shl1(r.v[e]) : r.v[e];
             work z[2 * N];
             z[0] = A::split_dc(y[0]);
             z[N] = A::split_nyquist(y[0]);
@@ -1278,7 +1291,7 @@ template <class PL, bool INV> struct TinyRfftFixBody {
             for (int e = 0; e < N; e++) {
                 work w = r.v[e];
                 if (PL::kOddLog2) w = A::shl1(w);
-                y[PS::out_index(e)] = A::sat_shl1(w);
+                y[PERM ? bitrev_const(PS::out_index(e), N) : PS::out_index(e)] = A::sat_shl1(w);
             }
             out_groups<0>(y, a.out);
         }

@@ -132,31 +132,37 @@ template <class ARITH, int KA, int KB = -1, int KC = -1> struct PassFix {
 
     /* TAIL: the stage is the last one of its pass (its results go to shared or global memory next) */
     template <int K, bool INV, int NBF, bool TAIL, bool PRE = false>
-    static FFT_HD void stage4(work &a, work &b, work &c, work &d, const telem *__restrict__ twp, int slot, int j)
+    static FFT_HD void stage4(work &a, work &b, work &c, work &d, const telem *__restrict__ twp, int slot, int j, int32_t ob)
     {
         if (K == ST_LAST4) {
             twid z = {0, 0};
-            ARITH::template bfly4<K, INV, TAIL>(a, b, c, d, z, z, z);
+            ARITH::template bfly4<K, INV, TAIL>(a, b, c, d, z, z, z, 0);
         } else {
             ARITH::template bfly4<K, INV, TAIL, PRE>(a, b, c, d, ARITH::tload(twp[slot * NBF + j]), ARITH::tload(twp[(slot + 1) * NBF + j]),
-                                          ARITH::tload(twp[(slot + 2) * NBF + j]));
+                                          ARITH::tload(twp[(slot + 2) * NBF + j]), ob);
         }
     }
+    /* Bias carried by the outputs of a butterfly (Arith::kBiased: ArithQ15): +32768 when they are points a or b of
+     * their next butterfly.  Inside a pass that is a compile-time fact of the register index: stage b reads
+     * (x[n], x[n + rc], x[n + 2 rc], x[n + 3 rc]) as (a, b, c, d), stage c reads x[4 g .. 4 g + 3]. */
+    static constexpr int32_t kBias = ARITH::kBiased ? 32768 : 0;
+    static FFT_HD constexpr int32_t bias_into_b(int o) { return ((o / rc) % 4 < 2) ? kBias : 0; }   /* outputs of stage a, butterfly o */
+    static FFT_HD constexpr int32_t bias_into_c(int u) { return (u % 4 < 2) ? kBias : 0; }          /* outputs of stage b, column u */
 
     /* radix-4 stage on the reference-layout table: W^1, W^2, W^3 at ia, 2 ia, 3 ia (arm_cfft_radix4_q31.c:229-266) */
     template <int K, bool INV, bool TAIL, bool PRE = false>
-    static FFT_HD void stage4d(work &a, work &b, work &c, work &d, const telem *__restrict__ tw, int ia)
+    static FFT_HD void stage4d(work &a, work &b, work &c, work &d, const telem *__restrict__ tw, int ia, int32_t ob)
     {
         if (K == ST_LAST4) {
             twid z = {0, 0};
-            ARITH::template bfly4<K, INV, TAIL>(a, b, c, d, z, z, z);
+            ARITH::template bfly4<K, INV, TAIL>(a, b, c, d, z, z, z, 0);
         } else {
-            ARITH::template bfly4<K, INV, TAIL, PRE>(a, b, c, d, ARITH::tload(tw[ia]), ARITH::tload(tw[2 * ia]), ARITH::tload(tw[3 * ia]));
+            ARITH::template bfly4<K, INV, TAIL, PRE>(a, b, c, d, ARITH::tload(tw[ia]), ARITH::tload(tw[2 * ia]), ARITH::tload(tw[3 * ia]), ob);
         }
     }
     /* same butterflies as compute(), twiddle indices as in fill(): S = product of the radices of the earlier passes */
     template <bool INV, int N, int S, bool PRE = false>
-    static FFT_HD void compute_direct(work *x, const telem *__restrict__ tw, int j)
+    static FFT_HD void compute_direct(work *x, const telem *__restrict__ tw, int j, int32_t tailBias = 0)
     {
         constexpr int NBF = N / R, Q = rb * rc;
         const int sp = S * (j / S);
@@ -166,7 +172,7 @@ template <class ARITH, int KA, int KB = -1, int KC = -1> struct PassFix {
             if (KA == ST_PRE2)
                 ARITH::template bfly2<INV, PRE>(x[o], x[o + Q], ARITH::tload(tw[ia]));
             else
-                stage4d<KA, INV, (KB < 0), PRE>(x[o], x[o + Q], x[o + 2 * Q], x[o + 3 * Q], tw, ia);
+                stage4d<KA, INV, (KB < 0), PRE>(x[o], x[o + Q], x[o + 2 * Q], x[o + 3 * Q], tw, ia, KB < 0 ? tailBias : bias_into_b(o));
         }
         if constexpr (KB >= 0) {                      /* stage b */
 #pragma unroll
@@ -174,19 +180,21 @@ template <class ARITH, int KA, int KB = -1, int KC = -1> struct PassFix {
 #pragma unroll
                 for (int u = 0; u < rc; u++) {
                     const int base = u + Q * v;
-                    stage4d<KB, INV, (KC < 0)>(x[base], x[base + rc], x[base + 2 * rc], x[base + 3 * rc], tw, ra * (sp + NBF * u));
+                    stage4d<KB, INV, (KC < 0)>(x[base], x[base + rc], x[base + 2 * rc], x[base + 3 * rc], tw, ra * (sp + NBF * u),
+                                               KC < 0 ? tailBias : bias_into_c(u));
                 }
         }
         if constexpr (KC >= 0) {                      /* stage c */
 #pragma unroll
             for (int g = 0; g < ra * rb; g++)
-                stage4d<KC, INV, true>(x[4 * g], x[4 * g + 1], x[4 * g + 2], x[4 * g + 3], tw, ra * rb * sp);
+                stage4d<KC, INV, true>(x[4 * g], x[4 * g + 1], x[4 * g + 2], x[4 * g + 3], tw, ra * rb * sp, tailBias);
         }
     }
 
     /* PRE: the inputs of stage a carry that stage's input shift already (Arith::load_shifted) */
+    /* tailBias: bias of the results of the pass's last stage (Engine::compute: 0 in the frame's last pass) */
     template <bool INV, int N, bool LASTPASS, bool PRE = false>
-    static FFT_HD void compute(work *x, const telem *__restrict__ twp, int j)
+    static FFT_HD void compute(work *x, const telem *__restrict__ twp, int j, int32_t tailBias = 0)
     {
         constexpr int NBF = N / R, Q = rb * rc;
 #pragma unroll
@@ -194,7 +202,7 @@ template <class ARITH, int KA, int KB = -1, int KC = -1> struct PassFix {
             if (KA == ST_PRE2)
                 ARITH::template bfly2<INV, PRE>(x[o], x[o + Q], ARITH::tload(twp[o * NBF + j]));
             else
-                stage4<KA, INV, NBF, (KB < 0), PRE>(x[o], x[o + Q], x[o + 2 * Q], x[o + 3 * Q], twp, o * ta, j);
+                stage4<KA, INV, NBF, (KB < 0), PRE>(x[o], x[o + Q], x[o + 2 * Q], x[o + 3 * Q], twp, o * ta, j, KB < 0 ? tailBias : bias_into_b(o));
         }
         if constexpr (KB >= 0) {                      /* stage b */
 #pragma unroll
@@ -202,13 +210,14 @@ template <class ARITH, int KA, int KB = -1, int KC = -1> struct PassFix {
 #pragma unroll
                 for (int u = 0; u < rc; u++) {
                     const int base = u + Q * v;
-                    stage4<KB, INV, NBF, (KC < 0)>(x[base], x[base + rc], x[base + 2 * rc], x[base + 3 * rc], twp, kOffB + u * tb, j);
+                    stage4<KB, INV, NBF, (KC < 0)>(x[base], x[base + rc], x[base + 2 * rc], x[base + 3 * rc], twp, kOffB + u * tb, j,
+                                                   KC < 0 ? tailBias : bias_into_c(u));
                 }
         }
         if constexpr (KC >= 0) {                      /* stage c */
 #pragma unroll
             for (int g = 0; g < ra * rb; g++)
-                stage4<KC, INV, NBF, true>(x[4 * g], x[4 * g + 1], x[4 * g + 2], x[4 * g + 3], twp, kOffC, j);
+                stage4<KC, INV, NBF, true>(x[4 * g], x[4 * g + 1], x[4 * g + 2], x[4 * g + 3], twp, kOffC, j, tailBias);
         }
     }
 };
@@ -366,7 +375,16 @@ template <class PL> struct Engine {
 #pragma unroll
         for (int b = 0; b < NB; b++) {
             const int j = bfly_index<PS::kMirror, T, NBF>(i, b);
-            if constexpr (PRE) {
+            if constexpr (A::kBiased) {
+                /* Biased arithmetic (ArithQ15::bfly4): the results of butterfly j land at positions
+                 * (j % S) + S (R (j / S) + t), t < R, and the next pass reads position p as point p / (N/4) of a
+                 * radix-4 butterfly (a, b, c, d): a or b -- the biased ones -- iff p < N/2 iff j < NBF/2, one
+                 * value per butterfly.  The frame's last pass produces plain results. */
+                static_assert(P == NP - 1 || (NBF % (2 * S) == 0), "the halves of the next pass must be whole butterfly blocks");
+                const int32_t tailBias = (P == NP - 1) ? 0 : (j < NBF / 2 ? 32768 : 0);
+                if constexpr (PS::kDirect) PS::template compute_direct<INV, N, S, PRE>(&r.v[b * R], tw, j, tailBias);
+                else PS::template compute<INV, N, (P == NP - 1), PRE>(&r.v[b * R], tw + PassOf<PL, P>::TWOFF, j, tailBias);
+            } else if constexpr (PRE) {
                 if constexpr (PS::kDirect) PS::template compute_direct<INV, N, S, true>(&r.v[b * R], tw, j);
                 else PS::template compute<INV, N, (P == NP - 1), true>(&r.v[b * R], tw + PassOf<PL, P>::TWOFF, j);
             } else {

@@ -29,7 +29,9 @@ struct KernelEntry {
      *       aux = split coefficients (ci32x4 per bin), shl1 as for cfft
      * cfft + spectrum epilogue (f32): in -> out = magnitudes, or out = peak values and aux = peak indices; tw = the
      *       cfft plan's twiddles; the shl1 slot carries the SpectrumMode (0 mag, 1 mag squared, 2 peak) */
-    int (*launch)(const void *in, void *out, uint64_t nFrames, int inv, const void *tw, const void *aux, int shl1,
+    /* aux2: rfft q31/q15 only -- the unordered layout of the complex transform (uint16 positions) when
+     *       bitReverseFlagR == 0, else null */
+    int (*launch)(const void *in, void *out, uint64_t nFrames, int inv, const void *tw, const void *aux, const void *aux2, int shl1,
                   int flavour, cudaStream_t st);
     /* number of elements of the pass-ordered twiddle table (+1 pad); fills hostOut when non-null */
     size_t (*twiddles)(const void *base, void *hostOut);

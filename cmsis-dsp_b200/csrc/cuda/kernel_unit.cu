@@ -537,7 +537,7 @@ static int cfft_go(const void *in, void *out, uint64_t nFrames, const void *tw, 
     typename BODY::Args a{(const elem *)in, (elem *)out, (const telem *)tw, (const uint16_t *)aux, 1.0f / (float)PL::N, shl1};
     return launch<BODY, PL>(a, nFrames, st);
 }
-static int ku_launch(const void *in, void *out, uint64_t nFrames, int inv, const void *tw, const void *aux, int shl1, int flavour, cudaStream_t st)
+static int ku_launch(const void *in, void *out, uint64_t nFrames, int inv, const void *tw, const void *aux, const void *, int shl1, int flavour, cudaStream_t st)
 {
     if (inv) return aux ? cfft_go<true, true>(in, out, nFrames, tw, aux, shl1, flavour, st) : cfft_go<true, false>(in, out, nFrames, tw, aux, shl1, flavour, st);
     return aux ? cfft_go<false, true>(in, out, nFrames, tw, aux, shl1, flavour, st) : cfft_go<false, false>(in, out, nFrames, tw, aux, shl1, flavour, st);
@@ -563,7 +563,7 @@ struct PIPE { static constexpr bool kHas = true, kPrefer = true; };
 #else
 typedef PipeOf<PL> PIPE;
 #endif
-static int ku_launch(const void *in, void *out, uint64_t nFrames, int, const void *tw, const void *aux, int, int flavour, cudaStream_t st)
+static int ku_launch(const void *in, void *out, uint64_t nFrames, int, const void *tw, const void *aux, const void *, int, int flavour, cudaStream_t st)
 {
 #if KU_N <= 64
     if (flavour == KF_PIPE && aligned16(in) && aligned16(out)) {
@@ -607,7 +607,7 @@ struct PIPE { static constexpr bool kHas = true, kPrefer = true; };
 #else
 typedef PipeOf<PL> PIPE;
 #endif
-static int ku_launch(const void *in, void *out, uint64_t nFrames, int, const void *tw, const void *aux, int, int flavour, cudaStream_t st)
+static int ku_launch(const void *in, void *out, uint64_t nFrames, int, const void *tw, const void *aux, const void *, int, int flavour, cudaStream_t st)
 {
 #if KU_N <= 64
     if (flavour == KF_PIPE && aligned16(in) && aligned16(out)) {
@@ -677,7 +677,7 @@ static int mag_go(const void *in, void *out, uint64_t nFrames, const void *tw, c
     a.mag = (float *)out; a.peakVal = (float *)out; a.peakIdx = (uint32_t *)aux;
     return launch<BODY, PL>(a, nFrames, st);
 }
-static int ku_launch(const void *in, void *out, uint64_t nFrames, int inv, const void *tw, const void *aux, int mode, int flavour, cudaStream_t st)
+static int ku_launch(const void *in, void *out, uint64_t nFrames, int inv, const void *tw, const void *aux, const void *, int mode, int flavour, cudaStream_t st)
 {
     switch (mode) {
     case SPEC_MAG: return inv ? mag_go<true, SPEC_MAG>(in, out, nFrames, tw, aux, flavour, st) : mag_go<false, SPEC_MAG>(in, out, nFrames, tw, aux, flavour, st);
@@ -708,7 +708,7 @@ typedef RfftF64FwdBody<PL> BODY;
 typedef RfftF64InvBody<PL> BODY;
 #endif
 /* in -> out (never aliased), tw = the twiddles of the KU_N-point f64 CFFT plan, aux = twiddleCoefF64_rfft (device) */
-static int ku_launch(const void *in, void *out, uint64_t nFrames, int, const void *tw, const void *aux, int, int, cudaStream_t st)
+static int ku_launch(const void *in, void *out, uint64_t nFrames, int, const void *tw, const void *aux, const void *, int, int, cudaStream_t st)
 {
 #if KU_OP == 11
     BODY::Args a{(const cf64 *)in, (cf64 *)out, (const cf64 *)tw, (const cf64 *)aux};
@@ -732,31 +732,38 @@ typedef PlanCfftFix<AR, KU_N>::type PL;
 struct PIPE { static constexpr bool kHas = (PL::NP == 1 && PL::T == 1), kPrefer = kHas; };
 #if KU_OP == 5 || KU_OP == 7
 static constexpr bool kKuInverse = false;
-typedef RfftFixFwdBody<PL> BODY;
-static BODY::Args ku_args(const void *in, void *out, const void *tw, const void *aux, int shl1)
+template <bool PERM> struct FixBody { typedef RfftFixFwdBody<PL, PERM> type; };
+template <bool PERM> static typename FixBody<PERM>::type::Args ku_args(const void *in, void *out, const void *tw, const void *aux, const void *aux2, int shl1)
 {
-    return BODY::Args{(const AR::elem *)in, (AR::elem *)out, (const AR::telem *)tw, (const ci32x4 *)aux, shl1};
+    return typename FixBody<PERM>::type::Args{(const AR::elem *)in, (AR::elem *)out, (const AR::telem *)tw, (const ci32x4 *)aux, shl1, (const uint16_t *)aux2};
 }
 #else
 static constexpr bool kKuInverse = true;
-typedef CfftBody<PL, true, false, false, true> BODY;
-static BODY::Args ku_args(const void *in, void *out, const void *tw, const void *aux, int shl1)
+template <bool PERM> struct FixBody { typedef CfftBody<PL, true, PERM, false, true> type; };
+template <bool PERM> static typename FixBody<PERM>::type::Args ku_args(const void *in, void *out, const void *tw, const void *aux, const void *aux2, int shl1)
 {
-    return BODY::Args{(const AR::elem *)in, (AR::elem *)out, (const AR::telem *)tw, nullptr, 0.0f, shl1, (const ci32x4 *)aux};
+    return typename FixBody<PERM>::type::Args{(const AR::elem *)in, (AR::elem *)out, (const AR::telem *)tw, (const uint16_t *)aux2, 0.0f, shl1, (const ci32x4 *)aux};
 }
 #endif
-/* in -> out (never aliased), tw = the pass-ordered twiddles of the KU_N-point CFFT plan, aux = split coefficients */
+typedef FixBody<false>::type BODY;
+/* in -> out (never aliased), tw = the pass-ordered twiddles of the KU_N-point CFFT plan, aux = split coefficients,
+ * aux2 = the unordered layout of the complex transform when bitReverseFlagR == 0 (else null) */
 /* (templates on the direction only so that the thread-per-frame body is not instantiated for the longer plans) */
-template <bool KI>
-static int fix_go(const void *in, void *out, uint64_t nFrames, const void *tw, const void *aux, int shl1, int flavour, cudaStream_t st)
+template <bool KI, bool PERM>
+static int fix_go2(const void *in, void *out, uint64_t nFrames, const void *tw, const void *aux, const void *aux2, int shl1, int flavour, cudaStream_t st)
 {
     if constexpr (PIPE::kHas) {
         if (flavour == KF_PIPE && aligned16(in) && aligned16(out)) {
-            typedef TinyRfftFixBody<PL, KI> TBODY;
+            typedef TinyRfftFixBody<PL, KI, PERM> TBODY;
             return launch_tiny<TBODY, PL>(typename TBODY::Args{(const AR::elem *)in, (AR::elem *)out, (const AR::telem *)tw, (const ci32x4 *)aux, shl1}, nFrames, st);
         }
     }
-    return launch<BODY, PL>(ku_args(in, out, tw, aux, shl1), nFrames, st);
+    return launch<typename FixBody<PERM>::type, PL>(ku_args<PERM>(in, out, tw, aux, aux2, shl1), nFrames, st);
+}
+template <bool KI>
+static int fix_go(const void *in, void *out, uint64_t nFrames, const void *tw, const void *aux, const void *aux2, int shl1, int flavour, cudaStream_t st)
+{
+    return aux2 ? fix_go2<KI, true>(in, out, nFrames, tw, aux, aux2, shl1, flavour, st) : fix_go2<KI, false>(in, out, nFrames, tw, aux, aux2, shl1, flavour, st);
 }
 template <bool KI> static int fix_facts(KernelFacts *f, int flavour)
 {
@@ -765,9 +772,9 @@ template <bool KI> static int fix_facts(KernelFacts *f, int flavour)
     }
     return facts_of<BODY, PL>(f);
 }
-static int ku_launch(const void *in, void *out, uint64_t nFrames, int, const void *tw, const void *aux, int shl1, int flavour, cudaStream_t st)
+static int ku_launch(const void *in, void *out, uint64_t nFrames, int, const void *tw, const void *aux, const void *aux2, int shl1, int flavour, cudaStream_t st)
 {
-    return fix_go<kKuInverse>(in, out, nFrames, tw, aux, shl1, flavour, st);
+    return fix_go<kKuInverse>(in, out, nFrames, tw, aux, aux2, shl1, flavour, st);
 }
 static int ku_facts(KernelFacts *f, int flavour) { return fix_facts<kKuInverse>(f, flavour); }
 typedef PL TWPLAN;

@@ -48,11 +48,15 @@ arm_status arm_cfft_radix4_batch_q31(const arm_cfft_radix4_instance_q31 *S, q31_
     if (!S || !radix4_len(S->fftLen) || arm_cfft_init_q31(&C, S->fftLen) != ARM_MATH_SUCCESS) return ARM_MATH_ARGUMENT_ERROR;
     return arm_cfft_batch_q31(&C, p, nFrames, S->ifftFlag, S->bitReverseFlag);
 }
+arm_status arm_cfft_batch_bitrev_order_f32(const arm_cfft_instance_f32 *S, float32_t *p, uint32_t nFrames, uint8_t ifftFlag);
+/* bitReverseFlag = 0: both functions leave the spectrum in plain binary bit-reversed order (the radix-4 stages write
+ * their outputs in the order a, c, b, d: arm_cfft_radix4_f32.c:261-330), measured on the compiled reference */
 static arm_status depr_f32(const arm_cfft_radix4_instance_f32 *S, float32_t *p, uint32_t nFrames, int radix4)
 {
     arm_cfft_instance_f32 C;
-    if (!S || !(radix4 ? radix4_len(S->fftLen) : radix2_len(S->fftLen)) || S->bitReverseFlag != 1) return ARM_MATH_ARGUMENT_ERROR;
+    if (!S || !(radix4 ? radix4_len(S->fftLen) : radix2_len(S->fftLen))) return ARM_MATH_ARGUMENT_ERROR;
     if (arm_cfft_init_f32(&C, S->fftLen) != ARM_MATH_SUCCESS) return ARM_MATH_ARGUMENT_ERROR;
+    if (!S->bitReverseFlag) return arm_cfft_batch_bitrev_order_f32(&C, p, nFrames, S->ifftFlag);
     return arm_cfft_batch_f32(&C, p, nFrames, S->ifftFlag, 1);
 }
 arm_status arm_cfft_radix4_batch_f32(const arm_cfft_radix4_instance_f32 *S, float32_t *p, uint32_t nFrames) { return depr_f32(S, p, nFrames, 1); }

@@ -36,68 +36,120 @@ arm_status arm_mfcc_init_##LEN##_f32(arm_mfcc_instance_f32 *S, uint32_t nbMelFil
 { return arm_mfcc_init_f32(S, LEN, nbMelFilters, nbDctOutputs, dctCoefs, filterPos, filterLengths, filterCoefs, windowCoefs); }
 MFCC_INIT(32) MFCC_INIT(64) MFCC_INIT(128) MFCC_INIT(256) MFCC_INIT(512) MFCC_INIT(1024) MFCC_INIT(2048) MFCC_INIT(4096)
 
-/* ---- device plan cache ---- */
-#define NPLAN 8
-typedef struct { arm_mfcc_instance_f32 key; int device; void *plan; unsigned age; } slot_t;
-static __thread slot_t g_slots[NPLAN];
-static __thread unsigned g_clock;
-static __thread void *g_stream;
-static __thread int g_stream_dev = -1;
-static __thread void *g_din, *g_dout;
-static __thread size_t g_din_cap, g_dout_cap;
+/* ---- device plan cache ----
+ * The instance is plain data owned by the caller, so the device-side plan (copies of the coefficient arrays) is kept
+ * here, process-wide, keyed by the device and by the CONTENT of the arrays: a 64-bit FNV-1a hash over the dimensions
+ * and every coefficient (about 9 KB for the 1024-point configuration, a few microseconds per call).  Keying on the
+ * array addresses alone would hand stale coefficients to a caller that rewrote its tables in place or whose
+ * allocator reused the addresses. */
+#include <pthread.h>
+#include "arm_cuda_engine.h"
 
-static int same_key(const arm_mfcc_instance_f32 *a, const arm_mfcc_instance_f32 *b)
+#define NPLAN 16
+typedef struct { uint64_t hash; int device; void *plan; unsigned age; } slot_t;
+static slot_t g_slots[NPLAN];
+static unsigned g_clock;
+static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
+
+static uint64_t fnv(uint64_t h, const void *data, size_t bytes)
 {
-    return a->dctCoefs == b->dctCoefs && a->filterCoefs == b->filterCoefs && a->windowCoefs == b->windowCoefs &&
-           a->filterPos == b->filterPos && a->filterLengths == b->filterLengths && a->fftLen == b->fftLen &&
-           a->nbMelFilters == b->nbMelFilters && a->nbDctOutputs == b->nbDctOutputs;
+    const unsigned char *p = (const unsigned char *)data;
+    size_t i = 0;
+    for (; i + 8 <= bytes; i += 8) {
+        uint64_t w;
+        memcpy(&w, p + i, 8);
+        h = (h ^ w) * 1099511628211ull;
+    }
+    for (; i < bytes; i++) h = (h ^ p[i]) * 1099511628211ull;
+    return h;
+}
+static uint64_t content_hash(const arm_mfcc_instance_f32 *S)
+{
+    uint64_t h = 1469598103934665603ull;
+    const uint32_t dims[3] = { S->fftLen, S->nbMelFilters, S->nbDctOutputs };
+    size_t taps = 0;
+    for (uint32_t f = 0; f < S->nbMelFilters; f++) taps += S->filterLengths[f];
+    h = fnv(h, dims, sizeof dims);
+    h = fnv(h, S->filterPos, S->nbMelFilters * sizeof(uint32_t));
+    h = fnv(h, S->filterLengths, S->nbMelFilters * sizeof(uint32_t));
+    h = fnv(h, S->dctCoefs, (size_t)S->nbMelFilters * S->nbDctOutputs * sizeof(float32_t));
+    h = fnv(h, S->filterCoefs, taps * sizeof(float32_t));
+    h = fnv(h, S->windowCoefs, (size_t)S->fftLen * sizeof(float32_t));
+    return h;
 }
 
-static int get_plan(const arm_mfcc_instance_f32 *S, void **plan)
+/* the plan of S on the CURRENT device (created on first use); the rfft tables the instance points at go first */
+static int get_plan(const arm_mfcc_instance_f32 *S, uint64_t hash, void **plan)
 {
     const int dev = cmsisdsp_cuda_get_device();
-    if (dev < 0) return -1;
+    if (dev < 0) return CMSISDSP_CUDA_ERR_NO_DEVICE;
+    const arm_rfft_fast_instance_f32 *R = &S->rfft;
+    if (!R->pTwiddleRFFT || !R->Sint.pTwiddle || R->fftLenRFFT != S->fftLen) return CMSISDSP_CUDA_ERR_ARGUMENT;
+    int rc = cmsisdsp_cuda_plan_upload(CMSISDSP_CUDA_F32, S->fftLen / 2, R->Sint.pTwiddle, R->Sint.pBitRevTable, R->Sint.bitRevLength);
+    if (!rc) rc = cmsisdsp_cuda_rfft_plan_upload(S->fftLen, R->pTwiddleRFFT);
+    if (rc) return rc;
+    pthread_mutex_lock(&g_mu);
     int victim = -1;
-    for (int k = 0; k < NPLAN; k++) {
-        if (g_slots[k].plan && g_slots[k].device == dev && same_key(&g_slots[k].key, S)) {
+    for (int k = 0; k < NPLAN; k++)
+        if (g_slots[k].plan && g_slots[k].device == dev && g_slots[k].hash == hash) {
             g_slots[k].age = ++g_clock;
             *plan = g_slots[k].plan;
+            pthread_mutex_unlock(&g_mu);
             return 0;
         }
-    }
     for (int k = 0; k < NPLAN && victim < 0; k++)
-        if (!g_slots[k].plan) victim = k;                    /* a free slot, else the least recently used */
-    if (victim < 0) {
-        victim = 0;
-        for (int k = 1; k < NPLAN; k++)
-            if (g_slots[k].age < g_slots[victim].age) victim = k;
-    }
-    /* the rfft plan of fftLen first (tables the instance points at) */
-    const arm_rfft_fast_instance_f32 *R = &S->rfft;
-    if (!R->pTwiddleRFFT || !R->Sint.pTwiddle || R->fftLenRFFT != S->fftLen) return -1;
-    if (!cmsisdsp_cuda_plan_ready(CMSISDSP_CUDA_F32, S->fftLen / 2) &&
-        cmsisdsp_cuda_plan_upload(CMSISDSP_CUDA_F32, S->fftLen / 2, R->Sint.pTwiddle, R->Sint.pBitRevTable, R->Sint.bitRevLength)) return -1;
-    if (!cmsisdsp_cuda_rfft_plan_ready(S->fftLen) && cmsisdsp_cuda_rfft_plan_upload(S->fftLen, R->pTwiddleRFFT)) return -1;
+        if (!g_slots[k].plan) victim = k;
     void *p = 0;
-    if (cmsisdsp_cuda_mfcc_plan_create(S->fftLen, S->nbMelFilters, S->nbDctOutputs, S->dctCoefs, S->filterPos,
-                                       S->filterLengths, S->filterCoefs, S->windowCoefs, &p)) return -1;
-    if (g_slots[victim].plan) cmsisdsp_cuda_mfcc_plan_destroy(g_slots[victim].plan);
-    g_slots[victim].key = *S;
+    rc = cmsisdsp_cuda_mfcc_plan_create(S->fftLen, S->nbMelFilters, S->nbDctOutputs, S->dctCoefs, S->filterPos,
+                                        S->filterLengths, S->filterCoefs, S->windowCoefs, &p);
+    if (rc) {
+        pthread_mutex_unlock(&g_mu);
+        return rc;
+    }
+    if (victim < 0) {
+        /* every slot is taken: this plan is used for the call and stays uncached (a cached plan may be in use by
+         * another thread's kernel, so none is evicted) */
+        pthread_mutex_unlock(&g_mu);
+        *plan = p;
+        return 1;
+    }
+    g_slots[victim].hash = hash;
     g_slots[victim].device = dev;
     g_slots[victim].plan = p;
     g_slots[victim].age = ++g_clock;
+    pthread_mutex_unlock(&g_mu);
     *plan = p;
     return 0;
 }
 
-static int grow(void **buf, size_t *cap, size_t bytes)
+/* drop every cached device plan (the caller guarantees that no MFCC call is in flight) */
+void arm_mfcc_release_plans(void)
 {
-    if (*cap >= bytes) return 0;
-    if (*buf) cmsisdsp_cuda_free(*buf);
-    *buf = 0; *cap = 0;
-    if (cmsisdsp_cuda_malloc(buf, bytes)) return -1;
-    *cap = bytes;
-    return 0;
+    pthread_mutex_lock(&g_mu);
+    for (int k = 0; k < NPLAN; k++) {
+        if (g_slots[k].plan) cmsisdsp_cuda_mfcc_plan_destroy(g_slots[k].plan);
+        g_slots[k].plan = 0;
+    }
+    pthread_mutex_unlock(&g_mu);
+}
+
+typedef struct { const arm_mfcc_instance_f32 *S; uint64_t hash; uint32_t hop; } mfcc_args;
+/* worker threads live for one call: the plan each one resolved in prepare() is found again at launch */
+static __thread void *t_plan;
+static __thread int t_plan_uncached;
+
+static int mfcc_prepare(const arm_cuda_job *job)
+{
+    const mfcc_args *a = (const mfcc_args *)job->self;
+    const int rc = get_plan(a->S, a->hash, &t_plan);
+    t_plan_uncached = (rc == 1);
+    return rc == 1 ? 0 : rc;
+}
+static int mfcc_launch(const arm_cuda_job *job, const void *din, void *dout, void *doutB, uint64_t n, void *stream)
+{
+    const mfcc_args *a = (const mfcc_args *)job->self;
+    (void)doutB;
+    return cmsisdsp_cuda_mfcc_f32(t_plan, din, a->hop, dout, n, stream);
 }
 
 arm_status arm_mfcc_batch_f32(const arm_mfcc_instance_f32 *S, const float32_t *pSrc, uint32_t hop,
@@ -106,38 +158,22 @@ arm_status arm_mfcc_batch_f32(const arm_mfcc_instance_f32 *S, const float32_t *p
     if (!S || !pSrc || !pDst || hop == 0 || (hop & 1u)) return ARM_MATH_ARGUMENT_ERROR;
     if (!S->dctCoefs || !S->filterCoefs || !S->windowCoefs || !S->filterPos || !S->filterLengths) return ARM_MATH_ARGUMENT_ERROR;
     if (nFrames == 0) return ARM_MATH_SUCCESS;
-    void *plan = 0;
-    if (get_plan(S, &plan)) return ARM_MATH_ARGUMENT_ERROR;
-    const int dev = cmsisdsp_cuda_get_device();
-    if (g_stream_dev != dev) {
-        if (cmsisdsp_cuda_stream_create(&g_stream)) return ARM_MATH_ARGUMENT_ERROR;
-        g_stream_dev = dev;
-        g_din = g_dout = 0; g_din_cap = g_dout_cap = 0;
+    const mfcc_args a = { S, content_hash(S), hop };
+    arm_cuda_job job = {0};
+    job.inStride = (size_t)hop * sizeof(float32_t);
+    job.inFrame = (size_t)S->fftLen * sizeof(float32_t);
+    job.outStride = job.outFrame = (size_t)S->nbDctOutputs * sizeof(float32_t);
+    job.prepare = mfcc_prepare;
+    job.launch = mfcc_launch;
+    job.self = &a;
+    const arm_status st = arm_cuda_run(&job, pSrc, pDst, nFrames);
+    if (t_plan_uncached && t_plan) {             /* single-device overflow plan of this thread (see get_plan) */
+        cmsisdsp_cuda_mfcc_plan_destroy(t_plan);
+        t_plan = 0;
+        t_plan_uncached = 0;
     }
-    const int inDev = cmsisdsp_cuda_is_device_pointer(pSrc), outDev = cmsisdsp_cuda_is_device_pointer(pDst);
-    if (inDev < 0 || outDev < 0 || inDev != outDev) return ARM_MATH_ARGUMENT_ERROR;
-    if (inDev) {
-        if (cmsisdsp_cuda_mfcc_f32(plan, pSrc, hop, pDst, nFrames, g_stream)) return ARM_MATH_ARGUMENT_ERROR;
-        return cmsisdsp_cuda_stream_synchronize(g_stream) ? ARM_MATH_ARGUMENT_ERROR : ARM_MATH_SUCCESS;
-    }
-    /* host buffers: chunks of frames through a device staging pair */
-    const uint64_t maxChunk = ((uint64_t)64 << 20) / (sizeof(float32_t) * (hop > S->fftLen ? hop : S->fftLen)) + 1;
-    for (uint64_t f = 0; f < nFrames;) {
-        const uint64_t n = (nFrames - f < maxChunk) ? nFrames - f : maxChunk;
-        const size_t inFloats = (size_t)(n - 1) * hop + S->fftLen, outFloats = (size_t)n * S->nbDctOutputs;
-        if (grow(&g_din, &g_din_cap, inFloats * sizeof(float32_t)) || grow(&g_dout, &g_dout_cap, outFloats * sizeof(float32_t)))
-            return ARM_MATH_ARGUMENT_ERROR;
-        if (cmsisdsp_cuda_memcpy_h2d(g_din, pSrc + f * hop, inFloats * sizeof(float32_t), g_stream) ||
-            cmsisdsp_cuda_mfcc_f32(plan, g_din, hop, g_dout, n, g_stream) ||
-            cmsisdsp_cuda_memcpy_d2h(pDst + f * S->nbDctOutputs, g_dout, outFloats * sizeof(float32_t), g_stream) ||
-            cmsisdsp_cuda_stream_synchronize(g_stream))
-            return ARM_MATH_ARGUMENT_ERROR;
-        f += n;
-    }
-    return ARM_MATH_SUCCESS;
+    return st;
 }
-
-extern arm_status arm_cuda_set_last_status(arm_status s);
 
 void arm_mfcc_f32(const arm_mfcc_instance_f32 *S, float32_t *pSrc, float32_t *pDst, float32_t *pTmp)
 {

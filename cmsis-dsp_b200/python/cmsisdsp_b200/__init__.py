@@ -24,6 +24,7 @@ RLENGTHS = [32, 64, 128, 256, 512, 1024, 2048, 4096]
 RFIX_LENGTHS = [32, 64, 128, 256, 512, 1024, 2048, 4096, 8192]      # arm_rfft_q31 / arm_rfft_q15
 ARM_MATH_SUCCESS = 0
 ARM_MATH_ARGUMENT_ERROR = -1
+ARM_MATH_CUDA_NO_DEVICE, ARM_MATH_CUDA_NO_PLAN, ARM_MATH_CUDA_RUNTIME_ERROR = -101, -102, -103
 TYPE_ID = {"f32": 0, "q31": 1, "q15": 2, "f64": 3}
 NP_DTYPE = {"f32": np.float32, "q31": np.int32, "q15": np.int16, "f64": np.float64}
 C_SCALAR = {"f32": C.c_float, "q31": C.c_int32, "q15": C.c_int16, "f64": C.c_double}
@@ -123,7 +124,8 @@ def cuda():
         "cmsisdsp_cuda_rfft_fast_f64": ([vp, vp, u32, u64, u8, vp], i),
         "cmsisdsp_cuda_rfft_f64_plan_upload": ([u32, vp], i), "cmsisdsp_cuda_rfft_f64_plan_ready": ([u32], i),
         "cmsisdsp_cuda_rfft_fix_plan_upload": ([i, u32, vp, vp, u32], i), "cmsisdsp_cuda_rfft_fix_plan_ready": ([i, u32], i),
-        "cmsisdsp_cuda_rfft_q31": ([vp, vp, u32, u64, u8, vp], i), "cmsisdsp_cuda_rfft_q15": ([vp, vp, u32, u64, u8, vp], i),
+        "cmsisdsp_cuda_rfft_q31": ([vp, vp, u32, u64, u8, u8, vp], i), "cmsisdsp_cuda_rfft_q15": ([vp, vp, u32, u64, u8, u8, vp], i),
+        "cmsisdsp_cuda_cfft_f32_bitrev_order": ([vp, u32, u64, u8, vp], i), "cmsisdsp_cuda_pointer_device": ([vp], i),
         "cmsisdsp_cuda_cfft_mag_f32": ([vp, vp, u32, u64, u8, u8, vp], i), "cmsisdsp_cuda_cfft_peak_f32": ([vp, vp, vp, u32, u64, u8, vp], i),
         "cmsisdsp_cuda_last_error": ([], C.c_char_p), "cmsisdsp_cuda_launch_count": ([], u64),
         "cmsisdsp_cuda_set_kernel_flavour": ([i], i),
@@ -171,6 +173,11 @@ def lib():
     L.arm_rfft_fast_batch_f64.argtypes = [C.POINTER(arm_rfft_fast_instance_f64), C.c_void_p, C.c_void_p, u32, u8]
     L.arm_rfft_fast_batch_f64.restype = i
     L.arm_cuda_last_status.argtypes, L.arm_cuda_last_status.restype = [], i
+    L.arm_cuda_set_devices.argtypes, L.arm_cuda_set_devices.restype = [C.POINTER(C.c_int32), u32], i
+    L.arm_cuda_get_devices.argtypes, L.arm_cuda_get_devices.restype = [C.POINTER(C.c_int32), u32], u32
+    L.arm_cuda_set_staging.argtypes, L.arm_cuda_set_staging.restype = [u32, u32], i
+    L.arm_cuda_release.argtypes, L.arm_cuda_release.restype = [], None
+    L.arm_mfcc_release_plans.argtypes, L.arm_mfcc_release_plans.restype = [], None
     for name in ("arm_cfft_mag_batch_f32", "arm_cfft_mag_squared_batch_f32"):
         f = getattr(L, name)
         f.argtypes, f.restype = [C.POINTER(arm_cfft_instance_f32), C.c_void_p, C.c_void_p, u32, u8], i
@@ -338,14 +345,29 @@ def rfft_fix_instance(kind, N, ifft=0, bitrev=1):
     return S
 
 
-def rfft_fix_batch(kind, N, x, ifft=0):
+def set_devices(devices=None):
+    """arm_cuda_set_devices: the devices host-pointer batch calls fan out over (None / []: the default list)"""
+    devices = list(devices or [])
+    arr = (C.c_int32 * max(1, len(devices)))(*devices)
+    st = lib().arm_cuda_set_devices(arr, len(devices))
+    if st != ARM_MATH_SUCCESS:
+        raise ValueError(f"arm_cuda_set_devices({devices}) -> {st}")
+
+
+def get_devices():
+    arr = (C.c_int32 * 16)()
+    n = lib().arm_cuda_get_devices(arr, 16)
+    return [int(arr[k]) for k in range(min(n, 16))]
+
+
+def rfft_fix_batch(kind, N, x, ifft=0, bitrev=1):
     """arm_rfft_batch_<q31|q15> on a host array: forward [..., N] -> [frames, 2N]; inverse [..., 2N] -> [frames, N]."""
     src = np.ascontiguousarray(x, dtype=NP_DTYPE[kind])
     per = 2 * N if ifft else N
     assert src.size % per == 0
     frames = src.size // per
     out = np.empty((frames, N if ifft else 2 * N), dtype=NP_DTYPE[kind])
-    S = rfft_fix_instance(kind, N, ifft, 1)
+    S = rfft_fix_instance(kind, N, ifft, bitrev)
     st = getattr(lib(), f"arm_rfft_batch_{kind}")(C.byref(S), src.ctypes.data, out.ctypes.data, frames)
     if st != ARM_MATH_SUCCESS:
         raise RuntimeError(f"arm_rfft_batch_{kind} -> {st}: {last_error()}")
@@ -407,8 +429,8 @@ def ensure_rfft_fix_plans(kind, N):
         raise RuntimeError(f"rfft_fix_plan_upload({kind},{N}) -> {rc}: {last_error()}")
 
 
-def rfft_fix_device(kind, N, d_in, d_out, n_frames, ifft=0, stream=0):
-    rc = getattr(cuda(), f"cmsisdsp_cuda_rfft_{kind}")(d_in, d_out, N, n_frames, int(ifft), stream)
+def rfft_fix_device(kind, N, d_in, d_out, n_frames, ifft=0, stream=0, bitrev=1):
+    rc = getattr(cuda(), f"cmsisdsp_cuda_rfft_{kind}")(d_in, d_out, N, n_frames, int(ifft), int(bitrev), stream)
     if rc:
         raise RuntimeError(f"cmsisdsp_cuda_rfft_{kind} -> {rc}: {last_error()}")
 

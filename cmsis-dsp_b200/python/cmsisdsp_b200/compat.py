@@ -87,9 +87,10 @@ def _mk_rfft_fix(kind):
         N = int(S.fftLenReal)
         per_in, per_out = (2 * N, N) if S.ifftFlagR else (N, 2 * N)
         a = np.ascontiguousarray(pSrc, dtype=NP_DTYPE[kind]).reshape(-1)
-        if S.ifftFlagR and a.size == N + 2:                      # the reference's inverse reads bins 0..N/2 only
-            a = np.concatenate([a, np.zeros(N - 2, dtype=a.dtype)])
-        src, n = _frames(a, NP_DTYPE[kind], per_in)
+        if S.ifftFlagR and a.size == N + 2:                      # the reference's inverse reads bins 0..N/2 only, and so does
+            src, n = a, 1                                        # the C entry point: an N + 2 buffer is enough for one frame
+        else:
+            src, n = _frames(a, NP_DTYPE[kind], per_in)
         out = np.empty(n * per_out, dtype=NP_DTYPE[kind])
         _check(getattr(lib(), f"arm_rfft_batch_{kind}")(C.byref(S), src.ctypes.data, out.ctypes.data, n), f"arm_rfft_{kind}")
         return out

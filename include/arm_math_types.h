@@ -40,7 +40,11 @@ typedef enum
     ARM_MATH_NANINF                  = -4,
     ARM_MATH_SINGULAR                = -5,
     ARM_MATH_TEST_FAILURE            = -6,
-    ARM_MATH_DECOMPOSITION_FAILURE   = -7
+    ARM_MATH_DECOMPOSITION_FAILURE   = -7,
+    /* B200 build only (the reference's values above are unchanged): why a batched / legacy exec call did not run */
+    ARM_MATH_CUDA_NO_DEVICE          = -101,   /* no usable CUDA device (there is no CPU fallback) */
+    ARM_MATH_CUDA_NO_PLAN            = -102,   /* the instance's tables are not resident on the device */
+    ARM_MATH_CUDA_RUNTIME_ERROR      = -103    /* a CUDA call failed: text in cmsisdsp_cuda_last_error() */
 } arm_status;
 
 #ifdef __cplusplus

@@ -3,6 +3,8 @@
  * front library (libcmsisdsp_b200.so).  Plain pointers and sizes only; no CUDA, C++ or
  * torch types appear in any signature, so it can be bound from C, ctypes, cgo, JNI ...
  *
+ * Device data must be aligned to one complex element (8 bytes f32 / q31, 4 bytes q15, 16 bytes f64); other
+ * pointers are refused with CMSISDSP_CUDA_ERR_ARGUMENT.
  * Every entry point works on the CURRENT device of the calling thread
  * (cmsisdsp_cuda_set_device) and enqueues on the given stream (NULL = default stream,
  * otherwise a cudaStream_t / CUstream handle cast to void*).  Transform entry points take
@@ -60,11 +62,16 @@ int  cmsisdsp_cuda_stream_destroy(void *stream);
 int  cmsisdsp_cuda_stream_synchronize(void *stream);
 /* 1 if ptr is device (or managed) memory usable by kernels on the current device, 0 if host, <0 on error */
 int  cmsisdsp_cuda_is_device_pointer(const void *ptr);
+/* ordinal of the device that owns ptr, -1 for host memory, < -1 on error */
+int  cmsisdsp_cuda_pointer_device(const void *ptr);
 /* CUDA-event timing on `stream`: begin/end return an opaque timer; elapsed in milliseconds */
 int  cmsisdsp_cuda_timer_begin(void **timer, void *stream);
 int  cmsisdsp_cuda_timer_end(void *timer, void *stream, float *elapsedMs);
 
-/* ---- plans: device-resident tables, keyed by (device, type, fftLen) ---- */
+/* ---- plans: device-resident tables, keyed by (device, type, fftLen) and by the CONTENT of the host tables ----
+ * Every *_plan_upload call is cheap when the tables are known (pointer compare + 32-sample fingerprint; a 64-bit hash
+ * of the whole table when the pointer is new) and selects, for the calling thread, the device copy the following
+ * transform calls of that (type, length) use.  Up to 4 distinct tables per (device, type, length). */
 /* pTwiddle: f32 -> 2*fftLen floats (cos,+sin); f64 -> 2*fftLen doubles; q31/q15 -> 3*fftLen/2 values (3N/4 pairs).
  * pBitRevTable/bitRevLength: the ordered swap list of the instance struct; it is expanded to the
  * output permutation used when bitReverseFlag == 0.  Idempotent. */
@@ -82,6 +89,9 @@ int  cmsisdsp_cuda_cfft_q31(void *d_p, uint32_t fftLen, uint64_t nFrames,
                             uint8_t ifftFlag, uint8_t bitReverseFlag, void *stream);
 int  cmsisdsp_cuda_cfft_q15(void *d_p, uint32_t fftLen, uint64_t nFrames,
                             uint8_t ifftFlag, uint8_t bitReverseFlag, void *stream);
+/* arm_cfft_f32 whose result is left in plain binary bit-reversed order: what the deprecated arm_cfft_radix4_f32 /
+ * arm_cfft_radix2_f32 produce with bitReverseFlag = 0 (arm_cfft_radix4_f32.c:81-118, arm_cfft_radix2_f32.c) */
+int  cmsisdsp_cuda_cfft_f32_bitrev_order(void *d_p, uint32_t fftLen, uint64_t nFrames, uint8_t ifftFlag, void *stream);
 /* d_p: nFrames*2*fftLen doubles, 16-byte aligned */
 int  cmsisdsp_cuda_cfft_f64(void *d_p, uint32_t fftLen, uint64_t nFrames,
                             uint8_t ifftFlag, uint8_t bitReverseFlag, void *stream);
@@ -109,7 +119,9 @@ int  cmsisdsp_cuda_cfft_peak_f32(const void *d_src, void *d_val, void *d_idx, ui
                                  uint8_t ifftFlag, void *stream);
 
 /* ---- arm_rfft_q31 / arm_rfft_q15 (Source/TransformFunctions/arm_rfft_q31.c:145-181, arm_rfft_q15.c:148-182) ----
- * fftLenReal in {32..8192}; bitReverseFlagR = 1 (natural-order spectrum).  The plan is the cfft plan of the
+ * fftLenReal in {32..8192}.  bitReverseFlagR is handed to the complex transform inside, as the reference does
+ * (arm_rfft_q31.c:164,173): 1 = natural order; 0 = that transform's result stays in bit-reversed order (forward: the
+ * split stage then reads it as if it were natural order).  The plan is the cfft plan of the
  * same type and length fftLenReal/2 (cmsisdsp_cuda_plan_upload) plus the split-stage coefficients: the
  * instance's pTwiddleAReal / pTwiddleBReal (realCoefA/B, read at twidCoefRModifier), compacted on upload.
  * forward (ifftFlagR = 0): d_src nFrames*fftLenReal scalars (left untouched), d_dst nFrames*2*fftLenReal
@@ -120,9 +132,9 @@ int  cmsisdsp_cuda_rfft_fix_plan_upload(int type, uint32_t fftLenReal, const voi
                                         const void *pTwiddleBReal, uint32_t twidCoefRModifier);
 int  cmsisdsp_cuda_rfft_fix_plan_ready(int type, uint32_t fftLenReal);
 int  cmsisdsp_cuda_rfft_q31(const void *d_src, void *d_dst, uint32_t fftLenReal, uint64_t nFrames,
-                            uint8_t ifftFlagR, void *stream);
+                            uint8_t ifftFlagR, uint8_t bitReverseFlagR, void *stream);
 int  cmsisdsp_cuda_rfft_q15(const void *d_src, void *d_dst, uint32_t fftLenReal, uint64_t nFrames,
-                            uint8_t ifftFlagR, void *stream);
+                            uint8_t ifftFlagR, uint8_t bitReverseFlagR, void *stream);
 
 /* ---- arm_mfcc_f32 front end (Source/TransformFunctions/arm_mfcc_f32.c:88-174, arm_mfcc_init_f32.c:91-121) ----
  * One fused kernel per frame batch: normalise, window, rfft, magnitude, mel filter bank, log, DCT.

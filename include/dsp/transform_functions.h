@@ -13,7 +13,7 @@
  * call stages them through device memory and returns when the result is back in the
  * buffer) or device pointers (the call enqueues on the library's stream and returns after
  * completion).  There is no CPU fallback: without a CUDA device the batched functions
- * return ARM_MATH_ARGUMENT_ERROR and the legacy void functions latch the error in
+ * return ARM_MATH_CUDA_NO_DEVICE and the legacy void functions latch the error in
  * arm_cuda_last_status().
  */
 #ifndef TRANSFORM_FUNCTIONS_H_
@@ -209,8 +209,8 @@ arm_status arm_cfft_radix2_batch_f32(const arm_cfft_radix2_instance_f32 *S, floa
  * (Include/dsp/transform_functions.h:508-521,566-617 q15, :655-668,694-745 q31).  fftLenReal in {32..8192}.
  * Buffers as in the reference: forward reads fftLenReal scalars and writes 2*fftLenReal (all fftLenReal
  * complex bins, conjugate half included); inverse reads bins 0..fftLenReal/2 and writes fftLenReal scalars.
- * bitReverseFlagR = 1 is the supported mode (natural-order spectrum); with 0 the exec functions do nothing
- * and report ARM_MATH_ARGUMENT_ERROR through arm_cuda_last_status(). */
+ * bitReverseFlagR is handed to the complex transform inside, as in the reference (arm_rfft_q31.c:164,173): with 0 that
+ * transform's result stays in bit-reversed order. */
 typedef struct
 {
           uint32_t fftLenReal;                /* length of the real FFT */
@@ -301,8 +301,9 @@ arm_status arm_mfcc_batch_f32(const arm_mfcc_instance_f32 *S, const float32_t *p
  *
  * nFrames frames stored back to back (frame stride 2*fftLen scalars for CFFT, fftLenRFFT
  * floats for RFFT), transformed exactly as nFrames calls of the single-frame function.
- * Returns ARM_MATH_SUCCESS, or ARM_MATH_ARGUMENT_ERROR for a NULL / unsupported instance
- * or a CUDA failure (text in cmsisdsp_cuda_last_error()).
+ * Returns ARM_MATH_SUCCESS; ARM_MATH_ARGUMENT_ERROR for a NULL / unsupported instance or buffer; ARM_MATH_CUDA_NO_DEVICE,
+ * ARM_MATH_CUDA_NO_PLAN or ARM_MATH_CUDA_RUNTIME_ERROR (arm_math_types.h) when the device side failed (text in
+ * cmsisdsp_cuda_last_error()).
  * arm_rfft_fast_batch_f32 leaves p untouched in both directions (the single-frame forward
  * call keeps the reference's documented side effect: p then holds the N/2-point CFFT). */
 arm_status arm_cfft_batch_f32(const arm_cfft_instance_f32 *S, float32_t *p, uint32_t nFrames,
@@ -338,6 +339,24 @@ arm_status arm_rfft_batch_q31(const arm_rfft_instance_q31 *S, const q31_t *pSrc,
 arm_status arm_rfft_batch_q15(const arm_rfft_instance_q15 *S, const q15_t *pSrc, q15_t *pDst, uint32_t nFrames);
 /* status of the most recent legacy (void) exec call on this thread */
 arm_status arm_cuda_last_status(void);
+
+/* ---------------------------------------------------------------- B200 extension: devices
+ *
+ * Device buffers: a call runs on the device that owns the buffers.  Host buffers: the frame range of a batched call
+ * is block-partitioned over the device list -- device g of G gets frames [g*ceil(B/G), min(B, (g+1)*ceil(B/G))) --
+ * one host thread, stream set and table cache per device, nothing exchanged between devices (frames are independent).
+ * The list is, in this order: arm_cuda_set_devices(); the environment variable CMSISDSP_CUDA_DEVICES ("all" or a comma
+ * list of ordinals); every visible device, the calling thread's current one first.  Small calls (under 8 MiB per
+ * device) use fewer devices; a single-frame legacy call always runs on the first one. */
+arm_status arm_cuda_set_devices(const int32_t *devices, uint32_t nDevices);      /* nDevices = 0: back to the default */
+uint32_t   arm_cuda_get_devices(int32_t *devices, uint32_t maxDevices);          /* returns the list's length */
+/* host buffers travel in chunks of chunkMiB MiB over nStreams streams per device (0 = leave unchanged; defaults 32 and
+ * 3, or CMSISDSP_CUDA_CHUNK_MIB / CMSISDSP_CUDA_NSTREAMS) */
+arm_status arm_cuda_set_staging(uint32_t chunkMiB, uint32_t nStreams);
+/* frees the calling thread's streams and staging buffers (also done when the thread exits) */
+void       arm_cuda_release(void);
+/* frees the cached device copies of MFCC coefficient sets (no MFCC call may be in flight) */
+void       arm_mfcc_release_plans(void);
 
 #ifdef __cplusplus
 }

@@ -160,7 +160,8 @@ def test_shared_objects_export_every_declared_symbol():
     # 4x(9 per-length inits + init + exec) [f32, q31, q15, f64] + 2 x rfft (8+1+1) [f32, f64] + 6 batch + last_status + mfcc (8+1+1+1)
     # + rfft_q31/q15 (init, exec, batch each; their per-length inits are declared through a macro)
     # + 3 fused spectrum epilogues (mag, mag squared, peak) + deprecated radix-4/2 API (4 x (init, exec, batch))
-    assert len(names) == 103
+    # + device list / staging / release (arm_cuda_set_devices, _get_devices, _set_staging, _release, arm_mfcc_release_plans)
+    assert len(names) == 108
     for name in names:
         assert hasattr(fr, name), name
     for N in RFIX_LENGTHS:
@@ -181,7 +182,7 @@ def test_shard_partition():
 
 
 def test_no_cpu_fallback_without_a_device():
-    """Without a CUDA device every exec entry point must FAIL (ARM_MATH_ARGUMENT_ERROR / a latched status), never
+    """Without a CUDA device every exec entry point must FAIL (ARM_MATH_CUDA_NO_DEVICE, returned or latched), never
     compute on the CPU: the buffers stay untouched.  Skipped where a GPU is visible."""
     cu, L = cd.cuda(), cd.lib()
     if cu.cmsisdsp_cuda_device_count() > 0:
@@ -189,31 +190,31 @@ def test_no_cpu_fallback_without_a_device():
     x = np.arange(2 * 64, dtype=np.float32)
     x0 = x.copy()
     S = cd.cfft_instance("f32", 64)
-    assert L.arm_cfft_batch_f32(C.byref(S), x.ctypes.data, 1, 0, 1) == cd.ARM_MATH_ARGUMENT_ERROR
+    assert L.arm_cfft_batch_f32(C.byref(S), x.ctypes.data, 1, 0, 1) == cd.ARM_MATH_CUDA_NO_DEVICE
     L.arm_cfft_f32(C.byref(S), x.ctypes.data, 0, 1)
-    assert L.arm_cuda_last_status() == cd.ARM_MATH_ARGUMENT_ERROR and np.array_equal(x, x0)
+    assert L.arm_cuda_last_status() == cd.ARM_MATH_CUDA_NO_DEVICE and np.array_equal(x, x0)
     out = np.zeros(64, dtype=np.float32)
     R = cd.rfft_instance(64)
-    assert L.arm_rfft_fast_batch_f32(C.byref(R), x.ctypes.data, out.ctypes.data, 1, 0) == cd.ARM_MATH_ARGUMENT_ERROR
-    assert L.arm_cfft_mag_batch_f32(C.byref(S), x.ctypes.data, out.ctypes.data, 1, 0) == cd.ARM_MATH_ARGUMENT_ERROR
+    assert L.arm_rfft_fast_batch_f32(C.byref(R), x.ctypes.data, out.ctypes.data, 1, 0) == cd.ARM_MATH_CUDA_NO_DEVICE
+    assert L.arm_cfft_mag_batch_f32(C.byref(S), x.ctypes.data, out.ctypes.data, 1, 0) == cd.ARM_MATH_CUDA_NO_DEVICE
     idx = np.zeros(1, dtype=np.uint32)
-    assert L.arm_cfft_peak_batch_f32(C.byref(S), x.ctypes.data, out.ctypes.data, idx.ctypes.data, 1, 0) == cd.ARM_MATH_ARGUMENT_ERROR
+    assert L.arm_cfft_peak_batch_f32(C.byref(S), x.ctypes.data, out.ctypes.data, idx.ctypes.data, 1, 0) == cd.ARM_MATH_CUDA_NO_DEVICE
     for kind in ("q31", "q15"):
         xi = np.arange(2 * 64, dtype=cd.NP_DTYPE[kind])
         Si = cd.cfft_instance(kind, 64)
-        assert getattr(L, f"arm_cfft_batch_{kind}")(C.byref(Si), xi.ctypes.data, 1, 0, 1) == cd.ARM_MATH_ARGUMENT_ERROR
+        assert getattr(L, f"arm_cfft_batch_{kind}")(C.byref(Si), xi.ctypes.data, 1, 0, 1) == cd.ARM_MATH_CUDA_NO_DEVICE
         Sr = cd.rfft_fix_instance(kind, 64)
         oi = np.zeros(128, dtype=cd.NP_DTYPE[kind])
-        assert getattr(L, f"arm_rfft_batch_{kind}")(C.byref(Sr), xi.ctypes.data, oi.ctypes.data, 1) == cd.ARM_MATH_ARGUMENT_ERROR
+        assert getattr(L, f"arm_rfft_batch_{kind}")(C.byref(Sr), xi.ctypes.data, oi.ctypes.data, 1) == cd.ARM_MATH_CUDA_NO_DEVICE
         assert not oi.any()
     xd = np.arange(2 * 64, dtype=np.float64)
     Sd = cd.cfft_instance("f64", 64)
-    assert L.arm_cfft_batch_f64(C.byref(Sd), xd.ctypes.data, 1, 0, 1) == cd.ARM_MATH_ARGUMENT_ERROR
+    assert L.arm_cfft_batch_f64(C.byref(Sd), xd.ctypes.data, 1, 0, 1) == cd.ARM_MATH_CUDA_NO_DEVICE
     L.arm_cfft_f64(C.byref(Sd), xd.ctypes.data, 0, 1)
-    assert L.arm_cuda_last_status() == cd.ARM_MATH_ARGUMENT_ERROR and np.array_equal(xd, np.arange(2 * 64, dtype=np.float64))
+    assert L.arm_cuda_last_status() == cd.ARM_MATH_CUDA_NO_DEVICE and np.array_equal(xd, np.arange(2 * 64, dtype=np.float64))
     Rd = cd.rfft_f64_instance(64)
     od = np.zeros(64)
-    assert L.arm_rfft_fast_batch_f64(C.byref(Rd), xd.ctypes.data, od.ctypes.data, 1, 0) == cd.ARM_MATH_ARGUMENT_ERROR and not od.any()
+    assert L.arm_rfft_fast_batch_f64(C.byref(Rd), xd.ctypes.data, od.ctypes.data, 1, 0) == cd.ARM_MATH_CUDA_NO_DEVICE and not od.any()
     bad64 = cd.arm_rfft_fast_instance_f64()
     for badlen in (0, 16, 48, 8192):
         assert L.arm_rfft_fast_init_f64(C.byref(bad64), badlen) == cd.ARM_MATH_ARGUMENT_ERROR

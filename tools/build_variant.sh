@@ -6,9 +6,9 @@
 set -e
 name=$1; flags=$2; ops=$3; lens=${4:-"16 32 64 128 256 512 1024 2048 4096"}
 cd "$(dirname "$0")/../cmsis-dsp_b200/csrc"
-B=../build_$name; L=../lib_$name
+B=../build/var_$name; L=../lib_$name
 mkdir -p $B $L
-cp -u ../build/*.o $B/
+cp -u ../build/*.o $B/ 2>/dev/null || true
 for op in $ops; do for n in $lens; do
   [ -f ../build/ku_${op}_${n}.o ] || continue
   ( nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --compiler-options -fPIC -Xptxas -v -I../../include -Icuda \
