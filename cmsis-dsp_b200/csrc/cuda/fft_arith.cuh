@@ -408,13 +408,20 @@ struct ArithQ31 {
  * of that.  x >> k is the upper word of the 64-bit product x * 2^(32-k), an IMAD.WIDE -- provided the factor is not
  * a compile-time constant (the compiler turns it back into a shift), so it lives in constant memory. */
 #if defined(__CUDACC__)
-static __constant__ int32_t g_shr_mul[3] = {1 << 16, 1 << 30, (int32_t)0x80000000u};   /* >> 16, >> 2, and -(x) >> 1 */
+static __constant__ int32_t g_shr_mul[5] = {1 << 16, 1 << 30, (int32_t)0x80000000u, 1, -1};   /* >> 16, >> 2, -(x) >> 1; +1, -1 */
 #endif
 #if !defined(__CUDA_ARCH__)
 /* host (the kernel emulator of the CPU tests): the same factors, so the emulator checks these very formulas */
-static const int32_t g_shr_mul_host[3] = {1 << 16, 1 << 30, (int32_t)0x80000000u};
+static const int32_t g_shr_mul_host[5] = {1 << 16, 1 << 30, (int32_t)0x80000000u, 1, -1};
 #define g_shr_mul g_shr_mul_host
 #endif
+/* a + b and a - b pinned to the FMA pipe (IMAD by a +-1 the compiler cannot see): ptxas balances adds between the
+ * pipes by its own model and leaves a third of them on the ALU pipe, which is the one these kernels saturate */
+#ifndef FFT_Q15_FMA_ADDS
+#define FFT_Q15_FMA_ADDS 1           /* measured (profiles/r2_notes.md): +2..5 points of HBM peak at every length */
+#endif
+FFT_HD int32_t qadd(int32_t a, int32_t b) { return FFT_Q15_FMA_ADDS ? a * g_shr_mul[3] + b : a + b; }
+FFT_HD int32_t qsub(int32_t a, int32_t b) { return FFT_Q15_FMA_ADDS ? b * g_shr_mul[4] + a : a - b; }
 FFT_HD int32_t shr16_fma(int32_t v) { return hi32_fma(v, g_shr_mul[0]); }
 FFT_HD int32_t shr2_fma(int32_t v) { return hi32_fma(v, g_shr_mul[1]); }
 
@@ -534,16 +541,16 @@ struct ArithQ15 {
             /* inputs >> 2 (plain, unbiased): nothing below can saturate or wrap (see the header of this section) */
             const int32_t T0 = PRE ? A.x : A.x >> 2, T1 = PRE ? A.y : A.y >> 2, C0 = PRE ? C.x : C.x >> 2, C1 = PRE ? C.y : C.y >> 2;
             const int32_t B0 = PRE ? B.x : B.x >> 2, B1 = PRE ? B.y : B.y >> 2, U0 = PRE ? D.x : D.x >> 2, U1 = PRE ? D.y : D.y >> 2;
-            const int32_t R0 = T0 + C0, R1 = T1 + C1, S0 = T0 - C0, S1 = T1 - C1;
-            const int32_t V0 = B0 + U0, V1 = B1 + U1, D0 = B0 - U0, D1 = B1 - U1;
+            const int32_t R0 = qadd(T0, C0), R1 = qadd(T1, C1), S0 = qsub(T0, C0), S1 = qsub(T1, C1);
+            const int32_t V0 = qadd(B0, U0), V1 = qadd(B1, U1), D0 = qsub(B0, U0), D1 = qsub(B1, U1);
             A = {(R0 >> 1) + (V0 >> 1) + ob, (R1 >> 1) + (V1 >> 1) + ob};
-            C = rot_q15<INV, kAluShift(TAIL)>(R0 - V0, R1 - V1, w2, ob);
+            C = rot_q15<INV, kAluShift(TAIL)>(qsub(R0, V0), qsub(R1, V1), w2, ob);
             if (!INV) {
-                B = rot_q15<INV, kAluShift(TAIL)>(S0 + D1, S1 - D0, w1, ob);
-                D = rot_q15<INV, kAluShift(TAIL)>(S0 - D1, S1 + D0, w3, ob);
+                B = rot_q15<INV, kAluShift(TAIL)>(qadd(S0, D1), qsub(S1, D0), w1, ob);
+                D = rot_q15<INV, kAluShift(TAIL)>(qsub(S0, D1), qadd(S1, D0), w3, ob);
             } else {
-                B = rot_q15<INV, kAluShift(TAIL)>(S0 - D1, S1 + D0, w1, ob);
-                D = rot_q15<INV, kAluShift(TAIL)>(S0 + D1, S1 - D0, w3, ob);
+                B = rot_q15<INV, kAluShift(TAIL)>(qsub(S0, D1), qadd(S1, D0), w1, ob);
+                D = rot_q15<INV, kAluShift(TAIL)>(qadd(S0, D1), qsub(S1, D0), w3, ob);
             }
             return;
         }
@@ -553,19 +560,19 @@ struct ArithQ15 {
         const int32_t V0 = half_sat_add16(B.x, D.x), V1 = half_sat_add16(B.y, D.y);
         const int32_t D0 = half_sat_sub16(B.x, D.x), D1 = half_sat_sub16(B.y, D.y);
         if (KIND == ST_MID4) {
-            A = {((R0 + V0) >> 1) + ob, ((R1 + V1) >> 1) + ob};
-            C = rot_q15<INV, kAluShift(TAIL)>(R0 - V0, R1 - V1, w2, ob);
+            A = {(qadd(R0, V0) >> 1) + ob, (qadd(R1, V1) >> 1) + ob};
+            C = rot_q15<INV, kAluShift(TAIL)>(qsub(R0, V0), qsub(R1, V1), w2, ob);
             if (!INV) {
-                B = rot_q15<INV, kAluShift(TAIL)>(S0 + D1, S1 - D0, w1, ob);
-                D = rot_q15<INV, kAluShift(TAIL)>(S0 - D1, S1 + D0, w3, ob);
+                B = rot_q15<INV, kAluShift(TAIL)>(qadd(S0, D1), qsub(S1, D0), w1, ob);
+                D = rot_q15<INV, kAluShift(TAIL)>(qsub(S0, D1), qadd(S1, D0), w3, ob);
             } else {
-                B = rot_q15<INV, kAluShift(TAIL)>(S0 - D1, S1 + D0, w1, ob);
-                D = rot_q15<INV, kAluShift(TAIL)>(S0 + D1, S1 - D0, w3, ob);
+                B = rot_q15<INV, kAluShift(TAIL)>(qsub(S0, D1), qadd(S1, D0), w1, ob);
+                D = rot_q15<INV, kAluShift(TAIL)>(qadd(S0, D1), qsub(S1, D0), w3, ob);
             }
         } else {
-            A = {R0 + V0, R1 + V1};
-            C = {R0 - V0, R1 - V1};
-            const work p = {S0 + D1, S1 - D0}, q = {S0 - D1, S1 + D0};
+            A = {qadd(R0, V0), qadd(R1, V1)};
+            C = {qsub(R0, V0), qsub(R1, V1)};
+            const work p = {qadd(S0, D1), qsub(S1, D0)}, q = {qsub(S0, D1), qadd(S1, D0)};
             B = INV ? q : p;
             D = INV ? p : q;
         }

@@ -34,7 +34,7 @@ typedef struct {
     void *buf[MAXS][NBUF];
     size_t cap[MAXS][NBUF];
 } dev_ctx;
-typedef struct { dev_ctx w[MAXW + 1]; } ctx_pool;     /* [MAXW]: the device-pointer path */
+typedef struct { dev_ctx w[MAXW]; } ctx_pool;
 
 static struct {
     pthread_mutex_t mu;
@@ -163,7 +163,7 @@ static void pool_free(void *p)
 {
     ctx_pool *pool = (ctx_pool *)p;
     if (!pool) return;
-    for (int w = 0; w <= MAXW; w++)
+    for (int w = 0; w < MAXW; w++)
         if (pool->w[w].device >= 0) ctx_release(&pool->w[w]);
     free(pool);
 }
@@ -175,7 +175,7 @@ static ctx_pool *pool_get(void)
     if (!pool) {
         pool = (ctx_pool *)calloc(1, sizeof *pool);
         if (!pool) return 0;
-        for (int w = 0; w <= MAXW; w++) pool->w[w].device = -1;
+        for (int w = 0; w < MAXW; w++) pool->w[w].device = -1;
         pthread_setspecific(g_key, pool);
     }
     return pool;
@@ -331,18 +331,18 @@ arm_status arm_cuda_run_device(const arm_cuda_job *job, const void *in, void *ou
     if (nFrames == 0) return ARM_MATH_SUCCESS;
     const int dev = cmsisdsp_cuda_pointer_device(in);
     if (dev < 0) return ARM_MATH_ARGUMENT_ERROR;
-    ctx_pool *pool = pool_get();
-    if (!pool) return ARM_MATH_CUDA_RUNTIME_ERROR;
     const int cur = cmsisdsp_cuda_get_device();
     if (cur < 0) return ARM_MATH_CUDA_NO_DEVICE;
     int rc = 0;
     if (cur != dev) rc = cmsisdsp_cuda_set_device(dev);        /* the call runs where the data is */
-    dev_ctx *c = &pool->w[MAXW];
-    if (!rc) rc = ctx_ensure(c, dev, 1);
+    /* The legacy default stream: the transform is ordered after whatever the caller enqueued on that stream or on
+     * any blocking stream (a cudaMemcpy, a kernel that produced the frames), as a C caller expects of a function
+     * that takes device buffers; the library's own streams are non-blocking and would race with such work. */
+    void *const st = 0;
     if (!rc) rc = job->prepare(job);
-    if (!rc) rc = job->launch(job, in, out, job->outB, nFrames, c->stream[0]);
-    if (!rc && job->out2 && job->post) rc = job->post(job, (void *)in, nFrames, c->stream[0]);
-    if (!rc) rc = cmsisdsp_cuda_stream_synchronize(c->stream[0]);
+    if (!rc) rc = job->launch(job, in, out, job->outB, nFrames, st);
+    if (!rc && job->out2 && job->post) rc = job->post(job, (void *)in, nFrames, st);
+    if (!rc) rc = cmsisdsp_cuda_stream_synchronize(st);
     if (cur != dev) cmsisdsp_cuda_set_device(cur);
     return arm_cuda_status_of(rc);
 }

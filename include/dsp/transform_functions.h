@@ -342,7 +342,9 @@ arm_status arm_cuda_last_status(void);
 
 /* ---------------------------------------------------------------- B200 extension: devices
  *
- * Device buffers: a call runs on the device that owns the buffers.  Host buffers: the frame range of a batched call
+ * Device buffers: a call runs on the device that owns the buffers, enqueued on the legacy default stream (so it is
+ * ordered after the caller's earlier work on that stream or on any blocking stream) and returns when the result is
+ * there.  Host buffers: the frame range of a batched call
  * is block-partitioned over the device list -- device g of G gets frames [g*ceil(B/G), min(B, (g+1)*ceil(B/G))) --
  * one host thread, stream set and table cache per device, nothing exchanged between devices (frames are independent).
  * The list is, in this order: arm_cuda_set_devices(); the environment variable CMSISDSP_CUDA_DEVICES ("all" or a comma
