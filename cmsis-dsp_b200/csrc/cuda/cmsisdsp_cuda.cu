@@ -150,7 +150,8 @@ struct Slot {
     DevPlan plan;                               /* cfft kinds */
     void *table = nullptr;                      /* rfft twiddles / split coefficients */
 };
-enum TableKind { TK_PLAN_F32 = 0, TK_PLAN_Q31, TK_PLAN_Q15, TK_PLAN_F64, TK_TWR_F32, TK_TWR_F64, TK_RCOEF_Q31, TK_RCOEF_Q15, TK_COUNT };
+enum TableKind { TK_PLAN_F32 = 0, TK_PLAN_Q31, TK_PLAN_Q15, TK_PLAN_F64, TK_TWR_F32, TK_TWR_F64, TK_RCOEF_Q31, TK_RCOEF_Q15,
+                 TK_R2TW_Q31, TK_R2TW_Q15, TK_COUNT };
 struct DevState {
     Slot slot[TK_COUNT][9][kSlots];
     uint16_t *bitrev[9] = {};     /* plain binary bit reversal of 0..N-1 (cfft_f32 in bit-reversed output order) */
@@ -612,6 +613,60 @@ extern "C" int cmsisdsp_cuda_rfft_q31(const void *d_src, void *d_dst, uint32_t f
 extern "C" int cmsisdsp_cuda_rfft_q15(const void *d_src, void *d_dst, uint32_t fftLenReal, uint64_t nFrames, uint8_t ifftFlagR,
                                       uint8_t bitReverseFlagR, void *stream)
 { return rfft_fix(CMSISDSP_CUDA_Q15, d_src, d_dst, fftLenReal, nFrames, ifftFlagR, bitReverseFlagR, stream); }
+
+/* ------------------------------------------------------------------ deprecated fixed-point radix-2 (radix2_fix.cu) */
+namespace b200fft { int shim_radix2_launch(int type, void *d_p, uint32_t N, uint64_t nFrames, int inv, const void *tw, cudaStream_t st); }
+
+/* pCoef / twidCoefModifier as in arm_cfft_radix2_instance_q31 / _q15: entry k * modifier of the table is W_fftLen^k */
+extern "C" int cmsisdsp_cuda_radix2_plan_upload(int type, uint32_t fftLen, const void *pCoef, uint32_t twidCoefModifier)
+{
+    const int li = len_index(fftLen);
+    if ((type != CMSISDSP_CUDA_Q31 && type != CMSISDSP_CUDA_Q15) || li < 0 || !pCoef || twidCoefModifier == 0 ||
+        (uint64_t)twidCoefModifier * fftLen > 4096u)
+        return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "radix2_plan_upload: bad type / length / pointer / modifier");
+    int dev;
+    int rc = cur_device(&dev);
+    if (rc) return rc;
+    const int kind = type == CMSISDSP_CUDA_Q31 ? TK_R2TW_Q31 : TK_R2TW_Q15;
+    const size_t scalar = type == CMSISDSP_CUDA_Q31 ? 4 : 2;
+    const uint32_t half = fftLen / 2;
+    const size_t span = ((size_t)2 * (half - 1) * twidCoefModifier + 2) * scalar;      /* the part of the table that is read */
+    std::lock_guard<std::mutex> lk(g_mu);
+    Slot *slots = g_dev[dev].slot[kind][li];
+    bool fresh;
+    uint32_t fp = 0;
+    uint64_t hash = 0;
+    const int s = find_slot(slots, pCoef, span, nullptr, 0, twidCoefModifier, &fresh, &fp, &hash);
+    if (s < 0) return s;
+    t_cur[dev][kind][li] = (uint8_t)s;
+    if (!fresh) return CMSISDSP_CUDA_OK;
+    std::vector<int32_t> tw((size_t)half * 2);
+    for (uint32_t k = 0; k < half; k++) {
+        const size_t e = (size_t)2 * k * twidCoefModifier;
+        if (type == CMSISDSP_CUDA_Q31) { tw[2 * k] = ((const int32_t *)pCoef)[e]; tw[2 * k + 1] = ((const int32_t *)pCoef)[e + 1]; }
+        else                           { tw[2 * k] = ((const int16_t *)pCoef)[e]; tw[2 * k + 1] = ((const int16_t *)pCoef)[e + 1]; }
+    }
+    rc = upload_raw(tw.data(), tw.size() * sizeof(int32_t), &slots[s].table);
+    if (rc) return rc;
+    claim(slots[s], pCoef, nullptr, twidCoefModifier, fp, hash);
+    return CMSISDSP_CUDA_OK;
+}
+static int radix2_fix(int type, void *d_p, uint32_t fftLen, uint64_t nFrames, uint8_t ifftFlag, void *stream)
+{
+    if (!d_p && nFrames) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "null data pointer");
+    const int li = len_index(fftLen);
+    if (li < 0) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "unsupported fftLen (16..4096, power of two)");
+    if (misaligned(d_p, elem_align(type))) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "cfft_radix2: device data must be aligned to one complex element");
+    const void *tw = nullptr;
+    int rc = get_table(type == CMSISDSP_CUDA_Q31 ? TK_R2TW_Q31 : TK_R2TW_Q15, li, &tw, "no radix-2 plan uploaded for this (device, type, fftLen)");
+    if (rc) return rc;
+    if ((size_t)fftLen * 8 > 48 * 1024) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "cfft_radix2: frame does not fit the kernel's shared memory");
+    return shim_radix2_launch(type, d_p, fftLen, nFrames, ifftFlag == 1, tw, (cudaStream_t)stream);
+}
+extern "C" int cmsisdsp_cuda_cfft_radix2_q31(void *d_p, uint32_t fftLen, uint64_t nFrames, uint8_t ifftFlag, void *stream)
+{ return radix2_fix(CMSISDSP_CUDA_Q31, d_p, fftLen, nFrames, ifftFlag, stream); }
+extern "C" int cmsisdsp_cuda_cfft_radix2_q15(void *d_p, uint32_t fftLen, uint64_t nFrames, uint8_t ifftFlag, void *stream)
+{ return radix2_fix(CMSISDSP_CUDA_Q15, d_p, fftLen, nFrames, ifftFlag, stream); }
 
 extern "C" int cmsisdsp_cuda_kernel_info(int op, uint32_t fftLen, int *threads, int *frames, int *smem, int *regs, int *ctasPerSm)
 {

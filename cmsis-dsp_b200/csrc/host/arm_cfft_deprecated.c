@@ -11,6 +11,8 @@
  * arm_radix4_butterfly_q31 with the per-length table, whose entries are the strided entries of the 4096-point one).
  */
 #include "arm_const_structs.h"
+#include "cmsisdsp_cuda.h"
+#include "arm_cuda_engine.h"
 
 arm_status arm_cuda_set_last_status(arm_status s);
 
@@ -35,6 +37,8 @@ DEPR_INIT(arm_cfft_radix4_init_q15, arm_cfft_radix4_instance_q15, twiddleCoef_40
 DEPR_INIT(arm_cfft_radix4_init_q31, arm_cfft_radix4_instance_q31, twiddleCoef_4096_q31, radix4_len, (void)0)
 DEPR_INIT(arm_cfft_radix4_init_f32, arm_cfft_radix4_instance_f32, twiddleCoef, radix4_len, S->onebyfftLen = 1.0f / (float32_t)fftLen)
 DEPR_INIT(arm_cfft_radix2_init_f32, arm_cfft_radix2_instance_f32, twiddleCoef, radix2_len, S->onebyfftLen = 1.0f / (float32_t)fftLen)
+DEPR_INIT(arm_cfft_radix2_init_q31, arm_cfft_radix2_instance_q31, twiddleCoef_4096_q31, radix2_len, (void)0)
+DEPR_INIT(arm_cfft_radix2_init_q15, arm_cfft_radix2_instance_q15, twiddleCoef_4096_q15, radix2_len, (void)0)
 
 arm_status arm_cfft_radix4_batch_q15(const arm_cfft_radix4_instance_q15 *S, q15_t *p, uint32_t nFrames)
 {
@@ -66,3 +70,42 @@ void arm_cfft_radix4_q15(const arm_cfft_radix4_instance_q15 *S, q15_t *pSrc) { a
 void arm_cfft_radix4_q31(const arm_cfft_radix4_instance_q31 *S, q31_t *pSrc) { arm_cuda_set_last_status(arm_cfft_radix4_batch_q31(S, pSrc, 1)); }
 void arm_cfft_radix4_f32(const arm_cfft_radix4_instance_f32 *S, float32_t *pSrc) { arm_cuda_set_last_status(arm_cfft_radix4_batch_f32(S, pSrc, 1)); }
 void arm_cfft_radix2_f32(const arm_cfft_radix2_instance_f32 *S, float32_t *pSrc) { arm_cuda_set_last_status(arm_cfft_radix2_batch_f32(S, pSrc, 1)); }
+
+/* ---- arm_cfft_radix2_q31 / _q15: log2(N) radix-2 stages with their own scaling (not the arm_cfft_q31 computation), own kernel ---- */
+typedef struct { int type; uint32_t N; const void *tw; uint32_t modifier; uint8_t ifftFlag; } r2_args;
+static int r2_prepare(const arm_cuda_job *job)
+{
+    const r2_args *a = (const r2_args *)job->self;
+    return cmsisdsp_cuda_radix2_plan_upload(a->type, a->N, a->tw, a->modifier);
+}
+static int r2_launch(const arm_cuda_job *job, const void *din, void *dout, void *doutB, uint64_t n, void *stream)
+{
+    const r2_args *a = (const r2_args *)job->self;
+    (void)din; (void)doutB;
+    return a->type == CMSISDSP_CUDA_Q31 ? cmsisdsp_cuda_cfft_radix2_q31(dout, a->N, n, a->ifftFlag, stream)
+                                        : cmsisdsp_cuda_cfft_radix2_q15(dout, a->N, n, a->ifftFlag, stream);
+}
+static arm_status r2_batch(int type, size_t scalarBytes, uint16_t fftLen, const void *tw, uint16_t modifier, uint8_t ifftFlag, void *p, uint32_t nFrames)
+{
+    if (!p || !tw || !radix2_len(fftLen) || modifier == 0 || (uint32_t)modifier * fftLen > 4096U) return ARM_MATH_ARGUMENT_ERROR;
+    const r2_args a = { type, fftLen, tw, modifier, ifftFlag };
+    arm_cuda_job job = {0};
+    job.inStride = job.inFrame = job.outStride = job.outFrame = (size_t)2 * fftLen * scalarBytes;
+    job.inPlace = 1;
+    job.prepare = r2_prepare;
+    job.launch = r2_launch;
+    job.self = &a;
+    return arm_cuda_run(&job, p, p, nFrames);
+}
+arm_status arm_cfft_radix2_batch_q31(const arm_cfft_radix2_instance_q31 *S, q31_t *p, uint32_t nFrames)
+{
+    if (!S) return ARM_MATH_ARGUMENT_ERROR;
+    return r2_batch(CMSISDSP_CUDA_Q31, sizeof(q31_t), S->fftLen, S->pTwiddle, S->twidCoefModifier, S->ifftFlag, p, nFrames);
+}
+arm_status arm_cfft_radix2_batch_q15(const arm_cfft_radix2_instance_q15 *S, q15_t *p, uint32_t nFrames)
+{
+    if (!S) return ARM_MATH_ARGUMENT_ERROR;
+    return r2_batch(CMSISDSP_CUDA_Q15, sizeof(q15_t), S->fftLen, S->pTwiddle, S->twidCoefModifier, S->ifftFlag, p, nFrames);
+}
+void arm_cfft_radix2_q31(const arm_cfft_radix2_instance_q31 *S, q31_t *pSrc) { arm_cuda_set_last_status(arm_cfft_radix2_batch_q31(S, pSrc, 1)); }
+void arm_cfft_radix2_q15(const arm_cfft_radix2_instance_q15 *S, q15_t *pSrc) { arm_cuda_set_last_status(arm_cfft_radix2_batch_q15(S, pSrc, 1)); }

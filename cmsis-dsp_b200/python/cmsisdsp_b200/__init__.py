@@ -126,6 +126,8 @@ def cuda():
         "cmsisdsp_cuda_rfft_fix_plan_upload": ([i, u32, vp, vp, u32], i), "cmsisdsp_cuda_rfft_fix_plan_ready": ([i, u32], i),
         "cmsisdsp_cuda_rfft_q31": ([vp, vp, u32, u64, u8, u8, vp], i), "cmsisdsp_cuda_rfft_q15": ([vp, vp, u32, u64, u8, u8, vp], i),
         "cmsisdsp_cuda_cfft_f32_bitrev_order": ([vp, u32, u64, u8, vp], i), "cmsisdsp_cuda_pointer_device": ([vp], i),
+        "cmsisdsp_cuda_radix2_plan_upload": ([i, u32, vp, u32], i),
+        "cmsisdsp_cuda_cfft_radix2_q31": ([vp, u32, u64, u8, vp], i), "cmsisdsp_cuda_cfft_radix2_q15": ([vp, u32, u64, u8, vp], i),
         "cmsisdsp_cuda_cfft_mag_f32": ([vp, vp, u32, u64, u8, u8, vp], i), "cmsisdsp_cuda_cfft_peak_f32": ([vp, vp, vp, u32, u64, u8, vp], i),
         "cmsisdsp_cuda_last_error": ([], C.c_char_p), "cmsisdsp_cuda_launch_count": ([], u64),
         "cmsisdsp_cuda_set_kernel_flavour": ([i], i),
@@ -183,7 +185,7 @@ def lib():
         f.argtypes, f.restype = [C.POINTER(arm_cfft_instance_f32), C.c_void_p, C.c_void_p, u32, u8], i
     L.arm_cfft_peak_batch_f32.argtypes = [C.POINTER(arm_cfft_instance_f32), C.c_void_p, C.c_void_p, C.c_void_p, u32, u8]
     L.arm_cfft_peak_batch_f32.restype = i
-    for name, k in (("radix4", "f32"), ("radix4", "q31"), ("radix4", "q15"), ("radix2", "f32")):
+    for name, k in (("radix4", "f32"), ("radix4", "q31"), ("radix4", "q15"), ("radix2", "f32"), ("radix2", "q31"), ("radix2", "q15")):
         inst = RADIX_INSTANCE[k]
         f = getattr(L, f"arm_cfft_{name}_init_{k}")
         f.argtypes, f.restype = [C.POINTER(inst), u16, u8, u8], i

@@ -136,6 +136,14 @@ int  cmsisdsp_cuda_rfft_q31(const void *d_src, void *d_dst, uint32_t fftLenReal,
 int  cmsisdsp_cuda_rfft_q15(const void *d_src, void *d_dst, uint32_t fftLenReal, uint64_t nFrames,
                             uint8_t ifftFlagR, uint8_t bitReverseFlagR, void *stream);
 
+/* ---- deprecated arm_cfft_radix2_q31 / arm_cfft_radix2_q15 (Source/TransformFunctions/arm_cfft_radix2_q31.c:62-318,
+ * arm_cfft_radix2_q15.c:62-78,275-386,577-681): log2(fftLen) radix-2 stages with their own per-stage scaling, then the
+ * bit reversal (always: natural-order result).  pCoef / twidCoefModifier as in the instance (the 4096-point table read
+ * with a stride); in place on nFrames frames of 2*fftLen scalars. ---- */
+int  cmsisdsp_cuda_radix2_plan_upload(int type, uint32_t fftLen, const void *pCoef, uint32_t twidCoefModifier);
+int  cmsisdsp_cuda_cfft_radix2_q31(void *d_p, uint32_t fftLen, uint64_t nFrames, uint8_t ifftFlag, void *stream);
+int  cmsisdsp_cuda_cfft_radix2_q15(void *d_p, uint32_t fftLen, uint64_t nFrames, uint8_t ifftFlag, void *stream);
+
 /* ---- arm_mfcc_f32 front end (Source/TransformFunctions/arm_mfcc_f32.c:88-174, arm_mfcc_init_f32.c:91-121) ----
  * One fused kernel per frame batch: normalise, window, rfft, magnitude, mel filter bank, log, DCT.
  * The plan keeps device copies of the caller's coefficient arrays (the arguments of arm_mfcc_init_f32);

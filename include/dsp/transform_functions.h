@@ -189,6 +189,8 @@ typedef struct
           float32_t  onebyfftLen;
 } arm_cfft_radix4_instance_f32;
 typedef arm_cfft_radix4_instance_f32 arm_cfft_radix2_instance_f32;     /* same fields (transform_functions.h:215-225) */
+typedef arm_cfft_radix4_instance_q31 arm_cfft_radix2_instance_q31;     /* same fields (transform_functions.h:163-172) */
+typedef arm_cfft_radix4_instance_q15 arm_cfft_radix2_instance_q15;     /* same fields (transform_functions.h:110-119) */
 
 arm_status arm_cfft_radix4_init_q15(arm_cfft_radix4_instance_q15 *S, uint16_t fftLen, uint8_t ifftFlag, uint8_t bitReverseFlag);
 arm_status arm_cfft_radix4_init_q31(arm_cfft_radix4_instance_q31 *S, uint16_t fftLen, uint8_t ifftFlag, uint8_t bitReverseFlag);
@@ -198,11 +200,20 @@ void arm_cfft_radix4_q15(const arm_cfft_radix4_instance_q15 *S, q15_t *pSrc);
 void arm_cfft_radix4_q31(const arm_cfft_radix4_instance_q31 *S, q31_t *pSrc);
 void arm_cfft_radix4_f32(const arm_cfft_radix4_instance_f32 *S, float32_t *pSrc);
 void arm_cfft_radix2_f32(const arm_cfft_radix2_instance_f32 *S, float32_t *pSrc);
+/* fixed-point radix-2 (arm_cfft_radix2_q31.c:62-81, arm_cfft_radix2_q15.c:62-78): their own algorithm and scaling, own
+ * kernel; fftLen 16..4096, every power of two; the result is always in natural order (the reference bit-reverses
+ * whatever bitReverseFlag says) */
+arm_status arm_cfft_radix2_init_q31(arm_cfft_radix2_instance_q31 *S, uint16_t fftLen, uint8_t ifftFlag, uint8_t bitReverseFlag);
+arm_status arm_cfft_radix2_init_q15(arm_cfft_radix2_instance_q15 *S, uint16_t fftLen, uint8_t ifftFlag, uint8_t bitReverseFlag);
+void arm_cfft_radix2_q31(const arm_cfft_radix2_instance_q31 *S, q31_t *pSrc);
+void arm_cfft_radix2_q15(const arm_cfft_radix2_instance_q15 *S, q15_t *pSrc);
 /* B200 extension: nFrames contiguous frames */
 arm_status arm_cfft_radix4_batch_q15(const arm_cfft_radix4_instance_q15 *S, q15_t *p, uint32_t nFrames);
 arm_status arm_cfft_radix4_batch_q31(const arm_cfft_radix4_instance_q31 *S, q31_t *p, uint32_t nFrames);
 arm_status arm_cfft_radix4_batch_f32(const arm_cfft_radix4_instance_f32 *S, float32_t *p, uint32_t nFrames);
 arm_status arm_cfft_radix2_batch_f32(const arm_cfft_radix2_instance_f32 *S, float32_t *p, uint32_t nFrames);
+arm_status arm_cfft_radix2_batch_q31(const arm_cfft_radix2_instance_q31 *S, q31_t *p, uint32_t nFrames);
+arm_status arm_cfft_radix2_batch_q15(const arm_cfft_radix2_instance_q15 *S, q15_t *p, uint32_t nFrames);
 
 /* ---------------------------------------------------------------- q15 / q31 RFFT
  * Instance, init and exec are the reference's generic (non-Neon, non-MVE) branch

@@ -198,7 +198,10 @@ void ref_cfft_mag_f32_batch(uint32_t N, const float *src, float *mag, float *val
 int ref_cfft_radix_batch(int kind, int radix, uint32_t N, void *p, uint64_t nFrames, int ifft, int bitrev)
 {
     arm_cfft_radix4_instance_f32 Sf4; arm_cfft_radix2_instance_f32 Sf2; arm_cfft_radix4_instance_q31 S31; arm_cfft_radix4_instance_q15 S15;
+    arm_cfft_radix2_instance_q31 R31; arm_cfft_radix2_instance_q15 R15;
     arm_status st = ARM_MATH_ARGUMENT_ERROR;
+    if (kind == 1 && radix == 2) st = arm_cfft_radix2_init_q31(&R31, (uint16_t)N, (uint8_t)ifft, (uint8_t)bitrev);
+    if (kind == 2 && radix == 2) st = arm_cfft_radix2_init_q15(&R15, (uint16_t)N, (uint8_t)ifft, (uint8_t)bitrev);
     if (kind == 0 && radix == 4) st = arm_cfft_radix4_init_f32(&Sf4, (uint16_t)N, (uint8_t)ifft, (uint8_t)bitrev);
     if (kind == 0 && radix == 2) st = arm_cfft_radix2_init_f32(&Sf2, (uint16_t)N, (uint8_t)ifft, (uint8_t)bitrev);
     if (kind == 1 && radix == 4) st = arm_cfft_radix4_init_q31(&S31, (uint16_t)N, (uint8_t)ifft, (uint8_t)bitrev);
@@ -207,6 +210,8 @@ int ref_cfft_radix_batch(int kind, int radix, uint32_t N, void *p, uint64_t nFra
     for (uint64_t f = 0; f < nFrames; f++) {
         if (kind == 0 && radix == 4) arm_cfft_radix4_f32(&Sf4, (float32_t *)p + 2ull * N * f);
         else if (kind == 0) arm_cfft_radix2_f32(&Sf2, (float32_t *)p + 2ull * N * f);
+        else if (kind == 1 && radix == 2) arm_cfft_radix2_q31(&R31, (q31_t *)p + 2ull * N * f);
+        else if (kind == 2 && radix == 2) arm_cfft_radix2_q15(&R15, (q15_t *)p + 2ull * N * f);
         else if (kind == 1) arm_cfft_radix4_q31(&S31, (q31_t *)p + 2ull * N * f);
         else arm_cfft_radix4_q15(&S15, (q15_t *)p + 2ull * N * f);
     }
@@ -216,6 +221,8 @@ const uint16_t *ref_arm_bit_rev_table(void) { return armBitRevTable; }
 uint32_t ref_sizeof_cfft_radix4_instance_f32(void) { return (uint32_t)sizeof(arm_cfft_radix4_instance_f32); }
 uint32_t ref_sizeof_cfft_radix4_instance_q31(void) { return (uint32_t)sizeof(arm_cfft_radix4_instance_q31); }
 uint32_t ref_sizeof_cfft_radix4_instance_q15(void) { return (uint32_t)sizeof(arm_cfft_radix4_instance_q15); }
+uint32_t ref_sizeof_cfft_radix2_instance_q31(void) { return (uint32_t)sizeof(arm_cfft_radix2_instance_q31); }
+uint32_t ref_sizeof_cfft_radix2_instance_q15(void) { return (uint32_t)sizeof(arm_cfft_radix2_instance_q15); }
 
 /* ---- arm_cfft_f64, frame by frame (single thread: used for parity only) ---- */
 int ref_cfft_f64_batch(uint32_t N, double *p, uint64_t nFrames, int ifft, int bitrev)

@@ -157,6 +157,16 @@ class _Lib:
         assert fn({"f32": 0, "q31": 1, "q15": 2}[kind], radix, N, y.ctypes.data, y.size // (2 * N), int(ifft), int(bitrev)) == 0
         return y
 
+    def cfft_radix2_fix(self, kind, N, x, ifft=0):
+        """deprecated arm_cfft_radix2_q31 / _q15 (oracle restatement; the compiled reference: cfft_radix(kind, 2, ...))"""
+        dt = {"q31": np.int32, "q15": np.int16}[kind]
+        y = np.ascontiguousarray(x, dtype=dt).copy()
+        fn = self._fn(f"cfft_radix2_{kind}_batch")
+        fn.argtypes = [C.c_uint32, C.c_void_p, C.c_uint64, C.c_int]
+        fn.restype = None
+        fn(N, y.ctypes.data, y.size // (2 * N), int(ifft))
+        return y
+
     def real_coef(self, kind, b):
         return np.ctypeslib.as_array(self._fn(f"real_coef_{kind}")(int(b)), shape=(8192,)).copy()
 

@@ -274,6 +274,39 @@ def test_deprecated_f32_radix_api_with_bit_reverse_flag_zero():
                     assert relrms(got.reshape(23, -1), ref().cfft_radix("f32", radix, N, x, ifft, 0)) <= F32_TOL, (radix, N, ifft)
 
 
+@pytest.mark.parametrize("kind", ["q31", "q15"])
+def test_deprecated_fixed_point_radix2_api_bit_exact(kind):
+    """arm_cfft_radix2_q31 / arm_cfft_radix2_q15 (their own algorithm and per-stage scaling: arm_cfft_radix2_q31.c:87-318,
+    arm_cfft_radix2_q15.c:275-386,577-681): memcmp-identical to the oracle restatement -- itself bit-identical to the
+    compiled reference (tests/test_oracle_vs_ref.py) -- for every length, both directions, both values of the (ignored)
+    bitReverseFlag, full-scale frames included; and to the compiled reference directly where it is built"""
+    for N in LENGTHS:
+        x = cfft_input(kind, N, frames=67, seed=N + 5)
+        info = np.iinfo(x.dtype)
+        x[0], x[1] = info.min, info.max
+        x[2, 0::2], x[2, 1::2] = info.min, info.max
+        for ifft in (0, 1):
+            want = oracle().cfft_radix2_fix(kind, N, x, ifft)
+            for bitrev in (1, 0):
+                got = cd.cfft_radix_batch(kind, 2, N, x, ifft, bitrev)
+                assert np.array_equal(got, want), (kind, N, ifft, bitrev)
+            if ref() is not None:
+                assert np.array_equal(want, ref().cfft_radix(kind, 2, N, x, ifft, 1)), (kind, N, ifft)
+    # legacy single-frame call and a device buffer
+    L = cd.lib()
+    S = cd.RADIX_INSTANCE[kind]()
+    assert getattr(L, f"arm_cfft_radix2_init_{kind}")(C.byref(S), 512, 1, 1) == 0
+    assert getattr(L, f"arm_cfft_radix2_init_{kind}")(C.byref(cd.RADIX_INSTANCE[kind]()), 100, 0, 1) == cd.ARM_MATH_ARGUMENT_ERROR
+    x = cfft_input(kind, 512, frames=3, seed=2)
+    y = x[1].copy()
+    getattr(L, f"arm_cfft_radix2_{kind}")(C.byref(S), y.ctypes.data)
+    assert L.arm_cuda_last_status() == 0, cd.last_error()
+    assert np.array_equal(y, oracle().cfft_radix2_fix(kind, 512, x[1], 1).reshape(-1))
+    p, keep = _dev_copy(x, 8 if kind == "q31" else 4)
+    assert getattr(L, f"arm_cfft_radix2_batch_{kind}")(C.byref(S), p, 3, ) == 0, cd.last_error()
+    assert np.array_equal(_back(keep, x.dtype, x.shape), oracle().cfft_radix2_fix(kind, 512, x, 1))
+
+
 # ------------------------------------------------------------------ plan cache keyed by table content
 
 def test_a_second_instance_with_other_tables_gets_its_own_plan():

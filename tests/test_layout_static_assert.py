@@ -33,6 +33,7 @@ STRUCTS = {
     "arm_rfft_instance_q15": RFIX, "arm_rfft_instance_q31": RFIX,
     "arm_cfft_radix4_instance_q15": RADIX, "arm_cfft_radix4_instance_q31": RADIX,
     "arm_cfft_radix4_instance_f32": RADIX + ["onebyfftLen"], "arm_cfft_radix2_instance_f32": RADIX + ["onebyfftLen"],
+    "arm_cfft_radix2_instance_q15": RADIX, "arm_cfft_radix2_instance_q31": RADIX,
     "arm_mfcc_instance_f32": ["dctCoefs", "filterCoefs", "windowCoefs", "filterPos", "filterLengths", "fftLen", "nbMelFilters",
                               "nbDctOutputs", "rfft"],
 }

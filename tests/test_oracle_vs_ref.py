@@ -170,3 +170,17 @@ def test_rfft_fast_f64_bit_exact_on_the_reference_tables(N):
         assert np.array_equal(oracle().rfft_f64(N, x, ifft, tc, tr).view(np.uint64), b.view(np.uint64)), (N, ifft)
         g = oracle().rfft_f64(N, x, ifft)
         assert np.sqrt(((g - b) ** 2).sum() / (b ** 2).sum()) <= 1e-15, (N, ifft)
+
+
+@pytest.mark.parametrize("kind", ["q31", "q15"])
+@pytest.mark.parametrize("N", LENGTHS)
+def test_deprecated_fixed_point_radix2_bit_exact(kind, N):
+    """oracle/orc_cfft_radix2_fix.c == the reference's arm_cfft_radix2_q31 / _q15 (arm_cfft_radix2_q31.c:62-318,
+    arm_cfft_radix2_q15.c:62-78,275-386,577-681), saturating / wrapping frames included; bitReverseFlag is ignored by
+    the reference (it always bit-reverses), so both values must give the same bits"""
+    rng = np.random.default_rng(3000 + N)
+    x = _inputs(kind, N, rng)
+    for ifft in (0, 1):
+        a = oracle().cfft_radix2_fix(kind, N, x, ifft)
+        for bitrev in (0, 1):
+            assert np.array_equal(a, ref().cfft_radix(kind, 2, N, x, ifft, bitrev)), (kind, N, ifft, bitrev)

@@ -16,6 +16,6 @@ for op in $ops; do for n in $lens; do
   while [ $(jobs -r | wc -l) -ge 8 ]; do wait -n; done
 done; done
 wait
-nvcc -shared -gencode arch=compute_100a,code=sm_100a $B/shim.o $B/mfcc.o $B/ku_*.o -o $L/libcmsisdsp_cuda.so
+nvcc -shared -gencode arch=compute_100a,code=sm_100a $B/shim.o $B/mfcc.o $B/radix2_fix.o $B/ku_*.o -o $L/libcmsisdsp_cuda.so
 cp ../lib/libcmsisdsp_b200.so $L/      # rpath $ORIGIN: picks the variant's shim next to it
 echo "built $L"
