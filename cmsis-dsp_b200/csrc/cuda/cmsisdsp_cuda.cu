@@ -151,7 +151,7 @@ struct Slot {
     void *table = nullptr;                      /* rfft twiddles / split coefficients */
 };
 enum TableKind { TK_PLAN_F32 = 0, TK_PLAN_Q31, TK_PLAN_Q15, TK_PLAN_F64, TK_TWR_F32, TK_TWR_F64, TK_RCOEF_Q31, TK_RCOEF_Q15,
-                 TK_R2TW_Q31, TK_R2TW_Q15, TK_COUNT };
+                 TK_R2TW_Q31, TK_R2TW_Q15, TK_WIN_F32, TK_COUNT };
 struct DevState {
     Slot slot[TK_COUNT][9][kSlots];
     uint16_t *bitrev[9] = {};     /* plain binary bit reversal of 0..N-1 (cfft_f32 in bit-reversed output order) */
@@ -613,6 +613,47 @@ extern "C" int cmsisdsp_cuda_rfft_q31(const void *d_src, void *d_dst, uint32_t f
 extern "C" int cmsisdsp_cuda_rfft_q15(const void *d_src, void *d_dst, uint32_t fftLenReal, uint64_t nFrames, uint8_t ifftFlagR,
                                       uint8_t bitReverseFlagR, void *stream)
 { return rfft_fix(CMSISDSP_CUDA_Q15, d_src, d_dst, fftLenReal, nFrames, ifftFlagR, bitReverseFlagR, stream); }
+
+/* ------------------------------------------------------------------ window multiply fused into the load (f32)
+ * arm_mult_f32(pSrc, window, pSrc, fftLen) + arm_rfft_fast_f32 (as arm_mfcc_f32.c:112,137 does), or a real window over
+ * the complex samples of arm_cfft_f32: the windowed frame never exists in memory. */
+extern "C" int cmsisdsp_cuda_window_upload(uint32_t length, const float *pWindow)
+{
+    const int li = len_index(length);
+    if (li < 0 || !pWindow) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "window_upload: bad length / pointer");
+    return table_upload(TK_WIN_F32, li, pWindow, length * sizeof(float));
+}
+extern "C" int cmsisdsp_cuda_cfft_window_f32(void *d_p, uint32_t fftLen, uint64_t nFrames, uint8_t ifftFlag, void *stream)
+{
+    if (!d_p && nFrames) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "null data pointer");
+    if (misaligned(d_p, 8)) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "cfft_window: device data must be 8-byte aligned");
+    DevPlan pl;
+    int rc = get_plan(CMSISDSP_CUDA_F32, fftLen, &pl);
+    if (rc) return rc;
+    const int li = len_index(fftLen);
+    const void *win = nullptr;
+    rc = get_table(TK_WIN_F32, li, &win, "no window uploaded for this (device, length)");
+    if (rc) return rc;
+    const KernelEntry *ke = kEntries[OP_CFFT_F32][li];
+    return ke->launch(d_p, d_p, nFrames, ifftFlag == 1, pl.tw, nullptr, win, 0, KF_DIRECT, (cudaStream_t)stream);
+}
+extern "C" int cmsisdsp_cuda_rfft_fast_window_f32(const void *d_p, void *d_out, uint32_t fftLenReal, uint64_t nFrames, void *stream)
+{
+    if ((!d_p || !d_out) && nFrames) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "null data pointer");
+    if (d_p == d_out && nFrames) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "rfft_fast_window: p and pOut must not alias");
+    if (misaligned(d_p, 8) || misaligned(d_out, 8)) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "rfft_fast_window: device data must be 8-byte aligned");
+    const int li = len_index(fftLenReal);
+    if (li < 1) return fail(CMSISDSP_CUDA_ERR_ARGUMENT, "unsupported rfft length (32..4096, power of two)");
+    DevPlan pl;
+    int rc = get_plan(CMSISDSP_CUDA_F32, fftLenReal / 2, &pl);
+    if (rc) return rc;
+    const void *twr = nullptr, *win = nullptr;
+    rc = get_table(TK_TWR_F32, li, &twr, "no rfft plan uploaded for this (device, fftLen)");
+    if (!rc) rc = get_table(TK_WIN_F32, li, &win, "no window uploaded for this (device, length)");
+    if (rc) return rc;
+    const KernelEntry *ke = kEntries[OP_RFFT_FWD][li - 1];
+    return ke->launch(d_p, d_out, nFrames, 0, pl.tw_rfwd, twr, win, 0, KF_DIRECT, (cudaStream_t)stream);
+}
 
 /* ------------------------------------------------------------------ deprecated fixed-point radix-2 (radix2_fix.cu) */
 namespace b200fft { int shim_radix2_launch(int type, void *d_p, uint32_t N, uint64_t nFrames, int inv, const void *tw, cudaStream_t st); }

@@ -100,7 +100,9 @@ template <> struct IsFloat<cf64> { static constexpr bool value = true; };
 /* RIFFT: the body is the core of the fixed-point inverse real FFT (arm_rfft_q31.c:160-167,
  * arm_rfft_q15.c:162-169): the load is the merge stage arm_split_rifft_* applied to the bins
  * X[k], X[N-k] of a 2N-bin spectrum frame, the store ends with arm_shift_*(.., 1, ..) */
-template <class PL, bool INV, bool PERM = false, bool STAGED = false, bool RIFFT = false> struct CfftBody {
+/* WIN (f32): every input sample is first multiplied by a real window value (arm_cmplx_mult_real_f32 /
+ * arm_mult_f32 fused into the load: the windowed frame never exists in memory) */
+template <class PL, bool INV, bool PERM = false, bool STAGED = false, bool RIFFT = false, bool WIN = false> struct CfftBody {
     typedef Engine<PL> Eng;
     typedef typename Eng::A A;
     typedef typename A::elem elem;
@@ -122,6 +124,7 @@ template <class PL, bool INV, bool PERM = false, bool STAGED = false, bool RIFFT
         float scale;             /* f32 inverse: 1/N */
         int shl1;                /* fixed point, N = 2*4^m: final << 1 of every word (== PL::kOddLog2: the kernels use the constant) */
         const ci32x4 *coef;      /* RIFFT only: split-stage coefficients of bins 0..N-1 */
+        const float *win;        /* WIN only: N window values */
     };
     /* frame-local view of the batch arguments; with STAGED the kernel overrides `in` */
     static FFT_HD Args for_frame(Args a, uint64_t frame)
@@ -149,10 +152,13 @@ template <class PL, bool INV, bool PERM = false, bool STAGED = false, bool RIFFT
                 } else {
                     w = A::load(ld_in<STAGED>(a.in + idx));
                 }
+                if constexpr (WIN) w = win_mul(w, a.win[idx]);
                 if (kF32 && INV) w.y = -w.y;                       /* conjugate input (cfft_f32.c:1252-1261) */
                 r.v[b * PS::R + e] = w;
             }
     }
+    static FFT_HD cf32 win_mul(cf32 w, float v) { return {w.x * v, w.y * v}; }
+    template <class W> static FFT_HD W win_mul(W w, float) { return w; }
     static FFT_HD void gstore(const Regs &r, const Args &a, int i)
     {
         typedef typename PassOf<PL, NP - 1>::type PS;
@@ -666,6 +672,7 @@ struct RfftFwdArgs {
     const cf32 *tw;      /* pass-ordered CFFT twiddles of this plan */
     const cf32 *twr;     /* twiddleCoef_rfft_(2N): (sin,cos)(2*pi*k/(2N)), k < N */
     cf32 *scratch;       /* 2R elements of shared memory per frame (set by the kernel) */
+    const cf32 *win;     /* WIN only: the 2N window values, viewed as N pairs */
 };
 struct RfftInvArgs {
     const cf32 *in;      /* packed spectrum, N complex */
@@ -676,7 +683,8 @@ struct RfftInvArgs {
     cf32 *scratch;       /* 2R elements of shared memory per frame (set by the kernel) */
 };
 
-template <class PL, bool STAGED = false> struct RfftFwdBody {
+/* WIN: the real samples are multiplied by a window first (arm_mult_f32 as in arm_mfcc_f32.c:112, fused into the load) */
+template <class PL, bool STAGED = false, bool WIN = false> struct RfftFwdBody {
     typedef Engine<PL> Eng;
     typedef typename Eng::Regs Regs;
     typedef cf32 elem;
@@ -706,8 +714,15 @@ template <class PL, bool STAGED = false> struct RfftFwdBody {
 #pragma unroll
         for (int b = 0; b < E / PS::R; b++)
 #pragma unroll
-            for (int e = 0; e < PS::R; e++)
-                r.v[b * PS::R + e] = ld_in<STAGED>(a.in + Eng::template in_index<0>(i, b, e));
+            for (int e = 0; e < PS::R; e++) {
+                const int idx = Eng::template in_index<0>(i, b, e);
+                cf32 v = ld_in<STAGED>(a.in + idx);
+                if constexpr (WIN) {
+                    const cf32 wv = a.win[idx];
+                    v = cf32{v.x * wv.x, v.y * wv.y};
+                }
+                r.v[b * PS::R + e] = v;
+            }
     }
     /* where a finished spectrum bin goes: by default into the packed spectrum at a.out (a fused
      * consumer such as the MFCC kernel passes its own sink and never materialises the spectrum) */

@@ -537,8 +537,26 @@ static int cfft_go(const void *in, void *out, uint64_t nFrames, const void *tw, 
     typename BODY::Args a{(const elem *)in, (elem *)out, (const telem *)tw, (const uint16_t *)aux, 1.0f / (float)PL::N, shl1};
     return launch<BODY, PL>(a, nFrames, st);
 }
-static int ku_launch(const void *in, void *out, uint64_t nFrames, int inv, const void *tw, const void *aux, const void *, int shl1, int flavour, cudaStream_t st)
+#if KU_OP == 0
+/* arm_cfft_f32 with a window multiply fused into the load (aux2 = N window values): the direct kernel, natural order */
+template <bool INV>
+static int cfft_win_go(const void *in, void *out, uint64_t nFrames, const void *tw, const void *win, cudaStream_t st)
 {
+    typedef CfftBody<PL, INV, false, false, false, true> BODY;
+    typename BODY::Args a{(const cf32 *)in, (cf32 *)out, (const cf32 *)tw, nullptr, 1.0f / (float)PL::N, 0, nullptr, (const float *)win};
+    return launch<BODY, PL>(a, nFrames, st);
+}
+#endif
+static int ku_launch(const void *in, void *out, uint64_t nFrames, int inv, const void *tw, const void *aux, const void *aux2, int shl1, int flavour, cudaStream_t st)
+{
+#if KU_OP == 0
+    if (aux2) {
+        if (aux) return shim_fail(CMSISDSP_CUDA_ERR_ARGUMENT, "windowed cfft_f32: natural-order output only", cudaSuccess);
+        return inv ? cfft_win_go<true>(in, out, nFrames, tw, aux2, st) : cfft_win_go<false>(in, out, nFrames, tw, aux2, st);
+    }
+#else
+    (void)aux2;
+#endif
     if (inv) return aux ? cfft_go<true, true>(in, out, nFrames, tw, aux, shl1, flavour, st) : cfft_go<true, false>(in, out, nFrames, tw, aux, shl1, flavour, st);
     return aux ? cfft_go<false, true>(in, out, nFrames, tw, aux, shl1, flavour, st) : cfft_go<false, false>(in, out, nFrames, tw, aux, shl1, flavour, st);
 }
@@ -563,8 +581,13 @@ struct PIPE { static constexpr bool kHas = true, kPrefer = true; };
 #else
 typedef PipeOf<PL> PIPE;
 #endif
-static int ku_launch(const void *in, void *out, uint64_t nFrames, int, const void *tw, const void *aux, const void *, int, int flavour, cudaStream_t st)
+static int ku_launch(const void *in, void *out, uint64_t nFrames, int, const void *tw, const void *aux, const void *aux2, int, int flavour, cudaStream_t st)
 {
+    if (aux2) {           /* window multiply fused into the load (aux2 = fftLenReal window values): the direct kernel */
+        typedef RfftFwdBody<PL, false, true> WBODY;
+        WBODY::Args a{(const cf32 *)in, (cf32 *)out, (const cf32 *)tw, (const cf32 *)aux, nullptr, (const cf32 *)aux2};
+        return launch<WBODY, PL>(a, nFrames, st);
+    }
 #if KU_N <= 64
     if (flavour == KF_PIPE && aligned16(in) && aligned16(out)) {
         typedef TinyRfftFwdBody<TPL> BODY;

@@ -100,6 +100,34 @@ arm_status arm_cfft_batch_f64(const arm_cfft_instance_f64 *S, float64_t *p, uint
                       S->pBitRevTable, S->bitRevLength, p, nFrames, ifftFlag, bitReverseFlag, 0);
 }
 
+/* arm_cfft_f32 on frames multiplied by a real window first (re and im of sample n times pWindow[n]): the multiply of
+ * arm_cmplx_mult_real_f32 fused into the transform's load */
+typedef struct { cfft_args c; const float32_t *win; } cwin_args;
+static int cwin_prepare(const arm_cuda_job *job)
+{
+    const cwin_args *a = (const cwin_args *)job->self;
+    int rc = cmsisdsp_cuda_plan_upload(a->c.type, a->c.fftLen, a->c.tw, a->c.br, a->c.brLen);
+    return rc ? rc : cmsisdsp_cuda_window_upload(a->c.fftLen, a->win);
+}
+static int cwin_launch(const arm_cuda_job *job, const void *din, void *dout, void *doutB, uint64_t n, void *stream)
+{
+    const cwin_args *a = (const cwin_args *)job->self;
+    (void)din; (void)doutB;
+    return cmsisdsp_cuda_cfft_window_f32(dout, a->c.fftLen, n, a->c.ifftFlag, stream);
+}
+arm_status arm_cfft_window_batch_f32(const arm_cfft_instance_f32 *S, const float32_t *pWindow, float32_t *p, uint32_t nFrames, uint8_t ifftFlag)
+{
+    if (!S || !pWindow || !p || !S->pTwiddle || !valid_len(S->fftLen)) return ARM_MATH_ARGUMENT_ERROR;
+    const cwin_args a = { { CMSISDSP_CUDA_F32, cmsisdsp_cuda_cfft_f32, S->fftLen, S->pTwiddle, S->pBitRevTable, S->bitRevLength, ifftFlag, 1, 0 }, pWindow };
+    arm_cuda_job job = {0};
+    job.inStride = job.inFrame = job.outStride = job.outFrame = (size_t)2 * S->fftLen * sizeof(float32_t);
+    job.inPlace = 1;
+    job.prepare = cwin_prepare;
+    job.launch = cwin_launch;
+    job.self = &a;
+    return arm_cuda_run(&job, p, p, nFrames);
+}
+
 /* ------------------------------------------------------------------ arm_rfft_fast_f32 / _f64 */
 
 typedef struct {
@@ -162,6 +190,38 @@ arm_status arm_rfft_fast_batch_f32(const arm_rfft_fast_instance_f32 *S, float32_
     return rfft_any(0, S->fftLenRFFT, S->Sint.fftLen, S->Sint.pTwiddle, S->Sint.pBitRevTable, S->Sint.bitRevLength,
                     S->pTwiddleRFFT, p, pOut, nFrames, ifftFlag, 0);
 }
+/* forward arm_rfft_fast_f32 of frames multiplied by pWindow first: arm_mult_f32 + arm_rfft_fast_f32 as in
+ * arm_mfcc_f32.c:112,137, one pass over memory; p is left untouched */
+typedef struct { rfft_args r; const float32_t *win; } rwin_args;
+static int rwin_prepare(const arm_cuda_job *job)
+{
+    const rwin_args *a = (const rwin_args *)job->self;
+    arm_cuda_job inner = *job;
+    inner.self = &a->r;
+    int rc = rfft_prepare(&inner);
+    return rc ? rc : cmsisdsp_cuda_window_upload(a->r.N, a->win);
+}
+static int rwin_launch(const arm_cuda_job *job, const void *din, void *dout, void *doutB, uint64_t n, void *stream)
+{
+    const rwin_args *a = (const rwin_args *)job->self;
+    (void)doutB;
+    return cmsisdsp_cuda_rfft_fast_window_f32(din, dout, a->r.N, n, stream);
+}
+arm_status arm_rfft_fast_window_batch_f32(const arm_rfft_fast_instance_f32 *S, const float32_t *pWindow, const float32_t *p,
+                                          float32_t *pOut, uint32_t nFrames)
+{
+    if (!S || !pWindow || !p || !pOut || (const void *)p == (const void *)pOut || !S->pTwiddleRFFT || !S->Sint.pTwiddle) return ARM_MATH_ARGUMENT_ERROR;
+    const uint32_t N = S->fftLenRFFT;
+    if (N < 32 || !valid_len(N) || S->Sint.fftLen != N / 2) return ARM_MATH_ARGUMENT_ERROR;
+    const rwin_args a = { { 0, N, S->Sint.pTwiddle, S->Sint.pBitRevTable, S->Sint.bitRevLength, S->pTwiddleRFFT, 0 }, pWindow };
+    arm_cuda_job job = {0};
+    job.inStride = job.inFrame = job.outStride = job.outFrame = (size_t)N * sizeof(float32_t);
+    job.prepare = rwin_prepare;
+    job.launch = rwin_launch;
+    job.self = &a;
+    return arm_cuda_run(&job, p, pOut, nFrames);
+}
+
 arm_status arm_rfft_fast_batch_f64(const arm_rfft_fast_instance_f64 *S, float64_t *p, float64_t *pOut,
                                    uint32_t nFrames, uint8_t ifftFlag)
 {

@@ -176,6 +176,9 @@ def lib():
     L.arm_rfft_fast_batch_f64.restype = i
     L.arm_cuda_last_status.argtypes, L.arm_cuda_last_status.restype = [], i
     L.arm_cuda_set_devices.argtypes, L.arm_cuda_set_devices.restype = [C.POINTER(C.c_int32), u32], i
+    L.arm_rfft_fast_window_batch_f32.argtypes = [C.POINTER(arm_rfft_fast_instance_f32), C.c_void_p, C.c_void_p, C.c_void_p, u32]
+    L.arm_rfft_fast_window_batch_f32.restype = i
+    L.arm_cfft_window_batch_f32.argtypes, L.arm_cfft_window_batch_f32.restype = [C.POINTER(arm_cfft_instance_f32), C.c_void_p, C.c_void_p, u32, u8], i
     L.arm_cuda_get_devices.argtypes, L.arm_cuda_get_devices.restype = [C.POINTER(C.c_int32), u32], u32
     L.arm_cuda_set_staging.argtypes, L.arm_cuda_set_staging.restype = [u32, u32], i
     L.arm_cuda_release.argtypes, L.arm_cuda_release.restype = [], None

@@ -136,6 +136,16 @@ int  cmsisdsp_cuda_rfft_q31(const void *d_src, void *d_dst, uint32_t fftLenReal,
 int  cmsisdsp_cuda_rfft_q15(const void *d_src, void *d_dst, uint32_t fftLenReal, uint64_t nFrames,
                             uint8_t ifftFlagR, uint8_t bitReverseFlagR, void *stream);
 
+/* ---- window multiply fused into the load of arm_cfft_f32 / arm_rfft_fast_f32 (forward) ----
+ * = arm_mult_f32(p, window, p, fftLen) + the transform, the pre-FFT step of Source/TransformFunctions/arm_mfcc_f32.c:112
+ * (windows: Source/WindowFunctions/arm_hamming_f32.c:72 ...), without the round trip of the windowed frame through
+ * memory.  cmsisdsp_cuda_window_upload makes `length` window values resident and selects them for the calling thread
+ * (content-keyed like the plans); the complex transform multiplies re and im of sample n by window[n]; natural-order
+ * output. */
+int  cmsisdsp_cuda_window_upload(uint32_t length, const float *pWindow);
+int  cmsisdsp_cuda_cfft_window_f32(void *d_p, uint32_t fftLen, uint64_t nFrames, uint8_t ifftFlag, void *stream);
+int  cmsisdsp_cuda_rfft_fast_window_f32(const void *d_p, void *d_out, uint32_t fftLenReal, uint64_t nFrames, void *stream);
+
 /* ---- deprecated arm_cfft_radix2_q31 / arm_cfft_radix2_q15 (Source/TransformFunctions/arm_cfft_radix2_q31.c:62-318,
  * arm_cfft_radix2_q15.c:62-78,275-386,577-681): log2(fftLen) radix-2 stages with their own per-stage scaling, then the
  * bit reversal (always: natural-order result).  pCoef / twidCoefModifier as in the instance (the 4096-point table read

@@ -343,6 +343,17 @@ arm_status arm_cfft_mag_squared_batch_f32(const arm_cfft_instance_f32 *S, const 
                                           uint32_t nFrames, uint8_t ifftFlag);
 arm_status arm_cfft_peak_batch_f32(const arm_cfft_instance_f32 *S, const float32_t *pSrc, float32_t *pResult,
                                    uint32_t *pIndex, uint32_t nFrames, uint8_t ifftFlag);
+/* Pre-FFT window multiply fused into the transform's load (the windowed frames never exist in memory):
+ *   arm_rfft_fast_window_batch_f32   = arm_mult_f32(p, pWindow, tmp, fftLenRFFT) + arm_rfft_fast_f32(S, tmp, pOut, 0) per
+ *       frame, the front of arm_mfcc_f32 (arm_mfcc_f32.c:112,137); pWindow: fftLenRFFT values (arm_hamming_f32 ...);
+ *       p is left untouched
+ *   arm_cfft_window_batch_f32        = re and im of sample n times pWindow[n] (arm_cmplx_mult_real_f32), then
+ *       arm_cfft_f32(S, p, ifftFlag, 1) in place; pWindow: fftLen values
+ * Host or device data pointers; pWindow is a host array (kept resident on the device, keyed by its content). */
+arm_status arm_rfft_fast_window_batch_f32(const arm_rfft_fast_instance_f32 *S, const float32_t *pWindow, const float32_t *p,
+                                          float32_t *pOut, uint32_t nFrames);
+arm_status arm_cfft_window_batch_f32(const arm_cfft_instance_f32 *S, const float32_t *pWindow, float32_t *p, uint32_t nFrames,
+                                     uint8_t ifftFlag);
 /* Fixed-point real FFT over nFrames frames; direction = S->ifftFlagR.  forward: pSrc frames fftLenReal
  * scalars apart, pDst frames 2*fftLenReal apart; inverse: pSrc frames 2*fftLenReal apart (bins
  * 0..fftLenReal/2 are read), pDst frames fftLenReal apart.  pSrc is left untouched. */

@@ -18,10 +18,18 @@
 #include <vector>
 
 struct TraceRec { int phase, seq, tid, off, bytes, st; };
-static bool g_trace_on = false;
-static std::vector<TraceRec> g_trace;
-static const char *g_cta_base = nullptr;
-static int g_cur_phase = 0, g_cur_tid = 0, g_cur_seq = 0;
+/* The file is compiled in EMU_PARTS parts (-DEMU_PART=k selects the entry points of part k; no EMU_PART: everything)
+ * so that the build runs in parallel (tests/emu/build.py): one translation unit takes minutes.  The trace state is
+ * shared between the parts (C++17 inline variables). */
+inline bool g_trace_on = false;
+inline std::vector<TraceRec> g_trace;
+inline const char *g_cta_base = nullptr;
+inline int g_cur_phase = 0, g_cur_tid = 0, g_cur_seq = 0;
+#if defined(EMU_PART)
+#define EMU_HAS(k) (EMU_PART == (k))
+#else
+#define EMU_HAS(k) 1
+#endif
 
 #define FFT_TRACE_SMEM(ptr, bytes, is_store)                                                                  \
     do {                                                                                                      \
@@ -160,6 +168,7 @@ static void rfft_fix_run(const void *in, void *out, uint64_t nFrames, int ifft, 
 
 extern "C" {
 
+#if EMU_HAS(0)
 int emu_cfft(int type, uint32_t N, void *data, uint64_t nFrames, int ifft, int bitrev, const void *tw, const uint16_t *perm)
 {
     const uint16_t *pp = bitrev ? nullptr : perm;
@@ -177,7 +186,9 @@ int emu_cfft(int type, uint32_t N, void *data, uint64_t nFrames, int ifft, int b
     default: return -1;
     }
 }
+#endif
 
+#if EMU_HAS(1)
 int emu_rfft(uint32_t Nreal, const float *in, float *out, uint64_t nFrames, int ifft, const void *tw, const void *twr)
 {
     switch (Nreal / 2) {
@@ -213,10 +224,12 @@ int emu_rfft(uint32_t Nreal, const float *in, float *out, uint64_t nFrames, int 
     default: return -1;
     }
 }
+#endif
 
 /* arm_rfft_q31 (type 1) / arm_rfft_q15 (type 2): Nreal = real length 32..8192; forward frames Nreal
  * scalars in -> 2*Nreal scalars out, inverse frames 2*Nreal scalars in -> Nreal out.  tw = the
  * reference-layout twiddles of the Nreal/2-point CFFT, coefA/B = realCoefA/B tables (8192 entries). */
+#if EMU_HAS(2)
 int emu_rfft_fix(int type, uint32_t Nreal, const void *in, void *out, uint64_t nFrames, int ifft, const void *tw,
                  const void *coefA, const void *coefB)
 {
@@ -243,9 +256,11 @@ int emu_rfft_fix(int type, uint32_t Nreal, const void *in, void *out, uint64_t n
     default: return -1;
     }
 }
+#endif
 
 /* arm_cfft_f32 + arm_cmplx_mag[_squared]_f32 fused (CfftMagBody, modes 0 / 1; the peak mode reduces with warp
  * shuffles and is exercised on the device only) */
+#if EMU_HAS(3)
 int emu_cfft_mag(uint32_t N, const float *in, float *mag, uint64_t nFrames, int ifft, int squared, const void *tw)
 {
     switch (N) {
@@ -273,7 +288,9 @@ int emu_cfft_mag(uint32_t N, const float *in, float *mag, uint64_t nFrames, int 
     default: return -1;
     }
 }
+#endif
 
+#if EMU_HAS(4)
 int emu_rfft64(uint32_t Nreal, const double *in, double *out, uint64_t nFrames, int ifft, const void *tw, const void *twr)
 {
     switch (Nreal / 2) {
@@ -300,7 +317,9 @@ int emu_rfft64(uint32_t Nreal, const double *in, double *out, uint64_t nFrames, 
     default: return -1;
     }
 }
+#endif
 
+#if EMU_HAS(4)
 void emu_trace_begin(void) { g_trace.clear(); g_trace_on = true; }
 
 /* Per (phase, is_store): number of warp-level requests and the shared-memory wavefronts they
@@ -347,5 +366,6 @@ int emu_trace_stats(int64_t *out, int maxRows)
     }
     return row;
 }
+#endif
 
 }  /* extern "C" */

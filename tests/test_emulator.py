@@ -4,6 +4,7 @@ the bit-exact fixed-point arithmetic are checked here without a GPU.  Also asser
 bank-conflict degree of every shared-memory exchange from the emulator's access trace."""
 import ctypes as C
 import os
+import sys
 import subprocess
 
 import numpy as np
@@ -20,11 +21,9 @@ CSRC = os.path.join(ROOT, "cmsis-dsp_b200", "csrc", "cuda")
 
 @pytest.fixture(scope="module")
 def emu():
-    so = os.path.join(EMU_DIR, "libemu.so")
-    deps = [os.path.join(EMU_DIR, "emu.cpp")] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
-    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas",
-                               "-I", CSRC, os.path.join(EMU_DIR, "emu.cpp"), "-o", so])
+    sys.path.insert(0, EMU_DIR)
+    import build as emu_build
+    so = emu_build.build()                     # parallel parts; only when a kernel header is newer than the library
     L = C.CDLL(so)
     L.emu_cfft.argtypes = [C.c_int, C.c_uint32, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.emu_rfft.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]

@@ -307,6 +307,41 @@ def test_deprecated_fixed_point_radix2_api_bit_exact(kind):
     assert np.array_equal(_back(keep, x.dtype, x.shape), oracle().cfft_radix2_fix(kind, 512, x, 1))
 
 
+# ------------------------------------------------------------------ pre-FFT window multiply as a fused prologue
+
+@pytest.mark.parametrize("N", [32, 64, 128, 256, 1024, 4096])
+def test_window_multiply_fused_into_the_transforms(N):
+    """arm_rfft_fast_window_batch_f32 = arm_mult_f32(p, window) + arm_rfft_fast_f32 (the front of arm_mfcc_f32.c:112,137),
+    arm_cfft_window_batch_f32 = a real window over the complex samples + arm_cfft_f32: against the oracle run on frames
+    windowed in numpy with the same single-precision multiply; host and device buffers; a second window of the same
+    length gets its own device copy"""
+    L = cd.lib()
+    n = np.arange(N)
+    hamming = (0.54 - 0.46 * np.cos(2 * np.pi * n / N)).astype(np.float32)       # arm_hamming_f32.c:72 (sym = False)
+    hann = (0.5 - 0.5 * np.cos(2 * np.pi * n / N)).astype(np.float32)
+    x = rfft_input(N, frames=61, seed=N)
+    R = cd.rfft_instance(N)
+    for win in (hamming, hann, hamming):
+        want = oracle().rfft(N, x * win[None, :], 0)
+        out = np.zeros_like(x)
+        xin = x.copy()
+        assert L.arm_rfft_fast_window_batch_f32(C.byref(R), win.ctypes.data, xin.ctypes.data, out.ctypes.data, 61) == 0, cd.last_error()
+        assert relrms(out, want) <= F32_TOL and np.array_equal(xin, x), N
+    p, keep_in = _dev_copy(x, 8)
+    q, keep_out = _dev_empty(x.nbytes, 0)
+    assert L.arm_rfft_fast_window_batch_f32(C.byref(R), hann.ctypes.data, p, q, 61) == 0, cd.last_error()
+    assert relrms(_back(keep_out, np.float32, x.shape), oracle().rfft(N, x * hann[None, :], 0)) <= F32_TOL
+    z = cfft_input("f32", N, frames=47, seed=N + 9)
+    S = cd.cfft_instance("f32", N)
+    zw = (z.reshape(47, N, 2) * hamming[None, :, None]).reshape(47, 2 * N)
+    for ifft in (0, 1):
+        y = z.copy()
+        assert L.arm_cfft_window_batch_f32(C.byref(S), hamming.ctypes.data, y.ctypes.data, 47, ifft) == 0, cd.last_error()
+        assert relrms(y, oracle().cfft("f32", N, zw, ifft, 1)) <= F32_TOL, (N, ifft)
+    assert L.arm_cfft_window_batch_f32(C.byref(S), None, z.ctypes.data, 47, 0) == cd.ARM_MATH_ARGUMENT_ERROR
+    assert L.arm_rfft_fast_window_batch_f32(C.byref(R), hann.ctypes.data, x.ctypes.data, x.ctypes.data, 61) == cd.ARM_MATH_ARGUMENT_ERROR
+
+
 # ------------------------------------------------------------------ plan cache keyed by table content
 
 def test_a_second_instance_with_other_tables_gets_its_own_plan():

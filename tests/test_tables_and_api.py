@@ -161,8 +161,8 @@ def test_shared_objects_export_every_declared_symbol():
     # + rfft_q31/q15 (init, exec, batch each; their per-length inits are declared through a macro)
     # + 3 fused spectrum epilogues (mag, mag squared, peak) + deprecated radix-4/2 API (4 x (init, exec, batch))
     # + device list / staging / release (arm_cuda_set_devices, _get_devices, _set_staging, _release, arm_mfcc_release_plans)
-    # + deprecated fixed-point radix-2 (2 x (init, exec, batch))
-    assert len(names) == 114
+    # + deprecated fixed-point radix-2 (2 x (init, exec, batch)) + 2 windowed transforms
+    assert len(names) == 116
     for name in names:
         assert hasattr(fr, name), name
     for N in RFIX_LENGTHS:
