@@ -432,12 +432,18 @@ template <class PL, bool PERM = false> struct RfftFixFwdBody {
         st_stream(a.out, A::store(A::split_dc(x0)));
         st_stream(a.out + N, A::store(A::split_nyquist(x0)));
     }
-    static FFT_HD void put_bin(const Args &a, int k, work s1, work s2)
+    static FFT_HD void put_bin_c(const Args &a, int k, work s1, work s2, ci32x4 c)
     {
-        const work o = A::split_fwd(s1, s2, a.coef[k]);
+        const work o = A::split_fwd(s1, s2, c);
         st_stream(a.out + k, A::store(o));
         st_stream(a.out + (2 * N - k), A::store(A::mirror(o)));
     }
+    static FFT_HD void put_bin(const Args &a, int k, work s1, work s2) { put_bin_c(a, k, s1, s2, a.coef[k]); }
+#if defined(FFT_RFIX_NO_PREFETCH)
+    static constexpr bool kPrefetch = false;
+#else
+    static constexpr bool kPrefetch = (NP > 1) && (E % 2 == 0) && sizeof(work) == 8;
+#endif
     template <int K> static FFT_HD void bins_in_regs(const Args &a, const work *y)
     {
         if constexpr (K < N) {
@@ -471,14 +477,38 @@ template <class PL, bool PERM = false> struct RfftFixFwdBody {
                     FFT_TRACE_SMEM(&sm[pos], (int)sizeof(xelem), 1);
                     sm[pos] = A::xstore(PL::kOddLog2 ? A::shl1(w) : w);             /* cfft_q31.c:803-820, cfft_q15.c:810-827 */
                 }
+            /* The data registers are free now: the split coefficients of this thread's first E/2 bins are fetched into
+             * them so that the loads fly across the barrier; the other half is fetched in one batch at the top of the
+             * next phase.  Loaded at the point of use (one 16-byte load per bin, each waiting for the previous bin's
+             * stores to issue) they formed a chain of E exposed L1/L2 latencies -- what the fused f64 kernel showed too
+             * (profiles/r1_f_notes.md). */
+            if constexpr (kPrefetch) {
+#pragma unroll
+                for (int m = 0; m < E / 2; m++) {
+                    const ci32x4 c = a.coef[i + T * m];
+                    r.v[2 * m] = work{c.a0, c.a1};
+                    r.v[2 * m + 1] = work{c.b0, c.b1};
+                }
+            }
         } else {
+            ci32x4 late[kPrefetch ? E / 2 : 1];
+            if constexpr (kPrefetch) {
+#pragma unroll
+                for (int m = E / 2; m < E; m++) late[m - E / 2] = a.coef[i + T * m];
+            }
 #pragma unroll
             for (int m = 0; m < E; m++) {
                 const int k = i + T * m;
                 FFT_TRACE_SMEM(&sm[k], (int)sizeof(xelem), 0);
                 FFT_TRACE_SMEM(&sm[k ? N - k : 0], (int)sizeof(xelem), 0);
-                if (m == 0 && i == 0) put_bin0(a, A::xload(sm[0]));
-                else put_bin(a, k, A::xload(sm[k]), A::xload(sm[N - k]));
+                if (m == 0 && i == 0) {
+                    put_bin0(a, A::xload(sm[0]));
+                } else if constexpr (kPrefetch) {
+                    const ci32x4 c = (m < E / 2) ? ci32x4{r.v[2 * m].x, r.v[2 * m].y, r.v[2 * m + 1].x, r.v[2 * m + 1].y} : late[m < E / 2 ? 0 : m - E / 2];
+                    put_bin_c(a, k, A::xload(sm[k]), A::xload(sm[N - k]), c);
+                } else {
+                    put_bin(a, k, A::xload(sm[k]), A::xload(sm[N - k]));
+                }
             }
         }
     }

@@ -28,7 +28,11 @@
  * N = 2048 (84.9 vs 84.3 %); N = 4096 stays on ptxas' own choice (128 registers, 2 CTAs of 256 threads: a third CTA
  * needs 80 registers, spills, 68.5 -> 48.8 %) */
 #define KU_MINB (KU_N == 1024 ? 4 : 5)
-#elif KU_OP == 0 || KU_OP == 3 || KU_OP == 4 || KU_OP == 9 || KU_OP == 6 || (KU_OP == 10 && KU_N <= 512) || KU_OP == 11 || (KU_OP == 12 && KU_N == 16) || (KU_OP == 1 && KU_N <= 2048) || (KU_OP == 5 && KU_N <= 256)
+#elif KU_OP == 5 && KU_N >= 128 && KU_N <= 2048
+/* rfft_q31 forward with the split coefficients prefetched across the barrier (RfftFixFwdBody::kPrefetch): 96 registers / 5
+ * CTAs; ptxas' own choice (72 registers) spills the prefetched values (profiles/r2_notes.md: +1..7 points over no prefetch) */
+#define KU_MINB 5
+#elif KU_OP == 0 || KU_OP == 3 || KU_OP == 4 || KU_OP == 9 || KU_OP == 6 || (KU_OP == 10 && KU_N <= 512) || KU_OP == 11 || (KU_OP == 12 && KU_N == 16) || (KU_OP == 1 && KU_N <= 2048) || (KU_OP == 5 && KU_N <= 64)
 #define KU_MINB 1
 #else
 #define KU_MINB 0
