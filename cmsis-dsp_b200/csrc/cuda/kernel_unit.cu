@@ -61,6 +61,27 @@
 #endif
 #endif
 
+/* Upper bound on the resident CTAs per SM the persistent pipelined kernel is launched with (its grid is occupancy x SMs).
+ * Forward rfft of complex length 512: the round-2 addressing rewrite freed registers (134 -> 116), a fourth CTA fits, and
+ * the kernel went from 95 to 86 % of the HBM peak -- four CTAs were already measured slower for this unit in round 1
+ * (profiles/r1_e_notes.md: 94.0 % at 3 CTAs, 87.9 % at 4).  More CTAs in flight only lengthen every frame's turn at the
+ * memory system here; three saturate it. */
+/* Round-2 sweep of the cap over every pipelined unit (profiles/r2_j_pipe_occupancy_caps.txt; 2 / 3 / 4 CTAs): the in-place
+ * complex FFT of N = 512 and 1024 -- the north_star's first target kernel -- runs at 98 % of the measured HBM peak with TWO
+ * resident CTAs (8 warps per SM) against 92 % with the four that fit; inverse rfft of complex length 256 and cfft + magnitude
+ * of N = 512 gain 3-6 points at three.  Everything else is best at what fits. */
+#ifndef KU_PIPE_MAXOCC
+#if KU_OP == 0 && KU_N == 2048
+#define KU_PIPE_MAXOCC 1             /* 95.9 % with one CTA (4 frames in flight per SM), 90.8 % with the two that fit */
+#elif KU_OP == 0 && (KU_N == 512 || KU_N == 1024)
+#define KU_PIPE_MAXOCC 2
+#elif (KU_OP == 3 && KU_N == 512) || (KU_OP == 4 && KU_N == 256) || (KU_OP == 9 && KU_N == 512)
+#define KU_PIPE_MAXOCC 3
+#else
+#define KU_PIPE_MAXOCC 64
+#endif
+#endif
+
 #if !defined(KU_OP) || !defined(KU_N)
 #error "compile with -DKU_OP=<0..12> -DKU_N=<length>"
 #endif
@@ -394,7 +415,11 @@ template <class BODY, class PL> static int pipe_occupancy(int *occOut)
         int o = 0;
         KU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, frame_kernel_pipe<BODY, PL>, PipeSmem<BODY, PL>::kCtaThreads, PipeSmem<BODY, PL>::kBytes));
         if (o < 1) return shim_fail(CMSISDSP_CUDA_ERR_RUNTIME, "pipelined kernel does not fit on an SM", cudaSuccess);
-        occ[dev] = o;
+        int cap = KU_PIPE_MAXOCC;
+        if (const char *e = getenv("CMSISDSP_CUDA_PIPE_MAXOCC")) {          /* A/B runs: cap every pipelined unit */
+            if (atoi(e) >= 1) cap = atoi(e);
+        }
+        occ[dev] = o < cap ? o : cap;
     }
     *occOut = occ[dev];
     return CMSISDSP_CUDA_OK;

@@ -201,7 +201,10 @@ template <int NC> struct MfccPipe {
      * the last row of a filter may touch, finite leftovers times zero coefficients), shifted by fl*T
      * floats so that the frames of a warp land in different banks */
     static_assert(2 * PL::kFrameElems >= NC + kRowTaps + (F - 1) * T, "magnitudes must fit in the frame slot");
-    static constexpr int kQuad = (T >= 4) ? 4 : 1;                                         /* lanes summed by shuffles before a partial sum is stored */
+#ifndef MFCC_QUAD
+#define MFCC_QUAD 2                  /* measured 4 / 2 / 1: 31.5 / 32.1 / 31.6 % at fftLen 1024 (profiles/r2_k_mfcc_quad.txt) */
+#endif
+    static constexpr int kQuad = (T >= MFCC_QUAD) ? MFCC_QUAD : 1;                         /* lanes summed by shuffles before a partial sum is stored */
     static constexpr int kPartStride = T / kQuad + 1;                                      /* per-filter partial sums, conflict-free both ways */
     /* resident CTAs per SM the register allocation aims at (E <= 32: 4 CTAs = 16 warps; above: shared memory allows 2) */
     static constexpr int kMinBlocks = (E <= 32) ? (NC >= 256 ? 3 : 4) : 2;      /* measured: 3 is 2.5 % faster than 4 at fftLen 512 / 1024 (same 128 registers) */
@@ -348,10 +351,8 @@ __global__ void __launch_bounds__(128, MfccPipe<NC>::kMinBlocks) mfcc_kernel_pip
             float acc = 0.0f;
             auto flush = [&](uint32_t f) {
                 float v = acc;
-                if (MP::kQuad == 4) {
-                    v += __shfl_xor_sync(0xffffffffu, v, 1);
-                    v += __shfl_xor_sync(0xffffffffu, v, 2);
-                }
+                if (MP::kQuad >= 2) v += __shfl_xor_sync(0xffffffffu, v, 1);
+                if (MP::kQuad >= 4) v += __shfl_xor_sync(0xffffffffu, v, 2);
                 if ((i & (MP::kQuad - 1)) == 0) part[f * MP::kPartStride + i / MP::kQuad] = v;
                 acc = 0.0f;
             };

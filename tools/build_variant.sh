@@ -9,7 +9,12 @@ cd "$(dirname "$0")/../cmsis-dsp_b200/csrc"
 B=../build/var_$name; L=../lib_$name
 mkdir -p $B $L
 cp -u ../build/*.o $B/ 2>/dev/null || true
-for op in $ops; do for n in $lens; do
+for op in $ops; do
+  if [ "$op" = mfcc ]; then
+    nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --compiler-options -fPIC -I../../include -Icuda $flags -c cuda/mfcc_unit.cu -o $B/mfcc.o &
+    continue
+  fi
+  for n in $lens; do
   [ -f ../build/ku_${op}_${n}.o ] || continue
   ( nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --compiler-options -fPIC -Xptxas -v -I../../include -Icuda \
       -DKU_OP=$op -DKU_N=$n $flags -c cuda/kernel_unit.cu -o $B/ku_${op}_${n}.o 2> $B/ku_${op}_${n}.ptxas || { tail -5 $B/ku_${op}_${n}.ptxas; exit 1; } ) &
