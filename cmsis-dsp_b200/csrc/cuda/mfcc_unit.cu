@@ -450,7 +450,12 @@ template <int NC> static int mfcc_launch(const MfccArgs &a, uint64_t nFrames, cu
 template <class X> static int to_device(X **d, const X *h, size_t n)
 {
     MF_TRY(cudaMalloc((void **)d, n * sizeof(X)));
-    MF_TRY(cudaMemcpy(*d, h, n * sizeof(X), cudaMemcpyHostToDevice));
+    const cudaError_t e = cudaMemcpy(*d, h, n * sizeof(X), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(*d);
+        *d = nullptr;
+        return shim_fail(CMSISDSP_CUDA_ERR_RUNTIME, "cudaMemcpy (mfcc coefficients)", e);
+    }
     return CMSISDSP_CUDA_OK;
 }
 
@@ -534,7 +539,7 @@ extern "C" int cmsisdsp_cuda_mfcc_plan_create(uint32_t fftLen, uint32_t nbMelFil
         (rc = to_device(&p->window, windowCoefs, fftLen)) || (rc = to_device(&p->pos, filterPos, nbMelFilters)) ||
         (rc = to_device(&p->len, filterLengths, nbMelFilters)) || (rc = to_device(&p->off, off.data(), nbMelFilters)) ||
         (rc = to_device(&p->dctT, dctT.data(), dctT.size()))) {
-        delete p;
+        cmsisdsp_cuda_mfcc_plan_destroy(p);           /* frees whatever was allocated so far (null pointers are fine) */
         return rc;
     }
     switch (fftLen / 2) {
@@ -545,7 +550,7 @@ extern "C" int cmsisdsp_cuda_mfcc_plan_create(uint32_t fftLen, uint32_t nbMelFil
     default: rc = mfcc_pipe_prepare<2048>(p, filterPos, filterLengths, off.data(), filterCoefs); break;
     }
     if (rc) {
-        delete p;
+        cmsisdsp_cuda_mfcc_plan_destroy(p);
         return rc;
     }
     *plan = p;
