@@ -266,8 +266,19 @@ FFT_HD int32_t hi32(int32_t a, int32_t b) { return hi32_xu(a, b); }
 #else
 FFT_HD int32_t hi32(int32_t a, int32_t b) { return hi32_fma(a, b); }
 #endif
-/* SMMULR / SMMLAR / SMMLSR (none.h:185-194) */
+/* SMMULR / SMMLAR / SMMLSR (none.h:185-194).
+ *
+ * The accumulating forms only ever keep the upper word, and `a << 32` does not touch the lower one, so
+ *     ((a << 32) + x*y + 2^31) >> 32 = a + ((x*y + 2^31) >> 32)
+ *     ((a << 32) - x*y + 2^31) >> 32 = a - ((x*y + 2^31 - 1) >> 32)       (floor(-v) = -ceil(v))
+ * with wrap-around adds (the reference's 64-bit sum wraps the same way).  Written like that every rounding
+ * multiply-accumulate is ONE IMAD.HI with the constant as its 64-bit addend (XU pipe) plus a share of a 3-input IADD3;
+ * written as the 64-bit expression ptxas emits IMAD.WIDE + a carry-generating IADD3 + IADD3.X (27 instructions per bin of
+ * the real-FFT split stage against 13), all on the FMA / ALU pipes that bound those kernels.  FFT_RMAC_WIDE restores the
+ * 64-bit form for A/B runs. */
 FFT_HD int32_t rhi32(int32_t x, int32_t y) { return (int32_t)(((int64_t)x * y + 0x80000000LL) >> 32); }
+FFT_HD int32_t rlo32(int32_t x, int32_t y) { return (int32_t)(((int64_t)x * y + 0x7fffffffLL) >> 32); }
+#if defined(FFT_RMAC_WIDE)
 FFT_HD int32_t rhi32_acc(int32_t a, int32_t x, int32_t y)
 {
     return (int32_t)((int64_t)(((uint64_t)(int64_t)a << 32) + (uint64_t)((int64_t)x * y) + 0x80000000ULL) >> 32);
@@ -276,6 +287,10 @@ FFT_HD int32_t rhi32_sub(int32_t a, int32_t x, int32_t y)
 {
     return (int32_t)((int64_t)(((uint64_t)(int64_t)a << 32) - (uint64_t)((int64_t)x * y) + 0x80000000ULL) >> 32);
 }
+#else
+FFT_HD int32_t rhi32_acc(int32_t a, int32_t x, int32_t y) { return (int32_t)((uint32_t)a + (uint32_t)rhi32(x, y)); }
+FFT_HD int32_t rhi32_sub(int32_t a, int32_t x, int32_t y) { return (int32_t)((uint32_t)a - (uint32_t)rlo32(x, y)); }
+#endif
 
 enum StageKind { ST_PRE2 = 0, ST_FIRST4 = 1, ST_MID4 = 2, ST_LAST4 = 3 };
 
@@ -380,9 +395,10 @@ struct ArithQ31 {
     static FFT_HD work mirror(work o) { return {o.x, wsub(0, o.y)}; }                 /* :327-329 */
     static FFT_HD work sat_shl1(work w)                                               /* arm_shift_q31(.., 1, ..) */
     {
-        const int64_t x = (int64_t)w.x * 2, y = (int64_t)w.y * 2;
-        return {x > INT32_MAX ? INT32_MAX : (x < INT32_MIN ? INT32_MIN : (int32_t)x),
-                y > INT32_MAX ? INT32_MAX : (y < INT32_MIN ? INT32_MIN : (int32_t)y)};
+        /* clamp, then double: two VIMNMX and an add per value (the 64-bit compare-and-select form costs five) */
+        const int32_t x = w.x > 0x3fffffff ? 0x3fffffff : (w.x < -0x40000000 ? -0x40000000 : w.x);
+        const int32_t y = w.y > 0x3fffffff ? 0x3fffffff : (w.y < -0x40000000 ? -0x40000000 : w.y);
+        return {x * 2, y * 2};
     }
 };
 
