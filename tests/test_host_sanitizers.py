@@ -16,8 +16,11 @@ import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-sys.path.insert(0, os.path.join(HERE, "c"))
-import build as cbuild  # noqa: E402
+import importlib.util  # noqa: E402
+
+_spec = importlib.util.spec_from_file_location("host_c_build", os.path.join(HERE, "c", "build.py"))   # tests/emu has a build.py too
+cbuild = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(cbuild)
 
 # CUDA maps its own address ranges: ASan must not protect the shadow gap; the driver's process-lifetime allocations are
 # not this library's leaks (the library's own are still reported: its frees happen before exit)
