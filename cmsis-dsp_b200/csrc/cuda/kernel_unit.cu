@@ -32,6 +32,14 @@
 /* rfft_q31 forward with the split coefficients prefetched across the barrier (RfftFixFwdBody::kPrefetch): 96 registers / 5
  * CTAs; ptxas' own choice (72 registers) spills the prefetched values (profiles/r2_notes.md: +1..7 points over no prefetch) */
 #define KU_MINB 5
+#elif KU_OP == 1 && (KU_N == 256 || KU_N == 1024)
+/* cfft_q31: ptxas' free choice is 82 registers, two above the step to a sixth resident CTA of 128 threads; 80 / 6 CTAs:
+ * N = 256 103.4 -> 106.3 %, N = 1024 85.0 -> 90.9 % of the HBM peak.  The same step for N = 512 (78 -> 72 registers, 7 CTAs)
+ * loses 3.6 points and is neutral at 2048 (profiles/r2_x_thresholds.txt) */
+#define KU_MINB 6
+#elif KU_OP == 2 && KU_N == 256
+/* cfft_q15 N = 256: 62 -> 56 registers, 9 CTAs instead of 8: 72.2 -> 75.2 % */
+#define KU_MINB 9
 #elif KU_OP == 6 && KU_N >= 128
 /* rfft_q31 inverse after the rounding multiply-accumulates moved to IMAD.HI (fft_arith.cuh: rhi32_acc): 96 registers / 5 CTAs
  * (profiles/r2_q_rmac.txt: real N = 256 ... 8192 66 / 69 / 62 / 58 / 54 / 46 % against 60 / 64 / 56 / 52 / 47 / 29 % with free
