@@ -349,6 +349,8 @@ def run_cuda(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # keeps NCCL's version banner off stdout: rank 0 prints ONE line
         dist.init_process_group("nccl", device_id=dev)
     cu = cd.cuda()
     cu.cmsisdsp_cuda_set_device(local_rank)
