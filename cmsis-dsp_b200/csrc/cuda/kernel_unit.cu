@@ -44,7 +44,7 @@
 /* rfft_q31 inverse after the rounding multiply-accumulates moved to IMAD.HI (fft_arith.cuh: rhi32_acc): 96 registers / 5 CTAs
  * (profiles/r2_q_rmac.txt: real N = 256 ... 8192 66 / 69 / 62 / 58 / 54 / 46 % against 60 / 64 / 56 / 52 / 47 / 29 % with free
  * registers (142, 3 CTAs); ptxas' own 56-72 registers / 7-9 CTAs are within half a point of 5) */
-#define KU_MINB 5
+#define KU_MINB (KU_N >= 256 && KU_N <= 1024 ? 7 : 5)      /* 72 registers / 7 CTAs at real N = 512 ... 2048: 69.1 / 63.0 / 60.3 % (profiles/r2_aa_rifft_minb.txt) */
 #elif KU_OP == 0 || KU_OP == 3 || KU_OP == 4 || KU_OP == 9 || KU_OP == 6 || (KU_OP == 10 && KU_N <= 512) || KU_OP == 11 || (KU_OP == 12 && KU_N == 16) || (KU_OP == 1 && KU_N <= 2048) || (KU_OP == 5 && KU_N <= 64)
 #define KU_MINB 1
 #else
