@@ -40,6 +40,10 @@
 #elif KU_OP == 2 && KU_N == 256
 /* cfft_q15 N = 256: 62 -> 56 registers, 9 CTAs instead of 8: 72.2 -> 75.2 % */
 #define KU_MINB 9
+#elif KU_OP == 2 && KU_N == 1024
+/* cfft_q15 N = 1024: 55 -> 48 registers (no spills), 10 CTAs instead of 9: 55.5 -> 56.6 %, twice in a row; the same bound
+ * loses 1-6 points at N = 128 / 512 / 2048 (profiles/r2_ac_q15_minb10.txt) */
+#define KU_MINB 10
 #elif KU_OP == 6 && KU_N >= 128
 /* rfft_q31 inverse after the rounding multiply-accumulates moved to IMAD.HI (fft_arith.cuh: rhi32_acc): 96 registers / 5 CTAs
  * (profiles/r2_q_rmac.txt: real N = 256 ... 8192 66 / 69 / 62 / 58 / 54 / 46 % against 60 / 64 / 56 / 52 / 47 / 29 % with free
