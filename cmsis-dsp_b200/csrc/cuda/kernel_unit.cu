@@ -40,6 +40,16 @@
 #elif KU_OP == 2 && KU_N == 256
 /* cfft_q15 N = 256: 62 -> 56 registers, 9 CTAs instead of 8: 72.2 -> 75.2 % */
 #define KU_MINB 9
+#elif (KU_OP == 1 || KU_OP == 2) && KU_N == 4096
+/* 256-thread CTAs: a bound of three lets ptxas take 78 (q31: three CTAs instead of four) / 64 (q15: still four) registers and
+ * schedule for them: cfft_q31 66.5 -> 68.2 %, cfft_q15 44.8 -> 47.1 %; a bound of two: 60.1 / 47.1 % (profiles/r2_ad_4096_minb.txt) */
+#define KU_MINB 3
+#elif KU_OP == 2 && KU_N == 512
+/* cfft_q15 N = 512: 64 registers / 8 CTAs instead of 54 / 9: 59.4 -> 60.5 % (N = 128 +0.3, N = 2048 -0.1: left alone; profiles/r2_ae_minb.txt) */
+#define KU_MINB 8
+#elif KU_OP == 7 && KU_N == 4096
+/* rfft_q15 forward, real N = 8192 (256-thread CTAs): 43.2 -> 44.4 % */
+#define KU_MINB 3
 #elif KU_OP == 2 && KU_N == 1024
 /* cfft_q15 N = 1024: 55 -> 48 registers (no spills), 10 CTAs instead of 9: 55.5 -> 56.6 %, twice in a row; the same bound
  * loses 1-6 points at N = 128 / 512 / 2048 (profiles/r2_ac_q15_minb10.txt) */
