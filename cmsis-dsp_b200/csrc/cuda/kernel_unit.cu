@@ -27,7 +27,7 @@
 /* cfft_f64: 128 registers / 4 CTAs at N = 1024 (92.1 vs 91.1 % of the HBM peak with free registers), 96 / 5 CTAs at
  * N = 2048 (84.9 vs 84.3 %); N = 4096 stays on ptxas' own choice (128 registers, 2 CTAs of 256 threads: a third CTA
  * needs 80 registers, spills, 68.5 -> 48.8 %) */
-#define KU_MINB (KU_N == 1024 ? 4 : 5)
+#define KU_MINB 4        /* round 2: N = 2048 with 128 / 4 as well: 84.0 -> 90.6 % (six CTAs of 80 registers: 55 %; profiles/r2_af_minb.txt) */
 #elif KU_OP == 5 && KU_N >= 128 && KU_N <= 2048
 /* rfft_q31 forward with the split coefficients prefetched across the barrier (RfftFixFwdBody::kPrefetch): 96 registers / 5
  * CTAs; ptxas' own choice (72 registers) spills the prefetched values (profiles/r2_notes.md: +1..7 points over no prefetch) */
@@ -47,6 +47,16 @@
 #elif KU_OP == 2 && KU_N == 512
 /* cfft_q15 N = 512: 64 registers / 8 CTAs instead of 54 / 9: 59.4 -> 60.5 % (N = 128 +0.3, N = 2048 -0.1: left alone; profiles/r2_ae_minb.txt) */
 #define KU_MINB 8
+#elif KU_OP == 12 && KU_N >= 256 && KU_N <= 2048
+/* rfft_fast_f64 inverse (KU_N = complex length), launch-bound sweep of round 2 (profiles/r2_ag_f64_minb.txt; % of the HBM peak
+ * at 3 / 4 / 5 CTAs aimed at, ptxas' own choice first): 256: 86.3 | 88.5 / 90.8 / 84.9; 512: 68.8 | 80.6 / 74.5 / 77.4;
+ * 1024: 65.9 | 67.5 / 66.3 / 73.8; 2048: 62.1 | 63.8 / 64.0 / 64.9 */
+#define KU_MINB (KU_N == 256 ? 4 : (KU_N == 512 ? 3 : 5))
+#elif KU_OP == 11 && KU_N == 256
+#define KU_MINB 4        /* rfft_fast_f64 forward, real N = 512: 93.1 -> 94.2 % */
+#elif KU_OP == 5 && KU_N == 4096
+/* rfft_q31 forward, real N = 8192 (256-thread CTAs): 64 registers / 4 CTAs instead of 77 / 3: 67.2 -> 67.9 % */
+#define KU_MINB 4
 #elif KU_OP == 7 && KU_N == 4096
 /* rfft_q15 forward, real N = 8192 (256-thread CTAs): 43.2 -> 44.4 % */
 #define KU_MINB 3
@@ -58,7 +68,7 @@
 /* rfft_q31 inverse after the rounding multiply-accumulates moved to IMAD.HI (fft_arith.cuh: rhi32_acc): 96 registers / 5 CTAs
  * (profiles/r2_q_rmac.txt: real N = 256 ... 8192 66 / 69 / 62 / 58 / 54 / 46 % against 60 / 64 / 56 / 52 / 47 / 29 % with free
  * registers (142, 3 CTAs); ptxas' own 56-72 registers / 7-9 CTAs are within half a point of 5) */
-#define KU_MINB (KU_N >= 256 && KU_N <= 1024 ? 7 : 5)      /* 72 registers / 7 CTAs at real N = 512 ... 2048: 69.1 / 63.0 / 60.3 % (profiles/r2_aa_rifft_minb.txt) */
+#define KU_MINB (KU_N >= 256 && KU_N <= 1024 ? 7 : (KU_N == 4096 ? 3 : 5))      /* 72 registers / 7 CTAs at real N = 512 ... 2048: 69.1 / 63.0 / 60.3 % (profiles/r2_aa_rifft_minb.txt) */
 #elif KU_OP == 0 || KU_OP == 3 || KU_OP == 4 || KU_OP == 9 || KU_OP == 6 || (KU_OP == 10 && KU_N <= 512) || KU_OP == 11 || (KU_OP == 12 && KU_N == 16) || (KU_OP == 1 && KU_N <= 2048) || (KU_OP == 5 && KU_N <= 64)
 #define KU_MINB 1
 #else
