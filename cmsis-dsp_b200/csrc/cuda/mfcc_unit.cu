@@ -191,7 +191,10 @@ template <int NC> struct MfccPipe {
     typedef RfftFwdBody<PL, true> BODY;
     typedef Engine<PL> Eng;
     static constexpr int T = PL::T, F = PL::F, E = PL::E;
-    static constexpr int kUnits = 4, kCtaThreads = 32 * kUnits;
+#ifndef MFCC_UNITS
+#define MFCC_UNITS 4
+#endif
+    static constexpr int kUnits = MFCC_UNITS, kCtaThreads = 32 * kUnits;
     static_assert(PL::kThreads == 32, "a unit of the pipelined MFCC kernel is one warp");
     static_assert(PL::kFrameElems % 2 == 0, "frame slots must be 16-byte aligned (bulk copy destination)");
     static constexpr int kFrameBytes = 2 * NC * (int)sizeof(float);
@@ -207,7 +210,12 @@ template <int NC> struct MfccPipe {
     static constexpr int kQuad = (T >= MFCC_QUAD) ? MFCC_QUAD : 1;                         /* lanes summed by shuffles before a partial sum is stored */
     static constexpr int kPartStride = T / kQuad + 1;                                      /* per-filter partial sums, conflict-free both ways */
     /* resident CTAs per SM the register allocation aims at (E <= 32: 4 CTAs = 16 warps; above: shared memory allows 2) */
-    static constexpr int kMinBlocks = (E <= 32) ? (NC >= 256 ? 3 : 4) : 2;      /* measured: 3 is 2.5 % faster than 4 at fftLen 512 / 1024 (same 128 registers) */
+#ifdef MFCC_MINBLOCKS
+    static constexpr int kMinBlocks = MFCC_MINBLOCKS;
+#else
+    static constexpr int kMinBlocks = (E <= 32) ? (NC >= 256 ? 3 : 4) : 2;
+#endif
+         /* measured: 3 is 2.5 % faster than 4 at fftLen 512 / 1024 (same 128 registers) */
     static constexpr int kHoistVals = (int)(sizeof(typename BODY::Hoist) / sizeof(cf32));
     /* byte offsets inside the CTA's dynamic shared memory */
     static constexpr int oBuf = 0;
@@ -222,7 +230,7 @@ template <int NC> struct MfccPipe {
 };
 
 template <int NC>
-__global__ void __launch_bounds__(128, MfccPipe<NC>::kMinBlocks) mfcc_kernel_pipe(const MfccArgs a, const uint64_t nFrames, const __grid_constant__ MfccRows rows)
+__global__ void __launch_bounds__(MfccPipe<NC>::kCtaThreads, MfccPipe<NC>::kMinBlocks) mfcc_kernel_pipe(const MfccArgs a, const uint64_t nFrames, const __grid_constant__ MfccRows rows)
 {
     typedef MfccPipe<NC> MP;
     typedef typename MP::PL PL;
