@@ -173,10 +173,10 @@ template <class PL, bool INV, bool PERM = false, bool STAGED = false, bool RIFFT
                 } else if (PL::kOddLog2) {
                     w = A::shl1(w);                                  /* cfft_q31.c:803-820, cfft_q15.c:810-827 */
                 }
-                if constexpr (RIFFT) w = A::sat_shl1(w);
                 int pos = k;
                 if constexpr (PERM) pos = (int)a.perm[k];
-                st_stream(a.out + pos, A::store(w));
+                if constexpr (RIFFT) st_stream(a.out + pos, A::store_sat_shl1(w));      /* arm_shift_*(.., 1, ..) of arm_rfft_* (inverse) */
+                else st_stream(a.out + pos, A::store(w));
             }
     }
     static FFT_HD cf32 scale_conj(cf32 w, float s) { return {w.x * s, -w.y * s}; }
