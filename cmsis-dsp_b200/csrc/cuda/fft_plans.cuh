@@ -90,6 +90,15 @@ FIXPLAN(2048, 128, 1,   4, 1, PF(ST_PRE2, ST_FIRST4), PF(ST_MID4, ST_MID4), PF(S
 FIXPLAN(4096, 256, 1,   4, 1, PF(ST_FIRST4, ST_MID4), PF(ST_MID4, ST_MID4), PF(ST_MID4, ST_LAST4))
 #undef PF
 #undef FIXPLAN
+/* q31, N = 64: four threads per frame and two passes (direct kernel, 82 registers / 5 CTAs) instead of one thread per frame (tiny
+ * kernel, 183 registers / 2 CTAs): cfft_q31 74.0 -> 86.5 % of the HBM peak, rfft_q31 real N = 128 forward 69.3 -> 66.8 %, inverse
+ * 55.2 -> 56.9 %.  The same plan for q15 is slower everywhere (cfft_q15 51.3 -> 46.6 %, rfft_q15 58 / 40 -> 37 / 30 %) and is not
+ * used (profiles/r2_aj_fix64.txt).  FFT_FIX64_ONE_THREAD restores the one-thread plan for A/B builds. */
+#if !defined(FFT_FIX64_ONE_THREAD)
+template <> struct PlanCfftFix<ArithQ31, 64> {
+    typedef Plan<ArithQ31, 64, 4, 32, 4, 1, PassFix<ArithQ31, ST_FIRST4, ST_MID4>, PassFix<ArithQ31, ST_LAST4>> type;
+};
+#endif
 
 /* ---- f64 complex (arm_cfft_f64.c: the fixed-point stage structure, 16-byte points) ----
  * 16 points (64 registers) per thread from N = 64 up; the short lengths use 4 threads per frame so that a
