@@ -85,7 +85,10 @@ FIXPLAN(256,  16,  8,   4, 1, PF(ST_FIRST4, ST_MID4), PF(ST_MID4, ST_LAST4))
  * threads and barriers: T = 32 / 64 / 128 for N = 1024 / 2048 / 4096) were also measured slower, by 8-25 %
  * (profiles/r1_e_notes.md): occupancy, not barrier count, is what these kernels live on */
 FIXPLAN(512,  32,  4,   4, 1, PF(ST_PRE2, ST_FIRST4), PF(ST_MID4, ST_MID4), PF(ST_LAST4))
-FIXPLAN(1024, 64,  2,   4, 1, PF(ST_FIRST4, ST_MID4), PF(ST_MID4, ST_MID4), PF(ST_LAST4))
+#ifndef FFT_FIX1024_F
+#define FFT_FIX1024_F 2
+#endif
+FIXPLAN(1024, 64,  FFT_FIX1024_F,   4, 1, PF(ST_FIRST4, ST_MID4), PF(ST_MID4, ST_MID4), PF(ST_LAST4))
 FIXPLAN(2048, 128, 1,   4, 1, PF(ST_PRE2, ST_FIRST4), PF(ST_MID4, ST_MID4), PF(ST_MID4, ST_LAST4))
 FIXPLAN(4096, 256, 1,   4, 1, PF(ST_FIRST4, ST_MID4), PF(ST_MID4, ST_MID4), PF(ST_MID4, ST_LAST4))
 #undef PF

@@ -76,6 +76,14 @@
 #endif
 #endif
 
+/* frames per CTA of the fixed-point N = 1024 plan (fft_plans.cuh; the twiddle tables do not depend on it): one frame = one CTA of
+ * two warps for the q15 complex FFT and the forward q15 real FFT -- the CTA-wide barrier between the passes then waits for one
+ * frame only: cfft_q15 56.6 -> 58.7 %, rfft_q15 forward 55.9 -> 57.5 %; q31 and the inverse real FFTs lose 0.3-2.4 points and
+ * keep two frames (profiles/r2_ak_fix1024_f1.txt) */
+#if !defined(FFT_FIX1024_F) && (KU_OP == 2 || KU_OP == 7) && KU_N == 1024
+#define FFT_FIX1024_F 1
+#endif
+
 #include "../../../include/cmsisdsp_cuda.h"
 #include "fft_plans.cuh"
 #include "kernel_entry.h"
