@@ -88,9 +88,12 @@ FIXPLAN(512,  32,  4,   4, 1, PF(ST_PRE2, ST_FIRST4), PF(ST_MID4, ST_MID4), PF(S
 #ifndef FFT_FIX1024_F
 #define FFT_FIX1024_F 2
 #endif
-FIXPLAN(1024, 64,  FFT_FIX1024_F,   4, 1, PF(ST_FIRST4, ST_MID4), PF(ST_MID4, ST_MID4), PF(ST_LAST4))
-FIXPLAN(2048, 128, 1,   4, 1, PF(ST_PRE2, ST_FIRST4), PF(ST_MID4, ST_MID4), PF(ST_MID4, ST_LAST4))
-FIXPLAN(4096, 256, 1,   4, 1, PF(ST_FIRST4, ST_MID4), PF(ST_MID4, ST_MID4), PF(ST_MID4, ST_LAST4))
+#ifndef FFT_FIX_LONG_T          /* A/B builds: threads per frame of the three long plans as a divisor (1: 16 points per thread, 2: 32) */
+#define FFT_FIX_LONG_T 1
+#endif
+FIXPLAN(1024, 64 / FFT_FIX_LONG_T,  FFT_FIX1024_F * FFT_FIX_LONG_T,   4, 1, PF(ST_FIRST4, ST_MID4), PF(ST_MID4, ST_MID4), PF(ST_LAST4))
+FIXPLAN(2048, 128 / FFT_FIX_LONG_T, FFT_FIX_LONG_T,   4, 1, PF(ST_PRE2, ST_FIRST4), PF(ST_MID4, ST_MID4), PF(ST_MID4, ST_LAST4))
+FIXPLAN(4096, 256 / FFT_FIX_LONG_T, 1,   4, 1, PF(ST_FIRST4, ST_MID4), PF(ST_MID4, ST_MID4), PF(ST_MID4, ST_LAST4))
 #undef PF
 #undef FIXPLAN
 /* q31, N = 64: four threads per frame and two passes (direct kernel, 82 registers / 5 CTAs) instead of one thread per frame (tiny
