@@ -8,7 +8,9 @@
  * worker), so a legacy single-frame call stays on the current device.
  * Staging: chunks of CMSISDSP_CUDA_CHUNK_MIB MiB (default 32) cycling over CMSISDSP_CUDA_NSTREAMS streams (default 3)
  * per worker; arm_cuda_set_staging() overrides both.  Chunk size and stream count were swept on a B200 (profiles/
- * r2_staging_sweep.txt).
+ * r2_staging_sweep.txt).  A call's first chunks grow geometrically from CMSISDSP_CUDA_RAMP_MIB MiB (default 4; 0: every
+ * chunk full-sized) and its last ones shrink the same way: a call takes the time of all its copies in one direction plus
+ * the FIRST chunk's copy in and the LAST chunk's copy out, which nothing overlaps (arm_cuda_set_staging_ramp()).
  * Streams and staging buffers belong to the calling host thread (one set per worker slot); they are released when the
  * thread exits or calls arm_cuda_release().
  */
@@ -26,6 +28,7 @@
 #define MIN_BYTES_PER_WORKER ((size_t)8 << 20)
 #define DEFAULT_CHUNK ((size_t)32 << 20)
 #define DEFAULT_NSTREAM 3
+#define DEFAULT_RAMP ((size_t)4 << 20)
 
 typedef struct {
     int device;                      /* -1: unused */
@@ -43,7 +46,8 @@ static struct {
     int dev[MAXW];
     size_t chunk;
     int nstream;
-} g_cfg = { PTHREAD_MUTEX_INITIALIZER, 0, 0, {0}, DEFAULT_CHUNK, DEFAULT_NSTREAM };
+    size_t ramp;                     /* size of a call's first and last chunk; 0: no ramp */
+} g_cfg = { PTHREAD_MUTEX_INITIALIZER, 0, 0, {0}, DEFAULT_CHUNK, DEFAULT_NSTREAM, DEFAULT_RAMP };
 
 static pthread_key_t g_key;
 static pthread_once_t g_once = PTHREAD_ONCE_INIT;
@@ -85,6 +89,8 @@ static void cfg_init_locked(void)
     if (e && atol(e) > 0 && atol(e) <= 4096) g_cfg.chunk = (size_t)atol(e) << 20;
     e = getenv("CMSISDSP_CUDA_NSTREAMS");
     if (e && atoi(e) >= 1 && atoi(e) <= MAXS) g_cfg.nstream = atoi(e);
+    e = getenv("CMSISDSP_CUDA_RAMP_MIB");
+    if (e && atol(e) >= 0 && atol(e) <= 4096) g_cfg.ramp = (size_t)atol(e) << 20;
 }
 
 arm_status arm_cuda_set_devices(const int32_t *devices, uint32_t nDevices)
@@ -138,12 +144,23 @@ arm_status arm_cuda_set_staging(uint32_t chunkMiB, uint32_t nStreams)
     return ARM_MATH_SUCCESS;
 }
 
-static void staging_config(size_t *chunk, int *nstream)
+arm_status arm_cuda_set_staging_ramp(uint32_t firstChunkMiB)
+{
+    if (firstChunkMiB > 4096) return ARM_MATH_ARGUMENT_ERROR;
+    pthread_mutex_lock(&g_cfg.mu);
+    cfg_init_locked();
+    g_cfg.ramp = (size_t)firstChunkMiB << 20;
+    pthread_mutex_unlock(&g_cfg.mu);
+    return ARM_MATH_SUCCESS;
+}
+
+static void staging_config(size_t *chunk, int *nstream, size_t *ramp)
 {
     pthread_mutex_lock(&g_cfg.mu);
     cfg_init_locked();
     *chunk = g_cfg.chunk;
     *nstream = g_cfg.nstream;
+    *ramp = g_cfg.ramp;
     pthread_mutex_unlock(&g_cfg.mu);
 }
 
@@ -227,7 +244,7 @@ typedef struct {
     uint64_t f0, f1;                 /* this worker's frames */
     const char *in;
     char *out;
-    size_t chunk;
+    size_t chunk, ramp;
     int nstream;
     int rc;                          /* shim code of the first failure */
 } work_item;
@@ -251,9 +268,21 @@ static void *worker(void *arg)
     uint64_t perChunk = it->chunk / (per ? per : 1);
     if (perChunk == 0) perChunk = 1;
     if (perChunk > it->f1 - it->f0) perChunk = it->f1 - it->f0;
+    /* chunk sizes: rampMin, 2 rampMin, 4 rampMin ... perChunk ... and never more than half of what is left (but at
+     * least rampMin), so the call ends on small chunks too */
+    uint64_t rampMin = it->ramp ? it->ramp / (per ? per : 1) : perChunk;
+    if (rampMin == 0) rampMin = 1;
+    if (rampMin > perChunk) rampMin = perChunk;
+    uint64_t up = rampMin, n = 0;
     int used = 0, s = 0;
-    for (uint64_t f = it->f0; f < it->f1 && !rc; f += perChunk, s = (s + 1) % it->nstream) {
-        const uint64_t n = (it->f1 - f < perChunk) ? it->f1 - f : perChunk;
+    for (uint64_t f = it->f0; f < it->f1 && !rc; f += n, s = (s + 1) % it->nstream) {
+        const uint64_t left = it->f1 - f;
+        uint64_t half = (left + 1) / 2;
+        if (half < rampMin) half = rampMin;
+        n = up < perChunk ? up : perChunk;
+        if (n > half) n = half;
+        if (n > left) n = left;
+        if (up < perChunk) up *= 2;
         void *st = c->stream[s], *din = 0, *dout = 0, *doutB = 0;
         if (s + 1 > used) used = s + 1;
         /* the stream serialises reuse of its staging buffers */
@@ -286,9 +315,9 @@ arm_status arm_cuda_run_host(const arm_cuda_job *job, const void *in, void *out,
     if (nd <= 0) return ARM_MATH_CUDA_NO_DEVICE;
     ctx_pool *pool = pool_get();
     if (!pool) return ARM_MATH_CUDA_RUNTIME_ERROR;
-    size_t chunk;
+    size_t chunk, ramp;
     int nstream;
-    staging_config(&chunk, &nstream);
+    staging_config(&chunk, &nstream, &ramp);
 
     size_t per = job->inStride > job->outStride ? job->inStride : job->outStride;
     const uint64_t total = nFrames * (uint64_t)(per ? per : 1);
@@ -307,7 +336,7 @@ arm_status arm_cuda_run_host(const arm_cuda_job *job, const void *in, void *out,
         if (f0 >= f1) break;
         work_item *it = &item[nw];
         it->job = job; it->ctx = &pool->w[nw]; it->device = devs[nw]; it->f0 = f0; it->f1 = f1;
-        it->in = (const char *)in; it->out = (char *)out; it->chunk = chunk; it->nstream = nstream; it->rc = 0;
+        it->in = (const char *)in; it->out = (char *)out; it->chunk = chunk; it->ramp = ramp; it->nstream = nstream; it->rc = 0;
         nw++;
     }
     const int cur = cmsisdsp_cuda_get_device();

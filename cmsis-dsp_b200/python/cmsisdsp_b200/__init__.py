@@ -181,6 +181,7 @@ def lib():
     L.arm_cfft_window_batch_f32.argtypes, L.arm_cfft_window_batch_f32.restype = [C.POINTER(arm_cfft_instance_f32), C.c_void_p, C.c_void_p, u32, u8], i
     L.arm_cuda_get_devices.argtypes, L.arm_cuda_get_devices.restype = [C.POINTER(C.c_int32), u32], u32
     L.arm_cuda_set_staging.argtypes, L.arm_cuda_set_staging.restype = [u32, u32], i
+    L.arm_cuda_set_staging_ramp.argtypes, L.arm_cuda_set_staging_ramp.restype = [u32], i
     L.arm_cuda_release.argtypes, L.arm_cuda_release.restype = [], None
     L.arm_mfcc_release_plans.argtypes, L.arm_mfcc_release_plans.restype = [], None
     for name in ("arm_cfft_mag_batch_f32", "arm_cfft_mag_squared_batch_f32"):

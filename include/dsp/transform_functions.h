@@ -377,6 +377,10 @@ uint32_t   arm_cuda_get_devices(int32_t *devices, uint32_t maxDevices);         
 /* host buffers travel in chunks of chunkMiB MiB over nStreams streams per device (0 = leave unchanged; defaults 32 and
  * 3, or CMSISDSP_CUDA_CHUNK_MIB / CMSISDSP_CUDA_NSTREAMS) */
 arm_status arm_cuda_set_staging(uint32_t chunkMiB, uint32_t nStreams);
+/* a call's first chunk has firstChunkMiB MiB, the next ones double up to chunkMiB, the last ones halve down again
+ * (default 4, or CMSISDSP_CUDA_RAMP_MIB; 0 = every chunk full-sized): the first copy in and the last copy out are the
+ * only transfers nothing overlaps */
+arm_status arm_cuda_set_staging_ramp(uint32_t firstChunkMiB);
 /* frees the calling thread's streams and staging buffers (also done when the thread exits) */
 void       arm_cuda_release(void);
 /* frees the cached device copies of MFCC coefficient sets (no MFCC call may be in flight) */

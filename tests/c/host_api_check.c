@@ -143,7 +143,14 @@ int main(void)
     expect(arm_cuda_set_staging(4, 2) == ARM_MATH_SUCCESS ? arm_rfft_fast_batch_f32(&rf, rin, spec, RB, 0) : ARM_MATH_ARGUMENT_ERROR,
            "forward, 4 MiB chunks on 2 streams");
     CHECK(!g_gpu || memcmp(spec, spec0, rn * sizeof(float)) == 0, "4 MiB x 2 staging: spectrum differs");
+    expect(arm_cuda_set_staging_ramp(1) == ARM_MATH_SUCCESS ? arm_rfft_fast_batch_f32(&rf, rin, spec, RB, 0) : ARM_MATH_ARGUMENT_ERROR,
+           "forward, 4 MiB chunks on 2 streams, chunk sizes ramping from 1 MiB");
+    CHECK(!g_gpu || memcmp(spec, spec0, rn * sizeof(float)) == 0, "ramped staging: spectrum differs");
+    expect(arm_cuda_set_staging_ramp(0) == ARM_MATH_SUCCESS ? arm_rfft_fast_batch_f32(&rf, rin, spec, RB, 0) : ARM_MATH_ARGUMENT_ERROR,
+           "forward, no ramp");
+    CHECK(!g_gpu || memcmp(spec, spec0, rn * sizeof(float)) == 0, "unramped staging: spectrum differs");
     arm_cuda_set_staging(32, 3);
+    arm_cuda_set_staging_ramp(4);
 
     /* ---- fixed point, in place: the fan-out must give the one-device bits ---- */
     {

@@ -199,11 +199,15 @@ def test_host_batches_fan_out_over_the_device_list():
             assert relrms(got[lo:hi], want[lo:hi]) <= F32_TOL, (devs, g)
         assert np.array_equal(cd.cfft_batch("q15", N, xq, 1, 0), wantq), devs
         assert relrms(cd.rfft_batch(2 * N, r, 0), wantr) <= F32_TOL, devs
-    # the staging knobs: tiny chunks over many streams, one big chunk on one stream
-    for chunk_mib, nstreams in ((1, 6), (512, 1), (32, 3)):
+    # the staging knobs: tiny chunks over many streams, one big chunk on one stream; chunk sizes ramping up from and
+    # down to 1 / 2 MiB (x[:3000] is 23 MiB: a worker's 11.7 MiB travel as 1 + 2 + 4 + 2.4 + 1.2 + 1 MiB, say), no ramp
+    for chunk_mib, nstreams, ramp_mib in ((1, 6, 0), (512, 1, 4), (4, 3, 1), (8, 2, 2), (32, 3, 4)):
         assert L.arm_cuda_set_staging(chunk_mib, nstreams) == 0
+        assert L.arm_cuda_set_staging_ramp(ramp_mib) == 0
         cd.set_devices([0, 0])
-        assert relrms(cd.cfft_batch("f32", N, x[:3000], 0, 1), want[:3000]) <= F32_TOL, (chunk_mib, nstreams)
+        assert relrms(cd.cfft_batch("f32", N, x[:3000], 0, 1), want[:3000]) <= F32_TOL, (chunk_mib, nstreams, ramp_mib)
+        assert np.array_equal(cd.cfft_batch("q15", N, xq[:5001], 1, 0), wantq[:5001]), (chunk_mib, nstreams, ramp_mib)
+    assert L.arm_cuda_set_staging_ramp(5000) == cd.ARM_MATH_ARGUMENT_ERROR
     cd.set_devices(None)
     assert len(cd.get_devices()) == cd.cuda().cmsisdsp_cuda_device_count()
     assert L.arm_cuda_set_devices((C.c_int32 * 1)(99), 1) == cd.ARM_MATH_ARGUMENT_ERROR

@@ -162,7 +162,7 @@ def test_shared_objects_export_every_declared_symbol():
     # + 3 fused spectrum epilogues (mag, mag squared, peak) + deprecated radix-4/2 API (4 x (init, exec, batch))
     # + device list / staging / release (arm_cuda_set_devices, _get_devices, _set_staging, _release, arm_mfcc_release_plans)
     # + deprecated fixed-point radix-2 (2 x (init, exec, batch)) + 2 windowed transforms
-    assert len(names) == 116
+    assert len(names) == 117
     for name in names:
         assert hasattr(fr, name), name
     for N in RFIX_LENGTHS:

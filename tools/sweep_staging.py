@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--frames", type=int, default=65536)
     ap.add_argument("--chunks", default="4,8,16,32,64,128,256")
     ap.add_argument("--streams", default="2,3,4,6")
+    ap.add_argument("--ramps", default="0", help="first / last chunk MiB of the geometric ramp (0: none)")
     ap.add_argument("--json", default=None)
     args = ap.parse_args()
     N, B = 4096, args.frames
@@ -40,10 +41,11 @@ def main():
     print("pinned copy peak:", json.dumps(peak), flush=True)
     rows = []
     for chunk in [int(v) for v in args.chunks.split(",")]:
-        for ns in [int(v) for v in args.streams.split(",")]:
+        for ns, ramp in [(int(v), int(r)) for v in args.streams.split(",") for r in args.ramps.split(",")]:
             assert L.arm_cuda_set_staging(chunk, ns) == 0
+            assert L.arm_cuda_set_staging_ramp(ramp) == 0
             best = float("inf")
-            for rep in range(3):
+            for rep in range(4):
                 t0 = time.perf_counter()
                 a = L.arm_rfft_fast_batch_f32(C.byref(S), hx.data_ptr(), hs.data_ptr(), B, 0)
                 b = L.arm_rfft_fast_batch_f32(C.byref(S), hs.data_ptr(), hy.data_ptr(), B, 1)
@@ -52,9 +54,9 @@ def main():
                 if rep:
                     best = min(best, dt)
             gbs = 2 * nbytes / best / 1e9
-            rows.append(dict(chunk_mib=chunk, streams=ns, seconds=best, msamples=B * N / best / 1e6, pcie_gbs_per_direction=gbs,
+            rows.append(dict(chunk_mib=chunk, streams=ns, ramp_mib=ramp, seconds=best, msamples=B * N / best / 1e6, pcie_gbs_per_direction=gbs,
                              frac_of_copy_peak=gbs / peak["both_gbs_per_direction"]))
-            print(f"chunk {chunk:4d} MiB  streams {ns}  {best * 1e3:8.1f} ms  {B * N / best / 1e6:8.0f} Msamples/s  {gbs:6.1f} GB/s per direction  "
+            print(f"chunk {chunk:4d} MiB  streams {ns}  ramp {ramp:3d} MiB  {best * 1e3:8.1f} ms  {B * N / best / 1e6:8.0f} Msamples/s  {gbs:6.1f} GB/s per direction  "
                   f"{100 * gbs / peak['both_gbs_per_direction']:5.1f}% of the pinned-copy peak", flush=True)
     err = float(((hy[:64] - hx[:64]).double().pow(2).sum() / hx[:64].double().pow(2).sum()).sqrt())
     print("round trip rel-RMS", err)
