@@ -350,6 +350,9 @@ __global__ void __launch_bounds__(MfccPipe<NC>::kCtaThreads, MfccPipe<NC>::kMinB
             BODY::special_bins(scratch, i, stw, MagSink{mag});
         }
         __syncwarp();
+#ifndef MFCC_ABLATE
+#define MFCC_ABLATE 0                /* timing experiments only (wrong results): 1 no mel loop, 2 no partial sums / log, 4 no DCT */
+#endif
         /* 4. mel filter bank (:150-160): a row = 2T consecutive bins, one float2 per lane, against
          * zero-padded coefficients; the row schedule sits in the constant bank, so the loop is
          * branch-uniform and free of dependent loads.  At the end of a filter the lane sums are
@@ -364,7 +367,7 @@ __global__ void __launch_bounds__(MfccPipe<NC>::kCtaThreads, MfccPipe<NC>::kMinB
                 if ((i & (MP::kQuad - 1)) == 0) part[f * MP::kPartStride + i / MP::kQuad] = v;
                 acc = 0.0f;
             };
-            uint32_t rr = 0;
+            uint32_t rr = (MFCC_ABLATE & 1) ? a.nRows : 0;
             for (; rr + 4 <= a.nRows; rr += 4) {
                 uint32_t d[4];
                 float2 m[4], c[4];
@@ -398,7 +401,7 @@ __global__ void __launch_bounds__(MfccPipe<NC>::kCtaThreads, MfccPipe<NC>::kMinB
             }
         }
         /* 5. sum the partial sums, times max, + 1e-6, log (:146,161-165) */
-        for (uint32_t f = i; f < a.nbMel; f += T) {
+        for (uint32_t f = (MFCC_ABLATE & 2) ? a.nbMel : i; f < a.nbMel; f += T) {
             const float *p = part + f * MP::kPartStride;
             float s[T / MP::kQuad];
 #pragma unroll
@@ -415,7 +418,7 @@ __global__ void __launch_bounds__(MfccPipe<NC>::kCtaThreads, MfccPipe<NC>::kMinB
             for (uint32_t q = i; q < a.nbDct; q += T) {
                 float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
                 const float *dq = dctT + q;
-                uint32_t f = 0;
+                uint32_t f = (MFCC_ABLATE & 4) ? a.nbMel - 1 : 0;
                 for (; f + 4 <= a.nbMel; f += 4) {
                     s0 = fmaf(dq[f * a.nbDct], mel[f], s0);
                     s1 = fmaf(dq[(f + 1) * a.nbDct], mel[f + 1], s1);
