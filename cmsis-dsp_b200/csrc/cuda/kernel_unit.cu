@@ -8,6 +8,7 @@
  * the way in and once on the way out; the only other traffic is the shared-memory exchange(s).
  */
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdlib.h>
 
 #include <type_traits>
@@ -152,8 +153,28 @@ __device__ __forceinline__ void run_phases(typename BODY::Regs &r, const typenam
     }
 }
 
+/* L2 prefetch distance of the direct kernel in units of "CTAs resident on the whole device" (0: off).  A CTA of the direct
+ * kernel starts with its frame's global loads and nothing else to do: ncu shows 12-15 % of the fixed-point kernels' warp
+ * time waiting for them (first use of the loaded words).  The frame that the CTA taking over this CTA's slot will want is
+ * blockIdx + (resident CTAs) away; every thread asks L2 for one 128-byte line of it (prefetch.global.L2, no register, no
+ * scoreboard), so that CTA's loads are L2 hits. */
+/* Measured per unit (profiles/r2_ar_prefetch.txt, r2_as_prefetch_b.txt; % of the HBM peak without -> with a distance of one
+ * device-load of CTAs): cfft_f64 N = 512 / 1024 / 2048 101.7 / 92.9 / 91.3 -> 104.3 / 99.2 / 94.8, cfft_q31 N = 512 / 1024
+ * 96.3 / 90.9 -> 97.6 / 92.4, rfft_q31 forward real N = 512 ... 4096 98.3 / 90.6 / 83.9 / 78.3 -> 102.3 / 92.0 / 85.0 / 78.9,
+ * rfft_fast_f64 forward real N = 256 / 2048 +1.9 / +1.5.  Neutral or slower (0 ... -2.5 points) for q15 (issue-bound: the 1-2
+ * extra instructions per thread cost more than the wait they remove), the inverse real FFTs, the short f32 lengths, and with
+ * twice the distance; cfft_f64 N = 4096 loses a resident CTA to two more registers.  Off everywhere else. */
+#ifndef KU_PREFETCH
+#if (KU_OP == 10 && (KU_N == 512 || KU_N == 1024 || KU_N == 2048)) || (KU_OP == 1 && (KU_N == 512 || KU_N == 1024)) || \
+    (KU_OP == 5 && KU_N >= 256 && KU_N <= 2048) || (KU_OP == 11 && (KU_N == 128 || KU_N == 1024))
+#define KU_PREFETCH 1
+#else
+#define KU_PREFETCH 0
+#endif
+#endif
+
 template <class BODY, class PL>
-__global__ void __launch_bounds__(PL::kThreads, KU_MINB) frame_kernel(typename BODY::Args base, uint64_t nFrames)
+__global__ void __launch_bounds__(PL::kThreads, KU_MINB) frame_kernel(typename BODY::Args base, uint64_t nFrames, uint32_t residentCtas)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typedef typename BODY::xelem xelem;                  /* shared-memory exchange element */
@@ -161,6 +182,15 @@ __global__ void __launch_bounds__(PL::kThreads, KU_MINB) frame_kernel(typename B
     const int fl = tid / PL::T, i = tid % PL::T;
     const uint64_t frame = (uint64_t)blockIdx.x * PL::F + fl;
     const bool valid = frame < nFrames;
+    if constexpr (KU_PREFETCH > 0) {
+        const uint64_t ahead = frame + (uint64_t)KU_PREFETCH * residentCtas * PL::F;
+        if (ahead < nFrames) {
+            const char *p = reinterpret_cast<const char *>(BODY::for_frame(base, ahead).in);
+            const size_t bytes = (size_t)(reinterpret_cast<const char *>(BODY::for_frame(base, 1).in) - reinterpret_cast<const char *>(base.in));
+            for (size_t off = (size_t)i * 128; off < bytes; off += (size_t)PL::T * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
+        }
+    }
     xelem *sm = reinterpret_cast<xelem *>(smem_raw) + fl * PL::kFrameElems;
     typename BODY::Args a = BODY::for_frame(base, valid ? frame : 0);
     BODY::set_scratch(a, reinterpret_cast<xelem *>(smem_raw) + PL::F * PL::kFrameElems + fl * PL::kSpecial);
@@ -413,7 +443,23 @@ static int launch(const typename BODY::Args &args, uint64_t nFrames, cudaStream_
     if (ctas > 0x7fffffffull) return shim_fail(CMSISDSP_CUDA_ERR_ARGUMENT, "batch too large for one launch", cudaSuccess);
     int rc = prepare<BODY, PL>();
     if (rc) return rc;
-    frame_kernel<BODY, PL><<<(unsigned)ctas, PL::kThreads, PL::kSmemBytes, st>>>(args, nFrames);
+    uint32_t resident = 0;
+    if (KU_PREFETCH > 0) {
+        static std::atomic<uint32_t> cached[64];          /* per device; several host threads may get here at once (same value) */
+        int dev = 0;
+        KU_TRY(cudaGetDevice(&dev));
+        if (dev >= 0 && dev < 64) {
+            resident = cached[dev].load(std::memory_order_relaxed);
+            if (!resident) {
+                int occ = 0, sms = 0;
+                KU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, frame_kernel<BODY, PL>, PL::kThreads, PL::kSmemBytes));
+                KU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+                resident = (uint32_t)(occ > 0 ? occ : 1) * (uint32_t)(sms > 0 ? sms : 1);
+                cached[dev].store(resident, std::memory_order_relaxed);
+            }
+        }
+    }
+    frame_kernel<BODY, PL><<<(unsigned)ctas, PL::kThreads, PL::kSmemBytes, st>>>(args, nFrames, resident);
     shim_count_launch();
     KU_TRY(cudaGetLastError());
     return CMSISDSP_CUDA_OK;
