@@ -161,12 +161,13 @@ __device__ __forceinline__ void run_phases(typename BODY::Regs &r, const typenam
 /* Measured per unit (profiles/r2_ar_prefetch.txt, r2_as_prefetch_b.txt; % of the HBM peak without -> with a distance of one
  * device-load of CTAs): cfft_f64 N = 512 / 1024 / 2048 101.7 / 92.9 / 91.3 -> 104.3 / 99.2 / 94.8, cfft_q31 N = 512 / 1024
  * 96.3 / 90.9 -> 97.6 / 92.4, rfft_q31 forward real N = 512 ... 4096 98.3 / 90.6 / 83.9 / 78.3 -> 102.3 / 92.0 / 85.0 / 78.9,
- * rfft_fast_f64 forward real N = 256 / 2048 +1.9 / +1.5.  Neutral or slower (0 ... -2.5 points) for q15 (issue-bound: the 1-2
+ * rfft_fast_f64 forward real N = 256 / 2048 +1.9 / +1.5 (within the run-to-run spread), inverse real N = 128 / 256 / 512 / 1024
+ * 71.8 / 85.4 / 92.6 / 81.4 -> 81.5 / 98.4 / 97.5 / 83.6 (r2_ax_f64_prefetch.txt).  Neutral or slower (0 ... -2.5 points) for q15 (issue-bound: the 1-2
  * extra instructions per thread cost more than the wait they remove), the inverse real FFTs, the short f32 lengths, and with
  * twice the distance; cfft_f64 N = 4096 loses a resident CTA to two more registers.  Off everywhere else. */
 #ifndef KU_PREFETCH
 #if (KU_OP == 10 && (KU_N == 512 || KU_N == 1024 || KU_N == 2048)) || (KU_OP == 1 && (KU_N == 512 || KU_N == 1024)) || \
-    (KU_OP == 5 && KU_N >= 256 && KU_N <= 2048) || (KU_OP == 11 && (KU_N == 128 || KU_N == 1024))
+    (KU_OP == 5 && KU_N >= 256 && KU_N <= 2048) || (KU_OP == 11 && (KU_N == 128 || KU_N == 1024)) || (KU_OP == 12 && KU_N >= 64 && KU_N <= 512)
 #define KU_PREFETCH 1
 #else
 #define KU_PREFETCH 0
@@ -376,8 +377,23 @@ template <class BODY, class PL> struct TinySmem {
     static constexpr int kBytes = kCtaThreads * kSlotBytes + kWarps * 8;
 };
 
+/* As KU_PREFETCH, for the thread-per-frame kernel: two to eleven CTAs per SM, each of which starts by waiting for its own
+ * bulk copies.  Measured per unit (profiles/r2_aw_tiny_prefetch.txt, % of the HBM peak without -> with): cfft_q31 N = 16
+ * 86.3 -> 99.5, cfft_f32 N = 16 87.1 -> 89.3, cfft + magnitude / peak N = 16 77.6 / 72.5 -> 82.3 / 93.5, cfft_q15 N = 32 / 64
+ * 62.1 / 51.3 -> 63.6 / 56.9, rfft_q31 forward real N = 64 80.7 -> 85.4, rfft_q15 forward / inverse real N = 64, 128 +1 ... +3.
+ * The units that already run at the HBM peak lose 7-28 points with it (f32 N = 32 / 64, every f32 real FFT, cfft_q31 N = 32):
+ * the prefetches are a second access stream into DRAM.  Off for those. */
+#ifndef KU_TINY_PREFETCH
+#if ((KU_OP == 0 || KU_OP == 1 || KU_OP == 9) && KU_N == 16) || (KU_OP == 2 && (KU_N == 32 || KU_N == 64)) || (KU_OP == 5 && KU_N == 32) || \
+    ((KU_OP == 7 || KU_OP == 8) && (KU_N == 32 || KU_N == 64))
+#define KU_TINY_PREFETCH 1
+#else
+#define KU_TINY_PREFETCH 0
+#endif
+#endif
+
 template <class BODY, class PL>
-__global__ void __launch_bounds__(TinySmem<BODY, PL>::kCtaThreads) frame_kernel_tiny(typename BODY::Args base, uint64_t nFrames)
+__global__ void __launch_bounds__(TinySmem<BODY, PL>::kCtaThreads) frame_kernel_tiny(typename BODY::Args base, uint64_t nFrames, uint32_t residentCtas)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     typedef TinySmem<BODY, PL> SM;
@@ -387,6 +403,14 @@ __global__ void __launch_bounds__(TinySmem<BODY, PL>::kCtaThreads) frame_kernel_
     void *slot = smem_raw + threadIdx.x * SM::kSlotBytes;
     const uint64_t frame = (uint64_t)blockIdx.x * SM::kFramesPerCta + threadIdx.x;
     const bool valid = frame < nFrames;
+    if constexpr (KU_TINY_PREFETCH > 0) {
+        const uint64_t ahead = frame + (uint64_t)KU_TINY_PREFETCH * residentCtas * SM::kFramesPerCta;
+        if (ahead < nFrames && (TT::kIn >= 128 || (threadIdx.x & 1) == 0)) {      /* 64-byte frames: one request per line */
+            const char *p = reinterpret_cast<const char *>(BODY::for_frame(base, ahead).in);
+#pragma unroll
+            for (int off = 0; off < TT::kIn; off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
+        }
+    }
 
     if (lane == 0) {
         mbar_init(bar, 32);
@@ -554,11 +578,13 @@ template <class BODY, class PL>
 static int launch_tiny(const typename BODY::Args &args, uint64_t nFrames, cudaStream_t st)
 {
     if (nFrames == 0) return CMSISDSP_CUDA_OK;
-    int rc = tiny_prepare<BODY, PL>(nullptr);
+    int occ = 0;
+    int rc = tiny_prepare<BODY, PL>(&occ);
     if (rc) return rc;
     const uint64_t ctas = (nFrames + TinySmem<BODY, PL>::kFramesPerCta - 1) / TinySmem<BODY, PL>::kFramesPerCta;
     if (ctas > 0x7fffffffull) return shim_fail(CMSISDSP_CUDA_ERR_ARGUMENT, "batch too large for one launch", cudaSuccess);
-    frame_kernel_tiny<BODY, PL><<<(unsigned)ctas, TinySmem<BODY, PL>::kCtaThreads, TinySmem<BODY, PL>::kBytes, st>>>(args, nFrames);
+    frame_kernel_tiny<BODY, PL><<<(unsigned)ctas, TinySmem<BODY, PL>::kCtaThreads, TinySmem<BODY, PL>::kBytes, st>>>(args, nFrames,
+                                                                                                                       (uint32_t)(occ * num_sms()));
     shim_count_launch();
     KU_TRY(cudaGetLastError());
     return CMSISDSP_CUDA_OK;
