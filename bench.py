@@ -349,8 +349,8 @@ def run_cuda(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # keeps NCCL's version banner off stdout: rank 0 prints ONE line
+        # NCCL_DEBUG is left as the launcher set it: with VERSION / WARN / INFO the library writes its own banner to stdout
+        # before rank 0's JSON line, which stays the LAST line of stdout
         dist.init_process_group("nccl", device_id=dev)
     cu = cd.cuda()
     cu.cmsisdsp_cuda_set_device(local_rank)
