@@ -243,6 +243,10 @@ template <class PL> __device__ __forceinline__ void unit_sync(int unit)
     else asm volatile("bar.sync %0, %1;" ::"r"(unit + 1), "r"(PL::kThreads) : "memory");
 }
 
+#ifndef KU_PIPE_PREFETCH
+#define KU_PIPE_PREFETCH 0           /* A/B: L2 prefetch of the group after the one being copied in */
+#endif
+
 template <class BODY, class PL>
 __global__ void __launch_bounds__(PipeSmem<BODY, PL>::kCtaThreads, PipeSmem<BODY, PL>::kMinBlocks)
 frame_kernel_pipe(typename BODY::Args base, uint64_t nFrames)
@@ -284,6 +288,10 @@ frame_kernel_pipe(typename BODY::Args base, uint64_t nFrames)
         const uint32_t bytes = group_bytes(g);
         mbar_expect_tx(bar, bytes);
         bulk_g2s(buf, base.in + g * (uint64_t)kGroupElems, bytes, bar);
+#if KU_PIPE_PREFETCH
+        if (g + stride < nGroups)           /* and ask L2 for the group after it */
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base.in + (g + stride) * (uint64_t)kGroupElems), "r"(group_bytes(g + stride)) : "memory");
+#endif
     };
     uint64_t g = (uint64_t)blockIdx.x * SM::kUnits + unit;
     if (ut == 0 && g < nGroups) fetch(g);
