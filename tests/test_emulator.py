@@ -103,10 +103,12 @@ def _trace(emu, run):
 
 
 @pytest.mark.parametrize("kind,limit", [("f32", 1.0), ("q31", 1.0), ("q15", 1.0)])
-@pytest.mark.parametrize("N", [256, 512, 1024, 2048, 4096])
+@pytest.mark.parametrize("N", [128, 256, 512, 1024, 2048, 4096])
 def test_exchange_bank_conflicts(emu, kind, N, limit):
     """wavefronts / ideal wavefronts of every exchange load/store: all three types exchange
-    8-byte elements (q15 travels sign-extended) and must be conflict-free for N >= 256."""
+    8-byte elements (q15 travels sign-extended) and must be conflict-free for N >= 128 (N = 128, eight threads per
+    frame: the fixed-point plan pads after every 8 elements -- with 16 the first pass's stores of the two frames of a
+    half-warp met in the same banks, ncu: 17 % excess wavefronts in the real FFT of N = 256, which is bound by that pipe)."""
     tw, _ = product_tables(kind, N)
     y = np.zeros((8, 2 * N), dtype=cd.NP_DTYPE[kind])
     rows = _trace(emu, lambda: emu.emu_cfft(cd.TYPE_ID[kind], N, y.ctypes.data, 8, 0, 1, tw.ctypes.data, None))
@@ -144,7 +146,7 @@ def test_f64_exchange_bank_conflicts(emu, N):
         assert nbytes == 16 and wf == ideal, (N, int(ph), "store" if st else "load", wf / ideal)
 
 
-@pytest.mark.parametrize("N", [512, 1024, 2048, 4096])
+@pytest.mark.parametrize("N", [256, 512, 1024, 2048, 4096])
 @pytest.mark.parametrize("ifft", [0, 1])
 def test_rfft_exchange_bank_conflicts(emu, N, ifft):
     """same for the rfft plans (mirror passes read / write the exchange in reversed lane order);
@@ -185,7 +187,7 @@ def test_rfft_fixed_point_bodies(emu, kind, N):
     n = emu.emu_trace_stats(rows.ctypes.data, 64)
     first_new = 2 if N // 2 <= 256 else 4          # the phases the fused split adds behind the CFFT's own (2- / 3-pass plans)
     for ph, st, nbytes, req, ideal, wf in rows[:n]:
-        if N // 2 >= 256 and ph >= first_new:
+        if (N // 2 >= 256 and ph >= first_new) or N // 2 == 128:
             assert wf == ideal, f"{kind} N={N} phase {ph} {'store' if st else 'load'}: {wf} wavefronts for {ideal} ideal"
     spec = np.concatenate([want, cfft_input(kind, N, frames=6, seed=11 * N)])       # genuine spectra + arbitrary bins
     want = oracle().rfft_fix(kind, N, spec, 1, 1)
