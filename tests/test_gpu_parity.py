@@ -720,6 +720,40 @@ def test_mfcc_both_kernels_ragged_batches(n):
         cu.cmsisdsp_cuda_set_kernel_flavour(-1)
 
 
+@pytest.mark.parametrize("n", [256, 1024])
+def test_mfcc_degenerate_frames(n):
+    """frames that exercise the normalisation branches of arm_mfcc_f32.c:104-146: all zeros (absmax = 0: neither scaling is
+    applied, every mel energy is 0 and the outputs are the DCT of log(1e-6)), one impulse (flat spectrum), very large and very
+    small amplitudes (the scale by 1 / max keeps the squared magnitudes inside the f32 range) -- both kernels against the
+    oracle, frame by frame.  (A frame whose upper bins are pure rounding noise, e.g. a constant, is NOT a parity case: the log
+    of a noise-floor energy differs between any two correct implementations.)"""
+    from oracle_lib import mfcc_config
+    cfg = mfcc_config(n)
+    m = cd.Mfcc(cfg)
+    cu = cd.cuda()
+    rng = np.random.default_rng(n)
+    noise = rng.standard_normal(n).astype(np.float32)
+    impulse = np.zeros(n, dtype=np.float32)
+    impulse[n // 3] = -0.75
+    names = ["zeros", "impulse", "noise * 1e30", "noise * 1e-30", "noise", "zeros again"]
+    frames = np.stack([np.zeros(n, dtype=np.float32), impulse, noise * np.float32(1e30), noise * np.float32(1e-30), noise,
+                       np.zeros(n, dtype=np.float32)])
+    x = frames.reshape(-1)
+    want = oracle().mfcc(cfg, x, threads=NT).astype(np.float64)
+    assert np.all(np.isfinite(want))
+    try:
+        for flavour in (0, 1):
+            assert cu.cmsisdsp_cuda_set_kernel_flavour(flavour) == 0
+            got = m.batch(x, hop=n).astype(np.float64)
+            assert np.all(np.isfinite(got)), flavour
+            for k, name in enumerate(names):
+                err = np.abs(got[k] - want[k])
+                assert np.all(err <= 1e-5 + 1.2e-3 * np.abs(want[k])), (flavour, name, float(err.max()), got[k][:4].tolist(), want[k][:4].tolist())
+            assert np.array_equal(got[0], got[-1])            # the two all-zero frames
+    finally:
+        cu.cmsisdsp_cuda_set_kernel_flavour(-1)
+
+
 def test_mfcc_config4_synthetic_audio_large_batch():
     """BASELINE config 4 on one GPU: 16 kHz synthetic audio (3 sines + noise), 1024-sample frames, the
     reference's 20-mel / 13-DCT / Hamming configuration; device-resident, 2^17 frames, stratified oracle check"""
