@@ -278,6 +278,28 @@ def test_edge_cases():
             assert relrms(got, want) <= F32_TOL if kind == "f32" else np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("N", [64, 1024, 4096])
+def test_f32_extreme_amplitudes_and_denormals(N):
+    """arm_cfft_f32 / arm_rfft_fast_f32 far from unit scale: 1e30 and 1e-30 ... 1e-36 keep the 2e-6 bar; at 1e-41 inputs,
+    intermediates and results are denormal -- the kernels compute with gradual underflow like the reference's generic-C build
+    on the host (no flush to zero: the same values are exactly zero in both), within what 7-bit significands allow"""
+    rng = np.random.default_rng(N)
+    for scale in (1e30, 1e-30, 1e-36):
+        x = (rng.standard_normal((6, 2 * N)) * scale).astype(np.float32)
+        r = (rng.standard_normal((6, N)) * scale).astype(np.float32)
+        for ifft in (0, 1):
+            assert relrms(cd.cfft_batch("f32", N, x, ifft, 1), oracle().cfft("f32", N, x, ifft, 1)) <= F32_TOL, (scale, ifft)
+        spec = oracle().rfft(N, r, 0)
+        assert relrms(cd.rfft_batch(N, r, 0), spec) <= F32_TOL, scale
+        assert relrms(cd.rfft_batch(N, spec, 1), oracle().rfft(N, spec, 1)) <= F32_TOL, scale
+    x = (rng.standard_normal((6, 2 * N)) * 1e-41).astype(np.float32)
+    assert np.count_nonzero(x) > N and np.abs(x).max() < 1.2e-38          # denormal inputs
+    for ifft in (0, 1):
+        got, want = cd.cfft_batch("f32", N, x, ifft, 1), oracle().cfft("f32", N, x, ifft, 1)
+        assert np.count_nonzero(want) > 0 and relrms(got, want) <= 2e-3, ifft
+        assert np.count_nonzero(got) >= 0.9 * np.count_nonzero(want), ifft   # not flushed
+
+
 def test_device_pointer_path_matches_host_path():
     torch = pytest.importorskip("torch")
     dev = torch.device("cuda", 0)
