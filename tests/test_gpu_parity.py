@@ -300,6 +300,35 @@ def test_f32_extreme_amplitudes_and_denormals(N):
         assert np.count_nonzero(got) >= 0.9 * np.count_nonzero(want), ifft   # not flushed
 
 
+@pytest.mark.parametrize("N", [64, 1024, 4096])
+def test_non_finite_frames_stay_in_their_frame(N):
+    """a frame with a NaN or an Inf comes out non-finite -- and its neighbours in the batch, which share shared-memory
+    buffers, CTAs and warps with it, do not change by a bit"""
+    rng = np.random.default_rng(3 * N)
+    frames, bad = 37, (5, 20, 36)
+    x = rng.standard_normal((frames, 2 * N)).astype(np.float32)
+    r = rng.standard_normal((frames, N)).astype(np.float32)
+    xp, rp = x.copy(), r.copy()
+    xp[5, 7], xp[20, 2 * N - 1], xp[36, 0] = np.nan, np.inf, -np.inf
+    rp[5, 7], rp[20, N - 1], rp[36, 0] = np.nan, np.inf, -np.inf
+    good = np.array([k for k in range(frames) if k not in bad])
+    for ifft in (0, 1):
+        y0, y1 = cd.cfft_batch("f32", N, x, ifft, 1), cd.cfft_batch("f32", N, xp, ifft, 1)
+        assert np.array_equal(y0[good], y1[good]), ("cfft", ifft)
+        for k in bad:                                        # (X[0] sums the real and the imaginary parts separately, trivial
+            assert np.mean(~np.isfinite(y1[k])) >= 0.45, ("cfft", ifft, k)     # twiddles are not multiplied: not EVERY output is hit)
+        z0, z1 = cd.rfft_batch(N, r, ifft), cd.rfft_batch(N, rp, ifft)
+        assert np.array_equal(z0[good], z1[good]), ("rfft", ifft)
+        for k in bad:
+            assert np.mean(~np.isfinite(z1[k])) >= 0.45, ("rfft", ifft, k)
+    if N == 1024:
+        from oracle_lib import mfcc_config
+        m = cd.Mfcc(mfcc_config(N))
+        m0, m1 = m.batch(r.reshape(-1), hop=N), m.batch(rp.reshape(-1), hop=N)
+        assert np.array_equal(m0[good], m1[good])
+        assert np.any(~np.isfinite(m1[5]))
+
+
 def test_device_pointer_path_matches_host_path():
     torch = pytest.importorskip("torch")
     dev = torch.device("cuda", 0)
