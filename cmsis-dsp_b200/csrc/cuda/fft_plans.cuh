@@ -59,7 +59,7 @@ template <int NC> struct PlanRfftInv;   /* leading Mirror pass */
 template <> struct PlanRfftInv<16>   { typedef Plan<ArithF32, 16, 1, 128, 0, 0, M8, F2> type; };
 template <> struct PlanRfftInv<32>   { typedef Plan<ArithF32, 32, 2, 64, 3, 1, M8, F4> type; };
 template <> struct PlanRfftInv<64>   { typedef Plan<ArithF32, 64, 4, 32, 3, 1, M8, F8> type; };
-template <> struct PlanRfftInv<128>  { typedef Plan<ArithF32, 128, 8, 16, 3, 1, M8, F16> type; };
+template <> struct PlanRfftInv<128>  { typedef Plan<ArithF32, 128, 8, 16, 3, 1, M8, F16> type; };   /* padding per 8: see the fixed-point N = 128 plan */
 template <> struct PlanRfftInv<256>  { typedef Plan<ArithF32, 256, 8, 16, 4, 1, M16, F16> type; };
 template <> struct PlanRfftInv<512>  { typedef Plan<ArithF32, 512, 16, 8, 4, 1, M16, F32> type; };
 template <> struct PlanRfftInv<1024> { typedef Plan<ArithF32, 1024, 16, 4, 5, 1, M32, F32> type; };
@@ -76,6 +76,11 @@ template <class AR, int N> struct PlanCfftFix;
 FIXPLAN(16,   1,   128, 0, 0, PF(ST_FIRST4, ST_LAST4))
 FIXPLAN(32,   1,   128, 0, 0, PF(ST_PRE2, ST_FIRST4, ST_LAST4))
 FIXPLAN(64,   1,   128, 0, 0, PF(ST_FIRST4, ST_MID4, ST_LAST4))
+/* N = 128: eight threads per frame, so a half-warp holds TWO frames.  A thread stores its radix-8 outputs at 8 i + e; with one padding
+ * element per 16 (PADA = 4) the stores of a frame cover the 8-byte bank slots {e .. e+3, e+8 .. e+11} and the neighbouring frame, placed
+ * 8 slots further for the sake of the loads, covers the same set: two wavefronts per store instead of one, seen as 17 % excess
+ * wavefronts in the (L1-bound) real FFTs of N = 256.  One padding element per 8 interleaves the two frames: conflict-free both ways
+ * (tests/test_emulator.py::test_exchange_bank_conflicts from N = 128; profiles/r2_bd_fix128_padding.txt). */
 FIXPLAN(128,  8,   16,  3, 1, PF(ST_PRE2, ST_FIRST4), PF(ST_MID4, ST_LAST4))
 FIXPLAN(256,  16,  8,   4, 1, PF(ST_FIRST4, ST_MID4), PF(ST_MID4, ST_LAST4))
 /* N >= 512: three passes of 16 points per thread.  Two passes of 32/64 points per thread (the f32
