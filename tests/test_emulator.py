@@ -94,12 +94,16 @@ def test_rfft_bodies(emu, N):
         assert relrms(got, want) <= 2e-6, (N, ifft)
 
 
-def _trace(emu, run):
-    emu.emu_trace_begin()
-    run()
+def _stats(emu):
     buf = np.zeros((64, 6), dtype=np.int64)
     n = emu.emu_trace_stats(buf.ctypes.data, 64)
     return buf[:n]
+
+
+def _trace(emu, run):
+    emu.emu_trace_begin()
+    run()
+    return _stats(emu)
 
 
 @pytest.mark.parametrize("kind,limit", [("f32", 1.0), ("q31", 1.0), ("q15", 1.0)])
@@ -212,3 +216,43 @@ def test_cfft_magnitude_epilogue_body(emu, N):
             assert emu.emu_cfft_mag(N, xin.ctypes.data, got.ctypes.data, frames, ifft, sq, tw.ctypes.data) == 0
             assert np.array_equal(xin, x)
             assert relrms(got, want) <= (4e-6 if sq else 2e-6), (N, ifft, sq)
+
+def test_every_plan_every_exchange_is_conflict_free(emu):
+    """the whole plan table at once: every traced shared-memory exchange of every (type, length, direction) -- complex
+    f32 / q31 / q15 / f64, real f32, real q31 / q15 -- costs exactly its ideal number of wavefronts (the plans with 8 threads
+    per frame were outside the per-family assertions above until ncu showed their conflicts on the GPU)"""
+    frames = 256
+
+    def bad_rows():
+        return [(int(ph), "store" if st else "load", int(ideal), int(wf)) for ph, st, nb, req, ideal, wf in _stats(emu) if wf > ideal]
+
+    for kind in ("f32", "q31", "q15", "f64"):
+        for N in LENGTHS:
+            tw, _ = product_tables(kind, N)
+            y = np.zeros((frames, 2 * N), dtype=cd.NP_DTYPE[kind])
+            emu.emu_trace_begin()
+            emu.emu_cfft(cd.TYPE_ID[kind], N, y.ctypes.data, frames, 0, 1, tw.ctypes.data, None)
+            assert not bad_rows(), ("cfft", kind, N, bad_rows())
+    for N in RLENGTHS:
+        tw, _ = cd.instance_tables(cd.cfft_instance("f32", N // 2), "f32")
+        S = cd.rfft_instance(N)
+        twr = np.ctypeslib.as_array(S.pTwiddleRFFT, shape=(N,)).copy()
+        for ifft in (0, 1):
+            x = np.zeros((frames, N), dtype=np.float32)
+            y = np.zeros_like(x)
+            emu.emu_trace_begin()
+            emu.emu_rfft(N, x.ctypes.data, y.ctypes.data, frames, ifft, tw.ctypes.data, twr.ctypes.data)
+            assert not bad_rows(), ("rfft f32", N, ifft, bad_rows())       # (the special-bin scratch accesses are not part of the trace)
+    for kind in ("q31", "q15"):
+        for N in RFIX_LENGTHS:
+            S = cd.rfft_fix_instance(kind, N)
+            A = np.ctypeslib.as_array(S.pTwiddleAReal, shape=(8192,))
+            B = np.ctypeslib.as_array(S.pTwiddleBReal, shape=(8192,))
+            tw, _ = cd.instance_tables(S.pCfft.contents, kind)
+            for ifft in (0, 1):
+                x = np.zeros((frames, 2 * N if ifft else N), dtype=cd.NP_DTYPE[kind])
+                got = np.zeros((frames, N if ifft else 2 * N), dtype=x.dtype)
+                emu.emu_trace_begin()
+                assert emu.emu_rfft_fix(cd.TYPE_ID[kind], N, x.ctypes.data, got.ctypes.data, frames, ifft, tw.ctypes.data,
+                                        A.ctypes.data, B.ctypes.data) == 0
+                assert not bad_rows(), ("rfft", kind, N, ifft, bad_rows())
